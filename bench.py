@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the ph-core device path on B200.
+
+Workload (BASELINE.json configs[1]): elementwise a*b+c with row-vector broadcasting on
+8192x8192 Float32 NArrays.  One "step" = the reference-faithful execution of `a * b + c`:
+two kernels with a materialised, individually rounded temporary
+    t = a * b      (b is [1, 8192]; algorithmic bytes 2*N*4 + 32 KiB = 536.9 MB)
+    out = t + c    (3*N*4 = 805.3 MB)
+=> 1342.2 MB of algorithmic traffic per step per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+N > 1 is launched by torchrun, one rank per GPU; elementwise work shards along the leading
+axis with no data-path collective (weak scaling: every rank owns an 8192x8192 shard).
+
+Prints ONE JSON line (rank 0).  `value` = whole-job GB/s with inputs resident in HBM;
+`e2e` = the same metric through the public API with HOST buffers (pinned H2D of a, b, c and
+D2H of the result inside the timed region); `roofline` describes the dominant kernel;
+`cpu_baseline` is the oracle's C port timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ROWS, COLS = 8192, 8192
+N = ROWS * COLS
+BYTES_MUL = 2 * N * 4 + COLS * 4          # read a, write t, read b once
+BYTES_ADD = 3 * N * 4                     # read t, read c, write out
+BYTES_STEP = BYTES_MUL + BYTES_ADD
+SEED = 20261017
+METRIC = "f32 elementwise HBM GB/s"
+WORKLOAD = "elementwise a*b+c, b=[1,8192] row-vector broadcast, 8192x8192 f32 (two reference-faithful kernels)"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_inputs(rank: int, rows: int = ROWS):
+    """Philox counter RNG, seed 20261017, stream = tensor id."""
+    def gen(stream, shape):
+        g = np.random.Generator(np.random.Philox(key=SEED, counter=[0, 0, stream, rank]))
+        return (g.random(shape, dtype=np.float32) * 2 - 1).astype(np.float32)
+    return gen(1, (rows, COLS)), gen(2, (1, COLS)), gen(3, (rows, COLS))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def physical_gpu_index(local: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local])
+        except Exception:
+            return local
+    return local
+
+
+# ----------------------------------------------------------------------------- CPU legs
+def cpu_flat_sample(rows: int, reps: int):
+    """oracle C port, flat loops + OpenMP on all host cores, on `rows` of the workload."""
+    from oracle import c_oracle as CO
+    a, b, c = make_inputs(0, rows)
+    out, tmp = np.empty_like(a), np.empty_like(a)
+    CO.flat_mul_rowvec_add_f32(a, b, c, out, tmp)        # warm (page faults)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        CO.flat_mul_rowvec_add_f32(a, b, c, out, tmp)
+        ts.append(time.perf_counter() - t0)
+    bytes_sample = BYTES_STEP * rows / ROWS
+    return bytes_sample / statistics.median(ts) / 1e9, CO.num_threads(), ts
+
+
+def cpu_ref_sample(rows: int):
+    """oracle C port keeping the reference's structure (1 thread, per-element coordinate
+    iterator + dot-product indexing, tile + two operators)."""
+    from oracle import c_oracle as CO
+    a, b, c = make_inputs(0, rows)
+    t0 = time.perf_counter()
+    CO.ref_mul_rowvec_add_f32(a, b, c)
+    dt = time.perf_counter() - t0
+    return (BYTES_STEP * rows / ROWS) / dt / 1e9, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference
+    is Crystal and no Crystal compiler exists in this image, so this is the oracle's C port
+    (kind "port") with every host thread it can use, on a bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rows = 2048                                            # 1/4 of the workload per step
+    from oracle import c_oracle as CO
+    a, b, c = make_inputs(0, rows)
+    out, tmp = np.empty_like(a), np.empty_like(a)
+    for _ in range(max(1, args.warmup)):
+        CO.flat_mul_rowvec_add_f32(a, b, c, out, tmp)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        CO.flat_mul_rowvec_add_f32(a, b, c, out, tmp)
+    dt = time.perf_counter() - t0
+    gbs = (BYTES_STEP * rows / ROWS) * args.steps / dt / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(gbs, 3), "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3 * ROWS / rows, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"{rows} of {ROWS} rows per step"},
+        "cpu_baseline": {"value": round(gbs, 3), "unit": "GB/s", "cores": CO.num_threads(), "kind": "port",
+                         "sample": f"{rows}x{COLS} f32 rows per step, flat loops + OpenMP"},
+        "e2e": {"value": round(gbs, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import ph_core_b200 as ph
+    from ph_core_b200 import DeviceNArray as D
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the device path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ph.init(local)
+    lib = ph.load()
+    stream = torch.cuda.ExternalStream(lib.ph_stream(), device=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- inputs resident in HBM (this rank's 8192x8192 shard of the [world*8192, 8192] array)
+    a_h, b_h, c_h = make_inputs(rank)
+    a, b, c = D.from_host(a_h), D.from_host(b_h), D.from_host(c_h)
+    t = D(a.shape, np.float32)
+    out = D(a.shape, np.float32)
+    da, dt_, dc, do = a.desc(), t.desc(), c.desc(), out.desc()
+    db = b.bcast_desc(a.shape)
+    F32, MUL, ADD = ph.K["PH_F32"], ph.K["PH_MUL"], ph.K["PH_ADD"]
+
+    def step():
+        ph.check(lib.ph_ewise_binary(MUL, F32, a.ptr, C.byref(da), b.ptr, C.byref(db), t.ptr, C.byref(dt_)))
+        ph.check(lib.ph_ewise_binary(ADD, F32, t.ptr, C.byref(dt_), c.ptr, C.byref(dc), out.ptr, C.byref(do)))
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+
+    # ---- timed region: K steps, CUDA events on the launching stream, clocks sampled
+    sampler = ClockSampler(physical_gpu_index(local))
+    sampler.start()
+    launches0 = lib.ph_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
+    barrier()
+    with torch.cuda.stream(stream):
+        ev[0].record(stream)
+        for i in range(args.steps):
+            ph.check(lib.ph_ewise_binary(MUL, F32, a.ptr, C.byref(da), b.ptr, C.byref(db), t.ptr, C.byref(dt_)))
+            ev[2 * i + 1].record(stream)
+            ph.check(lib.ph_ewise_binary(ADD, F32, t.ptr, C.byref(dt_), c.ptr, C.byref(dc), out.ptr, C.byref(do)))
+            ev[2 * i + 2].record(stream)
+    barrier()
+    launches = lib.ph_launch_count() - launches0
+    clocks = sampler.stop()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    mul_ms = [ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)]
+    add_ms = [ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps)]
+    if dist is not None:
+        tt = torch.tensor([total_ms], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    ms_per_step = total_ms / args.steps
+    value = BYTES_STEP * world / (ms_per_step * 1e-3) / 1e9
+
+    # ---- fused single-pass variant, reported beside the headline
+    for _ in range(3):
+        ph.check(lib.ph_ewise_mul_add(F32, a.ptr, C.byref(da), b.ptr, C.byref(db), c.ptr, C.byref(dc), out.ptr, C.byref(do)))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(args.steps):
+            ph.check(lib.ph_ewise_mul_add(F32, a.ptr, C.byref(da), b.ptr, C.byref(db), c.ptr, C.byref(dc), out.ptr, C.byref(do)))
+        e1.record(stream)
+    barrier()
+    fused_ms = e0.elapsed_time(e1) / args.steps
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies timed
+    pin = {}
+    for name, arr in (("a", a_h), ("b", b_h), ("c", c_h), ("out", np.empty_like(a_h))):
+        p = C.c_void_p()
+        ph.check(lib.ph_host_alloc(arr.nbytes, C.byref(p)))
+        view = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(arr.size,)).reshape(arr.shape)
+        if name != "out":
+            view[...] = arr
+        pin[name] = (p, view)
+
+    def e2e_step():
+        ph.check(lib.ph_h2d(a.ptr, pin["a"][0], a_h.nbytes))
+        ph.check(lib.ph_h2d(b.ptr, pin["b"][0], b_h.nbytes))
+        ph.check(lib.ph_h2d(c.ptr, pin["c"][0], c_h.nbytes))
+        step()
+        ph.check(lib.ph_d2h(pin["out"][0], out.ptr, a_h.nbytes))      # synchronises
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(e2e_steps):
+            e2e_step()
+        e1.record(stream)
+    barrier()
+    e2e_ms = e0.elapsed_time(e1) / e2e_steps
+    if dist is not None:
+        tt = torch.tensor([e2e_ms], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tt.item())
+    e2e_value = BYTES_STEP * world / (e2e_ms * 1e-3) / 1e9
+    e2e_out = pin["out"][1].copy()
+
+    # ---- parity spot check of the timed result (oracle = checker only)
+    from oracle import c_oracle as CO
+    chk_rows = 64
+    want = CO.flat_mul_rowvec_add_f32(a_h[:chk_rows].copy(), b_h, c_h[:chk_rows].copy())
+    parity_ok = bool(e2e_out[:chk_rows].tobytes() == want.tobytes())
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        dom_ms = statistics.mean(add_ms)
+        achieved = BYTES_ADD / (dom_ms * 1e-3) / 1e9
+        cpu_flat, cores, _ = cpu_flat_sample(2048, 5)
+        cpu_ref, cpu_ref_s = cpu_ref_sample(512)
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": round(ms_per_step, 5), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "shape_per_gpu": [ROWS, COLS], "bytes_per_step_per_gpu": BYTES_STEP,
+                       "parallelism": f"axis0-shard x{world}, no collective",
+                       "l2": "no flush needed: each 256 MiB operand exceeds the 126 MB L2",
+                       "seed": SEED},
+            "pct_of_peak": {"of_measured_copy": round(value / world / peak, 4), "of_nominal_8000": round(value / world / 8000, 4)},
+            "roofline": {"bound": "hbm", "kernel": "map_flat_kernel<BinaryOp<float,ADD>,8,2> (out = t + c)",
+                         "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": BYTES_ADD, "avg_launch_ms": round(dom_ms, 5),
+                         "other_kernels": {"map_rows_kernel<BinaryOp<float,MUL>,8,4> (t = a * b)": {
+                             "algorithmic_bytes_per_launch": BYTES_MUL, "avg_launch_ms": round(statistics.mean(mul_ms), 5),
+                             "achieved": round(BYTES_MUL / (statistics.mean(mul_ms) * 1e-3) / 1e9, 2)}}},
+            "fused_single_pass": {"ms_per_step": round(fused_ms, 5), "algorithmic_bytes": BYTES_ADD + COLS * 4,
+                                  "gbs": round((BYTES_ADD + COLS * 4) / (fused_ms * 1e-3) / 1e9, 2)},
+            "cpu_baseline": {"value": round(cpu_flat, 3), "unit": "GB/s", "cores": cores, "kind": "port",
+                             "sample": "2048 of 8192 rows, oracle C port: flat loops + OpenMP, median of 5",
+                             "reference_structure_1core": {"value": round(cpu_ref, 4), "unit": "GB/s", "cores": 1,
+                                                           "sample": f"512 of 8192 rows, {cpu_ref_s:.2f} s"}},
+            "e2e": {"value": round(e2e_value, 3), "unit": "GB/s", "ms_per_step": round(e2e_ms, 4),
+                    "h2d_bytes_per_step": int(a_h.nbytes + b_h.nbytes + c_h.nbytes), "d2h_bytes_per_step": int(a_h.nbytes),
+                    "steps": e2e_steps},
+            "gpu_launches": int(launches), "clocks": clocks, "parity_spot_check": parity_ok,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

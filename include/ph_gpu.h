@@ -1,0 +1,256 @@
+/* ph_gpu.h -- C-ABI of libphgpu.so: the device-resident NArray backing for
+ * ph-core's data-parallel hot path on NVIDIA B200 (sm_100a).
+ *
+ * ph-core (Crystal) has no FFI today; its seam is the mixin contract of
+ * MultiIndexable / MultiWritable (src/multi_indexable.cr:30-65,
+ * src/multi_writable.cr:5-44).  A Crystal `lib LibPhGpu` binding (see
+ * INTEGRATION.md) declares exactly the functions below, and the device-backed
+ * NArray overrides the reference methods each entry cites.
+ *
+ * Conventions
+ *   - every function returns int32 status: 0 = PH_OK; no exception / longjmp
+ *     crosses the boundary; ph_last_error_string() describes the last failure.
+ *   - plain pointers and sizes only.  `const void* dev` arguments are DEVICE
+ *     pointers (from ph_alloc or any CUDA allocator); `host` arguments are host.
+ *   - all SEMANTIC validation (ShapeError, DimensionError, IndexError) stays in
+ *     the host language and happens before a call; data-dependent errors
+ *     (OverflowError, DivisionByZeroError, ArgumentError) are accumulated in a
+ *     device flag word read by ph_take_arith_flags().
+ *   - launches are asynchronous on the library's per-device stream (ph_stream);
+ *     ph_d2h / ph_reduce_full / ph_take_arith_flags / ph_sync synchronise.
+ *   - not thread-safe by contract: the reference is single-threaded
+ *     (no spawn/Channel/Mutex anywhere in src/).
+ *   - there is no CPU fallback: without a CUDA device every compute entry
+ *     returns PH_ERR_CUDA.
+ */
+#ifndef PH_GPU_H
+#define PH_GPU_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PH_MAX_RANK 8
+
+/* ---- status codes ------------------------------------------------------ */
+enum {
+  PH_OK = 0,
+  PH_ERR_CUDA = 1,        /* a CUDA runtime call failed (incl. "no device") */
+  PH_ERR_INVALID = 2,     /* bad argument: null pointer, rank > 8, unknown enum */
+  PH_ERR_UNSUPPORTED = 3, /* op not defined for dtype (e.g. `&` on floats) */
+  PH_ERR_NCCL = 4,
+  PH_ERR_NOT_INIT = 5
+};
+
+/* ---- element types (Crystal primitive numerics + Bool) ------------------ */
+enum {
+  PH_F32 = 0, PH_F64 = 1, PH_I32 = 2, PH_I64 = 3,
+  PH_U8 = 4,  /* UInt8 and Bool (Slice(Bool) is one byte per element) */
+  PH_I8 = 5, PH_I16 = 6, PH_U16 = 7, PH_U32 = 8, PH_U64 = 9
+};
+
+/* ---- binary operators: the op list of src/multi_indexable.cr:960-975 ---- */
+enum {
+  PH_ADD = 0,      /* +   ints: overflow-checked                           */
+  PH_SUB = 1,      /* -                                                     */
+  PH_MUL = 2,      /* *                                                     */
+  PH_DIV = 3,      /* /   ints: result dtype is F64 (Int / Int -> Float64)  */
+  PH_FLOORDIV = 4, /* //  ints: floored, /0 -> DIV0, MIN//-1 -> ARGUMENT;
+                          floats: (a / b).floor                             */
+  PH_MOD = 5,      /* %   ints: floored modulo; floats: a - b*(a/b).floor,
+                          b == 0 -> DIV0                                    */
+  PH_POW = 6,      /* **  ints: checked square-and-multiply, exp<0 -> ARGUMENT;
+                          floats array**array: pow() (tolerance only)       */
+  PH_WADD = 7, PH_WSUB = 8, PH_WMUL = 9, PH_WPOW = 10, /* &+ &- &* &** wrap */
+  PH_AND = 11, PH_OR = 12, PH_XOR = 13,                 /* & | ^ (ints)     */
+  PH_POWI = 14     /* Float ** Int32 scalar: llvm.powi (compiler-rt loop);
+                      ph_ewise_scalar only, scalar holds an int32           */
+};
+
+/* comparisons: src/multi_indexable.cr:977-980, eq :899-913 */
+enum { PH_GT = 0, PH_LT = 1, PH_GE = 2, PH_LE = 3, PH_EQ = 4, PH_NE = 5 };
+
+/* unary: src/multi_indexable.cr:983-985 */
+enum { PH_POS = 0, PH_NEG = 1, PH_NOT = 2 };
+
+/* reductions: Enumerable#sum/min/max over NArray#each (src/n_array.cr:556-564),
+ * argmax idiom README.md:56-61 */
+enum { PH_SUM = 0, PH_MIN = 1, PH_MAX = 2, PH_ARGMAX = 3, PH_ARGMIN = 4 };
+
+/* arithmetic flag bits (ph_take_arith_flags) -> exception the host raises */
+enum {
+  PH_FLAG_OVERFLOW = 1, /* OverflowError                                   */
+  PH_FLAG_DIV0 = 2,     /* DivisionByZeroError                             */
+  PH_FLAG_NAN = 4,      /* ArgumentError: NaN met by max/min/argmax        */
+  PH_FLAG_ARGUMENT = 8  /* ArgumentError: MIN // -1, negative int exponent */
+};
+
+/* heat boundary modes */
+enum {
+  PH_HEAT_FIXED = 0,   /* N-D rule of SURVEY.md 8(a) a-9: boundary cells held */
+  PH_HEAT_EXAMPLE1D = 1 /* examples/heat_equation.cr:43-44 one-sided ends     */
+};
+
+/* ---- strided descriptor --------------------------------------------------
+ * What an IndexRegion (src/index_region.cr:54-94) or a View transform chain
+ * (src/view_util/transforms.cr) compiles to: element (not byte) units, signed
+ * strides, stride 0 = broadcast axis.  Element i = (i_0..i_{rank-1}) lives at
+ * base[offset + sum_k i_k * stride[k]].  Replaces per-element
+ * IndexRegion#local_to_absolute_unsafe (:621-637) + Buffered.coord_to_index_fast
+ * (src/buffered/buffered.cr:44-52). */
+typedef struct ph_desc {
+  int32_t rank;
+  int32_t _pad;
+  int64_t offset;
+  int64_t extent[PH_MAX_RANK];
+  int64_t stride[PH_MAX_RANK];
+} ph_desc;
+
+/* ---- runtime / storage: NArray buffer ownership, src/n_array.cr:20-79,
+ *      clone :372-374, fill :230-232 ----------------------------------------- */
+int32_t ph_init(int32_t device);              /* select device, create stream + pool */
+int32_t ph_shutdown(void);
+int32_t ph_device_count(int32_t* out);
+int32_t ph_sm_count(int32_t* out);
+int32_t ph_alloc(size_t nbytes, void** out_dev);     /* stream-ordered pool allocation */
+int32_t ph_free(void* dev);
+int32_t ph_h2d(void* dst_dev, const void* src_host, size_t nbytes);
+int32_t ph_d2h(void* dst_host, const void* src_dev, size_t nbytes);   /* synchronises */
+int32_t ph_d2d(void* dst_dev, const void* src_dev, size_t nbytes);    /* NArray#clone */
+int32_t ph_host_alloc(size_t nbytes, void** out_host);  /* pinned staging memory */
+int32_t ph_host_free(void* host);
+int32_t ph_sync(void);
+void*   ph_stream(void);                      /* the cudaStream_t launches go to */
+int32_t ph_set_stream(void* cuda_stream);     /* adopt a caller-owned stream (0 = own) */
+const char* ph_last_error_string(void);
+int32_t ph_take_arith_flags(uint32_t* out_flags);    /* read + clear; synchronises */
+int32_t ph_timer_start(void);                 /* CUDA event on ph_stream */
+int32_t ph_timer_stop(float* out_ms);         /* records, synchronises, elapsed ms */
+int64_t ph_launch_count(void);                /* kernels launched since ph_init */
+
+/* ---- elementwise (K1/K2): def_elementwise_binary, src/multi_indexable.cr:931-952
+ * -> map_with/each_with :1026-1102; all descriptors share rank and extents,
+ * broadcast operands carry stride 0.  Output dtype = dtype, except PH_DIV on an
+ * integer dtype which writes F64. */
+int32_t ph_ewise_binary(int32_t op, int32_t dtype,
+                        const void* a, const ph_desc* a_desc,
+                        const void* b, const ph_desc* b_desc,
+                        void* out, const ph_desc* out_desc);
+/* array (op) scalar: src/multi_indexable.cr:947-951 -> NArray#map src/n_array.cr:589-595;
+ * scalar (op) array (scalar_on_left != 0): src/patches/number.cr:6-15.
+ * `scalar_host` points at one element of `dtype` (an int32 for PH_POWI). */
+int32_t ph_ewise_scalar(int32_t op, int32_t dtype,
+                        const void* a, const ph_desc* a_desc,
+                        const void* scalar_host, int32_t scalar_on_left,
+                        void* out, const ph_desc* out_desc);
+/* unary + - ~ : src/multi_indexable.cr:954-958 */
+int32_t ph_ewise_unary(int32_t op, int32_t dtype,
+                       const void* a, const ph_desc* a_desc,
+                       void* out, const ph_desc* out_desc);
+/* fused out = (a * b) + c with TWO roundings (never an FMA): SURVEY.md 8(f) f-1;
+ * bit-identical to ph_ewise_binary(MUL) then ph_ewise_binary(ADD). */
+int32_t ph_ewise_mul_add(int32_t dtype,
+                         const void* a, const ph_desc* a_desc,
+                         const void* b, const ph_desc* b_desc,
+                         const void* c, const ph_desc* c_desc,
+                         void* out, const ph_desc* out_desc);
+
+/* ---- comparisons -> NArray(Bool) (K3): src/multi_indexable.cr:977-980, eq :899-920 */
+int32_t ph_compare(int32_t cmp, int32_t dtype,
+                   const void* a, const ph_desc* a_desc,
+                   const void* b, const ph_desc* b_desc,
+                   uint8_t* out, const ph_desc* out_desc);
+int32_t ph_compare_scalar(int32_t cmp, int32_t dtype,
+                          const void* a, const ph_desc* a_desc,
+                          const void* scalar_host, int32_t scalar_on_left,
+                          uint8_t* out, const ph_desc* out_desc);
+
+/* ---- masked store (K4): NArray#[]=(mask, value) src/n_array.cr:510-551,
+ *      MultiWritable#set_mask src/multi_writable.cr:154-172 ------------------- */
+int32_t ph_mask_set_scalar(int32_t elem_size, void* dst, const ph_desc* dst_desc,
+                           const uint8_t* mask, const ph_desc* mask_desc,
+                           const void* scalar_host);
+int32_t ph_mask_set_array(int32_t elem_size, void* dst, const ph_desc* dst_desc,
+                          const uint8_t* mask, const ph_desc* mask_desc,
+                          const void* src, const ph_desc* src_desc);
+
+/* ---- strided gather / scatter / fill (K5/K6/K10) ----------------------------
+ * ph_copy_strided: dst[dst_desc(i)] = src[src_desc(i)] for every i of the shared
+ * extents, in any order (the regions never alias).  Covers
+ *   gather  NArray#unsafe_fetch_chunk src/n_array.cr:450-453, View#to_narr
+ *           src/view.cr:123-126, MultiIndexable#permute/reverse/reshape
+ *           src/multi_indexable.cr:795-803   (dst_desc contiguous)
+ *   scatter NArray#unsafe_set_chunk(region, src) src/n_array.cr:484-492,
+ *           MutableView writes src/mutable_view.cr:16-18 (dst_desc strided) */
+int32_t ph_copy_strided(int32_t elem_size,
+                        const void* src, const ph_desc* src_desc,
+                        void* dst, const ph_desc* dst_desc);
+/* NArray#unsafe_set_chunk(region, value) src/n_array.cr:495-500; NArray.fill :230-232 */
+int32_t ph_fill_region(int32_t elem_size, void* dst, const ph_desc* dst_desc,
+                       const void* scalar_host);
+
+/* ---- reductions (K7/K8) --------------------------------------------------------
+ * Full: Enumerable#sum/min/max over NArray#each (src/n_array.cr:556-564); result
+ * written to HOST memory (`out_value_host`: one element of dtype; for ARGMAX /
+ * ARGMIN also the flat lex index of the FIRST extremum in `out_index_host`).
+ * `count_out` (optional) receives the element count (0 -> host raises EmptyError
+ * for min/max).  NaN under min/max/arg* sets PH_FLAG_NAN; integer SUM that
+ * leaves T's range at ANY prefix of the lex-order fold sets PH_FLAG_OVERFLOW. */
+int32_t ph_reduce_full(int32_t red, int32_t dtype,
+                       const void* a, const ph_desc* a_desc,
+                       void* out_value_host, int64_t* out_index_host);
+/* Same, result left on the device (for NCCL allreduce of per-GPU partials):
+ * out_value_dev: one element of dtype, out_index_dev: one int64 (may be null). */
+int32_t ph_reduce_full_dev(int32_t red, int32_t dtype,
+                           const void* a, const ph_desc* a_desc,
+                           void* out_value_dev, int64_t* out_index_dev);
+/* Per-axis (defined by each_slice(axis) + fold, src/multi_indexable.cr:742-748):
+ * out has a_desc's extents without `axis`; dtype for SUM/MIN/MAX, int64 for ARG*. */
+int32_t ph_reduce_axis(int32_t red, int32_t dtype,
+                       const void* a, const ph_desc* a_desc, int32_t axis,
+                       void* out, const ph_desc* out_desc);
+
+/* ---- heat stencil (K9): examples/heat_equation.cr:38-51 -------------------------
+ * One explicit step on a contiguous row-major grid of `rank` (1..3) axes;
+ * `coeff_host` points at one element of dtype (F32/F64).  in != out. */
+int32_t ph_heat_step(int32_t dtype, int32_t rank, const int64_t* extents,
+                     const void* coeff_host, int32_t boundary_mode,
+                     const void* in, void* out);
+/* `steps` steps ping-ponging between the two buffers; the final state is in
+ * buf_a if steps is even, buf_b if odd. */
+int32_t ph_heat_run(int32_t dtype, int32_t rank, const int64_t* extents,
+                    const void* coeff_host, int32_t boundary_mode,
+                    void* buf_a, void* buf_b, int64_t steps);
+/* Slab-decomposed step (axis 0 sharded): the local slab holds planes
+ * [1, n0_local] plus ghost planes 0 and n0_local+1 (extents[0] = n0_local + 2);
+ * has_lo / has_hi say whether a neighbour exists on that side (else the edge
+ * plane is a fixed global boundary).  Computes planes [p_begin, p_end) only, so
+ * the caller can do the two edge planes first, start the halo exchange, then the
+ * interior (examples/heat_equation.cr generalised). */
+int32_t ph_heat_step_slab(int32_t dtype, int32_t rank, const int64_t* extents,
+                          const void* coeff_host, int32_t has_lo, int32_t has_hi,
+                          int64_t p_begin, int64_t p_end,
+                          const void* in, void* out, void* cuda_stream);
+
+/* ---- multi-GPU (one process per GPU, NCCL over NVLink) ---------------------------- */
+int32_t ph_comm_unique_id(uint8_t* out128);                 /* rank 0; broadcast by the host */
+int32_t ph_comm_init(int32_t nranks, int32_t rank, const uint8_t* id128);
+int32_t ph_comm_destroy(void);
+int32_t ph_allreduce(int32_t red, int32_t dtype, void* buf_dev, int64_t count); /* SUM/MIN/MAX in place */
+int32_t ph_allgather(const void* send_dev, void* recv_dev, int64_t nbytes_per_rank);
+/* exchange one plane with each neighbour rank (lo = rank-1, hi = rank+1; -1 = none):
+ * sends send_lo -> lo, send_hi -> hi; receives recv_lo <- lo, recv_hi <- hi. */
+int32_t ph_halo_exchange(const void* send_lo, void* recv_lo, int32_t lo_rank,
+                         const void* send_hi, void* recv_hi, int32_t hi_rank,
+                         int64_t nbytes, void* cuda_stream);
+/* `steps` slab steps with the exchange overlapped with the interior update. */
+int32_t ph_heat_run_sharded(int32_t dtype, int32_t rank, const int64_t* local_extents,
+                            const void* coeff_host, void* buf_a, void* buf_b, int64_t steps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PH_GPU_H */

@@ -1,0 +1,12 @@
+"""ph-core_b200: device-resident NArray backing for ph-core's data-parallel hot path
+on NVIDIA B200 (sm_100a).  The product is csrc/ (hand-written CUDA behind the C-ABI of
+include/ph_gpu.h); this Python package is the thin host mirror used by tests and bench.
+There is no CPU fallback: importing works anywhere, computing needs the GPU library."""
+from . import _lib
+from ._lib import PhDesc, PhError, init, load, check, K
+from .narray import (DeviceNArray, ShapeError, DimensionError, CrIndexError, CrOverflowError,
+                     CrDivisionByZeroError, CrArgumentError, CrEmptyError, DeviceBlockError)
+
+__all__ = ["DeviceNArray", "PhDesc", "PhError", "init", "load", "check", "K", "ShapeError", "DimensionError",
+           "CrIndexError", "CrOverflowError", "CrDivisionByZeroError", "CrArgumentError", "CrEmptyError",
+           "DeviceBlockError"]

@@ -1,0 +1,156 @@
+"""ctypes binding of libphgpu.so (include/ph_gpu.h).  Plumbing only: every compute call
+goes to the CUDA library; if the library is missing or fails, this raises -- there is
+no CPU fallback anywhere in this package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libphgpu.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "ph_gpu.h")
+
+PH_MAX_RANK = 8
+
+
+class PhDesc(C.Structure):
+    """struct ph_desc (include/ph_gpu.h)"""
+    _fields_ = [("rank", C.c_int32), ("_pad", C.c_int32), ("offset", C.c_int64),
+                ("extent", C.c_int64 * PH_MAX_RANK), ("stride", C.c_int64 * PH_MAX_RANK)]
+
+    @classmethod
+    def make(cls, extents, strides, offset=0) -> "PhDesc":
+        d = cls()
+        if len(extents) > PH_MAX_RANK:
+            raise ValueError(f"rank {len(extents)} exceeds PH_MAX_RANK")
+        d.rank = len(extents)
+        d.offset = int(offset)
+        for i, (e, s) in enumerate(zip(extents, strides)):
+            d.extent[i] = int(e)
+            d.stride[i] = int(s)
+        return d
+
+    @classmethod
+    def contiguous(cls, shape) -> "PhDesc":
+        strides, acc = [], 1
+        for e in reversed(list(shape)):
+            strides.append(acc)
+            acc *= int(e)
+        return cls.make(list(shape), list(reversed(strides)))
+
+
+def header_constants() -> dict:
+    """Parse the enum constants out of ph_gpu.h so Python never re-declares them."""
+    text = open(HEADER_PATH).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    consts = {}
+    for body in re.findall(r"enum\s*\{(.*?)\}", text, flags=re.S):
+        nxt = 0
+        for item in body.split(","):
+            item = item.strip()
+            if not item:
+                continue
+            if "=" in item:
+                name, val = [x.strip() for x in item.split("=")]
+                nxt = int(val, 0)
+            else:
+                name = item
+            consts[name] = nxt
+            nxt += 1
+    return consts
+
+
+def header_functions() -> list:
+    """Names of every function ph_gpu.h declares."""
+    text = open(HEADER_PATH).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ph_[a-z0-9_]+)\s*\(", text)))
+
+
+K = header_constants()
+globals().update(K)
+
+
+class PhError(RuntimeError):
+    """A non-zero status from libphgpu (CUDA / NCCL / argument failure)."""
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PhError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp, i32, i64, u8p = C.c_void_p, C.c_int32, C.c_int64, C.c_void_p
+    dp = C.POINTER(PhDesc)
+    sig = {
+        "ph_init": [i32], "ph_shutdown": [], "ph_device_count": [C.POINTER(i32)], "ph_sm_count": [C.POINTER(i32)],
+        "ph_alloc": [C.c_size_t, C.POINTER(vp)], "ph_free": [vp],
+        "ph_h2d": [vp, vp, C.c_size_t], "ph_d2h": [vp, vp, C.c_size_t], "ph_d2d": [vp, vp, C.c_size_t],
+        "ph_host_alloc": [C.c_size_t, C.POINTER(vp)], "ph_host_free": [vp],
+        "ph_sync": [], "ph_set_stream": [vp], "ph_take_arith_flags": [C.POINTER(C.c_uint32)],
+        "ph_timer_start": [], "ph_timer_stop": [C.POINTER(C.c_float)],
+        "ph_ewise_binary": [i32, i32, vp, dp, vp, dp, vp, dp],
+        "ph_ewise_scalar": [i32, i32, vp, dp, vp, i32, vp, dp],
+        "ph_ewise_unary": [i32, i32, vp, dp, vp, dp],
+        "ph_ewise_mul_add": [i32, vp, dp, vp, dp, vp, dp, vp, dp],
+        "ph_compare": [i32, i32, vp, dp, vp, dp, u8p, dp],
+        "ph_compare_scalar": [i32, i32, vp, dp, vp, i32, u8p, dp],
+        "ph_mask_set_scalar": [i32, vp, dp, u8p, dp, vp],
+        "ph_mask_set_array": [i32, vp, dp, u8p, dp, vp, dp],
+        "ph_copy_strided": [i32, vp, dp, vp, dp],
+        "ph_fill_region": [i32, vp, dp, vp],
+        "ph_reduce_full": [i32, i32, vp, dp, vp, C.POINTER(i64)],
+        "ph_reduce_full_dev": [i32, i32, vp, dp, vp, vp],
+        "ph_reduce_axis": [i32, i32, vp, dp, i32, vp, dp],
+        "ph_heat_step": [i32, i32, C.POINTER(i64), vp, i32, vp, vp],
+        "ph_heat_run": [i32, i32, C.POINTER(i64), vp, i32, vp, vp, i64],
+        "ph_heat_step_slab": [i32, i32, C.POINTER(i64), vp, i32, i32, i64, i64, vp, vp, vp],
+        "ph_comm_unique_id": [vp], "ph_comm_init": [i32, i32, vp], "ph_comm_destroy": [],
+        "ph_allreduce": [i32, i32, vp, i64], "ph_allgather": [vp, vp, i64],
+        "ph_halo_exchange": [vp, vp, i32, vp, vp, i32, i64, vp],
+        "ph_heat_run_sharded": [i32, i32, C.POINTER(i64), vp, vp, vp, i64],
+    }
+    for name, args in sig.items():
+        if hasattr(lib, name):
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = i32
+    if hasattr(lib, "ph_stream"):
+        lib.ph_stream.restype = vp
+        lib.ph_stream.argtypes = []
+    if hasattr(lib, "ph_last_error_string"):
+        lib.ph_last_error_string.restype = C.c_char_p
+        lib.ph_last_error_string.argtypes = []
+    if hasattr(lib, "ph_launch_count"):
+        lib.ph_launch_count.restype = i64
+        lib.ph_launch_count.argtypes = []
+    _lib = lib
+    return lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        msg = load().ph_last_error_string()
+        raise PhError(f"libphgpu status {status}: {msg.decode() if msg else ''}")
+
+
+_inited_device = None
+
+
+def init(device: int | None = None) -> int:
+    """ph_init on `device` (default: LOCAL_RANK or 0).  Raises if there is no GPU."""
+    global _inited_device
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if _inited_device == device:
+        return device
+    check(load().ph_init(device))
+    _inited_device = device
+    return device

@@ -1,0 +1,388 @@
+// map_kernels.cuh -- the elementwise "map" kernel family (K1/K2/K3 of SURVEY.md 2.3).
+//
+// One functor F describes an N-input, 1-output element operation:
+//     using In = ...; using Out = ...; static constexpr int NIN = ...;
+//     static __device__ Out apply(const In (&x)[NIN], uint32_t& err);
+// and launch_map<F>() picks one of three kernels from the coalesced plan:
+//   flat : every operand is contiguous (or a broadcast scalar)      -> 256-bit vectors
+//   rows : innermost axis contiguous / broadcast, outer axes strided -> 256-bit vectors,
+//          row-vector operands are loaded once per block and kept in registers
+//   any  : arbitrary strides -> one element per thread per step
+// This replaces MultiIndexable.each_with's per-element coordinate loop
+// (src/multi_indexable.cr:1080-1102) and NArray#map (src/n_array.cr:589-595).
+#pragma once
+#include "ph_common.cuh"
+#include <algorithm>
+
+namespace ph {
+
+constexpr int MAP_THREADS = 256;
+
+enum OperandMode : int { OPND_ARRAY = 0, OPND_BCAST = 1, OPND_PARAM = 2, OPND_ROWVEC = 3 };
+
+template <int NIN>
+struct MapArgs {
+  const void* in[NIN];      // element 0 of each operand (offset already applied)
+  uint64_t param[NIN];      // scalar bits for OPND_PARAM
+  int mode[NIN];
+  void* out;
+  int64_t n;                // flat: elements; rows: inner extent
+  int64_t rows;             // rows: number of rows
+  int rows_per_block;
+  int all_array;            // every input is OPND_ARRAY
+  int64_t gx;               // rows: number of column tiles (1-D grid = gx * slabs * chunks)
+  uint32_t* flags;
+  OuterAxes outer;          // rows/any: operand k uses stride[k], the output uses stride[NIN]
+  // any-kernel only: innermost strides
+  int64_t inner_stride[NIN + 1];
+};
+
+template <typename F, int E>
+__device__ __forceinline__ void apply_group(const Group<typename F::In, E> (&x)[F::NIN],
+                                            Group<typename F::Out, E>& y, uint32_t& err) {
+#pragma unroll
+  for (int i = 0; i < E; i++) {
+    typename F::In v[F::NIN];
+#pragma unroll
+    for (int k = 0; k < F::NIN; k++) v[k] = x[k].v[i];
+    y.v[i] = F::apply(v, err);
+  }
+}
+
+// ------------------------------------------------------------------ flat
+template <typename F, int E, int UNROLL>
+__global__ void __launch_bounds__(MAP_THREADS) map_flat_kernel(const MapArgs<F::NIN> a) {
+  using In = typename F::In;
+  using Out = typename F::Out;
+  constexpr int NIN = F::NIN;
+  const int64_t tile = (int64_t)MAP_THREADS * E * UNROLL;
+  const int64_t base = (int64_t)blockIdx.x * tile;
+  uint32_t err = 0;
+  Out* __restrict__ out = reinterpret_cast<Out*>(a.out);
+
+  In scalar[NIN];
+#pragma unroll
+  for (int k = 0; k < NIN; k++) {
+    if (a.mode[k] == OPND_PARAM) scalar[k] = bits_to<In>(a.param[k]);
+    else if (a.mode[k] == OPND_BCAST) scalar[k] = *reinterpret_cast<const In*>(a.in[k]);
+    else scalar[k] = In();
+  }
+
+  if (base + tile <= a.n) {
+    Group<In, E> x[UNROLL][NIN];
+    if (a.all_array) {                       // hot path: no per-operand predicates
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++) {
+        const int64_t idx = base + ((int64_t)u * MAP_THREADS + threadIdx.x) * E;
+#pragma unroll
+        for (int k = 0; k < NIN; k++) x[u][k] = load_group<In, E>(reinterpret_cast<const In*>(a.in[k]) + idx);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++) {
+        const int64_t idx = base + ((int64_t)u * MAP_THREADS + threadIdx.x) * E;
+#pragma unroll
+        for (int k = 0; k < NIN; k++) {
+          if (a.mode[k] == OPND_ARRAY) x[u][k] = load_group<In, E>(reinterpret_cast<const In*>(a.in[k]) + idx);
+          else x[u][k] = splat_group<In, E>(scalar[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) {
+      const int64_t idx = base + ((int64_t)u * MAP_THREADS + threadIdx.x) * E;
+      Group<Out, E> y;
+      apply_group<F, E>(x[u], y, err);
+      store_group<Out, E>(out + idx, y);
+    }
+  } else {
+    for (int64_t i = base + threadIdx.x; i < a.n; i += MAP_THREADS) {
+      In v[NIN];
+#pragma unroll
+      for (int k = 0; k < NIN; k++)
+        v[k] = (a.mode[k] == OPND_ARRAY) ? reinterpret_cast<const In*>(a.in[k])[i] : scalar[k];
+      out[i] = F::apply(v, err);
+    }
+  }
+  if (err) atomicOr(a.flags, err);
+}
+
+// ------------------------------------------------------------------ rows
+// 1-D grid: the fastest block index tiles the inner axis (MAP_THREADS * E elements), the rest enumerates
+// (slab over the leading outer axes) x (chunk of rows_per_block rows of the LAST outer
+// axis), so inside a block consecutive rows differ by one constant stride per operand.
+template <typename F, int E, int UNROLL>
+__global__ void __launch_bounds__(MAP_THREADS) map_rows_kernel(const MapArgs<F::NIN> a) {
+  using In = typename F::In;
+  using Out = typename F::Out;
+  constexpr int NIN = F::NIN;
+  const int64_t by = (int64_t)blockIdx.x / a.gx;
+  const int64_t ctile = (int64_t)blockIdx.x - by * a.gx;
+  const int64_t col = (ctile * MAP_THREADS + threadIdx.x) * E;
+  if (col >= a.n) return;                          // whole groups only: n % E == 0 by dispatch
+  const int last = a.outer.n - 1;
+  const int64_t rows_last = a.outer.extent[last];
+  const int64_t chunks = (rows_last + a.rows_per_block - 1) / a.rows_per_block;
+  int64_t slab = by / chunks;
+  const int64_t chunk = by - slab * chunks;
+  uint32_t err = 0;
+
+  int64_t base[NIN + 1];
+#pragma unroll
+  for (int k = 0; k <= NIN; k++) base[k] = 0;
+  for (int ax = last - 1; ax >= 0; ax--) {         // leading outer axes: once per block
+    const int64_t e = a.outer.extent[ax];
+    const int64_t q = slab / e;
+    const int64_t c = slab - q * e;
+    slab = q;
+#pragma unroll
+    for (int k = 0; k <= NIN; k++) base[k] += c * a.outer.stride[k][ax];
+  }
+  int64_t step[NIN + 1];
+#pragma unroll
+  for (int k = 0; k <= NIN; k++) step[k] = a.outer.stride[k][last];
+
+  const In* in[NIN];
+  Group<In, E> fixed[NIN];                         // row-vector / scalar operands: loaded once
+#pragma unroll
+  for (int k = 0; k < NIN; k++) {
+    in[k] = reinterpret_cast<const In*>(a.in[k]) + base[k];
+    if (a.mode[k] == OPND_PARAM) fixed[k] = splat_group<In, E>(bits_to<In>(a.param[k]));
+    else if (a.mode[k] == OPND_ROWVEC) fixed[k] = load_group<In, E>(in[k] + col);
+    else fixed[k] = splat_group<In, E>(In());
+  }
+  Out* out = reinterpret_cast<Out*>(a.out) + base[NIN] + col;
+
+  const int64_t r0 = chunk * a.rows_per_block;
+  const int64_t r1 = (r0 + a.rows_per_block < rows_last) ? r0 + a.rows_per_block : rows_last;
+  int64_t r = r0;
+  // x[u][k] of a fixed operand is written once here and never again: inside the loop
+  // only array operands are (re)loaded, so the hot loop has no selects.
+  Group<In, E> x[UNROLL][NIN];
+#pragma unroll
+  for (int u = 0; u < UNROLL; u++)
+#pragma unroll
+    for (int k = 0; k < NIN; k++) x[u][k] = fixed[k];
+  for (; r + UNROLL <= r1; r += UNROLL) {
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) {
+#pragma unroll
+      for (int k = 0; k < NIN; k++) {
+        if (a.mode[k] == OPND_ARRAY) x[u][k] = load_group<In, E>(in[k] + (r + u) * step[k] + col);
+        else if (a.mode[k] == OPND_BCAST) x[u][k] = splat_group<In, E>(in[k][(r + u) * step[k]]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) {
+      Group<Out, E> y;
+      apply_group<F, E>(x[u], y, err);
+      store_group<Out, E>(out + (r + u) * step[NIN], y);
+    }
+  }
+  for (; r < r1; r++) {
+#pragma unroll
+    for (int k = 0; k < NIN; k++) {
+      if (a.mode[k] == OPND_ARRAY) x[0][k] = load_group<In, E>(in[k] + r * step[k] + col);
+      else if (a.mode[k] == OPND_BCAST) x[0][k] = splat_group<In, E>(in[k][r * step[k]]);
+    }
+    Group<Out, E> y;
+    apply_group<F, E>(x[0], y, err);
+    store_group<Out, E>(out + r * step[NIN], y);
+  }
+  if (err) atomicOr(a.flags, err);
+}
+
+// ------------------------------------------------------------------ any strides
+template <typename F>
+__global__ void __launch_bounds__(MAP_THREADS) map_any_kernel(const MapArgs<F::NIN> a, int64_t total) {
+  using In = typename F::In;
+  using Out = typename F::Out;
+  constexpr int NIN = F::NIN;
+  uint32_t err = 0;
+  const int64_t stride = (int64_t)gridDim.x * MAP_THREADS;
+  for (int64_t i = (int64_t)blockIdx.x * MAP_THREADS + threadIdx.x; i < total; i += stride) {
+    int64_t r = i / a.n;
+    const int64_t c = i - r * a.n;
+    int64_t off[NIN + 1];
+#pragma unroll
+    for (int k = 0; k <= NIN; k++) off[k] = c * a.inner_stride[k];
+    for (int ax = a.outer.n - 1; ax >= 0; ax--) {
+      const int64_t e = a.outer.extent[ax];
+      const int64_t q = r / e;
+      const int64_t cc = r - q * e;
+      r = q;
+#pragma unroll
+      for (int k = 0; k <= NIN; k++) off[k] += cc * a.outer.stride[k][ax];
+    }
+    In v[NIN];
+#pragma unroll
+    for (int k = 0; k < NIN; k++)
+      v[k] = (a.mode[k] == OPND_PARAM) ? bits_to<In>(a.param[k])
+                                       : reinterpret_cast<const In*>(a.in[k])[off[k]];
+    reinterpret_cast<Out*>(a.out)[off[NIN]] = F::apply(v, err);
+  }
+  if (err) atomicOr(a.flags, err);
+}
+
+// ------------------------------------------------------------------ dispatch
+struct MapOperand {
+  const void* base = nullptr;    // device pointer (element 0 of the buffer), or null for a param
+  const ph_desc* desc = nullptr;
+  uint64_t param = 0;
+  bool is_param = false;
+};
+
+template <typename F, int E, int UNROLL>
+inline int32_t launch_flat(const MapArgs<F::NIN>& a) {
+  const int64_t tile = (int64_t)MAP_THREADS * E * UNROLL;
+  const int64_t blocks = ceil_div(a.n, tile);
+  if (blocks > 0x7fffffffLL) return set_error(PH_ERR_INVALID, "array too large for one launch");
+  map_flat_kernel<F, E, UNROLL><<<(unsigned)blocks, MAP_THREADS, 0, rt().stream>>>(a);
+  PH_LAUNCH_CHECK("map_flat_kernel");
+  return PH_OK;
+}
+
+template <typename F, int E, int UNROLL>
+inline int32_t launch_rows(MapArgs<F::NIN>& a) {
+  const int64_t gx = ceil_div(a.n, (int64_t)MAP_THREADS * E);
+  const int64_t rows_last = a.outer.extent[a.outer.n - 1];
+  const int64_t slabs = a.rows / rows_last;
+  // enough blocks for ~8 waves, but >= 4*UNROLL rows per block so row-vectors amortise
+  const int64_t target_blocks = (int64_t)rt().sm_count * 8 * 8;
+  int64_t chunks = std::max<int64_t>(1, target_blocks / std::max<int64_t>(1, gx * slabs));
+  int64_t rpb = std::max<int64_t>(ceil_div(rows_last, chunks), std::min<int64_t>(rows_last, UNROLL * 4));
+  chunks = ceil_div(rows_last, rpb);
+  const int64_t blocks = gx * slabs * chunks;
+  if (blocks > 0x7fffffffLL) return set_error(PH_ERR_INVALID, "array too large for one launch");
+  a.rows_per_block = (int)std::min<int64_t>(rpb, 0x7fffffff);
+  a.gx = gx;
+  map_rows_kernel<F, E, UNROLL><<<(unsigned)blocks, MAP_THREADS, 0, rt().stream>>>(a);
+  PH_LAUNCH_CHECK("map_rows_kernel");
+  return PH_OK;
+}
+
+// ops[0..NIN-1] are the inputs, `out`/`out_desc` the output.
+template <typename F>
+int32_t launch_map(const MapOperand* ops, void* out, const ph_desc* out_desc) {
+  using In = typename F::In;
+  using Out = typename F::Out;
+  constexpr int NIN = F::NIN;
+  constexpr int WIDE = sizeof(In) > sizeof(Out) ? sizeof(In) : sizeof(Out);
+  PH_REQUIRE_INIT();
+  if (!out || !out_desc) return set_error(PH_ERR_INVALID, "null output");
+
+  // plan over the array operands + the output (output last)
+  const ph_desc* descs[MAX_OPERANDS];
+  int slot[NIN];
+  int nd = 0;
+  for (int k = 0; k < NIN; k++) {
+    if (ops[k].is_param) { slot[k] = -1; continue; }
+    if (!ops[k].base || !ops[k].desc) return set_error(PH_ERR_INVALID, "null input operand %d", k);
+    slot[k] = nd;
+    descs[nd++] = ops[k].desc;
+  }
+  const int out_slot = nd;
+  descs[nd++] = out_desc;
+  Plan p;
+  int32_t st = make_plan(p, nd, descs);
+  if (st != PH_OK) return st;
+  if (p.total == 0) return PH_OK;
+
+  MapArgs<NIN> a;
+  memset(&a, 0, sizeof(a));
+  a.flags = rt().d_flags;
+  a.out = reinterpret_cast<Out*>(out) + p.offset[out_slot];
+  for (int k = 0; k < NIN; k++) {
+    if (ops[k].is_param) { a.mode[k] = OPND_PARAM; a.param[k] = ops[k].param; a.in[k] = nullptr; }
+    else a.in[k] = reinterpret_cast<const In*>(ops[k].base) + p.offset[slot[k]];
+  }
+
+  const int inner = p.rank - 1;   // -1 when rank == 0 (single element)
+  auto in_stride = [&](int k, int ax) { return p.stride[slot[k]][ax]; };
+
+  // ---- vector width: every array operand and the output must be aligned to its group
+  auto pick_width = [&](bool rows) {
+    int vb = 32;
+    for (; vb > WIDE; vb >>= 1) {
+      const int e = vb / WIDE;
+      bool ok = (p.rank == 0 ? 1 : p.extent[inner]) % e == 0 || !rows;
+      auto aligned = [&](const void* ptr, int esz, int slot_idx) {
+        if (((uintptr_t)ptr) % (uintptr_t)(e * esz)) return false;
+        if (rows)
+          for (int ax = 0; ax < inner; ax++)
+            if ((p.stride[slot_idx][ax] * esz) % (e * esz)) return false;
+        return true;
+      };
+      if (!aligned(a.out, sizeof(Out), out_slot)) ok = false;
+      for (int k = 0; k < NIN && ok; k++) {
+        if (a.mode[k] == OPND_PARAM) continue;
+        if (p.rank > 0 && in_stride(k, inner) == 0) {   // broadcast along the inner axis: scalar loads
+          continue;
+        }
+        if (!aligned(a.in[k], sizeof(In), slot[k])) ok = false;
+      }
+      if (ok) break;
+    }
+    return vb;
+  };
+
+  // ---- flat?
+  bool flat = p.rank <= 1;
+  if (flat && p.rank == 1) {
+    if (p.stride[out_slot][0] != 1) flat = false;
+    for (int k = 0; k < NIN && flat; k++)
+      if (a.mode[k] != OPND_PARAM && in_stride(k, 0) != 1 && in_stride(k, 0) != 0) flat = false;
+  }
+  if (flat) {
+    a.n = p.total;
+    for (int k = 0; k < NIN; k++)
+      if (a.mode[k] != OPND_PARAM)
+        a.mode[k] = (p.rank == 0 || in_stride(k, 0) == 0) ? OPND_BCAST : OPND_ARRAY;
+    a.all_array = 1;
+    for (int k = 0; k < NIN; k++) if (a.mode[k] != OPND_ARRAY) a.all_array = 0;
+    const int vb = pick_width(false);
+    if (vb == 32 && WIDE <= 16) return launch_flat<F, 32 / WIDE, 2>(a);
+    if (vb >= 16 && WIDE <= 8) return launch_flat<F, 16 / WIDE, 4>(a);
+    return launch_flat<F, 1, 4>(a);
+  }
+
+  // ---- outer axes
+  a.outer.n = inner;
+  for (int ax = 0; ax < inner; ax++) {
+    a.outer.extent[ax] = p.extent[ax];
+    for (int k = 0; k < NIN; k++) a.outer.stride[k][ax] = (a.mode[k] == OPND_PARAM) ? 0 : in_stride(k, ax);
+    a.outer.stride[NIN][ax] = p.stride[out_slot][ax];
+  }
+  a.n = p.extent[inner];
+  a.rows = p.total / a.n;
+
+  // ---- rows?
+  bool rows = p.stride[out_slot][inner] == 1;
+  for (int k = 0; k < NIN && rows; k++)
+    if (a.mode[k] != OPND_PARAM && in_stride(k, inner) != 1 && in_stride(k, inner) != 0) rows = false;
+  if (rows) {
+    for (int k = 0; k < NIN; k++) {
+      if (a.mode[k] == OPND_PARAM) continue;
+      if (in_stride(k, inner) == 0) { a.mode[k] = OPND_BCAST; continue; }
+      bool rowvec = true;
+      for (int ax = 0; ax < inner; ax++) if (in_stride(k, ax) != 0) rowvec = false;
+      a.mode[k] = rowvec ? OPND_ROWVEC : OPND_ARRAY;
+    }
+    a.all_array = 1;
+    for (int k = 0; k < NIN; k++) if (a.mode[k] != OPND_ARRAY) a.all_array = 0;
+    const int vb = pick_width(true);
+    if (vb == 32 && WIDE <= 16) return launch_rows<F, 32 / WIDE, 4>(a);
+    if (vb >= 16 && WIDE <= 8) return launch_rows<F, 16 / WIDE, 4>(a);
+    return launch_rows<F, 1, 4>(a);
+  }
+
+  // ---- anything else
+  for (int k = 0; k < NIN; k++) a.inner_stride[k] = (a.mode[k] == OPND_PARAM) ? 0 : in_stride(k, inner);
+  a.inner_stride[NIN] = p.stride[out_slot][inner];
+  const int64_t blocks = std::min<int64_t>(ceil_div(p.total, MAP_THREADS), (int64_t)rt().sm_count * 32);
+  map_any_kernel<F><<<(unsigned)blocks, MAP_THREADS, 0, rt().stream>>>(a, p.total);
+  PH_LAUNCH_CHECK("map_any_kernel");
+  return PH_OK;
+}
+
+}  // namespace ph

@@ -1,0 +1,266 @@
+// runtime.cu -- device selection, stream, pool allocation, transfers, flags, timers,
+// and the descriptor planner shared by every kernel family.
+// Replaces the storage half of NArray (src/n_array.cr:20-79, 230-232, 372-395).
+#include "ph_common.cuh"
+#include <stdarg.h>
+#include <stdio.h>
+#include <algorithm>
+
+namespace ph {
+
+Runtime& rt() {
+  static Runtime r;
+  return r;
+}
+
+int32_t set_error(int32_t code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(rt().err, sizeof(rt().err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int32_t check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return PH_OK;
+  return set_error(PH_ERR_CUDA, "CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+}
+
+int32_t ensure_scratch(size_t bytes) {
+  Runtime& r = rt();
+  if (r.scratch_bytes >= bytes) return PH_OK;
+  if (r.d_scratch) {
+    PH_CUDA(cudaStreamSynchronize(r.stream));
+    PH_CUDA(cudaFree(r.d_scratch));
+    r.d_scratch = nullptr;
+    r.scratch_bytes = 0;
+  }
+  size_t want = std::max(bytes, (size_t)1 << 20);
+  PH_CUDA(cudaMalloc(&r.d_scratch, want));
+  r.scratch_bytes = want;
+  return PH_OK;
+}
+
+// Normalise N descriptors over shared extents: drop size-1 axes,
+// merge axis j into j+1 when stride[j] == stride[j+1] * extent[j+1] for EVERY operand.
+int32_t make_plan(Plan& p, int nops, const ph_desc* const* descs) {
+  if (nops < 1 || nops > MAX_OPERANDS) return set_error(PH_ERR_INVALID, "bad operand count %d", nops);
+  for (int k = 0; k < nops; k++) {
+    if (!descs[k]) return set_error(PH_ERR_INVALID, "null descriptor (operand %d)", k);
+    if (descs[k]->rank < 0 || descs[k]->rank > PH_MAX_RANK)
+      return set_error(PH_ERR_INVALID, "descriptor rank %d out of range (operand %d)", descs[k]->rank, k);
+    if (descs[k]->rank != descs[0]->rank)
+      return set_error(PH_ERR_INVALID, "descriptor ranks differ (%d vs %d)", descs[k]->rank, descs[0]->rank);
+    for (int i = 0; i < descs[0]->rank; i++)
+      if (descs[k]->extent[i] != descs[0]->extent[i])
+        return set_error(PH_ERR_INVALID, "descriptor extents differ on axis %d", i);
+  }
+  p.nops = nops;
+  p.rank = 0;
+  p.total = 1;
+  for (int k = 0; k < nops; k++) p.offset[k] = descs[k]->offset;
+  const int rank = descs[0]->rank;
+  for (int i = 0; i < rank; i++) {
+    int64_t e = descs[0]->extent[i];
+    if (e < 0) return set_error(PH_ERR_INVALID, "negative extent on axis %d", i);
+    p.total *= e;
+  }
+  if (rank == 0) p.total = 1;
+  if (p.total == 0) return PH_OK;
+  for (int i = 0; i < rank; i++) {
+    int64_t e = descs[0]->extent[i];
+    if (e == 1) continue;
+    bool merged = false;
+    if (p.rank > 0) {
+      int j = p.rank - 1;
+      bool ok = true;
+      for (int k = 0; k < nops; k++)
+        if (p.stride[k][j] != descs[k]->stride[i] * e) { ok = false; break; }
+      if (ok) {
+        p.extent[j] *= e;
+        for (int k = 0; k < nops; k++) p.stride[k][j] = descs[k]->stride[i];
+        merged = true;
+      }
+    }
+    if (!merged) {
+      p.extent[p.rank] = e;
+      for (int k = 0; k < nops; k++) p.stride[k][p.rank] = descs[k]->stride[i];
+      p.rank++;
+    }
+  }
+  return PH_OK;
+}
+
+}  // namespace ph
+
+using namespace ph;
+
+extern "C" {
+
+int32_t ph_device_count(int32_t* out) {
+  if (!out) return set_error(PH_ERR_INVALID, "null out");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { *out = 0; return check_cuda(e, "cudaGetDeviceCount"); }
+  *out = n;
+  return PH_OK;
+}
+
+int32_t ph_init(int32_t device) {
+  Runtime& r = rt();
+  if (r.inited && r.device == device) return PH_OK;
+  if (r.inited) ph_shutdown();
+  int n = 0;
+  PH_CUDA(cudaGetDeviceCount(&n));
+  if (device < 0 || device >= n) return set_error(PH_ERR_INVALID, "device %d not in [0,%d)", device, n);
+  PH_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  PH_CUDA(cudaGetDeviceProperties(&prop, device));
+  r.sm_count = prop.multiProcessorCount;
+  PH_CUDA(cudaStreamCreateWithFlags(&r.own_stream, cudaStreamNonBlocking));
+  PH_CUDA(cudaStreamCreateWithFlags(&r.aux_stream, cudaStreamNonBlocking));
+  r.stream = r.own_stream;
+  PH_CUDA(cudaEventCreateWithFlags(&r.ev_a, cudaEventDisableTiming));
+  PH_CUDA(cudaEventCreateWithFlags(&r.ev_b, cudaEventDisableTiming));
+  PH_CUDA(cudaEventCreate(&r.ev_t0));
+  PH_CUDA(cudaEventCreate(&r.ev_t1));
+  PH_CUDA(cudaMalloc((void**)&r.d_flags, 64));
+  PH_CUDA(cudaMemset(r.d_flags, 0, 64));
+  PH_CUDA(cudaMallocHost((void**)&r.h_flags, 64));
+  PH_CUDA(cudaMallocHost(&r.h_scratch, 256));
+  // keep freed blocks in the pool: fluent ops allocate one result array per operator
+  cudaMemPool_t pool;
+  PH_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t threshold = UINT64_MAX;
+  PH_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+  r.device = device;
+  r.launches = 0;
+  r.inited = true;
+  return PH_OK;
+}
+
+int32_t ph_shutdown(void) {
+  Runtime& r = rt();
+  if (!r.inited) return PH_OK;
+  cudaSetDevice(r.device);
+  cudaDeviceSynchronize();
+  if (r.d_scratch) cudaFree(r.d_scratch);
+  if (r.d_flags) cudaFree(r.d_flags);
+  if (r.h_flags) cudaFreeHost(r.h_flags);
+  if (r.h_scratch) cudaFreeHost(r.h_scratch);
+  if (r.ev_a) cudaEventDestroy(r.ev_a);
+  if (r.ev_b) cudaEventDestroy(r.ev_b);
+  if (r.ev_t0) cudaEventDestroy(r.ev_t0);
+  if (r.ev_t1) cudaEventDestroy(r.ev_t1);
+  if (r.own_stream) cudaStreamDestroy(r.own_stream);
+  if (r.aux_stream) cudaStreamDestroy(r.aux_stream);
+  r = Runtime();
+  return PH_OK;
+}
+
+int32_t ph_sm_count(int32_t* out) {
+  PH_REQUIRE_INIT();
+  if (!out) return set_error(PH_ERR_INVALID, "null out");
+  *out = rt().sm_count;
+  return PH_OK;
+}
+
+int32_t ph_alloc(size_t nbytes, void** out_dev) {
+  PH_REQUIRE_INIT();
+  if (!out_dev) return set_error(PH_ERR_INVALID, "null out_dev");
+  *out_dev = nullptr;
+  if (nbytes == 0) nbytes = 1;   // empty NArrays still own a (tiny) buffer
+  PH_CUDA(cudaMallocAsync(out_dev, nbytes, rt().stream));
+  return PH_OK;
+}
+
+int32_t ph_free(void* dev) {
+  PH_REQUIRE_INIT();
+  if (!dev) return PH_OK;
+  PH_CUDA(cudaFreeAsync(dev, rt().stream));
+  return PH_OK;
+}
+
+int32_t ph_h2d(void* dst_dev, const void* src_host, size_t nbytes) {
+  PH_REQUIRE_INIT();
+  if (nbytes == 0) return PH_OK;
+  if (!dst_dev || !src_host) return set_error(PH_ERR_INVALID, "null pointer in ph_h2d");
+  // synchronous w.r.t. the host pointer unless it is pinned (SURVEY.md 8(b) ownership)
+  PH_CUDA(cudaMemcpyAsync(dst_dev, src_host, nbytes, cudaMemcpyHostToDevice, rt().stream));
+  return PH_OK;
+}
+
+int32_t ph_d2h(void* dst_host, const void* src_dev, size_t nbytes) {
+  PH_REQUIRE_INIT();
+  if (nbytes == 0) return PH_OK;
+  if (!dst_host || !src_dev) return set_error(PH_ERR_INVALID, "null pointer in ph_d2h");
+  PH_CUDA(cudaMemcpyAsync(dst_host, src_dev, nbytes, cudaMemcpyDeviceToHost, rt().stream));
+  PH_CUDA(cudaStreamSynchronize(rt().stream));
+  return PH_OK;
+}
+
+int32_t ph_d2d(void* dst_dev, const void* src_dev, size_t nbytes) {
+  PH_REQUIRE_INIT();
+  if (nbytes == 0) return PH_OK;
+  if (!dst_dev || !src_dev) return set_error(PH_ERR_INVALID, "null pointer in ph_d2d");
+  PH_CUDA(cudaMemcpyAsync(dst_dev, src_dev, nbytes, cudaMemcpyDeviceToDevice, rt().stream));
+  return PH_OK;
+}
+
+int32_t ph_host_alloc(size_t nbytes, void** out_host) {
+  if (!out_host) return set_error(PH_ERR_INVALID, "null out_host");
+  PH_CUDA(cudaMallocHost(out_host, nbytes ? nbytes : 1));
+  return PH_OK;
+}
+
+int32_t ph_host_free(void* host) {
+  if (!host) return PH_OK;
+  PH_CUDA(cudaFreeHost(host));
+  return PH_OK;
+}
+
+int32_t ph_sync(void) {
+  PH_REQUIRE_INIT();
+  PH_CUDA(cudaStreamSynchronize(rt().stream));
+  return PH_OK;
+}
+
+void* ph_stream(void) { return (void*)rt().stream; }
+
+int32_t ph_set_stream(void* cuda_stream) {
+  PH_REQUIRE_INIT();
+  rt().stream = cuda_stream ? (cudaStream_t)cuda_stream : rt().own_stream;
+  return PH_OK;
+}
+
+const char* ph_last_error_string(void) { return rt().err; }
+
+int32_t ph_take_arith_flags(uint32_t* out_flags) {
+  PH_REQUIRE_INIT();
+  if (!out_flags) return set_error(PH_ERR_INVALID, "null out_flags");
+  Runtime& r = rt();
+  PH_CUDA(cudaMemcpyAsync(r.h_flags, r.d_flags, 4, cudaMemcpyDeviceToHost, r.stream));
+  PH_CUDA(cudaMemsetAsync(r.d_flags, 0, 4, r.stream));
+  PH_CUDA(cudaStreamSynchronize(r.stream));
+  *out_flags = *r.h_flags;
+  return PH_OK;
+}
+
+int32_t ph_timer_start(void) {
+  PH_REQUIRE_INIT();
+  PH_CUDA(cudaEventRecord(rt().ev_t0, rt().stream));
+  return PH_OK;
+}
+
+int32_t ph_timer_stop(float* out_ms) {
+  PH_REQUIRE_INIT();
+  if (!out_ms) return set_error(PH_ERR_INVALID, "null out_ms");
+  PH_CUDA(cudaEventRecord(rt().ev_t1, rt().stream));
+  PH_CUDA(cudaEventSynchronize(rt().ev_t1));
+  PH_CUDA(cudaEventElapsedTime(out_ms, rt().ev_t0, rt().ev_t1));
+  return PH_OK;
+}
+
+int64_t ph_launch_count(void) { return rt().launches; }
+
+}  // extern "C"
