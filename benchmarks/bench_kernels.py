@@ -1,0 +1,162 @@
+#!/usr/bin/env python
+"""Per-kernel bandwidth table for every BASELINE.json config.  One JSON row per
+kernel: algorithmic bytes, best/median ms over `reps` launches (CUDA events on the launching
+stream), GB/s, fraction of the measured copy peak and of the nominal 8 TB/s.
+    python benchmarks/bench_kernels.py [--quick] [--only NAME] > gpurun_out/kernels.jsonl"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import ph_core_b200 as ph
+from ph_core_b200 import DeviceNArray as D, heat, rng, _lib
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--quick", action="store_true")
+ap.add_argument("--only", default="")
+ap.add_argument("--reps", type=int, default=20)
+ap.add_argument("--big-heat", action="store_true", help="include the 2048^3 f32 stencil (69 GB)")
+args = ap.parse_args()
+
+ph.init(0)
+lib = ph.load()
+peak = 6546.2
+try:
+    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def timeit(fn, reps=None, warm=3):
+    reps = reps or args.reps
+    for _ in range(warm):
+        fn()
+    ts = []
+    ms = C.c_float()
+    for _ in range(reps):
+        ph.check(lib.ph_timer_start())
+        fn()
+        ph.check(lib.ph_timer_stop(C.byref(ms)))
+        ts.append(ms.value)
+    return min(ts), statistics.median(ts)
+
+
+def row(name, nbytes, fn, unit_count=None, unit=None, reps=None, note=""):
+    if args.only and args.only not in name:
+        return
+    best, med = timeit(fn, reps)
+    r = {"kernel": name, "bytes": int(nbytes), "ms_best": round(best, 5), "ms_median": round(med, 5),
+         "gbs": round(nbytes / (med * 1e-3) / 1e9, 1), "frac_measured": round(nbytes / (med * 1e-3) / 1e9 / peak, 4),
+         "frac_nominal_8000": round(nbytes / (med * 1e-3) / 1e9 / 8000, 4)}
+    if unit_count:
+        r[unit] = round(unit_count / (med * 1e-3) / 1e9, 2)
+    if note:
+        r["note"] = note
+    print(json.dumps(r), flush=True)
+
+
+def rand(shape, dtype, seed):
+    g = np.random.Generator(np.random.Philox(key=20261017, counter=[0, 0, seed, 0]))
+    if np.dtype(dtype).kind == "f":
+        return g.random(shape, dtype=dtype)
+    return g.integers(-8, 9, size=shape).astype(dtype)
+
+
+def dev_rand(shape, dtype, seed):
+    """Fill large arrays on the device from a small random tile (keeps host RAM/time small)."""
+    total = int(np.prod(shape))
+    tile = rand(min(total, 1 << 22), dtype, seed)
+    d = D(shape, dtype)
+    flat = D([total], dtype, d._buf)
+    t = D.from_host(tile)
+    pos = 0
+    while pos < total:
+        n = min(tile.size, total - pos)
+        ph.check(lib.ph_d2d(flat.ptr + pos * flat.dtype.itemsize, t.ptr, n * flat.dtype.itemsize))
+        pos += n
+    ph.check(lib.ph_sync())
+    return d
+
+
+# ------------------------------------------------------------------ config 1: elementwise 8192^2 f32
+E = (8192, 8192) if not args.quick else (2048, 8192)
+NE = E[0] * E[1]
+a, c = dev_rand(E, np.float32, 1), dev_rand(E, np.float32, 3)
+b = D.from_host(rand((1, E[1]), np.float32, 2))
+out = D(E, np.float32)
+F32 = ph.K["PH_F32"]
+da, dc, do, db = a.desc(), c.desc(), out.desc(), b.bcast_desc(E)
+row("ewise a+c same shape f32 (flat)", 3 * NE * 4,
+    lambda: ph.check(lib.ph_ewise_binary(ph.K["PH_ADD"], F32, a.ptr, C.byref(da), c.ptr, C.byref(dc), out.ptr, C.byref(do))))
+row("ewise a*b rowvec broadcast f32 (rows)", 2 * NE * 4 + E[1] * 4,
+    lambda: ph.check(lib.ph_ewise_binary(ph.K["PH_MUL"], F32, a.ptr, C.byref(da), b.ptr, C.byref(db), out.ptr, C.byref(do))))
+row("ewise fused (a*b)+c f32", 3 * NE * 4 + E[1] * 4,
+    lambda: ph.check(lib.ph_ewise_mul_add(F32, a.ptr, C.byref(da), b.ptr, C.byref(db), c.ptr, C.byref(dc), out.ptr, C.byref(do))))
+s2 = np.array(2.0, np.float32)
+row("ewise a*2 scalar f32", 2 * NE * 4,
+    lambda: ph.check(lib.ph_ewise_scalar(ph.K["PH_MUL"], F32, a.ptr, C.byref(da), s2.ctypes.data, 0, out.ptr, C.byref(do))))
+mask = D(E, np.bool_)
+dm = mask.desc()
+row("compare a>c -> bool f32", 2 * NE * 4 + NE,
+    lambda: ph.check(lib.ph_compare(ph.K["PH_GT"], F32, a.ptr, C.byref(da), c.ptr, C.byref(dc), mask.ptr, C.byref(dm))))
+row("mask store scalar f32", NE + 2 * NE * 4,
+    lambda: ph.check(lib.ph_mask_set_scalar(4, out.ptr, C.byref(do), mask.ptr, C.byref(dm), s2.ctypes.data)),
+    note="bytes = mask + read-modify-write of dst (upper bound; untouched groups skip dst)")
+row("mask store array f32", NE + 3 * NE * 4,
+    lambda: ph.check(lib.ph_mask_set_array(4, out.ptr, C.byref(do), mask.ptr, C.byref(dm), a.ptr, C.byref(da))))
+ai = dev_rand(E, np.int32, 4); ci = dev_rand(E, np.int32, 5); oi = D(E, np.int32)
+row("ewise a+c i32 overflow-checked", 3 * NE * 4,
+    lambda: ph.check(lib.ph_ewise_binary(ph.K["PH_ADD"], ph.K["PH_I32"], ai.ptr, C.byref(da), ci.ptr, C.byref(dc), oi.ptr, C.byref(do))))
+del a, c, out, mask, ai, ci, oi
+
+# ------------------------------------------------------------------ config 2: strided views 16384^2 f64
+S = 16384 if not args.quick else 4096
+src = dev_rand((S, S), np.float64, 6)
+NS = S * S
+row("gather narr[0..2.., ..-1] f64 (row-strided)", 2 * (NS // 2) * 8, lambda: src[rng(0, None, 2), rng(None, -1)])
+row("gather narr[.., 0..2..] f64 (col-strided)", 2 * (NS // 2) * 8, lambda: src[rng(None, None), rng(0, None, 2)],
+    note="physical sectors = 1.5x algorithmic; ceiling 66.7% on algorithmic bytes")
+row("gather reversed narr[..-1.., ..-1..] f64", 2 * NS * 8, lambda: src[rng(None, None, -1), rng(None, None, -1)])
+row("transposed copy narr.permute f64", 2 * NS * 8, lambda: src.permute())
+dst = D([S, S], np.float64)
+row("transposed scatter mutable_view.permute[..]=src f64", 2 * NS * 8,
+    lambda: dst.mutable_view().permute().set_chunk([], src))
+row("clone (contiguous copy) f64", 2 * NS * 8, lambda: src.clone())
+del src, dst
+
+# ------------------------------------------------------------------ config 3: reductions 1e9 f32
+R = (1000, 1000, 1000) if not args.quick else (250, 1000, 1000)
+NR = int(np.prod(R))
+x = dev_rand(R, np.float32, 7)
+for name in ["sum", "max", "argmax"]:
+    row(f"reduce full {name} f32 {R}", NR * 4, lambda name=name: getattr(x, name)(), reps=10)
+for axis in range(3):
+    for name in ["sum", "max", "argmax"]:
+        osz = NR // R[axis] * (8 if name == "argmax" else 4)
+        row(f"reduce axis={axis} {name} f32 {R}", NR * 4 + osz, lambda name=name, axis=axis: getattr(x, name)(axis=axis), reps=10)
+del x
+
+# ------------------------------------------------------------------ configs 4/5: heat
+H2 = (16384, 16384) if not args.quick else (4096, 4096)
+g = dev_rand(H2, np.float32, 8)
+cells = int(np.prod(H2))
+steps = 10
+row(f"heat 2-D {H2} f32 x{steps} steps", 8 * cells * steps, lambda: heat.simulate(g, 0.1, steps), cells * steps, "gcell_per_s", reps=5)
+del g
+H3 = (1024, 1024, 1024) if not args.quick else (256, 512, 512)
+g = dev_rand(H3, np.float32, 9)
+cells = int(np.prod(H3))
+row(f"heat 3-D {H3} f32 x{steps} steps", 8 * cells * steps, lambda: heat.simulate(g, 0.1, steps), cells * steps, "gcell_per_s", reps=5)
+del g
+if args.big_heat:
+    H3 = (2048, 2048, 2048)
+    g = D(H3, np.float32)
+    ph.check(lib.ph_fill_region(4, g.ptr, C.byref(g.desc()), np.array(1.0, np.float32).ctypes.data))
+    cells = int(np.prod(H3))
+    row(f"heat 3-D {H3} f32 x4 steps", 8 * cells * 4, lambda: heat.simulate(g, 0.1, 4), cells * 4, "gcell_per_s", reps=3)

@@ -1,0 +1,98 @@
+/* ph_host.h -- host-side index math of the device path: region literals -> canonical
+ * regions -> stride/offset descriptors, and view transforms folded onto descriptors.
+ *
+ * In the real drop-in this logic is Crystal (BASELINE.json north_star: "src/index_region.cr,
+ * src/coord_util.cr and src/shape_util.cr ... compile an IndexRegion into a compact
+ * stride/offset descriptor the kernels consume").  No Crystal compiler
+ * exists in this image, so the same rules are written here in C++ (the reference is
+ * compiled code) behind a C-ABI, mirroring the reference's names, argument meaning and
+ * error behaviour; INTEGRATION.md shows the Crystal methods they correspond to.
+ * Pure host code: no CUDA call, usable without a GPU.
+ */
+#ifndef PH_HOST_H
+#define PH_HOST_H
+
+#include <stdint.h>
+#include "ph_gpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* status codes: which exception class the reference raises */
+enum {
+  PH_HOST_OK = 0,
+  PH_HOST_INDEX_ERROR = 101,      /* IndexError      (range_syntax.cr:120-122,148-150; coord_util.cr:44-46) */
+  PH_HOST_DIMENSION_ERROR = 102,  /* DimensionError  (index_region.cr:199-201; coord_util.cr:77-79) */
+  PH_HOST_SHAPE_ERROR = 103,      /* ShapeError      (multi_indexable.cr:935-940; multi_writable.cr:58-60) */
+  PH_HOST_DIV0_ERROR = 104,       /* DivisionByZeroError (explicit step 0 with first == last) */
+  PH_HOST_NEEDS_COPY = 110,       /* reshape of a non-contiguous view: materialise first */
+  PH_HOST_INVALID = 111
+};
+
+/* One entry of a region literal after RangeSyntax.parse_range (range_syntax.cr:41-69):
+ * an Int (`is_index`), or first/step/last with nil-ness flags and exclusivity. */
+typedef struct ph_range_lit {
+  int32_t is_index;   /* literal was an Int: axis is dropped when `drop` */
+  int32_t has_first, has_last, has_step, exclusive;
+  int64_t first, last, step;   /* `first` holds the index when is_index */
+} ph_range_lit;
+
+/* IndexRegion(T) fields (index_region.cr:54-94) */
+typedef struct ph_region {
+  int32_t rank;                        /* proper dimensions */
+  int32_t drop;
+  int64_t first[PH_MAX_RANK], step[PH_MAX_RANK], last[PH_MAX_RANK], proper_shape[PH_MAX_RANK];
+  int32_t degeneracy[PH_MAX_RANK];
+  int32_t reduced_rank;
+  int64_t reduced_shape[PH_MAX_RANK];
+} ph_region;
+
+/* RangeSyntax.infer_range / canonicalize_range (range_syntax.cr:84-153) on one axis */
+int32_t ph_canonicalize_range(const ph_range_lit* lit, int64_t bound, int64_t* first, int64_t* step,
+                              int64_t* last, int64_t* size);
+/* CoordUtil.canonicalize_coord (coord_util.cr:76-82) */
+int32_t ph_canonicalize_coord(const int64_t* coord, int32_t ncoord, const int64_t* shape, int32_t rank,
+                              int64_t* out);
+/* IndexRegion.new(region_literal, bound_shape, drop) (index_region.cr:192-224) */
+int32_t ph_region_new(const ph_range_lit* lits, int32_t nlits, const int64_t* bound_shape, int32_t rank,
+                      int32_t drop, ph_region* out);
+/* IndexRegion.cover (index_region.cr:232-238) */
+int32_t ph_region_cover(const int64_t* bound_shape, int32_t rank, int32_t drop, ph_region* out);
+/* IndexRegion#fits_in? (:468-478): *fits = 0/1 */
+int32_t ph_region_fits_in(const ph_region* r, const int64_t* bound_shape, int32_t rank, int32_t* fits);
+/* IndexRegion#trim! (:502-515), #reverse! (:533-537), #translate! (:577-585) -- in place */
+int32_t ph_region_trim(ph_region* r, const int64_t* bound_shape, int32_t rank);
+int32_t ph_region_reverse(ph_region* r);
+int32_t ph_region_translate(ph_region* r, const int64_t* offset, int32_t noffset);
+
+/* ShapeUtil.compatible_shapes? (shape_util.cr:6-32): *ok = 0/1 */
+int32_t ph_shapes_compatible(const int64_t* a, int32_t na, const int64_t* b, int32_t nb, int32_t* ok);
+/* NEW ShapeUtil.broadcast_shapes: equal rank, each axis equal or 1 */
+int32_t ph_broadcast_shapes(const int64_t* a, const int64_t* b, int32_t rank, int64_t* out);
+
+/* Buffered.axis_strides (buffered.cr:15-24) as a descriptor of a whole row-major array */
+int32_t ph_desc_contiguous(const int64_t* shape, int32_t rank, ph_desc* out);
+/* NEW IndexRegion#to_descriptor: restrict the array / view `src` to `region`:
+ * offset += sum first*stride; kept axes get extent = proper_shape, stride = step*stride;
+ * all-dropped => rank-1 [size].  Replaces RegionTransform#apply (transforms.cr:215-221). */
+int32_t ph_desc_region(const ph_desc* src, const ph_region* region, ph_desc* out);
+/* PermuteTransform (transforms.cr:224-271): out axis i = src axis pattern[i];
+ * pattern == NULL => reversed axes (:236-238).  Bad axis -> IndexError (view.cr:73-75). */
+int32_t ph_desc_permute(const ph_desc* src, const int32_t* pattern, int32_t npattern, ph_desc* out);
+/* ReverseTransform (transforms.cr:273-305): every axis flipped */
+int32_t ph_desc_reverse(const ph_desc* src, ph_desc* out);
+/* ReshapeTransform (transforms.cr:118-189) when expressible as strides; element-count
+ * mismatch -> ShapeError (view.cr:59-61); not expressible -> PH_HOST_NEEDS_COPY */
+int32_t ph_desc_reshape(const ph_desc* src, const int64_t* new_shape, int32_t new_rank, ph_desc* out);
+/* stretch size-1 axes of `src` to `shape` with stride 0 (broadcast operand) */
+int32_t ph_desc_broadcast(const ph_desc* src, const int64_t* shape, int32_t rank, ph_desc* out);
+/* buffer offset of one coordinate (Buffered.coord_to_index_fast, buffered.cr:44-52) */
+int32_t ph_desc_offset_of(const ph_desc* d, const int64_t* coord, int32_t ncoord, int64_t* out);
+
+const char* ph_host_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PH_HOST_H */

@@ -4,9 +4,12 @@ include/ph_gpu.h); this Python package is the thin host mirror used by tests and
 There is no CPU fallback: importing works anywhere, computing needs the GPU library."""
 from . import _lib
 from ._lib import PhDesc, PhError, init, load, check, K
-from .narray import (DeviceNArray, ShapeError, DimensionError, CrIndexError, CrOverflowError,
+from .narray import (DeviceNArray, DeviceView, make_region, ShapeError, DimensionError, CrIndexError, CrOverflowError,
                      CrDivisionByZeroError, CrArgumentError, CrEmptyError, DeviceBlockError)
 
-__all__ = ["DeviceNArray", "PhDesc", "PhError", "init", "load", "check", "K", "ShapeError", "DimensionError",
+from .region import R, Step, rng, ALL
+from . import heat
+
+__all__ = ["DeviceNArray", "DeviceView", "make_region", "R", "Step", "rng", "ALL", "heat", "PhDesc", "PhError", "init", "load", "check", "K", "ShapeError", "DimensionError",
            "CrIndexError", "CrOverflowError", "CrDivisionByZeroError", "CrArgumentError", "CrEmptyError",
            "DeviceBlockError"]

@@ -40,9 +40,32 @@ class PhDesc(C.Structure):
         return cls.make(list(shape), list(reversed(strides)))
 
 
+class PhRangeLit(C.Structure):
+    """struct ph_range_lit (include/ph_host.h)"""
+    _fields_ = [("is_index", C.c_int32), ("has_first", C.c_int32), ("has_last", C.c_int32),
+                ("has_step", C.c_int32), ("exclusive", C.c_int32),
+                ("first", C.c_int64), ("last", C.c_int64), ("step", C.c_int64)]
+
+
+class PhRegion(C.Structure):
+    """struct ph_region (include/ph_host.h)"""
+    _fields_ = [("rank", C.c_int32), ("drop", C.c_int32),
+                ("first", C.c_int64 * PH_MAX_RANK), ("step", C.c_int64 * PH_MAX_RANK),
+                ("last", C.c_int64 * PH_MAX_RANK), ("proper_shape", C.c_int64 * PH_MAX_RANK),
+                ("degeneracy", C.c_int32 * PH_MAX_RANK), ("reduced_rank", C.c_int32),
+                ("reduced_shape", C.c_int64 * PH_MAX_RANK)]
+
+    @property
+    def shape(self):
+        return [int(self.reduced_shape[i]) for i in range(self.reduced_rank)]
+
+
+HOST_HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "ph_host.h")
+
+
 def header_constants() -> dict:
     """Parse the enum constants out of ph_gpu.h so Python never re-declares them."""
-    text = open(HEADER_PATH).read()
+    text = open(HEADER_PATH).read() + open(HOST_HEADER_PATH).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     consts = {}
     for body in re.findall(r"enum\s*\{(.*?)\}", text, flags=re.S):
@@ -62,8 +85,8 @@ def header_constants() -> dict:
 
 
 def header_functions() -> list:
-    """Names of every function ph_gpu.h declares."""
-    text = open(HEADER_PATH).read()
+    """Names of every function ph_gpu.h and ph_host.h declare."""
+    text = open(HEADER_PATH).read() + open(HOST_HEADER_PATH).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(ph_[a-z0-9_]+)\s*\(", text)))
 
@@ -86,7 +109,7 @@ def load() -> C.CDLL:
     if not os.path.exists(LIB_PATH):
         raise PhError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                       "(there is no CPU fallback)")
-    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(LIB_PATH)
     vp, i32, i64, u8p = C.c_void_p, C.c_int32, C.c_int64, C.c_void_p
     dp = C.POINTER(PhDesc)
     sig = {
@@ -117,6 +140,21 @@ def load() -> C.CDLL:
         "ph_halo_exchange": [vp, vp, i32, vp, vp, i32, i64, vp],
         "ph_heat_run_sharded": [i32, i32, C.POINTER(i64), vp, vp, vp, i64],
     }
+    i64p, i32p, rp, lp = C.POINTER(i64), C.POINTER(i32), C.POINTER(PhRegion), C.POINTER(PhRangeLit)
+    sig.update({
+        "ph_canonicalize_range": [lp, i64, i64p, i64p, i64p, i64p],
+        "ph_canonicalize_coord": [i64p, i32, i64p, i32, i64p],
+        "ph_region_new": [lp, i32, i64p, i32, i32, rp],
+        "ph_region_cover": [i64p, i32, i32, rp],
+        "ph_region_fits_in": [rp, i64p, i32, i32p],
+        "ph_region_trim": [rp, i64p, i32], "ph_region_reverse": [rp], "ph_region_translate": [rp, i64p, i32],
+        "ph_shapes_compatible": [i64p, i32, i64p, i32, i32p],
+        "ph_broadcast_shapes": [i64p, i64p, i32, i64p],
+        "ph_desc_contiguous": [i64p, i32, dp], "ph_desc_region": [dp, rp, dp],
+        "ph_desc_permute": [dp, i32p, i32, dp], "ph_desc_reverse": [dp, dp],
+        "ph_desc_reshape": [dp, i64p, i32, dp], "ph_desc_broadcast": [dp, i64p, i32, dp],
+        "ph_desc_offset_of": [dp, i64p, i32, i64p],
+    })
     for name, args in sig.items():
         if hasattr(lib, name):
             fn = getattr(lib, name)
@@ -128,6 +166,9 @@ def load() -> C.CDLL:
     if hasattr(lib, "ph_last_error_string"):
         lib.ph_last_error_string.restype = C.c_char_p
         lib.ph_last_error_string.argtypes = []
+    if hasattr(lib, "ph_host_last_error"):
+        lib.ph_host_last_error.restype = C.c_char_p
+        lib.ph_host_last_error.argtypes = []
     if hasattr(lib, "ph_launch_count"):
         lib.ph_launch_count.restype = i64
         lib.ph_launch_count.argtypes = []

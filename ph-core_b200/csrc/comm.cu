@@ -1,0 +1,256 @@
+// comm.cu -- multi-GPU plumbing: one process per GPU, NCCL over NVLink / NVSwitch.
+//
+// The reference has no distributed layer at all; this file adds only what
+// BASELINE.json's north_star partitions: reductions combine per-GPU partials with an
+// allreduce, and the heat grid is slab-decomposed along axis 0 with one-plane halos
+// exchanged by grouped ncclSend/ncclRecv on a side stream while the interior planes are
+// being updated on the main stream.
+#include "ph_common.cuh"
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is resolved at run time (see nccl_api)
+
+namespace ph {
+
+// NCCL is bound lazily with dlopen: a process that already loaded an NCCL (e.g. the one
+// bundled with PyTorch) keeps using that copy, and a process that never calls ph_comm_*
+// never loads NCCL at all.
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi& nccl() {
+  static NcclApi api;
+  return api;
+}
+static int32_t nccl_load() {
+  NcclApi& n = nccl();
+  if (n.handle) return PH_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);       // already in the process?
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+  if (!h) return set_error(PH_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+#define PH_SYM(field, name)                                                             \
+  *(void**)(&n.field) = dlsym(h, name);                                                 \
+  if (!n.field) return set_error(PH_ERR_NCCL, "libnccl is missing symbol %s", name);
+  PH_SYM(GetUniqueId, "ncclGetUniqueId") PH_SYM(CommInitRank, "ncclCommInitRank")
+  PH_SYM(CommDestroy, "ncclCommDestroy") PH_SYM(AllReduce, "ncclAllReduce")
+  PH_SYM(AllGather, "ncclAllGather") PH_SYM(Send, "ncclSend") PH_SYM(Recv, "ncclRecv")
+  PH_SYM(GroupStart, "ncclGroupStart") PH_SYM(GroupEnd, "ncclGroupEnd")
+  PH_SYM(GetErrorString, "ncclGetErrorString")
+#undef PH_SYM
+  n.handle = h;
+  return PH_OK;
+}
+#define PH_NCCL_LOAD()                      \
+  do {                                      \
+    int32_t _s = nccl_load();               \
+    if (_s != PH_OK) return _s;             \
+  } while (0)
+
+struct Comm {
+  ncclComm_t comm = nullptr;
+  int nranks = 1, rank = 0;
+  bool inited = false;
+};
+static Comm& cm() {
+  static Comm c;
+  return c;
+}
+
+static int32_t check_nccl(ncclResult_t r, const char* what) {
+  if (r == ncclSuccess) return PH_OK;
+  return set_error(PH_ERR_NCCL, "NCCL error %d (%s) at %s", (int)r, nccl().GetErrorString(r), what);
+}
+#define PH_NCCL(call)                                   \
+  do {                                                  \
+    int32_t _s = check_nccl((call), #call);             \
+    if (_s != PH_OK) return _s;                         \
+  } while (0)
+
+int32_t heat_slab_dispatch(int32_t dtype, int rank, const int64_t* ext, const void* coeff_host, int has_lo,
+                           int has_hi, int64_t p_begin, int64_t p_end, const void* in, void* out,
+                           cudaStream_t stream);
+
+static int32_t nccl_type(int32_t dtype, ncclDataType_t* t) {
+  switch (dtype) {
+    case PH_F32: *t = ncclFloat32; return PH_OK;
+    case PH_F64: *t = ncclFloat64; return PH_OK;
+    case PH_I32: *t = ncclInt32; return PH_OK;
+    case PH_I64: *t = ncclInt64; return PH_OK;
+    case PH_U8: *t = ncclUint8; return PH_OK;
+    case PH_I8: *t = ncclInt8; return PH_OK;
+    case PH_U32: *t = ncclUint32; return PH_OK;
+    case PH_U64: *t = ncclUint64; return PH_OK;
+    default: return set_error(PH_ERR_UNSUPPORTED, "dtype %d has no NCCL type", dtype);
+  }
+}
+
+static int32_t halo_exchange_impl(const void* send_lo, void* recv_lo, int lo_rank, const void* send_hi,
+                                  void* recv_hi, int hi_rank, int64_t nbytes, cudaStream_t s) {
+  Comm& c = cm();
+  if (lo_rank < 0 && hi_rank < 0) return PH_OK;
+  if (!c.inited) return set_error(PH_ERR_NOT_INIT, "ph_comm_init was not called");
+  PH_NCCL(nccl().GroupStart());
+  if (lo_rank >= 0) {
+    PH_NCCL(nccl().Send(send_lo, (size_t)nbytes, ncclUint8, lo_rank, c.comm, s));
+    PH_NCCL(nccl().Recv(recv_lo, (size_t)nbytes, ncclUint8, lo_rank, c.comm, s));
+  }
+  if (hi_rank >= 0) {
+    PH_NCCL(nccl().Send(send_hi, (size_t)nbytes, ncclUint8, hi_rank, c.comm, s));
+    PH_NCCL(nccl().Recv(recv_hi, (size_t)nbytes, ncclUint8, hi_rank, c.comm, s));
+  }
+  PH_NCCL(nccl().GroupEnd());
+  return PH_OK;
+}
+
+}  // namespace ph
+
+using namespace ph;
+
+extern "C" {
+
+int32_t ph_comm_unique_id(uint8_t* out128) {
+  if (!out128) return set_error(PH_ERR_INVALID, "null out128");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  PH_NCCL_LOAD();
+  ncclUniqueId id;
+  PH_NCCL(nccl().GetUniqueId(&id));
+  memcpy(out128, &id, 128);
+  return PH_OK;
+}
+
+int32_t ph_comm_init(int32_t nranks, int32_t rank, const uint8_t* id128) {
+  PH_REQUIRE_INIT();
+  Comm& c = cm();
+  if (c.inited) ph_comm_destroy();
+  if (nranks < 1 || rank < 0 || rank >= nranks) return set_error(PH_ERR_INVALID, "bad rank %d of %d", rank, nranks);
+  c.nranks = nranks; c.rank = rank;
+  if (nranks == 1) { c.inited = true; c.comm = nullptr; return PH_OK; }
+  if (!id128) return set_error(PH_ERR_INVALID, "null unique id");
+  PH_NCCL_LOAD();
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  PH_NCCL(nccl().CommInitRank(&c.comm, nranks, id, rank));
+  c.inited = true;
+  return PH_OK;
+}
+
+int32_t ph_comm_destroy(void) {
+  Comm& c = cm();
+  if (c.inited && c.comm) {
+    cudaDeviceSynchronize();
+    nccl().CommDestroy(c.comm);
+  }
+  c = Comm();
+  return PH_OK;
+}
+
+int32_t ph_allreduce(int32_t red, int32_t dtype, void* buf_dev, int64_t count) {
+  PH_REQUIRE_INIT();
+  Comm& c = cm();
+  if (!c.inited) return set_error(PH_ERR_NOT_INIT, "ph_comm_init was not called");
+  if (c.nranks == 1 || count == 0) return PH_OK;
+  ncclDataType_t t;
+  int32_t st = nccl_type(dtype, &t);
+  if (st != PH_OK) return st;
+  ncclRedOp_t op;
+  switch (red) {
+    case PH_SUM: op = ncclSum; break;
+    case PH_MIN: op = ncclMin; break;
+    case PH_MAX: op = ncclMax; break;
+    default: return set_error(PH_ERR_UNSUPPORTED, "allreduce supports SUM / MIN / MAX (arg* use ph_allgather)");
+  }
+  PH_NCCL(nccl().AllReduce(buf_dev, buf_dev, (size_t)count, t, op, c.comm, rt().stream));
+  return PH_OK;
+}
+
+int32_t ph_allgather(const void* send_dev, void* recv_dev, int64_t nbytes_per_rank) {
+  PH_REQUIRE_INIT();
+  Comm& c = cm();
+  if (!c.inited) return set_error(PH_ERR_NOT_INIT, "ph_comm_init was not called");
+  if (c.nranks == 1) {
+    if (send_dev != recv_dev)
+      PH_CUDA(cudaMemcpyAsync(recv_dev, send_dev, (size_t)nbytes_per_rank, cudaMemcpyDeviceToDevice, rt().stream));
+    return PH_OK;
+  }
+  PH_NCCL(nccl().AllGather(send_dev, recv_dev, (size_t)nbytes_per_rank, ncclUint8, c.comm, rt().stream));
+  return PH_OK;
+}
+
+int32_t ph_halo_exchange(const void* send_lo, void* recv_lo, int32_t lo_rank, const void* send_hi,
+                         void* recv_hi, int32_t hi_rank, int64_t nbytes, void* cuda_stream) {
+  PH_REQUIRE_INIT();
+  cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : rt().stream;
+  return halo_exchange_impl(send_lo, recv_lo, lo_rank, send_hi, recv_hi, hi_rank, nbytes, s);
+}
+
+// local_extents[0] = n0_local + 2 (ghost planes 0 and n0_local + 1).  Per step:
+//   main : update the two edge planes (1 and n0_local) first
+//   aux  : (after the edge planes) exchange them with the neighbours' ghost planes
+//   main : update the interior planes [2, n0_local) meanwhile
+//   main waits for aux before the next step reads the ghosts.
+int32_t ph_heat_run_sharded(int32_t dtype, int32_t rank, const int64_t* local_extents, const void* coeff_host,
+                            void* buf_a, void* buf_b, int64_t steps) {
+  PH_REQUIRE_INIT();
+  Runtime& r = rt();
+  Comm& c = cm();
+  if (!c.inited) return set_error(PH_ERR_NOT_INIT, "ph_comm_init was not called");
+  if (!local_extents || !coeff_host || !buf_a || !buf_b) return set_error(PH_ERR_INVALID, "null argument");
+  if (rank < 2 || rank > 3) return set_error(PH_ERR_UNSUPPORTED, "sharded stencil needs rank 2 or 3");
+  const int esz = dtype_size(dtype);
+  if (dtype != PH_F32 && dtype != PH_F64) return set_error(PH_ERR_UNSUPPORTED, "heat stencil is F32 / F64");
+  const int64_t n0 = local_extents[0];
+  if (n0 < 3) return set_error(PH_ERR_INVALID, "a slab needs at least one owned plane");
+  int64_t plane = 1;
+  for (int i = 1; i < rank; i++) plane *= local_extents[i];
+  const int64_t pbytes = plane * esz;
+  const int lo = c.rank > 0 ? c.rank - 1 : -1;
+  const int hi = c.rank < c.nranks - 1 ? c.rank + 1 : -1;
+  const int has_lo = lo >= 0, has_hi = hi >= 0;
+  char* bufs[2] = {reinterpret_cast<char*>(buf_a), reinterpret_cast<char*>(buf_b)};
+
+  // initial ghosts of buf_a, and the (constant) global-boundary planes of buf_b
+  int32_t st = halo_exchange_impl(bufs[0] + pbytes, bufs[0], lo, bufs[0] + (n0 - 2) * pbytes,
+                                  bufs[0] + (n0 - 1) * pbytes, hi, pbytes, r.stream);
+  if (st != PH_OK) return st;
+  if (!has_lo) PH_CUDA(cudaMemcpyAsync(bufs[1] + pbytes, bufs[0] + pbytes, pbytes, cudaMemcpyDeviceToDevice, r.stream));
+  if (!has_hi) PH_CUDA(cudaMemcpyAsync(bufs[1] + (n0 - 2) * pbytes, bufs[0] + (n0 - 2) * pbytes, pbytes,
+                                       cudaMemcpyDeviceToDevice, r.stream));
+
+  for (int64_t t = 0; t < steps; t++) {
+    const char* in = bufs[t & 1];
+    char* out = bufs[(t & 1) ^ 1];
+    // 1. edge planes (what the neighbours need)
+    st = heat_slab_dispatch(dtype, rank, local_extents, coeff_host, has_lo, has_hi, 1, 2, in, out, r.stream);
+    if (st != PH_OK) return st;
+    if (n0 - 2 > 1) {
+      st = heat_slab_dispatch(dtype, rank, local_extents, coeff_host, has_lo, has_hi, n0 - 2, n0 - 1, in, out, r.stream);
+      if (st != PH_OK) return st;
+    }
+    // 2. halo exchange on the side stream, overlapped with 3.
+    if (c.nranks > 1) {
+      PH_CUDA(cudaEventRecord(r.ev_a, r.stream));
+      PH_CUDA(cudaStreamWaitEvent(r.aux_stream, r.ev_a, 0));
+      st = halo_exchange_impl(out + pbytes, out, lo, out + (n0 - 2) * pbytes, out + (n0 - 1) * pbytes, hi, pbytes,
+                              r.aux_stream);
+      if (st != PH_OK) return st;
+      PH_CUDA(cudaEventRecord(r.ev_b, r.aux_stream));
+    }
+    // 3. interior planes
+    st = heat_slab_dispatch(dtype, rank, local_extents, coeff_host, has_lo, has_hi, 2, n0 - 2, in, out, r.stream);
+    if (st != PH_OK) return st;
+    if (c.nranks > 1) PH_CUDA(cudaStreamWaitEvent(r.stream, r.ev_b, 0));
+  }
+  return PH_OK;
+}
+
+}  // extern "C"

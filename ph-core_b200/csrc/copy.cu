@@ -1,0 +1,294 @@
+// copy.cu -- strided gather / scatter / fill / masked store (K4, K5, K6, K10).
+//
+// ph_copy_strided moves every element of a descriptor-described source region onto a
+// descriptor-described destination region.  It replaces the per-element loops of
+//   NArray#unsafe_fetch_chunk  src/n_array.cr:450-453     (gather, lex order)
+//   NArray#unsafe_set_chunk    src/n_array.cr:484-500     (scatter / fill)
+//   View#to_narr               src/view.cr:123-126        (transform chain -> copy)
+//   MutableView writes         src/mutable_view.cr:16-18
+// Element order is irrelevant on the device: both descriptors enumerate the same logical
+// coordinates, so element i of the region lands where the reference's lex iteration puts it.
+//
+// Kernel choice: contiguous -> 256-bit flat copy; inner axis contiguous on both sides ->
+// vectorised rows; inner stride != 1 (step slicing, reversal) -> scalar rows (coalesced at
+// sector granularity); unit-stride axis differs between source and destination (permuted
+// views, transposes) -> shared-memory tile transpose so both sides stay coalesced.
+#include "map_kernels.cuh"
+
+namespace ph {
+
+template <typename T>
+struct CopyOp {
+  using In = T;
+  using Out = T;
+  static constexpr int NIN = 1;
+  static __device__ __forceinline__ Out apply(const In (&x)[1], uint32_t&) { return x[0]; }
+};
+
+// ------------------------------------------------------------------ tile transpose
+constexpr int TT = 32;      // tile edge (elements)
+constexpr int TROWS = 8;    // block = TT x TROWS threads
+
+struct TransposeArgs {
+  const void* src;
+  void* dst;
+  int64_t extA, extB;                 // A: unit-stride axis of the source, B: of the destination
+  int64_t sA_src, sB_src, sA_dst, sB_dst;
+  int64_t tilesA, tilesB;
+  int n_outer;
+  int64_t outer_extent[PH_MAX_RANK];
+  int64_t outer_src[PH_MAX_RANK], outer_dst[PH_MAX_RANK];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(TT * TROWS) transpose_kernel(const TransposeArgs a) {
+  __shared__ T tile[TT][TT + 1];
+  int64_t bid = blockIdx.x;
+  const int64_t ta = bid % a.tilesA; bid /= a.tilesA;
+  const int64_t tb = bid % a.tilesB; bid /= a.tilesB;
+  int64_t off_src = 0, off_dst = 0;
+  for (int ax = a.n_outer - 1; ax >= 0; ax--) {
+    const int64_t c = bid % a.outer_extent[ax];
+    bid /= a.outer_extent[ax];
+    off_src += c * a.outer_src[ax];
+    off_dst += c * a.outer_dst[ax];
+  }
+  const T* __restrict__ src = reinterpret_cast<const T*>(a.src) + off_src;
+  T* __restrict__ dst = reinterpret_cast<T*>(a.dst) + off_dst;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  {
+    const int64_t ia = ta * TT + tx;               // threads run along A: coalesced source reads
+#pragma unroll
+    for (int j = 0; j < TT; j += TROWS) {
+      const int64_t ib = tb * TT + ty + j;
+      if (ia < a.extA && ib < a.extB) tile[ty + j][tx] = src[ia * a.sA_src + ib * a.sB_src];
+    }
+  }
+  __syncthreads();
+  {
+    const int64_t ib = tb * TT + tx;               // threads run along B: coalesced destination writes
+#pragma unroll
+    for (int j = 0; j < TT; j += TROWS) {
+      const int64_t ia = ta * TT + ty + j;
+      if (ia < a.extA && ib < a.extB) dst[ia * a.sA_dst + ib * a.sB_dst] = tile[tx][ty + j];
+    }
+  }
+}
+
+template <typename T>
+static int32_t try_transpose(const Plan& p, const void* src, void* dst, bool& done) {
+  done = false;
+  if (p.rank < 2) return PH_OK;
+  int A = -1, B = -1;
+  for (int ax = 0; ax < p.rank; ax++) {
+    if (A < 0 && (p.stride[0][ax] == 1 || p.stride[0][ax] == -1)) A = ax;
+    if (B < 0 && (p.stride[1][ax] == 1 || p.stride[1][ax] == -1)) B = ax;
+  }
+  if (A < 0 || B < 0 || A == B) return PH_OK;
+  if (p.extent[A] < 8 || p.extent[B] < 8) return PH_OK;      // too thin to tile: rows kernel
+  TransposeArgs a;
+  memset(&a, 0, sizeof(a));
+  a.src = reinterpret_cast<const T*>(src) + p.offset[0];
+  a.dst = reinterpret_cast<T*>(dst) + p.offset[1];
+  a.extA = p.extent[A]; a.extB = p.extent[B];
+  a.sA_src = p.stride[0][A]; a.sB_src = p.stride[0][B];
+  a.sA_dst = p.stride[1][A]; a.sB_dst = p.stride[1][B];
+  a.tilesA = ceil_div(a.extA, TT); a.tilesB = ceil_div(a.extB, TT);
+  int64_t blocks = a.tilesA * a.tilesB;
+  for (int ax = 0; ax < p.rank; ax++) {
+    if (ax == A || ax == B) continue;
+    a.outer_extent[a.n_outer] = p.extent[ax];
+    a.outer_src[a.n_outer] = p.stride[0][ax];
+    a.outer_dst[a.n_outer] = p.stride[1][ax];
+    a.n_outer++;
+    blocks *= p.extent[ax];
+  }
+  if (blocks > 0x7fffffffLL) return PH_OK;
+  dim3 block(TT, TROWS);
+  transpose_kernel<T><<<(unsigned)blocks, block, 0, rt().stream>>>(a);
+  PH_LAUNCH_CHECK("transpose_kernel");
+  done = true;
+  return PH_OK;
+}
+
+template <typename T>
+static int32_t copy_strided_t(const void* src, const ph_desc* sd, void* dst, const ph_desc* dd) {
+  const ph_desc* descs[2] = {sd, dd};
+  Plan p;
+  int32_t st = make_plan(p, 2, descs);
+  if (st != PH_OK) return st;
+  if (p.total == 0) return PH_OK;
+  bool done = false;
+  st = try_transpose<T>(p, src, dst, done);
+  if (st != PH_OK || done) return st;
+  MapOperand ops[1];
+  ops[0].base = src; ops[0].desc = sd;
+  return launch_map<CopyOp<T>>(ops, dst, dd);
+}
+
+template <typename T>
+static int32_t fill_t(void* dst, const ph_desc* dd, uint64_t bits) {
+  MapOperand ops[1];
+  ops[0].is_param = true; ops[0].param = bits;
+  return launch_map<CopyOp<T>>(ops, dst, dd);
+}
+
+// ------------------------------------------------------------------ masked store
+// dst[i] = mask[i] ? value : dst[i]   (NArray#[]=(mask, value), src/n_array.cr:510-551)
+template <typename T, int E>
+__global__ void __launch_bounds__(MAP_THREADS) mask_set_flat_kernel(T* __restrict__ dst,
+                                                                    const uint8_t* __restrict__ mask,
+                                                                    const T* __restrict__ src, uint64_t param,
+                                                                    int has_src, int64_t n) {
+  const int64_t tile = (int64_t)MAP_THREADS * E;
+  const int64_t base = (int64_t)blockIdx.x * tile;
+  const T scalar = bits_to<T>(param);
+  if (base + tile <= n) {
+    const int64_t idx = base + (int64_t)threadIdx.x * E;
+    Group<uint8_t, E> m = load_group<uint8_t, E>(mask + idx);
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < E; i++) any |= (m.v[i] != 0);
+    if (!any) return;                               // untouched groups cost only their mask bytes
+    Group<T, E> d = load_group<T, E>(dst + idx);
+    if (has_src) {
+      Group<T, E> s = load_group<T, E>(src + idx);
+#pragma unroll
+      for (int i = 0; i < E; i++) if (m.v[i]) d.v[i] = s.v[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < E; i++) if (m.v[i]) d.v[i] = scalar;
+    }
+    store_group<T, E>(dst + idx, d);
+  } else {
+    for (int64_t i = base + threadIdx.x; i < n; i += MAP_THREADS)
+      if (mask[i]) dst[i] = has_src ? src[i] : scalar;
+  }
+}
+
+struct MaskAnyArgs {
+  int rank;
+  int64_t extent[PH_MAX_RANK];
+  int64_t s_dst[PH_MAX_RANK], s_mask[PH_MAX_RANK], s_src[PH_MAX_RANK];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(MAP_THREADS) mask_set_any_kernel(T* dst, const uint8_t* mask, const T* src,
+                                                                   uint64_t param, int has_src,
+                                                                   const MaskAnyArgs a, int64_t total) {
+  const T scalar = bits_to<T>(param);
+  const int64_t stride = (int64_t)gridDim.x * MAP_THREADS;
+  for (int64_t i = (int64_t)blockIdx.x * MAP_THREADS + threadIdx.x; i < total; i += stride) {
+    int64_t r = i, od = 0, om = 0, os = 0;
+    for (int ax = a.rank - 1; ax >= 0; ax--) {
+      const int64_t q = r / a.extent[ax];
+      const int64_t c = r - q * a.extent[ax];
+      r = q;
+      od += c * a.s_dst[ax]; om += c * a.s_mask[ax]; os += c * a.s_src[ax];
+    }
+    if (mask[om]) dst[od] = has_src ? src[os] : scalar;
+  }
+}
+
+template <typename T>
+static int32_t mask_set_t(void* dst, const ph_desc* dd, const uint8_t* mask, const ph_desc* md, const void* src,
+                          const ph_desc* sd, uint64_t param) {
+  const int nops = src ? 3 : 2;
+  const ph_desc* descs[3] = {dd, md, sd};
+  Plan p;
+  int32_t st = make_plan(p, nops, descs);
+  if (st != PH_OK) return st;
+  if (p.total == 0) return PH_OK;
+  T* d = reinterpret_cast<T*>(dst) + p.offset[0];
+  const uint8_t* m = mask + p.offset[1];
+  const T* s = src ? reinterpret_cast<const T*>(src) + p.offset[2] : nullptr;
+  bool flat = p.rank <= 1;
+  if (flat && p.rank == 1)
+    for (int k = 0; k < nops; k++) if (p.stride[k][0] != 1) flat = false;
+  if (flat) {
+    constexpr int E = 32 / (int)sizeof(T) > 16 ? 16 : 32 / (int)sizeof(T);   // mask group <= 16 bytes
+    const bool aligned = ((uintptr_t)d % (E * sizeof(T)) == 0) && ((uintptr_t)m % E == 0) &&
+                         (!s || (uintptr_t)s % (E * sizeof(T)) == 0);
+    if (aligned) {
+      const int64_t blocks = ceil_div(p.total, (int64_t)MAP_THREADS * E);
+      mask_set_flat_kernel<T, E><<<(unsigned)blocks, MAP_THREADS, 0, rt().stream>>>(d, m, s, param, s != nullptr, p.total);
+    } else {
+      const int64_t blocks = ceil_div(p.total, (int64_t)MAP_THREADS);
+      mask_set_flat_kernel<T, 1><<<(unsigned)blocks, MAP_THREADS, 0, rt().stream>>>(d, m, s, param, s != nullptr, p.total);
+    }
+    PH_LAUNCH_CHECK("mask_set_flat_kernel");
+    return PH_OK;
+  }
+  MaskAnyArgs a;
+  memset(&a, 0, sizeof(a));
+  a.rank = p.rank;
+  for (int ax = 0; ax < p.rank; ax++) {
+    a.extent[ax] = p.extent[ax];
+    a.s_dst[ax] = p.stride[0][ax]; a.s_mask[ax] = p.stride[1][ax];
+    a.s_src[ax] = src ? p.stride[2][ax] : 0;
+  }
+  const int64_t blocks = std::min<int64_t>(ceil_div(p.total, MAP_THREADS), (int64_t)rt().sm_count * 32);
+  mask_set_any_kernel<T><<<(unsigned)blocks, MAP_THREADS, 0, rt().stream>>>(d, m, s, param, s != nullptr, a, p.total);
+  PH_LAUNCH_CHECK("mask_set_any_kernel");
+  return PH_OK;
+}
+
+}  // namespace ph
+
+using namespace ph;
+
+#define PH_SIZE_SWITCH(elem_size, CALL)                                                       \
+  switch (elem_size) {                                                                        \
+    case 1: return CALL(uint8_t);                                                             \
+    case 2: return CALL(uint16_t);                                                            \
+    case 4: return CALL(uint32_t);                                                            \
+    case 8: return CALL(uint64_t);                                                            \
+    default: return set_error(PH_ERR_UNSUPPORTED, "element size %d is not 1, 2, 4 or 8", elem_size); \
+  }
+
+extern "C" {
+
+int32_t ph_copy_strided(int32_t elem_size, const void* src, const ph_desc* src_desc, void* dst,
+                        const ph_desc* dst_desc) {
+  PH_REQUIRE_INIT();
+  if (!src || !dst || !src_desc || !dst_desc) return set_error(PH_ERR_INVALID, "null argument to ph_copy_strided");
+#define CALL(T) copy_strided_t<T>(src, src_desc, dst, dst_desc)
+  PH_SIZE_SWITCH(elem_size, CALL)
+#undef CALL
+}
+
+int32_t ph_fill_region(int32_t elem_size, void* dst, const ph_desc* dst_desc, const void* scalar_host) {
+  PH_REQUIRE_INIT();
+  if (!dst || !dst_desc || !scalar_host) return set_error(PH_ERR_INVALID, "null argument to ph_fill_region");
+  if (elem_size != 1 && elem_size != 2 && elem_size != 4 && elem_size != 8)
+    return set_error(PH_ERR_UNSUPPORTED, "element size %d is not 1, 2, 4 or 8", elem_size);
+  const uint64_t bits = host_scalar_bits(scalar_host, elem_size);
+#define CALL(T) fill_t<T>(dst, dst_desc, bits)
+  PH_SIZE_SWITCH(elem_size, CALL)
+#undef CALL
+}
+
+int32_t ph_mask_set_scalar(int32_t elem_size, void* dst, const ph_desc* dst_desc, const uint8_t* mask,
+                           const ph_desc* mask_desc, const void* scalar_host) {
+  PH_REQUIRE_INIT();
+  if (!dst || !dst_desc || !mask || !mask_desc || !scalar_host)
+    return set_error(PH_ERR_INVALID, "null argument to ph_mask_set_scalar");
+  if (elem_size != 1 && elem_size != 2 && elem_size != 4 && elem_size != 8)
+    return set_error(PH_ERR_UNSUPPORTED, "element size %d is not 1, 2, 4 or 8", elem_size);
+  const uint64_t bits = host_scalar_bits(scalar_host, elem_size);
+#define CALL(T) mask_set_t<T>(dst, dst_desc, mask, mask_desc, nullptr, nullptr, bits)
+  PH_SIZE_SWITCH(elem_size, CALL)
+#undef CALL
+}
+
+int32_t ph_mask_set_array(int32_t elem_size, void* dst, const ph_desc* dst_desc, const uint8_t* mask,
+                          const ph_desc* mask_desc, const void* src, const ph_desc* src_desc) {
+  PH_REQUIRE_INIT();
+  if (!dst || !dst_desc || !mask || !mask_desc || !src || !src_desc)
+    return set_error(PH_ERR_INVALID, "null argument to ph_mask_set_array");
+#define CALL(T) mask_set_t<T>(dst, dst_desc, mask, mask_desc, src, src_desc, 0)
+  PH_SIZE_SWITCH(elem_size, CALL)
+#undef CALL
+}
+
+}  // extern "C"

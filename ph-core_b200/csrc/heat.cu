@@ -1,0 +1,349 @@
+// heat.cu -- explicit heat-diffusion stencil (K9 of SURVEY.md 2.3).
+//
+// Reference: examples/heat_equation.cr:38-51 (update_temp) and :26-36 (simulate).
+//   PH_HEAT_EXAMPLE1D  the example verbatim: one-sided (zero-flux) ends,
+//        d[0] = (s[1]-s[0])*C; d[n-1] = (s[n-2]-s[n-1])*C;
+//        d[i] = ((s[i-1] - 2*s[i]) + s[i+1])*C;  s' = s + d
+//   PH_HEAT_FIXED      the N-D rule SURVEY.md 8(a) a-9 defines in reference operators:
+//        c = s[interior]; d_k = (s[lo_k] - 2*c) + s[hi_k]; lap = (d_0 + d_1) + d_2;
+//        s'[interior] = c + lap*C; boundary cells are held.
+// Every operator is one rounding in T (the __f*_rn intrinsics cannot be contracted), in
+// exactly the association order above, so ONE step is bit-identical to the reference's
+// operator-by-operator evaluation with materialised temporaries.
+//
+// Kernel: 2.5-D streaming.  A block owns a (rows x columns) tile and marches along axis 0;
+// each thread keeps its cells of planes z-1, z, z+1 in registers, so every cell is read from
+// HBM once (8 B per cell-update for f32: one read + one write).  In-plane neighbours come
+// from warp shuffles (x) and a double-buffered shared-memory row exchange (y); only the tile
+// halo is re-read (L2 hits).  Slabs for multi-GPU runs are split along axis 0, so halo
+// planes are contiguous and need no packing.
+#include "ph_common.cuh"
+#include "ops.cuh"
+#include <algorithm>
+
+namespace ph {
+
+constexpr int HEAT_TY = 8;            // warps per block (rows of the tile for rank 3)
+
+template <typename T>
+struct HeatArgs {
+  const T* in;
+  T* out;
+  int64_t n0, n1, n2;                 // extents: axis 0 (march), axis 1 (rows; 1 for rank 2), axis 2 (x)
+  int64_t z_begin, z_end;             // planes to update (interior only: 1 <= z < n0-1)
+  int64_t z_chunk;                    // planes per block along the march axis
+  T coeff;
+};
+
+template <typename T>
+__device__ __forceinline__ T heat_cell(T c, T zl, T zh, T yl, T yh, T xl, T xh, T coeff, int rank) {
+  const T two_c = f_mul((T)2, c);
+  const T d0 = f_add(f_sub(zl, two_c), zh);
+  T lap = d0;
+  if (rank == 3) {
+    const T d1 = f_add(f_sub(yl, two_c), yh);
+    const T d2 = f_add(f_sub(xl, two_c), xh);
+    lap = f_add(f_add(d0, d1), d2);
+  } else if (rank == 2) {
+    const T d1 = f_add(f_sub(xl, two_c), xh);
+    lap = f_add(d0, d1);
+  }
+  return f_add(c, f_mul(lap, coeff));
+}
+
+// RANK 3: block = 32 lanes (x, E cells each) x HEAT_TY warps (consecutive y rows).
+// RANK 2: block = 32 lanes x HEAT_TY warps, every warp owns its own x tile (no y axis).
+template <typename T, int E, int RANK>
+__global__ void __launch_bounds__(32 * HEAT_TY) heat_march_kernel(const HeatArgs<T> a) {
+  __shared__ Group<T, E> rows[2][HEAT_TY][32];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  int64_t x0, y;
+  if (RANK == 3) {
+    x0 = ((int64_t)blockIdx.x * 32 + lane) * E;
+    y = (int64_t)blockIdx.y * HEAT_TY + warp;
+  } else {
+    x0 = (((int64_t)blockIdx.x * HEAT_TY + warp) * 32 + lane) * E;
+    y = 0;
+  }
+  const int64_t zb = a.z_begin + (int64_t)blockIdx.z * a.z_chunk;
+  const int64_t ze = (zb + a.z_chunk < a.z_end) ? zb + a.z_chunk : a.z_end;
+  if (zb >= ze) return;
+  const bool active = x0 < a.n2 && y < a.n1;       // n2 % E == 0 by dispatch: whole groups
+  const int64_t plane = a.n1 * a.n2;
+  const int64_t row_off = y * a.n2 + x0;
+  const bool y_edge = (RANK == 3) && (y == 0 || y == a.n1 - 1);
+  // in-plane halo sources (clamped so the address is always valid; unused on boundaries)
+  const int64_t y_up = (y > 0 ? y - 1 : y) * a.n2 + x0;
+  const int64_t y_dn = (y + 1 < a.n1 ? y + 1 : y) * a.n2 + x0;
+  const bool need_up_global = (RANK == 3) && (warp == 0);
+  const bool need_dn_global = (RANK == 3) && (warp == HEAT_TY - 1 || y + 1 >= a.n1);
+
+  Group<T, E> prev, cur, next;
+  if (active) {
+    prev = load_group_plain<T, E>(a.in + (zb - 1) * plane + row_off);
+    cur = load_group_plain<T, E>(a.in + zb * plane + row_off);
+  } else {
+    prev = splat_group<T, E>((T)0);
+    cur = prev;
+  }
+  int buf = 0;
+  for (int64_t z = zb; z < ze; z++) {
+    const T* pz = a.in + z * plane;
+    next = active ? load_group_plain<T, E>(pz + plane + row_off) : splat_group<T, E>((T)0);
+    Group<T, E> up = cur, dn = cur;
+    T xl = (T)0, xr = (T)0;
+    if (active) {
+      if (need_up_global) up = load_group_plain<T, E>(pz + y_up);
+      if (need_dn_global) dn = load_group_plain<T, E>(pz + y_dn);
+      if (lane == 0 && x0 > 0) xl = pz[y * a.n2 + x0 - 1];
+      if (lane == 31 && x0 + E < a.n2) xr = pz[y * a.n2 + x0 + E];
+    }
+    if (RANK == 3) {
+      rows[buf][warp][lane] = cur;
+      __syncthreads();
+      if (!need_up_global) up = rows[buf][warp - 1][lane];
+      if (!need_dn_global) dn = rows[buf][warp + 1][lane];
+    }
+    const T from_left = __shfl_up_sync(0xffffffffu, cur.v[E - 1], 1);
+    const T from_right = __shfl_down_sync(0xffffffffu, cur.v[0], 1);
+    if (lane != 0) xl = from_left;
+    if (lane != 31) xr = from_right;
+    if (active) {
+      Group<T, E> res;
+#pragma unroll
+      for (int i = 0; i < E; i++) {
+        const T c = cur.v[i];
+        const T l = (i > 0) ? cur.v[i - 1] : xl;
+        const T r = (i < E - 1) ? cur.v[i + 1] : xr;
+        const int64_t x = x0 + i;
+        const bool fixed = y_edge || x == 0 || x == a.n2 - 1;
+        const T v = heat_cell<T>(c, prev.v[i], next.v[i], up.v[i], dn.v[i], l, r, a.coeff, RANK);
+        res.v[i] = fixed ? c : v;
+      }
+      store_group<T, E>(a.out + z * plane + row_off, res);
+    }
+    prev = cur;
+    cur = next;
+    buf ^= 1;
+  }
+}
+
+// rank 1, either boundary mode: one cell per thread
+template <typename T>
+__global__ void heat_1d_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t n, T coeff, int mode,
+                               int64_t begin, int64_t end) {
+  const int64_t i = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= end) return;
+  const T c = in[i];
+  if (mode == PH_HEAT_EXAMPLE1D) {
+    T d;
+    if (i == 0) d = f_mul(f_sub(in[1], c), coeff);
+    else if (i == n - 1) d = f_mul(f_sub(in[n - 2], c), coeff);
+    else d = f_mul(f_add(f_sub(in[i - 1], f_mul((T)2, c)), in[i + 1]), coeff);
+    out[i] = f_add(c, d);
+  } else {
+    if (i == 0 || i == n - 1) out[i] = c;
+    else out[i] = f_add(c, f_mul(f_add(f_sub(in[i - 1], f_mul((T)2, c)), in[i + 1]), coeff));
+  }
+}
+
+// rank 1, n <= 1024: the whole rod lives in shared memory for ALL steps (one launch instead
+// of one per step: the reference example is 21 points x 10 001 steps).
+template <typename T>
+__global__ void __launch_bounds__(1024) heat_1d_resident_kernel(T* __restrict__ a_buf, T* __restrict__ b_buf,
+                                                                 int n, T coeff, int mode, int64_t steps) {
+  __shared__ T s[2][1024];
+  const int i = threadIdx.x;
+  if (i < n) s[0][i] = a_buf[i];
+  __syncthreads();
+  int cur = 0;
+  for (int64_t t = 0; t < steps; t++) {
+    if (i < n) {
+      const T c = s[cur][i];
+      T r;
+      if (mode == PH_HEAT_EXAMPLE1D) {
+        T d;
+        if (i == 0) d = f_mul(f_sub(s[cur][1], c), coeff);
+        else if (i == n - 1) d = f_mul(f_sub(s[cur][n - 2], c), coeff);
+        else d = f_mul(f_add(f_sub(s[cur][i - 1], f_mul((T)2, c)), s[cur][i + 1]), coeff);
+        r = f_add(c, d);
+      } else {
+        if (i == 0 || i == n - 1) r = c;
+        else r = f_add(c, f_mul(f_add(f_sub(s[cur][i - 1], f_mul((T)2, c)), s[cur][i + 1]), coeff));
+      }
+      s[cur ^ 1][i] = r;
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+  T* dst = (steps & 1) ? b_buf : a_buf;            // same convention as the ping-pong path
+  if (i < n) dst[i] = s[cur][i];
+}
+
+// ------------------------------------------------------------------ host side
+template <typename T, int RANK>
+static int32_t launch_march(const T* in, T* out, int64_t n0, int64_t n1, int64_t n2, T coeff, int64_t z_begin,
+                            int64_t z_end, cudaStream_t stream) {
+  if (z_begin >= z_end) return PH_OK;
+  HeatArgs<T> a;
+  a.in = in; a.out = out; a.n0 = n0; a.n1 = n1; a.n2 = n2; a.coeff = coeff;
+  a.z_begin = z_begin; a.z_end = z_end;
+  constexpr int EV = 16 / (int)sizeof(T);
+  const bool vec = (n2 % EV == 0) && ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0);
+  const int e = vec ? EV : 1;
+  int64_t gx, gy;
+  if (RANK == 3) { gx = ceil_div(n2, (int64_t)32 * e); gy = ceil_div(n1, HEAT_TY); }
+  else { gx = ceil_div(n2, (int64_t)32 * e * HEAT_TY); gy = 1; }
+  // enough blocks for a few waves, but long marches so the 2-plane prologue stays negligible
+  const int64_t planes = z_end - z_begin;
+  const int64_t want = (int64_t)rt().sm_count * 8 * 4;
+  int64_t gz = std::max<int64_t>(1, std::min<int64_t>(ceil_div(want, gx * gy), ceil_div(planes, 32)));
+  a.z_chunk = ceil_div(planes, gz);
+  gz = ceil_div(planes, a.z_chunk);
+  if (gy > 65535 || gz > 65535) return set_error(PH_ERR_INVALID, "heat grid too large for one launch");
+  dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)gz), block(32 * HEAT_TY);
+  if (vec) heat_march_kernel<T, EV, RANK><<<grid, block, 0, stream>>>(a);
+  else heat_march_kernel<T, 1, RANK><<<grid, block, 0, stream>>>(a);
+  PH_LAUNCH_CHECK("heat_march_kernel");
+  return PH_OK;
+}
+
+// one step on planes [z_begin, z_end) of a rank-2/3 grid; boundary planes are NOT touched
+template <typename T>
+static int32_t heat_planes(int rank, const int64_t* ext, T coeff, const T* in, T* out, int64_t z_begin,
+                           int64_t z_end, cudaStream_t stream) {
+  if (rank == 3) return launch_march<T, 3>(in, out, ext[0], ext[1], ext[2], coeff, z_begin, z_end, stream);
+  return launch_march<T, 2>(in, out, ext[0], 1, ext[1], coeff, z_begin, z_end, stream);
+}
+
+template <typename T>
+static int32_t heat_step_t(int rank, const int64_t* ext, const void* coeff_host, int mode, const void* in_v,
+                           void* out_v) {
+  Runtime& r = rt();
+  T coeff;
+  memcpy(&coeff, coeff_host, sizeof(T));
+  const T* in = reinterpret_cast<const T*>(in_v);
+  T* out = reinterpret_cast<T*>(out_v);
+  int64_t total = 1;
+  for (int i = 0; i < rank; i++) total *= ext[i];
+  if (total == 0) return PH_OK;
+  if (rank == 1) {
+    const int64_t n = ext[0];
+    if (n < 3 && mode == PH_HEAT_FIXED) { PH_CUDA(cudaMemcpyAsync(out, in, n * sizeof(T), cudaMemcpyDeviceToDevice, r.stream)); return PH_OK; }
+    if (n < 2) { PH_CUDA(cudaMemcpyAsync(out, in, n * sizeof(T), cudaMemcpyDeviceToDevice, r.stream)); return PH_OK; }
+    heat_1d_kernel<T><<<(unsigned)ceil_div(n, 256), 256, 0, r.stream>>>(in, out, n, coeff, mode, 0, n);
+    PH_LAUNCH_CHECK("heat_1d_kernel");
+    return PH_OK;
+  }
+  if (mode != PH_HEAT_FIXED) return set_error(PH_ERR_UNSUPPORTED, "PH_HEAT_EXAMPLE1D is rank-1 only");
+  bool thin = false;
+  for (int i = 0; i < rank; i++) if (ext[i] < 3) thin = true;
+  const int64_t plane = total / ext[0];
+  if (thin) { PH_CUDA(cudaMemcpyAsync(out, in, total * sizeof(T), cudaMemcpyDeviceToDevice, r.stream)); return PH_OK; }
+  // nxt = s.clone on the two boundary planes, stencil on the interior planes
+  PH_CUDA(cudaMemcpyAsync(out, in, plane * sizeof(T), cudaMemcpyDeviceToDevice, r.stream));
+  PH_CUDA(cudaMemcpyAsync(out + (ext[0] - 1) * plane, in + (ext[0] - 1) * plane, plane * sizeof(T),
+                          cudaMemcpyDeviceToDevice, r.stream));
+  return heat_planes<T>(rank, ext, coeff, in, out, 1, ext[0] - 1, r.stream);
+}
+
+template <typename T>
+static int32_t heat_run_t(int rank, const int64_t* ext, const void* coeff_host, int mode, void* a_v, void* b_v,
+                          int64_t steps) {
+  Runtime& r = rt();
+  T coeff;
+  memcpy(&coeff, coeff_host, sizeof(T));
+  T* bufs[2] = {reinterpret_cast<T*>(a_v), reinterpret_cast<T*>(b_v)};
+  if (steps <= 0) return PH_OK;
+  if (rank == 1 && ext[0] <= 1024 && ext[0] >= 3) {
+    heat_1d_resident_kernel<T><<<1, 1024, 0, r.stream>>>(bufs[0], bufs[1], (int)ext[0], coeff, mode, steps);
+    PH_LAUNCH_CHECK("heat_1d_resident_kernel");
+    return PH_OK;
+  }
+  if (rank >= 2 && mode == PH_HEAT_FIXED) {
+    bool thin = false;
+    int64_t total = 1;
+    for (int i = 0; i < rank; i++) { total *= ext[i]; if (ext[i] < 3) thin = true; }
+    if (total == 0) return PH_OK;
+    if (!thin) {
+      // the boundary planes never change: copy them into the second buffer once, then
+      // every step is a single stencil launch over the interior planes
+      const int64_t plane = total / ext[0];
+      PH_CUDA(cudaMemcpyAsync(bufs[1], bufs[0], plane * sizeof(T), cudaMemcpyDeviceToDevice, r.stream));
+      PH_CUDA(cudaMemcpyAsync(bufs[1] + (ext[0] - 1) * plane, bufs[0] + (ext[0] - 1) * plane, plane * sizeof(T),
+                              cudaMemcpyDeviceToDevice, r.stream));
+      for (int64_t t = 0; t < steps; t++) {
+        int32_t st = heat_planes<T>(rank, ext, coeff, bufs[t & 1], bufs[(t & 1) ^ 1], 1, ext[0] - 1, r.stream);
+        if (st != PH_OK) return st;
+      }
+      return PH_OK;
+    }
+  }
+  for (int64_t t = 0; t < steps; t++) {
+    int32_t st = heat_step_t<T>(rank, ext, coeff_host, mode, bufs[t & 1], bufs[(t & 1) ^ 1]);
+    if (st != PH_OK) return st;
+  }
+  return PH_OK;
+}
+
+template <typename T>
+static int32_t heat_slab_t(int rank, const int64_t* ext, const void* coeff_host, int has_lo, int has_hi,
+                           int64_t p_begin, int64_t p_end, const void* in_v, void* out_v, cudaStream_t stream) {
+  T coeff;
+  memcpy(&coeff, coeff_host, sizeof(T));
+  // planes 0 and ext[0]-1 are ghosts; without a neighbour the adjacent plane is a fixed global boundary
+  const int64_t lo = has_lo ? 1 : 2;
+  const int64_t hi = has_hi ? ext[0] - 1 : ext[0] - 2;
+  const int64_t b = std::max<int64_t>(p_begin, lo), e = std::min<int64_t>(p_end, hi);
+  for (int i = 1; i < rank; i++) if (ext[i] < 3) return PH_OK;
+  return heat_planes<T>(rank, ext, coeff, reinterpret_cast<const T*>(in_v), reinterpret_cast<T*>(out_v), b, e, stream);
+}
+
+// exported to comm.cu
+int32_t heat_slab_dispatch(int32_t dtype, int rank, const int64_t* ext, const void* coeff_host, int has_lo,
+                           int has_hi, int64_t p_begin, int64_t p_end, const void* in, void* out,
+                           cudaStream_t stream) {
+  if (rank < 2 || rank > 3) return set_error(PH_ERR_UNSUPPORTED, "slab stencil needs rank 2 or 3 (got %d)", rank);
+  if (dtype == PH_F32) return heat_slab_t<float>(rank, ext, coeff_host, has_lo, has_hi, p_begin, p_end, in, out, stream);
+  if (dtype == PH_F64) return heat_slab_t<double>(rank, ext, coeff_host, has_lo, has_hi, p_begin, p_end, in, out, stream);
+  return set_error(PH_ERR_UNSUPPORTED, "the heat stencil is defined for F32 / F64");
+}
+
+}  // namespace ph
+
+using namespace ph;
+
+extern "C" {
+
+int32_t ph_heat_step(int32_t dtype, int32_t rank, const int64_t* extents, const void* coeff_host,
+                     int32_t boundary_mode, const void* in, void* out) {
+  PH_REQUIRE_INIT();
+  if (!extents || !coeff_host || !in || !out) return set_error(PH_ERR_INVALID, "null argument to ph_heat_step");
+  if (rank < 1 || rank > 3) return set_error(PH_ERR_UNSUPPORTED, "heat stencil rank must be 1..3 (got %d)", rank);
+  if (in == out) return set_error(PH_ERR_INVALID, "ph_heat_step needs distinct in / out buffers");
+  if (dtype == PH_F32) return heat_step_t<float>(rank, extents, coeff_host, boundary_mode, in, out);
+  if (dtype == PH_F64) return heat_step_t<double>(rank, extents, coeff_host, boundary_mode, in, out);
+  return set_error(PH_ERR_UNSUPPORTED, "the heat stencil is defined for F32 / F64");
+}
+
+int32_t ph_heat_run(int32_t dtype, int32_t rank, const int64_t* extents, const void* coeff_host,
+                    int32_t boundary_mode, void* buf_a, void* buf_b, int64_t steps) {
+  PH_REQUIRE_INIT();
+  if (!extents || !coeff_host || !buf_a || !buf_b) return set_error(PH_ERR_INVALID, "null argument to ph_heat_run");
+  if (rank < 1 || rank > 3) return set_error(PH_ERR_UNSUPPORTED, "heat stencil rank must be 1..3 (got %d)", rank);
+  if (dtype == PH_F32) return heat_run_t<float>(rank, extents, coeff_host, boundary_mode, buf_a, buf_b, steps);
+  if (dtype == PH_F64) return heat_run_t<double>(rank, extents, coeff_host, boundary_mode, buf_a, buf_b, steps);
+  return set_error(PH_ERR_UNSUPPORTED, "the heat stencil is defined for F32 / F64");
+}
+
+int32_t ph_heat_step_slab(int32_t dtype, int32_t rank, const int64_t* extents, const void* coeff_host,
+                          int32_t has_lo, int32_t has_hi, int64_t p_begin, int64_t p_end, const void* in,
+                          void* out, void* cuda_stream) {
+  PH_REQUIRE_INIT();
+  if (!extents || !coeff_host || !in || !out) return set_error(PH_ERR_INVALID, "null argument to ph_heat_step_slab");
+  cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : rt().stream;
+  return heat_slab_dispatch(dtype, rank, extents, coeff_host, has_lo, has_hi, p_begin, p_end, in, out, s);
+}
+
+}  // extern "C"

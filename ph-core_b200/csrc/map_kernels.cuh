@@ -31,9 +31,10 @@ struct MapArgs {
   int rows_per_block;
   int all_array;            // every input is OPND_ARRAY
   int64_t gx;               // rows: number of column tiles (1-D grid = gx * slabs * chunks)
+  int tx, tx_log2;          // rows: threads along the inner axis (power of two <= 256)
   uint32_t* flags;
   OuterAxes outer;          // rows/any: operand k uses stride[k], the output uses stride[NIN]
-  // any-kernel only: innermost strides
+  // rows kernel with E == 1: innermost strides (any value, incl. negative / zero)
   int64_t inner_stride[NIN + 1];
 };
 
@@ -108,17 +109,23 @@ __global__ void __launch_bounds__(MAP_THREADS) map_flat_kernel(const MapArgs<F::
 }
 
 // ------------------------------------------------------------------ rows
-// 1-D grid: the fastest block index tiles the inner axis (MAP_THREADS * E elements), the rest enumerates
-// (slab over the leading outer axes) x (chunk of rows_per_block rows of the LAST outer
-// axis), so inside a block consecutive rows differ by one constant stride per operand.
+// The general kernel: the innermost axis of the plan is spread over TX threads (E elements
+// each; E > 1 needs unit/zero inner strides, E == 1 takes any inner stride), TY = 256/TX
+// rows are processed side by side and UNROLL row-groups are in flight per thread.
+// 1-D grid: the fastest block index tiles the inner axis, the rest enumerates (slab over the
+// leading outer axes) x (chunk of rows_per_block rows of the LAST outer axis), so inside a
+// block consecutive rows differ by one constant stride per operand: no div/mod per element.
 template <typename F, int E, int UNROLL>
 __global__ void __launch_bounds__(MAP_THREADS) map_rows_kernel(const MapArgs<F::NIN> a) {
   using In = typename F::In;
   using Out = typename F::Out;
   constexpr int NIN = F::NIN;
+  const int tx = threadIdx.x & (a.tx - 1);
+  const int ty = threadIdx.x >> a.tx_log2;
+  const int TY = MAP_THREADS >> a.tx_log2;
   const int64_t by = (int64_t)blockIdx.x / a.gx;
   const int64_t ctile = (int64_t)blockIdx.x - by * a.gx;
-  const int64_t col = (ctile * MAP_THREADS + threadIdx.x) * E;
+  const int64_t col = (ctile * a.tx + tx) * E;
   if (col >= a.n) return;                          // whole groups only: n % E == 0 by dispatch
   const int last = a.outer.n - 1;
   const int64_t rows_last = a.outer.extent[last];
@@ -140,7 +147,11 @@ __global__ void __launch_bounds__(MAP_THREADS) map_rows_kernel(const MapArgs<F::
   }
   int64_t step[NIN + 1];
 #pragma unroll
-  for (int k = 0; k <= NIN; k++) step[k] = a.outer.stride[k][last];
+  for (int k = 0; k <= NIN; k++) {
+    step[k] = a.outer.stride[k][last];
+    if constexpr (E == 1) base[k] += col * a.inner_stride[k];
+    else base[k] += (k == NIN || a.mode[k] == OPND_ARRAY || a.mode[k] == OPND_ROWVEC) ? col : 0;
+  }
 
   const In* in[NIN];
   Group<In, E> fixed[NIN];                         // row-vector / scalar operands: loaded once
@@ -148,14 +159,14 @@ __global__ void __launch_bounds__(MAP_THREADS) map_rows_kernel(const MapArgs<F::
   for (int k = 0; k < NIN; k++) {
     in[k] = reinterpret_cast<const In*>(a.in[k]) + base[k];
     if (a.mode[k] == OPND_PARAM) fixed[k] = splat_group<In, E>(bits_to<In>(a.param[k]));
-    else if (a.mode[k] == OPND_ROWVEC) fixed[k] = load_group<In, E>(in[k] + col);
+    else if (a.mode[k] == OPND_ROWVEC) fixed[k] = load_group<In, E>(in[k]);
     else fixed[k] = splat_group<In, E>(In());
   }
-  Out* out = reinterpret_cast<Out*>(a.out) + base[NIN] + col;
+  Out* out = reinterpret_cast<Out*>(a.out) + base[NIN];
 
   const int64_t r0 = chunk * a.rows_per_block;
   const int64_t r1 = (r0 + a.rows_per_block < rows_last) ? r0 + a.rows_per_block : rows_last;
-  int64_t r = r0;
+  int64_t r = r0 + ty;
   // x[u][k] of a fixed operand is written once here and never again: inside the loop
   // only array operands are (re)loaded, so the hot loop has no selects.
   Group<In, E> x[UNROLL][NIN];
@@ -163,63 +174,31 @@ __global__ void __launch_bounds__(MAP_THREADS) map_rows_kernel(const MapArgs<F::
   for (int u = 0; u < UNROLL; u++)
 #pragma unroll
     for (int k = 0; k < NIN; k++) x[u][k] = fixed[k];
-  for (; r + UNROLL <= r1; r += UNROLL) {
+  for (; r + (int64_t)(UNROLL - 1) * TY < r1; r += (int64_t)UNROLL * TY) {
 #pragma unroll
     for (int u = 0; u < UNROLL; u++) {
 #pragma unroll
       for (int k = 0; k < NIN; k++) {
-        if (a.mode[k] == OPND_ARRAY) x[u][k] = load_group<In, E>(in[k] + (r + u) * step[k] + col);
-        else if (a.mode[k] == OPND_BCAST) x[u][k] = splat_group<In, E>(in[k][(r + u) * step[k]]);
+        if (a.mode[k] == OPND_ARRAY) x[u][k] = load_group<In, E>(in[k] + (r + (int64_t)u * TY) * step[k]);
+        else if (a.mode[k] == OPND_BCAST) x[u][k] = splat_group<In, E>(in[k][(r + (int64_t)u * TY) * step[k]]);
       }
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; u++) {
       Group<Out, E> y;
       apply_group<F, E>(x[u], y, err);
-      store_group<Out, E>(out + (r + u) * step[NIN], y);
+      store_group<Out, E>(out + (r + (int64_t)u * TY) * step[NIN], y);
     }
   }
-  for (; r < r1; r++) {
+  for (; r < r1; r += TY) {
 #pragma unroll
     for (int k = 0; k < NIN; k++) {
-      if (a.mode[k] == OPND_ARRAY) x[0][k] = load_group<In, E>(in[k] + r * step[k] + col);
+      if (a.mode[k] == OPND_ARRAY) x[0][k] = load_group<In, E>(in[k] + r * step[k]);
       else if (a.mode[k] == OPND_BCAST) x[0][k] = splat_group<In, E>(in[k][r * step[k]]);
     }
     Group<Out, E> y;
     apply_group<F, E>(x[0], y, err);
     store_group<Out, E>(out + r * step[NIN], y);
-  }
-  if (err) atomicOr(a.flags, err);
-}
-
-// ------------------------------------------------------------------ any strides
-template <typename F>
-__global__ void __launch_bounds__(MAP_THREADS) map_any_kernel(const MapArgs<F::NIN> a, int64_t total) {
-  using In = typename F::In;
-  using Out = typename F::Out;
-  constexpr int NIN = F::NIN;
-  uint32_t err = 0;
-  const int64_t stride = (int64_t)gridDim.x * MAP_THREADS;
-  for (int64_t i = (int64_t)blockIdx.x * MAP_THREADS + threadIdx.x; i < total; i += stride) {
-    int64_t r = i / a.n;
-    const int64_t c = i - r * a.n;
-    int64_t off[NIN + 1];
-#pragma unroll
-    for (int k = 0; k <= NIN; k++) off[k] = c * a.inner_stride[k];
-    for (int ax = a.outer.n - 1; ax >= 0; ax--) {
-      const int64_t e = a.outer.extent[ax];
-      const int64_t q = r / e;
-      const int64_t cc = r - q * e;
-      r = q;
-#pragma unroll
-      for (int k = 0; k <= NIN; k++) off[k] += cc * a.outer.stride[k][ax];
-    }
-    In v[NIN];
-#pragma unroll
-    for (int k = 0; k < NIN; k++)
-      v[k] = (a.mode[k] == OPND_PARAM) ? bits_to<In>(a.param[k])
-                                       : reinterpret_cast<const In*>(a.in[k])[off[k]];
-    reinterpret_cast<Out*>(a.out)[off[NIN]] = F::apply(v, err);
   }
   if (err) atomicOr(a.flags, err);
 }
@@ -244,13 +223,18 @@ inline int32_t launch_flat(const MapArgs<F::NIN>& a) {
 
 template <typename F, int E, int UNROLL>
 inline int32_t launch_rows(MapArgs<F::NIN>& a) {
-  const int64_t gx = ceil_div(a.n, (int64_t)MAP_THREADS * E);
+  const int64_t groups = ceil_div(a.n, (int64_t)E);
+  int tx = 1, lg = 0;
+  while (tx < MAP_THREADS && tx < groups) { tx <<= 1; lg++; }
+  const int ty = MAP_THREADS / tx;
+  a.tx = tx; a.tx_log2 = lg;
+  const int64_t gx = ceil_div(groups, (int64_t)tx);
   const int64_t rows_last = a.outer.extent[a.outer.n - 1];
   const int64_t slabs = a.rows / rows_last;
-  // enough blocks for ~8 waves, but >= 4*UNROLL rows per block so row-vectors amortise
+  // enough blocks for ~8 waves, but several row-groups per thread so row-vectors amortise
   const int64_t target_blocks = (int64_t)rt().sm_count * 8 * 8;
   int64_t chunks = std::max<int64_t>(1, target_blocks / std::max<int64_t>(1, gx * slabs));
-  int64_t rpb = std::max<int64_t>(ceil_div(rows_last, chunks), std::min<int64_t>(rows_last, UNROLL * 4));
+  int64_t rpb = std::max<int64_t>(ceil_div(rows_last, chunks), std::min<int64_t>(rows_last, (int64_t)UNROLL * 4 * ty));
   chunks = ceil_div(rows_last, rpb);
   const int64_t blocks = gx * slabs * chunks;
   if (blocks > 0x7fffffffLL) return set_error(PH_ERR_INVALID, "array too large for one launch");
@@ -346,8 +330,12 @@ int32_t launch_map(const MapOperand* ops, void* out, const ph_desc* out_desc) {
     return launch_flat<F, 1, 4>(a);
   }
 
-  // ---- outer axes
-  a.outer.n = inner;
+  // ---- outer axes (a strided 1-D plan gets a dummy outer axis of extent 1)
+  a.outer.n = inner > 0 ? inner : 1;
+  if (inner == 0) {
+    a.outer.extent[0] = 1;
+    for (int k = 0; k <= NIN; k++) a.outer.stride[k][0] = 0;
+  }
   for (int ax = 0; ax < inner; ax++) {
     a.outer.extent[ax] = p.extent[ax];
     for (int k = 0; k < NIN; k++) a.outer.stride[k][ax] = (a.mode[k] == OPND_PARAM) ? 0 : in_stride(k, ax);
@@ -355,34 +343,30 @@ int32_t launch_map(const MapOperand* ops, void* out, const ph_desc* out_desc) {
   }
   a.n = p.extent[inner];
   a.rows = p.total / a.n;
+  for (int k = 0; k < NIN; k++) a.inner_stride[k] = (a.mode[k] == OPND_PARAM) ? 0 : in_stride(k, inner);
+  a.inner_stride[NIN] = p.stride[out_slot][inner];
 
-  // ---- rows?
-  bool rows = p.stride[out_slot][inner] == 1;
-  for (int k = 0; k < NIN && rows; k++)
-    if (a.mode[k] != OPND_PARAM && in_stride(k, inner) != 1 && in_stride(k, inner) != 0) rows = false;
-  if (rows) {
+  // ---- vectorisable rows: unit inner stride on the output, unit / zero on the inputs
+  bool vec = p.stride[out_slot][inner] == 1;
+  for (int k = 0; k < NIN && vec; k++)
+    if (a.mode[k] != OPND_PARAM && in_stride(k, inner) != 1 && in_stride(k, inner) != 0) vec = false;
+  if (vec) {
     for (int k = 0; k < NIN; k++) {
       if (a.mode[k] == OPND_PARAM) continue;
       if (in_stride(k, inner) == 0) { a.mode[k] = OPND_BCAST; continue; }
       bool rowvec = true;
       for (int ax = 0; ax < inner; ax++) if (in_stride(k, ax) != 0) rowvec = false;
-      a.mode[k] = rowvec ? OPND_ROWVEC : OPND_ARRAY;
+      a.mode[k] = (rowvec && inner > 0) ? OPND_ROWVEC : OPND_ARRAY;
     }
-    a.all_array = 1;
-    for (int k = 0; k < NIN; k++) if (a.mode[k] != OPND_ARRAY) a.all_array = 0;
     const int vb = pick_width(true);
     if (vb == 32 && WIDE <= 16) return launch_rows<F, 32 / WIDE, 4>(a);
     if (vb >= 16 && WIDE <= 8) return launch_rows<F, 16 / WIDE, 4>(a);
     return launch_rows<F, 1, 4>(a);
   }
-
-  // ---- anything else
-  for (int k = 0; k < NIN; k++) a.inner_stride[k] = (a.mode[k] == OPND_PARAM) ? 0 : in_stride(k, inner);
-  a.inner_stride[NIN] = p.stride[out_slot][inner];
-  const int64_t blocks = std::min<int64_t>(ceil_div(p.total, MAP_THREADS), (int64_t)rt().sm_count * 32);
-  map_any_kernel<F><<<(unsigned)blocks, MAP_THREADS, 0, rt().stream>>>(a, p.total);
-  PH_LAUNCH_CHECK("map_any_kernel");
-  return PH_OK;
+  // ---- arbitrary inner strides: one element per thread per row, still no div/mod per element
+  for (int k = 0; k < NIN; k++)
+    if (a.mode[k] != OPND_PARAM) a.mode[k] = OPND_ARRAY;
+  return launch_rows<F, 1, 4>(a);
 }
 
 }  // namespace ph

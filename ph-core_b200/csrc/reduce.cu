@@ -1,0 +1,637 @@
+// reduce.cu -- full and per-axis reductions (K7, K8 of SURVEY.md 2.3).
+//
+// Replaces Crystal's Enumerable#sum/min/max folded over NArray#each
+// (src/n_array.cr:556-564, block form src/multi_indexable.cr:788-793) and the README's
+// argmax idiom (README.md:56-61).  Semantics kept from the reference:
+//   * max/min/argmax/argmin: strict > / < from the left, so the FIRST extremum wins (this
+//     also decides between -0.0 and +0.0); NaN -> PH_FLAG_NAN (host raises ArgumentError).
+//   * integer sum: OverflowError when ANY prefix of the lexicographic fold leaves T.  A
+//     commutative pre-filter (sum of positives / of negatives fit in T => no prefix can
+//     overflow) decides almost always; otherwise an ordered (sum, max-prefix, min-prefix)
+//     monoid pass decides exactly.
+//   * float sum: two-pass tree in T (deterministic for a given shape), tolerance-checked.
+// Per-axis reductions are defined as the fold of each_slice(axis) in increasing index
+// (src/multi_indexable.cr:742-748); the column-strip kernel keeps exactly that order.
+#include "map_kernels.cuh"
+#include "ops.cuh"
+#include <limits>
+
+namespace ph {
+
+constexpr int RED_THREADS = 256;
+
+// ---------------------------------------------------------------- helpers
+template <typename T> struct Acc { using type = T; };             // sum accumulator
+template <> struct Acc<int32_t> { using type = int64_t; };
+template <> struct Acc<int64_t> { using type = __int128; };
+template <> struct Acc<uint8_t> { using type = int64_t; };
+
+template <typename T> __device__ __forceinline__ T shfl_down_t(T v, int off) {
+  if constexpr (sizeof(T) == 16) {
+    uint64_t lo = (uint64_t)v, hi = (uint64_t)((unsigned __int128)v >> 64);
+    lo = __shfl_down_sync(0xffffffffu, lo, off);
+    hi = __shfl_down_sync(0xffffffffu, hi, off);
+    return (T)(((unsigned __int128)hi << 64) | lo);
+  } else {
+    return __shfl_down_sync(0xffffffffu, v, off);
+  }
+}
+
+template <typename T> __device__ __forceinline__ T lowest_of() {
+  if constexpr (std::is_same<T, float>::value) return -__int_as_float(0x7f800000);
+  else if constexpr (std::is_same<T, double>::value) return -__longlong_as_double(0x7ff0000000000000LL);
+  else return std::numeric_limits<T>::lowest();
+}
+template <typename T> __device__ __forceinline__ T highest_of() {
+  if constexpr (std::is_same<T, float>::value) return __int_as_float(0x7f800000);
+  else if constexpr (std::is_same<T, double>::value) return __longlong_as_double(0x7ff0000000000000LL);
+  else return std::numeric_limits<T>::max();
+}
+
+// (value, index) candidate for first-extremum selection
+template <typename T> struct Cand { T v; int64_t i; };
+template <typename T, bool IS_MAX>
+__device__ __forceinline__ Cand<T> better(const Cand<T>& a, const Cand<T>& b) {
+  // strictly better value wins; equal values -> lower index (the first one met in lex order)
+  const bool b_wins = IS_MAX ? (b.v > a.v || (b.v == a.v && b.i < a.i))
+                             : (b.v < a.v || (b.v == a.v && b.i < a.i));
+  return b_wins ? b : a;
+}
+
+__global__ void set_flag_kernel(uint32_t* flags, uint32_t bits) { atomicOr(flags, bits); }
+
+// ---------------------------------------------------------------- full sum (floats; ints: S, P, N)
+template <typename T> struct SumState {
+  using A = typename Acc<T>::type;
+  A s, pos, neg;
+};
+
+template <typename T, int E>
+__global__ void __launch_bounds__(RED_THREADS) sum_partial_kernel(const T* __restrict__ x, int64_t n,
+                                                                  SumState<T>* __restrict__ partials) {
+  using A = typename Acc<T>::type;
+  constexpr bool IS_INT = !is_float_t<T>::value;
+  constexpr int UNROLL = 4;
+  A acc[E];
+  A pos = 0, neg = 0;
+#pragma unroll
+  for (int i = 0; i < E; i++) acc[i] = 0;
+  const int64_t tile = (int64_t)RED_THREADS * E * UNROLL;
+  const int64_t ntiles = n / tile;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t base = t * tile + (int64_t)threadIdx.x * E;
+    Group<T, E> g[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) g[u] = load_group<T, E>(x + base + (int64_t)u * RED_THREADS * E);
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++)
+#pragma unroll
+      for (int i = 0; i < E; i++) {
+        if constexpr (IS_INT) {
+          const A v = (A)g[u].v[i];
+          acc[i] += v;
+          if (v > 0) pos += v; else neg += v;
+        } else {
+          acc[i] = f_add(acc[i], g[u].v[i]);
+        }
+      }
+  }
+  // tail (< one tile): spread over the first block
+  if (blockIdx.x == 0) {
+    for (int64_t i = ntiles * tile + threadIdx.x; i < n; i += RED_THREADS) {
+      if constexpr (IS_INT) {
+        const A v = (A)x[i];
+        acc[0] += v;
+        if (v > 0) pos += v; else neg += v;
+      } else {
+        acc[0] = f_add(acc[0], x[i]);
+      }
+    }
+  }
+  A s = acc[0];
+#pragma unroll
+  for (int i = 1; i < E; i++) {
+    if constexpr (IS_INT) s += acc[i]; else s = f_add(s, acc[i]);
+  }
+  // warp then block tree (fixed order => deterministic)
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    if constexpr (IS_INT) {
+      s += shfl_down_t<A>(s, off); pos += shfl_down_t<A>(pos, off); neg += shfl_down_t<A>(neg, off);
+    } else {
+      s = f_add(s, shfl_down_t<A>(s, off));
+    }
+  }
+  __shared__ A sh_s[RED_THREADS / 32], sh_p[RED_THREADS / 32], sh_n[RED_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sh_s[warp] = s; sh_p[warp] = pos; sh_n[warp] = neg; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    A ts = sh_s[0], tp = sh_p[0], tn = sh_n[0];
+    for (int w = 1; w < RED_THREADS / 32; w++) {
+      if constexpr (IS_INT) { ts += sh_s[w]; tp += sh_p[w]; tn += sh_n[w]; }
+      else ts = f_add(ts, sh_s[w]);
+    }
+    partials[blockIdx.x].s = ts; partials[blockIdx.x].pos = tp; partials[blockIdx.x].neg = tn;
+  }
+}
+
+// final: one block; result[0] = value (T), status[0] = 0 ok / 1 definitely-overflow / 2 need exact pass
+template <typename T>
+__global__ void sum_final_kernel(const SumState<T>* __restrict__ partials, int nparts, T* __restrict__ out_value,
+                                 int* __restrict__ status) {
+  using A = typename Acc<T>::type;
+  constexpr bool IS_INT = !is_float_t<T>::value;
+  if (threadIdx.x != 0) return;
+  A s = 0, p = 0, ng = 0;
+  for (int i = 0; i < nparts; i++) {
+    if constexpr (IS_INT) { s += partials[i].s; p += partials[i].pos; ng += partials[i].neg; }
+    else s = f_add(s, partials[i].s);
+  }
+  if constexpr (IS_INT) {
+    const A hi = (A)std::numeric_limits<T>::max(), lo = (A)std::numeric_limits<T>::lowest();
+    int st = 0;
+    if (s > hi || s < lo) st = 1;                    // the final prefix itself overflows
+    else if (p > hi || ng < lo) st = 2;              // some prefix MIGHT overflow: decide exactly
+    *status = st;
+    *out_value = (T)s;
+  } else {
+    *status = 0;
+    *out_value = s;
+  }
+}
+
+// Exact ordered pass for integer sums: monoid (sum, max prefix, min prefix) combined in lex order.
+template <typename T> struct Prefix {
+  using A = typename Acc<T>::type;
+  A s, mx, mn;
+};
+template <typename T>
+__device__ __forceinline__ Prefix<T> pcombine(const Prefix<T>& l, const Prefix<T>& r) {
+  Prefix<T> o;
+  o.s = l.s + r.s;
+  const typename Prefix<T>::A a = l.s + r.mx, b = l.s + r.mn;
+  o.mx = l.mx > a ? l.mx : a;
+  o.mn = l.mn < b ? l.mn : b;
+  return o;
+}
+// each block owns a CONTIGUOUS range; each thread a contiguous sub-range (uncoalesced but exact;
+// this kernel only runs when the commutative filter could not decide).
+template <typename T>
+__global__ void __launch_bounds__(RED_THREADS) sum_exact_kernel(const T* __restrict__ x, int64_t n,
+                                                                Prefix<T>* __restrict__ partials) {
+  using A = typename Acc<T>::type;
+  const int64_t nthreads = (int64_t)gridDim.x * RED_THREADS;
+  const int64_t per = (n + nthreads - 1) / nthreads;
+  const int64_t gid = (int64_t)blockIdx.x * RED_THREADS + threadIdx.x;
+  int64_t b = gid * per, e = b + per;
+  if (b > n) b = n;
+  if (e > n) e = n;
+  Prefix<T> st; st.s = 0; st.mx = 0; st.mn = 0;     // prefixes include the empty prefix (acc = 0)
+  for (int64_t i = b; i < e; i++) {
+    st.s += (A)x[i];
+    if (st.s > st.mx) st.mx = st.s;
+    if (st.s < st.mn) st.mn = st.s;
+  }
+  __shared__ Prefix<T> sh[RED_THREADS];
+  sh[threadIdx.x] = st;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Prefix<T> acc = sh[0];
+    for (int t = 1; t < RED_THREADS; t++) acc = pcombine<T>(acc, sh[t]);
+    partials[blockIdx.x] = acc;
+  }
+}
+template <typename T>
+__global__ void sum_exact_final_kernel(const Prefix<T>* __restrict__ partials, int nparts, int* __restrict__ status) {
+  using A = typename Acc<T>::type;
+  if (threadIdx.x != 0) return;
+  Prefix<T> acc = partials[0];
+  for (int i = 1; i < nparts; i++) acc = pcombine<T>(acc, partials[i]);
+  const A hi = (A)std::numeric_limits<T>::max(), lo = (A)std::numeric_limits<T>::lowest();
+  *status = (acc.mx > hi || acc.mn < lo) ? 1 : 0;
+}
+
+// ---------------------------------------------------------------- full min / max / argmin / argmax
+template <typename T, int E, bool IS_MAX>
+__global__ void __launch_bounds__(RED_THREADS) ext_partial_kernel(const T* __restrict__ x, int64_t n,
+                                                                  Cand<T>* __restrict__ partials,
+                                                                  uint32_t* __restrict__ flags) {
+  constexpr int UNROLL = 4;
+  Cand<T> best;
+  best.v = IS_MAX ? lowest_of<T>() : highest_of<T>();
+  best.i = INT64_MAX;
+  bool nan = false;
+  const int64_t tile = (int64_t)RED_THREADS * E * UNROLL;
+  const int64_t ntiles = n / tile;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t base = t * tile + (int64_t)threadIdx.x * E;
+    Group<T, E> g[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) g[u] = load_group<T, E>(x + base + (int64_t)u * RED_THREADS * E);
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++)
+#pragma unroll
+      for (int i = 0; i < E; i++) {
+        const T v = g[u].v[i];
+        if constexpr (is_float_t<T>::value) nan |= (v != v);
+        // indices grow monotonically within a thread, so strict comparison keeps the first
+        if (IS_MAX ? (v > best.v) : (v < best.v)) { best.v = v; best.i = base + (int64_t)u * RED_THREADS * E + i; }
+        else if (best.i == INT64_MAX && v == best.v) { best.i = base + (int64_t)u * RED_THREADS * E + i; }
+      }
+  }
+  if (blockIdx.x == 0) {
+    for (int64_t i = ntiles * tile + threadIdx.x; i < n; i += RED_THREADS) {
+      const T v = x[i];
+      if constexpr (is_float_t<T>::value) nan |= (v != v);
+      Cand<T> c; c.v = v; c.i = i;
+      best = better<T, IS_MAX>(best, c);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    Cand<T> o;
+    o.v = __shfl_down_sync(0xffffffffu, best.v, off);
+    o.i = __shfl_down_sync(0xffffffffu, best.i, off);
+    best = better<T, IS_MAX>(best, o);
+  }
+  __shared__ Cand<T> sh[RED_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) sh[warp] = best;
+  if (nan) atomicOr(flags, (uint32_t)PH_FLAG_NAN);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Cand<T> b = sh[0];
+    for (int w = 1; w < RED_THREADS / 32; w++) b = better<T, IS_MAX>(b, sh[w]);
+    partials[blockIdx.x] = b;
+  }
+}
+
+template <typename T, bool IS_MAX>
+__global__ void ext_final_kernel(const Cand<T>* __restrict__ partials, int nparts, T* __restrict__ out_value,
+                                 int64_t* __restrict__ out_index) {
+  if (threadIdx.x != 0) return;
+  Cand<T> b = partials[0];
+  for (int i = 1; i < nparts; i++) b = better<T, IS_MAX>(b, partials[i]);
+  *out_value = b.v;
+  if (out_index) *out_index = b.i;
+}
+
+// ---------------------------------------------------------------- per-axis: [outer, K, inner]
+// inner > 1: threads run along `inner` (coalesced), each folds its column over k = 0..K-1 in order.
+template <typename T, int E, int RED>
+__global__ void __launch_bounds__(RED_THREADS) axis_strip_kernel(const T* __restrict__ x, void* __restrict__ out,
+                                                                 int64_t outer, int64_t K, int64_t inner,
+                                                                 uint32_t* __restrict__ flags) {
+  constexpr int UNROLL = 4;
+  const int64_t groups = inner / E;                         // inner % E == 0 by dispatch
+  const int64_t gid = (int64_t)blockIdx.x * RED_THREADS + threadIdx.x;
+  if (gid >= outer * groups) return;
+  const int64_t o = gid / groups;
+  const int64_t c = (gid - o * groups) * E;
+  const T* p = x + o * K * inner + c;
+  uint32_t err = 0;
+  bool nan = false;
+  T acc[E];
+  int64_t arg[E];
+#pragma unroll
+  for (int i = 0; i < E; i++) { acc[i] = (RED == PH_SUM) ? (T)0 : p[i]; arg[i] = 0; }
+  int64_t k = (RED == PH_SUM) ? 0 : 1;
+  if constexpr (RED != PH_SUM && is_float_t<T>::value) {
+#pragma unroll
+    for (int i = 0; i < E; i++) nan |= (acc[i] != acc[i]);
+  }
+  auto fold = [&](const Group<T, E>& g, int64_t kk) {
+#pragma unroll
+    for (int i = 0; i < E; i++) {
+      const T v = g.v[i];
+      if constexpr (RED == PH_SUM) {
+        if constexpr (is_float_t<T>::value) acc[i] = f_add(acc[i], v);
+        else acc[i] = i_add<T>(acc[i], v, true, err);
+      } else {
+        if constexpr (is_float_t<T>::value) nan |= (v != v);
+        const bool take = (RED == PH_MAX || RED == PH_ARGMAX) ? (v > acc[i]) : (v < acc[i]);
+        if (take) { acc[i] = v; arg[i] = kk; }
+      }
+    }
+  };
+  for (; k + UNROLL <= K; k += UNROLL) {
+    Group<T, E> g[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) g[u] = load_group<T, E>(p + (k + u) * inner);
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) fold(g[u], k + u);
+  }
+  for (; k < K; k++) fold(load_group<T, E>(p + k * inner), k);
+  if constexpr (RED == PH_ARGMAX || RED == PH_ARGMIN) {
+    int64_t* q = reinterpret_cast<int64_t*>(out) + o * inner + c;
+#pragma unroll
+    for (int i = 0; i < E; i++) q[i] = arg[i];
+  } else {
+    Group<T, E> r;
+#pragma unroll
+    for (int i = 0; i < E; i++) r.v[i] = acc[i];
+    store_group<T, E>(reinterpret_cast<T*>(out) + o * inner + c, r);
+  }
+  if (err) atomicOr(flags, err);
+  if (nan) atomicOr(flags, (uint32_t)PH_FLAG_NAN);
+}
+
+// inner == 1: each row of K contiguous elements is reduced by TX cooperating threads.
+template <typename T, int RED>
+__global__ void __launch_bounds__(RED_THREADS) axis_row_kernel(const T* __restrict__ x, void* __restrict__ out,
+                                                               int64_t rows, int64_t K, int tx, int tx_log2,
+                                                               uint32_t* __restrict__ flags) {
+  constexpr bool IS_MAXLIKE = (RED == PH_MAX || RED == PH_ARGMAX);
+  const int lane = threadIdx.x & (tx - 1);
+  const int ty = threadIdx.x >> tx_log2;
+  const int TY = RED_THREADS >> tx_log2;
+  const int64_t row = (int64_t)blockIdx.x * TY + ty;
+  const bool live = row < rows;
+  const T* p = x + (live ? row : 0) * K;
+  bool nan = false;
+  uint32_t err = 0;
+  using A = typename Acc<T>::type;
+  A s = 0, pos = 0, neg = 0;
+  Cand<T> best;
+  best.v = IS_MAXLIKE ? lowest_of<T>() : highest_of<T>();
+  best.i = INT64_MAX;
+  if (live) {
+    for (int64_t k = lane; k < K; k += tx) {
+      const T v = p[k];
+      if constexpr (RED == PH_SUM) {
+        if constexpr (is_float_t<T>::value) s = f_add(s, v);
+        else { s += (A)v; if (v > 0) pos += (A)v; else neg += (A)v; }
+      } else {
+        if constexpr (is_float_t<T>::value) nan |= (v != v);
+        Cand<T> c; c.v = v; c.i = k;
+        best = better<T, IS_MAXLIKE>(best, c);
+      }
+    }
+  }
+  // combine the tx partials of a row (tx <= 32 stays inside a warp; larger rows use smem)
+  __shared__ A sh_s[RED_THREADS], sh_p[RED_THREADS], sh_n[RED_THREADS];
+  __shared__ Cand<T> sh_c[RED_THREADS];
+  if constexpr (RED == PH_SUM) { sh_s[threadIdx.x] = s; sh_p[threadIdx.x] = pos; sh_n[threadIdx.x] = neg; }
+  else sh_c[threadIdx.x] = best;
+  __syncthreads();
+  if (lane == 0 && live) {
+    const int b0 = ty << tx_log2;
+    if constexpr (RED == PH_SUM) {
+      A t = sh_s[b0];
+      for (int j = 1; j < tx; j++) { if constexpr (is_float_t<T>::value) t = f_add(t, sh_s[b0 + j]); else t += sh_s[b0 + j]; }
+      if constexpr (!is_float_t<T>::value) {
+        // checked fold: overflow at ANY prefix raises.  sum(positives) / sum(negatives) inside T
+        // proves no prefix can leave T; otherwise lane 0 replays the row in order (rare).
+        const A hi = (A)std::numeric_limits<T>::max(), lo = (A)std::numeric_limits<T>::lowest();
+        A tp = 0, tn = 0;
+        for (int j = 0; j < tx; j++) { tp += sh_p[b0 + j]; tn += sh_n[b0 + j]; }
+        if (tp > hi || tn < lo) {
+          A run = 0;
+          for (int64_t k = 0; k < K; k++) { run += (A)p[k]; if (run > hi || run < lo) { err |= PH_FLAG_OVERFLOW; break; } }
+        }
+      }
+      reinterpret_cast<T*>(out)[row] = (T)t;
+    } else {
+      Cand<T> b = sh_c[b0];
+      for (int j = 1; j < tx; j++) b = better<T, IS_MAXLIKE>(b, sh_c[b0 + j]);
+      if constexpr (RED == PH_ARGMAX || RED == PH_ARGMIN) reinterpret_cast<int64_t*>(out)[row] = b.i;
+      else reinterpret_cast<T*>(out)[row] = b.v;
+    }
+  }
+  if (err) atomicOr(flags, err);
+  if (nan) atomicOr(flags, (uint32_t)PH_FLAG_NAN);
+}
+
+// ---------------------------------------------------------------- host side
+static bool desc_is_contiguous(const ph_desc* d, int64_t& total) {
+  total = 1;
+  int64_t expect = 1;
+  bool ok = true;
+  for (int i = d->rank - 1; i >= 0; i--) {
+    if (d->extent[i] != 1 && d->stride[i] != expect) ok = false;
+    expect *= d->extent[i];
+    total *= d->extent[i];
+  }
+  if (d->rank == 0) total = 0;
+  return ok;
+}
+
+// returns a contiguous device pointer holding the described region (gathers if needed)
+template <typename T>
+static int32_t contiguous_input(const void* a, const ph_desc* d, const T** out_ptr, void** temp, int64_t& total) {
+  *temp = nullptr;
+  if (desc_is_contiguous(d, total)) {
+    *out_ptr = reinterpret_cast<const T*>(a) + d->offset;
+    return PH_OK;
+  }
+  if (total == 0) { *out_ptr = reinterpret_cast<const T*>(a); return PH_OK; }
+  PH_CUDA(cudaMallocAsync(temp, (size_t)total * sizeof(T), rt().stream));
+  ph_desc cd;
+  memset(&cd, 0, sizeof(cd));
+  cd.rank = d->rank;
+  int64_t acc = 1;
+  for (int i = d->rank - 1; i >= 0; i--) { cd.extent[i] = d->extent[i]; cd.stride[i] = acc; acc *= d->extent[i]; }
+  int32_t st = ph_copy_strided((int32_t)sizeof(T), a, d, *temp, &cd);
+  if (st != PH_OK) return st;
+  *out_ptr = reinterpret_cast<const T*>(*temp);
+  return PH_OK;
+}
+
+template <typename T>
+static int32_t reduce_full_t(int32_t red, const void* a, const ph_desc* d, void* out_value_dev,
+                             int64_t* out_index_dev) {
+  Runtime& r = rt();
+  const T* x;
+  void* temp;
+  int64_t n;
+  int32_t st = contiguous_input<T>(a, d, &x, &temp, n);
+  if (st != PH_OK) return st;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)r.sm_count * 8,
+                                                               ceil_div(n, (int64_t)RED_THREADS * 32)));
+  st = ensure_scratch((size_t)grid * 64 + 256);
+  if (st != PH_OK) return st;
+  int* status = reinterpret_cast<int*>(reinterpret_cast<char*>(r.d_scratch) + (size_t)grid * 64);
+  constexpr int E32 = 32 / (int)sizeof(T);
+  const bool al32 = ((uintptr_t)x % 32) == 0;
+  if (red == PH_SUM) {
+    if (n == 0) {                                         // Enumerable#sum of nothing is T.zero
+      PH_CUDA(cudaMemsetAsync(out_value_dev, 0, sizeof(T), r.stream));
+    } else {
+      SumState<T>* parts = reinterpret_cast<SumState<T>*>(r.d_scratch);
+      static_assert(sizeof(SumState<T>) <= 64, "partial too large");
+      if (al32) sum_partial_kernel<T, E32><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts);
+      else sum_partial_kernel<T, 1><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts);
+      PH_LAUNCH_CHECK("sum_partial_kernel");
+      sum_final_kernel<T><<<1, 32, 0, r.stream>>>(parts, grid, reinterpret_cast<T*>(out_value_dev), status);
+      PH_LAUNCH_CHECK("sum_final_kernel");
+      if constexpr (!is_float_t<T>::value) {
+        int* h = reinterpret_cast<int*>(r.h_scratch);
+        PH_CUDA(cudaMemcpyAsync(h, status, sizeof(int), cudaMemcpyDeviceToHost, r.stream));
+        PH_CUDA(cudaStreamSynchronize(r.stream));
+        int code = *h;
+        if (code == 2) {                                  // the filter could not decide: exact ordered pass
+          Prefix<T>* pp = reinterpret_cast<Prefix<T>*>(r.d_scratch);
+          static_assert(sizeof(Prefix<T>) <= 64, "partial too large");
+          sum_exact_kernel<T><<<grid, RED_THREADS, 0, r.stream>>>(x, n, pp);
+          PH_LAUNCH_CHECK("sum_exact_kernel");
+          sum_exact_final_kernel<T><<<1, 32, 0, r.stream>>>(pp, grid, status);
+          PH_LAUNCH_CHECK("sum_exact_final_kernel");
+          PH_CUDA(cudaMemcpyAsync(h, status, sizeof(int), cudaMemcpyDeviceToHost, r.stream));
+          PH_CUDA(cudaStreamSynchronize(r.stream));
+          code = *h;
+        }
+        if (code == 1) {
+          set_flag_kernel<<<1, 1, 0, r.stream>>>(r.d_flags, (uint32_t)PH_FLAG_OVERFLOW);
+          PH_LAUNCH_CHECK("set_flag_kernel");
+        }
+      }
+    }
+    if (out_index_dev) PH_CUDA(cudaMemsetAsync(out_index_dev, 0, 8, r.stream));
+  } else if (red == PH_MIN || red == PH_MAX || red == PH_ARGMIN || red == PH_ARGMAX) {
+    if (n == 0) {                                         // host raises Enumerable::EmptyError
+      PH_CUDA(cudaMemsetAsync(out_value_dev, 0, sizeof(T), r.stream));
+      if (out_index_dev) PH_CUDA(cudaMemsetAsync(out_index_dev, 0xff, 8, r.stream));
+    } else {
+      Cand<T>* parts = reinterpret_cast<Cand<T>*>(r.d_scratch);
+      const bool is_max = (red == PH_MAX || red == PH_ARGMAX);
+      if (is_max) {
+        if (al32) ext_partial_kernel<T, E32, true><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags);
+        else ext_partial_kernel<T, 1, true><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags);
+        PH_LAUNCH_CHECK("ext_partial_kernel");
+        ext_final_kernel<T, true><<<1, 32, 0, r.stream>>>(parts, grid, reinterpret_cast<T*>(out_value_dev), out_index_dev);
+      } else {
+        if (al32) ext_partial_kernel<T, E32, false><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags);
+        else ext_partial_kernel<T, 1, false><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags);
+        PH_LAUNCH_CHECK("ext_partial_kernel");
+        ext_final_kernel<T, false><<<1, 32, 0, r.stream>>>(parts, grid, reinterpret_cast<T*>(out_value_dev), out_index_dev);
+      }
+      PH_LAUNCH_CHECK("ext_final_kernel");
+    }
+  } else {
+    if (temp) cudaFreeAsync(temp, r.stream);
+    return set_error(PH_ERR_INVALID, "unknown reduction %d", red);
+  }
+  if (temp) PH_CUDA(cudaFreeAsync(temp, r.stream));
+  return PH_OK;
+}
+
+template <typename T, int RED>
+static int32_t reduce_axis_launch(const T* x, void* out, int64_t outer, int64_t K, int64_t inner) {
+  Runtime& r = rt();
+  if (inner > 1) {
+    constexpr int E32 = 32 / (int)sizeof(T), E16 = 16 / (int)sizeof(T);
+    constexpr bool ARG = (RED == PH_ARGMAX || RED == PH_ARGMIN);
+    const uintptr_t xa = (uintptr_t)x, oa = (uintptr_t)out;
+    const bool can32 = !ARG && inner % E32 == 0 && xa % 32 == 0 && oa % 32 == 0;
+    const bool can16 = inner % E16 == 0 && xa % 16 == 0 && (ARG || oa % 16 == 0);
+    // widest group that still leaves >= 512 threads per SM in flight
+    const int64_t want_threads = (int64_t)r.sm_count * 512;
+    int e = 1;
+    if (can32 && E32 > 1 && outer * (inner / E32) >= want_threads) e = E32;
+    else if (can16 && E16 > 1 && outer * (inner / E16) >= want_threads) e = E16;
+    const int64_t threads = outer * (inner / e);
+    const int64_t blocks = ceil_div(threads, RED_THREADS);
+    if (blocks > 0x7fffffffLL) return set_error(PH_ERR_INVALID, "array too large for one launch");
+    if (e == E32 && E32 > 1) axis_strip_kernel<T, E32, RED><<<(unsigned)blocks, RED_THREADS, 0, r.stream>>>(x, out, outer, K, inner, r.d_flags);
+    else if (e == E16 && E16 > 1) axis_strip_kernel<T, E16, RED><<<(unsigned)blocks, RED_THREADS, 0, r.stream>>>(x, out, outer, K, inner, r.d_flags);
+    else axis_strip_kernel<T, 1, RED><<<(unsigned)blocks, RED_THREADS, 0, r.stream>>>(x, out, outer, K, inner, r.d_flags);
+    PH_LAUNCH_CHECK("axis_strip_kernel");
+    return PH_OK;
+  }
+  int tx = 1, lg = 0;
+  while (tx < RED_THREADS && tx * 4 < K) { tx <<= 1; lg++; }
+  const int ty = RED_THREADS / tx;
+  const int64_t blocks = ceil_div(outer, ty);
+  if (blocks > 0x7fffffffLL) return set_error(PH_ERR_INVALID, "array too large for one launch");
+  axis_row_kernel<T, RED><<<(unsigned)blocks, RED_THREADS, 0, r.stream>>>(x, out, outer, K, tx, lg, r.d_flags);
+  PH_LAUNCH_CHECK("axis_row_kernel");
+  return PH_OK;
+}
+
+template <typename T>
+static int32_t reduce_axis_t(int32_t red, const void* a, const ph_desc* d, int32_t axis, void* out,
+                             const ph_desc* od) {
+  Runtime& r = rt();
+  if (axis < 0 || axis >= d->rank) return set_error(PH_ERR_INVALID, "axis %d out of range for rank %d", axis, d->rank);
+  int64_t ototal;
+  if (!od || !desc_is_contiguous(od, ototal) )
+    return set_error(PH_ERR_UNSUPPORTED, "ph_reduce_axis writes a contiguous output");
+  const T* x;
+  void* temp;
+  int64_t n;
+  int32_t st = contiguous_input<T>(a, d, &x, &temp, n);
+  if (st != PH_OK) return st;
+  int64_t outer = 1, inner = 1;
+  const int64_t K = d->extent[axis];
+  for (int i = 0; i < axis; i++) outer *= d->extent[i];
+  for (int i = axis + 1; i < d->rank; i++) inner *= d->extent[i];
+  if (outer * inner == 0 || K == 0) { if (temp) cudaFreeAsync(temp, r.stream); return PH_OK; }
+  const bool arg = (red == PH_ARGMAX || red == PH_ARGMIN);
+  void* o = arg ? (void*)(reinterpret_cast<int64_t*>(out) + od->offset) : (void*)(reinterpret_cast<T*>(out) + od->offset);
+  switch (red) {
+    case PH_SUM: st = reduce_axis_launch<T, PH_SUM>(x, o, outer, K, inner); break;
+    case PH_MIN: st = reduce_axis_launch<T, PH_MIN>(x, o, outer, K, inner); break;
+    case PH_MAX: st = reduce_axis_launch<T, PH_MAX>(x, o, outer, K, inner); break;
+    case PH_ARGMAX: st = reduce_axis_launch<T, PH_ARGMAX>(x, o, outer, K, inner); break;
+    case PH_ARGMIN: st = reduce_axis_launch<T, PH_ARGMIN>(x, o, outer, K, inner); break;
+    default: st = set_error(PH_ERR_INVALID, "unknown reduction %d", red);
+  }
+  if (temp) cudaFreeAsync(temp, r.stream);
+  return st;
+}
+
+}  // namespace ph
+
+using namespace ph;
+
+#define PH_RED_DTYPE_SWITCH(dtype, CALL)                                                   \
+  switch (dtype) {                                                                         \
+    case PH_F32: return CALL(float);                                                       \
+    case PH_F64: return CALL(double);                                                      \
+    case PH_I32: return CALL(int32_t);                                                     \
+    case PH_I64: return CALL(int64_t);                                                     \
+    case PH_U8: return CALL(uint8_t);                                                      \
+    default: return set_error(PH_ERR_UNSUPPORTED, "dtype %d has no reduction kernels", dtype); \
+  }
+
+extern "C" {
+
+int32_t ph_reduce_full_dev(int32_t red, int32_t dtype, const void* a, const ph_desc* a_desc,
+                           void* out_value_dev, int64_t* out_index_dev) {
+  PH_REQUIRE_INIT();
+  if (!a || !a_desc || !out_value_dev) return set_error(PH_ERR_INVALID, "null argument to ph_reduce_full_dev");
+#define CALL(T) reduce_full_t<T>(red, a, a_desc, out_value_dev, out_index_dev)
+  PH_RED_DTYPE_SWITCH(dtype, CALL)
+#undef CALL
+}
+
+int32_t ph_reduce_full(int32_t red, int32_t dtype, const void* a, const ph_desc* a_desc,
+                       void* out_value_host, int64_t* out_index_host) {
+  PH_REQUIRE_INIT();
+  if (!out_value_host) return set_error(PH_ERR_INVALID, "null out_value_host");
+  Runtime& r = rt();
+  int32_t st = ensure_scratch(1 << 20);
+  if (st != PH_OK) return st;
+  // results live at the end of the scratch area's first MiB
+  char* res = reinterpret_cast<char*>(r.d_scratch) + (1 << 20) - 64;
+  st = ph_reduce_full_dev(red, dtype, a, a_desc, res, reinterpret_cast<int64_t*>(res + 16));
+  if (st != PH_OK) return st;
+  char* h = reinterpret_cast<char*>(r.h_scratch) + 64;
+  PH_CUDA(cudaMemcpyAsync(h, res, 32, cudaMemcpyDeviceToHost, r.stream));
+  PH_CUDA(cudaStreamSynchronize(r.stream));
+  memcpy(out_value_host, h, dtype_size(dtype));
+  if (out_index_host) memcpy(out_index_host, h + 16, 8);
+  return PH_OK;
+}
+
+int32_t ph_reduce_axis(int32_t red, int32_t dtype, const void* a, const ph_desc* a_desc, int32_t axis,
+                       void* out, const ph_desc* out_desc) {
+  PH_REQUIRE_INIT();
+  if (!a || !a_desc || !out || !out_desc) return set_error(PH_ERR_INVALID, "null argument to ph_reduce_axis");
+#define CALL(T) reduce_axis_t<T>(red, a, a_desc, axis, out, out_desc)
+  PH_RED_DTYPE_SWITCH(dtype, CALL)
+#undef CALL
+}
+
+}  // extern "C"

@@ -1,19 +1,22 @@
-"""DeviceNArray: host-side mirror of ph-core's NArray API for the device path.
+"""DeviceNArray / DeviceView: host-side mirror of ph-core's NArray / View API for the device path.
 
 Mirrors the reference names and error behaviour (src/n_array.cr, src/multi_indexable.cr,
-src/multi_writable.cr) so the parity tests read like the reference's specs.  All data
-work is done by libphgpu kernels through the C-ABI; this file only validates shapes,
-builds descriptors and converts flag words into the reference's exception classes.
+src/multi_writable.cr, src/view.cr, src/mutable_view.cr) so the parity tests read like the
+reference's specs.  This file is plumbing: index math is done by the C++ host layer
+(include/ph_host.h), all data work by libphgpu kernels (include/ph_gpu.h).  It converts status
+codes / flag words into the reference's exception classes and never touches array data on
+the host, except through the explicit to_host / from_host transfers.
 """
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Sequence
+from typing import List, Optional, Sequence
 
 import numpy as np
 
 from . import _lib
-from ._lib import PhDesc, K, check
+from ._lib import PhDesc, PhRegion, PhRangeLit, K, check
+from . import region as _region
 
 
 # ---- the reference's exception classes (src/exceptions/exceptions.cr + Crystal stdlib)
@@ -77,11 +80,39 @@ def raise_for_flags(flags: int) -> None:
         raise CrArgumentError("Comparison of NaN failed")
 
 
+def host_check(status: int) -> None:
+    """ph_host.h status -> the reference's exception class."""
+    if status == 0:
+        return
+    msg = _lib.load().ph_host_last_error()
+    msg = msg.decode() if msg else ""
+    exc = {K["PH_HOST_INDEX_ERROR"]: CrIndexError, K["PH_HOST_DIMENSION_ERROR"]: DimensionError,
+           K["PH_HOST_SHAPE_ERROR"]: ShapeError, K["PH_HOST_DIV0_ERROR"]: CrDivisionByZeroError}.get(status)
+    if exc is None:
+        raise _lib.PhError(f"ph_host status {status}: {msg}")
+    raise exc(msg)
+
+
+def _i64(vals):
+    vals = [int(v) for v in vals]
+    return (C.c_int64 * max(1, len(vals)))(*vals)
+
+
+def make_region(literal: Sequence, bound_shape: Sequence[int], drop: bool = True) -> PhRegion:
+    """IndexRegion.new(region_literal, bound_shape, drop) (src/index_region.cr:192-224)."""
+    lits = [_region.marshal(l) for l in literal]
+    arr = (PhRangeLit * max(1, len(lits)))(*lits)
+    out = PhRegion()
+    host_check(_lib.load().ph_region_new(arr, len(lits), _i64(bound_shape), len(bound_shape), int(drop), C.byref(out)))
+    return out
+
+
 class _Buffer:
     """Ref-counted owner of one device allocation (reshape aliases the buffer,
     src/n_array.cr:429-433; views keep their source alive, src/view.cr:7)."""
 
     def __init__(self, nbytes: int):
+        _lib.init()
         self.nbytes = int(nbytes)
         p = C.c_void_p()
         check(_lib.load().ph_alloc(self.nbytes, C.byref(p)))
@@ -100,72 +131,209 @@ _BIN = {"+": "PH_ADD", "-": "PH_SUB", "*": "PH_MUL", "/": "PH_DIV", "//": "PH_FL
         "**": "PH_POW", "&+": "PH_WADD", "&-": "PH_WSUB", "&*": "PH_WMUL", "&**": "PH_WPOW",
         "&": "PH_AND", "|": "PH_OR", "^": "PH_XOR"}
 _CMP = {">": "PH_GT", "<": "PH_LT", ">=": "PH_GE", "<=": "PH_LE", "==": "PH_EQ", "!=": "PH_NE"}
+_RED = {"sum": "PH_SUM", "min": "PH_MIN", "max": "PH_MAX", "argmax": "PH_ARGMAX", "argmin": "PH_ARGMIN"}
 
 
-class DeviceNArray:
-    """Row-major N-D array resident in HBM (mirror of Phase::NArray, src/n_array.cr:15)."""
+class _Indexable:
+    """What DeviceNArray and DeviceView share: a buffer, a descriptor, a shape, a dtype
+    (the device-side MultiIndexable, src/multi_indexable.cr:30-65)."""
+    shape: List[int]
+    dtype: np.dtype
+    _buf: _Buffer
 
-    def __init__(self, shape: Sequence[int], dtype, buf: Optional[_Buffer] = None):
-        self.shape = [int(s) for s in shape]
-        self.dtype = np.dtype(dtype)
-        self.size = int(np.prod(self.shape, dtype=np.int64)) if self.shape else 0
-        self._buf = buf if buf is not None else _Buffer(max(1, self.size) * self.dtype.itemsize)
-
-    # ---- construction / transfer (explicit, never implicit) ------------------
-    @classmethod
-    def from_host(cls, arr: np.ndarray) -> "DeviceNArray":
-        """NArray#to_device: explicit host -> device transfer."""
-        _lib.init()
-        arr = np.ascontiguousarray(arr)
-        out = cls(arr.shape, arr.dtype)
-        if arr.size:
-            check(_lib.load().ph_h2d(out.ptr, arr.ctypes.data, arr.nbytes))
-            check(_lib.load().ph_sync())   # pageable source: keep it alive until copied
-        return out
-
-    @classmethod
-    def fill(cls, shape, value, dtype) -> "DeviceNArray":
-        """NArray.fill (src/n_array.cr:230-232)."""
-        _lib.init()
-        out = cls(shape, dtype)
-        if out.size:
-            v = np.array(value, dtype=out.dtype)
-            check(_lib.load().ph_fill_region(out.dtype.itemsize, out.ptr, C.byref(out.desc()), v.ctypes.data))
-        return out
-
-    def to_host(self) -> np.ndarray:
-        """NArray#to_host / to_narr: explicit device -> host transfer."""
-        out = np.empty(self.shape, dtype=self.dtype)
-        if self.size:
-            check(_lib.load().ph_d2h(out.ctypes.data, self.ptr, out.nbytes))
-        return out
+    def desc(self) -> PhDesc:
+        raise NotImplementedError
 
     @property
     def ptr(self) -> int:
         return self._buf.ptr
 
     @property
+    def size(self) -> int:
+        """MultiIndexable#size; NB the empty shape [] has size 0 (shape_util.cr:41-50)."""
+        if len(self.shape) == 0:
+            return 0
+        n = 1
+        for s in self.shape:
+            n *= int(s)
+        return n
+
+    @property
+    def dimensions(self) -> int:
+        return len(self.shape)
+
+    # ---- blocks are out of scope on the device path --------------------------------
+    def _no_blocks(self, *a, **k):
+        raise DeviceBlockError("arbitrary blocks cannot run on the device path")
+
+    map = map_with = each_with = map_with_coord = apply = process = build = each = each_coord = fast_each = _no_blocks
+
+    @property
     def buffer(self):
         """Buffered#buffer (src/buffered/buffered.cr:10) on a device array raises: no silent D2H."""
         raise DeviceBlockError("a device NArray has no host buffer; call to_host explicitly")
 
-    def desc(self) -> PhDesc:
-        return PhDesc.contiguous(self.shape)
+    # ---- views (src/multi_indexable.cr:881-895, src/view.cr) --------------------------
+    def view(self, *literal, drop: bool = True) -> "DeviceView":
+        v = DeviceView(self._buf, self.desc(), self.shape, self.dtype)
+        return v.view(*literal, drop=drop) if literal else v
 
-    def clone(self) -> "DeviceNArray":
-        """NArray#clone deep-copies (src/n_array.cr:372-374)."""
-        out = DeviceNArray(self.shape, self.dtype)
-        if self.size:
-            check(_lib.load().ph_d2d(out.ptr, self.ptr, self.size * self.dtype.itemsize))
+    mutable_view = view
+
+    # ---- gather: [] / get_chunk (src/multi_indexable.cr:338-356, 523-531) ---------------
+    def get_chunk(self, literal: Sequence, drop: bool = True) -> "DeviceNArray":
+        reg = literal if isinstance(literal, PhRegion) else make_region(literal, self.shape, drop)
+        return self.unsafe_fetch_chunk(reg)
+
+    def unsafe_fetch_chunk(self, reg: PhRegion) -> "DeviceNArray":
+        """NArray#unsafe_fetch_chunk (src/n_array.cr:450-453): one gather launch."""
+        src = PhDesc()
+        host_check(_lib.load().ph_desc_region(C.byref(self.desc()), C.byref(reg), C.byref(src)))
+        out = DeviceNArray(reg.shape, self.dtype)
+        if out.size:
+            check(_lib.load().ph_copy_strided(self.dtype.itemsize, self.ptr, C.byref(src), out.ptr, C.byref(out.desc())))
         return out
 
-    # ---- blocks are out of scope on the device path ------------------------------
-    def _no_blocks(self, *a, **k):
-        raise DeviceBlockError("arbitrary blocks cannot run on the device path")
+    def __getitem__(self, key):
+        if isinstance(key, _Indexable):                      # narr[mask] returns self (:479-481)
+            return self
+        if not isinstance(key, tuple):
+            key = (key,)
+        return self.get_chunk(list(key))
 
-    map = map_with = each_with = map_with_coord = apply = process = build = each = _no_blocks
+    def get(self, *coord):
+        """MultiIndexable#get / get_element (:567-575): one element, canonicalising the coord."""
+        if len(coord) == 1 and isinstance(coord[0], (list, tuple)):
+            coord = tuple(coord[0])
+        canon = (C.c_int64 * max(1, len(coord)))()
+        host_check(_lib.load().ph_canonicalize_coord(_i64(coord), len(coord), _i64(self.shape), len(self.shape), canon))
+        off = C.c_int64()
+        host_check(_lib.load().ph_desc_offset_of(C.byref(self.desc()), canon, len(coord), C.byref(off)))
+        out = np.empty(1, dtype=self.dtype)
+        check(_lib.load().ph_d2h(out.ctypes.data, self.ptr + off.value * self.dtype.itemsize, self.dtype.itemsize))
+        return out[0]
 
-    # ---- elementwise (src/multi_indexable.cr:931-985) -------------------------------
+    get_element = get
+
+    # ---- scatter / fill / mask store (src/multi_writable.cr:55-84, 127-172) ----------------
+    def set_element(self, coord, value) -> None:
+        canon = (C.c_int64 * max(1, len(coord)))()
+        host_check(_lib.load().ph_canonicalize_coord(_i64(coord), len(coord), _i64(self.shape), len(self.shape), canon))
+        off = C.c_int64()
+        host_check(_lib.load().ph_desc_offset_of(C.byref(self.desc()), canon, len(coord), C.byref(off)))
+        v = np.array([value], dtype=self.dtype)
+        check(_lib.load().ph_h2d(self.ptr + off.value * self.dtype.itemsize, v.ctypes.data, self.dtype.itemsize))
+        check(_lib.load().ph_sync())
+
+    def set_chunk(self, literal: Sequence, value) -> None:
+        reg = literal if isinstance(literal, PhRegion) else make_region(literal, self.shape)
+        if isinstance(value, _Indexable):
+            ok = C.c_int32()
+            host_check(_lib.load().ph_shapes_compatible(_i64(value.shape), len(value.shape), _i64(reg.shape),
+                                                        len(reg.shape), C.byref(ok)))
+            if not ok.value:                                 # multi_writable.cr:58-60
+                raise ShapeError(f"Cannot substitute: the given array has shape {value.shape}, but the region has "
+                                 f"shape {reg.shape}.")
+        self.unsafe_set_chunk(reg, value)
+
+    def unsafe_set_chunk(self, reg: PhRegion, value) -> None:
+        """NArray#unsafe_set_chunk (src/n_array.cr:484-500): one scatter / fill launch.  An array
+        source is streamed in ITS OWN lex order onto the region's lex order."""
+        lib = _lib.load()
+        dst = PhDesc()
+        host_check(lib.ph_desc_region(C.byref(self.desc()), C.byref(reg), C.byref(dst)))
+        nreg = 1
+        for i in range(dst.rank):
+            nreg *= dst.extent[i]
+        if nreg == 0:
+            return
+        if isinstance(value, _Indexable):
+            if value.dtype != self.dtype:
+                raise TypeError("device path: source and destination must share a dtype")
+            # compatible_shapes? allows trailing ones: view the source with the region's extents
+            sdesc = PhDesc()
+            reg_shape = [int(dst.extent[i]) for i in range(dst.rank)]
+            st = lib.ph_desc_reshape(C.byref(value.desc()), _i64(reg_shape), len(reg_shape), C.byref(sdesc))
+            if st == K["PH_HOST_NEEDS_COPY"]:
+                value = value.to_narr()
+                st = lib.ph_desc_reshape(C.byref(value.desc()), _i64(reg_shape), len(reg_shape), C.byref(sdesc))
+            host_check(st)
+            check(lib.ph_copy_strided(self.dtype.itemsize, value.ptr, C.byref(sdesc), self.ptr, C.byref(dst)))
+        else:
+            v = np.array(value, dtype=self.dtype)
+            check(lib.ph_fill_region(self.dtype.itemsize, self.ptr, C.byref(dst), v.ctypes.data))
+
+    def set_mask(self, mask: "_Indexable", value) -> None:
+        """NArray#[]=(mask, value) (src/n_array.cr:510-551)."""
+        lib = _lib.load()
+        if list(mask.shape) != list(self.shape):             # :511-513 (DimensionError on NArray)
+            raise DimensionError("Cannot perform masking: mask shape does not match array shape.")
+        if mask.dtype not in (np.dtype(np.bool_), np.dtype(np.uint8)):
+            raise TypeError("mask must be a Bool array")
+        if isinstance(value, _Indexable):
+            if list(value.shape) != list(self.shape):
+                raise DimensionError("Cannot perform masking: value shape does not match array shape.")
+            check(lib.ph_mask_set_array(self.dtype.itemsize, self.ptr, C.byref(self.desc()), mask.ptr,
+                                        C.byref(mask.desc()), value.ptr, C.byref(value.desc())))
+        else:
+            v = np.array(value, dtype=self.dtype)
+            check(lib.ph_mask_set_scalar(self.dtype.itemsize, self.ptr, C.byref(self.desc()), mask.ptr,
+                                         C.byref(mask.desc()), v.ctypes.data))
+
+    def __setitem__(self, key, value):
+        if isinstance(key, _Indexable):
+            return self.set_mask(key, value)
+        if not isinstance(key, tuple):
+            key = (key,)
+        self.set_chunk(list(key), value)
+
+    # ---- copies through views: permute / reverse / reshape (src/multi_indexable.cr:795-803) --
+    def to_narr(self) -> "DeviceNArray":
+        """View#to_narr (src/view.cr:123-126) / MultiIndexable#to_narr (:852-856): one gather."""
+        out = DeviceNArray(self.shape, self.dtype)
+        if out.size:
+            check(_lib.load().ph_copy_strided(self.dtype.itemsize, self.ptr, C.byref(self.desc()), out.ptr,
+                                              C.byref(out.desc())))
+        return out
+
+    def to_host(self) -> np.ndarray:
+        """Explicit device -> host transfer of the (materialised) contents."""
+        src = self if isinstance(self, DeviceNArray) else self.to_narr()
+        out = np.empty(src.shape, dtype=src.dtype)
+        if out.size:
+            check(_lib.load().ph_d2h(out.ctypes.data, src.ptr, out.nbytes))
+        return out
+
+    # ---- slices / tile (src/multi_indexable.cr:742-786, 818-843) ----------------------------
+    def each_slice(self, axis: int = 0):
+        for i in range(self.shape[axis]):
+            lit = [_region.ALL] * len(self.shape)
+            lit[axis] = i
+            yield self.get_chunk(lit)
+
+    def slices(self, axis: int = 0):
+        return list(self.each_slice(axis))
+
+    def tile(self, counts: Sequence[int]) -> "DeviceNArray":
+        """MultiIndexable#tile (:818-827): out[c] = self[c % shape]; as a descriptor every axis
+        becomes (count, extent) with strides (0, stride) -- no modulo on the device."""
+        if len(counts) != len(self.shape):
+            raise DimensionError("tile counts have the wrong number of dimensions")
+        if 2 * len(self.shape) > _lib.PH_MAX_RANK:
+            raise ShapeError("tile supports rank <= 4 on the device path")
+        d = self.desc()
+        ext, strd = [], []
+        for i, c in enumerate(counts):
+            ext += [int(c), int(d.extent[i])]
+            strd += [0, int(d.stride[i])]
+        src = PhDesc.make(ext, strd, d.offset)
+        out = DeviceNArray([s * int(c) for s, c in zip(self.shape, counts)], self.dtype)
+        if out.size:
+            check(_lib.load().ph_copy_strided(self.dtype.itemsize, self.ptr, C.byref(src), out.ptr,
+                                              C.byref(PhDesc.contiguous(ext))))
+        return out
+
+    # ---- elementwise (src/multi_indexable.cr:931-985) -------------------------------------
     def _result_dtype(self, op: str):
         if op == "/" and self.dtype.kind in "iu":
             return np.dtype(np.float64)
@@ -175,60 +343,52 @@ class DeviceNArray:
         lib = _lib.load()
         code = K[_BIN[op]]
         dt = dtype_code(self.dtype)
-        if isinstance(other, DeviceNArray):
+        if isinstance(other, _Indexable):
             if other.dtype != self.dtype:
                 raise TypeError("device path: operands must share a dtype")
             a, b = (other, self) if reflected else (self, other)
-            if a.shape != b.shape:                          # multi_indexable.cr:935-940
+            if list(a.shape) != list(b.shape):                # multi_indexable.cr:935-940
                 raise ShapeError(f"The shape of this MultiIndexable ({a.shape}) does not match the shape of "
                                  f"the one provided ({b.shape}), so '{op}' cannot be applied element-wise.")
             out = DeviceNArray(a.shape, self._result_dtype(op))
-            d = a.desc()
-            check(lib.ph_ewise_binary(code, dt, a.ptr, C.byref(d), b.ptr, C.byref(d), out.ptr, C.byref(d)))
+            check(lib.ph_ewise_binary(code, dt, a.ptr, C.byref(a.desc()), b.ptr, C.byref(b.desc()), out.ptr,
+                                      C.byref(out.desc())))
             return out
         # scalar: array.map &.op(other) (:947-951) / Number#op(narr) (patches/number.cr:6-15)
         out = DeviceNArray(self.shape, self._result_dtype(op))
-        d = self.desc()
         if op == "**" and self.dtype.kind == "f" and isinstance(other, (int, np.integer)) and not reflected:
             s = np.array(other, dtype=np.int32)
             code = K["PH_POWI"]
         else:
             s = np.array(other, dtype=self.dtype)
-        check(lib.ph_ewise_scalar(code, dt, self.ptr, C.byref(d), s.ctypes.data, int(reflected), out.ptr, C.byref(d)))
-        return out
-
-    def broadcast_op(self, op: str, other: "DeviceNArray") -> "DeviceNArray":
-        """NEW (ShapeUtil.broadcast_shapes, SURVEY.md 7.3a): equal rank, size-1 axes stretch."""
-        if len(self.shape) != len(other.shape):
-            raise ShapeError("broadcast requires equal rank")
-        shape = []
-        for x, y in zip(self.shape, other.shape):
-            if x == y or y == 1:
-                shape.append(x)
-            elif x == 1:
-                shape.append(y)
-            else:
-                raise ShapeError(f"shapes {self.shape} and {other.shape} cannot be broadcast")
-        out = DeviceNArray(shape, self._result_dtype(op))
-        da, db, do = self.bcast_desc(shape), other.bcast_desc(shape), out.desc()
-        check(_lib.load().ph_ewise_binary(K[_BIN[op]], dtype_code(self.dtype), self.ptr, C.byref(da),
-                                          other.ptr, C.byref(db), out.ptr, C.byref(do)))
+        check(lib.ph_ewise_scalar(code, dt, self.ptr, C.byref(self.desc()), s.ctypes.data, int(reflected), out.ptr,
+                                  C.byref(out.desc())))
         return out
 
     def bcast_desc(self, shape) -> PhDesc:
-        d = self.desc()
-        for i, (mine, want) in enumerate(zip(self.shape, shape)):
-            d.extent[i] = want
-            if mine == 1 and want != 1:
-                d.stride[i] = 0
-        return d
+        out = PhDesc()
+        host_check(_lib.load().ph_desc_broadcast(C.byref(self.desc()), _i64(shape), len(shape), C.byref(out)))
+        return out
 
-    def mul_add(self, b: "DeviceNArray", c: "DeviceNArray") -> "DeviceNArray":
-        """Fused (self * b) + c with two roundings; b may broadcast."""
+    def broadcast_op(self, op: str, other: "_Indexable") -> "DeviceNArray":
+        """NEW (ShapeUtil.broadcast_shapes, SURVEY.md 7.3a): equal rank, size-1 axes stretch."""
+        if len(self.shape) != len(other.shape):
+            raise ShapeError("broadcast requires equal rank")
+        shape = (C.c_int64 * max(1, len(self.shape)))()
+        host_check(_lib.load().ph_broadcast_shapes(_i64(self.shape), _i64(other.shape), len(self.shape), shape))
+        shape = [int(shape[i]) for i in range(len(self.shape))]
+        out = DeviceNArray(shape, self._result_dtype(op))
+        da, db = self.bcast_desc(shape), other.bcast_desc(shape)
+        check(_lib.load().ph_ewise_binary(K[_BIN[op]], dtype_code(self.dtype), self.ptr, C.byref(da),
+                                          other.ptr, C.byref(db), out.ptr, C.byref(out.desc())))
+        return out
+
+    def mul_add(self, b: "_Indexable", c: "_Indexable") -> "DeviceNArray":
+        """Fused (self * b) + c with two roundings; b and c may broadcast."""
         out = DeviceNArray(self.shape, self.dtype)
-        da, db, dc, do = self.desc(), b.bcast_desc(self.shape), c.bcast_desc(self.shape), out.desc()
+        da, db, dc = self.desc(), b.bcast_desc(self.shape), c.bcast_desc(self.shape)
         check(_lib.load().ph_ewise_mul_add(dtype_code(self.dtype), self.ptr, C.byref(da), b.ptr, C.byref(db),
-                                           c.ptr, C.byref(dc), out.ptr, C.byref(do)))
+                                           c.ptr, C.byref(dc), out.ptr, C.byref(out.desc())))
         return out
 
     def __add__(self, o): return self._binary("+", o)
@@ -255,8 +415,8 @@ class DeviceNArray:
 
     def _unary(self, name: str) -> "DeviceNArray":
         out = DeviceNArray(self.shape, self.dtype)
-        d = self.desc()
-        check(_lib.load().ph_ewise_unary(K[name], dtype_code(self.dtype), self.ptr, C.byref(d), out.ptr, C.byref(d)))
+        check(_lib.load().ph_ewise_unary(K[name], dtype_code(self.dtype), self.ptr, C.byref(self.desc()), out.ptr,
+                                         C.byref(out.desc())))
         return out
 
     def __pos__(self): return self._unary("PH_POS")
@@ -266,18 +426,18 @@ class DeviceNArray:
     def _compare(self, op: str, other, reflected=False, eq_style=False) -> "DeviceNArray":
         lib = _lib.load()
         out = DeviceNArray(self.shape, np.bool_)
-        d = self.desc()
         dt = dtype_code(self.dtype)
-        if isinstance(other, DeviceNArray):
-            if other.shape != self.shape:
+        if isinstance(other, _Indexable):
+            if list(other.shape) != list(self.shape):
                 if eq_style:                                    # multi_indexable.cr:900-902
                     raise DimensionError("Cannot compute the element-wise equality: shapes differ")
                 raise ShapeError("shapes differ")               # :935-940
-            check(lib.ph_compare(K[_CMP[op]], dt, self.ptr, C.byref(d), other.ptr, C.byref(d), out.ptr, C.byref(d)))
+            check(lib.ph_compare(K[_CMP[op]], dt, self.ptr, C.byref(self.desc()), other.ptr, C.byref(other.desc()),
+                                 out.ptr, C.byref(out.desc())))
         else:
             s = np.array(other, dtype=self.dtype)
-            check(lib.ph_compare_scalar(K[_CMP[op]], dt, self.ptr, C.byref(d), s.ctypes.data, int(reflected),
-                                        out.ptr, C.byref(d)))
+            check(lib.ph_compare_scalar(K[_CMP[op]], dt, self.ptr, C.byref(self.desc()), s.ctypes.data, int(reflected),
+                                        out.ptr, C.byref(out.desc())))
         return out
 
     def __gt__(self, o): return self._compare(">", o)
@@ -286,7 +446,81 @@ class DeviceNArray:
     def __le__(self, o): return self._compare("<=", o)
     def eq(self, o): return self._compare("==", o, eq_style=True)   # MultiIndexable#eq (:899-913)
 
-    # ---- data-dependent errors -----------------------------------------------------
+    def equals(self, other: "_Indexable") -> bool:
+        """NArray#== (src/n_array.cr:440-447) for two device arrays."""
+        if not isinstance(other, _Indexable) or list(other.shape) != list(self.shape) or other.dtype != self.dtype:
+            return False
+        if self.size == 0:
+            return True
+        v = self.eq(other).min()
+        return bool(v)
+
+    # ---- reductions (Enumerable over NArray#each, src/n_array.cr:556-564) ---------------------
+    def _reduce_full(self, name: str):
+        lib = _lib.load()
+        if self.size == 0:
+            if name == "sum":
+                return self.dtype.type(0)
+            raise CrEmptyError("Empty enumerable")
+        dt = np.dtype(np.uint8) if self.dtype == np.dtype(np.bool_) else self.dtype
+        val = np.zeros(1, dtype=dt)
+        idx = C.c_int64(-1)
+        check(lib.ph_reduce_full(K[_RED[name]], dtype_code(dt), self.ptr, C.byref(self.desc()), val.ctypes.data,
+                                 C.byref(idx)))
+        DeviceNArray.raise_pending()
+        return val[0], idx.value
+
+    def sum(self, axis: Optional[int] = None):
+        if axis is not None:
+            return self._reduce_axis("sum", axis)
+        r = self._reduce_full("sum")
+        return r[0] if isinstance(r, tuple) else r
+
+    def max(self, axis: Optional[int] = None):
+        return self._reduce_axis("max", axis) if axis is not None else self._reduce_full("max")[0]
+
+    def min(self, axis: Optional[int] = None):
+        return self._reduce_axis("min", axis) if axis is not None else self._reduce_full("min")[0]
+
+    def argmax(self, axis: Optional[int] = None):
+        """README.md:56-61 idiom: (max, coord of the FIRST maximum); per axis: Int64 indices."""
+        if axis is not None:
+            return self._reduce_axis("argmax", axis)
+        v, i = self._reduce_full("argmax")
+        return v, self.index_to_coord(i)
+
+    def argmin(self, axis: Optional[int] = None):
+        if axis is not None:
+            return self._reduce_axis("argmin", axis)
+        v, i = self._reduce_full("argmin")
+        return v, self.index_to_coord(i)
+
+    def index_to_coord(self, index: int) -> List[int]:
+        """Buffered.index_to_coord (src/buffered/buffered.cr:66-77) on the lex index."""
+        coord = []
+        for length in reversed(self.shape):
+            coord.append(index % length)
+            index //= length
+        return list(reversed(coord))
+
+    def _reduce_axis(self, name: str, axis: int) -> "DeviceNArray":
+        if axis < 0 or axis >= len(self.shape):
+            raise CrIndexError(f"axis {axis} is not present in a {len(self.shape)}-dimensional MultiIndexable")
+        if self.shape[axis] == 0 and name != "sum":
+            raise CrEmptyError("Empty enumerable")
+        out_shape = [s for i, s in enumerate(self.shape) if i != axis] or [1]
+        out_dtype = np.dtype(np.int64) if name.startswith("arg") else self.dtype
+        out = DeviceNArray(out_shape, out_dtype)
+        if out.size:
+            if self.shape[axis] == 0:
+                out.set_chunk([], 0)
+            else:
+                check(_lib.load().ph_reduce_axis(K[_RED[name]], dtype_code(self.dtype), self.ptr, C.byref(self.desc()),
+                                                 axis, out.ptr, C.byref(out.desc())))
+        DeviceNArray.raise_pending()
+        return out
+
+    # ---- data-dependent errors -----------------------------------------------------------
     @staticmethod
     def take_flags() -> int:
         f = C.c_uint32()
@@ -298,3 +532,142 @@ class DeviceNArray:
         """Synchronise and raise OverflowError / DivisionByZeroError / ArgumentError if any
         launched op hit one (SURVEY.md 8(b) error conventions)."""
         raise_for_flags(DeviceNArray.take_flags())
+
+
+class DeviceNArray(_Indexable):
+    """Row-major N-D array resident in HBM (mirror of Phase::NArray, src/n_array.cr:15)."""
+
+    def __init__(self, shape: Sequence[int], dtype, buf: Optional[_Buffer] = None):
+        self.shape = [int(s) for s in shape]
+        self.dtype = np.dtype(dtype)
+        self._buf = buf if buf is not None else _Buffer(max(1, self.size) * self.dtype.itemsize)
+
+    def desc(self) -> PhDesc:
+        return PhDesc.contiguous(self.shape)
+
+    # ---- construction / transfer (explicit, never implicit) ------------------
+    @classmethod
+    def from_host(cls, arr: np.ndarray) -> "DeviceNArray":
+        """NArray#to_device: explicit host -> device transfer."""
+        _lib.init()
+        arr = np.ascontiguousarray(arr)
+        out = cls(arr.shape, arr.dtype)
+        if arr.size:
+            check(_lib.load().ph_h2d(out.ptr, arr.ctypes.data, arr.nbytes))
+            check(_lib.load().ph_sync())   # pageable source: keep it alive until copied
+        return out
+
+    @classmethod
+    def fill(cls, shape, value, dtype) -> "DeviceNArray":
+        """NArray.fill (src/n_array.cr:230-232)."""
+        out = cls(shape, dtype)
+        if out.size:
+            v = np.array(value, dtype=out.dtype)
+            check(_lib.load().ph_fill_region(out.dtype.itemsize, out.ptr, C.byref(out.desc()), v.ctypes.data))
+        return out
+
+    def clone(self) -> "DeviceNArray":
+        """NArray#clone deep-copies (src/n_array.cr:372-374)."""
+        out = DeviceNArray(self.shape, self.dtype)
+        if self.size:
+            check(_lib.load().ph_d2d(out.ptr, self.ptr, self.size * self.dtype.itemsize))
+        return out
+
+    dup = clone
+
+    def reshape(self, *new_shape) -> "DeviceNArray":
+        """NArray#reshape ALIASES the buffer (src/n_array.cr:429-433)."""
+        if len(new_shape) == 1 and isinstance(new_shape[0], (list, tuple)):
+            new_shape = tuple(new_shape[0])
+        n = 1
+        for s in new_shape:
+            n *= int(s)
+        if (n if new_shape else 0) != self.size:
+            raise ShapeError(f"Cannot change shape from {self.shape} to {list(new_shape)}: reshape cannot add or "
+                             "remove elements.")
+        return DeviceNArray(new_shape, self.dtype, self._buf)
+
+    def flatten(self) -> "DeviceNArray":
+        return self.reshape(self.size)
+
+    def permute(self, *order) -> "DeviceNArray":
+        """MultiIndexable#permute = view.permute + copy (src/multi_indexable.cr:795-803)."""
+        return self.view().permute(*order).to_narr()
+
+    def reverse(self) -> "DeviceNArray":
+        return self.view().reverse().to_narr()
+
+
+class DeviceView(_Indexable):
+    """Lazy view: source buffer + ONE descriptor.  Region / Permute / Reverse transforms
+    (src/view_util/transforms.cr) are affine in the coordinate, so a chain of them folds into
+    (offset, extent[], stride[]) as it is built; Reshape folds when it is expressible in
+    strides and otherwise materialises first.  Reads gather, writes scatter
+    (MutableView, src/mutable_view.cr:16-18)."""
+
+    def __init__(self, buf: _Buffer, desc: PhDesc, shape, dtype):
+        self._buf = buf
+        self._desc = desc
+        self.shape = [int(s) for s in shape]
+        self.dtype = np.dtype(dtype)
+
+    def desc(self) -> PhDesc:
+        d = PhDesc()
+        C.memmove(C.byref(d), C.byref(self._desc), C.sizeof(PhDesc))
+        return d
+
+    def clone(self) -> "DeviceView":
+        return DeviceView(self._buf, self.desc(), self.shape, self.dtype)
+
+    def view(self, *literal, drop: bool = True) -> "DeviceView":
+        """View#view / restrict_to (src/view.cr:36-56)."""
+        if len(literal) == 1 and isinstance(literal[0], (list, PhRegion)):
+            literal = literal[0]
+        if isinstance(literal, PhRegion):
+            reg = literal
+        elif len(literal) == 0:
+            return self.clone()
+        else:
+            reg = make_region(list(literal), self.shape, drop)
+        out = PhDesc()
+        host_check(_lib.load().ph_desc_region(C.byref(self._desc), C.byref(reg), C.byref(out)))
+        return DeviceView(self._buf, out, reg.shape, self.dtype)
+
+    mutable_view = view
+
+    def unsafe_fetch_chunk(self, reg: PhRegion) -> "DeviceView":
+        """View#unsafe_fetch_chunk returns a view (src/view.cr:105-107)."""
+        return self.view(reg)
+
+    def get_chunk(self, literal: Sequence, drop: bool = True) -> "DeviceView":
+        reg = literal if isinstance(literal, PhRegion) else make_region(literal, self.shape, drop)
+        return self.view(reg)
+
+    def permute(self, *order) -> "DeviceView":
+        """View#permute! (src/view.cr:72-81); no argument = reversed axes."""
+        if len(order) == 1 and isinstance(order[0], (list, tuple)):
+            order = tuple(order[0])
+        out = PhDesc()
+        if order:
+            pat = (C.c_int32 * len(order))(*[int(o) for o in order])
+            host_check(_lib.load().ph_desc_permute(C.byref(self._desc), pat, len(order), C.byref(out)))
+        else:
+            host_check(_lib.load().ph_desc_permute(C.byref(self._desc), None, 0, C.byref(out)))
+        return DeviceView(self._buf, out, [int(out.extent[i]) for i in range(out.rank)], self.dtype)
+
+    def reverse(self) -> "DeviceView":
+        """View#reverse! (src/view.cr:96-99): every axis flipped."""
+        out = PhDesc()
+        host_check(_lib.load().ph_desc_reverse(C.byref(self._desc), C.byref(out)))
+        return DeviceView(self._buf, out, self.shape, self.dtype)
+
+    def reshape(self, *new_shape) -> "DeviceView":
+        """View#reshape! (src/view.cr:58-66)."""
+        if len(new_shape) == 1 and isinstance(new_shape[0], (list, tuple)):
+            new_shape = tuple(new_shape[0])
+        out = PhDesc()
+        st = _lib.load().ph_desc_reshape(C.byref(self._desc), _i64(new_shape), len(new_shape), C.byref(out))
+        if st == K["PH_HOST_NEEDS_COPY"]:
+            return self.to_narr().view().reshape(*new_shape)
+        host_check(st)
+        return DeviceView(self._buf, out, list(new_shape), self.dtype)

@@ -15,9 +15,21 @@ def bits_equal(a: np.ndarray, b: np.ndarray) -> bool:
     return a.tobytes() == b.tobytes()
 
 
+def _canon_nan(x: np.ndarray) -> np.ndarray:
+    """IEEE-754 leaves the sign/payload of a generated NaN unspecified: x86 (where the
+    reference runs) yields the negative "real indefinite" 0xFFC00000 and propagates operand
+    payloads, sm_100 yields 0x7FFFFFFF.  NaN-ness must match exactly; the payload cannot."""
+    if x.dtype.kind != "f":
+        return x
+    y = x.copy()
+    y[np.isnan(y)] = np.nan
+    return y
+
+
 def assert_bits(got: np.ndarray, want: np.ndarray, what=""):
     assert got.shape == want.shape, f"{what}: shape {got.shape} != {want.shape}"
     assert got.dtype == want.dtype, f"{what}: dtype {got.dtype} != {want.dtype}"
+    got, want = _canon_nan(got), _canon_nan(want)
     if got.tobytes() != want.tobytes():
         ga, wa = got.reshape(-1), want.reshape(-1)
         gv = ga.view(np.uint8).reshape(ga.size, -1)

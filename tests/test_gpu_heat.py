@@ -1,0 +1,123 @@
+"""T2 parity (GPU): the heat stencil vs the oracle.
+Reference: examples/heat_equation.cr:5-51; N-D rule: SURVEY.md 8(a) a-9.
+One step is bit-exact (same operator order, no FMA); multi-step runs are held to the
+north_star tolerances (1e-6 f64, 1e-4 f32) -- and in fact stay bit-exact too."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import ph_core_b200 as ph
+from ph_core_b200 import DeviceNArray as D, heat
+from oracle import ph_oracle as O
+from gpu_util import assert_bits
+
+
+def test_example_1d_replay():
+    """The example verbatim: N = 21 f64, 10 001 steps (examples/heat_equation.cr:22-36)."""
+    state = np.full(21, 20.0); state[0], state[-1] = 0.0, 100.0
+    c = O.heat_example_coeff()
+    one = heat.update_temp(D.from_host(state), c, heat.EXAMPLE1D).to_host()
+    assert_bits(one, O.heat_step_1d_example(state, c), "one step")
+    got = heat.simulate(D.from_host(state), c, 10001, heat.EXAMPLE1D).to_host()
+    want = O.heat_simulate_1d_example()
+    np.testing.assert_allclose(got, want, rtol=1e-6)
+    assert_bits(got, want, "10001 steps")
+    assert abs(got.sum() - 480.0) < 1e-9
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [3, 21, 1024, 1025, 5000])
+def test_1d_both_modes(dtype, n):
+    rs = np.random.RandomState(n)
+    s = (rs.rand(n) * 100).astype(dtype)
+    c = dtype(0.25)
+    assert_bits(heat.update_temp(D.from_host(s), c, heat.EXAMPLE1D).to_host(), O.heat_step_1d_example(s, c), "example")
+    assert_bits(heat.update_temp(D.from_host(s), c, heat.FIXED).to_host(), O.heat_step_nd(s, c), "fixed")
+    want = s.copy()
+    for _ in range(7):
+        want = O.heat_step_nd(want, c)
+    assert_bits(heat.simulate(D.from_host(s), c, 7, heat.FIXED).to_host(), want, "7 fixed steps")
+    want = s.copy()
+    for _ in range(6):
+        want = O.heat_step_1d_example(want, c)
+    assert_bits(heat.simulate(D.from_host(s), c, 6, heat.EXAMPLE1D).to_host(), want, "6 example steps")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", [(3, 3), (5, 4), (64, 128), (37, 1000), (300, 33), (130, 1028), (4, 4100)])
+def test_2d_one_step_and_run(dtype, shape):
+    rs = np.random.RandomState(shape[0])
+    s = (rs.rand(*shape) * 100).astype(dtype)
+    c = dtype(0.1)
+    assert_bits(heat.update_temp(D.from_host(s), c).to_host(), O.heat_step_nd(s, c), f"2d step {shape}")
+    want = s.copy()
+    for _ in range(5):
+        want = O.heat_step_nd(want, c)
+    assert_bits(heat.simulate(D.from_host(s), c, 5).to_host(), want, f"2d 5 steps {shape}")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", [(3, 3, 3), (5, 6, 4), (9, 16, 128), (40, 37, 132), (7, 70, 31), (66, 9, 260), (34, 8, 1024)])
+def test_3d_one_step_and_run(dtype, shape):
+    rs = np.random.RandomState(shape[1])
+    s = (rs.rand(*shape) * 100).astype(dtype)
+    c = dtype(0.1)
+    assert_bits(heat.update_temp(D.from_host(s), c).to_host(), O.heat_step_nd(s, c), f"3d step {shape}")
+    want = s.copy()
+    for _ in range(4):
+        want = O.heat_step_nd(want, c)
+    assert_bits(heat.simulate(D.from_host(s), c, 4).to_host(), want, f"3d 4 steps {shape}")
+
+
+def test_3d_100_steps_tolerance_and_conservation():
+    """256-class grid, 100 steps, f32: north_star tolerance 1e-4 vs the oracle."""
+    rs = np.random.RandomState(20261017 % 2**31)
+    shape = (48, 64, 128)
+    z, y, x = np.meshgrid(*[np.linspace(-1, 1, n) for n in shape], indexing="ij")
+    s = (np.exp(-4 * (x * x + y * y + z * z)) * 100 + rs.rand(*shape)).astype(np.float32)
+    want = s.copy()
+    for _ in range(100):
+        want = O.heat_step_nd(want, np.float32(0.1))
+    got = heat.simulate(D.from_host(s), np.float32(0.1), 100).to_host()
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4)
+    assert_bits(got, want, "100 steps stay bit-exact")
+    assert np.array_equal(got[0], s[0]) and np.array_equal(got[:, :, -1], s[:, :, -1])   # boundary held
+
+
+def test_heat_slab_matches_whole_grid():
+    """Slab decomposition emulated on one GPU: two slabs with ghost planes,
+    halos exchanged by copies, must be bit-identical to the undivided grid."""
+    import ctypes as C
+    from ph_core_b200 import _lib
+    lib = _lib.load()
+    rs = np.random.RandomState(1)
+    shape = (20, 24, 64)
+    s = (rs.rand(*shape) * 100).astype(np.float32)
+    c = np.array(0.1, np.float32)
+    want = s.copy()
+    steps = 6
+    for _ in range(steps):
+        want = O.heat_step_nd(want, np.float32(0.1))
+    half = shape[0] // 2
+    slabs = []
+    for r in range(2):
+        loc = np.zeros((half + 2,) + shape[1:], np.float32)
+        loc[1:-1] = s[r * half:(r + 1) * half]
+        if r == 0:
+            loc[-1] = s[half]
+        else:
+            loc[0] = s[half - 1]
+        slabs.append([D.from_host(loc), D.from_host(loc)])
+    ext = (C.c_int64 * 3)(half + 2, shape[1], shape[2])
+    plane = shape[1] * shape[2] * 4
+    for t in range(steps):
+        for r in range(2):
+            src, dst = slabs[r][t & 1], slabs[r][(t & 1) ^ 1]
+            ph.check(lib.ph_heat_step_slab(ph.K["PH_F32"], 3, ext, c.ctypes.data, int(r > 0), int(r < 1), 1, half + 1,
+                                           src.ptr, dst.ptr, None))
+        a, b = slabs[0][(t & 1) ^ 1], slabs[1][(t & 1) ^ 1]
+        ph.check(lib.ph_d2d(a.ptr + (half + 1) * plane, b.ptr + 1 * plane, plane))       # rank0 hi ghost <- rank1 first
+        ph.check(lib.ph_d2d(b.ptr, a.ptr + half * plane, plane))                          # rank1 lo ghost <- rank0 last
+    got = np.concatenate([slabs[0][steps & 1].to_host()[1:-1], slabs[1][steps & 1].to_host()[1:-1]])
+    assert_bits(got, want, "two slabs == whole grid")

@@ -1,0 +1,234 @@
+"""T2 parity (GPU): strided gather / scatter / fill / mask store / views vs the oracle, bit-exact.
+Reference: NArray#unsafe_fetch_chunk / unsafe_set_chunk / []=(mask) src/n_array.cr:450-551,
+View / MutableView src/view.cr, src/mutable_view.cr, transforms src/view_util/transforms.cr."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import ph_core_b200 as ph
+from ph_core_b200 import DeviceNArray as D
+from oracle import ph_oracle as O
+from oracle.ph_oracle import rng, R
+from gpu_util import assert_bits
+import test_oracle_goldens as G
+
+
+def stock():
+    return np.array([[0, 1, 2], [3, 4, 5]], dtype=np.int32)
+
+
+def test_fetch_chunk_goldens():
+    """spec/n_array_spec.cr:211-229"""
+    d = D.from_host(stock())
+    assert d[1, rng(0, 2, 2)].to_host().tolist() == [3, 5]
+    assert d[-2, rng(-1, 0)].to_host().tolist() == [2, 1, 0]
+    e = d[rng(0, 0, exclusive=True), rng(0, 0, exclusive=True)]
+    assert e.shape == [0, 0] and e.to_host().shape == (0, 0)
+    assert d.get(1, 1) == 4 and d.get([-1, -1]) == 5
+    assert d[rng(None, None), 1].to_host().tolist() == [1, 4]          # README.md:46
+
+
+def test_set_chunk_goldens():
+    """spec/n_array_spec.cr:238-295"""
+    d = D.from_host(stock()); d[1, rng(0, 2, 2)] = D.from_host(np.array([6, 7], np.int32))
+    assert d.to_host().tolist() == [[0, 1, 2], [6, 4, 7]]
+    d = D.from_host(stock()); d[-2, rng(-1, 0)] = D.from_host(np.array([6, 7, 8], np.int32))
+    assert d.to_host().tolist() == [[8, 7, 6], [3, 4, 5]]
+    d = D.from_host(stock()); d[rng(0, 0, exclusive=True), rng(0, 0, exclusive=True)] = D.from_host(np.zeros(0, np.int32))
+    assert d.to_host().tolist() == stock().tolist()
+    d = D.from_host(stock()); d[1, rng(0, 2, 2)] = 6
+    assert d.to_host().tolist() == [[0, 1, 2], [6, 4, 6]]
+    d = D.from_host(stock()); d[-2, rng(-1, 0)] = 6
+    assert d.to_host().tolist() == [[6, 6, 6], [3, 4, 5]]
+    d = D.from_host(stock()); d[rng(0, 0, exclusive=True), rng(0, 0, exclusive=True)] = 6
+    assert d.to_host().tolist() == stock().tolist()
+
+
+def test_multi_writable_goldens():
+    """spec/multi_writable_spec.cr:14-41, 67-93"""
+    base = np.arange(12, dtype=np.int64).reshape(3, 4)
+    d = D.from_host(base); d[rng(1, None), rng(1, None)] = 10
+    exp = base.reshape(-1).copy(); exp[5:8] = 10; exp[9:12] = 10
+    assert d.to_host().reshape(-1).tolist() == exp.tolist()
+    d = D.from_host(base); d[rng(1, None), rng(1, None)] = D.from_host(np.arange(10, 16).reshape(2, 3))
+    exp = base.reshape(-1).copy(); exp[5:8] = [10, 11, 12]; exp[9:12] = [13, 14, 15]
+    assert d.to_host().reshape(-1).tolist() == exp.tolist()
+    with pytest.raises(ph.ShapeError):
+        d[rng(2, None), rng(2, None)] = D.from_host(np.arange(10, 16).reshape(2, 3))
+    d = D.from_host(base); d.set_element([-1, -2], 77)
+    assert d.to_host()[2, 2] == 77
+    for bad in ([10, 10], [-10, -10]):
+        with pytest.raises(ph.CrIndexError):
+            d.set_element(bad, 1)
+    # trailing-ones compatibility (shape_util.cr:6-32): a [2,3,1] source into a [2,3] region
+    d = D.from_host(base); d[rng(1, None), rng(1, None)] = D.from_host(np.arange(20, 26).reshape(2, 3, 1))
+    assert d.to_host()[1:, 1:].reshape(-1).tolist() == list(range(20, 26))
+
+
+def test_mask_goldens():
+    """spec/n_array_spec.cr:297-333"""
+    mask = D.from_host(np.array([[True, False, True], [False, True, False]]))
+    d = D.from_host(stock()); d[mask] = 6
+    assert d.to_host().tolist() == [[6, 1, 6], [3, 6, 5]]
+    d = D.from_host(stock()); d[mask] = D.from_host(stock()) + 10
+    assert d.to_host().tolist() == [[10, 1, 12], [3, 14, 5]]
+    with pytest.raises(ph.DimensionError):
+        d[D.from_host(np.zeros((3, 2), np.bool_))] = 6
+    assert d[mask] is d                                                # multi_indexable.cr:479-481
+    # `narr[mask] += 1` expands to narr[mask] = narr[mask] + 1
+    d = D.from_host(stock()); d[mask] = d[mask] + 1
+    assert d.to_host().tolist() == [[1, 1, 3], [3, 5, 5]]
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.int16, np.float32, np.float64])
+def test_mask_store_large(dtype):
+    rs = np.random.RandomState(4)
+    for n in [1, 31, 4096, 100003]:
+        a = (rs.rand(n) * 100).astype(dtype)
+        v = (rs.rand(n) * 100).astype(dtype)
+        m = rs.rand(n) < 0.3
+        m[: n // 3] = False                                           # long untouched runs
+        want = a.copy(); O.mask_set(want, m, v)
+        d = D.from_host(a); d[D.from_host(m)] = D.from_host(v)
+        assert_bits(d.to_host(), want, f"mask array {n}")
+        want = a.copy(); want[m] = dtype(7)
+        d = D.from_host(a); d[D.from_host(m)] = 7
+        assert_bits(d.to_host(), want, f"mask scalar {n}")
+
+
+@pytest.mark.parametrize("shape", [[2, 3, 4], [3, 5], [3, 4], [1], [1, 1, 1]])
+@pytest.mark.parametrize("drop", [True, False])
+def test_conformance_regions(shape, drop):
+    """multi_indexable_tester.cr:416-456 replayed on the device array."""
+    n = np.arange(int(np.prod(shape)), dtype=np.int64).reshape(shape)
+    d = D.from_host(n)
+    for lit in G.valid_regions(shape):
+        want = O.fetch_chunk(n, O.IndexRegion.new(lit, shape, drop))
+        got = d.get_chunk(lit, drop)
+        assert got.shape == list(want.shape)
+        assert_bits(got.to_host(), want, f"{lit}")
+    for lit, exc in G.invalid_regions(shape):
+        want = {O.CrIndexError: ph.CrIndexError, O.DimensionError: ph.DimensionError}[exc]
+        with pytest.raises(want):
+            d.get_chunk(lit, drop)
+    for c in np.ndindex(*shape):                                     # get over all coords (:374-387)
+        assert d.get(*c) == n[c]
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.int16, np.float32, np.float64])
+def test_gather_scatter_shapes(dtype):
+    """Gather + scatter over regions that exercise every kernel: contiguous, row-strided,
+    column-strided, reversed, tiny inner extent, odd offsets."""
+    rs = np.random.RandomState(8)
+    shape = [37, 50, 24]
+    n = (rs.rand(*shape) * 200).astype(dtype)
+    d = D.from_host(n)
+    lits = [
+        [rng(None, None)],
+        [rng(0, None, 2), rng(None, -1)],
+        [rng(None, None), rng(0, None, 2)],
+        [rng(None, None), rng(None, None), rng(0, None, 2)],
+        [rng(None, None, -1), rng(None, None, -1), rng(None, None, -1)],
+        [rng(5, 30, 3), 7, rng(20, 2, -3)],
+        [3, rng(1, 48), rng(1, 22)],
+        [rng(1, 36), rng(1, 49), 5],
+        [rng(2, 2), rng(None, None), rng(None, None)],
+        [rng(36, 0, -5), rng(49, 1, -7), rng(23, 0, -1)],
+    ]
+    for lit in lits:
+        reg = O.IndexRegion.new(lit, shape)
+        want = O.fetch_chunk_fast(n, reg)
+        assert_bits(d.get_chunk(lit).to_host(), want, f"gather {lit}")
+        src = (rs.rand(*want.shape) * 200).astype(dtype)
+        exp = n.copy(); O.set_chunk_fast(exp, reg, src)
+        t = D.from_host(n); t.set_chunk(lit, D.from_host(src))
+        assert_bits(t.to_host(), exp, f"scatter {lit}")
+        exp = n.copy(); O.set_chunk_fast(exp, reg, dtype(9))
+        t = D.from_host(n); t.set_chunk(lit, 9)
+        assert_bits(t.to_host(), exp, f"fill {lit}")
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.float32, np.float64])
+def test_views_and_transposes(dtype):
+    """View chains -> one descriptor -> one gather (view.cr:43-126); permute/reverse/reshape
+    copies (multi_indexable.cr:795-803); MutableView scatter (mutable_view.cr:16-18)."""
+    rs = np.random.RandomState(3)
+    n = (rs.rand(45, 70, 33) * 250).astype(dtype)
+    d = D.from_host(n)
+    assert_bits(d.permute().to_host(), np.ascontiguousarray(np.transpose(n)), "permute default")
+    for order in [(0, 2, 1), (1, 0, 2), (2, 0, 1), (1, 2, 0)]:
+        assert_bits(d.permute(*order).to_host(), np.ascontiguousarray(np.transpose(n, order)), f"permute {order}")
+    assert_bits(d.reverse().to_host(), np.ascontiguousarray(n[::-1, ::-1, ::-1]), "reverse")
+    assert_bits(d.view().reshape(45 * 70, 33).to_narr().to_host(), n.reshape(45 * 70, 33), "reshape view")
+    r = d.reshape(70, 45, 33)                                        # aliases the buffer (n_array.cr:429-433)
+    r[0, 0, 0] = 123
+    assert d.get(0, 0, 0) == dtype(123)
+    n = d.to_host()
+    # chain: region -> permute -> reverse -> region, against the oracle's transform chain
+    ov = O.View(n).view([rng(2, 40, 2), rng(None, None), rng(30, 3, -3)]).permute([2, 0, 1]).reverse().view([rng(1, 7), rng(None, None), rng(0, None, 5)])
+    dv = d.view(rng(2, 40, 2), rng(None, None), rng(30, 3, -3)).permute(2, 0, 1).reverse().view(rng(1, 7), rng(None, None), rng(0, None, 5))
+    assert dv.shape == ov.shape
+    assert_bits(dv.to_narr().to_host(), ov.to_narr(), "view chain")
+    # non-contiguous reshape materialises first
+    ov2 = O.View(n).view([rng(0, None, 2), rng(None, None), rng(None, None)]).permute([1, 0, 2])
+    dv2 = d.view(rng(0, None, 2), rng(None, None), rng(None, None)).permute(1, 0, 2)
+    assert_bits(dv2.reshape(70 * 23, 33).to_narr().to_host(), ov2.to_narr().reshape(70 * 23, 33), "reshape after permute")
+    # MutableView: transposed scatter
+    z = D.from_host(np.zeros((64, 48), dtype))
+    src = (rs.rand(48, 64) * 250).astype(dtype)
+    z.mutable_view().permute(1, 0)[rng(None, None), rng(None, None)] = D.from_host(src)
+    assert_bits(z.to_host(), np.ascontiguousarray(src.T), "transposed scatter")
+    z.mutable_view().permute(1, 0)[rng(1, 2), 0] = 99
+    h = z.to_host(); assert h[0, 1] == dtype(99) and h[0, 2] == dtype(99)
+    with pytest.raises(ph.CrIndexError):
+        d.view().permute(0, 1, 3)
+    with pytest.raises(ph.ShapeError):
+        d.view().reshape(5, 5)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", [(1000, 1030), (257, 33), (64, 64), (8, 4099), (3, 5, 1024, 40)])
+def test_transpose_tile_kernel(dtype, shape):
+    """The shared-memory tile transpose on ragged 2-D tiles and batched (rank-4) permutes."""
+    n = np.arange(int(np.prod(shape)), dtype=dtype).reshape(shape)
+    d = D.from_host(n)
+    order = tuple(range(len(shape) - 2)) + (len(shape) - 1, len(shape) - 2)
+    assert_bits(d.permute(*order).to_host(), np.ascontiguousarray(np.transpose(n, order)), "tile transpose")
+    # transposed + reversed + strided source
+    v = d.view().permute(*order).reverse()
+    assert_bits(v.to_narr().to_host(), np.ascontiguousarray(np.transpose(n, order)[tuple(slice(None, None, -1) for _ in shape)]), "rev transpose")
+
+
+def test_slices_tile_equals():
+    """README.md:63-64, multi_indexable.cr:806-827, n_array.cr:440-447"""
+    b = np.array([[0, 1, 2], [10, 11, 12]], np.int32)
+    d = D.from_host(b)
+    assert [s.to_host().tolist() for s in d.slices(axis=1)] == [[0, 10], [1, 11], [2, 12]]
+    assert [s.to_host().tolist() for s in d.slices()] == [[0, 1, 2], [10, 11, 12]]
+    unit = D.from_host(np.array([[1, 2], [3, 4]], np.int32))
+    assert unit.tile([2, 3]).to_host().tolist() == [[1, 2, 1, 2, 1, 2], [3, 4, 3, 4, 3, 4]] * 2
+    big = np.arange(35, dtype=np.float32).reshape(5, 7)
+    assert_bits(D.from_host(big).tile([3, 2]).to_host(), O.tile(big, [3, 2]), "tile")
+    assert d.equals(D.from_host(b)) and not d.equals(D.from_host(b + 1)) and not d.equals(unit)
+    c = d.clone(); c[0, 0] = 5
+    assert d.get(0, 0) == 0 and c.get(0, 0) == 5                       # clone deep-copies
+    assert D.fill([3, 2], 7, np.int64).to_host().tolist() == [[7, 7]] * 3
+
+
+def test_large_strided_configs_small_scale():
+    """BASELINE config 2 shapes at 1/16 scale: narr[0..2.., ..-1], narr[.., 0..2..], reversed,
+    transposed copy, transposed scatter, and the literal narr[..2, ..-1] (rows 0..2 inclusive)."""
+    nrow = ncol = 1024
+    n = np.arange(nrow * ncol, dtype=np.float64).reshape(nrow, ncol)     # value = flat index
+    d = D.from_host(n)
+    assert_bits(d[rng(0, None, 2), rng(None, -1)].to_host(), n[0::2, :], "rows strided")
+    assert_bits(d[rng(None, None), rng(0, None, 2)].to_host(), np.ascontiguousarray(n[:, 0::2]), "cols strided")
+    assert_bits(d[rng(None, None, -1), rng(None, None, -1)].to_host(), np.ascontiguousarray(n[::-1, ::-1]), "reversed")
+    assert_bits(d.permute().to_host(), np.ascontiguousarray(n.T), "transposed copy")
+    lit = d[rng(None, 2), rng(None, -1)]
+    assert lit.shape == [3, ncol]
+    assert_bits(lit.to_host(), n[0:3, :], "literal ..2, ..-1")
+    z = D.fill([nrow, ncol], 0.0, np.float64)
+    z.mutable_view().permute()[rng(None, None), rng(None, None)] = d
+    assert_bits(z.to_host(), np.ascontiguousarray(n.T), "transposed scatter")
