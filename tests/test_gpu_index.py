@@ -35,8 +35,11 @@ def test_set_chunk_goldens():
     assert d.to_host().tolist() == [[0, 1, 2], [6, 4, 7]]
     d = D.from_host(stock()); d[-2, rng(-1, 0)] = D.from_host(np.array([6, 7, 8], np.int32))
     assert d.to_host().tolist() == [[8, 7, 6], [3, 4, 5]]
-    d = D.from_host(stock()); d[rng(0, 0, exclusive=True), rng(0, 0, exclusive=True)] = D.from_host(np.zeros(0, np.int32))
+    empty = ph.make_region([rng(0, 0, exclusive=True), rng(0, 0, exclusive=True)], [2, 3])
+    d = D.from_host(stock()); d.unsafe_set_chunk(empty, D.from_host(np.zeros(0, np.int32)))     # the spec calls the unsafe form
     assert d.to_host().tolist() == stock().tolist()
+    with pytest.raises(ph.ShapeError):                                  # set_chunk checks compatible_shapes? ([0] vs [0, 0])
+        d[rng(0, 0, exclusive=True), rng(0, 0, exclusive=True)] = D.from_host(np.zeros(0, np.int32))
     d = D.from_host(stock()); d[1, rng(0, 2, 2)] = 6
     assert d.to_host().tolist() == [[0, 1, 2], [6, 4, 6]]
     d = D.from_host(stock()); d[-2, rng(-1, 0)] = 6
