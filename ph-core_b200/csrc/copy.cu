@@ -111,6 +111,189 @@ static int32_t try_transpose(const Plan& p, const void* src, void* dst, bool& do
   return PH_OK;
 }
 
+// ------------------------------------------------------------------ inner-strided rows
+// Gather / scatter whose innermost axis is not unit-stride on one side (step slicing
+// `0..2..`, reversal `..-1..`, a scatter into every k-th column).  One element per thread per
+// row is instruction-bound on B200 (~20 instructions per 8 bytes), so a thread moves a group
+// of E elements (32 bytes): each side is read / written as
+//   VEC    stride +1 : one 256-bit access
+//   REV    stride -1 : one 256-bit access + in-register reversal
+//   STEP2  stride +2 : two 256-bit loads, keep the even lanes (source side only)
+//   STRIDED any other stride: E scalar accesses
+// Same block mapping as map_rows_kernel: TX threads along the inner axis, 256/TX rows side by
+// side, outer coordinates decomposed once per block.
+enum SideMode : int { SIDE_VEC = 0, SIDE_REV = 1, SIDE_STEP2 = 2, SIDE_STRIDED = 3 };
+
+struct CopyRowsArgs {
+  const void* src;
+  void* dst;
+  int64_t n;                  // inner extent
+  int64_t s_src, s_dst;       // inner strides (elements)
+  int64_t rows;
+  int rows_per_block;
+  int64_t gx;
+  int tx, tx_log2;
+  OuterAxes outer;            // stride[0] = source, stride[1] = destination
+};
+
+template <typename T, int E, int SM>
+__device__ __forceinline__ Group<T, E> load_side(const T* row, int64_t col, int64_t stride) {
+  Group<T, E> g;
+  if constexpr (SM == SIDE_VEC) {
+    g = load_group<T, E>(row + col);
+  } else if constexpr (SM == SIDE_REV) {
+    const Group<T, E> t = load_group<T, E>(row - col - (E - 1));
+#pragma unroll
+    for (int i = 0; i < E; i++) g.v[i] = t.v[E - 1 - i];
+  } else if constexpr (SM == SIDE_STEP2) {
+    const Group<T, E> a = load_group<T, E>(row + 2 * col);
+    const Group<T, E> b = load_group<T, E>(row + 2 * col + E);
+#pragma unroll
+    for (int i = 0; i < E; i++) g.v[i] = (2 * i < E) ? a.v[(2 * i) % E] : b.v[(2 * i) % E];
+  } else {
+#pragma unroll
+    for (int i = 0; i < E; i++) g.v[i] = row[(col + i) * stride];
+  }
+  return g;
+}
+
+template <typename T, int E, int DM>
+__device__ __forceinline__ void store_side(T* row, int64_t col, int64_t stride, const Group<T, E>& g) {
+  if constexpr (DM == SIDE_VEC) {
+    store_group<T, E>(row + col, g);
+  } else if constexpr (DM == SIDE_REV) {
+    Group<T, E> t;
+#pragma unroll
+    for (int i = 0; i < E; i++) t.v[i] = g.v[E - 1 - i];
+    store_group<T, E>(row - col - (E - 1), t);
+  } else {
+#pragma unroll
+    for (int i = 0; i < E; i++) row[(col + i) * stride] = g.v[i];
+  }
+}
+
+template <typename T, int E, int SM, int DM>
+__global__ void __launch_bounds__(MAP_THREADS) copy_rows_kernel(const CopyRowsArgs a) {
+  constexpr int UNROLL = 2;
+  const int tx = threadIdx.x & (a.tx - 1);
+  const int ty = threadIdx.x >> a.tx_log2;
+  const int TY = MAP_THREADS >> a.tx_log2;
+  const int64_t by = (int64_t)blockIdx.x / a.gx;
+  const int64_t ctile = (int64_t)blockIdx.x - by * a.gx;
+  const int64_t col = (ctile * a.tx + tx) * E;
+  if (col >= a.n) return;
+  // STEP2 loads touch one element past the last kept one: keep the last group of a row scalar
+  const bool full = (col + E <= a.n) && !(SM == SIDE_STEP2 && col + E >= a.n);
+  const int last = a.outer.n - 1;
+  const int64_t rows_last = a.outer.extent[last];
+  const int64_t chunks = (rows_last + a.rows_per_block - 1) / a.rows_per_block;
+  int64_t slab = by / chunks;
+  const int64_t chunk = by - slab * chunks;
+  int64_t bs = 0, bd = 0;
+  for (int ax = last - 1; ax >= 0; ax--) {
+    const int64_t e = a.outer.extent[ax];
+    const int64_t q = slab / e;
+    const int64_t c = slab - q * e;
+    slab = q;
+    bs += c * a.outer.stride[0][ax];
+    bd += c * a.outer.stride[1][ax];
+  }
+  const int64_t ss = a.outer.stride[0][last], sd = a.outer.stride[1][last];
+  const T* src = reinterpret_cast<const T*>(a.src) + bs;
+  T* dst = reinterpret_cast<T*>(a.dst) + bd;
+  const int64_t r0 = chunk * a.rows_per_block;
+  const int64_t r1 = (r0 + a.rows_per_block < rows_last) ? r0 + a.rows_per_block : rows_last;
+  if (full) {
+    int64_t r = r0 + ty;
+    for (; r + (int64_t)(UNROLL - 1) * TY < r1; r += (int64_t)UNROLL * TY) {
+      Group<T, E> g[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++) g[u] = load_side<T, E, SM>(src + (r + (int64_t)u * TY) * ss, col, a.s_src);
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++) store_side<T, E, DM>(dst + (r + (int64_t)u * TY) * sd, col, a.s_dst, g[u]);
+    }
+    for (; r < r1; r += TY) {
+      const Group<T, E> g = load_side<T, E, SM>(src + r * ss, col, a.s_src);
+      store_side<T, E, DM>(dst + r * sd, col, a.s_dst, g);
+    }
+  } else {                                       // ragged last group of a row: element-wise
+    for (int64_t r = r0 + ty; r < r1; r += TY)
+      for (int64_t c = col; c < a.n; c++) dst[r * sd + c * a.s_dst] = src[r * ss + c * a.s_src];
+  }
+}
+
+template <typename T, int E, int SM, int DM>
+static int32_t launch_copy_rows(CopyRowsArgs& a) {
+  const int64_t groups = ceil_div(a.n, (int64_t)E);
+  int tx = 1, lg = 0;
+  while (tx < MAP_THREADS && tx < groups) { tx <<= 1; lg++; }
+  const int ty = MAP_THREADS / tx;
+  a.tx = tx; a.tx_log2 = lg;
+  a.gx = ceil_div(groups, (int64_t)tx);
+  const int64_t rows_last = a.outer.extent[a.outer.n - 1];
+  const int64_t slabs = a.rows / rows_last;
+  const int64_t target_blocks = (int64_t)rt().sm_count * 8 * 8;
+  int64_t chunks = std::max<int64_t>(1, target_blocks / std::max<int64_t>(1, a.gx * slabs));
+  int64_t rpb = std::max<int64_t>(ceil_div(rows_last, chunks), std::min<int64_t>(rows_last, (int64_t)4 * ty));
+  chunks = ceil_div(rows_last, rpb);
+  const int64_t blocks = a.gx * slabs * chunks;
+  if (blocks > 0x7fffffffLL) return set_error(PH_ERR_INVALID, "array too large for one launch");
+  a.rows_per_block = (int)std::min<int64_t>(rpb, 0x7fffffff);
+  copy_rows_kernel<T, E, SM, DM><<<(unsigned)blocks, MAP_THREADS, 0, rt().stream>>>(a);
+  PH_LAUNCH_CHECK("copy_rows_kernel");
+  return PH_OK;
+}
+
+// returns done = false when both inner strides are +1 (the vectorised map path is better)
+template <typename T>
+static int32_t try_copy_rows(const Plan& p, const void* src, void* dst, bool& done) {
+  done = false;
+  if (p.rank < 1) return PH_OK;
+  const int inner = p.rank - 1;
+  const int64_t s_src = p.stride[0][inner], s_dst = p.stride[1][inner];
+  if (s_src == 1 && s_dst == 1) return PH_OK;
+  if (s_dst == 0) return PH_OK;
+  constexpr int E = 32 / (int)sizeof(T);
+  CopyRowsArgs a;
+  memset(&a, 0, sizeof(a));
+  const T* sp = reinterpret_cast<const T*>(src) + p.offset[0];
+  T* dp = reinterpret_cast<T*>(dst) + p.offset[1];
+  a.src = sp; a.dst = dp;
+  a.n = p.extent[inner];
+  a.s_src = s_src; a.s_dst = s_dst;
+  a.rows = p.total / a.n;
+  a.outer.n = inner > 0 ? inner : 1;
+  if (inner == 0) { a.outer.extent[0] = 1; a.outer.stride[0][0] = 0; a.outer.stride[1][0] = 0; }
+  bool outer_src_ok = true, outer_dst_ok = true;
+  for (int ax = 0; ax < inner; ax++) {
+    a.outer.extent[ax] = p.extent[ax];
+    a.outer.stride[0][ax] = p.stride[0][ax];
+    a.outer.stride[1][ax] = p.stride[1][ax];
+    if (p.stride[0][ax] % E) outer_src_ok = false;
+    if (p.stride[1][ax] % E) outer_dst_ok = false;
+  }
+  auto elem_index = [](const void* ptr) { return (int64_t)((uintptr_t)ptr / sizeof(T)); };
+  const bool byte_ok_s = ((uintptr_t)sp % sizeof(T)) == 0, byte_ok_d = ((uintptr_t)dp % sizeof(T)) == 0;
+  int sm = SIDE_STRIDED, dm = SIDE_STRIDED;
+  if (byte_ok_s && outer_src_ok) {
+    if (s_src == 1 && elem_index(sp) % E == 0) sm = SIDE_VEC;
+    else if (s_src == -1 && (elem_index(sp) + 1) % E == 0) sm = SIDE_REV;
+    else if (s_src == 2 && elem_index(sp) % E == 0) sm = SIDE_STEP2;
+  }
+  if (byte_ok_d && outer_dst_ok) {
+    if (s_dst == 1 && elem_index(dp) % E == 0) dm = SIDE_VEC;
+    else if (s_dst == -1 && (elem_index(dp) + 1) % E == 0) dm = SIDE_REV;
+  }
+  int32_t st;
+#define PH_COPY_CASE(SMV, DMV) if (sm == SMV && dm == DMV) { st = launch_copy_rows<T, E, SMV, DMV>(a); done = (st == PH_OK); return st; }
+  PH_COPY_CASE(SIDE_VEC, SIDE_REV) PH_COPY_CASE(SIDE_VEC, SIDE_STRIDED)
+  PH_COPY_CASE(SIDE_REV, SIDE_VEC) PH_COPY_CASE(SIDE_REV, SIDE_REV) PH_COPY_CASE(SIDE_REV, SIDE_STRIDED)
+  PH_COPY_CASE(SIDE_STEP2, SIDE_VEC) PH_COPY_CASE(SIDE_STEP2, SIDE_REV) PH_COPY_CASE(SIDE_STEP2, SIDE_STRIDED)
+  PH_COPY_CASE(SIDE_STRIDED, SIDE_VEC) PH_COPY_CASE(SIDE_STRIDED, SIDE_REV) PH_COPY_CASE(SIDE_STRIDED, SIDE_STRIDED)
+#undef PH_COPY_CASE
+  return PH_OK;   // (VEC, VEC): both sides contiguous but stride flags said otherwise -> map path
+}
+
 template <typename T>
 static int32_t copy_strided_t(const void* src, const ph_desc* sd, void* dst, const ph_desc* dd) {
   const ph_desc* descs[2] = {sd, dd};
@@ -120,6 +303,8 @@ static int32_t copy_strided_t(const void* src, const ph_desc* sd, void* dst, con
   if (p.total == 0) return PH_OK;
   bool done = false;
   st = try_transpose<T>(p, src, dst, done);
+  if (st != PH_OK || done) return st;
+  st = try_copy_rows<T>(p, src, dst, done);
   if (st != PH_OK || done) return st;
   MapOperand ops[1];
   ops[0].base = src; ops[0].desc = sd;

@@ -20,6 +20,7 @@
 #include "ph_common.cuh"
 #include "ops.cuh"
 #include <algorithm>
+#include <stdlib.h>
 
 namespace ph {
 
@@ -55,6 +56,100 @@ __device__ __forceinline__ T heat_cell(T c, T zl, T zh, T yl, T yh, T xl, T xh, 
 // RANK 2: block = 32 lanes x HEAT_TY warps, every warp owns its own x tile (no y axis).
 template <typename T, int E, int RANK>
 __global__ void __launch_bounds__(32 * HEAT_TY) heat_march_kernel(const HeatArgs<T> a) {
+  __shared__ Group<T, E> rows[2][HEAT_TY][32];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  int64_t x0, y;
+  if (RANK == 3) {
+    x0 = ((int64_t)blockIdx.x * 32 + lane) * E;
+    y = (int64_t)blockIdx.y * HEAT_TY + warp;
+  } else {
+    x0 = (((int64_t)blockIdx.x * HEAT_TY + warp) * 32 + lane) * E;
+    y = 0;
+  }
+  const int64_t zb = a.z_begin + (int64_t)blockIdx.z * a.z_chunk;
+  const int64_t ze = (zb + a.z_chunk < a.z_end) ? zb + a.z_chunk : a.z_end;
+  if (zb >= ze) return;
+  const bool active = x0 < a.n2 && y < a.n1;       // n2 % E == 0 by dispatch: whole groups
+  const int64_t plane = a.n1 * a.n2;
+  const int64_t row_off = y * a.n2 + x0;
+  const bool y_edge = (RANK == 3) && (y == 0 || y == a.n1 - 1);
+  // in-plane halo sources (clamped so the address is always valid; unused on boundaries)
+  const int64_t y_up = (y > 0 ? y - 1 : y) * a.n2 + x0;
+  const int64_t y_dn = (y + 1 < a.n1 ? y + 1 : y) * a.n2 + x0;
+  const bool need_up_global = (RANK == 3) && (warp == 0);
+  const bool need_dn_global = (RANK == 3) && (warp == HEAT_TY - 1 || y + 1 >= a.n1);
+
+  Group<T, E> prev, cur, next;
+  Group<T, E> up_c, dn_c, up_n, dn_n;              // y-halo rows of the current / next plane (edge warps)
+  T xl_c = (T)0, xr_c = (T)0, xl_n = (T)0, xr_n = (T)0;
+  const bool left_halo = active && lane == 0 && x0 > 0;
+  const bool right_halo = active && lane == 31 && x0 + E < a.n2;
+  if (active) {
+    prev = load_group<T, E>(a.in + (zb - 1) * plane + row_off);
+    cur = load_group<T, E>(a.in + zb * plane + row_off);
+  } else {
+    prev = splat_group<T, E>((T)0);
+    cur = prev;
+  }
+  up_c = cur; dn_c = cur;
+  {
+    const T* pz = a.in + zb * plane;
+    if (active && need_up_global) up_c = load_group_plain<T, E>(pz + y_up);
+    if (active && need_dn_global) dn_c = load_group_plain<T, E>(pz + y_dn);
+    if (left_halo) xl_c = pz[y * a.n2 + x0 - 1];
+    if (right_halo) xr_c = pz[y * a.n2 + x0 + E];
+  }
+  int buf = 0;
+  for (int64_t z = zb; z < ze; z++) {
+    // everything plane z+1 needs is requested now and consumed one iteration later
+    const T* pn = a.in + (z + 1) * plane;
+    next = active ? load_group<T, E>(pn + row_off) : splat_group<T, E>((T)0);   // streamed once: no L1 allocation
+    up_n = next; dn_n = next;
+    if (z + 1 < ze) {
+      if (active && need_up_global) up_n = load_group_plain<T, E>(pn + y_up);
+      if (active && need_dn_global) dn_n = load_group_plain<T, E>(pn + y_dn);
+      if (left_halo) xl_n = pn[y * a.n2 + x0 - 1];
+      if (right_halo) xr_n = pn[y * a.n2 + x0 + E];
+    }
+    Group<T, E> up = up_c, dn = dn_c;
+    if (RANK == 3) {
+      rows[buf][warp][lane] = cur;
+      __syncthreads();
+      if (!need_up_global) up = rows[buf][warp - 1][lane];
+      if (!need_dn_global) dn = rows[buf][warp + 1][lane];
+    }
+    T xl = xl_c, xr = xr_c;
+    const T from_left = __shfl_up_sync(0xffffffffu, cur.v[E - 1], 1);
+    const T from_right = __shfl_down_sync(0xffffffffu, cur.v[0], 1);
+    if (lane != 0) xl = from_left;
+    if (lane != 31) xr = from_right;
+    if (active) {
+      Group<T, E> res;
+#pragma unroll
+      for (int i = 0; i < E; i++) {
+        const T c = cur.v[i];
+        const T l = (i > 0) ? cur.v[i - 1] : xl;
+        const T r = (i < E - 1) ? cur.v[i + 1] : xr;
+        const int64_t x = x0 + i;
+        const bool fixed = y_edge || x == 0 || x == a.n2 - 1;
+        const T v = heat_cell<T>(c, prev.v[i], next.v[i], up.v[i], dn.v[i], l, r, a.coeff, RANK);
+        res.v[i] = fixed ? c : v;
+      }
+      store_group<T, E>(a.out + z * plane + row_off, res);
+    }
+    prev = cur;
+    cur = next;
+    up_c = up_n; dn_c = dn_n; xl_c = xl_n; xr_c = xr_n;
+    buf ^= 1;
+  }
+}
+
+// ---- v1 (halo loads consumed in the same iteration, L1-allocating loads): kept for A/B runs
+// RANK 3: block = 32 lanes (x, E cells each) x HEAT_TY warps (consecutive y rows).
+// RANK 2: block = 32 lanes x HEAT_TY warps, every warp owns its own x tile (no y axis).
+template <typename T, int E, int RANK>
+__global__ void __launch_bounds__(32 * HEAT_TY) heat_march_kernel_v1(const HeatArgs<T> a) {
   __shared__ Group<T, E> rows[2][HEAT_TY][32];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -189,9 +284,18 @@ static int32_t launch_march(const T* in, T* out, int64_t n0, int64_t n1, int64_t
   HeatArgs<T> a;
   a.in = in; a.out = out; a.n0 = n0; a.n1 = n1; a.n2 = n2; a.coeff = coeff;
   a.z_begin = z_begin; a.z_end = z_end;
-  constexpr int EV = 16 / (int)sizeof(T);
+  constexpr int EW = 32 / (int)sizeof(T), EV = 16 / (int)sizeof(T);
+  // widest group (256-bit, then 128-bit) that divides the row, keeps rows aligned and still
+  // fills a warp; scalar otherwise
+  const bool wide = (n2 % EW == 0) && n2 >= 32 * EW && ((uintptr_t)in % 32 == 0) && ((uintptr_t)out % 32 == 0);
   const bool vec = (n2 % EV == 0) && ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0);
-  const int e = vec ? EV : 1;
+  int e = wide ? EW : (vec ? EV : 1);
+  if (const char* knob = getenv("PH_HEAT_GROUP_BYTES")) {      // tuning knob: 32 / 16 / 0 (scalar)
+    const int b = atoi(knob);
+    if (b == 16 && vec) e = EV;
+    else if (b == 32 && !wide && vec) e = EV;
+    else if (b == 0) e = 1;
+  }
   int64_t gx, gy;
   if (RANK == 3) { gx = ceil_div(n2, (int64_t)32 * e); gy = ceil_div(n1, HEAT_TY); }
   else { gx = ceil_div(n2, (int64_t)32 * e * HEAT_TY); gy = 1; }
@@ -203,7 +307,15 @@ static int32_t launch_march(const T* in, T* out, int64_t n0, int64_t n1, int64_t
   gz = ceil_div(planes, a.z_chunk);
   if (gy > 65535 || gz > 65535) return set_error(PH_ERR_INVALID, "heat grid too large for one launch");
   dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)gz), block(32 * HEAT_TY);
-  if (vec) heat_march_kernel<T, EV, RANK><<<grid, block, 0, stream>>>(a);
+  static const int variant = getenv("PH_HEAT_VARIANT") ? atoi(getenv("PH_HEAT_VARIANT")) : 2;
+  if (variant == 1) {
+    if (e == EV && EV > 1) heat_march_kernel_v1<T, EV, RANK><<<grid, block, 0, stream>>>(a);
+    else heat_march_kernel_v1<T, 1, RANK><<<grid, block, 0, stream>>>(a);
+    PH_LAUNCH_CHECK("heat_march_kernel_v1");
+    return PH_OK;
+  }
+  if (e == EW && EW != EV) heat_march_kernel<T, EW, RANK><<<grid, block, 0, stream>>>(a);
+  else if (e == EV && EV > 1) heat_march_kernel<T, EV, RANK><<<grid, block, 0, stream>>>(a);
   else heat_march_kernel<T, 1, RANK><<<grid, block, 0, stream>>>(a);
   PH_LAUNCH_CHECK("heat_march_kernel");
   return PH_OK;

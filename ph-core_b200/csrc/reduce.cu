@@ -37,6 +37,17 @@ template <typename T> __device__ __forceinline__ T shfl_down_t(T v, int off) {
   }
 }
 
+template <typename T> __device__ __forceinline__ T shfl_xor_t(T v, int off) {
+  if constexpr (sizeof(T) == 16) {
+    uint64_t lo = (uint64_t)v, hi = (uint64_t)((unsigned __int128)v >> 64);
+    lo = __shfl_xor_sync(0xffffffffu, lo, off);
+    hi = __shfl_xor_sync(0xffffffffu, hi, off);
+    return (T)(((unsigned __int128)hi << 64) | lo);
+  } else {
+    return __shfl_xor_sync(0xffffffffu, v, off);
+  }
+}
+
 template <typename T> __device__ __forceinline__ T lowest_of() {
   if constexpr (std::is_same<T, float>::value) return -__int_as_float(0x7f800000);
   else if constexpr (std::is_same<T, double>::value) return -__longlong_as_double(0x7ff0000000000000LL);
@@ -213,6 +224,21 @@ __global__ void sum_exact_final_kernel(const Prefix<T>* __restrict__ partials, i
 }
 
 // ---------------------------------------------------------------- full min / max / argmin / argmax
+// Running extremum of a register tile.  f32 uses max.NaN / min.NaN (one instruction that also
+// propagates NaN, so NaN detection is free); other types compare + select and test NaN apart.
+template <typename T, bool IS_MAX>
+__device__ __forceinline__ T ext2(T a, T b, bool& nan) {
+  if constexpr (std::is_same<T, float>::value) {
+    float r;
+    if (IS_MAX) asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    else asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+  } else {
+    if constexpr (is_float_t<T>::value) nan |= (b != b);
+    return IS_MAX ? (b > a ? b : a) : (b < a ? b : a);
+  }
+}
+
 template <typename T, int E, bool IS_MAX>
 __global__ void __launch_bounds__(RED_THREADS) ext_partial_kernel(const T* __restrict__ x, int64_t n,
                                                                   Cand<T>* __restrict__ partials,
@@ -229,16 +255,30 @@ __global__ void __launch_bounds__(RED_THREADS) ext_partial_kernel(const T* __res
     Group<T, E> g[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; u++) g[u] = load_group<T, E>(x + base + (int64_t)u * RED_THREADS * E);
+    // 1. extremum of this thread's 4*E register values (1 instruction per element for f32)
+    T m = g[0].v[0];
+    if constexpr (is_float_t<T>::value && !std::is_same<T, float>::value) nan |= (m != m);
 #pragma unroll
     for (int u = 0; u < UNROLL; u++)
 #pragma unroll
-      for (int i = 0; i < E; i++) {
-        const T v = g[u].v[i];
-        if constexpr (is_float_t<T>::value) nan |= (v != v);
-        // indices grow monotonically within a thread, so strict comparison keeps the first
-        if (IS_MAX ? (v > best.v) : (v < best.v)) { best.v = v; best.i = base + (int64_t)u * RED_THREADS * E + i; }
-        else if (best.i == INT64_MAX && v == best.v) { best.i = base + (int64_t)u * RED_THREADS * E + i; }
-      }
+      for (int i = 0; i < E; i++)
+        if (u || i) m = ext2<T, IS_MAX>(m, g[u].v[i], nan);
+    if constexpr (std::is_same<T, float>::value) nan |= (m != m);
+    // 2. only a strictly better tile can change the answer (indices grow with t, so on a tie
+    //    the earlier element stays); then find the FIRST register holding the extremum.
+    const bool improves = IS_MAX ? (m > best.v) : (m < best.v);
+    if (improves || (best.i == INT64_MAX && m == best.v)) {
+      bool found = false;
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++)
+#pragma unroll
+        for (int i = 0; i < E; i++)
+          if (!found && g[u].v[i] == m) {
+            found = true;
+            best.v = g[u].v[i];                      // the element itself (keeps the sign of a zero)
+            best.i = base + (int64_t)u * RED_THREADS * E + i;
+          }
+    }
   }
   if (blockIdx.x == 0) {
     for (int64_t i = ntiles * tile + threadIdx.x; i < n; i += RED_THREADS) {
@@ -293,7 +333,7 @@ __global__ void __launch_bounds__(RED_THREADS) axis_strip_kernel(const T* __rest
   uint32_t err = 0;
   bool nan = false;
   T acc[E];
-  int64_t arg[E];
+  int32_t arg[E];                                           // an axis extent always fits Int32
 #pragma unroll
   for (int i = 0; i < E; i++) { acc[i] = (RED == PH_SUM) ? (T)0 : p[i]; arg[i] = 0; }
   int64_t k = (RED == PH_SUM) ? 0 : 1;
@@ -301,7 +341,7 @@ __global__ void __launch_bounds__(RED_THREADS) axis_strip_kernel(const T* __rest
 #pragma unroll
     for (int i = 0; i < E; i++) nan |= (acc[i] != acc[i]);
   }
-  auto fold = [&](const Group<T, E>& g, int64_t kk) {
+  auto fold = [&](const Group<T, E>& g, int32_t kk) {
 #pragma unroll
     for (int i = 0; i < E; i++) {
       const T v = g.v[i];
@@ -320,13 +360,13 @@ __global__ void __launch_bounds__(RED_THREADS) axis_strip_kernel(const T* __rest
 #pragma unroll
     for (int u = 0; u < UNROLL; u++) g[u] = load_group<T, E>(p + (k + u) * inner);
 #pragma unroll
-    for (int u = 0; u < UNROLL; u++) fold(g[u], k + u);
+    for (int u = 0; u < UNROLL; u++) fold(g[u], (int32_t)(k + u));
   }
-  for (; k < K; k++) fold(load_group<T, E>(p + k * inner), k);
+  for (; k < K; k++) fold(load_group<T, E>(p + k * inner), (int32_t)k);
   if constexpr (RED == PH_ARGMAX || RED == PH_ARGMIN) {
     int64_t* q = reinterpret_cast<int64_t*>(out) + o * inner + c;
 #pragma unroll
-    for (int i = 0; i < E; i++) q[i] = arg[i];
+    for (int i = 0; i < E; i++) q[i] = (int64_t)arg[i];
   } else {
     Group<T, E> r;
 #pragma unroll
@@ -337,12 +377,16 @@ __global__ void __launch_bounds__(RED_THREADS) axis_strip_kernel(const T* __rest
   if (nan) atomicOr(flags, (uint32_t)PH_FLAG_NAN);
 }
 
-// inner == 1: each row of K contiguous elements is reduced by TX cooperating threads.
-template <typename T, int RED>
+// inner == 1: each row of K contiguous elements is reduced by TX cooperating threads (TX a
+// power of two; <= 32 combines with shuffles, larger through shared memory).  Lanes read
+// consecutive 32-byte groups (E elements), UNROLL groups in flight per lane.
+template <typename T, int E, int RED>
 __global__ void __launch_bounds__(RED_THREADS) axis_row_kernel(const T* __restrict__ x, void* __restrict__ out,
                                                                int64_t rows, int64_t K, int tx, int tx_log2,
                                                                uint32_t* __restrict__ flags) {
   constexpr bool IS_MAXLIKE = (RED == PH_MAX || RED == PH_ARGMAX);
+  constexpr int UNROLL = 4;
+  using A = typename Acc<T>::type;
   const int lane = threadIdx.x & (tx - 1);
   const int ty = threadIdx.x >> tx_log2;
   const int TY = RED_THREADS >> tx_log2;
@@ -351,52 +395,86 @@ __global__ void __launch_bounds__(RED_THREADS) axis_row_kernel(const T* __restri
   const T* p = x + (live ? row : 0) * K;
   bool nan = false;
   uint32_t err = 0;
-  using A = typename Acc<T>::type;
   A s = 0, pos = 0, neg = 0;
-  Cand<T> best;
-  best.v = IS_MAXLIKE ? lowest_of<T>() : highest_of<T>();
-  best.i = INT64_MAX;
-  if (live) {
-    for (int64_t k = lane; k < K; k += tx) {
-      const T v = p[k];
+  T bv = IS_MAXLIKE ? lowest_of<T>() : highest_of<T>();
+  int32_t bi = INT32_MAX;
+  auto fold = [&](const Group<T, E>& g, int32_t k0) {
+#pragma unroll
+    for (int i = 0; i < E; i++) {
+      const T v = g.v[i];
       if constexpr (RED == PH_SUM) {
         if constexpr (is_float_t<T>::value) s = f_add(s, v);
         else { s += (A)v; if (v > 0) pos += (A)v; else neg += (A)v; }
       } else {
         if constexpr (is_float_t<T>::value) nan |= (v != v);
-        Cand<T> c; c.v = v; c.i = k;
-        best = better<T, IS_MAXLIKE>(best, c);
+        // k grows monotonically inside a lane: strict comparison keeps the first extremum
+        const bool take = (IS_MAXLIKE ? (v > bv) : (v < bv)) || (bi == INT32_MAX && v == bv);
+        if (take) { bv = v; bi = k0 + i; }
+      }
+    }
+  };
+  if (live) {
+    const int64_t groups = K / E;                 // K % E == 0 by dispatch (E == 1 otherwise)
+    int64_t g0 = lane;
+    for (; g0 + (int64_t)(UNROLL - 1) * tx < groups; g0 += (int64_t)UNROLL * tx) {
+      Group<T, E> g[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++) g[u] = load_group<T, E>(p + (g0 + (int64_t)u * tx) * E);
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++) fold(g[u], (int32_t)((g0 + (int64_t)u * tx) * E));
+    }
+    for (; g0 < groups; g0 += tx) fold(load_group<T, E>(p + g0 * E), (int32_t)(g0 * E));
+  }
+  Cand<T> best; best.v = bv; best.i = (bi == INT32_MAX) ? INT64_MAX : (int64_t)bi;
+  if (tx <= 32) {
+    for (int off = tx >> 1; off > 0; off >>= 1) {
+      if constexpr (RED == PH_SUM) {
+        if constexpr (is_float_t<T>::value) s = f_add(s, shfl_xor_t<A>(s, off));
+        else {
+          s += shfl_xor_t<A>(s, off); pos += shfl_xor_t<A>(pos, off);
+          neg += shfl_xor_t<A>(neg, off);
+        }
+      } else {
+        Cand<T> o;
+        o.v = __shfl_xor_sync(0xffffffffu, best.v, off);
+        o.i = __shfl_xor_sync(0xffffffffu, best.i, off);
+        best = better<T, IS_MAXLIKE>(best, o);
+      }
+    }
+  } else {
+    __shared__ A sh_s[RED_THREADS], sh_p[RED_THREADS], sh_n[RED_THREADS];
+    __shared__ Cand<T> sh_c[RED_THREADS];
+    if constexpr (RED == PH_SUM) { sh_s[threadIdx.x] = s; sh_p[threadIdx.x] = pos; sh_n[threadIdx.x] = neg; }
+    else sh_c[threadIdx.x] = best;
+    __syncthreads();
+    if (lane == 0) {
+      const int b0 = ty << tx_log2;
+      for (int j = 1; j < tx; j++) {
+        if constexpr (RED == PH_SUM) {
+          if constexpr (is_float_t<T>::value) s = f_add(s, sh_s[b0 + j]);
+          else { s += sh_s[b0 + j]; pos += sh_p[b0 + j]; neg += sh_n[b0 + j]; }
+        } else {
+          best = better<T, IS_MAXLIKE>(best, sh_c[b0 + j]);
+        }
       }
     }
   }
-  // combine the tx partials of a row (tx <= 32 stays inside a warp; larger rows use smem)
-  __shared__ A sh_s[RED_THREADS], sh_p[RED_THREADS], sh_n[RED_THREADS];
-  __shared__ Cand<T> sh_c[RED_THREADS];
-  if constexpr (RED == PH_SUM) { sh_s[threadIdx.x] = s; sh_p[threadIdx.x] = pos; sh_n[threadIdx.x] = neg; }
-  else sh_c[threadIdx.x] = best;
-  __syncthreads();
   if (lane == 0 && live) {
-    const int b0 = ty << tx_log2;
     if constexpr (RED == PH_SUM) {
-      A t = sh_s[b0];
-      for (int j = 1; j < tx; j++) { if constexpr (is_float_t<T>::value) t = f_add(t, sh_s[b0 + j]); else t += sh_s[b0 + j]; }
       if constexpr (!is_float_t<T>::value) {
         // checked fold: overflow at ANY prefix raises.  sum(positives) / sum(negatives) inside T
         // proves no prefix can leave T; otherwise lane 0 replays the row in order (rare).
         const A hi = (A)std::numeric_limits<T>::max(), lo = (A)std::numeric_limits<T>::lowest();
-        A tp = 0, tn = 0;
-        for (int j = 0; j < tx; j++) { tp += sh_p[b0 + j]; tn += sh_n[b0 + j]; }
-        if (tp > hi || tn < lo) {
+        if (pos > hi || neg < lo) {
           A run = 0;
           for (int64_t k = 0; k < K; k++) { run += (A)p[k]; if (run > hi || run < lo) { err |= PH_FLAG_OVERFLOW; break; } }
         }
       }
-      reinterpret_cast<T*>(out)[row] = (T)t;
+      reinterpret_cast<T*>(out)[row] = (T)s;
+    } else if constexpr (RED == PH_ARGMAX || RED == PH_ARGMIN) {
+      reinterpret_cast<int64_t*>(out)[row] = best.i;
     } else {
-      Cand<T> b = sh_c[b0];
-      for (int j = 1; j < tx; j++) b = better<T, IS_MAXLIKE>(b, sh_c[b0 + j]);
-      if constexpr (RED == PH_ARGMAX || RED == PH_ARGMIN) reinterpret_cast<int64_t*>(out)[row] = b.i;
-      else reinterpret_cast<T*>(out)[row] = b.v;
+      reinterpret_cast<T*>(out)[row] = best.v;
     }
   }
   if (err) atomicOr(flags, err);
@@ -539,12 +617,18 @@ static int32_t reduce_axis_launch(const T* x, void* out, int64_t outer, int64_t 
     PH_LAUNCH_CHECK("axis_strip_kernel");
     return PH_OK;
   }
+  // last axis: rows of K contiguous elements
+  constexpr int E32 = 32 / (int)sizeof(T);
+  const bool vec = E32 > 1 && K % E32 == 0 && ((uintptr_t)x % 32) == 0;
+  const int e = vec ? E32 : 1;
+  const int64_t groups = K / e;
   int tx = 1, lg = 0;
-  while (tx < RED_THREADS && tx * 4 < K) { tx <<= 1; lg++; }
+  while (tx < RED_THREADS && (int64_t)tx * 8 < groups) { tx <<= 1; lg++; }   // <= 8 groups per lane
   const int ty = RED_THREADS / tx;
   const int64_t blocks = ceil_div(outer, ty);
   if (blocks > 0x7fffffffLL) return set_error(PH_ERR_INVALID, "array too large for one launch");
-  axis_row_kernel<T, RED><<<(unsigned)blocks, RED_THREADS, 0, r.stream>>>(x, out, outer, K, tx, lg, r.d_flags);
+  if (vec) axis_row_kernel<T, E32, RED><<<(unsigned)blocks, RED_THREADS, 0, r.stream>>>(x, out, outer, K, tx, lg, r.d_flags);
+  else axis_row_kernel<T, 1, RED><<<(unsigned)blocks, RED_THREADS, 0, r.stream>>>(x, out, outer, K, tx, lg, r.d_flags);
   PH_LAUNCH_CHECK("axis_row_kernel");
   return PH_OK;
 }

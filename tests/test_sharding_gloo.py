@@ -1,0 +1,110 @@
+"""CPU, world_size 2, gloo: the N > 1 host logic -- axis-0 shard ranges, slab layout with
+ghost planes, halo neighbours, and the combination rules for sharded reductions.  The
+compute inside each rank is the ORACLE (this is a test of the partitioning logic, which is
+what runs on the host at N > 1); 1-vs-N agreement must be bit-identical for the stencil and
+max/argmax, and exact for exactly-summable sums."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ph_core_b200 import sharding as S
+    from oracle import ph_oracle as O
+    rs = np.random.RandomState(42)
+    field = (rs.rand(11, 9, 8) * 100).astype(np.float32)          # 11 planes: uneven split 6 + 5
+    steps = 5
+    # ---- heat: slab decomposition + halo exchange over gloo send/recv
+    lay = S.slab_layout(field.shape[0], world, rank)
+    cur = S.slab_from_global(field, world, rank)
+    for _ in range(steps):
+        # the full-slab oracle step holds plane 0 / -1 fixed: exactly the ghost-plane contract;
+        # an owned global-boundary plane (no neighbour) must additionally stay fixed
+        nxt = O.heat_step_nd(cur, np.float32(0.1))
+        if lay["lo_rank"] < 0:
+            nxt[1] = cur[1]
+        if lay["hi_rank"] < 0:
+            nxt[-2] = cur[-2]
+        reqs = []
+        lo_recv, hi_recv = torch.zeros(nxt[0].shape), torch.zeros(nxt[0].shape)
+        if lay["lo_rank"] >= 0:
+            reqs.append(dist.isend(torch.from_numpy(nxt[1].copy()), lay["lo_rank"]))
+            reqs.append(dist.irecv(lo_recv, lay["lo_rank"]))
+        if lay["hi_rank"] >= 0:
+            reqs.append(dist.isend(torch.from_numpy(nxt[-2].copy()), lay["hi_rank"]))
+            reqs.append(dist.irecv(hi_recv, lay["hi_rank"]))
+        for r in reqs:
+            r.wait()
+        if lay["lo_rank"] >= 0:
+            nxt[0] = lo_recv.numpy()
+        if lay["hi_rank"] >= 0:
+            nxt[-1] = hi_recv.numpy()
+        cur = nxt
+    np.save(os.path.join(out_dir, f"heat_{rank}.npy"), cur[1:-1])
+    # ---- reductions over axis-0 shards
+    data = rs.randint(-8, 9, size=(10, 7)).astype(np.float32)
+    data[3, 2] = data[8, 1] = 50.0                                 # tie across the two shards
+    a, b = S.shard_range(data.shape[0], world, rank)
+    local = data[a:b]
+    part = torch.tensor([float(local.sum(dtype=np.float64))], dtype=torch.float64)
+    dist.all_reduce(part)
+    v, i = O.reduce_argmax(local)
+    pairs = [None] * world
+    dist.all_gather_object(pairs, (float(v), int(i + a * data.shape[1])))
+    best = S.combine_extremum([p[0] for p in pairs], [p[1] for p in pairs], True)
+    axis0 = torch.from_numpy(O.reduce_axis(local, 0, "sum").astype(np.float64))
+    dist.all_reduce(axis0)
+    np.save(os.path.join(out_dir, f"red_{rank}.npy"), np.array([part.item(), best[0], best[1]] + axis0.tolist()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_partitioning(tmp_path):
+    from oracle import ph_oracle as O
+    from ph_core_b200 import sharding as S
+    world, port = 2, _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    rs = np.random.RandomState(42)
+    field = (rs.rand(11, 9, 8) * 100).astype(np.float32)
+    want = field.copy()
+    for _ in range(5):
+        want = O.heat_step_nd(want, np.float32(0.1))
+    got = np.concatenate([np.load(tmp_path / f"heat_{r}.npy") for r in range(world)])
+    assert got.tobytes() == want.tobytes()                          # slabbing changes no cell's arithmetic
+    data = rs.randint(-8, 9, size=(10, 7)).astype(np.float32)
+    data[3, 2] = data[8, 1] = 50.0
+    for r in range(world):
+        red = np.load(tmp_path / f"red_{r}.npy")
+        assert red[0] == data.sum(dtype=np.float64)
+        assert (red[1], int(red[2])) == (50.0, 3 * 7 + 2)           # lower flat index wins the tie
+        assert red[3:].tolist() == data.sum(axis=0).tolist()
+
+
+def test_shard_ranges_cover_exactly():
+    from ph_core_b200 import sharding as S
+    for n in [0, 1, 7, 8, 1000, 2048]:
+        for world in [1, 2, 3, 4, 8]:
+            ranges = [S.shard_range(n, world, r) for r in range(world)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == n
+            assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in ranges]
+            assert max(sizes) - min(sizes) <= 1
+    lay = S.slab_layout(2048, 8, 0); assert lay["lo_rank"] == -1 and lay["hi_rank"] == 1 and lay["local_planes"] == 258
+    lay = S.slab_layout(2048, 8, 7); assert lay["hi_rank"] == -1 and lay["start"] == 1792
+    assert S.combine_extremum([3.0, 9.0, 9.0], [5, 40, 12], True) == (9.0, 12)
+    assert S.combine_extremum([3.0, 1.0, 1.0], [5, 40, 12], False) == (1.0, 12)
+    assert S.combine_extremum([3.0, 0.0], [5, -1], True) == (3.0, 5)    # empty shard ignored
