@@ -76,7 +76,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -124,6 +124,7 @@ def physical_gpu_index(local: int) -> int:
 def cpu_flat_sample(rows: int, reps: int):
     """oracle C port, flat loops + OpenMP on all host cores, on `rows` of the workload."""
     from oracle import c_oracle as CO
+    CO.use_all_cores()
     a, b, c = make_inputs(0, rows)
     out, tmp = np.empty_like(a), np.empty_like(a)
     CO.flat_mul_rowvec_add_f32(a, b, c, out, tmp)        # warm (page faults)
@@ -156,6 +157,7 @@ def run_reference(args):
         return
     rows = 2048                                            # 1/4 of the workload per step
     from oracle import c_oracle as CO
+    CO.use_all_cores()
     a, b, c = make_inputs(0, rows)
     out, tmp = np.empty_like(a), np.empty_like(a)
     for _ in range(max(1, args.warmup)):
@@ -234,7 +236,6 @@ def run_ours(args):
             ev[2 * i + 2].record(stream)
     barrier()
     launches = lib.ph_launch_count() - launches0
-    clocks = sampler.stop()
     total_ms = ev[0].elapsed_time(ev[-1])
     mul_ms = [ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)]
     add_ms = [ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps)]
@@ -268,20 +269,44 @@ def run_ours(args):
             view[...] = arr
         pin[name] = (p, view)
 
+    # The user-level call sequence: explicit H2D of the operands, the two operators, explicit
+    # D2H of the result.  Rows are processed in chunks on three streams so the upload of chunk
+    # i+1, the kernels of chunk i and the download of chunk i-1 overlap (PCIe is full duplex).
+    CH = 8
+    rows_per = ROWS // CH
+    streams = [torch.cuda.Stream(device=torch.device("cuda", local)) for _ in range(3)]
+    isz = 4
+
     def e2e_step():
-        ph.check(lib.ph_h2d(a.ptr, pin["a"][0], a_h.nbytes))
+        ph.check(lib.ph_set_stream(streams[0].cuda_stream))
         ph.check(lib.ph_h2d(b.ptr, pin["b"][0], b_h.nbytes))
-        ph.check(lib.ph_h2d(c.ptr, pin["c"][0], c_h.nbytes))
-        step()
-        ph.check(lib.ph_d2h(pin["out"][0], out.ptr, a_h.nbytes))      # synchronises
+        b_ready = torch.cuda.Event()
+        b_ready.record(streams[0])
+        for k in range(CH):
+            st = streams[k % 3]
+            st.wait_event(b_ready)
+            ph.check(lib.ph_set_stream(st.cuda_stream))
+            off = k * rows_per * COLS * isz
+            nb = rows_per * COLS * isz
+            ph.check(lib.ph_h2d(a.ptr + off, pin["a"][0].value + off, nb))
+            ph.check(lib.ph_h2d(c.ptr + off, pin["c"][0].value + off, nb))
+            dk = ph.PhDesc.make([rows_per, COLS], [COLS, 1], k * rows_per * COLS)
+            dbk = ph.PhDesc.make([rows_per, COLS], [0, 1], 0)
+            ph.check(lib.ph_ewise_binary(MUL, F32, a.ptr, C.byref(dk), b.ptr, C.byref(dbk), t.ptr, C.byref(dk)))
+            ph.check(lib.ph_ewise_binary(ADD, F32, t.ptr, C.byref(dk), c.ptr, C.byref(dk), out.ptr, C.byref(dk)))
+            ph.check(lib.ph_d2h_async(pin["out"][0].value + off, out.ptr + off, nb))
+        for st in streams:
+            stream.wait_stream(st)
+        ph.check(lib.ph_set_stream(None))
 
     e2e_steps = max(2, min(args.steps, 5))
     e2e_step()
     barrier()
-    t0 = time.perf_counter()
     with torch.cuda.stream(stream):
         e0.record(stream)
         for _ in range(e2e_steps):
+            for st in streams:
+                st.wait_stream(stream)
             e2e_step()
         e1.record(stream)
     barrier()
@@ -292,6 +317,7 @@ def run_ours(args):
         e2e_ms = float(tt.item())
     e2e_value = BYTES_STEP * world / (e2e_ms * 1e-3) / 1e9
     e2e_out = pin["out"][1].copy()
+    clocks = sampler.stop()          # sampled across the headline, fused and e2e timed regions
 
     # ---- parity spot check of the timed result (oracle = checker only)
     from oracle import c_oracle as CO
@@ -299,12 +325,26 @@ def run_ours(args):
     want = CO.flat_mul_rowvec_add_f32(a_h[:chk_rows].copy(), b_h, c_h[:chk_rows].copy())
     parity_ok = bool(e2e_out[:chk_rows].tobytes() == want.tobytes())
 
+    extras = None
+    if not args.no_extras:
+        try:
+            extras = run_extras(ph, lib, dist, world, rank, torch)
+        except Exception as e:                       # extras never invalidate the headline
+            extras = {"error": repr(e)}
+
     if rank == 0:
         peak, peak_src = measured_peak()
         dom_ms = statistics.mean(add_ms)
         achieved = BYTES_ADD / (dom_ms * 1e-3) / 1e9
-        cpu_flat, cores, _ = cpu_flat_sample(2048, 5)
-        cpu_ref, cpu_ref_s = cpu_ref_sample(512)
+        if world == 1:
+            cpu_flat, cores, _ = cpu_flat_sample(2048, 5)
+            cpu_ref, cpu_ref_s = cpu_ref_sample(512)
+            cpu_baseline = {"value": round(cpu_flat, 3), "unit": "GB/s", "cores": cores, "kind": "port",
+                            "sample": "2048 of 8192 rows, oracle C port: flat loops + OpenMP, median of 5",
+                            "reference_structure_1core": {"value": round(cpu_ref, 4), "unit": "GB/s", "cores": 1,
+                                                          "sample": f"512 of 8192 rows, {cpu_ref_s:.2f} s"}}
+        else:
+            cpu_baseline = None                     # timed on rank 0 at N=1 only (contract)
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": round(ms_per_step, 5), "higher_is_better": True,
@@ -323,26 +363,88 @@ def run_ours(args):
                              "achieved": round(BYTES_MUL / (statistics.mean(mul_ms) * 1e-3) / 1e9, 2)}}},
             "fused_single_pass": {"ms_per_step": round(fused_ms, 5), "algorithmic_bytes": BYTES_ADD + COLS * 4,
                                   "gbs": round((BYTES_ADD + COLS * 4) / (fused_ms * 1e-3) / 1e9, 2)},
-            "cpu_baseline": {"value": round(cpu_flat, 3), "unit": "GB/s", "cores": cores, "kind": "port",
-                             "sample": "2048 of 8192 rows, oracle C port: flat loops + OpenMP, median of 5",
-                             "reference_structure_1core": {"value": round(cpu_ref, 4), "unit": "GB/s", "cores": 1,
-                                                           "sample": f"512 of 8192 rows, {cpu_ref_s:.2f} s"}},
+            "cpu_baseline": cpu_baseline,
             "e2e": {"value": round(e2e_value, 3), "unit": "GB/s", "ms_per_step": round(e2e_ms, 4),
                     "h2d_bytes_per_step": int(a_h.nbytes + b_h.nbytes + c_h.nbytes), "d2h_bytes_per_step": int(a_h.nbytes),
-                    "steps": e2e_steps},
+                    "steps": e2e_steps, "how": "pinned host buffers; 8 row-chunks on 3 streams so H2D, kernels and D2H overlap"},
             "gpu_launches": int(launches), "clocks": clocks, "parity_spot_check": parity_ok,
+            "extras": extras,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
 
+def run_extras(ph, lib, dist, world, rank, torch):
+    """Secondary BASELINE.json configs reported beside the headline (same JSON line, key
+    `extras`): the 2048^3 f32 heat stencil slab-decomposed over the N ranks with NCCL halo
+    exchange (STRONG scaling: the grid is fixed), and the full sum of a 1e9-element f32 array
+    sharded along axis 0 with an NCCL allreduce of the per-GPU partials."""
+    from ph_core_b200 import DeviceNArray as D, sharding as S, heat
+    out = {}
+    S.comm_init(dist)
+    # ---- heat 3-D 2048^3
+    G = 2048
+    lay = S.slab_layout(G, world, rank)
+    one = np.array(1.0, np.float32)
+    coeff = np.array(0.1, np.float32)
+    steps = 10
+    if world == 1:
+        a, b = D([G, G, G], np.float32), D([G, G, G], np.float32)
+        ph.check(lib.ph_fill_region(4, a.ptr, C.byref(a.desc()), one.ctypes.data))
+        run = lambda n: heat.simulate(a, 0.1, n)
+    else:
+        shape = [lay["local_planes"], G, G]
+        a, b = D(shape, np.float32), D(shape, np.float32)
+        ph.check(lib.ph_fill_region(4, a.ptr, C.byref(a.desc()), one.ctypes.data))
+        ph.check(lib.ph_fill_region(4, b.ptr, C.byref(b.desc()), one.ctypes.data))
+        run = lambda n: S.heat_run_sharded(a, b, 0.1, n)
+    run(2)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = C.c_float()
+    ph.check(lib.ph_timer_start())
+    run(steps)
+    ph.check(lib.ph_timer_stop(C.byref(ms)))
+    t = torch.tensor([ms.value], device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    heat_ms = float(t.item()) / steps
+    out["heat3d_2048_f32"] = {"gcell_updates_per_s": round(G ** 3 / (heat_ms * 1e-3) / 1e9, 2), "ms_per_step": round(heat_ms, 4),
+                              "grid": [G, G, G], "steps": steps, "scaling": "strong",
+                              "decomposition": f"axis-0 slabs x{world}, 1-plane NCCL send/recv halos overlapped with the interior",
+                              "hbm_gbs_per_gpu": round(8 * G ** 3 / world / (heat_ms * 1e-3) / 1e9, 1)}
+    del a, b
+    # ---- full sum of 1e9 f32 sharded along axis 0
+    n_total = 1000 * 1000 * 1000
+    r0, r1 = S.shard_range(1000, world, rank)
+    x = D([r1 - r0, 1000, 1000], np.float32)
+    ph.check(lib.ph_fill_region(4, x.ptr, C.byref(x.desc()), one.ctypes.data))
+    S.reduce_full_sharded(x, "sum")
+    torch.cuda.synchronize()
+    reps = 10
+    ph.check(lib.ph_timer_start())
+    for _ in range(reps):
+        total = S.reduce_full_sharded(x, "sum")
+    ph.check(lib.ph_timer_stop(C.byref(ms)))
+    t = torch.tensor([ms.value], device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    red_ms = float(t.item()) / reps
+    out["reduce_sum_1e9_f32"] = {"gbs": round(4 * n_total / (red_ms * 1e-3) / 1e9, 1), "ms": round(red_ms, 4),
+                                 "result_ok": bool(abs(float(total) - n_total) <= 1e-4 * n_total),
+                                 "collective": "ncclAllReduce of one f32 partial per GPU" if world > 1 else "none"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the heat / reduction extras")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -22,10 +22,13 @@ ap.add_argument("--quick", action="store_true")
 ap.add_argument("--only", default="")
 ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--big-heat", action="store_true", help="include the 2048^3 f32 stencil (69 GB)")
+ap.add_argument("--heat-shape", default="", help="only run the 3-D stencil on this z,y,x grid")
 args = ap.parse_args()
 
 ph.init(0)
 lib = ph.load()
+if args.heat_shape:
+    args.only = "custom-heat"
 peak = 6546.2
 try:
     peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
@@ -83,6 +86,14 @@ def dev_rand(shape, dtype, seed):
     ph.check(lib.ph_sync())
     return d
 
+
+if args.heat_shape:
+    H3 = tuple(int(v) for v in args.heat_shape.split(","))
+    g = D(H3, np.float32)
+    ph.check(lib.ph_fill_region(4, g.ptr, C.byref(g.desc()), np.array(1.0, np.float32).ctypes.data))
+    cells = int(np.prod(H3))
+    row(f"custom-heat 3-D {H3} f32 x4 steps", 8 * cells * 4, lambda: heat.simulate(g, 0.1, 4), cells * 4, "gcell_per_s", reps=3)
+    sys.exit(0)
 
 # ------------------------------------------------------------------ config 1: elementwise 8192^2 f32
 E = (8192, 8192) if not args.quick else (2048, 8192)

@@ -30,6 +30,16 @@ def _shape(shape):
     return (C.c_int64 * len(shape))(*[int(s) for s in shape])
 
 
+def use_all_cores() -> int:
+    """Use every host core the process may run on (overrides torchrun's OMP_NUM_THREADS=1)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    load().oracle_set_threads(C.c_int(n))
+    return num_threads()
+
+
 def num_threads() -> int:
     return int(load().oracle_num_threads())
 

@@ -22,6 +22,15 @@
 
 #define MAXR 8
 
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline wants every host core it can use */
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -54,9 +54,15 @@ __device__ __forceinline__ T heat_cell(T c, T zl, T zh, T yl, T yh, T xl, T xh, 
 
 // RANK 3: block = 32 lanes (x, E cells each) x HEAT_TY warps (consecutive y rows).
 // RANK 2: block = 32 lanes x HEAT_TY warps, every warp owns its own x tile (no y axis).
+//
+// The loop is written for a low instruction count (the first version was issue-bound at
+// ~48 instructions per cell): pointers advance by one plane per iteration, the y-halo rows
+// travel through the same shared-memory exchange as the tile rows (rows 0 and TY+1), all
+// halo loads are issued one plane ahead, inactive threads read clamped addresses instead of
+// branching, and the fixed-boundary test is three per-thread flags.
 template <typename T, int E, int RANK>
 __global__ void __launch_bounds__(32 * HEAT_TY) heat_march_kernel(const HeatArgs<T> a) {
-  __shared__ Group<T, E> rows[2][HEAT_TY][32];
+  __shared__ Group<T, E> rows[2][HEAT_TY + 2][32];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   int64_t x0, y;
@@ -71,156 +77,91 @@ __global__ void __launch_bounds__(32 * HEAT_TY) heat_march_kernel(const HeatArgs
   const int64_t ze = (zb + a.z_chunk < a.z_end) ? zb + a.z_chunk : a.z_end;
   if (zb >= ze) return;
   const bool active = x0 < a.n2 && y < a.n1;       // n2 % E == 0 by dispatch: whole groups
+  const int64_t xc = active ? x0 : a.n2 - E;       // clamped: inactive threads load valid data
+  const int64_t yc = (y < a.n1) ? y : a.n1 - 1;
   const int64_t plane = a.n1 * a.n2;
-  const int64_t row_off = y * a.n2 + x0;
-  const bool y_edge = (RANK == 3) && (y == 0 || y == a.n1 - 1);
-  // in-plane halo sources (clamped so the address is always valid; unused on boundaries)
-  const int64_t y_up = (y > 0 ? y - 1 : y) * a.n2 + x0;
-  const int64_t y_dn = (y + 1 < a.n1 ? y + 1 : y) * a.n2 + x0;
-  const bool need_up_global = (RANK == 3) && (warp == 0);
-  const bool need_dn_global = (RANK == 3) && (warp == HEAT_TY - 1 || y + 1 >= a.n1);
+  const bool fix_all = (RANK == 3) && (yc == 0 || yc == a.n1 - 1);
+  const bool fix_first = (xc == 0), fix_last = (xc + E == a.n2);
+  // y halo: warp 0 fetches the row above the tile, the last warp the row below it
+  const bool halo_up = (RANK == 3) && warp == 0;
+  const bool halo_dn = (RANK == 3) && warp == HEAT_TY - 1;
+  const int64_t yh = halo_up ? (yc > 0 ? yc - 1 : yc) : (yc + 1 < a.n1 ? yc + 1 : yc);
+  const int halo_row = halo_up ? 0 : HEAT_TY + 1;
+  // x halo: lane 0 fetches the cell left of the warp's span, lane 31 the cell right of it
+  const bool xh_left = lane == 0, xh_right = lane == 31;
+  const int64_t xh = xh_left ? (xc > 0 ? xc - 1 : xc) : (xc + E < a.n2 ? xc + E : xc);
 
-  Group<T, E> prev, cur, next;
-  Group<T, E> up_c, dn_c, up_n, dn_n;              // y-halo rows of the current / next plane (edge warps)
-  T xl_c = (T)0, xr_c = (T)0, xl_n = (T)0, xr_n = (T)0;
-  const bool left_halo = active && lane == 0 && x0 > 0;
-  const bool right_halo = active && lane == 31 && x0 + E < a.n2;
-  if (active) {
-    prev = load_group<T, E>(a.in + (zb - 1) * plane + row_off);
-    cur = load_group<T, E>(a.in + zb * plane + row_off);
-  } else {
-    prev = splat_group<T, E>((T)0);
-    cur = prev;
-  }
-  up_c = cur; dn_c = cur;
-  {
-    const T* pz = a.in + zb * plane;
-    if (active && need_up_global) up_c = load_group_plain<T, E>(pz + y_up);
-    if (active && need_dn_global) dn_c = load_group_plain<T, E>(pz + y_dn);
-    if (left_halo) xl_c = pz[y * a.n2 + x0 - 1];
-    if (right_halo) xr_c = pz[y * a.n2 + x0 + E];
-  }
+  const T* p_next = a.in + zb * plane + yc * a.n2 + xc;       // -> plane z of this thread's group
+  const T* p_halo = a.in + zb * plane + yh * a.n2 + xc;       // -> plane z of the halo row
+  const T* p_xh = a.in + zb * plane + yc * a.n2 + xh;         // -> plane z of the x-halo cell
+  T* p_out = a.out + zb * plane + yc * a.n2 + xc;
+
+  // Register pipeline over planes: P = z-1, C = z, N = z+1 are needed by the stencil at z; F = z+2
+  // is requested now and first used one step later, so one full step of work hides its latency.
+  const T* p_last = a.in + (a.n0 - 1) * plane + yc * a.n2 + xc;     // clamp for the final look-ahead
+  Group<T, E> g0 = load_group<T, E>(p_next - plane);     // plane z-1
+  Group<T, E> g1 = load_group<T, E>(p_next);             // plane z
+  p_next += plane;
+  Group<T, E> g2 = load_group<T, E>(p_next);             // plane z+1
+  Group<T, E> g3;                                        // plane z+2
+  Group<T, E> halo = g1;
+  if (halo_up || halo_dn) halo = load_group_plain<T, E>(p_halo);
+  T xhv = (xh_left || xh_right) ? *p_xh : (T)0;
   int buf = 0;
-  for (int64_t z = zb; z < ze; z++) {
-    // everything plane z+1 needs is requested now and consumed one iteration later
-    const T* pn = a.in + (z + 1) * plane;
-    next = active ? load_group<T, E>(pn + row_off) : splat_group<T, E>((T)0);   // streamed once: no L1 allocation
-    up_n = next; dn_n = next;
+  int64_t z = zb;
+  // one plane; the caller rotates which register group plays which role (four steps per trip),
+  // so there are no register-to-register copies
+  auto step = [&](const Group<T, E>& P, const Group<T, E>& C, const Group<T, E>& N, Group<T, E>& F) {
+    p_next += plane; p_halo += plane; p_xh += plane;
+    F = load_group<T, E>(p_next <= p_last ? p_next : p_last);
+    Group<T, E> halo_n = C;
+    T xhv_n = (T)0;
     if (z + 1 < ze) {
-      if (active && need_up_global) up_n = load_group_plain<T, E>(pn + y_up);
-      if (active && need_dn_global) dn_n = load_group_plain<T, E>(pn + y_dn);
-      if (left_halo) xl_n = pn[y * a.n2 + x0 - 1];
-      if (right_halo) xr_n = pn[y * a.n2 + x0 + E];
+      if (halo_up || halo_dn) halo_n = load_group_plain<T, E>(p_halo);
+      if (xh_left || xh_right) xhv_n = *p_xh;
     }
-    Group<T, E> up = up_c, dn = dn_c;
+    Group<T, E> up = C, dn = C;
     if (RANK == 3) {
-      rows[buf][warp][lane] = cur;
+      rows[buf][warp + 1][lane] = C;
+      if (halo_up || halo_dn) rows[buf][halo_row][lane] = halo;
       __syncthreads();
-      if (!need_up_global) up = rows[buf][warp - 1][lane];
-      if (!need_dn_global) dn = rows[buf][warp + 1][lane];
+      up = rows[buf][warp][lane];
+      dn = rows[buf][warp + 2][lane];
     }
-    T xl = xl_c, xr = xr_c;
-    const T from_left = __shfl_up_sync(0xffffffffu, cur.v[E - 1], 1);
-    const T from_right = __shfl_down_sync(0xffffffffu, cur.v[0], 1);
-    if (lane != 0) xl = from_left;
-    if (lane != 31) xr = from_right;
-    if (active) {
-      Group<T, E> res;
+    const T from_left = __shfl_up_sync(0xffffffffu, C.v[E - 1], 1);
+    const T from_right = __shfl_down_sync(0xffffffffu, C.v[0], 1);
+    const T xl = xh_left ? xhv : from_left;
+    const T xr = xh_right ? xhv : from_right;
+    Group<T, E> res = C;
+    if (!fix_all) {                                      // warp-uniform
 #pragma unroll
       for (int i = 0; i < E; i++) {
-        const T c = cur.v[i];
-        const T l = (i > 0) ? cur.v[i - 1] : xl;
-        const T r = (i < E - 1) ? cur.v[i + 1] : xr;
-        const int64_t x = x0 + i;
-        const bool fixed = y_edge || x == 0 || x == a.n2 - 1;
-        const T v = heat_cell<T>(c, prev.v[i], next.v[i], up.v[i], dn.v[i], l, r, a.coeff, RANK);
-        res.v[i] = fixed ? c : v;
+        const T l = (i > 0) ? C.v[i - 1] : xl;
+        const T r = (i < E - 1) ? C.v[i + 1] : xr;
+        res.v[i] = heat_cell<T>(C.v[i], P.v[i], N.v[i], up.v[i], dn.v[i], l, r, a.coeff, RANK);
       }
-      store_group<T, E>(a.out + z * plane + row_off, res);
+      if (fix_first) res.v[0] = C.v[0];
+      if (fix_last) res.v[E - 1] = C.v[E - 1];
     }
-    prev = cur;
-    cur = next;
-    up_c = up_n; dn_c = dn_n; xl_c = xl_n; xr_c = xr_n;
+    if (active) store_group<T, E>(p_out, res);
+    p_out += plane;
+    halo = halo_n;
+    xhv = xhv_n;
     buf ^= 1;
+    z++;
+  };
+  while (z + 4 <= ze) {
+    step(g0, g1, g2, g3);
+    step(g1, g2, g3, g0);
+    step(g2, g3, g0, g1);
+    step(g3, g0, g1, g2);
   }
-}
-
-// ---- v1 (halo loads consumed in the same iteration, L1-allocating loads): kept for A/B runs
-// RANK 3: block = 32 lanes (x, E cells each) x HEAT_TY warps (consecutive y rows).
-// RANK 2: block = 32 lanes x HEAT_TY warps, every warp owns its own x tile (no y axis).
-template <typename T, int E, int RANK>
-__global__ void __launch_bounds__(32 * HEAT_TY) heat_march_kernel_v1(const HeatArgs<T> a) {
-  __shared__ Group<T, E> rows[2][HEAT_TY][32];
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  int64_t x0, y;
-  if (RANK == 3) {
-    x0 = ((int64_t)blockIdx.x * 32 + lane) * E;
-    y = (int64_t)blockIdx.y * HEAT_TY + warp;
-  } else {
-    x0 = (((int64_t)blockIdx.x * HEAT_TY + warp) * 32 + lane) * E;
-    y = 0;
-  }
-  const int64_t zb = a.z_begin + (int64_t)blockIdx.z * a.z_chunk;
-  const int64_t ze = (zb + a.z_chunk < a.z_end) ? zb + a.z_chunk : a.z_end;
-  if (zb >= ze) return;
-  const bool active = x0 < a.n2 && y < a.n1;       // n2 % E == 0 by dispatch: whole groups
-  const int64_t plane = a.n1 * a.n2;
-  const int64_t row_off = y * a.n2 + x0;
-  const bool y_edge = (RANK == 3) && (y == 0 || y == a.n1 - 1);
-  // in-plane halo sources (clamped so the address is always valid; unused on boundaries)
-  const int64_t y_up = (y > 0 ? y - 1 : y) * a.n2 + x0;
-  const int64_t y_dn = (y + 1 < a.n1 ? y + 1 : y) * a.n2 + x0;
-  const bool need_up_global = (RANK == 3) && (warp == 0);
-  const bool need_dn_global = (RANK == 3) && (warp == HEAT_TY - 1 || y + 1 >= a.n1);
-
-  Group<T, E> prev, cur, next;
-  if (active) {
-    prev = load_group_plain<T, E>(a.in + (zb - 1) * plane + row_off);
-    cur = load_group_plain<T, E>(a.in + zb * plane + row_off);
-  } else {
-    prev = splat_group<T, E>((T)0);
-    cur = prev;
-  }
-  int buf = 0;
-  for (int64_t z = zb; z < ze; z++) {
-    const T* pz = a.in + z * plane;
-    next = active ? load_group_plain<T, E>(pz + plane + row_off) : splat_group<T, E>((T)0);
-    Group<T, E> up = cur, dn = cur;
-    T xl = (T)0, xr = (T)0;
-    if (active) {
-      if (need_up_global) up = load_group_plain<T, E>(pz + y_up);
-      if (need_dn_global) dn = load_group_plain<T, E>(pz + y_dn);
-      if (lane == 0 && x0 > 0) xl = pz[y * a.n2 + x0 - 1];
-      if (lane == 31 && x0 + E < a.n2) xr = pz[y * a.n2 + x0 + E];
+  if (z < ze) {
+    step(g0, g1, g2, g3);
+    if (z < ze) {
+      step(g1, g2, g3, g0);
+      if (z < ze) step(g2, g3, g0, g1);
     }
-    if (RANK == 3) {
-      rows[buf][warp][lane] = cur;
-      __syncthreads();
-      if (!need_up_global) up = rows[buf][warp - 1][lane];
-      if (!need_dn_global) dn = rows[buf][warp + 1][lane];
-    }
-    const T from_left = __shfl_up_sync(0xffffffffu, cur.v[E - 1], 1);
-    const T from_right = __shfl_down_sync(0xffffffffu, cur.v[0], 1);
-    if (lane != 0) xl = from_left;
-    if (lane != 31) xr = from_right;
-    if (active) {
-      Group<T, E> res;
-#pragma unroll
-      for (int i = 0; i < E; i++) {
-        const T c = cur.v[i];
-        const T l = (i > 0) ? cur.v[i - 1] : xl;
-        const T r = (i < E - 1) ? cur.v[i + 1] : xr;
-        const int64_t x = x0 + i;
-        const bool fixed = y_edge || x == 0 || x == a.n2 - 1;
-        const T v = heat_cell<T>(c, prev.v[i], next.v[i], up.v[i], dn.v[i], l, r, a.coeff, RANK);
-        res.v[i] = fixed ? c : v;
-      }
-      store_group<T, E>(a.out + z * plane + row_off, res);
-    }
-    prev = cur;
-    cur = next;
-    buf ^= 1;
   }
 }
 
@@ -307,13 +248,6 @@ static int32_t launch_march(const T* in, T* out, int64_t n0, int64_t n1, int64_t
   gz = ceil_div(planes, a.z_chunk);
   if (gy > 65535 || gz > 65535) return set_error(PH_ERR_INVALID, "heat grid too large for one launch");
   dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)gz), block(32 * HEAT_TY);
-  static const int variant = getenv("PH_HEAT_VARIANT") ? atoi(getenv("PH_HEAT_VARIANT")) : 2;
-  if (variant == 1) {
-    if (e == EV && EV > 1) heat_march_kernel_v1<T, EV, RANK><<<grid, block, 0, stream>>>(a);
-    else heat_march_kernel_v1<T, 1, RANK><<<grid, block, 0, stream>>>(a);
-    PH_LAUNCH_CHECK("heat_march_kernel_v1");
-    return PH_OK;
-  }
   if (e == EW && EW != EV) heat_march_kernel<T, EW, RANK><<<grid, block, 0, stream>>>(a);
   else if (e == EV && EV > 1) heat_march_kernel<T, EV, RANK><<<grid, block, 0, stream>>>(a);
   else heat_march_kernel<T, 1, RANK><<<grid, block, 0, stream>>>(a);
@@ -321,11 +255,21 @@ static int32_t launch_march(const T* in, T* out, int64_t n0, int64_t n1, int64_t
   return PH_OK;
 }
 
+// heat_tma.cu: TMA-fed shared-memory pipeline (preferred for rank 3 when the shape allows)
+template <typename T>
+int32_t heat_tma_planes(const T* in, T* out, int64_t n0, int64_t n1, int64_t n2, T coeff, int64_t z_begin,
+                        int64_t z_end, cudaStream_t stream, bool* used);
+
 // one step on planes [z_begin, z_end) of a rank-2/3 grid; boundary planes are NOT touched
 template <typename T>
 static int32_t heat_planes(int rank, const int64_t* ext, T coeff, const T* in, T* out, int64_t z_begin,
                            int64_t z_end, cudaStream_t stream) {
-  if (rank == 3) return launch_march<T, 3>(in, out, ext[0], ext[1], ext[2], coeff, z_begin, z_end, stream);
+  if (rank == 3) {
+    bool used = false;
+    int32_t st = heat_tma_planes<T>(in, out, ext[0], ext[1], ext[2], coeff, z_begin, z_end, stream, &used);
+    if (st != PH_OK || used) return st;
+    return launch_march<T, 3>(in, out, ext[0], ext[1], ext[2], coeff, z_begin, z_end, stream);
+  }
   return launch_march<T, 2>(in, out, ext[0], 1, ext[1], coeff, z_begin, z_end, stream);
 }
 

@@ -199,6 +199,14 @@ int32_t ph_d2h(void* dst_host, const void* src_dev, size_t nbytes) {
   return PH_OK;
 }
 
+int32_t ph_d2h_async(void* dst_host, const void* src_dev, size_t nbytes) {
+  PH_REQUIRE_INIT();
+  if (nbytes == 0) return PH_OK;
+  if (!dst_host || !src_dev) return set_error(PH_ERR_INVALID, "null pointer in ph_d2h_async");
+  PH_CUDA(cudaMemcpyAsync(dst_host, src_dev, nbytes, cudaMemcpyDeviceToHost, rt().stream));
+  return PH_OK;
+}
+
 int32_t ph_d2d(void* dst_dev, const void* src_dev, size_t nbytes) {
   PH_REQUIRE_INIT();
   if (nbytes == 0) return PH_OK;

@@ -1,7 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for v in "1 16" "2 16" "2 32"; do set -- $v; echo "variant $1 bytes $2"; PH_HEAT_VARIANT=$1 PH_HEAT_GROUP_BYTES=$2 timeout 300 python benchmarks/bench_kernels.py --only "heat 3-D" 2>&1 | cut -c1-200; done
-PH_HEAT_VARIANT=1 PH_HEAT_GROUP_BYTES=16 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"heat_march" -s 4 -c 2 -o gpurun_out/prof_heat_v1 -f python benchmarks/bench_kernels.py --quick --only "heat 3-D" --reps 1 > gpurun_out/ncu_heat1.log 2>&1
-PH_HEAT_VARIANT=2 PH_HEAT_GROUP_BYTES=16 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"heat_march" -s 4 -c 2 -o gpurun_out/prof_heat_v2 -f python benchmarks/bench_kernels.py --quick --only "heat 3-D" --reps 1 > gpurun_out/ncu_heat2.log 2>&1
-PH_HEAT_VARIANT=2 PH_HEAT_GROUP_BYTES=32 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"heat_march" -s 4 -c 2 -o gpurun_out/prof_heat_v2w -f python benchmarks/bench_kernels.py --quick --only "heat 3-D" --reps 1 > gpurun_out/ncu_heat2w.log 2>&1
-ls gpurun_out | grep heat
+for ty in 16 32; do
+echo "TMA rows $ty"
+PH_HEAT_TMA_ROWS=$ty timeout 300 python -m pytest tests/test_gpu_heat.py -m gpu -q --timeout 120 -x 2>&1 | tail -1
+PH_HEAT_TMA_ROWS=$ty timeout 300 python benchmarks/bench_kernels.py --heat-shape 1024,1024,1024 2>&1 | cut -c1-200
+PH_HEAT_TMA_ROWS=$ty timeout 300 python benchmarks/bench_kernels.py --heat-shape 2048,2048,2048 2>&1 | cut -c1-200
+done
+PH_HEAT_TMA_ROWS=16 timeout 900 ncu --set full --clock-control none -k regex:"heat_tma" -s 4 -c 1 -o gpurun_out/prof_heat_tma_2k16 -f python benchmarks/bench_kernels.py --heat-shape 256,2048,2048 --reps 1 > gpurun_out/ncu_heat_tma.log 2>&1
