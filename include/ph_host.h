@@ -57,6 +57,12 @@ int32_t ph_canonicalize_coord(const int64_t* coord, int32_t ncoord, const int64_
 /* IndexRegion.new(region_literal, bound_shape, drop) (index_region.cr:192-224) */
 int32_t ph_region_new(const ph_range_lit* lits, int32_t nlits, const int64_t* bound_shape, int32_t rank,
                       int32_t drop, ph_region* out);
+/* IndexRegion.new(region_literal, bound_shape, drop, trim_to:) (index_region.cr:133-168):
+ * infer (no bounds check) against `bound_shape`, then trim! to `trim_to`.  `bound_shape` may
+ * be NULL (absolute literals only: a negative index raises IndexError).  Used by
+ * MultiIndexable#get_available (multi_indexable.cr:411-413). */
+int32_t ph_region_new_trimmed(const ph_range_lit* lits, int32_t nlits, const int64_t* bound_shape,
+                              const int64_t* trim_to, int32_t rank, int32_t drop, ph_region* out);
 /* IndexRegion.cover (index_region.cr:232-238) */
 int32_t ph_region_cover(const int64_t* bound_shape, int32_t rank, int32_t drop, ph_region* out);
 /* IndexRegion#fits_in? (:468-478): *fits = 0/1 */

@@ -146,6 +146,7 @@ def load() -> C.CDLL:
         "ph_canonicalize_coord": [i64p, i32, i64p, i32, i64p],
         "ph_region_new": [lp, i32, i64p, i32, i32, rp],
         "ph_region_cover": [i64p, i32, i32, rp],
+        "ph_region_new_trimmed": [lp, i32, i64p, i64p, i32, i32, rp],
         "ph_region_fits_in": [rp, i64p, i32, i32p],
         "ph_region_trim": [rp, i64p, i32], "ph_region_reverse": [rp], "ph_region_translate": [rp, i64p, i32],
         "ph_shapes_compatible": [i64p, i32, i64p, i32, i32p],

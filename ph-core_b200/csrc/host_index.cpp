@@ -145,6 +145,36 @@ int32_t ph_region_new(const ph_range_lit* lits, int32_t nlits, const int64_t* bo
   return PH_HOST_OK;
 }
 
+int32_t ph_region_new_trimmed(const ph_range_lit* lits, int32_t nlits, const int64_t* bound_shape,
+                              const int64_t* trim_to, int32_t rank, int32_t drop, ph_region* out) {
+  if (!out || (nlits > 0 && !lits) || (rank > 0 && !trim_to)) return fail(PH_HOST_INVALID, "null argument");
+  if (rank > PH_MAX_RANK || nlits > rank) return fail(PH_HOST_DIMENSION_ERROR, "region literal has more dimensions than the shape");
+  const bool allow_relative = bound_shape != nullptr;
+  const int64_t* bound = allow_relative ? bound_shape : trim_to;
+  memset(out, 0, sizeof(*out));
+  out->rank = rank;
+  out->drop = drop ? 1 : 0;
+  for (int i = 0; i < nlits; i++) {
+    const ph_range_lit& l = lits[i];
+    if (!allow_relative) {                        // RangeSyntax.ensure_nonnegative (range_syntax.cr:71-82)
+      const bool neg = l.is_index ? l.first < 0 : ((l.has_first && l.first < 0) || (l.has_last && l.last < 0));
+      if (neg) return fail(PH_HOST_INDEX_ERROR, "Negative indices have no meaning when a bounding shape is not provided.");
+    }
+    Axis ax = {0, 0, 0, 0};
+    int32_t st = infer_axis(l, bound[i], ax);
+    if (st != PH_HOST_OK) return st;
+    out->first[i] = ax.first; out->step[i] = ax.step; out->last[i] = ax.last; out->proper_shape[i] = ax.size;
+    out->degeneracy[i] = (l.is_index && drop) ? 1 : 0;
+  }
+  for (int i = nlits; i < rank; i++) {
+    out->first[i] = 0; out->step[i] = 1;
+    out->last[i] = bound[i] - 1;
+    out->proper_shape[i] = bound[i];
+  }
+  finish_region(*out);
+  return ph_region_trim(out, trim_to, rank);
+}
+
 int32_t ph_region_cover(const int64_t* bound_shape, int32_t rank, int32_t drop, ph_region* out) {
   if (!out || (rank > 0 && !bound_shape) || rank > PH_MAX_RANK) return fail(PH_HOST_INVALID, "bad argument");
   memset(out, 0, sizeof(*out));

@@ -380,87 +380,67 @@ __global__ void __launch_bounds__(RED_THREADS) axis_strip_kernel(const T* __rest
 // inner == 1: each row of K contiguous elements is reduced by TX cooperating threads (TX a
 // power of two; <= 32 combines with shuffles, larger through shared memory).  Lanes read
 // consecutive 32-byte groups (E elements), UNROLL groups in flight per lane.
+// min/max/arg*: pass 1 finds the row extremum M (one max.NaN per element for f32); the index of
+// its FIRST occurrence -- needed for arg*, and for max/min only when M is a zero whose sign
+// depends on which zero came first -- is found by a second pass over the L1/L2-resident row.
 template <typename T, int E, int RED>
 __global__ void __launch_bounds__(RED_THREADS) axis_row_kernel(const T* __restrict__ x, void* __restrict__ out,
                                                                int64_t rows, int64_t K, int tx, int tx_log2,
                                                                uint32_t* __restrict__ flags) {
   constexpr bool IS_MAXLIKE = (RED == PH_MAX || RED == PH_ARGMAX);
+  constexpr bool IS_ARG = (RED == PH_ARGMAX || RED == PH_ARGMIN);
   constexpr int UNROLL = 4;
   using A = typename Acc<T>::type;
+  __shared__ A sh_s[RED_THREADS], sh_p[RED_THREADS], sh_n[RED_THREADS];
+  __shared__ T sh_m[RED_THREADS];
+  __shared__ int32_t sh_i[RED_THREADS];
   const int lane = threadIdx.x & (tx - 1);
   const int ty = threadIdx.x >> tx_log2;
   const int TY = RED_THREADS >> tx_log2;
+  const int b0 = ty << tx_log2;
   const int64_t row = (int64_t)blockIdx.x * TY + ty;
   const bool live = row < rows;
   const T* p = x + (live ? row : 0) * K;
+  const int64_t groups = K / E;                   // K % E == 0 by dispatch (E == 1 otherwise)
   bool nan = false;
   uint32_t err = 0;
-  A s = 0, pos = 0, neg = 0;
-  T bv = IS_MAXLIKE ? lowest_of<T>() : highest_of<T>();
-  int32_t bi = INT32_MAX;
-  auto fold = [&](const Group<T, E>& g, int32_t k0) {
+
+  if constexpr (RED == PH_SUM) {
+    A s = 0, pos = 0, neg = 0;
+    auto fold = [&](const Group<T, E>& g) {
 #pragma unroll
-    for (int i = 0; i < E; i++) {
-      const T v = g.v[i];
-      if constexpr (RED == PH_SUM) {
+      for (int i = 0; i < E; i++) {
+        const T v = g.v[i];
         if constexpr (is_float_t<T>::value) s = f_add(s, v);
         else { s += (A)v; if (v > 0) pos += (A)v; else neg += (A)v; }
-      } else {
-        if constexpr (is_float_t<T>::value) nan |= (v != v);
-        // k grows monotonically inside a lane: strict comparison keeps the first extremum
-        const bool take = (IS_MAXLIKE ? (v > bv) : (v < bv)) || (bi == INT32_MAX && v == bv);
-        if (take) { bv = v; bi = k0 + i; }
       }
-    }
-  };
-  if (live) {
-    const int64_t groups = K / E;                 // K % E == 0 by dispatch (E == 1 otherwise)
-    int64_t g0 = lane;
-    for (; g0 + (int64_t)(UNROLL - 1) * tx < groups; g0 += (int64_t)UNROLL * tx) {
-      Group<T, E> g[UNROLL];
+    };
+    if (live) {
+      int64_t g0 = lane;
+      for (; g0 + (int64_t)(UNROLL - 1) * tx < groups; g0 += (int64_t)UNROLL * tx) {
+        Group<T, E> g[UNROLL];
 #pragma unroll
-      for (int u = 0; u < UNROLL; u++) g[u] = load_group<T, E>(p + (g0 + (int64_t)u * tx) * E);
+        for (int u = 0; u < UNROLL; u++) g[u] = load_group<T, E>(p + (g0 + (int64_t)u * tx) * E);
 #pragma unroll
-      for (int u = 0; u < UNROLL; u++) fold(g[u], (int32_t)((g0 + (int64_t)u * tx) * E));
+        for (int u = 0; u < UNROLL; u++) fold(g[u]);
+      }
+      for (; g0 < groups; g0 += tx) fold(load_group<T, E>(p + g0 * E));
     }
-    for (; g0 < groups; g0 += tx) fold(load_group<T, E>(p + g0 * E), (int32_t)(g0 * E));
-  }
-  Cand<T> best; best.v = bv; best.i = (bi == INT32_MAX) ? INT64_MAX : (int64_t)bi;
-  if (tx <= 32) {
-    for (int off = tx >> 1; off > 0; off >>= 1) {
-      if constexpr (RED == PH_SUM) {
+    if (tx <= 32) {
+      for (int off = tx >> 1; off > 0; off >>= 1) {
         if constexpr (is_float_t<T>::value) s = f_add(s, shfl_xor_t<A>(s, off));
-        else {
-          s += shfl_xor_t<A>(s, off); pos += shfl_xor_t<A>(pos, off);
-          neg += shfl_xor_t<A>(neg, off);
-        }
-      } else {
-        Cand<T> o;
-        o.v = __shfl_xor_sync(0xffffffffu, best.v, off);
-        o.i = __shfl_xor_sync(0xffffffffu, best.i, off);
-        best = better<T, IS_MAXLIKE>(best, o);
+        else { s += shfl_xor_t<A>(s, off); pos += shfl_xor_t<A>(pos, off); neg += shfl_xor_t<A>(neg, off); }
       }
-    }
-  } else {
-    __shared__ A sh_s[RED_THREADS], sh_p[RED_THREADS], sh_n[RED_THREADS];
-    __shared__ Cand<T> sh_c[RED_THREADS];
-    if constexpr (RED == PH_SUM) { sh_s[threadIdx.x] = s; sh_p[threadIdx.x] = pos; sh_n[threadIdx.x] = neg; }
-    else sh_c[threadIdx.x] = best;
-    __syncthreads();
-    if (lane == 0) {
-      const int b0 = ty << tx_log2;
-      for (int j = 1; j < tx; j++) {
-        if constexpr (RED == PH_SUM) {
+    } else {
+      sh_s[threadIdx.x] = s; sh_p[threadIdx.x] = pos; sh_n[threadIdx.x] = neg;
+      __syncthreads();
+      if (lane == 0)
+        for (int j = 1; j < tx; j++) {
           if constexpr (is_float_t<T>::value) s = f_add(s, sh_s[b0 + j]);
           else { s += sh_s[b0 + j]; pos += sh_p[b0 + j]; neg += sh_n[b0 + j]; }
-        } else {
-          best = better<T, IS_MAXLIKE>(best, sh_c[b0 + j]);
         }
-      }
     }
-  }
-  if (lane == 0 && live) {
-    if constexpr (RED == PH_SUM) {
+    if (lane == 0 && live) {
       if constexpr (!is_float_t<T>::value) {
         // checked fold: overflow at ANY prefix raises.  sum(positives) / sum(negatives) inside T
         // proves no prefix can leave T; otherwise lane 0 replays the row in order (rare).
@@ -471,10 +451,61 @@ __global__ void __launch_bounds__(RED_THREADS) axis_row_kernel(const T* __restri
         }
       }
       reinterpret_cast<T*>(out)[row] = (T)s;
-    } else if constexpr (RED == PH_ARGMAX || RED == PH_ARGMIN) {
-      reinterpret_cast<int64_t*>(out)[row] = best.i;
+    }
+  } else {
+    // ---- pass 1: row extremum
+    T m = IS_MAXLIKE ? lowest_of<T>() : highest_of<T>();
+    auto fold = [&](const Group<T, E>& g) {
+#pragma unroll
+      for (int i = 0; i < E; i++) m = ext2<T, IS_MAXLIKE>(m, g.v[i], nan);
+    };
+    if (live) {
+      int64_t g0 = lane;
+      for (; g0 + (int64_t)(UNROLL - 1) * tx < groups; g0 += (int64_t)UNROLL * tx) {
+        Group<T, E> g[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) g[u] = load_group_plain<T, E>(p + (g0 + (int64_t)u * tx) * E);
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) fold(g[u]);
+      }
+      for (; g0 < groups; g0 += tx) fold(load_group_plain<T, E>(p + g0 * E));
+    }
+    if (tx <= 32) {
+      for (int off = tx >> 1; off > 0; off >>= 1) m = ext2<T, IS_MAXLIKE>(m, __shfl_xor_sync(0xffffffffu, m, off), nan);
     } else {
-      reinterpret_cast<T*>(out)[row] = best.v;
+      sh_m[threadIdx.x] = m;
+      __syncthreads();
+      m = sh_m[b0];
+      for (int j = 1; j < tx; j++) m = ext2<T, IS_MAXLIKE>(m, sh_m[b0 + j], nan);
+    }
+    if constexpr (std::is_same<T, float>::value) nan |= (m != m);
+    // ---- pass 2: index of the first element equal to M (arg*, or a zero extremum)
+    int32_t bi = INT32_MAX;
+    const bool need_index = IS_ARG || (is_float_t<T>::value && m == (T)0);
+    if (live && need_index && !nan) {
+      for (int64_t g0 = lane; g0 < groups; g0 += tx) {
+        if (bi != INT32_MAX) break;               // k grows inside a lane: the first hit is the lane's first
+        const Group<T, E> g = load_group_plain<T, E>(p + g0 * E);
+#pragma unroll
+        for (int i = 0; i < E; i++)
+          if (bi == INT32_MAX && g.v[i] == m) bi = (int32_t)(g0 * E) + i;
+      }
+    }
+    if (tx <= 32) {
+      for (int off = tx >> 1; off > 0; off >>= 1) {
+        const int32_t o = __shfl_xor_sync(0xffffffffu, bi, off);
+        bi = o < bi ? o : bi;
+      }
+    } else {
+      __syncthreads();
+      sh_i[threadIdx.x] = bi;
+      __syncthreads();
+      if (lane == 0)
+        for (int j = 1; j < tx; j++) bi = sh_i[b0 + j] < bi ? sh_i[b0 + j] : bi;
+    }
+    if (lane == 0 && live) {
+      if constexpr (IS_ARG) reinterpret_cast<int64_t*>(out)[row] = (bi == INT32_MAX) ? 0 : (int64_t)bi;
+      else reinterpret_cast<T*>(out)[row] = (need_index && bi != INT32_MAX) ? p[bi] : m;   // keeps the first zero's sign
     }
   }
   if (err) atomicOr(flags, err);
@@ -601,7 +632,7 @@ static int32_t reduce_axis_launch(const T* x, void* out, int64_t outer, int64_t 
     constexpr int E32 = 32 / (int)sizeof(T), E16 = 16 / (int)sizeof(T);
     constexpr bool ARG = (RED == PH_ARGMAX || RED == PH_ARGMIN);
     const uintptr_t xa = (uintptr_t)x, oa = (uintptr_t)out;
-    const bool can32 = !ARG && inner % E32 == 0 && xa % 32 == 0 && oa % 32 == 0;
+    const bool can32 = inner % E32 == 0 && xa % 32 == 0 && (ARG || oa % 32 == 0);
     const bool can16 = inner % E16 == 0 && xa % 16 == 0 && (ARG || oa % 16 == 0);
     // widest group that still leaves >= 512 threads per SM in flight
     const int64_t want_threads = (int64_t)r.sm_count * 512;

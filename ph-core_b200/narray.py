@@ -194,6 +194,28 @@ class _Indexable:
             check(_lib.load().ph_copy_strided(self.dtype.itemsize, self.ptr, C.byref(src), out.ptr, C.byref(out.desc())))
         return out
 
+    def get_available(self, literal: Sequence, drop: bool = True):
+        """MultiIndexable#get_available (:411-413): the literal is trimmed to fit, never raises
+        for an over-long range."""
+        lits = [_region.marshal(l) for l in literal]
+        arr = (PhRangeLit * max(1, len(lits)))(*lits)
+        reg = PhRegion()
+        host_check(_lib.load().ph_region_new_trimmed(arr, len(lits), _i64(self.shape), _i64(self.shape),
+                                                     len(self.shape), int(drop), C.byref(reg)))
+        return self.unsafe_fetch_chunk(reg)
+
+    def has_region(self, literal: Sequence, drop: bool = True) -> bool:
+        """MultiIndexable#has_region? (:313-318)."""
+        try:
+            make_region(literal, self.shape, drop)
+            return True
+        except (CrIndexError, DimensionError):
+            return False
+
+    def get_chunk_or_none(self, literal: Sequence, drop: bool = True):
+        """MultiIndexable#[]? (:540-546): nil instead of raising."""
+        return self.get_chunk(literal, drop) if self.has_region(literal, drop) else None
+
     def __getitem__(self, key):
         if isinstance(key, _Indexable):                      # narr[mask] returns self (:479-481)
             return self
@@ -445,6 +467,7 @@ class _Indexable:
     def __ge__(self, o): return self._compare(">=", o)
     def __le__(self, o): return self._compare("<=", o)
     def eq(self, o): return self._compare("==", o, eq_style=True)   # MultiIndexable#eq (:899-913)
+    def match(self, value): return self._compare("==", value)        # MultiIndexable#=~ (:916-920)
 
     def equals(self, other: "_Indexable") -> bool:
         """NArray#== (src/n_array.cr:440-447) for two device arrays."""

@@ -235,3 +235,21 @@ def test_large_strided_configs_small_scale():
     z = D.fill([nrow, ncol], 0.0, np.float64)
     z.mutable_view().permute()[rng(None, None), rng(None, None)] = d
     assert_bits(z.to_host(), np.ascontiguousarray(n.T), "transposed scatter")
+
+
+def test_get_available_and_optional_chunk():
+    """multi_indexable.cr:397-413 (get_available), :313-318 (has_region?), :540-546 ([]?)."""
+    n = np.arange(6, dtype=np.int32).reshape(2, 3) + 1                  # [[1,2,3],[4,5,6]]
+    d = D.from_host(n)
+    assert d.get_available([rng(1, 5), 1]).to_host().tolist() == [5]    # the doc example
+    with pytest.raises(ph.CrIndexError):
+        d.get_chunk([rng(1, 5), 1])
+    assert d.has_region([rng(0, None), rng(1, 2)]) and not d.has_region([rng(1, None), rng(10, 12)])
+    assert d.get_chunk_or_none([rng(1, None), rng(10, 12)]) is None
+    assert d.get_chunk_or_none([rng(0, None), rng(1, 2)]).to_host().tolist() == [[2, 3], [5, 6]]
+    big = np.arange(7 * 9, dtype=np.float32).reshape(7, 9)
+    db = D.from_host(big)
+    for lit in ([rng(2, 30), rng(0, 100, 2)], [rng(20, 3, -3), rng(4, None)], [rng(5, 5), rng(8, 40)]):
+        want = O.fetch_chunk(big, O.IndexRegion.new_trimmed(lit, list(big.shape), bound_shape=list(big.shape)))
+        assert_bits(db.get_available(lit).to_host(), want, f"get_available {lit}")
+    assert_bits(db.match(5.0).to_host(), big == 5.0, "=~")

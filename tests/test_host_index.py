@@ -276,3 +276,39 @@ def test_transform_goldens():
     with pytest.raises(ph.CrIndexError):
         bad = (C.c_int32 * 2)(0, 2)
         host_check(lib.ph_desc_permute(C.byref(d), bad, 2, C.byref(nd)))
+
+
+def test_trimmed_regions_match_oracle():
+    """IndexRegion.new(literal, bound_shape, trim_to:) (index_region.cr:133-168) -- the region
+    behind MultiIndexable#get_available -- against the oracle on random literals."""
+    lib = _lib.load()
+    rs = np.random.RandomState(77)
+    ok = 0
+    for _ in range(1500):
+        rank = int(rs.randint(1, 4))
+        shape = [int(rs.randint(1, 8)) for _ in range(rank)]
+        lit = []
+        for i in range(int(rs.randint(0, rank + 1))):
+            a, b = int(rs.randint(0, 12)), int(rs.randint(0, 12))
+            kind = rs.randint(0, 4)
+            lit.append(a if kind == 0 else rng(a, b) if kind == 1 else rng(a, None) if kind == 2
+                       else rng(a, b, int(rs.choice([-2, -1, 1, 2, 3]))))
+        drop = bool(rs.randint(0, 2))
+        lits = [ph.region.marshal(l) for l in lit]
+        arr = (_lib.PhRangeLit * max(1, len(lits)))(*lits)
+        reg = _lib.PhRegion()
+        st = lib.ph_region_new_trimmed(arr, len(lits), _i64(shape), _i64(shape), rank, int(drop), C.byref(reg))
+        try:
+            oreg = O.IndexRegion.new_trimmed(lit, shape, bound_shape=shape, drop=drop)
+        except O.CrIndexError:
+            assert st == ph.K["PH_HOST_INDEX_ERROR"], (lit, shape)
+            continue
+        except O.CrDivisionByZeroError:
+            continue
+        assert st == 0, (lit, shape, lib.ph_host_last_error())
+        assert reg.shape == oreg.shape, (lit, shape)
+        for i in range(rank):
+            if oreg.step[i] != 0:
+                assert (reg.first[i], reg.step[i], reg.last[i]) == (oreg.first[i], oreg.step[i], oreg.last[i]), (lit, shape)
+        ok += 1
+    assert ok > 500
