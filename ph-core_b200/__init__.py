@@ -9,7 +9,9 @@ from .narray import (DeviceNArray, DeviceView, make_region, ShapeError, Dimensio
 
 from .region import R, Step, rng, ALL
 from . import heat
+from . import io
+from . import sharding
 
-__all__ = ["DeviceNArray", "DeviceView", "make_region", "R", "Step", "rng", "ALL", "heat", "PhDesc", "PhError", "init", "load", "check", "K", "ShapeError", "DimensionError",
+__all__ = ["DeviceNArray", "DeviceView", "make_region", "R", "Step", "rng", "ALL", "heat", "io", "sharding", "PhDesc", "PhError", "init", "load", "check", "K", "ShapeError", "DimensionError",
            "CrIndexError", "CrOverflowError", "CrDivisionByZeroError", "CrArgumentError", "CrEmptyError",
            "DeviceBlockError"]

@@ -22,6 +22,7 @@ struct CopyOp {
   using In = T;
   using Out = T;
   static constexpr int NIN = 1;
+  static constexpr bool kCompact = false;
   static __device__ __forceinline__ Out apply(const In (&x)[1], uint32_t&) { return x[0]; }
 };
 

@@ -14,6 +14,7 @@ namespace ph {
   int32_t mul_add_##S(const void*, const ph_desc*, const void*, const ph_desc*, const void*,              \
                       const ph_desc*, void*, const ph_desc*);
 PH_DECL(f32) PH_DECL(f64) PH_DECL(i32) PH_DECL(i64)
+PH_DECL(u8) PH_DECL(i8) PH_DECL(i16) PH_DECL(u16) PH_DECL(u32) PH_DECL(u64)
 #undef PH_DECL
 }  // namespace ph
 
@@ -25,6 +26,12 @@ using namespace ph;
     case PH_F64: return CALL(f64);                                                    \
     case PH_I32: return CALL(i32);                                                    \
     case PH_I64: return CALL(i64);                                                    \
+    case PH_U8: return CALL(u8);                                                      \
+    case PH_I8: return CALL(i8);                                                      \
+    case PH_I16: return CALL(i16);                                                    \
+    case PH_U16: return CALL(u16);                                                    \
+    case PH_U32: return CALL(u32);                                                    \
+    case PH_U64: return CALL(u64);                                                    \
     default: return set_error(PH_ERR_UNSUPPORTED, "dtype %d has no arithmetic kernels", dtype); \
   }
 

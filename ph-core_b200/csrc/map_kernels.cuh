@@ -326,7 +326,9 @@ int32_t launch_map(const MapOperand* ops, void* out, const ph_desc* out_desc) {
     for (int k = 0; k < NIN; k++) if (a.mode[k] != OPND_ARRAY) a.all_array = 0;
     const int vb = pick_width(false);
     if (vb == 32 && WIDE <= 16) return launch_flat<F, 32 / WIDE, 2>(a);
-    if (vb >= 16 && WIDE <= 8) return launch_flat<F, 16 / WIDE, 4>(a);
+    if constexpr (!F::kCompact) {
+      if (vb >= 16 && WIDE <= 8) return launch_flat<F, 16 / WIDE, 4>(a);
+    }
     return launch_flat<F, 1, 4>(a);
   }
 
@@ -360,7 +362,9 @@ int32_t launch_map(const MapOperand* ops, void* out, const ph_desc* out_desc) {
     }
     const int vb = pick_width(true);
     if (vb == 32 && WIDE <= 16) return launch_rows<F, 32 / WIDE, 4>(a);
-    if (vb >= 16 && WIDE <= 8) return launch_rows<F, 16 / WIDE, 4>(a);
+    if constexpr (!F::kCompact) {
+      if (vb >= 16 && WIDE <= 8) return launch_rows<F, 16 / WIDE, 4>(a);
+    }
     return launch_rows<F, 1, 4>(a);
   }
   // ---- arbitrary inner strides: one element per thread per row, still no div/mod per element

@@ -144,17 +144,31 @@ __device__ __forceinline__ T f_powi(T a, int32_t n) {
   return recip ? f_div((T)1, r) : r;
 }
 
+// Hot (op, dtype) pairs get every vector-width variant of the map kernels; the rest only the
+// widest and the scalar one (keeps the library small; alignment-odd views of rare ops still work).
+template <typename T> struct is_main_t : std::false_type {};
+template <> struct is_main_t<float> : std::true_type {};
+template <> struct is_main_t<double> : std::true_type {};
+template <> struct is_main_t<int32_t> : std::true_type {};
+template <> struct is_main_t<int64_t> : std::true_type {};
+
 // ---------------------------------------------------------------- binary functors
 template <typename T, int OP> struct BinOut { using type = T; };
 template <> struct BinOut<int32_t, PH_DIV> { using type = double; };
 template <> struct BinOut<int64_t, PH_DIV> { using type = double; };
 template <> struct BinOut<uint8_t, PH_DIV> { using type = double; };
+template <> struct BinOut<int8_t, PH_DIV> { using type = double; };
+template <> struct BinOut<int16_t, PH_DIV> { using type = double; };
+template <> struct BinOut<uint16_t, PH_DIV> { using type = double; };
+template <> struct BinOut<uint32_t, PH_DIV> { using type = double; };
+template <> struct BinOut<uint64_t, PH_DIV> { using type = double; };
 
 template <typename T, int OP>
 struct BinaryOp {
   using In = T;
   using Out = typename BinOut<T, OP>::type;
   static constexpr int NIN = 2;
+  static constexpr bool kCompact = !(is_main_t<T>::value && (OP == PH_ADD || OP == PH_SUB || OP == PH_MUL || OP == PH_DIV));
   static __device__ __forceinline__ Out apply(const In (&x)[2], uint32_t& err) {
     const T a = x[0], b = x[1];
     if constexpr (is_float_t<T>::value) {
@@ -196,6 +210,7 @@ struct PowiOp {
   using In = T;
   using Out = T;
   static constexpr int NIN = 2;
+  static constexpr bool kCompact = true;
   static __device__ __forceinline__ Out apply(const In (&x)[2], uint32_t&) {
     int32_t n;
     if constexpr (sizeof(T) == 4) n = __float_as_int(x[1]);
@@ -209,6 +224,7 @@ struct CompareOp {
   using In = T;
   using Out = uint8_t;
   static constexpr int NIN = 2;
+  static constexpr bool kCompact = !is_main_t<T>::value;
   static __device__ __forceinline__ Out apply(const In (&x)[2], uint32_t&) {
     if constexpr (CMP == PH_GT) return x[0] > x[1];
     else if constexpr (CMP == PH_LT) return x[0] < x[1];
@@ -224,6 +240,7 @@ struct UnaryOp {
   using In = T;
   using Out = T;
   static constexpr int NIN = 1;
+  static constexpr bool kCompact = true;
   static __device__ __forceinline__ Out apply(const In (&x)[1], uint32_t& err) {
     if constexpr (OP == PH_POS) return x[0];
     else if constexpr (OP == PH_NEG) {
@@ -242,6 +259,7 @@ struct MulAddOp {
   using In = T;
   using Out = T;
   static constexpr int NIN = 3;
+  static constexpr bool kCompact = !is_main_t<T>::value;
   static __device__ __forceinline__ Out apply(const In (&x)[3], uint32_t& err) {
     if constexpr (is_float_t<T>::value) return f_add(f_mul(x[0], x[1]), x[2]);
     else return i_add<T>(i_mul<T>(x[0], x[1], true, err), x[2], true, err);

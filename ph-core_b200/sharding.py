@@ -146,3 +146,127 @@ def heat_run_sharded(slab, other, coeff, steps: int):
     check(lib.ph_heat_run_sharded(dtype_code(slab.dtype), len(slab.shape), ext, c.ctypes.data, slab.ptr, other.ptr,
                                   int(steps)))
     return other if steps % 2 else slab
+
+
+# ---------------------------------------------------------------- f-3: a sharded NArray
+class ShardedNArray:
+    """An NArray distributed along axis 0 over the ranks of the job: every
+    rank holds the contiguous row range `shard_range(shape[0], world, rank)` as an ordinary
+    DeviceNArray.  Elementwise ops, comparisons and masked stores are purely local; full
+    reductions combine per-GPU partials (allreduce / allgather of (value, index) pairs);
+    per-axis reductions allreduce only when the reduced axis is the sharded one; slicing is
+    local as long as axis 0 is taken whole.  Transposes across shards (an all-to-all) are not
+    offered: gather to one GPU first."""
+
+    def __init__(self, global_shape: Sequence[int], local):
+        self.shape = [int(s) for s in global_shape]
+        self.local = local
+        self.world, self.rank = world_rank()
+        self.row0, self.row1 = shard_range(self.shape[0], self.world, self.rank)
+        if list(local.shape) != [self.row1 - self.row0] + self.shape[1:]:
+            raise ValueError(f"local shard has shape {local.shape}, expected {[self.row1 - self.row0] + self.shape[1:]}")
+
+    @property
+    def dtype(self):
+        return self.local.dtype
+
+    @classmethod
+    def from_global(cls, host: np.ndarray) -> "ShardedNArray":
+        """Every rank passes the same host array and keeps its own rows."""
+        from .narray import DeviceNArray
+        world, rank = world_rank()
+        a, b = shard_range(host.shape[0], world, rank)
+        return cls(host.shape, DeviceNArray.from_host(np.ascontiguousarray(host[a:b])))
+
+    def to_global(self) -> np.ndarray:
+        """Assemble the whole array on every rank's host (allgather of the shards)."""
+        from .narray import _Buffer
+        lib = _lib.load()
+        mine = self.local.to_host()
+        if self.world == 1:
+            return mine
+        row_elems = int(np.prod(self.shape[1:], dtype=np.int64)) if len(self.shape) > 1 else 1
+        rows_max = -(-self.shape[0] // self.world)
+        nbytes = rows_max * row_elems * self.dtype.itemsize
+        send = _Buffer(max(1, nbytes))
+        recv = _Buffer(max(1, nbytes * self.world))
+        if mine.nbytes:
+            check(lib.ph_d2d(send.ptr, self.local.ptr, mine.nbytes))
+        check(lib.ph_allgather(send.ptr, recv.ptr, nbytes))
+        raw = np.zeros(nbytes * self.world, dtype=np.uint8)
+        check(lib.ph_d2h(raw.ctypes.data, recv.ptr, raw.nbytes))
+        parts = []
+        for r in range(self.world):
+            a, b = shard_range(self.shape[0], self.world, r)
+            n = (b - a) * row_elems * self.dtype.itemsize
+            parts.append(raw[r * nbytes: r * nbytes + n].view(self.dtype).reshape([b - a] + self.shape[1:]))
+        return np.concatenate(parts, axis=0)
+
+    # ---- elementwise / compare: local, shapes checked on the GLOBAL shape ------------------
+    def _wrap(self, local, shape=None):
+        return ShardedNArray(self.shape if shape is None else shape, local)
+
+    def _peer(self, other):
+        from .narray import ShapeError
+        if isinstance(other, ShardedNArray):
+            if other.shape != self.shape:
+                raise ShapeError(f"The shape of this MultiIndexable ({self.shape}) does not match the shape of the "
+                                 f"one provided ({other.shape}).")
+            return other.local
+        return other
+
+    def __add__(self, o): return self._wrap(self.local + self._peer(o))
+    def __sub__(self, o): return self._wrap(self.local - self._peer(o))
+    def __mul__(self, o): return self._wrap(self.local * self._peer(o))
+    def __truediv__(self, o): return self._wrap(self.local / self._peer(o))
+    def __gt__(self, o): return self._wrap(self.local > self._peer(o))
+    def __lt__(self, o): return self._wrap(self.local < self._peer(o))
+    def __ge__(self, o): return self._wrap(self.local >= self._peer(o))
+    def __le__(self, o): return self._wrap(self.local <= self._peer(o))
+    def eq(self, o): return self._wrap(self.local.eq(self._peer(o)))
+
+    def set_mask(self, mask: "ShardedNArray", value) -> None:
+        self.local.set_mask(mask.local, self._peer(value))
+
+    def __getitem__(self, key):
+        """Slicing that leaves axis 0 whole is local (the result stays sharded the same way)."""
+        if not isinstance(key, tuple):
+            key = (key,)
+        first = key[0] if key else None
+        whole = first is None or (hasattr(first, "begin") and first.begin is None and first.end is None
+                                  and not getattr(first, "exclusive", False))
+        if not whole:
+            raise NotImplementedError("slicing the sharded axis needs a redistribution: gather first (f-3 'next')")
+        loc = self.local.get_chunk(list(key))
+        return ShardedNArray([self.shape[0]] + loc.shape[1:], loc)
+
+    # ---- reductions -----------------------------------------------------------------------
+    def _row_elems(self):
+        return int(np.prod(self.shape[1:], dtype=np.int64)) if len(self.shape) > 1 else 1
+
+    def sum(self, axis=None):
+        return self._reduce("sum", axis)
+
+    def max(self, axis=None):
+        return self._reduce("max", axis)
+
+    def min(self, axis=None):
+        return self._reduce("min", axis)
+
+    def argmax(self):
+        v, i = reduce_full_sharded(self.local, "argmax", self.row0 * self._row_elems())
+        coord = []
+        for length in reversed(self.shape):
+            coord.append(i % length)
+            i //= length
+        return v, list(reversed(coord))
+
+    def _reduce(self, name, axis):
+        from .narray import dtype_code, _RED
+        if axis is None:
+            return reduce_full_sharded(self.local, name, self.row0 * self._row_elems())
+        part = getattr(self.local, name)(axis=axis)
+        if axis == 0:                          # partial over my rows -> allreduce of the [inner] plane
+            check(_lib.load().ph_allreduce(K[_RED[name]], dtype_code(part.dtype), part.ptr, part.size))
+            return part                        # replicated DeviceNArray
+        return ShardedNArray([self.shape[0]] + part.shape[1:], part)   # kept axis 0: still sharded

@@ -63,6 +63,20 @@ def main():
     part = x.sum(axis=0)
     ph.check(ph.load().ph_allreduce(ph.K["PH_SUM"], ph.K["PH_F32"], part.ptr, part.size))
     assert part.to_host().tobytes() == data.sum(axis=0, dtype=np.float64).astype(np.float32).tobytes()
+    # ---- f-3: ShardedNArray behaves like the undivided array
+    g = rs.randint(-8, 9, size=(6 * world + 2, 12, 10)).astype(np.float32)
+    h = rs.randint(-8, 9, size=(6 * world + 2, 12, 10)).astype(np.float32)
+    sg, sh = S.ShardedNArray.from_global(g), S.ShardedNArray.from_global(h)
+    assert ((sg * sh + sg) - 2.0).to_global().tobytes() == ((g * h + g) - np.float32(2.0)).tobytes()
+    assert (sg > sh).to_global().tobytes() == (g > h).tobytes()
+    assert sg.sum() == np.float32(g.sum(dtype=np.float64)) and sg.max() == g.max()
+    flat = int(np.argmax(g.reshape(-1)))
+    assert sg.argmax() == (g.max(), list(np.unravel_index(flat, g.shape)))
+    assert sg.sum(axis=0).to_host().tobytes() == g.sum(axis=0, dtype=np.float64).astype(np.float32).tobytes()
+    assert sg.max(axis=2).to_global().tobytes() == g.max(axis=2).tobytes()
+    assert sg[ph.ALL, ph.rng(1, 9, 2), 3].to_global().tobytes() == np.ascontiguousarray(g[:, 1:10:2, 3]).tobytes()
+    sg.set_mask(sg > sh, 0.0)
+    assert sg.to_global().tobytes() == np.where(g > h, np.float32(0), g).tobytes()
     dist.barrier()
     if rank == 0:
         print(f"MGPU_OK world={world}")

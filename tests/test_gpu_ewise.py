@@ -240,3 +240,40 @@ def test_empty_and_scalar_arrays():
         assert got.shape == tuple(shape)
         if a.size:
             assert (got == 2).all()
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.int8, np.int16, np.uint16, np.uint32, np.uint64])
+def test_small_and_unsigned_ints(dtype):
+    """Every Crystal primitive integer: checked / wrapping / floored semantics, flags, compare."""
+    info = np.iinfo(dtype)
+    rs = np.random.RandomState(13)
+    for n in [1, 100, 4099, 70001]:
+        hi = min(int(info.max), 2**31 - 1)
+        lo = max(int(info.min), -2**31)
+        a = rs.randint(lo, hi, size=n, dtype=np.int64).astype(dtype)
+        b = rs.randint(lo, hi, size=n, dtype=np.int64).astype(dtype)
+        b[b == 0] = 1
+        da, db = D.from_host(a), D.from_host(b)
+        for op in ["+", "-", "*", "//", "%", "&+", "&-", "&*", "&", "|", "^", "/"]:
+            want, wflags = O.ewise(op, a, b)
+            got = dev_op(op, da, db).to_host()
+            assert take_flags() == wflags, (op, np.dtype(dtype))
+            assert_bits(got, want, f"{op} {np.dtype(dtype)} n={n}")
+        small = (a % 7).astype(dtype)
+        e = (rs.randint(0, 5, size=n)).astype(dtype)
+        for op in ["**", "&**"]:
+            want, wflags = O.ewise(op, small, e)
+            got = dev_op(op, D.from_host(small), D.from_host(e)).to_host()
+            assert take_flags() == wflags
+            assert_bits(got, want, f"{op} {np.dtype(dtype)}")
+        assert_bits((da > db).to_host(), O.compare(">", a, b), "cmp")
+        assert_bits(da.eq(db).to_host(), O.compare("==", a, b), "eq")
+        s = dtype(3)
+        want, wf = O.ewise("*", a, s); got = (da * 3).to_host(); assert take_flags() == wf; assert_bits(got, want, "scalar *")
+        want, wf = O.ewise("-", s, a); got = (3 - da).to_host(); assert take_flags() == wf; assert_bits(got, want, "scalar - left")
+    with pytest.raises(ph.CrDivisionByZeroError):
+        _ = D.from_host(np.array([5], dtype)) // D.from_host(np.array([0], dtype))
+        D.raise_pending()
+    with pytest.raises(ph.CrOverflowError):
+        _ = D.from_host(np.array([info.max], dtype)) + D.from_host(np.array([1], dtype))
+        D.raise_pending()
