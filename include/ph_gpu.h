@@ -220,11 +220,12 @@ int32_t ph_reduce_axis(int32_t red, int32_t dtype,
 int32_t ph_heat_step(int32_t dtype, int32_t rank, const int64_t* extents,
                      const void* coeff_host, int32_t boundary_mode,
                      const void* in, void* out);
-/* `steps` steps ping-ponging between the two buffers; the final state is in
- * buf_a if steps is even, buf_b if odd. */
-int32_t ph_heat_run(int32_t dtype, int32_t rank, const int64_t* extents,
-                    const void* coeff_host, int32_t boundary_mode,
-                    void* buf_a, void* buf_b, int64_t steps);
+/* `steps` steps between the two buffers.  *final_is_b (may be NULL) receives 1 when the final
+ * state is in buf_b, 0 when it is in buf_a: rank-3 grids advance TWO time steps per pass over
+ * HBM when the shape allows (temporal blocking, bit-identical to single steps), so the parity
+ * of `steps` does not tell.  With a NULL pointer the caller must not rely on either buffer. */
+int32_t ph_heat_run(int32_t dtype, int32_t rank, const int64_t* extents, const void* coeff_host,
+                    int32_t boundary_mode, void* buf_a, void* buf_b, int64_t steps, int32_t* final_is_b);
 /* Slab-decomposed step (axis 0 sharded): the local slab holds planes
  * [1, n0_local] plus ghost planes 0 and n0_local+1 (extents[0] = n0_local + 2);
  * has_lo / has_hi say whether a neighbour exists on that side (else the edge

@@ -133,7 +133,7 @@ def load() -> C.CDLL:
         "ph_reduce_full_dev": [i32, i32, vp, dp, vp, vp],
         "ph_reduce_axis": [i32, i32, vp, dp, i32, vp, dp],
         "ph_heat_step": [i32, i32, C.POINTER(i64), vp, i32, vp, vp],
-        "ph_heat_run": [i32, i32, C.POINTER(i64), vp, i32, vp, vp, i64],
+        "ph_heat_run": [i32, i32, C.POINTER(i64), vp, i32, vp, vp, i64, C.POINTER(i32)],
         "ph_heat_step_slab": [i32, i32, C.POINTER(i64), vp, i32, i32, i64, i64, vp, vp, vp],
         "ph_comm_unique_id": [vp], "ph_comm_init": [i32, i32, vp], "ph_comm_destroy": [],
         "ph_allreduce": [i32, i32, vp, i64], "ph_allgather": [vp, vp, i64],

@@ -260,6 +260,10 @@ template <typename T>
 int32_t heat_tma_planes(const T* in, T* out, int64_t n0, int64_t n1, int64_t n2, T coeff, int64_t z_begin,
                         int64_t z_end, cudaStream_t stream, bool* used);
 
+template <typename T>
+int32_t heat_tma2_planes(const T* in, T* out, int64_t n0, int64_t n1, int64_t n2, T coeff, int64_t z_begin,
+                         int64_t z_end, cudaStream_t stream, bool* used);
+
 // one step on planes [z_begin, z_end) of a rank-2/3 grid; boundary planes are NOT touched
 template <typename T>
 static int32_t heat_planes(int rank, const int64_t* ext, T coeff, const T* in, T* out, int64_t z_begin,
@@ -306,11 +310,12 @@ static int32_t heat_step_t(int rank, const int64_t* ext, const void* coeff_host,
 
 template <typename T>
 static int32_t heat_run_t(int rank, const int64_t* ext, const void* coeff_host, int mode, void* a_v, void* b_v,
-                          int64_t steps) {
+                          int64_t steps, int32_t* final_is_b) {
   Runtime& r = rt();
   T coeff;
   memcpy(&coeff, coeff_host, sizeof(T));
   T* bufs[2] = {reinterpret_cast<T*>(a_v), reinterpret_cast<T*>(b_v)};
+  *final_is_b = (int32_t)(steps > 0 ? (steps & 1) : 0);     // the plain ping-pong convention
   if (steps <= 0) return PH_OK;
   if (rank == 1 && ext[0] <= 1024 && ext[0] >= 3) {
     heat_1d_resident_kernel<T><<<1, 1024, 0, r.stream>>>(bufs[0], bufs[1], (int)ext[0], coeff, mode, steps);
@@ -329,10 +334,21 @@ static int32_t heat_run_t(int rank, const int64_t* ext, const void* coeff_host, 
       PH_CUDA(cudaMemcpyAsync(bufs[1], bufs[0], plane * sizeof(T), cudaMemcpyDeviceToDevice, r.stream));
       PH_CUDA(cudaMemcpyAsync(bufs[1] + (ext[0] - 1) * plane, bufs[0] + (ext[0] - 1) * plane, plane * sizeof(T),
                               cudaMemcpyDeviceToDevice, r.stream));
-      for (int64_t t = 0; t < steps; t++) {
-        int32_t st = heat_planes<T>(rank, ext, coeff, bufs[t & 1], bufs[(t & 1) ^ 1], 1, ext[0] - 1, r.stream);
+      int cur = 0;
+      int64_t left = steps;
+      while (left > 0) {
+        if (rank == 3 && left >= 2) {            // two time steps per pass over HBM when the shape allows
+          bool used = false;
+          int32_t st = heat_tma2_planes<T>(bufs[cur], bufs[cur ^ 1], ext[0], ext[1], ext[2], coeff, 1, ext[0] - 1,
+                                           r.stream, &used);
+          if (st != PH_OK) return st;
+          if (used) { cur ^= 1; left -= 2; continue; }
+        }
+        int32_t st = heat_planes<T>(rank, ext, coeff, bufs[cur], bufs[cur ^ 1], 1, ext[0] - 1, r.stream);
         if (st != PH_OK) return st;
+        cur ^= 1; left -= 1;
       }
+      *final_is_b = cur;
       return PH_OK;
     }
   }
@@ -384,12 +400,14 @@ int32_t ph_heat_step(int32_t dtype, int32_t rank, const int64_t* extents, const 
 }
 
 int32_t ph_heat_run(int32_t dtype, int32_t rank, const int64_t* extents, const void* coeff_host,
-                    int32_t boundary_mode, void* buf_a, void* buf_b, int64_t steps) {
+                    int32_t boundary_mode, void* buf_a, void* buf_b, int64_t steps, int32_t* final_is_b) {
   PH_REQUIRE_INIT();
   if (!extents || !coeff_host || !buf_a || !buf_b) return set_error(PH_ERR_INVALID, "null argument to ph_heat_run");
   if (rank < 1 || rank > 3) return set_error(PH_ERR_UNSUPPORTED, "heat stencil rank must be 1..3 (got %d)", rank);
-  if (dtype == PH_F32) return heat_run_t<float>(rank, extents, coeff_host, boundary_mode, buf_a, buf_b, steps);
-  if (dtype == PH_F64) return heat_run_t<double>(rank, extents, coeff_host, boundary_mode, buf_a, buf_b, steps);
+  int32_t dummy = 0;
+  if (!final_is_b) final_is_b = &dummy;
+  if (dtype == PH_F32) return heat_run_t<float>(rank, extents, coeff_host, boundary_mode, buf_a, buf_b, steps, final_is_b);
+  if (dtype == PH_F64) return heat_run_t<double>(rank, extents, coeff_host, boundary_mode, buf_a, buf_b, steps, final_is_b);
   return set_error(PH_ERR_UNSUPPORTED, "the heat stencil is defined for F32 / F64");
 }
 

@@ -35,6 +35,7 @@ def simulate(state: DeviceNArray, coeff, steps: int, mode: int = FIXED) -> Devic
         raise TypeError("the heat stencil is defined for Float32 / Float64")
     other = DeviceNArray(state.shape, state.dtype)
     c = np.array(coeff, dtype=state.dtype)
+    final_is_b = C.c_int32(0)
     check(_lib.load().ph_heat_run(dtype_code(state.dtype), len(state.shape), _ext(state.shape), c.ctypes.data,
-                                  mode, state.ptr, other.ptr, int(steps)))
-    return other if steps % 2 else state
+                                  mode, state.ptr, other.ptr, int(steps), C.byref(final_is_b)))
+    return other if final_is_b.value else state

@@ -1,9 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for ty in 16 32; do
-echo "TMA rows $ty"
-PH_HEAT_TMA_ROWS=$ty timeout 300 python -m pytest tests/test_gpu_heat.py -m gpu -q --timeout 120 -x 2>&1 | tail -1
-PH_HEAT_TMA_ROWS=$ty timeout 300 python benchmarks/bench_kernels.py --heat-shape 1024,1024,1024 2>&1 | cut -c1-200
-PH_HEAT_TMA_ROWS=$ty timeout 300 python benchmarks/bench_kernels.py --heat-shape 2048,2048,2048 2>&1 | cut -c1-200
-done
-PH_HEAT_TMA_ROWS=16 timeout 900 ncu --set full --clock-control none -k regex:"heat_tma" -s 4 -c 1 -o gpurun_out/prof_heat_tma_2k16 -f python benchmarks/bench_kernels.py --heat-shape 256,2048,2048 --reps 1 > gpurun_out/ncu_heat_tma.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_heat.py tests/test_gpu_example.py -m gpu -q --timeout 300 2>&1 | tail -6
+timeout 300 python benchmarks/bench_kernels.py --heat-shape 1024,1024,1024 2>&1 | cut -c1-220
+timeout 300 python benchmarks/bench_kernels.py --heat-shape 2048,2048,2048 2>&1 | cut -c1-220
+PH_HEAT_NO_FUSE2=1 timeout 300 python benchmarks/bench_kernels.py --heat-shape 2048,2048,2048 2>&1 | cut -c1-220
+timeout 900 ncu --set full --clock-control none -k regex:"heat_tma2" -s 2 -c 1 -o /tmp/prof_tma2 -f python benchmarks/bench_kernels.py --heat-shape 256,2048,2048 --reps 1 > gpurun_out/ncu_tma2.log 2>&1
+python benchmarks/ncu_summary.py /tmp/prof_tma2.ncu-rep gpurun_out/ncu_heat_tma2.csv; cat gpurun_out/ncu_heat_tma2.csv

@@ -68,6 +68,9 @@ def test_3d_one_step_and_run(dtype, shape):
     for _ in range(4):
         want = O.heat_step_nd(want, c)
     assert_bits(heat.simulate(D.from_host(s), c, 4).to_host(), want, f"3d 4 steps {shape}")
+    for _ in range(3):                                             # 7 = 3 two-step passes + 1 single step
+        want = O.heat_step_nd(want, c)
+    assert_bits(heat.simulate(D.from_host(s), c, 7).to_host(), want, f"3d 7 steps {shape}")
 
 
 def test_3d_100_steps_tolerance_and_conservation():
@@ -83,6 +86,20 @@ def test_3d_100_steps_tolerance_and_conservation():
     np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4)
     assert_bits(got, want, "100 steps stay bit-exact")
     assert np.array_equal(got[0], s[0]) and np.array_equal(got[:, :, -1], s[:, :, -1])   # boundary held
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_3d_two_step_pass_tiles_and_chunks(dtype):
+    """Shapes that span several TMA tiles in x / y and several z-chunks, so tile halos, the
+    recomputed t+1 planes at chunk seams and partial tiles of the two-step kernel are all hit."""
+    rs = np.random.RandomState(5)
+    for shape in [(150, 40, 272), (70, 35, 516), (200, 19, 128)]:
+        s = (rs.rand(*shape) * 100).astype(dtype)
+        c = dtype(0.1)
+        want = s.copy()
+        for _ in range(6):
+            want = O.heat_step_nd(want, c)
+        assert_bits(heat.simulate(D.from_host(s), c, 6).to_host(), want, f"6 steps {shape}")
 
 
 def test_heat_slab_matches_whole_grid():
