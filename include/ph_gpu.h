@@ -237,6 +237,15 @@ int32_t ph_heat_step_slab(int32_t dtype, int32_t rank, const int64_t* extents,
                           int64_t p_begin, int64_t p_end,
                           const void* in, void* out, void* cuda_stream);
 
+/* The same with `ghost_planes` (1 or 2) ghost planes per side (extents[0] = owned + 2 * ghost_planes;
+ * owned planes are [ghost_planes, extents[0] - ghost_planes)).  two_steps != 0 (needs 2 ghost planes,
+ * rank 3): planes [p_begin, p_end) of `out` receive time t+2 from time t in `in` in ONE pass over HBM
+ * (temporal blocking; bit-identical to two ph_heat_step_slab passes). */
+int32_t ph_heat_pass_slab(int32_t dtype, int32_t rank, const int64_t* extents,
+                          const void* coeff_host, int32_t ghost_planes, int32_t two_steps,
+                          int32_t has_lo, int32_t has_hi, int64_t p_begin, int64_t p_end,
+                          const void* in, void* out, void* cuda_stream);
+
 /* ---- multi-GPU (one process per GPU, NCCL over NVLink) ---------------------------- */
 int32_t ph_comm_unique_id(uint8_t* out128);                 /* rank 0; broadcast by the host */
 int32_t ph_comm_init(int32_t nranks, int32_t rank, const uint8_t* id128);
@@ -248,9 +257,14 @@ int32_t ph_allgather(const void* send_dev, void* recv_dev, int64_t nbytes_per_ra
 int32_t ph_halo_exchange(const void* send_lo, void* recv_lo, int32_t lo_rank,
                          const void* send_hi, void* recv_hi, int32_t hi_rank,
                          int64_t nbytes, void* cuda_stream);
-/* `steps` slab steps with the exchange overlapped with the interior update. */
+/* `steps` slab steps with the exchange overlapped with the interior update.  The local slab
+ * holds `ghost_planes` (1 or 2) ghost planes on either side of its owned planes
+ * (local_extents[0] = owned + 2 * ghost_planes).  With 2 ghost planes a rank-3 grid advances
+ * two time steps per pass over HBM and per exchange (bit-identical to single steps).
+ * *final_is_b (may be NULL) = 1 when the final state is in buf_b. */
 int32_t ph_heat_run_sharded(int32_t dtype, int32_t rank, const int64_t* local_extents,
-                            const void* coeff_host, void* buf_a, void* buf_b, int64_t steps);
+                            const void* coeff_host, int32_t ghost_planes, void* buf_a, void* buf_b,
+                            int64_t steps, int32_t* final_is_b);
 
 #ifdef __cplusplus
 }

@@ -76,9 +76,10 @@ static int32_t check_nccl(ncclResult_t r, const char* what) {
     if (_s != PH_OK) return _s;                         \
   } while (0)
 
-int32_t heat_slab_dispatch(int32_t dtype, int rank, const int64_t* ext, const void* coeff_host, int has_lo,
+int32_t heat_slab_dispatch(int32_t dtype, int rank, const int64_t* ext, const void* coeff_host, int ghost, int has_lo,
                            int has_hi, int64_t p_begin, int64_t p_end, const void* in, void* out,
-                           cudaStream_t stream);
+                           cudaStream_t stream, bool two_step);
+bool heat_two_step_usable(int32_t dtype, int rank, const int64_t* ext);
 
 static int32_t nccl_type(int32_t dtype, ncclDataType_t* t) {
   switch (dtype) {
@@ -193,13 +194,16 @@ int32_t ph_halo_exchange(const void* send_lo, void* recv_lo, int32_t lo_rank, co
   return halo_exchange_impl(send_lo, recv_lo, lo_rank, send_hi, recv_hi, hi_rank, nbytes, s);
 }
 
-// local_extents[0] = n0_local + 2 (ghost planes 0 and n0_local + 1).  Per step:
-//   main : update the two edge planes (1 and n0_local) first
+// local_extents[0] = n0_local + 2 g, g = ghost_planes per side (1 or 2).  Per pass:
+//   main : update the g edge planes on either side first (what the neighbours need)
 //   aux  : (after the edge planes) exchange them with the neighbours' ghost planes
-//   main : update the interior planes [2, n0_local) meanwhile
-//   main waits for aux before the next step reads the ghosts.
+//   main : update the interior planes meanwhile
+//   main waits for aux before the next pass reads the ghosts.
+// g = 1: every pass is one time step.  g = 2 (rank 3, shape permitting): a pass advances TWO time
+// steps with the temporally blocked kernel (heat_tma.cu), so both the HBM traffic and the number
+// of exchanges per time step halve; an odd last step is a single step.
 int32_t ph_heat_run_sharded(int32_t dtype, int32_t rank, const int64_t* local_extents, const void* coeff_host,
-                            void* buf_a, void* buf_b, int64_t steps) {
+                            int32_t ghost_planes, void* buf_a, void* buf_b, int64_t steps, int32_t* final_is_b) {
   PH_REQUIRE_INIT();
   Runtime& r = rt();
   Comm& c = cm();
@@ -208,8 +212,10 @@ int32_t ph_heat_run_sharded(int32_t dtype, int32_t rank, const int64_t* local_ex
   if (rank < 2 || rank > 3) return set_error(PH_ERR_UNSUPPORTED, "sharded stencil needs rank 2 or 3");
   const int esz = dtype_size(dtype);
   if (dtype != PH_F32 && dtype != PH_F64) return set_error(PH_ERR_UNSUPPORTED, "heat stencil is F32 / F64");
+  const int g = ghost_planes;
+  if (g != 1 && g != 2) return set_error(PH_ERR_INVALID, "ghost_planes must be 1 or 2 (got %d)", g);
   const int64_t n0 = local_extents[0];
-  if (n0 < 3) return set_error(PH_ERR_INVALID, "a slab needs at least one owned plane");
+  if (n0 - 2 * g < g) return set_error(PH_ERR_INVALID, "a slab needs at least %d owned planes", g);
   int64_t plane = 1;
   for (int i = 1; i < rank; i++) plane *= local_extents[i];
   const int64_t pbytes = plane * esz;
@@ -217,39 +223,51 @@ int32_t ph_heat_run_sharded(int32_t dtype, int32_t rank, const int64_t* local_ex
   const int hi = c.rank < c.nranks - 1 ? c.rank + 1 : -1;
   const int has_lo = lo >= 0, has_hi = hi >= 0;
   char* bufs[2] = {reinterpret_cast<char*>(buf_a), reinterpret_cast<char*>(buf_b)};
+  int32_t dummy = 0;
+  if (!final_is_b) final_is_b = &dummy;
+  *final_is_b = 0;
+  const bool can_two = g == 2 && heat_two_step_usable(dtype, rank, local_extents);
 
+  // g lowest owned planes -> lo neighbour's upper ghosts, g highest owned planes -> hi neighbour's lower ghosts
+  auto exchange = [&](char* buf, cudaStream_t s) {
+    return halo_exchange_impl(buf + g * pbytes, buf, lo, buf + (n0 - 2 * g) * pbytes, buf + (n0 - g) * pbytes, hi,
+                              g * pbytes, s);
+  };
   // initial ghosts of buf_a, and the (constant) global-boundary planes of buf_b
-  int32_t st = halo_exchange_impl(bufs[0] + pbytes, bufs[0], lo, bufs[0] + (n0 - 2) * pbytes,
-                                  bufs[0] + (n0 - 1) * pbytes, hi, pbytes, r.stream);
+  int32_t st = exchange(bufs[0], r.stream);
   if (st != PH_OK) return st;
-  if (!has_lo) PH_CUDA(cudaMemcpyAsync(bufs[1] + pbytes, bufs[0] + pbytes, pbytes, cudaMemcpyDeviceToDevice, r.stream));
-  if (!has_hi) PH_CUDA(cudaMemcpyAsync(bufs[1] + (n0 - 2) * pbytes, bufs[0] + (n0 - 2) * pbytes, pbytes,
+  if (!has_lo) PH_CUDA(cudaMemcpyAsync(bufs[1] + g * pbytes, bufs[0] + g * pbytes, pbytes, cudaMemcpyDeviceToDevice, r.stream));
+  if (!has_hi) PH_CUDA(cudaMemcpyAsync(bufs[1] + (n0 - g - 1) * pbytes, bufs[0] + (n0 - g - 1) * pbytes, pbytes,
                                        cudaMemcpyDeviceToDevice, r.stream));
 
-  for (int64_t t = 0; t < steps; t++) {
-    const char* in = bufs[t & 1];
-    char* out = bufs[(t & 1) ^ 1];
-    // 1. edge planes (what the neighbours need)
-    st = heat_slab_dispatch(dtype, rank, local_extents, coeff_host, has_lo, has_hi, 1, 2, in, out, r.stream);
-    if (st != PH_OK) return st;
-    if (n0 - 2 > 1) {
-      st = heat_slab_dispatch(dtype, rank, local_extents, coeff_host, has_lo, has_hi, n0 - 2, n0 - 1, in, out, r.stream);
-      if (st != PH_OK) return st;
-    }
-    // 2. halo exchange on the side stream, overlapped with 3.
-    if (c.nranks > 1) {
+  int cur = 0;
+  int64_t left = steps;
+  while (left > 0) {
+    const bool two = can_two && left >= 2;
+    const char* in = bufs[cur];
+    char* out = bufs[cur ^ 1];
+    auto update = [&](int64_t b, int64_t e) {
+      return heat_slab_dispatch(dtype, rank, local_extents, coeff_host, g, has_lo, has_hi, b, e, in, out, r.stream, two);
+    };
+    const int64_t own_b = g, own_e = n0 - g;
+    if (own_e - own_b > 2 * g && c.nranks > 1) {
+      // 1. edge planes  2. exchange on the side stream, overlapped with  3. the interior planes
+      if ((st = update(own_b, own_b + g)) != PH_OK) return st;
+      if ((st = update(own_e - g, own_e)) != PH_OK) return st;
       PH_CUDA(cudaEventRecord(r.ev_a, r.stream));
       PH_CUDA(cudaStreamWaitEvent(r.aux_stream, r.ev_a, 0));
-      st = halo_exchange_impl(out + pbytes, out, lo, out + (n0 - 2) * pbytes, out + (n0 - 1) * pbytes, hi, pbytes,
-                              r.aux_stream);
-      if (st != PH_OK) return st;
+      if ((st = exchange(out, r.aux_stream)) != PH_OK) return st;
       PH_CUDA(cudaEventRecord(r.ev_b, r.aux_stream));
+      if ((st = update(own_b + g, own_e - g)) != PH_OK) return st;
+      PH_CUDA(cudaStreamWaitEvent(r.stream, r.ev_b, 0));
+    } else {
+      if ((st = update(own_b, own_e)) != PH_OK) return st;
+      if (c.nranks > 1 && (st = exchange(out, r.stream)) != PH_OK) return st;
     }
-    // 3. interior planes
-    st = heat_slab_dispatch(dtype, rank, local_extents, coeff_host, has_lo, has_hi, 2, n0 - 2, in, out, r.stream);
-    if (st != PH_OK) return st;
-    if (c.nranks > 1) PH_CUDA(cudaStreamWaitEvent(r.stream, r.ev_b, 0));
+    cur ^= 1;
+    left -= two ? 2 : 1;
   }
+  *final_is_b = cur;
   return PH_OK;
 }
 

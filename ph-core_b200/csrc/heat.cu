@@ -262,7 +262,10 @@ int32_t heat_tma_planes(const T* in, T* out, int64_t n0, int64_t n1, int64_t n2,
 
 template <typename T>
 int32_t heat_tma2_planes(const T* in, T* out, int64_t n0, int64_t n1, int64_t n2, T coeff, int64_t z_begin,
-                         int64_t z_end, cudaStream_t stream, bool* used);
+                         int64_t z_end, int64_t fixed_lo, int64_t fixed_hi, cudaStream_t stream, bool* used);
+
+template <typename T>
+bool heat_tma2_usable(int64_t n1, int64_t n2);
 
 // one step on planes [z_begin, z_end) of a rank-2/3 grid; boundary planes are NOT touched
 template <typename T>
@@ -340,7 +343,7 @@ static int32_t heat_run_t(int rank, const int64_t* ext, const void* coeff_host, 
         if (rank == 3 && left >= 2) {            // two time steps per pass over HBM when the shape allows
           bool used = false;
           int32_t st = heat_tma2_planes<T>(bufs[cur], bufs[cur ^ 1], ext[0], ext[1], ext[2], coeff, 1, ext[0] - 1,
-                                           r.stream, &used);
+                                           0, ext[0] - 1, r.stream, &used);
           if (st != PH_OK) return st;
           if (used) { cur ^= 1; left -= 2; continue; }
         }
@@ -359,27 +362,50 @@ static int32_t heat_run_t(int rank, const int64_t* ext, const void* coeff_host, 
   return PH_OK;
 }
 
+// Slab with `g` ghost planes per side (g = 1: one step per exchange; g = 2: two).  Owned planes are
+// [g, n0-g); without a neighbour the first / last owned plane is the fixed global boundary.
+// two_step: planes [p_begin, p_end) of `out` receive time t+2 (rank 3, g = 2, shape accepted by
+// heat_tma2_usable); otherwise time t+1.
 template <typename T>
-static int32_t heat_slab_t(int rank, const int64_t* ext, const void* coeff_host, int has_lo, int has_hi,
-                           int64_t p_begin, int64_t p_end, const void* in_v, void* out_v, cudaStream_t stream) {
+static int32_t heat_slab_t(int rank, const int64_t* ext, const void* coeff_host, int g, int has_lo, int has_hi,
+                           int64_t p_begin, int64_t p_end, const void* in_v, void* out_v, cudaStream_t stream,
+                           bool two_step) {
   T coeff;
   memcpy(&coeff, coeff_host, sizeof(T));
-  // planes 0 and ext[0]-1 are ghosts; without a neighbour the adjacent plane is a fixed global boundary
-  const int64_t lo = has_lo ? 1 : 2;
-  const int64_t hi = has_hi ? ext[0] - 1 : ext[0] - 2;
+  const int64_t n0 = ext[0];
+  const int64_t lo = has_lo ? g : g + 1;
+  const int64_t hi = has_hi ? n0 - g : n0 - g - 1;
   const int64_t b = std::max<int64_t>(p_begin, lo), e = std::min<int64_t>(p_end, hi);
   for (int i = 1; i < rank; i++) if (ext[i] < 3) return PH_OK;
-  return heat_planes<T>(rank, ext, coeff, reinterpret_cast<const T*>(in_v), reinterpret_cast<T*>(out_v), b, e, stream);
+  const T* in = reinterpret_cast<const T*>(in_v);
+  T* out = reinterpret_cast<T*>(out_v);
+  if (two_step) {
+    if (rank != 3 || g < 2) return set_error(PH_ERR_INVALID, "two-step slab update needs rank 3 and 2 ghost planes");
+    bool used = false;
+    int32_t st = heat_tma2_planes<T>(in, out, n0, ext[1], ext[2], coeff, b, e, has_lo ? -1 : g, has_hi ? n0 : n0 - g - 1,
+                                     stream, &used);
+    if (st != PH_OK) return st;
+    if (!used) return set_error(PH_ERR_INVALID, "two-step slab update: buffers must be 16-byte aligned");
+    return PH_OK;
+  }
+  return heat_planes<T>(rank, ext, coeff, in, out, b, e, stream);
 }
 
 // exported to comm.cu
-int32_t heat_slab_dispatch(int32_t dtype, int rank, const int64_t* ext, const void* coeff_host, int has_lo,
+int32_t heat_slab_dispatch(int32_t dtype, int rank, const int64_t* ext, const void* coeff_host, int ghost, int has_lo,
                            int has_hi, int64_t p_begin, int64_t p_end, const void* in, void* out,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, bool two_step) {
   if (rank < 2 || rank > 3) return set_error(PH_ERR_UNSUPPORTED, "slab stencil needs rank 2 or 3 (got %d)", rank);
-  if (dtype == PH_F32) return heat_slab_t<float>(rank, ext, coeff_host, has_lo, has_hi, p_begin, p_end, in, out, stream);
-  if (dtype == PH_F64) return heat_slab_t<double>(rank, ext, coeff_host, has_lo, has_hi, p_begin, p_end, in, out, stream);
+  if (dtype == PH_F32) return heat_slab_t<float>(rank, ext, coeff_host, ghost, has_lo, has_hi, p_begin, p_end, in, out, stream, two_step);
+  if (dtype == PH_F64) return heat_slab_t<double>(rank, ext, coeff_host, ghost, has_lo, has_hi, p_begin, p_end, in, out, stream, two_step);
   return set_error(PH_ERR_UNSUPPORTED, "the heat stencil is defined for F32 / F64");
+}
+
+bool heat_two_step_usable(int32_t dtype, int rank, const int64_t* ext) {
+  if (rank != 3) return false;
+  if (dtype == PH_F32) return heat_tma2_usable<float>(ext[1], ext[2]);
+  if (dtype == PH_F64) return heat_tma2_usable<double>(ext[1], ext[2]);
+  return false;
 }
 
 }  // namespace ph
@@ -417,7 +443,20 @@ int32_t ph_heat_step_slab(int32_t dtype, int32_t rank, const int64_t* extents, c
   PH_REQUIRE_INIT();
   if (!extents || !coeff_host || !in || !out) return set_error(PH_ERR_INVALID, "null argument to ph_heat_step_slab");
   cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : rt().stream;
-  return heat_slab_dispatch(dtype, rank, extents, coeff_host, has_lo, has_hi, p_begin, p_end, in, out, s);
+  return heat_slab_dispatch(dtype, rank, extents, coeff_host, 1, has_lo, has_hi, p_begin, p_end, in, out, s, false);
+}
+
+int32_t ph_heat_pass_slab(int32_t dtype, int32_t rank, const int64_t* extents, const void* coeff_host,
+                          int32_t ghost_planes, int32_t two_steps, int32_t has_lo, int32_t has_hi, int64_t p_begin,
+                          int64_t p_end, const void* in, void* out, void* cuda_stream) {
+  PH_REQUIRE_INIT();
+  if (!extents || !coeff_host || !in || !out) return set_error(PH_ERR_INVALID, "null argument to ph_heat_pass_slab");
+  if (ghost_planes < 1 || ghost_planes > 2) return set_error(PH_ERR_INVALID, "ghost_planes must be 1 or 2");
+  if (two_steps && !heat_two_step_usable(dtype, rank, extents))
+    return set_error(PH_ERR_UNSUPPORTED, "the two-steps-per-pass kernel cannot take this grid (rank 3, x extent a multiple of 16 bytes)");
+  cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : rt().stream;
+  return heat_slab_dispatch(dtype, rank, extents, coeff_host, ghost_planes, has_lo, has_hi, p_begin, p_end, in, out, s,
+                            two_steps != 0);
 }
 
 }  // extern "C"

@@ -15,6 +15,7 @@
 #include "ops.cuh"
 #include <cuda.h>
 #include <algorithm>
+#include <type_traits>
 #include <stdlib.h>
 
 namespace ph {
@@ -151,16 +152,22 @@ __global__ void __launch_bounds__(32 * TMA_TY) heat_tma_kernel(const __grid_cons
 
 // ---------------------------------------------------------------------------- two steps per pass
 // Temporal blocking: one pass over HBM advances the grid by TWO time steps, so the traffic
-// per cell-update drops from 8 to 4 bytes (f32).  Ring A holds TMA-fed planes of time t with a
-// 2-cell halo; every plane p the block first computes time t+1 on a (TY+2) x (W+2) region
-// into ring B (shared memory only), then time t+2 on its TY x W tile for plane p-1 from ring
-// B and writes that to HBM.  Every cell value is produced by exactly the same operations in
-// the same order as two single-step passes (boundary cells are copied forward at t+1 just as
-// they are held by a single step), so the result is bit-identical.
-constexpr int TMA2_STAGES_A = 6;
-constexpr int TMA2_STAGES_B = 4;
-
-template <typename T, int TY> struct Tma2Tile {
+// per cell-update drops from 8 to ~4.5 bytes (f32) and the kernel stops being HBM-bound.
+// It is then bound by instruction issue, so the loop is built for a low instruction count:
+//   * ring A: TMA-fed planes of time t with a 2-cell halo (as above);
+//   * a thread owns TWO adjacent rows x one 16-byte group and marches along z keeping its own
+//     cells of planes p-1, p, p+1 (time t) AND of planes p-2, p-1, p (time t+1) in registers:
+//     per plane it reads only the new plane's own cells, the two rows above / below its pair
+//     and the x-neighbour cells from shared memory (1 LDS per cell-update instead of 1.75);
+//   * time t+1 of plane p goes to ring B (2 stages) only so that NEIGHBOUR threads can read
+//     it; time t+2 of plane p-1 is computed in the same iteration and streamed to HBM;
+//   * the (TY+2) x (W+2) halo of time t+1 is produced by two dedicated warps (one for the
+//     rows -1 / TY, one for the columns -1 / W), so the TY/2 main warps never diverge;
+//   * one __syncthreads per plane; role rotation by a 3x unrolled loop (no register copies).
+// Every cell value is produced by exactly the same operations in the same order as two
+// single-step passes (fixed cells are copied forward at t+1 just as a single step holds
+// them), so the result is bit-identical.
+template <typename T, int TY, int STAGES> struct Tma2Tile {
   static constexpr int E = 16 / (int)sizeof(T);
   static constexpr int W = 32 * E;
   static constexpr int PITCH = W + 2 * E;
@@ -168,7 +175,18 @@ template <typename T, int TY> struct Tma2Tile {
   static constexpr int A_BYTES = ROWS_A * PITCH * (int)sizeof(T);
   static constexpr int A_STAGE = (A_BYTES + 127) / 128 * 128;
   static constexpr int B_STAGE = (ROWS_B * PITCH * (int)sizeof(T) + 127) / 128 * 128;
-  static constexpr int SMEM = TMA2_STAGES_A * A_STAGE + TMA2_STAGES_B * B_STAGE;
+  static constexpr int SMEM = STAGES * A_STAGE + 2 * B_STAGE;
+  static constexpr int OWN_WARPS = TY / 2;
+  static constexpr int THREADS = 32 * (OWN_WARPS + 2);
+};
+
+template <typename T>
+struct HeatTma2Args {
+  T* out;
+  int64_t n0, n1, n2;
+  int64_t z_begin, z_end, z_chunk;
+  int64_t fixed_lo, fixed_hi;        // planes <= fixed_lo or >= fixed_hi are held (global boundary planes)
+  T coeff;
 };
 
 template <typename T>
@@ -180,25 +198,44 @@ __device__ __forceinline__ T heat7(T c, T zl, T zh, T yl, T yh, T xl, T xh, T co
   return f_add(c, f_mul(f_add(f_add(d0, d1), d2), coeff));
 }
 
-template <typename T, int TY>
-__global__ void __launch_bounds__(32 * TY) heat_tma2_kernel(const __grid_constant__ CUtensorMap in_map,
-                                                            const HeatTmaArgs<T> a) {
-  using Tile = Tma2Tile<T, TY>;
-  constexpr int E = Tile::E, PITCH = Tile::PITCH;
+template <typename T, int E, bool EDGE>
+__device__ __forceinline__ Group<T, E> heat_row(const Group<T, E>& c, const Group<T, E>& zl, const Group<T, E>& zh,
+                                                const Group<T, E>& yl, const Group<T, E>& yh, T xl, T xr, T coeff,
+                                                bool fix_first, bool fix_last) {
+  Group<T, E> res;
+#pragma unroll
+  for (int i = 0; i < E; i++) {
+    const T l = (i > 0) ? c.v[i - 1] : xl;
+    const T r = (i < E - 1) ? c.v[i + 1] : xr;
+    res.v[i] = heat7<T>(c.v[i], zl.v[i], zh.v[i], yl.v[i], yh.v[i], l, r, coeff);
+  }
+  if (EDGE) {                                   // first / last column of the grid is held
+    if (fix_first) res.v[0] = c.v[0];
+    if (fix_last) res.v[E - 1] = c.v[E - 1];
+  }
+  return res;
+}
+
+template <typename T, int TY, int STAGES>
+__global__ void __launch_bounds__(Tma2Tile<T, TY, STAGES>::THREADS, (TY <= 16 ? 2 : 1))
+heat_tma2_kernel(const __grid_constant__ CUtensorMap in_map, const HeatTma2Args<T> a) {
+  using Tile = Tma2Tile<T, TY, STAGES>;
+  using G = Group<T, Tile::E>;
+  constexpr int E = Tile::E, PITCH = Tile::PITCH, W = Tile::W;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ uint64_t full[TMA2_STAGES_A];
+  __shared__ uint64_t full[STAGES];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int64_t tile_x = (int64_t)blockIdx.x * Tile::W;
+  const int64_t tile_x = (int64_t)blockIdx.x * W;
   const int64_t tile_y = (int64_t)blockIdx.y * TY;
   const int64_t zb = a.z_begin + (int64_t)blockIdx.z * a.z_chunk;
   const int64_t ze = (zb + a.z_chunk < a.z_end) ? zb + a.z_chunk : a.z_end;
   if (zb >= ze) return;
-  T* const ringA = reinterpret_cast<T*>(smem_raw);
-  T* const ringB = reinterpret_cast<T*>(smem_raw + (size_t)TMA2_STAGES_A * Tile::A_STAGE);
+  const T* const ringA = reinterpret_cast<const T*>(smem_raw);
+  T* const ringB = reinterpret_cast<T*>(smem_raw + (size_t)STAGES * Tile::A_STAGE);
   constexpr int A_ELEMS = Tile::A_STAGE / (int)sizeof(T), B_ELEMS = Tile::B_STAGE / (int)sizeof(T);
 
-  // time-t planes zb-2 .. ze+1 stream through ring A in order; plane index k = plane - (zb-2)
+  // time-t planes zb-2 .. ze+1 stream through ring A in order; k = plane - (zb-2) lives in stage k % STAGES
   const int nA = (int)(ze - zb) + 4;
   auto issue = [&](int stage, int k) {
     mbar_expect_tx(&full[stage], (uint32_t)Tile::A_BYTES);
@@ -206,119 +243,187 @@ __global__ void __launch_bounds__(32 * TY) heat_tma2_kernel(const __grid_constan
                 (int)(zb - 2 + k), &full[stage]);
   };
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TMA2_STAGES_A; s++) mbar_init(&full[s], 1);
+    for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
   if (threadIdx.x == 0)
-    for (int k = 0; k < TMA2_STAGES_A && k < nA; k++) issue(k, k);
+    for (int k = 0; k < STAGES && k < nA; k++) issue(k, k);
 
-  // ---- per-thread geometry (tile-local row r in [-2, TY+1], col c in [-E, W+E-1])
-  const int c0 = lane * E;
-  auto offA = [&](int r, int c) { return (r + 2) * PITCH + (c + E); };
-  auto offB = [&](int r, int c) { return (r + 1) * PITCH + (c + E); };
-  // Boundary cells are carried forward unchanged.  Positions OUTSIDE the grid only ever feed
-  // boundary cells, so their values are don't-cares: only the grid's first / last row and
-  // column need a test, and those are per-thread constants.
+  // tile-local row r in [-2, TY+1], column c in [-E, W+E-1]
+  auto offA = [](int r, int c) { return (r + 2) * PITCH + (c + E); };
+  auto offB = [](int r, int c) { return (r + 1) * PITCH + (c + E); };
   const int64_t plane = a.n1 * a.n2;
-  const int64_t gy_own = tile_y + warp, gx_own = tile_x + c0;
-  const bool active = gx_own < a.n2 && gy_own < a.n1;
-  const bool fix_first = gx_own == 0, fix_last = gx_own + E == a.n2;
-  const bool row_fixed_own = gy_own == 0 || gy_own == a.n1 - 1;
-  const int r_extra = warp == 0 ? -1 : TY;
-  const int64_t gy_extra = tile_y + r_extra;
-  const bool row_fixed_extra = gy_extra == 0 || gy_extra == a.n1 - 1;
-  T* p_out = a.out + zb * plane + gy_own * a.n2 + gx_own;
+  const int iters = (int)(ze - zb) + 2;          // t+1 planes p = zb-1 .. ze; output plane q = p-1 once it >= 2
 
-  // time t+1 of the E cells at (r, c0) / of the single cell (r, c) of plane p into ring B
-  auto t1_group = [&](const T* Ap, const T* Ac, const T* An, T* Bc, int r, bool fixed) {
-    const int o = offA(r, c0);
-    const Group<T, E> cc = *reinterpret_cast<const Group<T, E>*>(Ac + o);
-    Group<T, E> res = cc;
-    if (!fixed) {
-      const Group<T, E> zl = *reinterpret_cast<const Group<T, E>*>(Ap + o);
-      const Group<T, E> zh = *reinterpret_cast<const Group<T, E>*>(An + o);
-      const Group<T, E> up = *reinterpret_cast<const Group<T, E>*>(Ac + o - PITCH);
-      const Group<T, E> dn = *reinterpret_cast<const Group<T, E>*>(Ac + o + PITCH);
-      const T xl = Ac[o - 1], xr = Ac[o + E];
-#pragma unroll
-      for (int i = 0; i < E; i++) {
-        const T l = (i > 0) ? cc.v[i - 1] : xl;
-        const T rr = (i < E - 1) ? cc.v[i + 1] : xr;
-        res.v[i] = heat7<T>(cc.v[i], zl.v[i], zh.v[i], up.v[i], dn.v[i], l, rr, a.coeff);
-      }
-      if (fix_first) res.v[0] = cc.v[0];
-      if (fix_last) res.v[E - 1] = cc.v[E - 1];
-    }
-    *reinterpret_cast<Group<T, E>*>(Bc + offB(r, c0)) = res;
-  };
-  // the extra columns -1 and W are never grid-boundary columns (tiles start on multiples of W)
-  auto t1_cell = [&](const T* Ap, const T* Ac, const T* An, T* Bc, int r, int c, bool fixed) {
-    const int o = offA(r, c);
-    const T cc = Ac[o];
-    Bc[offB(r, c)] = fixed ? cc : heat7<T>(cc, Ap[o], An[o], Ac[o - PITCH], Ac[o + PITCH], Ac[o - 1], Ac[o + 1], a.coeff);
-  };
-
-  int sa_p = 0, sa_c = 1, sa_n = 2;              // ring-A stages of time-t planes p-1, p, p+1
+  // ring bookkeeping shared by the three roles (identical in every thread)
+  int sc = 1, sn = 2;                            // stages of time-t planes p, p+1
   uint32_t par_n = 0;
-  int sb = 0;                                    // ring-B stage that receives time-(t+1) plane p
+  int bsel = 0;                                  // ring-B stage receiving time-(t+1) plane p
+  int it = 0;
+  int64_t p = zb - 1;
+  auto advance = [&]() {                         // end of a plane: recycle A[p]'s stage, rotate
+    __syncthreads();
+    if (threadIdx.x == 0 && it + STAGES + 1 < nA) issue(sc, it + STAGES + 1);
+    sc = sn;
+    if (++sn == STAGES) { sn = 0; par_n ^= 1; }
+    bsel ^= 1;
+    it++; p++;
+  };
+  // prologue common to all roles: planes zb-2 and zb-1 have landed; own cells are read by the
+  // caller, then stage 0 is recycled
   mbar_wait(&full[0], 0);
   mbar_wait(&full[1], 0);
-  // p runs over the time-(t+1) planes zb-1 .. ze; output plane q = p-1 is written once p >= zb+1
-  const int iters = (int)(ze - zb) + 2;
-  for (int it = 0; it < iters; it++) {
-    const int64_t p = zb - 1 + it;
-    mbar_wait(&full[sa_n], par_n);
-    const T* Ap = ringA + sa_p * A_ELEMS;
-    const T* Ac = ringA + sa_c * A_ELEMS;
-    const T* An = ringA + sa_n * A_ELEMS;
-    T* Bc = ringB + sb * B_ELEMS;
-    const bool plane_free = p >= 1 && p <= a.n0 - 2;
-    // ---- time t+1 on rows -1 .. TY, cols -1 .. W of plane p
-    {
-      const bool fx = !plane_free || row_fixed_own;
-      t1_group(Ap, Ac, An, Bc, warp, fx);
-      if (lane == 0) t1_cell(Ap, Ac, An, Bc, warp, -1, fx);
-      if (lane == 31) t1_cell(Ap, Ac, An, Bc, warp, Tile::W, fx);
-    }
-    if (warp < 2) {                              // the two extra rows
-      const bool fx = !plane_free || row_fixed_extra;
-      t1_group(Ap, Ac, An, Bc, r_extra, fx);
-      if (lane == 0) t1_cell(Ap, Ac, An, Bc, r_extra, -1, fx);
-      if (lane == 31) t1_cell(Ap, Ac, An, Bc, r_extra, Tile::W, fx);
-    }
-    __syncthreads();                             // ring-B plane p complete; ring-A plane p-1 no longer needed
-    if (threadIdx.x == 0 && it + TMA2_STAGES_A < nA) issue(sa_p, it + TMA2_STAGES_A);
-    // ---- time t+2 on the TY x W tile of plane q = p-1 from ring-B planes q-1, q, q+1
-    if (it >= 2) {
-      const T* Bq_l = ringB + ((sb + 2) & 3) * B_ELEMS;   // plane p-2
-      const T* Bq = ringB + ((sb + 3) & 3) * B_ELEMS;     // plane p-1
-      const T* Bq_h = Bc;                                  // plane p
-      const int o = offB(warp, c0);
-      const Group<T, E> cc = *reinterpret_cast<const Group<T, E>*>(Bq + o);
-      Group<T, E> res = cc;
-      if (!row_fixed_own) {
-        const Group<T, E> zl = *reinterpret_cast<const Group<T, E>*>(Bq_l + o);
-        const Group<T, E> zh = *reinterpret_cast<const Group<T, E>*>(Bq_h + o);
-        const Group<T, E> up = *reinterpret_cast<const Group<T, E>*>(Bq + o - PITCH);
-        const Group<T, E> dn = *reinterpret_cast<const Group<T, E>*>(Bq + o + PITCH);
-        const T xl = Bq[o - 1], xr = Bq[o + E];
-#pragma unroll
-        for (int i = 0; i < E; i++) {
-          const T l = (i > 0) ? cc.v[i - 1] : xl;
-          const T rr = (i < E - 1) ? cc.v[i + 1] : xr;
-          res.v[i] = heat7<T>(cc.v[i], zl.v[i], zh.v[i], up.v[i], dn.v[i], l, rr, a.coeff);
+
+  if (warp < Tile::OWN_WARPS + 1) {
+    // ------------------------------------------------------------ group rows: a pair of rows x one group per thread
+    const bool own = warp < Tile::OWN_WARPS;     // own rows 2w, 2w+1 (t+1 and t+2)  /  halo rows -1, TY (t+1 only)
+    const int r0 = own ? 2 * warp : -1, r1 = own ? 2 * warp + 1 : TY;
+    const int c0 = lane * E;
+    const int oa0 = offA(r0, c0), oa1 = offA(r1, c0), ob0 = offB(r0, c0), ob1 = offB(r1, c0);
+    const int64_t gx = tile_x + c0, gy0 = tile_y + r0, gy1 = tile_y + r1;
+    const bool fix_first = gx == 0, fix_last = gx + E == a.n2;
+    const bool rowfix0 = gy0 == 0 || gy0 == a.n1 - 1, rowfix1 = gy1 == 0 || gy1 == a.n1 - 1;
+    const bool act0 = own && gx < a.n2 && gy0 < a.n1, act1 = own && gx < a.n2 && gy1 < a.n1;
+    T* p_out0 = a.out + zb * plane + gy0 * a.n2 + gx;
+    T* p_out1 = p_out0 + a.n2;
+    const T coeff = a.coeff;
+    // warp-uniform: both rows lie strictly inside the grid and the tile is not the first / last
+    // in x, so no cell of this warp is ever held and every store is in range
+    const bool fast = own && gy0 > 0 && gy1 < a.n1 - 1 && tile_x > 0 && tile_x + W < a.n2;
+
+    G a0[3], a1[3], b0[3], b1[3];                // rotating roles: [P, C, N] of time t (a) and time t+1 (b)
+    a0[0] = *reinterpret_cast<const G*>(ringA + oa0);
+    a1[0] = *reinterpret_cast<const G*>(ringA + oa1);
+    a0[1] = *reinterpret_cast<const G*>(ringA + A_ELEMS + oa0);
+    a1[1] = *reinterpret_cast<const G*>(ringA + A_ELEMS + oa1);
+    b0[0] = a0[1]; b1[0] = a1[1]; b0[1] = a0[1]; b1[1] = a1[1];      // placeholders until two t+1 planes exist
+    __syncthreads();
+    if (threadIdx.x == 0 && STAGES < nA) issue(0, STAGES);
+
+    // OWN: adjacent rows (the pair shares its middle neighbours through registers) and the t+2
+    // phase; !OWN: the two halo rows.  FAST: no held cell, no range test (see `fast`); the first
+    // and the last plane of a march always take the general form (they may be held planes).
+    auto step = [&](auto own_t, auto fast_t, G& aP0, G& aP1, G& aC0, G& aC1, G& aN0, G& aN1, G& bP0, G& bP1, G& bC0,
+                    G& bC1, G& bN0, G& bN1) {
+      constexpr bool OWN = decltype(own_t)::value, FAST = decltype(fast_t)::value;
+      mbar_wait(&full[sn], par_n);               // planes land in order: p+1 here => p here
+      const T* An = ringA + sn * A_ELEMS;
+      const T* Ac = ringA + sc * A_ELEMS;
+      aN0 = *reinterpret_cast<const G*>(An + oa0);
+      aN1 = *reinterpret_cast<const G*>(An + oa1);
+      // ---- time t+1 of plane p, rows r0 / r1
+      {
+        const G up0 = *reinterpret_cast<const G*>(Ac + oa0 - PITCH);
+        const G dn1 = *reinterpret_cast<const G*>(Ac + oa1 + PITCH);
+        const T xl0 = Ac[oa0 - 1], xr0 = Ac[oa0 + E], xl1 = Ac[oa1 - 1], xr1 = Ac[oa1 + E];
+        if constexpr (OWN && FAST) {
+          bN0 = heat_row<T, E, false>(aC0, aP0, aN0, up0, aC1, xl0, xr0, coeff, false, false);
+          bN1 = heat_row<T, E, false>(aC1, aP1, aN1, aC0, dn1, xl1, xr1, coeff, false, false);
+        } else {
+          const bool plane_held = p <= a.fixed_lo || p >= a.fixed_hi;
+          G dn0, up1;
+          if constexpr (OWN) { dn0 = aC1; up1 = aC0; }
+          else { dn0 = *reinterpret_cast<const G*>(Ac + oa0 + PITCH); up1 = *reinterpret_cast<const G*>(Ac + oa1 - PITCH); }
+          const G t0 = heat_row<T, E, true>(aC0, aP0, aN0, up0, dn0, xl0, xr0, coeff, fix_first, fix_last);
+          const G t1 = heat_row<T, E, true>(aC1, aP1, aN1, up1, dn1, xl1, xr1, coeff, fix_first, fix_last);
+          bN0 = (plane_held || rowfix0) ? aC0 : t0;
+          bN1 = (plane_held || rowfix1) ? aC1 : t1;
         }
-        if (fix_first) res.v[0] = cc.v[0];
-        if (fix_last) res.v[E - 1] = cc.v[E - 1];
       }
-      if (active) store_group<T, E>(p_out, res);
-      p_out += plane;
+      T* Bw = ringB + bsel * B_ELEMS;
+      *reinterpret_cast<G*>(Bw + ob0) = bN0;
+      *reinterpret_cast<G*>(Bw + ob1) = bN1;
+      // ---- time t+2 of plane q = p-1 (own rows only): z-neighbours from registers, the rest from ring B
+      if (OWN && (FAST || it >= 2)) {            // a FAST step is never one of the first two planes
+        const T* Bq = ringB + (bsel ^ 1) * B_ELEMS;
+        const G up0 = *reinterpret_cast<const G*>(Bq + ob0 - PITCH);
+        const G dn1 = *reinterpret_cast<const G*>(Bq + ob1 + PITCH);
+        const T xl0 = Bq[ob0 - 1], xr0 = Bq[ob0 + E], xl1 = Bq[ob1 - 1], xr1 = Bq[ob1 + E];
+        if constexpr (FAST) {
+          const G res0 = heat_row<T, E, false>(bC0, bP0, bN0, up0, bC1, xl0, xr0, coeff, false, false);
+          const G res1 = heat_row<T, E, false>(bC1, bP1, bN1, bC0, dn1, xl1, xr1, coeff, false, false);
+          store_group<T, E>(p_out0, res0);
+          store_group<T, E>(p_out1, res1);
+        } else {
+          const G t0 = heat_row<T, E, true>(bC0, bP0, bN0, up0, bC1, xl0, xr0, coeff, fix_first, fix_last);
+          const G t1 = heat_row<T, E, true>(bC1, bP1, bN1, bC0, dn1, xl1, xr1, coeff, fix_first, fix_last);
+          if (act0) store_group<T, E>(p_out0, rowfix0 ? bC0 : t0);
+          if (act1) store_group<T, E>(p_out1, rowfix1 ? bC1 : t1);
+        }
+        p_out0 += plane; p_out1 += plane;
+      }
+      advance();
+    };
+#define PH_ROT0 a0[0], a1[0], a0[1], a1[1], a0[2], a1[2], b0[0], b1[0], b0[1], b1[1], b0[2], b1[2]
+#define PH_ROT1 a0[1], a1[1], a0[2], a1[2], a0[0], a1[0], b0[1], b1[1], b0[2], b1[2], b0[0], b1[0]
+#define PH_ROT2 a0[2], a1[2], a0[0], a1[0], a0[1], a1[1], b0[2], b1[2], b0[0], b1[0], b0[1], b1[1]
+    auto run = [&](auto own_t, auto fast_t) {
+      const std::false_type general;
+      step(own_t, general, PH_ROT0);             // it = 0: plane zb-1 may be a held plane, no output yet
+      step(own_t, general, PH_ROT1);             // it = 1: no output yet
+      while (iters - it >= 4) {
+        step(own_t, fast_t, PH_ROT2);
+        step(own_t, fast_t, PH_ROT0);
+        step(own_t, fast_t, PH_ROT1);
+      }
+      const int rem = iters - it;                // 1..3 planes left (iters >= 3); the last one may be a held plane
+      if (rem == 1) {
+        step(own_t, general, PH_ROT2);
+      } else if (rem == 2) {
+        step(own_t, fast_t, PH_ROT2);
+        step(own_t, general, PH_ROT0);
+      } else {
+        step(own_t, fast_t, PH_ROT2);
+        step(own_t, fast_t, PH_ROT0);
+        step(own_t, general, PH_ROT1);
+      }
+    };
+    if (fast) run(std::true_type{}, std::true_type{});
+    else if (own) run(std::true_type{}, std::false_type{});
+    else run(std::false_type{}, std::false_type{});
+#undef PH_ROT0
+#undef PH_ROT1
+#undef PH_ROT2
+  } else {
+    // ------------------------------------------------------------ edge columns -1 and W of time t+1, rows -1 .. TY
+    // (never grid-boundary columns: tiles start on multiples of W and n2 % E == 0)
+    const bool work = lane < TY + 2;
+    const int r = work ? lane - 1 : 0;
+    const int oa0 = offA(r, -1), oa1 = offA(r, W), ob0 = offB(r, -1), ob1 = offB(r, W);
+    const int64_t gy = tile_y + r;
+    const bool rowfix = gy == 0 || gy == a.n1 - 1;
+    const T coeff = a.coeff;
+    T e0[3], e1[3];
+    e0[0] = ringA[oa0]; e1[0] = ringA[oa1];
+    e0[1] = ringA[A_ELEMS + oa0]; e1[1] = ringA[A_ELEMS + oa1];
+    __syncthreads();
+    auto step = [&](T& eP0, T& eP1, T& eC0, T& eC1, T& eN0, T& eN1) {
+      mbar_wait(&full[sn], par_n);
+      const T* An = ringA + sn * A_ELEMS;
+      const T* Ac = ringA + sc * A_ELEMS;
+      eN0 = An[oa0]; eN1 = An[oa1];
+      T v0 = eC0, v1 = eC1;
+      if (!(p <= a.fixed_lo || p >= a.fixed_hi) && !rowfix) {
+        v0 = heat7<T>(eC0, eP0, eN0, Ac[oa0 - PITCH], Ac[oa0 + PITCH], Ac[oa0 - 1], Ac[oa0 + 1], coeff);
+        v1 = heat7<T>(eC1, eP1, eN1, Ac[oa1 - PITCH], Ac[oa1 + PITCH], Ac[oa1 - 1], Ac[oa1 + 1], coeff);
+      }
+      if (work) {
+        T* Bw = ringB + bsel * B_ELEMS;
+        Bw[ob0] = v0; Bw[ob1] = v1;
+      }
+      advance();
+    };
+    while (it + 3 <= iters) {
+      step(e0[0], e1[0], e0[1], e1[1], e0[2], e1[2]);
+      step(e0[1], e1[1], e0[2], e1[2], e0[0], e1[0]);
+      step(e0[2], e1[2], e0[0], e1[0], e0[1], e1[1]);
     }
-    sa_p = sa_c; sa_c = sa_n;
-    if (++sa_n == TMA2_STAGES_A) { sa_n = 0; par_n ^= 1; }
-    sb = (sb + 1) & 3;
+    if (it < iters) {
+      step(e0[0], e1[0], e0[1], e1[1], e0[2], e1[2]);
+      if (it < iters) step(e0[1], e1[1], e0[2], e1[2], e0[0], e1[0]);
+    }
   }
 }
 
@@ -390,19 +495,13 @@ static int32_t heat_tma_launch(const T* in, T* out, int64_t n0, int64_t n1, int6
 }
 
 // two steps per pass; *used = false => caller runs two single steps instead
-template <typename T>
-int32_t heat_tma2_planes(const T* in, T* out, int64_t n0, int64_t n1, int64_t n2, T coeff, int64_t z_begin,
-                         int64_t z_end, cudaStream_t stream, bool* used) {
-  constexpr int TY = 16;
-  using Tile = Tma2Tile<T, TY>;
-  *used = false;
-  if (z_begin >= z_end) { *used = true; return PH_OK; }
-  static const bool disabled = getenv("PH_HEAT_NO_TMA") != nullptr || getenv("PH_HEAT_NO_FUSE2") != nullptr;
-  if (disabled) return PH_OK;
+template <typename T, int TY, int STAGES>
+static int32_t heat_tma2_launch(const T* in, T* out, int64_t n0, int64_t n1, int64_t n2, T coeff, int64_t z_begin,
+                                int64_t z_end, int64_t fixed_lo, int64_t fixed_hi, cudaStream_t stream, bool* used) {
+  using Tile = Tma2Tile<T, TY, STAGES>;
+  static_assert(TY % 2 == 0 && TY + 2 <= 32, "the edge-column warp covers rows -1 .. TY with one lane each");
   EncodeTiledFn enc = encode_fn();
   if (!enc) return PH_OK;
-  if ((uintptr_t)in % 16 || (uintptr_t)out % 16 || (n2 * sizeof(T)) % 16 || n2 % Tile::E) return PH_OK;
-  if (n0 > 0x7fffffff || n1 > 0x7fffffff || n2 > 0x7fffffff) return PH_OK;
   CUtensorMap map;
   const cuuint64_t dims[3] = {(cuuint64_t)n2, (cuuint64_t)n1, (cuuint64_t)n0};
   const cuuint64_t strides[2] = {(cuuint64_t)n2 * sizeof(T), (cuuint64_t)n1 * n2 * sizeof(T)};
@@ -412,33 +511,69 @@ int32_t heat_tma2_planes(const T* in, T* out, int64_t n0, int64_t n1, int64_t n2
   CUresult r = enc(&map, dt, 3, const_cast<T*>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return PH_OK;
-  HeatTmaArgs<T> a;
+  HeatTma2Args<T> a;
   a.out = out; a.n0 = n0; a.n1 = n1; a.n2 = n2; a.coeff = coeff;
-  a.z_begin = z_begin; a.z_end = z_end;
+  a.z_begin = z_begin; a.z_end = z_end; a.fixed_lo = fixed_lo; a.fixed_hi = fixed_hi;
   const int64_t gx = ceil_div(n2, (int64_t)Tile::W), gy = ceil_div(n1, (int64_t)TY);
   const int64_t planes = z_end - z_begin;
-  // 2 resident blocks per SM x ~6 waves; chunks of >= 64 planes (each chunk recomputes 2 planes of t+1)
-  const int64_t want = (int64_t)rt().sm_count * 2 * 6;
+  // resident blocks per SM x ~6 waves; chunks of >= 64 planes (each chunk re-reads 4 planes and
+  // recomputes 2 planes of t+1)
+  const int per_sm = std::max(1, std::min(2, (int)(220 * 1024 / Tile::SMEM)));
+  const int64_t want = (int64_t)rt().sm_count * per_sm * 6;
   int64_t gz = std::max<int64_t>(1, std::min<int64_t>(ceil_div(want, gx * gy), ceil_div(planes, 64)));
   a.z_chunk = ceil_div(planes, gz);
   gz = ceil_div(planes, a.z_chunk);
   if (gy > 65535 || gz > 65535) return PH_OK;
   static bool attr_set = false;
   if (!attr_set) {
-    PH_CUDA(cudaFuncSetAttribute(heat_tma2_kernel<T, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tile::SMEM));
+    PH_CUDA(cudaFuncSetAttribute(heat_tma2_kernel<T, TY, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tile::SMEM));
     attr_set = true;
   }
-  dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)gz), block(32 * TY);
-  heat_tma2_kernel<T, TY><<<grid, block, Tile::SMEM, stream>>>(map, a);
+  dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)gz), block(Tile::THREADS);
+  heat_tma2_kernel<T, TY, STAGES><<<grid, block, Tile::SMEM, stream>>>(map, a);
   PH_LAUNCH_CHECK("heat_tma2_kernel");
   *used = true;
   return PH_OK;
 }
 
+// Planes [z_begin, z_end) of `out` receive time t+2; `in` holds time t on planes
+// [z_begin-2, z_end+2) (missing planes outside the array are never used: planes <= fixed_lo and
+// >= fixed_hi are held fixed, and a fixed plane ignores its neighbours).
+template <typename T>
+int32_t heat_tma2_planes(const T* in, T* out, int64_t n0, int64_t n1, int64_t n2, T coeff, int64_t z_begin,
+                         int64_t z_end, int64_t fixed_lo, int64_t fixed_hi, cudaStream_t stream, bool* used) {
+  *used = false;
+  if (z_begin >= z_end) { *used = true; return PH_OK; }
+  static const bool disabled = getenv("PH_HEAT_NO_TMA") != nullptr || getenv("PH_HEAT_NO_FUSE2") != nullptr;
+  if (disabled) return PH_OK;
+  constexpr int E = 16 / (int)sizeof(T);
+  if ((uintptr_t)in % 16 || (uintptr_t)out % 16 || (n2 * sizeof(T)) % 16 || n2 % E) return PH_OK;
+  if (n0 > 0x7fffffff || n1 > 0x7fffffff || n2 > 0x7fffffff) return PH_OK;
+  static const int cfg = getenv("PH_HEAT_TB_CFG") ? atoi(getenv("PH_HEAT_TB_CFG")) : 0;     // tuning knob
+  switch (cfg) {
+    case 1: return heat_tma2_launch<T, 16, 4>(in, out, n0, n1, n2, coeff, z_begin, z_end, fixed_lo, fixed_hi, stream, used);
+    case 2: return heat_tma2_launch<T, 16, 8>(in, out, n0, n1, n2, coeff, z_begin, z_end, fixed_lo, fixed_hi, stream, used);
+    case 3: return heat_tma2_launch<T, 24, 5>(in, out, n0, n1, n2, coeff, z_begin, z_end, fixed_lo, fixed_hi, stream, used);
+    case 4: return heat_tma2_launch<T, 8, 6>(in, out, n0, n1, n2, coeff, z_begin, z_end, fixed_lo, fixed_hi, stream, used);
+    default: return heat_tma2_launch<T, 16, 6>(in, out, n0, n1, n2, coeff, z_begin, z_end, fixed_lo, fixed_hi, stream, used);
+  }
+}
+
+// shape-only test (identical on every rank of a sharded run): can the two-step kernel take this grid?
+template <typename T>
+bool heat_tma2_usable(int64_t n1, int64_t n2) {
+  constexpr int E = 16 / (int)sizeof(T);
+  if (getenv("PH_HEAT_NO_TMA") != nullptr || getenv("PH_HEAT_NO_FUSE2") != nullptr) return false;
+  if (!encode_fn()) return false;
+  return n2 % E == 0 && n1 >= 3 && n2 >= 3 && n1 <= 0x7fffffff && n2 <= 0x7fffffff && ceil_div(n1, (int64_t)8) <= 65535;
+}
+template bool heat_tma2_usable<float>(int64_t, int64_t);
+template bool heat_tma2_usable<double>(int64_t, int64_t);
+
 template int32_t heat_tma2_planes<float>(const float*, float*, int64_t, int64_t, int64_t, float, int64_t, int64_t,
-                                         cudaStream_t, bool*);
+                                         int64_t, int64_t, cudaStream_t, bool*);
 template int32_t heat_tma2_planes<double>(const double*, double*, int64_t, int64_t, int64_t, double, int64_t, int64_t,
-                                          cudaStream_t, bool*);
+                                          int64_t, int64_t, cudaStream_t, bool*);
 
 template <typename T>
 int32_t heat_tma_planes(const T* in, T* out, int64_t n0, int64_t n1, int64_t n2, T coeff, int64_t z_begin,

@@ -4,7 +4,7 @@ Host logic only (which rows / planes a rank owns, who its neighbours are, how pe
 results combine) plus thin wrappers that drive the NCCL entry points of libphgpu.  The
 reference has no distributed layer; only what BASELINE.json's north_star partitions is here:
 elementwise ops and reductions split along the leading axis, the heat grid is slab-decomposed
-along axis 0 with one ghost plane per side.
+along axis 0 with one (or, for the two-steps-per-pass stencil, two) ghost planes per side.
 """
 from __future__ import annotations
 
@@ -25,24 +25,26 @@ def shard_range(n: int, world: int, rank: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < extra else 0)
 
 
-def slab_layout(n0: int, world: int, rank: int) -> dict:
+def slab_layout(n0: int, world: int, rank: int, ghost: int = 1) -> dict:
     """Slab of a grid split along axis 0: owned planes [start, stop) live at local planes
-    [1, 1 + count); local planes 0 and count + 1 are ghosts.  A rank at either end of the
-    grid has no neighbour there: its first / last owned plane is the fixed global boundary."""
+    [ghost, ghost + count); `ghost` planes on either side are ghosts (1: one time step per halo
+    exchange; 2: two, for the temporally blocked stencil).  A rank at either end of the grid has
+    no neighbour there: its first / last owned plane is the fixed global boundary."""
     start, stop = shard_range(n0, world, rank)
-    return {"start": start, "stop": stop, "count": stop - start, "local_planes": stop - start + 2,
+    return {"start": start, "stop": stop, "count": stop - start, "ghost": ghost,
+            "local_planes": stop - start + 2 * ghost,
             "lo_rank": rank - 1 if rank > 0 else -1, "hi_rank": rank + 1 if rank < world - 1 else -1}
 
 
-def slab_from_global(field: np.ndarray, world: int, rank: int) -> np.ndarray:
+def slab_from_global(field: np.ndarray, world: int, rank: int, ghost: int = 1) -> np.ndarray:
     """Local slab (with ghost planes filled from the neighbouring planes of `field`)."""
-    lay = slab_layout(field.shape[0], world, rank)
+    lay = slab_layout(field.shape[0], world, rank, ghost)
     loc = np.zeros((lay["local_planes"],) + field.shape[1:], dtype=field.dtype)
-    loc[1:-1] = field[lay["start"]:lay["stop"]]
+    loc[ghost:ghost + lay["count"]] = field[lay["start"]:lay["stop"]]
     if lay["lo_rank"] >= 0:
-        loc[0] = field[lay["start"] - 1]
+        loc[:ghost] = field[lay["start"] - ghost:lay["start"]]
     if lay["hi_rank"] >= 0:
-        loc[-1] = field[lay["stop"]]
+        loc[ghost + lay["count"]:] = field[lay["stop"]:lay["stop"] + ghost]
     return loc
 
 
@@ -136,16 +138,18 @@ def _allgather_host_int(v: int) -> List[int]:
     return [int(o.item()) for o in outs]
 
 
-def heat_run_sharded(slab, other, coeff, steps: int):
-    """`steps` steps on this rank's slab (ghost planes included) with the halo exchange
-    overlapped with the interior update; returns the buffer holding the final state."""
+def heat_run_sharded(slab, other, coeff, steps: int, ghost: int = 1):
+    """`steps` steps on this rank's slab (`ghost` ghost planes per side included) with the halo
+    exchange overlapped with the interior update; returns the buffer holding the final state.
+    ghost = 2 lets a rank-3 grid advance two time steps per pass over HBM and per exchange."""
     from .narray import dtype_code
     lib = _lib.load()
     c = np.array(coeff, dtype=slab.dtype)
     ext = (C.c_int64 * len(slab.shape))(*[int(s) for s in slab.shape])
-    check(lib.ph_heat_run_sharded(dtype_code(slab.dtype), len(slab.shape), ext, c.ctypes.data, slab.ptr, other.ptr,
-                                  int(steps)))
-    return other if steps % 2 else slab
+    final_is_b = C.c_int32(0)
+    check(lib.ph_heat_run_sharded(dtype_code(slab.dtype), len(slab.shape), ext, c.ctypes.data, int(ghost), slab.ptr,
+                                  other.ptr, int(steps), C.byref(final_is_b)))
+    return other if final_is_b.value else slab
 
 
 # ---------------------------------------------------------------- f-3: a sharded NArray

@@ -27,27 +27,30 @@ def main():
     world, rank = S.comm_init(dist)
     rs = np.random.RandomState(7)
 
-    # ---- heat, small grid vs oracle (uneven split)
+    # ---- heat, small grid vs oracle (uneven split); one ghost plane (a step per exchange) and two
+    #      (two time steps per pass and per exchange), odd and even step counts
     field = (rs.rand(4 * world + 3, 20, 36) * 100).astype(np.float32)
-    steps = 7
-    want = field.copy()
-    for _ in range(steps):
-        want = O.heat_step_nd(want, np.float32(0.1))
-    lay = S.slab_layout(field.shape[0], world, rank)
-    loc = S.slab_from_global(field, world, rank)
-    a, b = D.from_host(loc), D.from_host(loc)
-    fin = S.heat_run_sharded(a, b, 0.1, steps).to_host()[1:-1]
-    assert fin.tobytes() == want[lay["start"]:lay["stop"]].tobytes(), f"rank {rank}: small heat slab differs from oracle"
+    for ghost, steps in ((1, 7), (2, 7), (2, 6)):
+        want = field.copy()
+        for _ in range(steps):
+            want = O.heat_step_nd(want, np.float32(0.1))
+        lay = S.slab_layout(field.shape[0], world, rank, ghost)
+        loc = S.slab_from_global(field, world, rank, ghost)
+        a, b = D.from_host(loc), D.from_host(loc)
+        fin = S.heat_run_sharded(a, b, 0.1, steps, ghost).to_host()[ghost:-ghost]
+        assert fin.tobytes() == want[lay["start"]:lay["stop"]].tobytes(), \
+            f"rank {rank}: small heat slab (ghost {ghost}, {steps} steps) differs from oracle"
 
     # ---- heat, larger grid vs a single-GPU run of the same library (rank 0 computes it)
     big = (rs.rand(16 * world, 96, 256) * 100).astype(np.float32)
-    steps = 9
-    lay = S.slab_layout(big.shape[0], world, rank)
-    loc = S.slab_from_global(big, world, rank)
-    a, b = D.from_host(loc), D.from_host(loc)
-    fin = S.heat_run_sharded(a, b, 0.1, steps).to_host()[1:-1]
-    whole = heat.simulate(D.from_host(big), 0.1, steps).to_host()
-    assert fin.tobytes() == whole[lay["start"]:lay["stop"]].tobytes(), f"rank {rank}: big heat slab differs from 1-GPU run"
+    for ghost, steps in ((1, 9), (2, 9), (2, 12)):
+        lay = S.slab_layout(big.shape[0], world, rank, ghost)
+        loc = S.slab_from_global(big, world, rank, ghost)
+        a, b = D.from_host(loc), D.from_host(loc)
+        fin = S.heat_run_sharded(a, b, 0.1, steps, ghost).to_host()[ghost:-ghost]
+        whole = heat.simulate(D.from_host(big), 0.1, steps).to_host()
+        assert fin.tobytes() == whole[lay["start"]:lay["stop"]].tobytes(), \
+            f"rank {rank}: big heat slab (ghost {ghost}, {steps} steps) differs from 1-GPU run"
 
     # ---- sharded reductions
     data = rs.randint(-8, 9, size=(8 * world + 1, 50, 30)).astype(np.float32)

@@ -138,3 +138,64 @@ def test_heat_slab_matches_whole_grid():
         ph.check(lib.ph_d2d(b.ptr, a.ptr + half * plane, plane))                          # rank1 lo ghost <- rank0 last
     got = np.concatenate([slabs[0][steps & 1].to_host()[1:-1], slabs[1][steps & 1].to_host()[1:-1]])
     assert_bits(got, want, "two slabs == whole grid")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_two_step_slabs_match_whole_grid(dtype):
+    """Two slabs with TWO ghost planes per side, advanced two time steps per pass
+    (ph_heat_pass_slab, two_steps = 1) with the 2-plane halos exchanged by copies every pass:
+    bit-identical to the undivided grid stepped by the oracle."""
+    import ctypes as C
+    from ph_core_b200 import _lib
+    lib = _lib.load()
+    rs = np.random.RandomState(11)
+    shape = (22, 37, 144)
+    s = (rs.rand(*shape) * 100).astype(dtype)
+    c = np.array(0.1, dtype)
+    steps = 6
+    want = s.copy()
+    for _ in range(steps):
+        want = O.heat_step_nd(want, dtype(0.1))
+    g, half = 2, shape[0] // 2
+    slabs = []
+    for r in range(2):
+        loc = np.zeros((half + 2 * g,) + shape[1:], dtype)
+        loc[g:-g] = s[r * half:(r + 1) * half]
+        if r == 0:
+            loc[-g:] = s[half:half + g]
+        else:
+            loc[:g] = s[half - g:half]
+        slabs.append([D.from_host(loc), D.from_host(loc)])
+    ext = (C.c_int64 * 3)(half + 2 * g, shape[1], shape[2])
+    plane = shape[1] * shape[2] * np.dtype(dtype).itemsize
+    code = ph.K["PH_F32"] if dtype == np.float32 else ph.K["PH_F64"]
+    for t in range(steps // 2):
+        for r in range(2):
+            src, dst = slabs[r][t & 1], slabs[r][(t & 1) ^ 1]
+            # edges first, then the interior: the split a sharded run uses
+            for b, e in ((g, 2 * g), (half, half + g), (2 * g, half)):
+                ph.check(lib.ph_heat_pass_slab(code, 3, ext, c.ctypes.data, g, 1, int(r > 0), int(r < 1), b, e,
+                                               src.ptr, dst.ptr, None))
+        a, b = slabs[0][(t & 1) ^ 1], slabs[1][(t & 1) ^ 1]
+        ph.check(lib.ph_d2d(a.ptr + (half + g) * plane, b.ptr + g * plane, g * plane))    # rank0 hi ghosts <- rank1 first two
+        ph.check(lib.ph_d2d(b.ptr, a.ptr + half * plane, g * plane))                      # rank1 lo ghosts <- rank0 last two
+    fin = (steps // 2) & 1
+    got = np.concatenate([slabs[0][fin].to_host()[g:-g], slabs[1][fin].to_host()[g:-g]])
+    assert_bits(got, want, "two 2-ghost slabs, two steps per pass == whole grid")
+
+
+def test_sharded_run_single_rank_two_ghost_layout():
+    """ph_heat_run_sharded on a 1-rank communicator with the 2-ghost layout (no neighbours: the
+    ghost planes are unused and planes 2 / n-3 are the fixed boundary) == the plain run."""
+    from ph_core_b200 import sharding as S
+    S.comm_init()
+    rs = np.random.RandomState(12)
+    field = (rs.rand(19, 21, 40) * 100).astype(np.float32)
+    for steps in (5, 8):
+        want = field.copy()
+        for _ in range(steps):
+            want = O.heat_step_nd(want, np.float32(0.1))
+        loc = S.slab_from_global(field, 1, 0, ghost=2)
+        a, b = D.from_host(loc), D.from_host(loc)
+        got = S.heat_run_sharded(a, b, 0.1, steps, ghost=2).to_host()[2:-2]
+        assert_bits(got, want, f"1-rank sharded run, 2 ghost planes, {steps} steps")

@@ -56,6 +56,36 @@ def _worker(rank, world, port, out_dir):
             nxt[-1] = hi_recv.numpy()
         cur = nxt
     np.save(os.path.join(out_dir, f"heat_{rank}.npy"), cur[1:-1])
+    # ---- heat with TWO ghost planes per side: two time steps per 2-plane exchange (the layout the
+    #      temporally blocked kernel uses, ph_heat_run_sharded ghost_planes = 2)
+    g = 2
+    lay = S.slab_layout(field.shape[0], world, rank, ghost=g)
+    cur = S.slab_from_global(field, world, rank, ghost=g)
+    for _ in range(3):                                             # 3 passes = 6 steps
+        nxt = cur
+        for _ in range(2):
+            prev, nxt = nxt, O.heat_step_nd(nxt, np.float32(0.1))
+            if lay["lo_rank"] < 0:
+                nxt[:g + 1] = prev[:g + 1]                          # unused ghosts + the fixed global boundary plane
+            if lay["hi_rank"] < 0:
+                nxt[-g - 1:] = prev[-g - 1:]
+        # after two local steps only the owned planes are valid: refresh both ghost planes
+        reqs = []
+        lo_recv, hi_recv = torch.zeros(nxt[:g].shape), torch.zeros(nxt[:g].shape)
+        if lay["lo_rank"] >= 0:
+            reqs.append(dist.isend(torch.from_numpy(nxt[g:2 * g].copy()), lay["lo_rank"]))
+            reqs.append(dist.irecv(lo_recv, lay["lo_rank"]))
+        if lay["hi_rank"] >= 0:
+            reqs.append(dist.isend(torch.from_numpy(nxt[-2 * g:-g].copy()), lay["hi_rank"]))
+            reqs.append(dist.irecv(hi_recv, lay["hi_rank"]))
+        for r in reqs:
+            r.wait()
+        if lay["lo_rank"] >= 0:
+            nxt[:g] = lo_recv.numpy()
+        if lay["hi_rank"] >= 0:
+            nxt[-g:] = hi_recv.numpy()
+        cur = nxt
+    np.save(os.path.join(out_dir, f"heat2_{rank}.npy"), cur[g:-g])
     # ---- reductions over axis-0 shards
     data = rs.randint(-8, 9, size=(10, 7)).astype(np.float32)
     data[3, 2] = data[8, 1] = 50.0                                 # tie across the two shards
@@ -85,6 +115,9 @@ def test_two_rank_partitioning(tmp_path):
         want = O.heat_step_nd(want, np.float32(0.1))
     got = np.concatenate([np.load(tmp_path / f"heat_{r}.npy") for r in range(world)])
     assert got.tobytes() == want.tobytes()                          # slabbing changes no cell's arithmetic
+    want = O.heat_step_nd(want, np.float32(0.1))                    # 6 steps for the 2-ghost-plane run
+    got2 = np.concatenate([np.load(tmp_path / f"heat2_{r}.npy") for r in range(world)])
+    assert got2.tobytes() == want.tobytes()
     data = rs.randint(-8, 9, size=(10, 7)).astype(np.float32)
     data[3, 2] = data[8, 1] = 50.0
     for r in range(world):
@@ -105,6 +138,7 @@ def test_shard_ranges_cover_exactly():
             assert max(sizes) - min(sizes) <= 1
     lay = S.slab_layout(2048, 8, 0); assert lay["lo_rank"] == -1 and lay["hi_rank"] == 1 and lay["local_planes"] == 258
     lay = S.slab_layout(2048, 8, 7); assert lay["hi_rank"] == -1 and lay["start"] == 1792
+    lay = S.slab_layout(2048, 8, 3, ghost=2); assert lay["local_planes"] == 260 and lay["ghost"] == 2
     assert S.combine_extremum([3.0, 9.0, 9.0], [5, 40, 12], True) == (9.0, 12)
     assert S.combine_extremum([3.0, 1.0, 1.0], [5, 40, 12], False) == (1.0, 12)
     assert S.combine_extremum([3.0, 0.0], [5, -1], True) == (3.0, 5)    # empty shard ignored
