@@ -255,6 +255,32 @@ static int32_t try_copy_rows(const Plan& p, const void* src, void* dst, bool& do
   if (s_src == 1 && s_dst == 1) return PH_OK;
   if (s_dst == 0) return PH_OK;
   constexpr int E = 32 / (int)sizeof(T);
+  if (inner == 0) {
+    // One long strided row (e.g. a fully reversed contiguous array, whose axes coalesce into a
+    // single axis of stride -1): as a single row every thread would move ONE group and pay the
+    // whole per-thread setup for it (measured 55 instructions per element, 0.78 of peak).  Fold
+    // it back into rows of L elements so the row loop below amortises the setup; the remainder
+    // (< L elements) goes through the same path as a short row.
+    constexpr int64_t L = (int64_t)MAP_THREADS * E * 4;
+    if (p.extent[0] >= 2 * L) {
+      const int64_t rows = p.extent[0] / L;
+      Plan q = p;
+      q.rank = 2;
+      q.extent[0] = rows; q.extent[1] = L;
+      for (int k = 0; k < 2; k++) { q.stride[k][0] = L * p.stride[k][0]; q.stride[k][1] = p.stride[k][0]; }
+      q.total = rows * L;
+      int32_t st = try_copy_rows<T>(q, src, dst, done);
+      if (st != PH_OK || !done) return st;
+      const int64_t rem = p.extent[0] - rows * L;
+      if (rem > 0) {
+        Plan t = p;
+        t.extent[0] = rem; t.total = rem;
+        for (int k = 0; k < 2; k++) t.offset[k] = p.offset[k] + rows * L * p.stride[k][0];
+        st = try_copy_rows<T>(t, src, dst, done);
+      }
+      return st;
+    }
+  }
   CopyRowsArgs a;
   memset(&a, 0, sizeof(a));
   const T* sp = reinterpret_cast<const T*>(src) + p.offset[0];

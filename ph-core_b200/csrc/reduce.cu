@@ -48,6 +48,23 @@ template <typename T> __device__ __forceinline__ T shfl_xor_t(T v, int off) {
   }
 }
 
+// read a value another block of this launch wrote (L2, never a stale L1 line)
+template <typename T> __device__ __forceinline__ T ld_cg(const T* p) {
+  if constexpr (sizeof(T) == 16) {
+    const unsigned long long* q = reinterpret_cast<const unsigned long long*>(p);
+    const unsigned long long lo = __ldcg(q), hi = __ldcg(q + 1);
+    return (T)(((unsigned __int128)hi << 64) | lo);
+  } else if constexpr (sizeof(T) == 8) {
+    const unsigned long long v = __ldcg(reinterpret_cast<const unsigned long long*>(p));
+    T r; memcpy(&r, &v, 8); return r;
+  } else if constexpr (sizeof(T) == 4) {
+    const unsigned int v = __ldcg(reinterpret_cast<const unsigned int*>(p));
+    T r; memcpy(&r, &v, 4); return r;
+  } else {
+    return *reinterpret_cast<const volatile T*>(p);
+  }
+}
+
 template <typename T> __device__ __forceinline__ T lowest_of() {
   if constexpr (std::is_same<T, float>::value) return -__int_as_float(0x7f800000);
   else if constexpr (std::is_same<T, double>::value) return -__longlong_as_double(0x7ff0000000000000LL);
@@ -77,9 +94,15 @@ template <typename T> struct SumState {
   A s, pos, neg;
 };
 
+// The block that finishes LAST (atomic ticket) folds the per-block partials: no second launch, and
+// the fold order is fixed (thread j takes partials j, j+256, ... in order, then a fixed tree), so
+// the result is deterministic for a given grid.  out_value = the sum in T; status = 0 ok /
+// 1 definitely-overflow / 2 need the exact ordered pass (integers only).
 template <typename T, int E>
 __global__ void __launch_bounds__(RED_THREADS) sum_partial_kernel(const T* __restrict__ x, int64_t n,
-                                                                  SumState<T>* __restrict__ partials) {
+                                                                  SumState<T>* __restrict__ partials,
+                                                                  T* __restrict__ out_value, int* __restrict__ status,
+                                                                  unsigned int* __restrict__ ticket) {
   using A = typename Acc<T>::type;
   constexpr bool IS_INT = !is_float_t<T>::value;
   constexpr int UNROLL = 4;
@@ -124,51 +147,59 @@ __global__ void __launch_bounds__(RED_THREADS) sum_partial_kernel(const T* __res
   for (int i = 1; i < E; i++) {
     if constexpr (IS_INT) s += acc[i]; else s = f_add(s, acc[i]);
   }
-  // warp then block tree (fixed order => deterministic)
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    if constexpr (IS_INT) {
-      s += shfl_down_t<A>(s, off); pos += shfl_down_t<A>(pos, off); neg += shfl_down_t<A>(neg, off);
-    } else {
-      s = f_add(s, shfl_down_t<A>(s, off));
-    }
-  }
   __shared__ A sh_s[RED_THREADS / 32], sh_p[RED_THREADS / 32], sh_n[RED_THREADS / 32];
+  __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) { sh_s[warp] = s; sh_p[warp] = pos; sh_n[warp] = neg; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    A ts = sh_s[0], tp = sh_p[0], tn = sh_n[0];
-    for (int w = 1; w < RED_THREADS / 32; w++) {
-      if constexpr (IS_INT) { ts += sh_s[w]; tp += sh_p[w]; tn += sh_n[w]; }
-      else ts = f_add(ts, sh_s[w]);
+  // warp then block tree (fixed order => deterministic); thread 0 ends up with the block totals
+  auto block_fold = [&](A& ts, A& tp, A& tn) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      if constexpr (IS_INT) {
+        ts += shfl_down_t<A>(ts, off); tp += shfl_down_t<A>(tp, off); tn += shfl_down_t<A>(tn, off);
+      } else {
+        ts = f_add(ts, shfl_down_t<A>(ts, off));
+      }
     }
-    partials[blockIdx.x].s = ts; partials[blockIdx.x].pos = tp; partials[blockIdx.x].neg = tn;
+    if (lane == 0) { sh_s[warp] = ts; sh_p[warp] = tp; sh_n[warp] = tn; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      ts = sh_s[0]; tp = sh_p[0]; tn = sh_n[0];
+      for (int w = 1; w < RED_THREADS / 32; w++) {
+        if constexpr (IS_INT) { ts += sh_s[w]; tp += sh_p[w]; tn += sh_n[w]; }
+        else ts = f_add(ts, sh_s[w]);
+      }
+    }
+  };
+  block_fold(s, pos, neg);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x].s = s; partials[blockIdx.x].pos = pos; partials[blockIdx.x].neg = neg;
+    __threadfence();
+    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
   }
-}
-
-// final: one block; result[0] = value (T), status[0] = 0 ok / 1 definitely-overflow / 2 need exact pass
-template <typename T>
-__global__ void sum_final_kernel(const SumState<T>* __restrict__ partials, int nparts, T* __restrict__ out_value,
-                                 int* __restrict__ status) {
-  using A = typename Acc<T>::type;
-  constexpr bool IS_INT = !is_float_t<T>::value;
-  if (threadIdx.x != 0) return;
-  A s = 0, p = 0, ng = 0;
-  for (int i = 0; i < nparts; i++) {
-    if constexpr (IS_INT) { s += partials[i].s; p += partials[i].pos; ng += partials[i].neg; }
-    else s = f_add(s, partials[i].s);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  A fs = 0, fp = 0, fn = 0;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += RED_THREADS) {
+    const SumState<T>* q = partials + i;
+    if constexpr (IS_INT) { fs += ld_cg(&q->s); fp += ld_cg(&q->pos); fn += ld_cg(&q->neg); }
+    else fs = f_add(fs, ld_cg(&q->s));
   }
-  if constexpr (IS_INT) {
-    const A hi = (A)std::numeric_limits<T>::max(), lo = (A)std::numeric_limits<T>::lowest();
-    int st = 0;
-    if (s > hi || s < lo) st = 1;                    // the final prefix itself overflows
-    else if (p > hi || ng < lo) st = 2;              // some prefix MIGHT overflow: decide exactly
-    *status = st;
-    *out_value = (T)s;
-  } else {
-    *status = 0;
-    *out_value = s;
+  __syncthreads();                                   // sh_* are reused
+  block_fold(fs, fp, fn);
+  if (threadIdx.x == 0) {
+    if constexpr (IS_INT) {
+      const A hi = (A)std::numeric_limits<T>::max(), lo = (A)std::numeric_limits<T>::lowest();
+      int st = 0;
+      if (fs > hi || fs < lo) st = 1;                // the final prefix itself overflows
+      else if (fp > hi || fn < lo) st = 2;           // some prefix MIGHT overflow: decide exactly
+      *status = st;
+      *out_value = (T)fs;
+    } else {
+      *status = 0;
+      *out_value = fs;
+    }
+    *ticket = 0;                                     // ready for the next launch on this stream
   }
 }
 
@@ -239,14 +270,22 @@ __device__ __forceinline__ T ext2(T a, T b, bool& nan) {
   }
 }
 
+// Hot loop: 4 x 32-byte loads, the extremum of the 32 register values, and -- only when a tile
+// strictly improves on the running extremum -- the tile NUMBER.  The first index inside the
+// winning tile is searched once per thread after the loop (the tile is re-read, 128 bytes), so
+// the loop carries no index arithmetic and few registers.  Tiles are visited in increasing
+// index order, so "strictly improves" keeps the FIRST extremum.  The last block to finish
+// (atomic ticket) folds the per-block candidates: no second launch.
 template <typename T, int E, bool IS_MAX>
 __global__ void __launch_bounds__(RED_THREADS) ext_partial_kernel(const T* __restrict__ x, int64_t n,
                                                                   Cand<T>* __restrict__ partials,
-                                                                  uint32_t* __restrict__ flags) {
+                                                                  uint32_t* __restrict__ flags,
+                                                                  T* __restrict__ out_value,
+                                                                  int64_t* __restrict__ out_index,
+                                                                  unsigned int* __restrict__ ticket) {
   constexpr int UNROLL = 4;
-  Cand<T> best;
-  best.v = IS_MAX ? lowest_of<T>() : highest_of<T>();
-  best.i = INT64_MAX;
+  T best_v = IS_MAX ? lowest_of<T>() : highest_of<T>();
+  int64_t best_t = -1;
   bool nan = false;
   const int64_t tile = (int64_t)RED_THREADS * E * UNROLL;
   const int64_t ntiles = n / tile;
@@ -255,7 +294,6 @@ __global__ void __launch_bounds__(RED_THREADS) ext_partial_kernel(const T* __res
     Group<T, E> g[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; u++) g[u] = load_group<T, E>(x + base + (int64_t)u * RED_THREADS * E);
-    // 1. extremum of this thread's 4*E register values (1 instruction per element for f32)
     T m = g[0].v[0];
     if constexpr (is_float_t<T>::value && !std::is_same<T, float>::value) nan |= (m != m);
 #pragma unroll
@@ -264,20 +302,25 @@ __global__ void __launch_bounds__(RED_THREADS) ext_partial_kernel(const T* __res
       for (int i = 0; i < E; i++)
         if (u || i) m = ext2<T, IS_MAX>(m, g[u].v[i], nan);
     if constexpr (std::is_same<T, float>::value) nan |= (m != m);
-    // 2. only a strictly better tile can change the answer (indices grow with t, so on a tie
-    //    the earlier element stays); then find the FIRST register holding the extremum.
-    const bool improves = IS_MAX ? (m > best.v) : (m < best.v);
-    if (improves || (best.i == INT64_MAX && m == best.v)) {
-      bool found = false;
+    const bool improves = IS_MAX ? (m > best_v) : (m < best_v);
+    if (improves || (best_t < 0 && m == best_v)) { best_v = m; best_t = t; }
+  }
+  Cand<T> best;
+  best.v = best_v;
+  best.i = INT64_MAX;
+  if (best_t >= 0) {                                 // first register of the winning tile holding the extremum
+    const int64_t base = best_t * tile + (int64_t)threadIdx.x * E;
+    bool found = false;
 #pragma unroll
-      for (int u = 0; u < UNROLL; u++)
+    for (int u = 0; u < UNROLL; u++) {
+      const Group<T, E> g = load_group_plain<T, E>(x + base + (int64_t)u * RED_THREADS * E);
 #pragma unroll
-        for (int i = 0; i < E; i++)
-          if (!found && g[u].v[i] == m) {
-            found = true;
-            best.v = g[u].v[i];                      // the element itself (keeps the sign of a zero)
-            best.i = base + (int64_t)u * RED_THREADS * E + i;
-          }
+      for (int i = 0; i < E; i++)
+        if (!found && g.v[i] == best_v) {
+          found = true;
+          best.v = g.v[i];                           // the element itself (keeps the sign of a zero)
+          best.i = base + (int64_t)u * RED_THREADS * E + i;
+        }
     }
   }
   if (blockIdx.x == 0) {
@@ -288,33 +331,50 @@ __global__ void __launch_bounds__(RED_THREADS) ext_partial_kernel(const T* __res
       best = better<T, IS_MAX>(best, c);
     }
   }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    Cand<T> o;
-    o.v = __shfl_down_sync(0xffffffffu, best.v, off);
-    o.i = __shfl_down_sync(0xffffffffu, best.i, off);
-    best = better<T, IS_MAX>(best, o);
-  }
   __shared__ Cand<T> sh[RED_THREADS / 32];
+  __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) sh[warp] = best;
+  auto block_fold = [&](Cand<T>& b) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      Cand<T> o;
+      o.v = __shfl_down_sync(0xffffffffu, b.v, off);
+      o.i = __shfl_down_sync(0xffffffffu, b.i, off);
+      b = better<T, IS_MAX>(b, o);
+    }
+    if (lane == 0) sh[warp] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      b = sh[0];
+      for (int w = 1; w < RED_THREADS / 32; w++) b = better<T, IS_MAX>(b, sh[w]);
+    }
+  };
+  block_fold(best);
   if (nan) atomicOr(flags, (uint32_t)PH_FLAG_NAN);
-  __syncthreads();
   if (threadIdx.x == 0) {
-    Cand<T> b = sh[0];
-    for (int w = 1; w < RED_THREADS / 32; w++) b = better<T, IS_MAX>(b, sh[w]);
-    partials[blockIdx.x] = b;
+    partials[blockIdx.x] = best;
+    __threadfence();
+    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
   }
-}
-
-template <typename T, bool IS_MAX>
-__global__ void ext_final_kernel(const Cand<T>* __restrict__ partials, int nparts, T* __restrict__ out_value,
-                                 int64_t* __restrict__ out_index) {
-  if (threadIdx.x != 0) return;
-  Cand<T> b = partials[0];
-  for (int i = 1; i < nparts; i++) b = better<T, IS_MAX>(b, partials[i]);
-  *out_value = b.v;
-  if (out_index) *out_index = b.i;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  Cand<T> fin;
+  fin.v = IS_MAX ? lowest_of<T>() : highest_of<T>();
+  fin.i = INT64_MAX;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += RED_THREADS) {
+    Cand<T> c;
+    c.v = ld_cg(&partials[i].v);
+    c.i = ld_cg(&partials[i].i);
+    fin = better<T, IS_MAX>(fin, c);
+  }
+  __syncthreads();                                   // sh is reused
+  block_fold(fin);
+  if (threadIdx.x == 0) {
+    *out_value = fin.v;
+    if (out_index) *out_index = fin.i;
+    *ticket = 0;
+  }
 }
 
 // ---------------------------------------------------------------- per-axis: [outer, K, inner]
@@ -512,6 +572,114 @@ __global__ void __launch_bounds__(RED_THREADS) axis_row_kernel(const T* __restri
   if (nan) atomicOr(flags, (uint32_t)PH_FLAG_NAN);
 }
 
+// inner == 1, short rows (K <= 32 lanes x G groups x E elements): the whole row lives in the
+// registers of TX <= 32 lanes of ONE warp.  Every lane issues all of its G 32-byte loads before
+// the first use (no loop, no trip-count arithmetic: the looped kernel above spent ~7 instructions
+// per element and was latency-bound at 0.87 of the copy peak), folds them, and the lanes combine
+// with shuffles.  arg* / a zero extremum: only lanes whose own extremum equals the row's search
+// their registers for the first match (no second pass over memory).
+template <typename T, int E, int G, int RED>
+__global__ void __launch_bounds__(RED_THREADS) axis_rowreg_kernel(const T* __restrict__ x, void* __restrict__ out,
+                                                                  int64_t rows, int64_t K, int tx_log2,
+                                                                  uint32_t* __restrict__ flags) {
+  constexpr bool IS_MAXLIKE = (RED == PH_MAX || RED == PH_ARGMAX);
+  constexpr bool IS_ARG = (RED == PH_ARGMAX || RED == PH_ARGMIN);
+  using A = typename Acc<T>::type;
+  const int tx = 1 << tx_log2;
+  const int lane = threadIdx.x & (tx - 1);
+  const int64_t row = (int64_t)blockIdx.x * (RED_THREADS >> tx_log2) + (threadIdx.x >> tx_log2);
+  const bool live = row < rows;
+  const T* p = x + (live ? row : 0) * K;
+  const int groups = (int)(K / E);                // K % E == 0 and groups <= 32 * G by dispatch
+  Group<T, E> g[G];
+  bool has[G];
+#pragma unroll
+  for (int u = 0; u < G; u++) {
+    const int gi = lane + u * tx;
+    has[u] = live && gi < groups;
+    if (has[u]) g[u] = load_group<T, E>(p + (int64_t)gi * E);
+  }
+  bool nan = false;
+  uint32_t err = 0;
+  if constexpr (RED == PH_SUM) {
+    A s = 0, pos = 0, neg = 0;
+    if constexpr (is_float_t<T>::value) {
+      A acc[E];
+#pragma unroll
+      for (int i = 0; i < E; i++) acc[i] = has[0] ? g[0].v[i] : (T)0;
+#pragma unroll
+      for (int u = 1; u < G; u++)
+        if (has[u]) {
+#pragma unroll
+          for (int i = 0; i < E; i++) acc[i] = f_add(acc[i], g[u].v[i]);
+        }
+#pragma unroll
+      for (int w = E / 2; w > 0; w >>= 1)
+#pragma unroll
+        for (int i = 0; i < w; i++) acc[i] = f_add(acc[i], acc[i + w]);
+      s = acc[0];
+    } else {
+#pragma unroll
+      for (int u = 0; u < G; u++)
+        if (has[u]) {
+#pragma unroll
+          for (int i = 0; i < E; i++) { const A v = (A)g[u].v[i]; s += v; if (v > 0) pos += v; else neg += v; }
+        }
+    }
+    for (int off = tx >> 1; off > 0; off >>= 1) {
+      if constexpr (is_float_t<T>::value) s = f_add(s, shfl_xor_t<A>(s, off));
+      else { s += shfl_xor_t<A>(s, off); pos += shfl_xor_t<A>(pos, off); neg += shfl_xor_t<A>(neg, off); }
+    }
+    if (lane == 0 && live) {
+      if constexpr (!is_float_t<T>::value) {
+        const A hi = (A)std::numeric_limits<T>::max(), lo = (A)std::numeric_limits<T>::lowest();
+        if (pos > hi || neg < lo) {               // some prefix might leave T: replay the row in order (rare)
+          A run = 0;
+          for (int64_t k = 0; k < K; k++) { run += (A)p[k]; if (run > hi || run < lo) { err |= PH_FLAG_OVERFLOW; break; } }
+        }
+      }
+      reinterpret_cast<T*>(out)[row] = (T)s;
+    }
+  } else {
+    T m = IS_MAXLIKE ? lowest_of<T>() : highest_of<T>();
+#pragma unroll
+    for (int u = 0; u < G; u++)
+      if (has[u]) {
+#pragma unroll
+        for (int i = 0; i < E; i++) m = ext2<T, IS_MAXLIKE>(m, g[u].v[i], nan);
+      }
+    T M = m;
+    for (int off = tx >> 1; off > 0; off >>= 1) M = ext2<T, IS_MAXLIKE>(M, __shfl_xor_sync(0xffffffffu, M, off), nan);
+    if constexpr (std::is_same<T, float>::value) nan |= (M != M);
+    int32_t bi = INT32_MAX;
+    T zv = M;
+    const bool need_index = IS_ARG || (is_float_t<T>::value && M == (T)0);
+    // rows sharing a warp (TX < 32) may disagree on need_index: branch on a warp-uniform vote so
+    // the shuffles below are executed by all 32 lanes
+    const bool warp_need = IS_ARG ? true : (__any_sync(0xffffffffu, need_index) != 0);
+    if (warp_need) {
+      if (need_index && m == M) {                 // NaN rows never match
+#pragma unroll
+        for (int u = 0; u < G; u++)
+#pragma unroll
+          for (int i = 0; i < E; i++)
+            if (has[u] && bi == INT32_MAX && g[u].v[i] == M) { bi = (lane + u * tx) * E + i; zv = g[u].v[i]; }
+      }
+      for (int off = tx >> 1; off > 0; off >>= 1) {
+        const int32_t ob = __shfl_xor_sync(0xffffffffu, bi, off);
+        const T oz = __shfl_xor_sync(0xffffffffu, zv, off);
+        if (ob < bi) { bi = ob; zv = oz; }
+      }
+    }
+    if (lane == 0 && live) {
+      if constexpr (IS_ARG) reinterpret_cast<int64_t*>(out)[row] = (bi == INT32_MAX) ? 0 : (int64_t)bi;
+      else reinterpret_cast<T*>(out)[row] = (need_index && bi != INT32_MAX) ? zv : M;   // keeps the first zero's sign
+    }
+  }
+  if (err) atomicOr(flags, err);
+  if (nan) atomicOr(flags, (uint32_t)PH_FLAG_NAN);
+}
+
 // ---------------------------------------------------------------- host side
 static bool desc_is_contiguous(const ph_desc* d, int64_t& total) {
   total = 1;
@@ -547,6 +715,16 @@ static int32_t contiguous_input(const void* a, const ph_desc* d, const T** out_p
   return PH_OK;
 }
 
+// one zero-initialised device word; the last block of every fused reduction resets it
+static unsigned int* reduce_ticket() {
+  static unsigned int* t = nullptr;
+  if (!t) {
+    if (cudaMalloc(&t, 256) != cudaSuccess) { t = nullptr; return nullptr; }
+    cudaMemset(t, 0, 256);
+  }
+  return t;
+}
+
 template <typename T>
 static int32_t reduce_full_t(int32_t red, const void* a, const ph_desc* d, void* out_value_dev,
                              int64_t* out_index_dev) {
@@ -556,11 +734,24 @@ static int32_t reduce_full_t(int32_t red, const void* a, const ph_desc* d, void*
   int64_t n;
   int32_t st = contiguous_input<T>(a, d, &x, &temp, n);
   if (st != PH_OK) return st;
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)r.sm_count * 8,
+  // persistent grid: exactly the blocks that are resident at once (a partial second wave would
+  // leave the GPU mostly idle while it runs), fewer for small inputs
+  static int resident_sum = 0, resident_ext = 0;
+  if (!resident_sum) {
+    int a = 0, b = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sum_partial_kernel<T, 32 / (int)sizeof(T)>, RED_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ext_partial_kernel<T, 32 / (int)sizeof(T), true>, RED_THREADS, 0);
+    resident_sum = std::max(1, a);
+    resident_ext = std::max(1, b);
+  }
+  const int per_sm = (red == PH_SUM) ? resident_sum : resident_ext;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)r.sm_count * per_sm,
                                                                ceil_div(n, (int64_t)RED_THREADS * 32)));
   st = ensure_scratch((size_t)grid * 64 + 256);
   if (st != PH_OK) return st;
   int* status = reinterpret_cast<int*>(reinterpret_cast<char*>(r.d_scratch) + (size_t)grid * 64);
+  unsigned int* ticket = reduce_ticket();
+  if (!ticket) return set_error(PH_ERR_CUDA, "cannot allocate the reduction ticket");
   constexpr int E32 = 32 / (int)sizeof(T);
   const bool al32 = ((uintptr_t)x % 32) == 0;
   if (red == PH_SUM) {
@@ -569,11 +760,10 @@ static int32_t reduce_full_t(int32_t red, const void* a, const ph_desc* d, void*
     } else {
       SumState<T>* parts = reinterpret_cast<SumState<T>*>(r.d_scratch);
       static_assert(sizeof(SumState<T>) <= 64, "partial too large");
-      if (al32) sum_partial_kernel<T, E32><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts);
-      else sum_partial_kernel<T, 1><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts);
+      T* ov = reinterpret_cast<T*>(out_value_dev);
+      if (al32) sum_partial_kernel<T, E32><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, ov, status, ticket);
+      else sum_partial_kernel<T, 1><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, ov, status, ticket);
       PH_LAUNCH_CHECK("sum_partial_kernel");
-      sum_final_kernel<T><<<1, 32, 0, r.stream>>>(parts, grid, reinterpret_cast<T*>(out_value_dev), status);
-      PH_LAUNCH_CHECK("sum_final_kernel");
       if constexpr (!is_float_t<T>::value) {
         int* h = reinterpret_cast<int*>(r.h_scratch);
         PH_CUDA(cudaMemcpyAsync(h, status, sizeof(int), cudaMemcpyDeviceToHost, r.stream));
@@ -604,18 +794,15 @@ static int32_t reduce_full_t(int32_t red, const void* a, const ph_desc* d, void*
     } else {
       Cand<T>* parts = reinterpret_cast<Cand<T>*>(r.d_scratch);
       const bool is_max = (red == PH_MAX || red == PH_ARGMAX);
+      T* ov = reinterpret_cast<T*>(out_value_dev);
       if (is_max) {
-        if (al32) ext_partial_kernel<T, E32, true><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags);
-        else ext_partial_kernel<T, 1, true><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags);
-        PH_LAUNCH_CHECK("ext_partial_kernel");
-        ext_final_kernel<T, true><<<1, 32, 0, r.stream>>>(parts, grid, reinterpret_cast<T*>(out_value_dev), out_index_dev);
+        if (al32) ext_partial_kernel<T, E32, true><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags, ov, out_index_dev, ticket);
+        else ext_partial_kernel<T, 1, true><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags, ov, out_index_dev, ticket);
       } else {
-        if (al32) ext_partial_kernel<T, E32, false><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags);
-        else ext_partial_kernel<T, 1, false><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags);
-        PH_LAUNCH_CHECK("ext_partial_kernel");
-        ext_final_kernel<T, false><<<1, 32, 0, r.stream>>>(parts, grid, reinterpret_cast<T*>(out_value_dev), out_index_dev);
+        if (al32) ext_partial_kernel<T, E32, false><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags, ov, out_index_dev, ticket);
+        else ext_partial_kernel<T, 1, false><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags, ov, out_index_dev, ticket);
       }
-      PH_LAUNCH_CHECK("ext_final_kernel");
+      PH_LAUNCH_CHECK("ext_partial_kernel");
     }
   } else {
     if (temp) cudaFreeAsync(temp, r.stream);
@@ -653,6 +840,17 @@ static int32_t reduce_axis_launch(const T* x, void* out, int64_t outer, int64_t 
   const bool vec = E32 > 1 && K % E32 == 0 && ((uintptr_t)x % 32) == 0;
   const int e = vec ? E32 : 1;
   const int64_t groups = K / e;
+  if (vec && groups <= 32 * 8) {                  // the row fits the registers of one warp
+    const int G = groups <= 32 * 4 ? 4 : 8;
+    int tx = 1, lg = 0;
+    while (tx < 32 && (int64_t)tx * G < groups) { tx <<= 1; lg++; }
+    const int64_t blocks = ceil_div(outer, (int64_t)(RED_THREADS / tx));
+    if (blocks > 0x7fffffffLL) return set_error(PH_ERR_INVALID, "array too large for one launch");
+    if (G == 4) axis_rowreg_kernel<T, E32, 4, RED><<<(unsigned)blocks, RED_THREADS, 0, r.stream>>>(x, out, outer, K, lg, r.d_flags);
+    else axis_rowreg_kernel<T, E32, 8, RED><<<(unsigned)blocks, RED_THREADS, 0, r.stream>>>(x, out, outer, K, lg, r.d_flags);
+    PH_LAUNCH_CHECK("axis_rowreg_kernel");
+    return PH_OK;
+  }
   int tx = 1, lg = 0;
   while (tx < RED_THREADS && (int64_t)tx * 8 < groups) { tx <<= 1; lg++; }   // <= 8 groups per lane
   const int ty = RED_THREADS / tx;

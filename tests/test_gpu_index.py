@@ -237,6 +237,27 @@ def test_large_strided_configs_small_scale():
     assert_bits(z.to_host(), np.ascontiguousarray(n.T), "transposed scatter")
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.uint8, np.int16])
+def test_long_single_row_strided_copies(dtype):
+    """One long strided row (axes of a reversed contiguous array coalesce into a single axis): the
+    copy folds it into rows of L elements plus a remainder; gathers and scatters, steps -1, 2, -3."""
+    n = 5 * 16384 + 77                                                   # not a multiple of any row length
+    a = (np.arange(n) % 251).astype(dtype)
+    d = D.from_host(a)
+    assert_bits(d[rng(None, None, -1)].to_host(), np.ascontiguousarray(a[::-1]), "1-D reversed")
+    assert_bits(d[rng(0, None, 2)].to_host(), np.ascontiguousarray(a[0::2]), "1-D step 2")
+    assert_bits(d[rng(n - 1, 0, -3)].to_host(), np.ascontiguousarray(a[n - 1::-3]), "1-D step -3")
+    m = a[:n - 77].reshape(5, 16384)                                     # 2-D, both axes reversed -> one axis of stride -1
+    assert_bits(D.from_host(m)[rng(None, None, -1), rng(None, None, -1)].to_host(), np.ascontiguousarray(m[::-1, ::-1]), "2-D reversed")
+    z = D.fill([n], 0, dtype)                                            # scatter through a reversed destination
+    z[rng(None, None, -1)] = d
+    assert_bits(z.to_host(), np.ascontiguousarray(a[::-1]), "reversed scatter")
+    z2 = D.fill([2 * n], 0, dtype)
+    z2[rng(1, None, 2)] = d
+    want = np.zeros(2 * n, dtype); want[1::2] = a
+    assert_bits(z2.to_host(), want, "step-2 scatter")
+
+
 def test_get_available_and_optional_chunk():
     """multi_indexable.cr:397-413 (get_available), :313-318 (has_region?), :540-546 ([]?)."""
     n = np.arange(6, dtype=np.int32).reshape(2, 3) + 1                  # [[1,2,3],[4,5,6]]

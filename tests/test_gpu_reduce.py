@@ -116,6 +116,32 @@ def test_axis_sum_float(dtype, tol):
     np.testing.assert_allclose(d.sum(axis=2).to_host(), np.sum(a.astype(np.float64), axis=2), rtol=tol)
 
 
+@pytest.mark.parametrize("K", [8, 64, 1000, 2048])
+def test_last_axis_register_kernel_zero_signs_ties_nan(K):
+    """Rows that fit one warp's registers (axis_rowreg_kernel): rows sharing a warp disagree on
+    whether the extremum is a zero (first zero's sign must survive), ties keep the first index,
+    a NaN anywhere raises."""
+    rs = np.random.RandomState(K)
+    a = -(rs.rand(6, K).astype(np.float32) + 1)                    # all negative
+    a[0, K // 2] = -0.0; a[0, K - 1] = 0.0                          # max = zero, the FIRST one is -0.0
+    a[2, 3] = 0.0; a[2, 5] = -0.0                                   # first zero is +0.0
+    a[4, 1] = a[4, K - 2] = -0.5; a[4, 0] = -0.75                   # tie for the max on a non-zero value
+    a[4, 2:K - 2] = -3.0
+    d = D.from_host(a)
+    got = d.max(axis=1).to_host()
+    assert np.signbit(got[0]) and not np.signbit(got[2]) and got[0] == 0 and got[2] == 0
+    assert_bits(got[[1, 3, 5]], a[[1, 3, 5]].max(axis=1), "plain rows")
+    arg = d.argmax(axis=1).to_host()
+    assert arg[0] == K // 2 and arg[2] == 3 and arg[4] == 1
+    assert arg.tolist() == [int(O.reduce_argmax(r, "max")[1]) for r in a]
+    mn = d.argmin(axis=1).to_host()
+    assert mn.tolist() == [int(O.reduce_argmax(r, "min")[1]) for r in a]
+    np.testing.assert_allclose(d.sum(axis=1).to_host(), a.astype(np.float64).sum(axis=1), rtol=F32_TOL)
+    a[3, K - 1] = np.nan
+    with pytest.raises(ph.CrArgumentError):
+        D.from_host(a).max(axis=1)
+
+
 def test_axis_int_overflow_and_errors():
     a = np.array([[2**31 - 1, 1], [1, 1], [-5, 1]], np.int32)
     with pytest.raises(ph.CrOverflowError):
