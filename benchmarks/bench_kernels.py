@@ -36,7 +36,9 @@ except Exception:
     pass
 
 
-def timeit(fn, reps=None, warm=3):
+def timeit(fn, reps=None, warm=3, inner=4):
+    """`inner` back-to-back launches between two CUDA events (a lone launch would add ~2.5 us of
+    launch latency and ramp to kernels that run for 80 us), repeated `reps` times."""
     reps = reps or args.reps
     for _ in range(warm):
         fn()
@@ -44,9 +46,10 @@ def timeit(fn, reps=None, warm=3):
     ms = C.c_float()
     for _ in range(reps):
         ph.check(lib.ph_timer_start())
-        fn()
+        for _ in range(inner):
+            fn()
         ph.check(lib.ph_timer_stop(C.byref(ms)))
-        ts.append(ms.value)
+        ts.append(ms.value / inner)
     return min(ts), statistics.median(ts)
 
 
