@@ -41,8 +41,8 @@ BYTES_ADD = 3 * N * 4                     # read t, read c, write out
 BYTES_STEP = BYTES_MUL + BYTES_ADD
 SEED = 20261017
 # dram__bytes_read.sum + dram__bytes_write.sum of one `out = t + c` launch, from the committed
-# ncu --set full capture of this very command (profiles/r01_ncu_bench_kernels.csv): 536.92 + 223.49 MB
-NCU_TRAFFIC_ADD = 760418048
+# ncu --set full capture of this very command (profiles/r01_ncu_bench_kernels.csv): 536.89 + 222.32 MB
+NCU_TRAFFIC_ADD = 759209728
 METRIC = "f32 elementwise HBM GB/s"
 WORKLOAD = "elementwise a*b+c, b=[1,8192] row-vector broadcast, 8192x8192 f32 (two reference-faithful kernels)"
 
@@ -402,7 +402,7 @@ def run_ours(args):
                          "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": NCU_TRAFFIC_ADD, "peak_source": peak_src,
                          "traffic_source": "profiles/r01_ncu_bench_kernels.csv (ncu --set full, dram__bytes_read.sum + "
-                                           "dram__bytes_write.sum per launch; 45 MB of the 268 MB written are still dirty in L2 at kernel end)",
+                                           "dram__bytes_write.sum per launch; 46 MB of the 268 MB written are still dirty in L2 at kernel end)",
                          "algorithmic_bytes_per_launch": BYTES_ADD, "avg_launch_ms": round(dom_ms, 5),
                          "launches_timed": len(add_ms),
                          "other_kernels": {"map_flat_kernel<BinaryOp<float,MUL>,8,2> (t = a * b, b periodic: the [1,8192] row vector)": {
