@@ -20,6 +20,7 @@
 #include "ph_common.cuh"
 #include "ops.cuh"
 #include <algorithm>
+#include <type_traits>
 #include <stdlib.h>
 
 namespace ph {
@@ -165,6 +166,145 @@ __global__ void __launch_bounds__(32 * HEAT_TY) heat_march_kernel(const HeatArgs
   }
 }
 
+// ------------------------------------------------------------------ rank 2, two steps per pass
+// Temporal blocking for the 2-D grid: one pass over HBM advances TWO time steps (4.3 instead of
+// 8 bytes of DRAM traffic per cell-update for f32).  No shared memory at all: a WARP owns an
+// x-segment of 32 groups and marches down axis 0; a lane keeps its group of rows p-1 .. p+4 at
+// time t (three rows are loads in flight: 96 bytes per lane) and of rows p-2, p-1, p at time
+// t+1 in registers, rotated by a 6x unrolled loop (no register copies); x-neighbours come from
+// warp shuffles at both time levels (the default keeps 9 time-t rows, i.e. 6 loads in flight per
+// lane).  Lanes 0 and 31 are halo lanes: they compute time t+1
+// only (of which just the cell next to lane 1 / lane 30 is ever used, so THEIR outer neighbour
+// is a don't-care and no halo loads exist); lanes 1..30 write time t+2.  Same operations in
+// the same order as two single steps => bit-identical.
+template <typename T>
+struct Heat2dTbArgs {
+  const T* in;
+  T* out;
+  int64_t n0, n2;                     // rows (march axis), columns
+  int64_t z_begin, z_end, z_chunk;    // rows to update
+  int64_t fixed_lo, fixed_hi;         // rows <= fixed_lo or >= fixed_hi are held
+  int64_t tiles;                      // x tiles of 30 * E output cells
+  T coeff;
+};
+
+template <typename T>
+__device__ __forceinline__ T heat5(T c, T up, T dn, T xl, T xr, T coeff) {
+  const T two_c = f_mul((T)2, c);
+  const T d0 = f_add(f_sub(up, two_c), dn);
+  const T d1 = f_add(f_sub(xl, two_c), xr);
+  return f_add(c, f_mul(f_add(d0, d1), coeff));
+}
+
+template <typename T, int E, bool EDGE>
+__device__ __forceinline__ Group<T, E> heat5_row(const Group<T, E>& c, const Group<T, E>& up, const Group<T, E>& dn,
+                                                 T coeff, bool fix_first, bool fix_last) {
+  const T xl = __shfl_up_sync(0xffffffffu, c.v[E - 1], 1);
+  const T xr = __shfl_down_sync(0xffffffffu, c.v[0], 1);
+  Group<T, E> res;
+#pragma unroll
+  for (int i = 0; i < E; i++) {
+    const T l = (i > 0) ? c.v[i - 1] : xl;
+    const T r = (i < E - 1) ? c.v[i + 1] : xr;
+    res.v[i] = heat5<T>(c.v[i], up.v[i], dn.v[i], l, r, coeff);
+  }
+  if (EDGE) {
+    if (fix_first) res.v[0] = c.v[0];
+    if (fix_last) res.v[E - 1] = c.v[E - 1];
+  }
+  return res;
+}
+
+template <int N, typename F, int I = 0>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<N, F, I + 1>(static_cast<F&&>(f));
+  }
+}
+
+// NA = time-t row slots per lane (a multiple of 3): rows p-1 .. p+NA-2, of which NA-3 are loads in flight.
+template <typename T, int E, int MINB, int NA>
+__global__ void __launch_bounds__(32 * HEAT_TY, MINB) heat2d_tb_kernel(const Heat2dTbArgs<T> a) {
+  static_assert(NA % 3 == 0 && NA >= 6, "the t and t+1 register rings rotate together");
+  using G = Group<T, E>;
+  const int lane = threadIdx.x & 31;
+  const int64_t tile = (int64_t)blockIdx.x * HEAT_TY + (threadIdx.x >> 5);
+  if (tile >= a.tiles) return;                                   // whole warps only: shuffles stay full
+  const int64_t zb = a.z_begin + (int64_t)blockIdx.y * a.z_chunk;
+  const int64_t ze = (zb + a.z_chunk < a.z_end) ? zb + a.z_chunk : a.z_end;
+  if (zb >= ze) return;
+  const int64_t gx = tile * (30 * E) - E + (int64_t)lane * E;    // first column of this lane's group
+  const bool in_range = gx >= 0 && gx + E <= a.n2;               // n2 % E == 0: a group is all in or all out
+  const bool writes = in_range && lane >= 1 && lane <= 30;
+  const bool fix_first = gx == 0, fix_last = gx + E == a.n2;
+  const int64_t x_first = tile * (30 * E) - E;
+  const bool fast = x_first > 0 && x_first + 32 * E < a.n2;      // warp-uniform: no held column, all lanes in range
+  const T coeff = a.coeff;
+  const T* col = a.in + (in_range ? gx : 0);
+  T* p_out = a.out + zb * a.n2 + (in_range ? gx : 0);
+  auto load_row = [&](int64_t r) {                               // rows outside the grid are never used: clamp
+    r = r < 0 ? 0 : (r > a.n0 - 1 ? a.n0 - 1 : r);
+    return load_group<T, E>(col + r * a.n2);
+  };
+  auto zero = [&]() { return splat_group<T, E>((T)0); };
+
+  G ra[NA], rb[3];                                               // time t rows p-1 .. p+NA-2 ; time t+1 rows p-2 .. p
+  int64_t p = zb - 1;
+  int it = 0;
+  const int iters = (int)(ze - zb) + 2;
+#pragma unroll
+  for (int k = 0; k < NA - 1; k++) ra[k] = in_range ? load_row(p - 1 + k) : zero();
+  rb[0] = ra[1]; rb[1] = ra[1];                                  // placeholders until two t+1 rows exist
+
+  // aP, aC, aN: time-t rows p-1, p, p+1; aF: receives row p+NA-2.  FAST: no held cell, every lane in
+  // range; the first and last row of a march always take the general form (possibly held rows).
+  auto step = [&](auto fast_t, G& aP, G& aC, G& aN, G& aF, G& bP, G& bC, G& bN) {
+    constexpr bool FAST = decltype(fast_t)::value;
+    if constexpr (FAST) aF = load_row(p + NA - 2);
+    else aF = in_range ? load_row(p + NA - 2) : zero();
+    if constexpr (FAST) {
+      bN = heat5_row<T, E, false>(aC, aP, aN, coeff, false, false);
+    } else {
+      const bool held = p <= a.fixed_lo || p >= a.fixed_hi;
+      const G t = heat5_row<T, E, true>(aC, aP, aN, coeff, fix_first, fix_last);
+      bN = held ? aC : t;
+    }
+    if (FAST || it >= 2) {                                       // time t+2 of row q = p-1
+      if constexpr (FAST) {
+        const G res = heat5_row<T, E, false>(bC, bP, bN, coeff, false, false);
+        if (lane >= 1 && lane <= 30) store_group<T, E>(p_out, res);
+      } else {
+        const G res = heat5_row<T, E, true>(bC, bP, bN, coeff, fix_first, fix_last);
+        if (writes) store_group<T, E>(p_out, res);
+      }
+      p_out += a.n2;
+    }
+    it++; p++;
+  };
+  // rotation I = it mod NA (NA % 3 == 0, so the t+1 ring's rotation is I mod 3)
+  auto step_rot = [&](auto fast_t, auto rot) {
+    constexpr int I = decltype(rot)::value;
+    step(fast_t, ra[I % NA], ra[(I + 1) % NA], ra[(I + 2) % NA], ra[(I + NA - 1) % NA], rb[I % 3], rb[(I + 1) % 3],
+         rb[(I + 2) % 3]);
+  };
+  auto step_k = [&](auto fast_t, int k) {
+    static_for<NA>([&](auto rot) { if (k == decltype(rot)::value) step_rot(fast_t, rot); });
+  };
+  auto run = [&](auto fast_t) {
+    const std::false_type general;
+    step_rot(general, std::integral_constant<int, 0>{});         // it = 0: row zb-1 may be held, no output yet
+    step_rot(general, std::integral_constant<int, 1>{});         // it = 1: no output yet
+    while (iters - it >= NA + 1)
+      static_for<NA>([&](auto r) { step_rot(fast_t, std::integral_constant<int, (decltype(r)::value + 2) % NA>{}); });
+    int k = 2;                                                   // 1..NA rows left (iters >= 3); the last may be held
+    while (iters - it > 1) { step_k(fast_t, k); k = k + 1 == NA ? 0 : k + 1; }
+    step_k(general, k);
+  };
+  if (fast) run(std::true_type{});
+  else run(std::false_type{});
+}
+
 // rank 1, either boundary mode: one cell per thread
 template <typename T>
 __global__ void heat_1d_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t n, T coeff, int mode,
@@ -255,6 +395,52 @@ static int32_t launch_march(const T* in, T* out, int64_t n0, int64_t n1, int64_t
   return PH_OK;
 }
 
+// rank 2, two steps per pass; *used = false => the caller runs two single steps instead
+template <typename T>
+static bool heat2d_tb_shape_ok(int64_t n2) {
+  constexpr int E = 32 / (int)sizeof(T);
+  return getenv("PH_HEAT_NO_FUSE2") == nullptr && n2 % E == 0 && n2 >= 3;
+}
+
+template <typename T, int E, int MINB, int NA>
+static int32_t heat2d_tb_launch(const T* in, T* out, int64_t n0, int64_t n2, T coeff, int64_t z_begin, int64_t z_end,
+                                int64_t fixed_lo, int64_t fixed_hi, cudaStream_t stream) {
+  Heat2dTbArgs<T> a;
+  a.in = in; a.out = out; a.n0 = n0; a.n2 = n2; a.coeff = coeff;
+  a.z_begin = z_begin; a.z_end = z_end; a.fixed_lo = fixed_lo; a.fixed_hi = fixed_hi;
+  a.tiles = ceil_div(n2 + E, (int64_t)30 * E);          // lane 1 of tile 0 holds column 0; cover column n2-1
+  const int64_t gx = ceil_div(a.tiles, HEAT_TY);
+  // resident blocks per SM x ~4 waves of warps; chunks of >= 128 rows (each chunk re-reads 4 rows)
+  const int64_t rows = z_end - z_begin;
+  const int64_t want = (int64_t)rt().sm_count * MINB * 4;
+  int64_t gy = std::max<int64_t>(1, std::min<int64_t>(ceil_div(want, gx), ceil_div(rows, 128)));
+  a.z_chunk = ceil_div(rows, gy);
+  gy = ceil_div(rows, a.z_chunk);
+  if (gy > 65535) return set_error(PH_ERR_INVALID, "heat grid too large for one launch");
+  dim3 grid((unsigned)gx, (unsigned)gy), block(32 * HEAT_TY);
+  heat2d_tb_kernel<T, E, MINB, NA><<<grid, block, 0, stream>>>(a);
+  PH_LAUNCH_CHECK("heat2d_tb_kernel");
+  return PH_OK;
+}
+
+template <typename T>
+static int32_t heat2d_tb_planes(const T* in, T* out, int64_t n0, int64_t n2, T coeff, int64_t z_begin, int64_t z_end,
+                                int64_t fixed_lo, int64_t fixed_hi, cudaStream_t stream, bool* used) {
+  *used = false;
+  if (z_begin >= z_end) { *used = true; return PH_OK; }
+  if (!heat2d_tb_shape_ok<T>(n2) || (uintptr_t)in % 32 || (uintptr_t)out % 32) return PH_OK;
+  static const int cfg = getenv("PH_HEAT2D_CFG") ? atoi(getenv("PH_HEAT2D_CFG")) : 0;     // tuning knob
+  *used = true;
+  constexpr int EW = 32 / (int)sizeof(T), EV = 16 / (int)sizeof(T);
+  // measured on 16384^2 f32 (Gcell/s): 16-byte groups, 3 blocks/SM, 9 row slots 1389; 6 slots 1352;
+  // 2 blocks/SM with 9 / 12 slots 1171 / 1148; 32-byte groups, 2 blocks/SM 1167 (occupancy beats depth)
+  switch (cfg) {
+    case 1: return heat2d_tb_launch<T, EV, 3, 6>(in, out, n0, n2, coeff, z_begin, z_end, fixed_lo, fixed_hi, stream);
+    case 2: return heat2d_tb_launch<T, EW, 2, 6>(in, out, n0, n2, coeff, z_begin, z_end, fixed_lo, fixed_hi, stream);
+    default: return heat2d_tb_launch<T, EV, 3, 9>(in, out, n0, n2, coeff, z_begin, z_end, fixed_lo, fixed_hi, stream);
+  }
+}
+
 // heat_tma.cu: TMA-fed shared-memory pipeline (preferred for rank 3 when the shape allows)
 template <typename T>
 int32_t heat_tma_planes(const T* in, T* out, int64_t n0, int64_t n1, int64_t n2, T coeff, int64_t z_begin,
@@ -340,10 +526,13 @@ static int32_t heat_run_t(int rank, const int64_t* ext, const void* coeff_host, 
       int cur = 0;
       int64_t left = steps;
       while (left > 0) {
-        if (rank == 3 && left >= 2) {            // two time steps per pass over HBM when the shape allows
+        if (left >= 2) {                         // two time steps per pass over HBM when the shape allows
           bool used = false;
-          int32_t st = heat_tma2_planes<T>(bufs[cur], bufs[cur ^ 1], ext[0], ext[1], ext[2], coeff, 1, ext[0] - 1,
-                                           0, ext[0] - 1, r.stream, &used);
+          int32_t st = rank == 3
+              ? heat_tma2_planes<T>(bufs[cur], bufs[cur ^ 1], ext[0], ext[1], ext[2], coeff, 1, ext[0] - 1, 0,
+                                    ext[0] - 1, r.stream, &used)
+              : heat2d_tb_planes<T>(bufs[cur], bufs[cur ^ 1], ext[0], ext[1], coeff, 1, ext[0] - 1, 0, ext[0] - 1,
+                                    r.stream, &used);
           if (st != PH_OK) return st;
           if (used) { cur ^= 1; left -= 2; continue; }
         }
@@ -380,12 +569,13 @@ static int32_t heat_slab_t(int rank, const int64_t* ext, const void* coeff_host,
   const T* in = reinterpret_cast<const T*>(in_v);
   T* out = reinterpret_cast<T*>(out_v);
   if (two_step) {
-    if (rank != 3 || g < 2) return set_error(PH_ERR_INVALID, "two-step slab update needs rank 3 and 2 ghost planes");
+    if (g < 2) return set_error(PH_ERR_INVALID, "two-step slab update needs 2 ghost planes");
     bool used = false;
-    int32_t st = heat_tma2_planes<T>(in, out, n0, ext[1], ext[2], coeff, b, e, has_lo ? -1 : g, has_hi ? n0 : n0 - g - 1,
-                                     stream, &used);
+    const int64_t flo = has_lo ? -1 : g, fhi = has_hi ? n0 : n0 - g - 1;
+    int32_t st = rank == 3 ? heat_tma2_planes<T>(in, out, n0, ext[1], ext[2], coeff, b, e, flo, fhi, stream, &used)
+                           : heat2d_tb_planes<T>(in, out, n0, ext[1], coeff, b, e, flo, fhi, stream, &used);
     if (st != PH_OK) return st;
-    if (!used) return set_error(PH_ERR_INVALID, "two-step slab update: buffers must be 16-byte aligned");
+    if (!used) return set_error(PH_ERR_INVALID, "two-step slab update: buffers must be 32-byte aligned");
     return PH_OK;
   }
   return heat_planes<T>(rank, ext, coeff, in, out, b, e, stream);
@@ -402,6 +592,7 @@ int32_t heat_slab_dispatch(int32_t dtype, int rank, const int64_t* ext, const vo
 }
 
 bool heat_two_step_usable(int32_t dtype, int rank, const int64_t* ext) {
+  if (rank == 2) return dtype == PH_F32 ? heat2d_tb_shape_ok<float>(ext[1]) : (dtype == PH_F64 && heat2d_tb_shape_ok<double>(ext[1]));
   if (rank != 3) return false;
   if (dtype == PH_F32) return heat_tma2_usable<float>(ext[1], ext[2]);
   if (dtype == PH_F64) return heat_tma2_usable<double>(ext[1], ext[2]);
@@ -453,7 +644,7 @@ int32_t ph_heat_pass_slab(int32_t dtype, int32_t rank, const int64_t* extents, c
   if (!extents || !coeff_host || !in || !out) return set_error(PH_ERR_INVALID, "null argument to ph_heat_pass_slab");
   if (ghost_planes < 1 || ghost_planes > 2) return set_error(PH_ERR_INVALID, "ghost_planes must be 1 or 2");
   if (two_steps && !heat_two_step_usable(dtype, rank, extents))
-    return set_error(PH_ERR_UNSUPPORTED, "the two-steps-per-pass kernel cannot take this grid (rank 3, x extent a multiple of 16 bytes)");
+    return set_error(PH_ERR_UNSUPPORTED, "the two-steps-per-pass kernels cannot take this grid (rank 2 / 3, x extent a multiple of 32 / 16 bytes)");
   cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : rt().stream;
   return heat_slab_dispatch(dtype, rank, extents, coeff_host, ghost_planes, has_lo, has_hi, p_begin, p_end, in, out, s,
                             two_steps != 0);

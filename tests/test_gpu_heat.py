@@ -58,6 +58,63 @@ def test_2d_one_step_and_run(dtype, shape):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_2d_two_step_pass_tiles_and_chunks(dtype):
+    """The 2-D two-steps-per-pass kernel (warp-shuffle temporal blocking): shapes with one partial
+    tile, several tiles (30 groups of output each), a last tile holding only the final columns,
+    row counts that split into several chunks, and odd / even step counts."""
+    rs = np.random.RandomState(17)
+    for shape, steps in [((9, 8), 4), ((40, 240), 6), ((33, 248), 7), ((300, 488), 6), ((700, 1024), 8),
+                         ((131, 2056), 5), ((520, 16), 10)]:
+        s = (rs.rand(*shape) * 100).astype(dtype)
+        c = dtype(0.1)
+        want = s.copy()
+        for _ in range(steps):
+            want = O.heat_step_nd(want, c)
+        assert_bits(heat.simulate(D.from_host(s), c, steps).to_host(), want, f"2d {steps} steps {shape}")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_2d_two_step_slabs_match_whole_grid(dtype):
+    """Rank-2 slabs with two ghost rows per side advanced two steps per pass (ph_heat_pass_slab)."""
+    import ctypes as C
+    from ph_core_b200 import _lib
+    lib = _lib.load()
+    rs = np.random.RandomState(23)
+    shape = (44, 520)
+    s = (rs.rand(*shape) * 100).astype(dtype)
+    c = np.array(0.1, dtype)
+    steps = 6
+    want = s.copy()
+    for _ in range(steps):
+        want = O.heat_step_nd(want, dtype(0.1))
+    g, half = 2, shape[0] // 2
+    slabs = []
+    for r in range(2):
+        loc = np.zeros((half + 2 * g, shape[1]), dtype)
+        loc[g:-g] = s[r * half:(r + 1) * half]
+        if r == 0:
+            loc[-g:] = s[half:half + g]
+        else:
+            loc[:g] = s[half - g:half]
+        slabs.append([D.from_host(loc), D.from_host(loc)])
+    ext = (C.c_int64 * 2)(half + 2 * g, shape[1])
+    row = shape[1] * np.dtype(dtype).itemsize
+    code = ph.K["PH_F32"] if dtype == np.float32 else ph.K["PH_F64"]
+    for t in range(steps // 2):
+        for r in range(2):
+            src, dst = slabs[r][t & 1], slabs[r][(t & 1) ^ 1]
+            for b, e in ((g, 2 * g), (half, half + g), (2 * g, half)):
+                ph.check(lib.ph_heat_pass_slab(code, 2, ext, c.ctypes.data, g, 1, int(r > 0), int(r < 1), b, e,
+                                               src.ptr, dst.ptr, None))
+        a, b = slabs[0][(t & 1) ^ 1], slabs[1][(t & 1) ^ 1]
+        ph.check(lib.ph_d2d(a.ptr + (half + g) * row, b.ptr + g * row, g * row))
+        ph.check(lib.ph_d2d(b.ptr, a.ptr + half * row, g * row))
+    fin = (steps // 2) & 1
+    got = np.concatenate([slabs[0][fin].to_host()[g:-g], slabs[1][fin].to_host()[g:-g]])
+    assert_bits(got, want, "two 2-ghost 2-D slabs, two steps per pass == whole grid")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("shape", [(3, 3, 3), (5, 6, 4), (9, 16, 128), (40, 37, 132), (7, 70, 31), (66, 9, 260), (34, 8, 1024)])
 def test_3d_one_step_and_run(dtype, shape):
     rs = np.random.RandomState(shape[1])
