@@ -6,6 +6,7 @@
 // exchanged by grouped ncclSend/ncclRecv on a side stream while the interior planes are
 // being updated on the main stream.
 #include "ph_common.cuh"
+#include <stdlib.h>
 #include <dlfcn.h>
 #include <nccl.h>   // types only: the library is resolved at run time (see nccl_api)
 
@@ -250,7 +251,8 @@ int32_t ph_heat_run_sharded(int32_t dtype, int32_t rank, const int64_t* local_ex
       return heat_slab_dispatch(dtype, rank, local_extents, coeff_host, g, has_lo, has_hi, b, e, in, out, r.stream, two);
     };
     const int64_t own_b = g, own_e = n0 - g;
-    if (own_e - own_b > 2 * g && c.nranks > 1) {
+    static const bool no_overlap = getenv("PH_HEAT_NO_OVERLAP") != nullptr;    // measurement knob
+    if (own_e - own_b > 2 * g && c.nranks > 1 && !no_overlap) {
       // 1. edge planes  2. exchange on the side stream, overlapped with  3. the interior planes
       if ((st = update(own_b, own_b + g)) != PH_OK) return st;
       if ((st = update(own_e - g, own_e)) != PH_OK) return st;

@@ -1,8 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_heat.py -m gpu -q --timeout 300 -x -k "2d" 2>&1 | tail -3
-for cfg in 0 1 2 3 4; do
-echo "2D cfg $cfg"
-PH_HEAT2D_CFG=$cfg timeout 300 python -m pytest tests/test_gpu_heat.py -m gpu -q --timeout 300 -x -k "2d_two_step" 2>&1 | tail -1
-PH_HEAT2D_CFG=$cfg timeout 300 python benchmarks/bench_kernels.py --only "heat 2-D" 2>&1 | cut -c1-220
-done
+for cfg in 0 1 2; do for m in 48 64 96 128; do
+echo "cfg $cfg march $m: $(PH_HEAT_TB_CFG=$cfg PH_HEAT_TB_MARCH=$m timeout 300 python benchmarks/bench_kernels.py --heat-shape 2048,2048,2048 2>&1 | grep -o 'gcell_per_s.*')"
+done; done
+echo "1024: $(timeout 300 python benchmarks/bench_kernels.py --heat-shape 1024,1024,1024 2>&1 | grep -o 'gcell_per_s.*')"
+echo "256 slab: $(timeout 300 python benchmarks/bench_kernels.py --heat-shape 256,2048,2048 2>&1 | grep -o 'gcell_per_s.*')"

@@ -141,3 +141,23 @@ def test_config5_heat_large_locality():
         # faces of the crop that are NOT grid boundaries received wrong (held) data: trim k cells there
         sl = tuple(slice(0 if lo == 0 else k, None if hi == n else -k) for lo, hi in ((z0, z1), (y0, y1), (x0, x1)))
         assert_bits(got[sl], want[sl], f"crop {(z0, y0, x0)}")
+
+
+def test_two_steps_per_pass_equal_single_steps_at_scale():
+    """The temporally blocked kernels (two time steps per pass over HBM) against the SAME library's
+    single-step entry point applied step by step, at sizes the oracle cannot reach: 2-D 16384^2
+    f32 (BASELINE configs[0] generalised) and a 3-D slab of 2048^2 planes.  Bit-identical."""
+    lib = _lib.load()
+    for shape, steps in (((16384, 16384), 4), ((96, 2048, 2048), 5)):
+        total = int(np.prod(shape))
+        tile = (np.random.RandomState(len(shape)).rand(1 << 22) * 100).astype(np.float32)
+        g = D(list(shape), np.float32)
+        t = D.from_host(tile)
+        for pos in range(0, total, tile.size):
+            ph.check(lib.ph_d2d(g.ptr + pos * 4, t.ptr, min(tile.size, total - pos) * 4))
+        cur = g
+        for _ in range(steps):
+            cur = heat.update_temp(cur, 0.1)                      # one launch per step (ph_heat_step)
+        fused = heat.simulate(g.clone(), 0.1, steps)              # ph_heat_run: two steps per pass (+ an odd one)
+        assert fused.equals(cur), f"{shape}: fused run differs from {steps} single steps"
+        del cur, fused, g
