@@ -196,10 +196,10 @@ int32_t ph_halo_exchange(const void* send_lo, void* recv_lo, int32_t lo_rank, co
 }
 
 // local_extents[0] = n0_local + 2 g, g = ghost_planes per side (1 or 2).  Per pass:
-//   main : update the g edge planes on either side first (what the neighbours need)
-//   aux  : (after the edge planes) exchange them with the neighbours' ghost planes
-//   main : update the interior planes meanwhile
-//   main waits for aux before the next pass reads the ghosts.
+//   side stream (high priority): update the g edge planes on either side (what the neighbours
+//                need), then exchange them with the neighbours' ghost planes;
+//   main stream: update the interior planes at the same time;
+//   each stream waits for the other's previous pass (events), see the loop below.
 // g = 1: every pass is one time step.  g = 2 (rank 3, shape permitting): a pass advances TWO time
 // steps with the temporally blocked kernel (heat_tma.cu), so both the HBM traffic and the number
 // of exchanges per time step halve; an odd last step is a single step.
@@ -241,34 +241,47 @@ int32_t ph_heat_run_sharded(int32_t dtype, int32_t rank, const int64_t* local_ex
   if (!has_hi) PH_CUDA(cudaMemcpyAsync(bufs[1] + (n0 - g - 1) * pbytes, bufs[0] + (n0 - g - 1) * pbytes, pbytes,
                                        cudaMemcpyDeviceToDevice, r.stream));
 
+  // Two streams per pass.  side (high priority): the g edge planes on either side, then the grouped
+  // send/recv of exactly those planes.  main: the interior planes, CONCURRENTLY with the edges (both
+  // read `in` and write disjoint planes of `out`), so the small, latency-bound edge launches never
+  // hold the interior back and the exchange runs under it.  Dependencies of pass k:
+  //   edges(k)    <- exchange(k-1) [same stream], interior(k-1) [ev_a: main -> side]
+  //   interior(k) <- edges(k-1)                  [ev_b: side -> main]
+  static const bool no_overlap = getenv("PH_HEAT_NO_OVERLAP") != nullptr;    // measurement knob
+  const int64_t own_b = g, own_e = n0 - g;
+  const bool split = own_e - own_b > 2 * g && c.nranks > 1 && !no_overlap;
+  cudaStream_t side = r.aux_stream;
+  if (split) {
+    PH_CUDA(cudaEventRecord(r.ev_a, r.stream));
+    PH_CUDA(cudaStreamWaitEvent(side, r.ev_a, 0));             // initial ghosts / boundary copies are on main
+    PH_CUDA(cudaEventRecord(r.ev_b, side));
+  }
   int cur = 0;
   int64_t left = steps;
   while (left > 0) {
     const bool two = can_two && left >= 2;
     const char* in = bufs[cur];
     char* out = bufs[cur ^ 1];
-    auto update = [&](int64_t b, int64_t e) {
-      return heat_slab_dispatch(dtype, rank, local_extents, coeff_host, g, has_lo, has_hi, b, e, in, out, r.stream, two);
+    auto update = [&](int64_t b, int64_t e, cudaStream_t s) {
+      return heat_slab_dispatch(dtype, rank, local_extents, coeff_host, g, has_lo, has_hi, b, e, in, out, s, two);
     };
-    const int64_t own_b = g, own_e = n0 - g;
-    static const bool no_overlap = getenv("PH_HEAT_NO_OVERLAP") != nullptr;    // measurement knob
-    if (own_e - own_b > 2 * g && c.nranks > 1 && !no_overlap) {
-      // 1. edge planes  2. exchange on the side stream, overlapped with  3. the interior planes
-      if ((st = update(own_b, own_b + g)) != PH_OK) return st;
-      if ((st = update(own_e - g, own_e)) != PH_OK) return st;
+    if (split) {
+      PH_CUDA(cudaStreamWaitEvent(side, r.ev_a, 0));           // previous interior
+      PH_CUDA(cudaStreamWaitEvent(r.stream, r.ev_b, 0));       // previous edges + exchange
+      if ((st = update(own_b, own_b + g, side)) != PH_OK) return st;
+      if ((st = update(own_e - g, own_e, side)) != PH_OK) return st;
+      if ((st = exchange(out, side)) != PH_OK) return st;
+      PH_CUDA(cudaEventRecord(r.ev_b, side));
+      if ((st = update(own_b + g, own_e - g, r.stream)) != PH_OK) return st;
       PH_CUDA(cudaEventRecord(r.ev_a, r.stream));
-      PH_CUDA(cudaStreamWaitEvent(r.aux_stream, r.ev_a, 0));
-      if ((st = exchange(out, r.aux_stream)) != PH_OK) return st;
-      PH_CUDA(cudaEventRecord(r.ev_b, r.aux_stream));
-      if ((st = update(own_b + g, own_e - g)) != PH_OK) return st;
-      PH_CUDA(cudaStreamWaitEvent(r.stream, r.ev_b, 0));
     } else {
-      if ((st = update(own_b, own_e)) != PH_OK) return st;
+      if ((st = update(own_b, own_e, r.stream)) != PH_OK) return st;
       if (c.nranks > 1 && (st = exchange(out, r.stream)) != PH_OK) return st;
     }
     cur ^= 1;
     left -= two ? 2 : 1;
   }
+  if (split) PH_CUDA(cudaStreamWaitEvent(r.stream, r.ev_b, 0));   // the caller's stream sees the whole run
   *final_is_b = cur;
   return PH_OK;
 }

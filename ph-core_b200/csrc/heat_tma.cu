@@ -20,6 +20,13 @@
 
 namespace ph {
 
+// Packed f32x2 adds (FADD2) in the two-step stencil: bit-identical and 20 % fewer instructions
+// (ncu: 1175 M -> 941 M warp instructions, issue 68 % -> 53 %), but SLOWER on B200 (2048^3: 1452 ->
+// 1381 Gcell/s; barrier + short-scoreboard stalls up): FADD2 does not run at twice the FADD rate, so
+// the FP pipe, not the issue slot, becomes the limit.  Kept for A/B runs, off by default.
+#ifndef PH_HEAT_F32X2
+#define PH_HEAT_F32X2 0
+#endif
 constexpr int TMA_STAGES = 6;       // planes resident in shared memory (3 in use + 3 in flight)
 
 template <typename T, int TMA_TY> struct TmaTile {
@@ -198,10 +205,71 @@ __device__ __forceinline__ T heat7(T c, T zl, T zh, T yl, T yh, T xl, T xh, T co
   return f_add(c, f_mul(f_add(f_add(d0, d1), d2), coeff));
 }
 
+// ---- packed f32x2 arithmetic (sm_100: FADD2).  add / sub with an explicit .rn are single IEEE
+// operations per lane exactly like __fadd_rn; there is NO packed multiply in heat_row_f32x2 (ptxas
+// fuses mul.f32x2 + add.f32x2 into FFMA2 even under --fmad=false), the two multiplies per cell pair
+// stay scalar __fmul_rn, which is never contracted.  Halves the FP issue slots of the stencil.
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// heat7 on one 4-cell group of floats, two cells per instruction where the operands are aligned
+// register pairs (z and y neighbours, the centre); the x-neighbour differences are shifted by one
+// cell and stay scalar.  2*c is computed as c + c (the same value, exactly).  Same operations in
+// the same order per cell as heat7 => bit-identical.
+template <bool EDGE>
+__device__ __forceinline__ Group<float, 4> heat_row_f32x2(const Group<float, 4>& c, const Group<float, 4>& zl,
+                                                          const Group<float, 4>& zh, const Group<float, 4>& yl,
+                                                          const Group<float, 4>& yh, float xl, float xr, float coeff,
+                                                          bool fix_first, bool fix_last) {
+  const uint64_t c0 = c.raw.q[0], c1 = c.raw.q[1];
+  const uint64_t tc0 = f2_add(c0, c0), tc1 = f2_add(c1, c1);
+  const uint64_t d0a = f2_add(f2_sub(zl.raw.q[0], tc0), zh.raw.q[0]), d0b = f2_add(f2_sub(zl.raw.q[1], tc1), zh.raw.q[1]);
+  const uint64_t d1a = f2_add(f2_sub(yl.raw.q[0], tc0), yh.raw.q[0]), d1b = f2_add(f2_sub(yl.raw.q[1], tc1), yh.raw.q[1]);
+  float t0, t1, t2, t3;
+  f2_unpack(tc0, t0, t1);
+  f2_unpack(tc1, t2, t3);
+  const float e0 = f_add(f_sub(xl, t0), c.v[1]);
+  const float e1 = f_add(f_sub(c.v[0], t1), c.v[2]);
+  const float e2 = f_add(f_sub(c.v[1], t2), c.v[3]);
+  const float e3 = f_add(f_sub(c.v[2], t3), xr);
+  const uint64_t lapa = f2_add(f2_add(d0a, d1a), f2_pack(e0, e1));
+  const uint64_t lapb = f2_add(f2_add(d0b, d1b), f2_pack(e2, e3));
+  float l0, l1, l2, l3;
+  f2_unpack(lapa, l0, l1);
+  f2_unpack(lapb, l2, l3);
+  Group<float, 4> res;
+  res.raw.q[0] = f2_add(c0, f2_pack(f_mul(l0, coeff), f_mul(l1, coeff)));
+  res.raw.q[1] = f2_add(c1, f2_pack(f_mul(l2, coeff), f_mul(l3, coeff)));
+  if (EDGE) {
+    if (fix_first) res.v[0] = c.v[0];
+    if (fix_last) res.v[3] = c.v[3];
+  }
+  return res;
+}
+
 template <typename T, int E, bool EDGE>
 __device__ __forceinline__ Group<T, E> heat_row(const Group<T, E>& c, const Group<T, E>& zl, const Group<T, E>& zh,
                                                 const Group<T, E>& yl, const Group<T, E>& yh, T xl, T xr, T coeff,
                                                 bool fix_first, bool fix_last) {
+  if constexpr (std::is_same<T, float>::value && E == 4 && PH_HEAT_F32X2) {
+    return heat_row_f32x2<EDGE>(c, zl, zh, yl, yh, xl, xr, coeff, fix_first, fix_last);
+  }
   Group<T, E> res;
 #pragma unroll
   for (int i = 0; i < E; i++) {
@@ -482,10 +550,10 @@ static int32_t heat_tma_launch(const T* in, T* out, int64_t n0, int64_t n1, int6
   gz = ceil_div(planes, a.z_chunk);
   if (gy > 65535 || gz > 65535) return PH_OK;
   const size_t smem = (size_t)TMA_STAGES * Tile::STAGE_BYTES;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static int attr_dev = -1;                         // function attributes are per device
+  if (attr_dev != rt().device) {
     PH_CUDA(cudaFuncSetAttribute(heat_tma_kernel<T, TMA_TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+    attr_dev = rt().device;
   }
   dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)gz), block(32 * TMA_TY);
   heat_tma_kernel<T, TMA_TY><<<grid, block, smem, stream>>>(map, a);
@@ -529,10 +597,10 @@ static int32_t heat_tma2_launch(const T* in, T* out, int64_t n0, int64_t n1, int
   a.z_chunk = ceil_div(planes, gz);
   gz = ceil_div(planes, a.z_chunk);
   if (gy > 65535 || gz > 65535) return PH_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static int attr_dev = -1;                         // function attributes are per device
+  if (attr_dev != rt().device) {
     PH_CUDA(cudaFuncSetAttribute(heat_tma2_kernel<T, TY, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tile::SMEM));
-    attr_set = true;
+    attr_dev = rt().device;
   }
   dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)gz), block(Tile::THREADS);
   heat_tma2_kernel<T, TY, STAGES><<<grid, block, Tile::SMEM, stream>>>(map, a);

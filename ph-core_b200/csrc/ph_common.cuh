@@ -17,7 +17,7 @@ struct Runtime {
   cudaStream_t stream = nullptr;       // the stream launches go to
   cudaStream_t aux_stream = nullptr;   // halo exchange / overlap
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
-  uint32_t* d_flags = nullptr;         // device arithmetic flag word
+  uint32_t* d_flags = nullptr;         // device arithmetic flag word (d_flags[8] = reduction ticket)
   uint32_t* h_flags = nullptr;         // pinned mirror
   void* d_scratch = nullptr;           // reduction partials
   size_t scratch_bytes = 0;

@@ -715,15 +715,9 @@ static int32_t contiguous_input(const void* a, const ph_desc* d, const T** out_p
   return PH_OK;
 }
 
-// one zero-initialised device word; the last block of every fused reduction resets it
-static unsigned int* reduce_ticket() {
-  static unsigned int* t = nullptr;
-  if (!t) {
-    if (cudaMalloc(&t, 256) != cudaSuccess) { t = nullptr; return nullptr; }
-    cudaMemset(t, 0, 256);
-  }
-  return t;
-}
+// one zero-initialised device word (allocated with the flag word by ph_init, so it follows the
+// device); the last block of every fused reduction resets it
+static unsigned int* reduce_ticket() { return rt().d_flags ? rt().d_flags + 8 : nullptr; }
 
 template <typename T>
 static int32_t reduce_full_t(int32_t red, const void* a, const ph_desc* d, void* out_value_dev,
@@ -736,8 +730,9 @@ static int32_t reduce_full_t(int32_t red, const void* a, const ph_desc* d, void*
   if (st != PH_OK) return st;
   // persistent grid: exactly the blocks that are resident at once (a partial second wave would
   // leave the GPU mostly idle while it runs), fewer for small inputs
-  static int resident_sum = 0, resident_ext = 0;
-  if (!resident_sum) {
+  static int resident_sum = 0, resident_ext = 0, resident_dev = -1;
+  if (resident_dev != r.device) {
+    resident_dev = r.device;
     int a = 0, b = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sum_partial_kernel<T, 32 / (int)sizeof(T)>, RED_THREADS, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ext_partial_kernel<T, 32 / (int)sizeof(T), true>, RED_THREADS, 0);

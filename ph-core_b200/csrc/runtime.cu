@@ -118,7 +118,13 @@ int32_t ph_init(int32_t device) {
   PH_CUDA(cudaGetDeviceProperties(&prop, device));
   r.sm_count = prop.multiProcessorCount;
   PH_CUDA(cudaStreamCreateWithFlags(&r.own_stream, cudaStreamNonBlocking));
-  PH_CUDA(cudaStreamCreateWithFlags(&r.aux_stream, cudaStreamNonBlocking));
+  {
+    // the side stream carries halo edges + exchange of sharded stencil runs: highest priority, so its
+    // few blocks are placed ahead of the interior update that runs concurrently on the main stream
+    int prio_lo = 0, prio_hi = 0;
+    PH_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    PH_CUDA(cudaStreamCreateWithPriority(&r.aux_stream, cudaStreamNonBlocking, prio_hi));
+  }
   r.stream = r.own_stream;
   PH_CUDA(cudaEventCreateWithFlags(&r.ev_a, cudaEventDisableTiming));
   PH_CUDA(cudaEventCreateWithFlags(&r.ev_b, cudaEventDisableTiming));
