@@ -16,3 +16,5 @@ for l in open("gpurun_out/bench_n$n.json"):
 PY
   fi
 done
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29799 benchmarks/bench_heat_sharded.py --grid 2048,2048,2048 --steps 20 --reps 3 2>&1 | grep "^{"
+PH_HEAT_NO_OVERLAP=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29798 benchmarks/bench_heat_sharded.py --grid 2048,2048,2048 --steps 20 --reps 3 2>&1 | grep "^{"
