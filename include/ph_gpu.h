@@ -252,6 +252,11 @@ int32_t ph_comm_init(int32_t nranks, int32_t rank, const uint8_t* id128);
 int32_t ph_comm_destroy(void);
 int32_t ph_allreduce(int32_t red, int32_t dtype, void* buf_dev, int64_t count); /* SUM/MIN/MAX in place */
 int32_t ph_allgather(const void* send_dev, void* recv_dev, int64_t nbytes_per_rank);
+/* personalised all-to-all (the exchange step of a transpose across axis-0 shards): arrays of
+ * nranks entries; block p of the send list goes to rank p, block p of the receive list comes from
+ * rank p; byte counts may be 0.  No reference counterpart (ph-core is single-process): SURVEY.md 8(f) f-3. */
+int32_t ph_alltoallv(const void* const* send_dev, const int64_t* send_bytes,
+                     void* const* recv_dev, const int64_t* recv_bytes);
 /* exchange one plane with each neighbour rank (lo = rank-1, hi = rank+1; -1 = none):
  * sends send_lo -> lo, send_hi -> hi; receives recv_lo <- lo, recv_hi <- hi. */
 int32_t ph_halo_exchange(const void* send_lo, void* recv_lo, int32_t lo_rank,

@@ -138,6 +138,7 @@ def load() -> C.CDLL:
         "ph_heat_pass_slab": [i32, i32, C.POINTER(i64), vp, i32, i32, i32, i32, i64, i64, vp, vp, vp],
         "ph_comm_unique_id": [vp], "ph_comm_init": [i32, i32, vp], "ph_comm_destroy": [],
         "ph_allreduce": [i32, i32, vp, i64], "ph_allgather": [vp, vp, i64],
+        "ph_alltoallv": [C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), C.POINTER(i64)],
         "ph_halo_exchange": [vp, vp, i32, vp, vp, i32, i64, vp],
         "ph_heat_run_sharded": [i32, i32, C.POINTER(i64), vp, i32, vp, vp, i64, C.POINTER(i32)],
     }

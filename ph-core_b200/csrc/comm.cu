@@ -188,6 +188,32 @@ int32_t ph_allgather(const void* send_dev, void* recv_dev, int64_t nbytes_per_ra
   return PH_OK;
 }
 
+// Personalised all-to-all: block p of the send list goes to rank p, block p of the receive list
+// comes from rank p (byte counts per peer; 0 = nothing).  One grouped ncclSend/ncclRecv per peer
+// pair, the rank's own block is a device copy.  This is the exchange step of a transpose across
+// axis-0 shards (ShardedNArray.permute), the one place on the path where data must change owner.
+int32_t ph_alltoallv(const void* const* send_dev, const int64_t* send_bytes, void* const* recv_dev,
+                     const int64_t* recv_bytes) {
+  PH_REQUIRE_INIT();
+  Comm& c = cm();
+  if (!c.inited) return set_error(PH_ERR_NOT_INIT, "ph_comm_init was not called");
+  if (!send_dev || !send_bytes || !recv_dev || !recv_bytes) return set_error(PH_ERR_INVALID, "null argument to ph_alltoallv");
+  cudaStream_t s = rt().stream;
+  const int me = c.rank;
+  if (send_bytes[me] != recv_bytes[me]) return set_error(PH_ERR_INVALID, "ph_alltoallv: own block sizes differ");
+  if (send_bytes[me] > 0 && send_dev[me] != recv_dev[me])
+    PH_CUDA(cudaMemcpyAsync(recv_dev[me], send_dev[me], (size_t)send_bytes[me], cudaMemcpyDeviceToDevice, s));
+  if (c.nranks == 1) return PH_OK;
+  PH_NCCL(nccl().GroupStart());
+  for (int p = 0; p < c.nranks; p++) {
+    if (p == me) continue;
+    if (send_bytes[p] > 0) PH_NCCL(nccl().Send(send_dev[p], (size_t)send_bytes[p], ncclUint8, p, c.comm, s));
+    if (recv_bytes[p] > 0) PH_NCCL(nccl().Recv(recv_dev[p], (size_t)recv_bytes[p], ncclUint8, p, c.comm, s));
+  }
+  PH_NCCL(nccl().GroupEnd());
+  return PH_OK;
+}
+
 int32_t ph_halo_exchange(const void* send_lo, void* recv_lo, int32_t lo_rank, const void* send_hi,
                          void* recv_hi, int32_t hi_rank, int64_t nbytes, void* cuda_stream) {
   PH_REQUIRE_INIT();

@@ -48,6 +48,37 @@ def slab_from_global(field: np.ndarray, world: int, rank: int, ghost: int = 1) -
     return loc
 
 
+def transpose_plan(shape: Sequence[int], pattern: Sequence[int], world: int, rank: int) -> dict:
+    """Host plan of `permute(pattern)` on an array sharded along axis 0 whose result is sharded
+    along ITS axis 0 (= old axis k = pattern[0]).  For every peer q:
+      send[q] = (k0, k1): the slice of old axis k this rank cuts out of its rows for q (q's share
+                of the new leading axis); the block is sent already permuted, so its shape is
+                send_shape[q];
+      recv[q] = (p0, p1): the old-axis-0 rows q owns; its block lands at positions p0..p1-1 of new
+                axis j (where old axis 0 ends up), shape recv_shape[q].
+    pattern[0] == 0 needs no exchange (`local` = True)."""
+    shape = [int(v) for v in shape]
+    pattern = [int(v) for v in pattern]
+    if sorted(pattern) != list(range(len(shape))):
+        raise IndexError(f"permute pattern {pattern} is not a permutation of the axes of a rank-{len(shape)} array")
+    new_shape = [shape[a] for a in pattern]
+    if pattern[0] == 0:
+        return {"local": True, "new_shape": new_shape}
+    k, j = pattern[0], pattern.index(0)
+    r0, r1 = shard_range(shape[0], world, rank)
+    m0, m1 = shard_range(shape[k], world, rank)
+    plan = {"local": False, "new_shape": new_shape, "k": k, "j": j, "my_rows": (r0, r1), "my_new_rows": (m0, m1),
+            "send": [], "recv": [], "send_shape": [], "recv_shape": []}
+    for q in range(world):
+        k0, k1 = shard_range(shape[k], world, q)
+        p0, p1 = shard_range(shape[0], world, q)
+        ss = list(new_shape); ss[0] = k1 - k0; ss[j] = r1 - r0
+        rs = list(new_shape); rs[0] = m1 - m0; rs[j] = p1 - p0
+        plan["send"].append((k0, k1)); plan["recv"].append((p0, p1))
+        plan["send_shape"].append(ss); plan["recv_shape"].append(rs)
+    return plan
+
+
 def combine_extremum(values: Sequence, indices: Sequence[int], is_max: bool = True):
     """Per-rank (value, global lex index) pairs -> the FIRST extremum: best value, then the
     lowest index (README.md:56-61 semantics across shards)."""
@@ -159,8 +190,8 @@ class ShardedNArray:
     DeviceNArray.  Elementwise ops, comparisons and masked stores are purely local; full
     reductions combine per-GPU partials (allreduce / allgather of (value, index) pairs);
     per-axis reductions allreduce only when the reduced axis is the sharded one; slicing is
-    local as long as axis 0 is taken whole.  Transposes across shards (an all-to-all) are not
-    offered: gather to one GPU first."""
+    local as long as axis 0 is taken whole; `permute` moves data between shards with one
+    personalised all-to-all (ph_alltoallv)."""
 
     def __init__(self, global_shape: Sequence[int], local):
         self.shape = [int(s) for s in global_shape]
@@ -243,6 +274,55 @@ class ShardedNArray:
             raise NotImplementedError("slicing the sharded axis needs a redistribution: gather first (f-3 'next')")
         loc = self.local.get_chunk(list(key))
         return ShardedNArray([self.shape[0]] + loc.shape[1:], loc)
+
+    # ---- transposes across shards: the one real exchange step (all-to-all) --------------------
+    def permute(self, *pattern) -> "ShardedNArray":
+        """MultiIndexable#permute (src/multi_indexable.cr:795-803; default = reversed axes,
+        transforms.cr:236-238) on the distributed array; the result is sharded along its own axis
+        0.  Every rank cuts its rows into one block per peer, permutes each block locally (one
+        strided gather), exchanges them with ph_alltoallv, and scatters what it receives into its
+        shard of the result (one strided scatter per peer)."""
+        from .narray import DeviceNArray
+        from .region import rng, ALL
+        nd = len(self.shape)
+        pat = list(pattern[0]) if len(pattern) == 1 and isinstance(pattern[0], (list, tuple)) else list(pattern)
+        if not pat:
+            pat = list(reversed(range(nd)))
+        plan = transpose_plan(self.shape, pat, self.world, self.rank)
+        if plan["local"]:
+            return ShardedNArray(plan["new_shape"], self.local.permute(*pat))      # axis 0 stays put: no exchange
+        lib = _lib.load()
+        k, j = plan["k"], plan["j"]
+        m0, m1 = plan["my_new_rows"]
+        out = DeviceNArray([m1 - m0] + plan["new_shape"][1:], self.dtype)
+        isz = self.dtype.itemsize
+        sends, recvs = [], []
+        for q in range(self.world):
+            k0, k1 = plan["send"][q]
+            n_send = int(np.prod(plan["send_shape"][q], dtype=np.int64))
+            if n_send:
+                lit = [ALL] * nd
+                lit[k] = rng(k0, k1 - 1)
+                blk = self.local.view(*lit).permute(*pat).to_narr()       # contiguous, already permuted
+            else:
+                blk = None
+            n_recv = int(np.prod(plan["recv_shape"][q], dtype=np.int64))
+            sends.append(blk)
+            recvs.append(DeviceNArray(plan["recv_shape"][q], self.dtype) if n_recv else None)
+        vp = C.c_void_p
+        sp = (vp * self.world)(*[b.ptr if b is not None else None for b in sends])
+        rp = (vp * self.world)(*[b.ptr if b is not None else None for b in recvs])
+        sb = (C.c_int64 * self.world)(*[b.size * isz if b is not None else 0 for b in sends])
+        rb = (C.c_int64 * self.world)(*[b.size * isz if b is not None else 0 for b in recvs])
+        check(lib.ph_alltoallv(sp, sb, rp, rb))
+        for q in range(self.world):
+            if recvs[q] is None:
+                continue
+            p0, p1 = plan["recv"][q]
+            lit = [ALL] * nd
+            lit[j] = rng(p0, p1 - 1)
+            out.set_chunk(lit, recvs[q])
+        return ShardedNArray(plan["new_shape"], out)
 
     # ---- reductions -----------------------------------------------------------------------
     def _row_elems(self):

@@ -78,6 +78,14 @@ def main():
     assert sg.sum(axis=0).to_host().tobytes() == g.sum(axis=0, dtype=np.float64).astype(np.float32).tobytes()
     assert sg.max(axis=2).to_global().tobytes() == g.max(axis=2).tobytes()
     assert sg[ph.ALL, ph.rng(1, 9, 2), 3].to_global().tobytes() == np.ascontiguousarray(g[:, 1:10:2, 3]).tobytes()
+    # transposes across shards (ph_alltoallv): default pattern = reversed axes, then two others
+    assert sg.permute().to_global().tobytes() == np.ascontiguousarray(g.transpose(2, 1, 0)).tobytes()
+    assert sg.permute(1, 0, 2).to_global().tobytes() == np.ascontiguousarray(g.transpose(1, 0, 2)).tobytes()
+    assert sg.permute(0, 2, 1).to_global().tobytes() == np.ascontiguousarray(g.transpose(0, 2, 1)).tobytes()
+    m2 = rs.rand(1000 * world + 3, 517).astype(np.float64)
+    t2 = S.ShardedNArray.from_global(m2).permute()
+    assert t2.shape == [517, 1000 * world + 3] and t2.to_global().tobytes() == np.ascontiguousarray(m2.T).tobytes()
+    assert t2.permute().to_global().tobytes() == m2.tobytes()              # transposing twice is the identity
     sg.set_mask(sg > sh, 0.0)
     assert sg.to_global().tobytes() == np.where(g > h, np.float32(0), g).tobytes()
     dist.barrier()

@@ -86,6 +86,38 @@ def _worker(rank, world, port, out_dir):
             nxt[-g:] = hi_recv.numpy()
         cur = nxt
     np.save(os.path.join(out_dir, f"heat2_{rank}.npy"), cur[g:-g])
+    # ---- transpose across shards: the plan of ShardedNArray.permute driven with numpy blocks
+    #      and gloo send/recv standing in for ph_alltoallv
+    tsrc = rs.randint(0, 1000, size=(7, 5, 6)).astype(np.int32)     # uneven split 4 + 3 on axis 0
+    for pat in ([2, 1, 0], [1, 0, 2], [2, 0, 1], [0, 2, 1]):
+        plan = S.transpose_plan(tsrc.shape, pat, world, rank)
+        r0, r1 = S.shard_range(tsrc.shape[0], world, rank)
+        mine = tsrc[r0:r1]
+        if plan["local"]:
+            res = np.ascontiguousarray(mine.transpose(pat))
+        else:
+            k, j = plan["k"], plan["j"]
+            m0, m1 = plan["my_new_rows"]
+            res = np.zeros([m1 - m0] + plan["new_shape"][1:], np.int32)
+            reqs, bufs = [], {}
+            for q in range(world):
+                k0, k1 = plan["send"][q]
+                sl = [slice(None)] * 3; sl[k] = slice(k0, k1)
+                blk = np.ascontiguousarray(mine[tuple(sl)].transpose(pat))
+                assert list(blk.shape) == plan["send_shape"][q]
+                if q == rank:
+                    bufs[q] = torch.from_numpy(blk.copy())
+                else:
+                    reqs.append(dist.isend(torch.from_numpy(blk), q))
+                    bufs[q] = torch.zeros(plan["recv_shape"][q], dtype=torch.int32)
+                    reqs.append(dist.irecv(bufs[q], q))
+            for rq in reqs:
+                rq.wait()
+            for q in range(world):
+                p0, p1 = plan["recv"][q]
+                sl = [slice(None)] * 3; sl[j] = slice(p0, p1)
+                res[tuple(sl)] = bufs[q].numpy()
+        np.save(os.path.join(out_dir, f"perm_{''.join(map(str, pat))}_{rank}.npy"), res)
     # ---- reductions over axis-0 shards
     data = rs.randint(-8, 9, size=(10, 7)).astype(np.float32)
     data[3, 2] = data[8, 1] = 50.0                                 # tie across the two shards
@@ -118,6 +150,10 @@ def test_two_rank_partitioning(tmp_path):
     want = O.heat_step_nd(want, np.float32(0.1))                    # 6 steps for the 2-ghost-plane run
     got2 = np.concatenate([np.load(tmp_path / f"heat2_{r}.npy") for r in range(world)])
     assert got2.tobytes() == want.tobytes()
+    tsrc = rs.randint(0, 1000, size=(7, 5, 6)).astype(np.int32)
+    for pat in ([2, 1, 0], [1, 0, 2], [2, 0, 1], [0, 2, 1]):
+        got = np.concatenate([np.load(tmp_path / f"perm_{''.join(map(str, pat))}_{r}.npy") for r in range(world)])
+        assert got.tobytes() == np.ascontiguousarray(tsrc.transpose(pat)).tobytes(), pat
     data = rs.randint(-8, 9, size=(10, 7)).astype(np.float32)
     data[3, 2] = data[8, 1] = 50.0
     for r in range(world):
