@@ -363,6 +363,7 @@ def run_ours(args):
     want = CO.flat_mul_rowvec_add_f32(a_h[:chk_rows].copy(), b_h, c_h[:chk_rows].copy())
     parity_ok = bool(e2e_out[:chk_rows].tobytes() == want.tobytes())
 
+    os.sched_setaffinity(0, all_cpus)               # the CPU baselines may use every host core
     extras = None
     if not args.no_extras:
         try:
@@ -370,7 +371,6 @@ def run_ours(args):
         except Exception as e:                       # extras never invalidate the headline
             extras = {"error": repr(e)}
 
-    os.sched_setaffinity(0, all_cpus)               # the CPU baseline may use every host core
     if rank == 0:
         peak, peak_src = measured_peak()
         dom_ms = statistics.mean(add_ms)
@@ -465,6 +465,27 @@ def run_extras(ph, lib, dist, world, rank, torch):
                                                "2-plane NCCL send/recv halos every 2 steps, overlapped with the interior",
                               "algorithmic_bytes_per_cell_update": 8,
                               "hbm_gbs_per_gpu": round(8 * G ** 3 / world / (heat_ms * 1e-3) / 1e9, 1)}
+    if world == 1:
+        # the reference's CPU path beside it: the slice-arithmetic step through ph-core's operator
+        # structure (C port, one thread) on a 160^3 sample, and the flat OpenMP loop nest on 512^3
+        from oracle import c_oracle as CO
+        rs = np.random.RandomState(1)
+        small = (rs.rand(160, 160, 160) * 100).astype(np.float32)
+        t0 = time.perf_counter(); CO.ref_heat_step_3d_f32(small, 0.1); dt_ref = time.perf_counter() - t0
+        CO.use_all_cores()
+        mid = (rs.rand(512, 512, 512) * 100).astype(np.float32)
+        tmp = np.empty_like(mid)
+        CO.flat_heat_step_3d_f32(mid, 0.1, tmp)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            CO.flat_heat_step_3d_f32(mid, 0.1, tmp)
+        dt_flat = (time.perf_counter() - t0) / 3
+        out["heat3d_2048_f32"]["cpu_baseline"] = {
+            "value": round(small.size / dt_ref / 1e9, 5), "unit": "Gcell-updates/s", "cores": 1, "kind": "port",
+            "sample": f"one step of a 160^3 f32 grid through the reference's operator structure ({dt_ref:.2f} s)",
+            "flat_openmp_all_cores": {"value": round(mid.size / dt_flat / 1e9, 3), "cores": CO.num_threads(),
+                                      "sample": "512^3 f32, flat loop nest + OpenMP, mean of 3"}}
+        del small, mid, tmp
     del a, b
     # ---- full sum of 1e9 f32 sharded along axis 0
     n_total = 1000 * 1000 * 1000
@@ -485,6 +506,18 @@ def run_extras(ph, lib, dist, world, rank, torch):
     out["reduce_sum_1e9_f32"] = {"gbs": round(4 * n_total / (red_ms * 1e-3) / 1e9, 1), "ms": round(red_ms, 4),
                                  "result_ok": bool(abs(float(total) - n_total) <= 1e-4 * n_total),
                                  "collective": "ncclAllReduce of one f32 partial per GPU" if world > 1 else "none"}
+    if world == 1:
+        from oracle import c_oracle as CO
+        xs = np.random.RandomState(2).rand(200_000_000).astype(np.float32)
+        t0 = time.perf_counter(); CO.ref_sum_f32(xs); dt_ref = time.perf_counter() - t0
+        CO.use_all_cores()
+        CO.flat_sum_f32(xs)
+        t0 = time.perf_counter(); CO.flat_sum_f32(xs); dt_flat = time.perf_counter() - t0
+        out["reduce_sum_1e9_f32"]["cpu_baseline"] = {
+            "value": round(xs.nbytes / dt_ref / 1e9, 3), "unit": "GB/s", "cores": 1, "kind": "port",
+            "sample": f"2e8 of 1e9 elements, Enumerable#sum as a sequential f32 left fold ({dt_ref:.2f} s)",
+            "flat_openmp_all_cores": {"value": round(xs.nbytes / dt_flat / 1e9, 2), "cores": CO.num_threads(),
+                                      "sample": "2e8 elements, OpenMP reduction in f64"}}
     return out
 
 

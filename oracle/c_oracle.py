@@ -78,3 +78,32 @@ def flat_binary(op: int, a, b, out=None) -> np.ndarray:
     fn = {np.dtype(np.float32): load().flat_binary_f32, np.dtype(np.float64): load().flat_binary_f64}[a.dtype]
     fn(C.c_int(op), _p(a), _p(b), _p(out), C.c_int64(a.size))
     return out
+
+
+def ref_heat_step_3d_f32(s: np.ndarray, coeff) -> np.ndarray:
+    """One 3-D heat step through the reference's operator structure (slices fetched with the
+    lexicographic iterator, one materialised array per operator), one thread."""
+    assert s.dtype == np.float32 and s.ndim == 3 and s.flags.c_contiguous
+    out = np.empty_like(s)
+    load().ref_heat_step_3d_f32(_p(s), _p(out), _shape(s.shape), C.c_float(float(coeff)))
+    return out
+
+
+def flat_heat_step_3d_f32(s: np.ndarray, coeff, out=None) -> np.ndarray:
+    assert s.dtype == np.float32 and s.ndim == 3 and s.flags.c_contiguous
+    out = np.empty_like(s) if out is None else out
+    load().flat_heat_step_3d_f32(_p(s), _p(out), _shape(s.shape), C.c_float(float(coeff)))
+    return out
+
+
+def ref_sum_f32(x: np.ndarray) -> np.float32:
+    """Enumerable#sum: sequential left fold in f32, one thread."""
+    lib = load()
+    lib.ref_sum_f32.restype = C.c_float
+    return np.float32(lib.ref_sum_f32(_p(x), C.c_int64(x.size)))
+
+
+def flat_sum_f32(x: np.ndarray) -> float:
+    lib = load()
+    lib.flat_sum_f32.restype = C.c_double
+    return float(lib.flat_sum_f32(_p(x), C.c_int64(x.size)))

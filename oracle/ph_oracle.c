@@ -179,3 +179,100 @@ void flat_mul_rowvec_add_f32(const float* a, const float* b, const float* c, flo
   }
 DEF_FLAT_BINARY(flat_binary_f32, float)
 DEF_FLAT_BINARY(flat_binary_f64, double)
+
+/* ---- gather / scatter, reference structure ---------------------------------------------
+ * NArray#unsafe_fetch_chunk (src/n_array.cr:450-453): a lexicographic iterator over the region
+ * yields buffer indices, the chunk is filled in lex order.  unsafe_set_chunk (:484-492) is the
+ * mirror image.  first/step/last are per axis, in elements of `shape`. */
+static void ref_fetch_chunk_f32(const float* src, const int64_t* shape, int rank, const int64_t* first,
+                                const int64_t* step, const int64_t* last, float* out) {
+  lex_iter it;
+  lex_init(&it, rank, first, step, last, shape);
+  int64_t idx = 0;
+  while (lex_next(&it)) out[idx++] = src[it.buffer_index];
+}
+
+static void ref_set_chunk_f32(float* dst, const int64_t* shape, int rank, const int64_t* first,
+                              const int64_t* step, const int64_t* last, const float* src) {
+  lex_iter it;
+  lex_init(&it, rank, first, step, last, shape);
+  int64_t idx = 0;
+  while (lex_next(&it)) dst[it.buffer_index] = src[idx++];
+}
+
+/* NArray#map with a scalar (src/n_array.cr:589-595 through multi_indexable.cr:947-951) */
+static void ref_map_scalar_f32(int op, const float* a, float s, float* out, int64_t n) {
+  for (int64_t i = 0; i < n; i++) out[i] = op == 2 ? a[i] * s : (op == 0 ? a[i] + s : a[i] - s);
+}
+
+/* One 3-D heat step exactly as the slice arithmetic of SURVEY.md 8(a) a-9 would run through
+ * ph-core's operators (examples/heat_equation.cr:38-51 generalised): every slice is a fetched
+ * chunk, every operator a materialised array, one thread.
+ *   c = s[1...-1, 1...-1, 1...-1]; two_c = c * 2
+ *   d_k = (s[lo_k] - two_c) + s[hi_k];  lap = (d_0 + d_1) + d_2
+ *   nxt = s.clone; nxt[1...-1, ...] = c + lap * C                                            */
+void ref_heat_step_3d_f32(const float* s, float* nxt, const int64_t* shape, float coeff) {
+  const int64_t n0 = shape[0], n1 = shape[1], n2 = shape[2];
+  memcpy(nxt, s, sizeof(float) * n0 * n1 * n2);                       /* s.clone */
+  if (n0 < 3 || n1 < 3 || n2 < 3) return;
+  const int64_t ishape[3] = {n0 - 2, n1 - 2, n2 - 2};
+  const int64_t m = ishape[0] * ishape[1] * ishape[2];
+  float* c = (float*)malloc(sizeof(float) * m);
+  float* two_c = (float*)malloc(sizeof(float) * m);
+  float* lo = (float*)malloc(sizeof(float) * m);
+  float* hi = (float*)malloc(sizeof(float) * m);
+  float* t = (float*)malloc(sizeof(float) * m);
+  float* d = (float*)malloc(sizeof(float) * m);
+  float* lap = (float*)malloc(sizeof(float) * m);
+  const int64_t one[3] = {1, 1, 1};
+  int64_t first[3] = {1, 1, 1}, last[3] = {n0 - 2, n1 - 2, n2 - 2};
+  ref_fetch_chunk_f32(s, shape, 3, first, one, last, c);
+  ref_map_scalar_f32(2, c, 2.0f, two_c, m);
+  for (int k = 0; k < 3; k++) {
+    int64_t f[3] = {1, 1, 1}, l[3] = {n0 - 2, n1 - 2, n2 - 2};
+    f[k] = 0; l[k] = shape[k] - 3;
+    ref_fetch_chunk_f32(s, shape, 3, f, one, l, lo);                  /* s[lo_k] */
+    f[k] = 2; l[k] = shape[k] - 1;
+    ref_fetch_chunk_f32(s, shape, 3, f, one, l, hi);                  /* s[hi_k] */
+    ref_map_with_f32(1, lo, two_c, t, ishape, 3);                     /* lo - two_c */
+    ref_map_with_f32(0, t, hi, d, ishape, 3);                         /* ... + hi   */
+    if (k == 0) memcpy(lap, d, sizeof(float) * m);
+    else { ref_map_with_f32(0, lap, d, t, ishape, 3); memcpy(lap, t, sizeof(float) * m); }
+  }
+  ref_map_scalar_f32(2, lap, coeff, t, m);                            /* lap * C */
+  ref_map_with_f32(0, c, t, d, ishape, 3);                            /* c + ... */
+  ref_set_chunk_f32(nxt, shape, 3, first, one, last, d);              /* nxt[interior] = ... */
+  free(c); free(two_c); free(lo); free(hi); free(t); free(d); free(lap);
+}
+
+/* the same step as one flat loop nest + OpenMP: the most generous CPU baseline */
+void flat_heat_step_3d_f32(const float* s, float* nxt, const int64_t* shape, float coeff) {
+  const int64_t n0 = shape[0], n1 = shape[1], n2 = shape[2], p = n1 * n2;
+#pragma omp parallel for schedule(static)
+  for (int64_t z = 0; z < n0; z++)
+    for (int64_t y = 0; y < n1; y++)
+      for (int64_t x = 0; x < n2; x++) {
+        const int64_t i = z * p + y * n2 + x;
+        if (z == 0 || z == n0 - 1 || y == 0 || y == n1 - 1 || x == 0 || x == n2 - 1) { nxt[i] = s[i]; continue; }
+        const float c = s[i], two_c = c * 2.0f;
+        const float d0 = (s[i - p] - two_c) + s[i + p];
+        const float d1 = (s[i - n2] - two_c) + s[i + n2];
+        const float d2 = (s[i - 1] - two_c) + s[i + 1];
+        nxt[i] = c + ((d0 + d1) + d2) * coeff;
+      }
+}
+
+/* Enumerable#sum over NArray#each (src/n_array.cr:556-564): a left fold in T, one thread */
+float ref_sum_f32(const float* x, int64_t n) {
+  float acc = 0.0f;
+  for (int64_t i = 0; i < n; i++) acc = acc + x[i];
+  return acc;
+}
+
+/* per-thread partial sums in double + OpenMP reduction: the most generous CPU baseline */
+double flat_sum_f32(const float* x, int64_t n) {
+  double acc = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : acc)
+  for (int64_t i = 0; i < n; i++) acc += (double)x[i];
+  return acc;
+}

@@ -526,3 +526,21 @@ def test_heat_nd_definition():
     d1 = f(f(s[i, j - 1, k] - f(f(2) * c)) + s[i, j + 1, k])
     d2 = f(f(s[i, j, k - 1] - f(f(2) * c)) + s[i, j, k + 1])
     assert n[i, j, k] == f(c + f(f(f(d0 + d1) + d2) * f(0.1)))
+
+
+def test_c_port_heat_and_sum_match_the_numpy_oracle():
+    """The C ports timed as CPU baselines (reference-structured and flat OpenMP) restate the
+    same arithmetic as the numpy oracle: 3-D heat step bit for bit, sequential f32 sum exactly."""
+    from oracle import c_oracle as CO
+    rs = np.random.RandomState(9)
+    for shape in [(3, 3, 3), (5, 4, 7), (20, 17, 33), (2, 9, 9)]:
+        s = (rs.rand(*shape) * 100).astype(np.float32)
+        want = O.heat_step_nd(s, np.float32(0.1))
+        assert CO.ref_heat_step_3d_f32(s, 0.1).tobytes() == want.tobytes(), shape
+        assert CO.flat_heat_step_3d_f32(s, 0.1).tobytes() == want.tobytes(), shape
+    x = rs.rand(100_003).astype(np.float32)
+    acc = np.float32(0)
+    for v in x[:2000]:
+        acc = np.float32(acc + v)                                    # Enumerable#sum: left fold in T
+    assert CO.ref_sum_f32(x[:2000].copy()) == acc
+    assert abs(CO.flat_sum_f32(x) - float(x.astype(np.float64).sum())) < 1e-6 * x.size
