@@ -14,6 +14,11 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+# Rows here repeat ONE kernel on the SAME operands back to back; with the library's alternating
+# traversal direction every repetition would find the far end of its inputs in L2 (+10 % on the
+# elementwise rows).  That reuse is real for chained operators (bench.py measures it on a*b+c) but
+# an artefact here, so the per-kernel table streams every launch the same way: HBM numbers.
+os.environ.setdefault("PH_FLAT_NO_ALTERNATE", "1")
 import ph_core_b200 as ph
 from ph_core_b200 import DeviceNArray as D, heat, rng, _lib
 

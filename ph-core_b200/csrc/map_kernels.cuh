@@ -13,6 +13,7 @@
 #pragma once
 #include "ph_common.cuh"
 #include <algorithm>
+#include <stdlib.h>
 
 namespace ph {
 
@@ -31,6 +32,7 @@ struct MapArgs {
   int rows_per_block;
   int all_array;            // every input is OPND_ARRAY
   uint32_t period;          // flat: OPND_PERIODIC operands repeat every `period` elements (0 = none)
+  int reverse;              // flat: visit the tiles from the last to the first (see launch_flat)
   int64_t gx;               // rows: number of column tiles (1-D grid = gx * slabs * chunks)
   int tx, tx_log2;          // rows: threads along the inner axis (power of two <= 256)
   uint32_t* flags;
@@ -58,7 +60,7 @@ __global__ void __launch_bounds__(MAP_THREADS) map_flat_kernel(const MapArgs<F::
   using Out = typename F::Out;
   constexpr int NIN = F::NIN;
   const int64_t tile = (int64_t)MAP_THREADS * E * UNROLL;
-  const int64_t base = (int64_t)blockIdx.x * tile;
+  const int64_t base = (int64_t)(a.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * tile;
   uint32_t err = 0;
   Out* __restrict__ out = reinterpret_cast<Out*>(a.out);
 
@@ -220,11 +222,19 @@ struct MapOperand {
   bool is_param = false;
 };
 
+// Consecutive flat launches traverse their arrays in OPPOSITE directions.  The fluent API runs an
+// expression as a chain of launches, each consuming the array the previous one produced
+// (`t = a * b` then `t + c`); when a launch ends, the last ~100 MB it wrote are still in the
+// 126 MB L2.  A consumer that starts from the far end reads them from L2 instead of HBM (and a
+// temporary that is overwritten while still resident never reaches HBM at all).  Elementwise
+// results do not depend on the visiting order.  PH_FLAT_NO_ALTERNATE=1 disables it (A/B runs).
 template <typename F, int E, int UNROLL>
-inline int32_t launch_flat(const MapArgs<F::NIN>& a) {
+inline int32_t launch_flat(MapArgs<F::NIN>& a) {
   const int64_t tile = (int64_t)MAP_THREADS * E * UNROLL;
   const int64_t blocks = ceil_div(a.n, tile);
   if (blocks > 0x7fffffffLL) return set_error(PH_ERR_INVALID, "array too large for one launch");
+  static const bool alternate = getenv("PH_FLAT_NO_ALTERNATE") == nullptr;
+  a.reverse = alternate ? (int)(rt().flat_launches++ & 1) : 0;
   map_flat_kernel<F, E, UNROLL><<<(unsigned)blocks, MAP_THREADS, 0, rt().stream>>>(a);
   PH_LAUNCH_CHECK("map_flat_kernel");
   return PH_OK;

@@ -24,6 +24,7 @@ struct Runtime {
   void* h_scratch = nullptr;           // pinned result staging (64 B)
   int sm_count = 148;
   long long launches = 0;
+  unsigned long long flat_launches = 0; // parity = traversal direction of the next flat elementwise launch
   char err[512] = {0};
 };
 Runtime& rt();
