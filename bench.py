@@ -12,10 +12,15 @@ two kernels with a materialised, individually rounded temporary
 N > 1 is launched by torchrun, one rank per GPU; elementwise work shards along the leading
 axis with no data-path collective (weak scaling: every rank owns an 8192x8192 shard).
 
-Prints ONE JSON line (rank 0).  `value` = whole-job GB/s with inputs resident in HBM;
-`e2e` = the same metric through the public API with HOST buffers (pinned H2D of a, b, c and
-D2H of the result inside the timed region); `roofline` describes the dominant kernel;
-`cpu_baseline` is the oracle's C port timed on this box's host cores on a bounded sample.
+Prints ONE JSON line (rank 0).  `value` = whole-job GB/s with inputs resident in HBM (two CUDA
+events around the K steps); `e2e` = the same metric through the public API with HOST buffers
+(pinned H2D of a, b, c and D2H of the result inside the timed region); `roofline` describes the
+dominant kernel (its own duration from events on every 8th step of the same timed region, DRAM
+traffic from the committed ncu capture); `cpu_baseline` = the oracle's C port of the REFERENCE'S
+structure (single thread: ph-core has no threads) timed on this box, with the flat OpenMP loop on
+all cores reported beside it; `extras` = the 2048^3 heat stencil and the 1e9-element sum (BASELINE
+configs 3 and 4), each with its own CPU baseline at N = 1.
+`--impl reference` times that same reference-structured port as the reference arm.
 """
 from __future__ import annotations
 
