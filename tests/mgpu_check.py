@@ -52,6 +52,19 @@ def main():
         assert fin.tobytes() == whole[lay["start"]:lay["stop"]].tobytes(), \
             f"rank {rank}: big heat slab (ghost {ghost}, {steps} steps) differs from 1-GPU run"
 
+    # ---- 2-D grid (BASELINE configs[0] generalised), two ghost rows, two steps per pass
+    flat2 = (rs.rand(64 * world + 5, 520) * 100).astype(np.float32)
+    for ghost, steps in ((2, 8), (2, 5), (1, 3)):
+        want = flat2.copy()
+        for _ in range(steps):
+            want = O.heat_step_nd(want, np.float32(0.1))
+        lay = S.slab_layout(flat2.shape[0], world, rank, ghost)
+        loc = S.slab_from_global(flat2, world, rank, ghost)
+        a, b = D.from_host(loc), D.from_host(loc)
+        fin = S.heat_run_sharded(a, b, 0.1, steps, ghost).to_host()[ghost:-ghost]
+        assert fin.tobytes() == want[lay["start"]:lay["stop"]].tobytes(), \
+            f"rank {rank}: 2-D heat slab (ghost {ghost}, {steps} steps) differs from oracle"
+
     # ---- sharded reductions
     data = rs.randint(-8, 9, size=(8 * world + 1, 50, 30)).astype(np.float32)
     data[3, 2, 1] = data[-1, 4, 4] = 99.0                      # tie across shards
