@@ -45,11 +45,11 @@ BYTES_MUL = 2 * N * 4 + COLS * 4          # read a, write t, read b once
 BYTES_ADD = 3 * N * 4                     # read t, read c, write out
 BYTES_STEP = BYTES_MUL + BYTES_ADD
 SEED = 20261017
-# dram__bytes_read.sum + dram__bytes_write.sum of one `out = t + c` launch, from the committed
-# ncu --set full capture of this very command (profiles/r01_ncu_bench_kernels.csv): 536.89 + 222.32 MB
-NCU_TRAFFIC_ADD = 759209728
-METRIC = "f32 elementwise HBM GB/s"
-WORKLOAD = "elementwise a*b+c, b=[1,8192] row-vector broadcast, 8192x8192 f32 (two reference-faithful kernels)"
+# dram__bytes_read.sum + dram__bytes_write.sum of one `out = t + c` launch of this very command,
+# captured in ONE ncu pass with the caches left alone (profiles/r01_bench_dram_warm.csv):
+# 504.0 MB read (33 MB of the temporary come from L2) + 273.3 MB written.  The cold-cache
+# `--set full` capture (profiles/r01_ncu_bench_kernels.csv) reads 536.9 MB = the algorithmic bytes.
+NCU_TRAFFIC_ADD = 777292032
 
 
 def measured_peak():
@@ -408,8 +408,8 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "map_flat_kernel<BinaryOp<float,ADD>,8,2> (out = t + c, all operands contiguous)",
                          "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": NCU_TRAFFIC_ADD, "peak_source": peak_src,
-                         "traffic_source": "profiles/r01_ncu_bench_kernels.csv (ncu --set full, dram__bytes_read.sum + "
-                                           "dram__bytes_write.sum per launch; 46 MB of the 268 MB written are still dirty in L2 at kernel end)",
+                         "traffic_source": "profiles/r01_bench_dram_warm.csv (ncu, one pass, --cache-control none: dram__bytes_read.sum 504.0 MB "
+                                           "+ dram__bytes_write.sum 273.3 MB per launch; cold-cache --set full capture: 536.9 MB read)",
                          "algorithmic_bytes_per_launch": BYTES_ADD, "avg_launch_ms": round(dom_ms, 5),
                          "launches_timed": len(add_ms),
                          "other_kernels": {"map_flat_kernel<BinaryOp<float,MUL>,8,2> (t = a * b, b periodic: the [1,8192] row vector)": {

@@ -26,6 +26,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--quick", action="store_true")
 ap.add_argument("--only", default="")
 ap.add_argument("--reps", type=int, default=20)
+ap.add_argument("--warm", type=int, default=3, help="untimed launches per row (0 under ncu)")
+ap.add_argument("--inner", type=int, default=4, help="back-to-back launches per timing (1 under ncu)")
 ap.add_argument("--big-heat", action="store_true", help="include the 2048^3 f32 stencil (69 GB)")
 ap.add_argument("--heat-shape", default="", help="only run the 3-D stencil on this z,y,x grid")
 args = ap.parse_args()
@@ -41,10 +43,12 @@ except Exception:
     pass
 
 
-def timeit(fn, reps=None, warm=3, inner=4):
+def timeit(fn, reps=None, warm=None, inner=None):
     """`inner` back-to-back launches between two CUDA events (a lone launch would add ~2.5 us of
     launch latency and ramp to kernels that run for 80 us), repeated `reps` times."""
-    reps = reps or args.reps
+    reps = min(reps or args.reps, args.reps)       # --reps 1 (ncu runs) caps the per-row defaults too
+    warm = args.warm if warm is None else warm
+    inner = args.inner if inner is None else inner
     for _ in range(warm):
         fn()
     ts = []
