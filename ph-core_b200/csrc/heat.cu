@@ -11,7 +11,11 @@
 // exactly the association order above, so ONE step is bit-identical to the reference's
 // operator-by-operator evaluation with materialised temporaries.
 //
-// Kernel: 2.5-D streaming.  A block owns a (rows x columns) tile and marches along axis 0;
+// Kernels.  `simulate` (ph_heat_run, ph_heat_run_sharded with two ghost planes) advances TWO time
+// steps per pass over HBM: heat2d_tb_kernel below for rank 2 (warp-shuffle temporal blocking) and
+// heat_tma2_kernel in heat_tma.cu for rank 3 (TMA ring + register marching).  A single step
+// (`update_temp`, an odd last step, shapes the two-step kernels cannot take) uses heat_tma_kernel
+// (rank 3) or the 2.5-D streaming kernel here: a block owns a (rows x columns) tile and marches along axis 0;
 // each thread keeps its cells of planes z-1, z, z+1 in registers, so every cell is read from
 // HBM once (8 B per cell-update for f32: one read + one write).  In-plane neighbours come
 // from warp shuffles (x) and a double-buffered shared-memory row exchange (y); only the tile

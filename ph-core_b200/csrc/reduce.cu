@@ -9,7 +9,8 @@
 //     commutative pre-filter (sum of positives / of negatives fit in T => no prefix can
 //     overflow) decides almost always; otherwise an ordered (sum, max-prefix, min-prefix)
 //     monoid pass decides exactly.
-//   * float sum: two-pass tree in T (deterministic for a given shape), tolerance-checked.
+//   * float sum: per-block tree in T, then the last block to finish folds the partials in a
+//     fixed order inside the same launch (deterministic for a given shape), tolerance-checked.
 // Per-axis reductions are defined as the fold of each_slice(axis) in increasing index
 // (src/multi_indexable.cr:742-748); the column-strip kernel keeps exactly that order.
 #include "map_kernels.cuh"
