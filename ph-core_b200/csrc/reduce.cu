@@ -26,6 +26,11 @@ template <typename T> struct Acc { using type = T; };             // sum accumul
 template <> struct Acc<int32_t> { using type = int64_t; };
 template <> struct Acc<int64_t> { using type = __int128; };
 template <> struct Acc<uint8_t> { using type = int64_t; };
+template <> struct Acc<int8_t> { using type = int64_t; };
+template <> struct Acc<int16_t> { using type = int64_t; };
+template <> struct Acc<uint16_t> { using type = int64_t; };
+template <> struct Acc<uint32_t> { using type = int64_t; };
+template <> struct Acc<uint64_t> { using type = __int128; };
 
 template <typename T> __device__ __forceinline__ T shfl_down_t(T v, int off) {
   if constexpr (sizeof(T) == 16) {
@@ -901,6 +906,11 @@ using namespace ph;
     case PH_I32: return CALL(int32_t);                                                     \
     case PH_I64: return CALL(int64_t);                                                     \
     case PH_U8: return CALL(uint8_t);                                                      \
+    case PH_I8: return CALL(int8_t);                                                       \
+    case PH_I16: return CALL(int16_t);                                                     \
+    case PH_U16: return CALL(uint16_t);                                                    \
+    case PH_U32: return CALL(uint32_t);                                                    \
+    case PH_U64: return CALL(uint64_t);                                                    \
     default: return set_error(PH_ERR_UNSUPPORTED, "dtype %d has no reduction kernels", dtype); \
   }
 

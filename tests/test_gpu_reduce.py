@@ -142,6 +142,36 @@ def test_last_axis_register_kernel_zero_signs_ties_nan(K):
         D.from_host(a).max(axis=1)
 
 
+@pytest.mark.parametrize("dtype", [np.int8, np.int16, np.uint8, np.uint16, np.uint32, np.uint64])
+def test_remaining_crystal_integer_types(dtype):
+    """Every Crystal primitive integer reduces on the device: sum (overflow-checked in T: raises when
+    a prefix leaves T), min / max / arg* (first extremum), full and per axis."""
+    rs = np.random.RandomState(31)
+    info = np.iinfo(dtype)
+    lo = -3 if info.min < 0 else 0
+    a = rs.randint(lo, 4, size=(6, 40, 24)).astype(dtype)          # |sum| stays far inside Int8 per row
+    a[2, 7, 5] = a[4, 1, 2] = 50                                   # tie for the max
+    d = D.from_host(a)
+    if info.max > a.astype(np.int64).sum():
+        assert d.sum() == dtype(int(a.astype(np.int64).sum()))
+    else:                                                          # Int8 / UInt8: the total leaves T
+        with pytest.raises(ph.CrOverflowError):
+            d.sum()
+        take_flags()
+    assert d.max() == 50 and d.min() == a.min()
+    v, c = d.argmax(); assert (v, c) == (dtype(50), [2, 7, 5])
+    for axis in range(3):
+        for which in ["max", "min", "argmax", "argmin"]:
+            assert_bits(getattr(d, which)(axis=axis).to_host(), O.reduce_axis(a, axis, which), f"{which} axis={axis}")
+    row_sums = a.astype(np.int64).sum(axis=2)
+    if row_sums.max() <= info.max and row_sums.min() >= info.min:
+        assert_bits(d.sum(axis=2).to_host(), row_sums.astype(dtype), "sum axis=2")
+    big = np.full(300, info.max // 100 + 1, dtype)                 # 300 x (max/100 + 1) overflows T
+    with pytest.raises(ph.CrOverflowError):
+        D.from_host(big).sum()
+    take_flags()
+
+
 def test_axis_int_overflow_and_errors():
     a = np.array([[2**31 - 1, 1], [1, 1], [-5, 1]], np.int32)
     with pytest.raises(ph.CrOverflowError):
