@@ -45,6 +45,9 @@ BYTES_MUL = 2 * N * 4 + COLS * 4          # read a, write t, read b once
 BYTES_ADD = 3 * N * 4                     # read t, read c, write out
 BYTES_STEP = BYTES_MUL + BYTES_ADD
 SEED = 20261017
+METRIC = "f32 elementwise HBM GB/s"   # BASELINE.json metric, first clause (the heat clause is in extras)
+WORKLOAD = ("elementwise a*b+c, b=[1,8192] row-vector broadcast, 8192x8192 f32 "
+            "(two reference-faithful kernels)")
 # dram__bytes_read.sum + dram__bytes_write.sum of one `out = t + c` launch of this very command,
 # captured in ONE ncu pass with the caches left alone (profiles/r01_bench_dram_warm.csv):
 # 504.0 MB read (33 MB of the temporary come from L2) + 273.3 MB written.  The cold-cache
