@@ -1,0 +1,349 @@
+// device_narray_spec.cpp -- the reference's own specs for the hot path, replayed on the
+// device-backed array through the C++ host layer (include/ph_narray.hpp).  Each block cites
+// the spec it replays; expectations are the reference's golden literals, typed in here (no
+// oracle is linked: this program is product-side host code + libphgpu only).
+//
+//   spec/n_array_spec.cr:211-333, 446-447   fetch / set chunk, mask store, elementwise
+//   spec/multi_writable_spec.cr:14-93       [1.., 1..] scalar / array / out of bounds, set_element
+//   spec/view_util/*_transform_spec.cr      permute / reshape / reverse known answers
+//   README.md:22-64                         narr + narr2, narr * narr2, get, [.., 1], argmax, slices
+//   examples/heat_equation.cr               21-point rod, 10 001 steps
+//
+// Build: make -C tests/cpp      Run: tests/cpp/device_narray_spec   (exit 0 = all specs passed)
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/ph_narray.hpp"
+
+using namespace Phase;
+template <class T> using V = std::vector<T>;
+
+static int g_failed = 0, g_passed = 0;
+static std::string g_current;
+
+// variadic: region literals `{1, all}` carry commas
+#define EXPECT(...)                                                                              \
+  do {                                                                                           \
+    if (!(__VA_ARGS__)) { std::printf("  FAIL %s:%d  %s   [%s]\n", __FILE__, __LINE__, #__VA_ARGS__, g_current.c_str()); g_failed++; } \
+    else g_passed++;                                                                             \
+  } while (0)
+#define EXPECT_RAISES(ExcType, ...)                                                              \
+  do {                                                                                           \
+    bool raised_ = false;                                                                        \
+    try { __VA_ARGS__; } catch (const ExcType&) { raised_ = true; }                              \
+    if (!raised_) { std::printf("  FAIL %s:%d  expected %s from: %s   [%s]\n", __FILE__, __LINE__, #ExcType, #__VA_ARGS__, g_current.c_str()); g_failed++; } \
+    else g_passed++;                                                                             \
+  } while (0)
+
+static void it(const char* name, const std::function<void()>& body) {
+  g_current = name;
+  int before = g_failed;
+  try { body(); }
+  catch (const std::exception& e) { std::printf("  FAIL unexpected exception in '%s': %s\n", name, e.what()); g_failed++; }
+  std::printf("%s %s\n", g_failed == before ? "ok  " : "FAIL", name);
+}
+
+static DeviceNArray<int32_t> stock_narr() { return DeviceNArray<int32_t>::from_host({2, 3}, V<int32_t>{0, 1, 2, 3, 4, 5}); }   // spec/n_array_spec.cr:7
+template <class T> static DeviceNArray<T> narr(const Shape& shape, const V<T>& v) { return DeviceNArray<T>::from_host(shape, v); }
+
+// Region literals -> {first, step, last} at bound 10: spec/spec_helper.cr:64-158 through
+// spec/index_region_spec.cr.  Pure host code (ph_host.h): runs with --host-only on a box without a GPU.
+static void host_specs() {
+  it("region literals at bound 10 (spec_helper.cr:64-131)", [] {
+    struct Case { Lit lit; int64_t first, step, last; };
+    const int64_t bound = 10, mid = 5;
+    const Case cases[] = {
+        {range(mid, mid), mid, 1, mid},   {range(nil, mid), 0, 1, mid},      {range_ex(nil, mid), 0, 1, mid - 1},
+        {Lit(0), 0, 1, 0},                {Lit(bound - 1), 9, 1, 9},         {range(mid, 0), mid, -1, 0},
+        {range(mid, -1, nil), mid, -1, 0}, {range_ex(0, 2, bound), 0, 2, 8},  {range_ex(0, 2, bound - 1), 0, 2, 8},
+        {range(5, -3, 1), 5, -3, 2},
+        // implicit bounds
+        {range(nil, nil), 0, 1, 9},       {range_ex(nil, nil), 0, 1, 9},     {range(mid, nil), mid, 1, 9},
+        {range(nil, -1, nil), 9, -1, 0},  {range_ex(nil, -1, 2), 9, -1, 3},  {range(nil, -4, nil), 9, -4, 1},
+        // negative indices
+        {range(-bound, nil), 0, 1, 9},    {range(nil, -bound), 0, 1, 0},     {range(nil, -1), 0, 1, 9},
+        {range(-mid, -mid + 2), 5, 1, 7}, {Lit(-mid), 5, 1, 5},
+    };
+    for (const Case& c : cases) {
+      IndexRegion reg({c.lit}, {bound}, false);
+      EXPECT(reg.r.first[0] == c.first && reg.r.step[0] == c.step && reg.r.last[0] == c.last);
+      EXPECT(reg.r.proper_shape[0] == (c.last - c.first) / c.step + 1);
+    }
+  });
+  it("out-of-bounds and malformed literals raise (spec_helper.cr:133-158; index_region_spec.cr:64-77)", [] {
+    EXPECT_RAISES(IndexError, IndexRegion({range(nil, 10)}, {10}));
+    EXPECT_RAISES(IndexError, IndexRegion({range(-11, nil)}, {10}));
+    EXPECT_RAISES(IndexError, IndexRegion({Lit(10)}, {10}));
+    EXPECT_RAISES(IndexError, IndexRegion({Lit(-11)}, {10}));
+    EXPECT_RAISES(DimensionError, IndexRegion({all, all, all}, {10, 10}));
+    IndexRegion padded({Lit(1)}, {2, 3});                       // short literals are padded with `..`
+    EXPECT(padded.shape() == Shape({3}) && padded.proper_shape() == Shape({1, 3}));
+    IndexRegion scalar({Lit(1), Lit(2)}, {2, 3});               // every axis dropped -> [1] (index_region.cr:323-335)
+    EXPECT(scalar.shape() == Shape({1}));
+    IndexRegion kept({Lit(1), Lit(2)}, {2, 3}, false);
+    EXPECT(kept.shape() == Shape({1, 1}));
+    IndexRegion empty({range_ex(0, 0), range_ex(0, 0)}, {2, 3});
+    EXPECT(empty.shape() == Shape({0, 0}) && empty.size() == 0);
+  });
+  it("trim! / translate! / reverse! / fits_in? / cover (index_region_spec.cr:218-371)", [] {
+    IndexRegion reg({range(0, 2, 8)}, {10});
+    EXPECT(reg.shape() == Shape({5}) && reg.fits_in({9}) && !reg.fits_in({8}));
+    reg.trim({5});
+    EXPECT(reg.shape() == Shape({3}) && reg.r.last[0] == 4);
+    IndexRegion two({range(1, 2), range(0, 2, 4)}, {10, 10});
+    IndexRegion moved = two;
+    moved.translate({3, 1});
+    EXPECT(moved.r.first[0] == 4 && moved.r.last[0] == 5 && moved.r.first[1] == 1 && moved.r.last[1] == 5 && moved.shape() == two.shape());
+    EXPECT_RAISES(IndexError, IndexRegion(two).translate({-4, 0}));
+    IndexRegion rev = two;
+    rev.reverse();
+    EXPECT(rev.r.first[1] == 4 && rev.r.last[1] == 0 && rev.r.step[1] == -2 && rev.shape() == two.shape());
+    IndexRegion cov = IndexRegion::cover({4, 0, 2});
+    EXPECT(cov.shape() == Shape({4, 0, 2}) && cov.size() == 0);
+    EXPECT(shape_to_size({}) == 0 && shape_to_size({3, 4}) == 12);
+  });
+}
+
+int main(int argc, char** argv) {
+  if (argc > 1 && std::strcmp(argv[1], "--host-only") == 0) {
+    host_specs();
+    std::printf("%d expectations passed, %d failed (host-only)\n", g_passed, g_failed);
+    return g_failed ? 1 : 0;
+  }
+  try { Device::init(0); }
+  catch (const DeviceError& e) {
+    std::fprintf(stderr, "device_narray_spec: %s\nno CUDA device -- the device path has no CPU fallback\n", e.what());
+    return 3;
+  }
+
+  host_specs();
+
+  it("#unsafe_fetch_chunk goldens (n_array_spec.cr:211-229)", [] {
+    auto s = stock_narr();
+    auto a = s.unsafe_fetch_chunk(IndexRegion({1, range(0, 2, 2)}, {2, 3}));
+    EXPECT(a.shape() == Shape({2}) && a.to_host() == V<int32_t>({3, 5}));
+    auto b = s.unsafe_fetch_chunk(IndexRegion({-2, range(-1, 0)}, {2, 3}));
+    EXPECT(b.to_host() == V<int32_t>({2, 1, 0}));
+    auto e = s.unsafe_fetch_chunk(IndexRegion({range_ex(0, 0), range_ex(0, 0)}, {2, 3}));
+    EXPECT(e.shape() == Shape({0, 0}) && e.size() == 0 && e.to_host().empty());
+    EXPECT(s.get({1, 1}) == 4);                       // #unsafe_fetch_element :231-236
+    EXPECT(s.get({-1, -1}) == 5);
+  });
+
+  it("#unsafe_set_chunk goldens (n_array_spec.cr:238-295)", [] {
+    auto n = stock_narr().clone();
+    n.unsafe_set_chunk(IndexRegion({1, range(0, 2, 2)}, {2, 3}), narr<int32_t>({2}, {6, 7}));
+    EXPECT(n.to_host() == V<int32_t>({0, 1, 2, 6, 4, 7}));
+    n = stock_narr().clone();
+    n.unsafe_set_chunk(IndexRegion({-2, range(-1, 0)}, {2, 3}), narr<int32_t>({3}, {6, 7, 8}));
+    EXPECT(n.to_host() == V<int32_t>({8, 7, 6, 3, 4, 5}));
+    n = stock_narr().clone();
+    IndexRegion empty({range_ex(0, 0), range_ex(0, 0)}, {2, 3});
+    n.unsafe_set_chunk(empty, narr<int32_t>({1}, {0})[{range_ex(nil, -1)}]);       // NArray[0][...-1]
+    EXPECT(n == stock_narr());
+    n.unsafe_set_chunk(IndexRegion({1, range(0, 2, 2)}, {2, 3}), 6);
+    EXPECT(n.to_host() == V<int32_t>({0, 1, 2, 6, 4, 6}));
+    n = stock_narr().clone();
+    n.unsafe_set_chunk(IndexRegion({-2, range(-1, 0)}, {2, 3}), 6);
+    EXPECT(n.to_host() == V<int32_t>({6, 6, 6, 3, 4, 5}));
+    n = stock_narr().clone();
+    n.unsafe_set_chunk(empty, 6);
+    EXPECT(n == stock_narr());
+  });
+
+  it("[]=(mask, value) goldens (n_array_spec.cr:297-333)", [] {
+    auto mask = narr<Bool>({2, 3}, {1, 0, 1, 0, 1, 0});
+    auto n = stock_narr().clone();
+    n.set_mask(mask, 6);
+    EXPECT(n.to_host() == V<int32_t>({6, 1, 6, 3, 6, 5}));
+    n = stock_narr().clone();
+    n.set_mask(mask, stock_narr() + 10);
+    EXPECT(n.to_host() == V<int32_t>({10, 1, 12, 3, 14, 5}));
+    EXPECT_RAISES(DimensionError, n.set_mask(narr<Bool>({3, 2}, {1, 0, 1, 0, 1, 0}), 6));
+    EXPECT(&n[mask] == static_cast<const MultiIndexable<int32_t>*>(&n));   // narr[mask] is self (multi_indexable.cr:479-481)
+  });
+
+  it("elementwise goldens (n_array_spec.cr:317-319, 446-447, 462-466; README.md:22-41)", [] {
+    auto s = stock_narr();
+    EXPECT((s + 10).to_host() == V<int32_t>({10, 11, 12, 13, 14, 15}));
+    EXPECT((s * 2).to_host() == V<int32_t>({0, 2, 4, 6, 8, 10}));
+    EXPECT(s.pow(2).to_host() == V<int32_t>({0, 1, 4, 9, 16, 25}));
+    EXPECT((s * 2 + s) == s * 3);
+    auto a = narr<int32_t>({2, 3}, {1, 0, 0, 0, 1, 0});
+    auto b = narr<int32_t>({2, 3}, {0, 1, 2, 10, 11, 12});
+    EXPECT((a + b).to_host() == V<int32_t>({1, 1, 2, 10, 12, 12}));
+    EXPECT((a * b).to_host() == V<int32_t>({0, 0, 0, 0, 11, 0}));
+    EXPECT(a.get({0, 0}) == 1);
+    EXPECT(a[{all, 1}].to_host() == V<int32_t>({0, 1}));
+    EXPECT(a.view({all, 1}).to_narr().to_host() == V<int32_t>({0, 1}));
+    // scalar on the LEFT keeps operand order (patches/number.cr:6-15)
+    EXPECT((10 - s).to_host() == V<int32_t>({10, 9, 8, 7, 6, 5}));
+    // Int / Int -> Float64
+    auto q = (s / 2);
+    static_assert(std::is_same<decltype(q), DeviceNArray<double>>::value, "Int / Int is Float64");
+    EXPECT(q.to_host() == V<double>({0.0, 0.5, 1.0, 1.5, 2.0, 2.5}));
+    EXPECT(s.floordiv(-2).to_host() == V<int32_t>({0, -1, -1, -2, -2, -3}));   // floored
+    EXPECT((s % -4).to_host() == V<int32_t>({0, -3, -2, -1, 0, -3}));          // sign of the divisor
+    EXPECT((-s).to_host() == V<int32_t>({0, -1, -2, -3, -4, -5}));
+    EXPECT((~s).to_host() == V<int32_t>({-1, -2, -3, -4, -5, -6}));
+    EXPECT(((s & 6) | 1).to_host() == V<int32_t>({1, 1, 3, 3, 5, 5}));
+    // comparisons -> NArray(Bool)
+    EXPECT((s > 2).to_host() == V<Bool>({0, 0, 0, 1, 1, 1}));
+    EXPECT((s <= b).to_host() == V<Bool>({1, 1, 1, 1, 1, 1}));
+    EXPECT(s.eq(b).to_host() == V<Bool>({1, 1, 1, 0, 0, 0}));
+    EXPECT(s.match(4).to_host() == V<Bool>({0, 0, 0, 0, 1, 0}));
+    EXPECT_RAISES(ShapeError, s + narr<int32_t>({3, 2}, {0, 1, 2, 3, 4, 5}));        // multi_indexable.cr:935-940
+    EXPECT_RAISES(DimensionError, s.eq(narr<int32_t>({3, 2}, {0, 1, 2, 3, 4, 5})));   // :900-902
+  });
+
+  it("float ops are single IEEE operations; a*b+c is two roundings", [] {
+    // 1 + 2^-24 is not representable: (1 * (1 + 2^-23)) + 2^-24 ... choose operands where an FMA would differ
+    float a = 1.0f + std::ldexp(1.0f, -12), b = 1.0f + std::ldexp(1.0f, -12), c = -1.0f;
+    float two = (a * b);            // rounded product
+    volatile float want = two + c;  // second rounding
+    auto A = DeviceNArray<float>::fill({1000}, a), B = DeviceNArray<float>::fill({1000}, b), Cc = DeviceNArray<float>::fill({1000}, c);
+    auto got = (A * B + Cc).to_host();
+    auto fused = A.mul_add(B, Cc).to_host();
+    float fma_result = std::fma(a, b, c);
+    EXPECT(got[0] == want && got[999] == want);
+    EXPECT(fused[0] == want && fused[500] == want);
+    EXPECT(fma_result != want);     // the test would not notice an FMA otherwise
+    auto p = DeviceNArray<double>::fill({4}, 0.05).pow(2).to_host();               // Float ** Int = powi (heat_equation.cr:20)
+    EXPECT(p[0] == 0.05 * 0.05);
+  });
+
+  it("data-dependent errors come back as the reference's classes", [] {
+    auto big = DeviceNArray<int32_t>::fill({100}, std::numeric_limits<int32_t>::max());
+    auto r = big + 1;
+    EXPECT_RAISES(OverflowError, Device::raise_pending());
+    EXPECT((big.wrapping_add(1)).get({0}) == std::numeric_limits<int32_t>::min());   // &+ wraps
+    Device::raise_pending();
+    auto z = stock_narr().floordiv(0);
+    EXPECT_RAISES(DivisionByZeroError, Device::raise_pending());
+    auto nanarr = narr<float>({3}, {1.0f, std::nanf(""), 2.0f});
+    EXPECT_RAISES(ArgumentError, nanarr.max());
+    EXPECT_RAISES(EmptyError, DeviceNArray<float>::fill({3, 0, 2}, 0.0f).max());
+    EXPECT(DeviceNArray<float>::fill({3, 0, 2}, 0.0f).sum() == 0.0f);
+  });
+
+  it("MultiWritable goldens (multi_writable_spec.cr:14-93)", [] {
+    V<int64_t> base(12);
+    for (int i = 0; i < 12; i++) base[i] = i;
+    auto d = narr<int64_t>({3, 4}, base);
+    d.set_chunk({range(1, nil), range(1, nil)}, 10);
+    EXPECT(d.to_host() == V<int64_t>({0, 1, 2, 3, 4, 10, 10, 10, 8, 10, 10, 10}));
+    d = narr<int64_t>({3, 4}, base);
+    d.set_chunk({range(1, nil), range(1, nil)}, narr<int64_t>({2, 3}, {10, 11, 12, 13, 14, 15}));
+    EXPECT(d.to_host() == V<int64_t>({0, 1, 2, 3, 4, 10, 11, 12, 8, 13, 14, 15}));
+    EXPECT_RAISES(ShapeError, d.set_chunk({range(2, nil), range(2, nil)}, narr<int64_t>({2, 3}, {10, 11, 12, 13, 14, 15})));
+    EXPECT_RAISES(IndexError, d.set_chunk({range(1, 7), range(1, nil)}, 10));
+    d.set_element({-1, -2}, 77);
+    EXPECT(d.get({2, 2}) == 77);
+    EXPECT_RAISES(IndexError, d.set_element({10, 10}, 1));
+    EXPECT_RAISES(IndexError, d.set_element({-10, -10}, 1));
+    // trailing ones are compatible (shape_util.cr:6-32)
+    d.set_chunk({range(1, nil), range(1, nil)}, narr<int64_t>({2, 3, 1}, {20, 21, 22, 23, 24, 25}));
+    EXPECT(d[{range(1, nil), range(1, nil)}].to_host() == V<int64_t>({20, 21, 22, 23, 24, 25}));
+  });
+
+  it("view transforms (permute / reshape / reverse specs; view.cr)", [] {
+    V<int32_t> v(24);
+    for (int i = 0; i < 24; i++) v[i] = i;
+    auto n = narr<int32_t>({2, 3, 4}, v);
+    auto t = n.permute();                                   // reversed axes -> [4,3,2]
+    EXPECT(t.shape() == Shape({4, 3, 2}) && t.get({3, 2, 1}) == n.get({1, 2, 3}) && t.get({1, 0, 1}) == 13);
+    auto p = n.view().permute({1, 2, 0});                   // out axis i = source axis pattern[i]
+    EXPECT(p.shape() == Shape({3, 4, 2}) && p.get({2, 3, 1}) == n.get({1, 2, 3}));
+    auto r = n.reverse();                                   // every axis flipped
+    EXPECT(r.get({0, 0, 0}) == 23 && r.to_host()[1] == 22);
+    auto rs = n.view().reshape({6, 4});                      // [3,4]->[6,2]-style reshape keeps lex order
+    EXPECT(rs.get({5, 3}) == 23 && rs.get({2, 1}) == 9);
+    auto chain = n.view({all, range(nil, -1, nil), range(0, 2, nil)}).permute().reverse();
+    auto host = chain.to_narr();
+    EXPECT(host.shape() == Shape({2, 3, 2}));
+    EXPECT(host.get({0, 0, 0}) == n.get({1, 0, 2}) && host.get({1, 2, 1}) == n.get({0, 2, 0}));
+    EXPECT_RAISES(ShapeError, n.view().reshape({5, 5}));
+    EXPECT_RAISES(IndexError, n.view().permute({0, 1, 5}));
+    // MutableView write-through: scatter through the chain (mutable_view.cr:16-18)
+    auto m = narr<int32_t>({2, 3}, {0, 0, 0, 0, 0, 0});
+    m.mutable_view().permute().set_chunk({all, all}, narr<int32_t>({3, 2}, {1, 2, 3, 4, 5, 6}));
+    EXPECT(m.to_host() == V<int32_t>({1, 3, 5, 2, 4, 6}));
+    // reshape ALIASES the buffer (n_array.cr:429-433); clone does not
+    auto alias = m.reshape({3, 2});
+    alias.set_element({0, 0}, 99);
+    EXPECT(m.get({0, 0}) == 99 && m.clone().data() != m.data() && alias.data() == m.data());
+  });
+
+  it("reductions, argmax idiom and slices (README.md:56-64)", [] {
+    auto b = narr<int32_t>({2, 3}, {0, 1, 2, 10, 11, 12});
+    auto am = b.argmax();
+    EXPECT(am.first == 12 && am.second == Coord({1, 2}));
+    EXPECT(b.sum() == 36 && b.min() == 0 && b.max() == 12);
+    auto sl = b.slices(1);
+    EXPECT(sl.size() == 3 && sl[0].to_host() == V<int32_t>({0, 10}) && sl[2].to_host() == V<int32_t>({2, 12}));
+    EXPECT(b.sum(0).to_host() == V<int32_t>({10, 12, 14}) && b.sum(1).to_host() == V<int32_t>({3, 33}));
+    EXPECT(b.argmax(1).to_host() == V<int64_t>({2, 2}) && b.max(0).to_host() == V<int32_t>({10, 11, 12}));
+    auto ties = narr<float>({2, 4}, {1, 7, 7, 0, 7, 7, 7, 7});
+    EXPECT(ties.argmax().second == Coord({0, 1}));         // the FIRST maximum wins
+    EXPECT(ties.argmax(1).to_host() == V<int64_t>({1, 0}));
+    auto tiled = narr<int32_t>({1, 3}, {1, 2, 3}).tile({2, 2});   // multi_indexable.cr:818-827
+    EXPECT(tiled.shape() == Shape({2, 6}) && tiled.to_host() == V<int32_t>({1, 2, 3, 1, 2, 3, 1, 2, 3, 1, 2, 3}));
+    // broadcasting is defined as tile + op
+    auto col = narr<int32_t>({2, 1}, {100, 200});
+    EXPECT(b.broadcast_op(PH_ADD, col) == b + col.tile({1, 3}));
+  });
+
+  it("arbitrary blocks raise instead of running on the CPU", [] {
+    auto s = stock_narr();
+    EXPECT_RAISES(DeviceBlockError, s.map([](int32_t x) { return x * x; }));
+    EXPECT_RAISES(DeviceBlockError, s.each_with(s, [](int32_t, int32_t) {}));
+    EXPECT_RAISES(DeviceBlockError, s.view().process([](int32_t x) { return x; }));
+    EXPECT_RAISES(DeviceBlockError, DeviceNArray<int32_t>::build(Shape({2, 3}), [](const Coord&) { return 0; }));
+  });
+
+  it("get_available / has_region? / region edge cases", [] {
+    auto s = stock_narr();
+    EXPECT(s.get_available({range(0, 5), range(1, 9)}).to_host() == V<int32_t>({1, 2, 4, 5}));
+    EXPECT(s.has_region({range(0, 1), 2}) && !s.has_region({range(0, 2), 2}) && !s.has_region({0, 0, 0}));
+    EXPECT_RAISES(IndexError, s[{5, 0}]);
+    EXPECT_RAISES(DimensionError, s[{0, 0, 0}]);
+    EXPECT(s.get_chunk({1, all}, false).shape() == Shape({1, 3}));     // drop: false keeps the axis
+    IndexRegion reg({range(0, 2, 8)}, {10});
+    EXPECT(reg.shape() == Shape({5}) && reg.fits_in({9}) && !reg.fits_in({8}));
+    reg.trim({5});
+    EXPECT(reg.shape() == Shape({3}));
+  });
+
+  it("examples/heat_equation.cr: 21 points, 10 001 steps", [] {
+    const double COEFF = (237 * 0.01) / ((double)(2700 * 900) * (0.05 * 0.05));
+    auto state = DeviceNArray<double>::fill({21}, 20.0);
+    state.set_element({0}, 0.0);
+    state.set_element({-1}, 100.0);
+    auto fin = Heat::simulate(state, COEFF, 10001, PH_HEAT_EXAMPLE1D).to_host();
+    double sum = 0;
+    for (double x : fin) sum += x;
+    EXPECT(std::fabs(sum - 480.0) < 1e-9);                                   // zero-flux ends conserve heat
+    EXPECT(std::fabs(fin[0] - 14.381532) < 1e-6 && std::fabs(fin[20] - 42.473872) < 1e-6);
+    // one fused step == the slice-arithmetic form written with the reference's operators (N-D rule, 2-D)
+    const int64_t H = 37, W = 53;
+    V<float> init((size_t)(H * W));
+    for (size_t i = 0; i < init.size(); i++) init[i] = (float)((i * 2654435761u) % 1000) / 7.0f;
+    auto s = narr<float>({H, W}, init);
+    const float C = 0.1f;
+    auto c = s[{range_ex(1, -1), range_ex(1, -1)}];
+    auto d0 = (s[{range_ex(0, -2), range_ex(1, -1)}] - 2.0f * c) + s[{range(2, nil), range_ex(1, -1)}];
+    auto d1 = (s[{range_ex(1, -1), range_ex(0, -2)}] - 2.0f * c) + s[{range_ex(1, -1), range(2, nil)}];
+    auto nxt = s.clone();
+    nxt.set_chunk({range_ex(1, -1), range_ex(1, -1)}, c + (d0 + d1) * C);
+    EXPECT(Heat::update_temp(s, C) == nxt);                                  // bit-identical
+  });
+
+  std::printf("%d expectations passed, %d failed, %lld kernel launches\n", g_passed, g_failed, (long long)ph_launch_count());
+  Device::shutdown();
+  return g_failed ? 1 : 0;
+}
