@@ -22,6 +22,11 @@ module Phase
       d
     end
 
+    # `ShapeUtil.shape_to_size` in Int64 (the empty shape [] has size 0).
+    def self.element_count(shape : Indexable(Int)) : Int64
+      shape.empty? ? 0_i64 : shape.reduce(1_i64) { |acc, n| acc * n }
+    end
+
     def self.count(d : Desc) : Int64
       n = 1_i64
       d.rank.times { |i| n *= d.extent[i] }

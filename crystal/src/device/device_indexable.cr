@@ -7,13 +7,18 @@ module Phase
   # fall to a per-element host loop: gathers, scatters, masked stores, operators, comparisons,
   # reductions become single kernel launches, and every block-taking method raises.
   module DeviceIndexable(T)
+    # Included here (not in the classes) so that `DeviceIndexable(T)` is a subtype of
+    # `MultiIndexable(T)`: overloads restricted to it are strictly more specific than the
+    # mixin's per-element defaults and always win.
+    include MultiIndexable::Mutable(T)
+
     abstract def dev : DeviceBuffer
     abstract def desc : LibPhGpu::Desc
 
-    protected def desc_ptr : LibPhGpu::Desc*
-      d = desc
-      box = Pointer(LibPhGpu::Desc).malloc(1) # the GC keeps it alive across the (synchronous) call
-      box.value = d
+    # A heap copy of the descriptor for the duration of one (synchronous) C call.
+    def desc_ptr : LibPhGpu::Desc*
+      box = Pointer(LibPhGpu::Desc).malloc(1)
+      box.value = desc
       box
     end
 
@@ -90,13 +95,14 @@ module Phase
       return if Descriptor.count(dst) == 0
       region_shape = Array(Int64).new(dst.rank) { |i| dst.extent[i] }
       # `compatible_shapes?` lets trailing ones differ: view the source with the region's extents
-      src_desc = Descriptor.reshape(src.desc, region_shape)
-      holder = src
-      unless src_desc
-        holder = src.to_narr
-        src_desc = Descriptor.reshape(holder.desc, region_shape).not_nil!
+      if folded = Descriptor.reshape(src.desc, region_shape)
+        src_desc = folded
+        Device.check LibPhGpu.ph_copy_strided(elem_size, src.dev.ptr, pointerof(src_desc), dev.ptr, pointerof(dst))
+      else
+        copy = src.to_narr # a strided source whose extents cannot be regrouped in place
+        src_desc = Descriptor.reshape(copy.desc, region_shape).not_nil!
+        Device.check LibPhGpu.ph_copy_strided(elem_size, copy.dev.ptr, pointerof(src_desc), dev.ptr, pointerof(dst))
       end
-      Device.check LibPhGpu.ph_copy_strided(elem_size, holder.dev.ptr, pointerof(src_desc), dev.ptr, pointerof(dst))
     end
 
     # A host source is uploaded first (explicitly visible in the signature: it is an NArray).
@@ -200,6 +206,10 @@ module Phase
 
     def /(other : T)
       launch_scalar(LibPhGpu::Op::Div, other, false, DeviceNArray(typeof(T.zero / T.zero)).new(shape_internal))
+    end
+
+    def scalar_on_left_div(scalar : T)
+      launch_scalar(LibPhGpu::Op::Div, scalar, true, DeviceNArray(typeof(T.zero / T.zero)).new(shape_internal))
     end
 
     # `Float ** Int32` is llvm.powi in Crystal: bit-exact on the device (compiler-rt's loop)
@@ -351,7 +361,7 @@ module Phase
       raise Enumerable::EmptyError.new if shape_internal[axis] == 0 && red != LibPhGpu::Red::Sum
       if result.size > 0
         if shape_internal[axis] == 0
-          result.unsafe_set_chunk(IndexRegion.cover(result.shape_internal), result.sample_zero)
+          result.zero! # the sum over no elements
         else
           a = desc
           Device.check LibPhGpu.ph_reduce_axis(red.value, Device.dtype(T), dev.ptr, pointerof(a), axis, result.dev.ptr, result.desc_ptr)
@@ -390,7 +400,7 @@ module Phase
     # ---- slices / tile ---------------------------------------------------------------------------
     def slices(axis = 0) : Array(DeviceNArray(T))
       Array(DeviceNArray(T)).new(shape_internal[axis]) do |i|
-        literal = Array(Int32 | Range(Nil, Nil)).new(shape_internal.size) { |k| k == axis ? i : (..) }
+        literal = Array(Int32 | Range(Nil, Nil)).new(shape_internal.size) { |k| k == axis ? i : Range.new(nil, nil) }
         unsafe_fetch_chunk(IndexRegion.new(literal, shape_internal))
       end
     end

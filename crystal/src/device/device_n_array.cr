@@ -1,0 +1,132 @@
+require "./device_indexable"
+
+module Phase
+  # Row-major N-D array resident in HBM: the device twin of `NArray(T)`. It includes the same
+  # mixin `NArray` includes, so every caller of `MultiIndexable` / `MultiWritable` / `View`
+  # keeps working; `DeviceIndexable` then replaces the per-element defaults with kernel launches.
+  #
+  # ```crystal
+  # a = NArray.build(8192, 8192) { |c| (c[0] ^ c[1]).to_f32 }.to_device
+  # b = DeviceNArray(Float32).fill([8192, 8192], 0.5_f32)
+  # c = (a * b + a)[0..2.., ..-1] # two elementwise kernels and one gather, nothing leaves HBM
+  # max, coord = c.argmax
+  # host = c.to_host # explicit transfer back
+  # ```
+  class DeviceNArray(T)
+    include DeviceIndexable(T) # brings MultiIndexable::Mutable(T) with it
+
+    getter dev : DeviceBuffer
+    getter desc : LibPhGpu::Desc
+    @shape : Array(Int32)
+
+    # Uninitialised storage of the given shape.
+    def initialize(shape : Enumerable(Int))
+      @shape = shape.map do |dim|
+        raise DimensionError.new("Cannot create DeviceNArray: One or more of the provided dimensions was negative.") if dim < 0
+        dim.to_i32
+      end.to_a
+      @desc = Descriptor.contiguous(@shape)
+      @dev = DeviceBuffer.new(Descriptor.element_count(@shape) * sizeof(T))
+    end
+
+    # Aliases an existing buffer (`reshape`).
+    protected def initialize(shape : Array(Int32), @dev : DeviceBuffer)
+      @shape = shape.dup
+      @desc = Descriptor.contiguous(@shape)
+    end
+
+    protected def shape_internal : Array(Int32)
+      @shape
+    end
+
+    # Picked up by `MultiIndexable#map_with` through `responds_to?`; a host Slice is uploaded.
+    def self.of_buffer(shape : Array(Int32), buffer : Slice(T)) : self
+      from_host(NArray.of_buffer(shape, buffer))
+    end
+
+    # `NArray#to_device`: the explicit host -> device transfer.
+    def self.from_host(src : NArray(T)) : self
+      result = new(src.shape)
+      if result.size > 0
+        Device.check LibPhGpu.ph_h2d(result.dev.ptr, src.buffer.to_unsafe.as(Void*), LibC::SizeT.new(src.buffer.bytesize))
+        Device.sync # the GC may free `src` as soon as we return
+      end
+      result
+    end
+
+    def self.fill(shape : Enumerable(Int), value : T) : self
+      result = new(shape)
+      result.fill!(value)
+      result
+    end
+
+    def self.build(*args, **opts, &block)
+      raise DeviceBlockError.new("build")
+    end
+
+    def fill!(value : T) : self
+      if size > 0
+        d = @desc
+        Device.check LibPhGpu.ph_fill_region(sizeof(T).to_i32, @dev.ptr, pointerof(d), pointerof(value).as(Void*))
+      end
+      self
+    end
+
+    def zero! : self
+      fill!(T.zero)
+    end
+
+    # Deep copy, like `NArray#clone`.
+    def clone : self
+      result = DeviceNArray(T).new(@shape)
+      Device.check LibPhGpu.ph_d2d(result.dev.ptr, @dev.ptr, LibC::SizeT.new(size * sizeof(T))) if size > 0
+      result
+    end
+
+    def dup : self
+      clone
+    end
+
+    # Like `NArray#reshape`, the result shares this array's buffer.
+    def reshape(new_shape : Enumerable(Int)) : self
+      new_shape = new_shape.map(&.to_i32).to_a
+      if Descriptor.element_count(new_shape) != size
+        raise ShapeError.new("Cannot change shape from #{@shape.join('x')} (#{size} elements) to #{new_shape.join('x')} (#{Descriptor.element_count(new_shape)} elements) because reshape cannot add or remove elements.")
+      end
+      DeviceNArray(T).new(new_shape, @dev)
+    end
+
+    def reshape(*new_shape : Int) : self
+      reshape(new_shape)
+    end
+
+    def flatten : self
+      reshape([size.to_i32])
+    end
+
+    # Copying transforms = view + `to_narr`, as in `MultiIndexable#permute / #reverse`.
+    def permute(order : Enumerable? = nil) : DeviceNArray(T)
+      view.permute(order).to_narr
+    end
+
+    def permute(*order : Int) : DeviceNArray(T)
+      permute(order)
+    end
+
+    def reverse : DeviceNArray(T)
+      view.reverse.to_narr
+    end
+
+    # Releases the HBM now instead of at the next GC cycle.
+    def free : Nil
+      @dev.free
+    end
+  end
+
+  class NArray(T)
+    # The explicit host -> device transfer.
+    def to_device : DeviceNArray(T)
+      DeviceNArray(T).from_host(self)
+    end
+  end
+end
