@@ -219,6 +219,27 @@ class MultiIndexable {
   T* data() const { return static_cast<T*>(buf_->ptr); }
   const std::shared_ptr<DeviceBuffer>& buffer_owner() const { return buf_; }
 
+  // ---- small host-side queries (multi_indexable.cr:100-237) ------------------------------------
+  bool empty() const { return size() == 0; }                  // empty? :107-109
+  bool scalar() const { return size() == 1; }                 // scalar? :119-121
+  T first() const {                                           // :176-182
+    if (size() == 0) throw ShapeError("This MultiIndexable has zero elements (shape: " + shape_str(shape_) + ").");
+    return get(Coord(shape_.size(), 0));
+  }
+  T last() const {                                            // :197-203
+    if (size() == 0) throw ShapeError("This MultiIndexable has zero elements (shape: " + shape_str(shape_) + ").");
+    Coord c(shape_);
+    for (int64_t& x : c) x -= 1;
+    return get(c);
+  }
+  T to_scalar() const {                                       // :131-137
+    if (!scalar())
+      throw ShapeError("Only single-element MultiIndexables can be converted to scalars, but this one has " + std::to_string(size()) +
+                       " elements (shape: " + shape_str(shape_) + ").");
+    return first();
+  }
+  double to_f() const { return (double)to_scalar(); }         // :160-162
+
   // ---- blocks: out of scope on the device path, and they say so ---------------------------
   template <class... A> [[noreturn]] void map(A&&...) const { no_blocks("map"); }
   template <class... A> [[noreturn]] void map_with(A&&...) const { no_blocks("map_with"); }

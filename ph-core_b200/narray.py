@@ -162,6 +162,51 @@ class _Indexable:
     def dimensions(self) -> int:
         return len(self.shape)
 
+    # ---- small host-side queries (src/multi_indexable.cr:100-237) -----------------------
+    def empty(self) -> bool:
+        """MultiIndexable#empty? (:107-109)."""
+        return self.size == 0
+
+    def scalar(self) -> bool:
+        """MultiIndexable#scalar? (:119-121): exactly one element, in any number of dimensions."""
+        return self.size == 1
+
+    def to_scalar(self):
+        """MultiIndexable#to_scalar (:131-137): the sole element, ShapeError otherwise.  This is how a
+        fully indexed chunk (`state[1]`, a 1-element array) becomes a number in the reference."""
+        if not self.scalar():
+            raise ShapeError(f"Only single-element MultiIndexables can be converted to scalars, but this one has "
+                             f"{self.size} elements (shape: {self.shape}).")
+        return self.first()
+
+    def to_scalar_or_none(self):
+        """MultiIndexable#to_scalar? (:145-148)."""
+        return self.first() if self.scalar() else None
+
+    def to_f(self) -> float:
+        """MultiIndexable#to_f (:160-162)."""
+        return float(self.to_scalar())
+
+    def first(self):
+        """MultiIndexable#first (:176-182): the element at the zero coordinate."""
+        if self.size == 0:
+            raise ShapeError(f"This MultiIndexable has zero elements (shape: {self.shape}).")
+        return self.get([0] * len(self.shape))
+
+    def last(self):
+        """MultiIndexable#last (:197-203): the element at the largest coordinate."""
+        if self.size == 0:
+            raise ShapeError(f"This MultiIndexable has zero elements (shape: {self.shape}).")
+        return self.get([s - 1 for s in self.shape])
+
+    def sample(self, random=None):
+        """MultiIndexable#sample (:234-237): one element at a random coordinate (one tiny D2H)."""
+        import random as _random
+        if self.size == 0:
+            raise ShapeError(f"Can't sample empty collection. (shape: {self.shape})")
+        r = random or _random
+        return self.get([r.randrange(s) for s in self.shape])
+
     # ---- blocks are out of scope on the device path --------------------------------
     def _no_blocks(self, *a, **k):
         raise DeviceBlockError("arbitrary blocks cannot run on the device path")

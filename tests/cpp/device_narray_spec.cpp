@@ -329,6 +329,25 @@ int main(int argc, char** argv) {
     for (double x : fin) sum += x;
     EXPECT(std::fabs(sum - 480.0) < 1e-9);                                   // zero-flux ends conserve heat
     EXPECT(std::fabs(fin[0] - 14.381532) < 1e-6 && std::fabs(fin[20] - 42.473872) < 1e-6);
+    // update_temp written literally with the reference's operators (heat_equation.cr:38-51): one-element
+    // chunks, array-valued []=, scalar on the left -- bit-identical to the fused example kernel
+    {
+      auto st = state.clone();
+      for (int step = 0; step < 2; step++) {
+        auto temp_diff = DeviceNArray<double>::fill(st.shape(), 0.0);
+        temp_diff.set_chunk({0}, (st[{1}] - st[{0}]) * COEFF);
+        temp_diff.set_chunk({-1}, (st[{-2}] - st[{-1}]) * COEFF);
+        auto centre = st[{range_ex(1, -1)}];
+        for (int64_t idx = 0; idx < centre.shape()[0]; idx++) {
+          double center_temp = centre[{idx}].to_scalar();
+          temp_diff.set_chunk({idx + 1}, (st[{idx}] - 2 * center_temp + st[{idx + 2}]) * COEFF);
+        }
+        st = st + temp_diff;
+      }
+      EXPECT(st == Heat::simulate(state, COEFF, 2, PH_HEAT_EXAMPLE1D));
+      EXPECT(st[{3}].scalar() && !st.scalar() && !st.empty() && st.last() == 100.0 + (st.last() - 100.0));
+      EXPECT_RAISES(ShapeError, st.to_scalar());
+    }
     // one fused step == the slice-arithmetic form written with the reference's operators (N-D rule, 2-D)
     const int64_t H = 37, W = 53;
     V<float> init((size_t)(H * W));

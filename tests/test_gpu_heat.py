@@ -256,3 +256,34 @@ def test_sharded_run_single_rank_two_ghost_layout():
         a, b = D.from_host(loc), D.from_host(loc)
         got = S.heat_run_sharded(a, b, 0.1, steps, ghost=2).to_host()[2:-2]
         assert_bits(got, want, f"1-rank sharded run, 2 ghost planes, {steps} steps")
+
+
+def test_example_update_temp_written_with_the_reference_operators():
+    """examples/heat_equation.cr:38-51 replayed LITERALLY on device arrays: one-element chunks
+    (`state[1] - state[0]`), array-valued `[]=`, `2 * center_temp` with the scalar on the left,
+    `to_scalar` on fully indexed chunks.  Every operator is its own launch; the result must be
+    bit-identical to the oracle's restatement and to the fused PH_HEAT_EXAMPLE1D kernel."""
+    from ph_core_b200.region import rng
+    coeff = O.heat_example_coeff()
+    host = np.full(21, 20.0)
+    host[0], host[-1] = 0.0, 100.0
+    state = D.from_host(host)
+    want = host.copy()
+    for _ in range(3):
+        temp_diff = D.fill(state.shape, 0.0, np.float64)                       # :39
+        temp_diff[0] = (state[1] - state[0]) * coeff                           # :43
+        temp_diff[-1] = (state[-2] - state[-1]) * coeff                        # :44
+        centre = state[rng(1, -1, exclusive=True)]                              # :46
+        assert centre.shape == [19]
+        for idx in range(centre.shape[0]):
+            center_temp = centre[idx].to_scalar()                               # each_with_index yields elements
+            temp_diff[idx + 1] = (state[idx] - 2 * center_temp + state[idx + 2]) * coeff   # :47
+        state = state + temp_diff                                               # :50 (map_with_coord { el + temp_diff.get(idx) })
+        want = O.heat_step_1d_example(want, coeff)
+        assert_bits(state.to_host(), want, "literal update_temp")
+    assert_bits(heat.simulate(D.from_host(host), coeff, 3, heat.EXAMPLE1D).to_host(), want, "fused example kernel")
+    assert state[0].scalar() and not state.scalar() and not state.empty()
+    assert state.first() == want[0] and state.last() == want[-1] and state[3].to_f() == float(want[3])
+    with pytest.raises(ph.ShapeError):
+        state.to_scalar()
+    assert state.to_scalar_or_none() is None and state.sample() in want
