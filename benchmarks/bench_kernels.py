@@ -62,10 +62,10 @@ def timeit(fn, reps=None, warm=None, inner=None):
     return min(ts), statistics.median(ts)
 
 
-def row(name, nbytes, fn, unit_count=None, unit=None, reps=None, note=""):
+def row(name, nbytes, fn, unit_count=None, unit=None, reps=None, note="", inner=None):
     if args.only and args.only not in name:
         return
-    best, med = timeit(fn, reps)
+    best, med = timeit(fn, reps, inner=inner)
     r = {"kernel": name, "bytes": int(nbytes), "ms_best": round(best, 5), "ms_median": round(med, 5),
          "gbs": round(nbytes / (med * 1e-3) / 1e9, 1), "frac_measured": round(nbytes / (med * 1e-3) / 1e9 / peak, 4),
          "frac_nominal_8000": round(nbytes / (med * 1e-3) / 1e9 / 8000, 4)}
@@ -136,6 +136,28 @@ row("mask store array f32", NE + 3 * NE * 4,
 ai = dev_rand(E, np.int32, 4); ci = dev_rand(E, np.int32, 5); oi = D(E, np.int32)
 row("ewise a+c i32 overflow-checked", 3 * NE * 4,
     lambda: ph.check(lib.ph_ewise_binary(ph.K["PH_ADD"], ph.K["PH_I32"], ai.ptr, C.byref(da), ci.ptr, C.byref(dc), oi.ptr, C.byref(do))))
+# ---- SURVEY.md 8(f) "next" rows on the same arrays: tile (f-2) and fill
+row("fill 8192^2 f32 (NArray.fill)", NE * 4,
+    lambda: ph.check(lib.ph_fill_region(4, out.ptr, C.byref(do), s2.ctypes.data)), note="write-only stream")
+def tile_descs(srcarr, counts):
+    """The rank-2N stride-0 source descriptor of MultiIndexable#tile and the contiguous destination."""
+    d = srcarr.desc()
+    ext, strd = [], []
+    for i, cnt in enumerate(counts):
+        ext += [int(cnt), int(d.extent[i])]
+        strd += [0, int(d.stride[i])]
+    return ph.PhDesc.make(ext, strd, d.offset), ph.PhDesc.contiguous(ext)
+ts, td = tile_descs(b, [E[0], 1])
+row("tile [1,8192] x [8192,1] f32 (broadcast oracle)", NE * 4 + E[1] * 4,
+    lambda: ph.check(lib.ph_copy_strided(4, b.ptr, C.byref(ts), out.ptr, C.byref(td))),
+    note="f-2: rank-4 stride-0 descriptor, no modulo on the device")
+row("tile [1,8192] x [8192,1] f32 through the Python mirror", NE * 4 + E[1] * 4, lambda: b.tile([E[0], 1]),
+    note="same kernel + result allocation + ~10 ctypes calls per launch: host-bound")
+quarter = a[rng(0, E[0] // 2, exclusive=True), rng(0, E[1] // 2, exclusive=True)]
+qs, qd = tile_descs(quarter, [2, 2])
+row("tile [4096,4096] x [2,2] f32", NE * 4 + NE, lambda: ph.check(lib.ph_copy_strided(4, quarter.ptr, C.byref(qs), out.ptr, C.byref(qd))),
+    note="f-2: every source element read 4 times (3 of them from L2)")
+del quarter
 del a, c, out, mask, ai, ci, oi
 
 # ------------------------------------------------------------------ config 2: strided views 16384^2 f64
@@ -151,7 +173,46 @@ dst = D([S, S], np.float64)
 row("transposed scatter mutable_view.permute[..]=src f64", 2 * NS * 8,
     lambda: dst.mutable_view().permute().set_chunk([], src))
 row("clone (contiguous copy) f64", 2 * NS * 8, lambda: src.clone())
-del src, dst
+del dst
+# ---- f-2: each_slice on a rank-3 view of the same buffer (one gather launch per slice)
+cube = D([64, S // 64 * S // 1024, 1024], np.float64, src._buf) if S % 64 == 0 else None
+if cube is not None:
+    ncube = cube.size
+    sl_out = D([cube.shape[1], 1024], np.float64)
+    cd = cube.desc()
+    def slice_descs(axis, idx):
+        ext = [int(cd.extent[i]) for i in range(3) if i != axis]
+        strd = [int(cd.stride[i]) for i in range(3) if i != axis]
+        return ph.PhDesc.make(ext, strd, idx * int(cd.stride[axis])), ph.PhDesc.contiguous(ext)
+    s0 = [slice_descs(0, i) for i in range(64)]
+    def run_slices(descs):
+        for sd, dd in descs:
+            ph.check(lib.ph_copy_strided(8, cube.ptr, C.byref(sd), sl_out.ptr, C.byref(dd)))
+    row("each_slice(axis=0) of [64,%d,1024] f64 (64 contiguous gathers)" % cube.shape[1], 2 * ncube * 8,
+        lambda: run_slices(s0), reps=5, inner=1, note="f-2: 64 launches of 32 MiB each, descriptors prebuilt")
+    step1 = max(1, cube.shape[1] // 64)
+    s1 = [slice_descs(1, j) for j in range(0, cube.shape[1], step1)][:64]
+    row("each_slice(axis=1)[::%d] of the same f64 (strided gathers)" % step1, 2 * 64 * 64 * 1024 * 8,
+        lambda: run_slices(s1), reps=5, inner=1, note="f-2: 64 slices of [64,1024] (1 KiB rows, 32 MiB apart), 512 KiB per launch: launch-bound")
+    row("slices(axis=0) through the Python mirror", 2 * ncube * 8, lambda: cube.slices(0), reps=5, inner=1,
+        note="same kernels + region parse, descriptor compile and allocation per slice in Python: host-bound")
+    del sl_out
+# ---- f-4: binary dump / load of a device array (host file system either side of the path)
+import tempfile, time as _time
+from ph_core_b200 import io as phio
+if not args.only or "dump" in args.only:
+    part = D([(1 << 23) if args.quick else (1 << 26)], np.float64, src._buf)      # 64 MiB quick / 512 MiB
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "a.phbin")
+        t0 = _time.perf_counter(); phio.dump(part, path); t1 = _time.perf_counter()
+        back = phio.load(path); ph.check(lib.ph_sync()); t2 = _time.perf_counter()
+        ok = bool(back.equals(part))
+    nb = part.size * 8
+    print(json.dumps({"kernel": "io dump / load binary f64 (%d MiB, tmpfs or local disk)" % (nb >> 20), "bytes": nb,
+                      "dump_gbs": round(nb / (t1 - t0) / 1e9, 2), "load_gbs": round(nb / (t2 - t1) / 1e9, 2),
+                      "round_trip_bit_exact": ok, "note": "f-4: wall clock incl. D2H / H2D and file I/O; host-bound"}), flush=True)
+    del part, back
+del src
 
 # ------------------------------------------------------------------ config 3: reductions 1e9 f32
 R = (1000, 1000, 1000) if not args.quick else (250, 1000, 1000)

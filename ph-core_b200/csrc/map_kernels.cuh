@@ -34,6 +34,9 @@ struct MapArgs {
   uint32_t period;          // flat: OPND_PERIODIC operands repeat every `period` elements (0 = none)
   int reverse;              // flat: visit the tiles from the last to the first (see launch_flat)
   int64_t gx;               // rows: number of column tiles (1-D grid = gx * slabs * chunks)
+  uint32_t chunks;          // rows: row chunks of the last outer axis per slab
+  uint32_t slabs;           // rows: product of the leading outer extents
+  int slab_fastest;         // rows: consecutive blocks visit consecutive slabs (see launch_rows)
   int tx, tx_log2;          // rows: threads along the inner axis (power of two <= 256)
   uint32_t* flags;
   OuterAxes outer;          // rows/any: operand k uses stride[k], the output uses stride[NIN]
@@ -134,23 +137,27 @@ __global__ void __launch_bounds__(MAP_THREADS) map_rows_kernel(const MapArgs<F::
   const int tx = threadIdx.x & (a.tx - 1);
   const int ty = threadIdx.x >> a.tx_log2;
   const int TY = MAP_THREADS >> a.tx_log2;
-  const int64_t by = (int64_t)blockIdx.x / a.gx;
-  const int64_t ctile = (int64_t)blockIdx.x - by * a.gx;
-  const int64_t col = (ctile * a.tx + tx) * E;
+  // blockIdx.x < 2^31, so the whole decomposition runs in 32-bit unsigned arithmetic (a 64-bit
+  // division is ~100 instructions, and every thread of the block repeats this set-up)
+  const uint32_t gx = (uint32_t)a.gx;
+  const uint32_t by = blockIdx.x / gx;
+  const uint32_t ctile = blockIdx.x - by * gx;
+  const int64_t col = ((int64_t)ctile * a.tx + tx) * E;
   if (col >= a.n) return;                          // whole groups only: n % E == 0 by dispatch
   const int last = a.outer.n - 1;
   const int64_t rows_last = a.outer.extent[last];
-  const int64_t chunks = (rows_last + a.rows_per_block - 1) / a.rows_per_block;
-  int64_t slab = by / chunks;
-  const int64_t chunk = by - slab * chunks;
+  uint32_t slab, chunk;
+  if (a.slab_fastest) { chunk = by / a.slabs; slab = by - chunk * a.slabs; }
+  else { slab = by / a.chunks; chunk = by - slab * a.chunks; }
   uint32_t err = 0;
 
   int64_t base[NIN + 1];
 #pragma unroll
   for (int k = 0; k <= NIN; k++) base[k] = 0;
   for (int ax = last - 1; ax >= 0; ax--) {         // leading outer axes: once per block
-    const int64_t e = a.outer.extent[ax];
-    const int64_t q = slab / e;
+    const int64_t e64 = a.outer.extent[ax];
+    const uint32_t e = e64 > 0x7fffffffLL ? 0x80000000u : (uint32_t)e64;   // slab < 2^31 <= e: q = 0
+    const uint32_t q = slab / e;
     const int64_t c = slab - q * e;
     slab = q;
 #pragma unroll
@@ -175,7 +182,7 @@ __global__ void __launch_bounds__(MAP_THREADS) map_rows_kernel(const MapArgs<F::
   }
   Out* out = reinterpret_cast<Out*>(a.out) + base[NIN];
 
-  const int64_t r0 = chunk * a.rows_per_block;
+  const int64_t r0 = (int64_t)chunk * a.rows_per_block;
   const int64_t r1 = (r0 + a.rows_per_block < rows_last) ? r0 + a.rows_per_block : rows_last;
   int64_t r = r0 + ty;
   // x[u][k] of a fixed operand is written once here and never again: inside the loop
@@ -250,15 +257,29 @@ inline int32_t launch_rows(MapArgs<F::NIN>& a) {
   const int64_t gx = ceil_div(groups, (int64_t)tx);
   const int64_t rows_last = a.outer.extent[a.outer.n - 1];
   const int64_t slabs = a.rows / rows_last;
-  // enough blocks for ~8 waves, but several row-groups per thread so row-vectors amortise
+  // enough blocks for ~8 waves, but several row-groups per thread so that the per-block set-up and
+  // row-vector loads amortise: 4 unrolled batches per thread, or one when that would leave fewer
+  // than half the wanted blocks (a 256 MB output tiled [2,2]: 2048 blocks = 2.3 waves with a tail)
   const int64_t target_blocks = (int64_t)rt().sm_count * 8 * 8;
   int64_t chunks = std::max<int64_t>(1, target_blocks / std::max<int64_t>(1, gx * slabs));
-  int64_t rpb = std::max<int64_t>(ceil_div(rows_last, chunks), std::min<int64_t>(rows_last, (int64_t)UNROLL * 4 * ty));
+  int64_t rows_min = (int64_t)UNROLL * 4 * ty;
+  if (gx * slabs * ceil_div(rows_last, rows_min) < target_blocks / 2) rows_min = (int64_t)UNROLL * ty;
+  int64_t rpb = std::max<int64_t>(ceil_div(rows_last, chunks), std::min<int64_t>(rows_last, rows_min));
   chunks = ceil_div(rows_last, rpb);
   const int64_t blocks = gx * slabs * chunks;
   if (blocks > 0x7fffffffLL) return set_error(PH_ERR_INVALID, "array too large for one launch");
   a.rows_per_block = (int)std::min<int64_t>(rpb, 0x7fffffff);
   a.gx = gx;
+  a.chunks = (uint32_t)chunks;
+  a.slabs = (uint32_t)slabs;
+  // An input with stride 0 on a leading outer axis (a tile count, a broadcast plane) is re-read by
+  // every slab along that axis: let consecutive blocks walk the slabs first, so the re-reads run
+  // together and hit L2 instead of coming back to HBM once per slab.
+  a.slab_fastest = 0;
+  for (int k = 0; k < F::NIN && slabs > 1; k++)
+    if (a.mode[k] == OPND_ARRAY || a.mode[k] == OPND_BCAST)
+      for (int ax = 0; ax + 1 < a.outer.n; ax++)
+        if (a.outer.extent[ax] > 1 && a.outer.stride[k][ax] == 0) a.slab_fastest = 1;
   map_rows_kernel<F, E, UNROLL><<<(unsigned)blocks, MAP_THREADS, 0, rt().stream>>>(a);
   PH_LAUNCH_CHECK("map_rows_kernel");
   return PH_OK;
@@ -391,10 +412,25 @@ int32_t launch_map(const MapOperand* ops, void* out, const ph_desc* out_desc) {
     a.outer.extent[0] = 1;
     for (int k = 0; k <= NIN; k++) a.outer.stride[k][0] = 0;
   }
+  // A block walks rows of the LAST outer axis only (the leading ones are decomposed once per
+  // block).  The visiting order of an elementwise map is free, so when that axis is short --
+  // `tile` makes axes of extent 2, a [N, 3, C] slice has one of 3 -- the longest outer axis
+  // takes its place: otherwise every thread would pay the per-block set-up (two 64-bit
+  // divisions per leading axis) for one or two 32-byte groups (tile [4096,4096] x [2,2]:
+  // 197 instructions per thread, 0.52 of the copy peak).
+  int order[PH_MAX_RANK];
+  for (int ax = 0; ax < inner; ax++) order[ax] = ax;
+  if (inner >= 2 && p.extent[inner - 1] < 64) {
+    int longest = inner - 1;
+    for (int ax = 0; ax < inner - 1; ax++) if (p.extent[ax] > p.extent[longest]) longest = ax;
+    order[longest] = inner - 1;
+    order[inner - 1] = longest;
+  }
   for (int ax = 0; ax < inner; ax++) {
-    a.outer.extent[ax] = p.extent[ax];
-    for (int k = 0; k < NIN; k++) a.outer.stride[k][ax] = (a.mode[k] == OPND_PARAM) ? 0 : in_stride(k, ax);
-    a.outer.stride[NIN][ax] = p.stride[out_slot][ax];
+    const int from = order[ax];
+    a.outer.extent[ax] = p.extent[from];
+    for (int k = 0; k < NIN; k++) a.outer.stride[k][ax] = (a.mode[k] == OPND_PARAM) ? 0 : in_stride(k, from);
+    a.outer.stride[NIN][ax] = p.stride[out_slot][from];
   }
   a.n = p.extent[inner];
   a.rows = p.total / a.n;

@@ -70,7 +70,8 @@ def dump(arr: DeviceNArray, path: str) -> None:
     with open(path, "wb") as f:
         f.write(_MAGIC)
         f.write(header)
-        f.write(host.tobytes())
+        if host.size:
+            f.write(memoryview(np.ascontiguousarray(host)).cast("B"))  # no second host copy
 
 
 def load(path: str) -> DeviceNArray:
@@ -80,7 +81,7 @@ def load(path: str) -> DeviceNArray:
         header = json.loads(f.readline())
         dtype = np.dtype(header["dtype"])
         shape: Sequence[int] = header["shape"]
-        data = np.frombuffer(f.read(), dtype=dtype)
+        data = np.fromfile(f, dtype=dtype)                              # straight into the array's own buffer
     size = int(np.prod(shape, dtype=np.int64)) if len(shape) else 0
     if data.size != size:
         raise ShapeError(f"binary dump holds {data.size} elements, the header's shape {shape} needs {size}")

@@ -274,3 +274,33 @@ def test_get_available_and_optional_chunk():
         want = O.fetch_chunk(big, O.IndexRegion.new_trimmed(lit, list(big.shape), bound_shape=list(big.shape)))
         assert_bits(db.get_available(lit).to_host(), want, f"get_available {lit}")
     assert_bits(db.match(5.0).to_host(), big == 5.0, "=~")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.uint8])
+def test_short_last_outer_axis_is_reordered(dtype):
+    """Plans whose last outer axis is short (tile counts of 2, a [N, 3, C] slice) walk their LONGEST
+    outer axis inside a block instead (map_kernels.cuh); results cannot depend on that choice."""
+    rs = np.random.RandomState(12)
+    src = (rs.rand(300, 264) * 200).astype(dtype)
+    for counts in ([2, 2], [3, 1], [1, 5], [2, 3]):
+        assert_bits(D.from_host(src).tile(counts).to_host(), np.tile(src, counts), f"tile {counts}")
+    cube = (rs.rand(70, 3, 520) * 200).astype(dtype)
+    d = D.from_host(cube)
+    # a strided rank-3 operand (axes cannot merge) with a last outer axis of extent 3, elementwise and gathered
+    sub = d[rng(None, None), rng(None, None), rng(0, 511)]
+    assert_bits(sub.to_host(), cube[:, :, :512], "gather [70,3,512]")
+    v = d.view(rng(None, None), rng(None, None), rng(0, 511))
+    if np.dtype(dtype).kind == "f":
+        want, _ = O.ewise("*", cube[:, :, :512].copy(), cube[:, :, 8:].copy())
+        got = v * d.view(rng(None, None), rng(None, None), rng(8, None))
+        assert_bits(got.to_host(), want, "strided * strided, outer [70,3]")
+    # scatter into a region whose last outer axis has extent 2
+    dst = D.fill([40, 2, 300], 0, dtype)
+    dst[rng(None, None), rng(None, None), rng(4, 259)] = D.from_host(np.ascontiguousarray(cube[:40, :2, :256]))
+    want = np.zeros((40, 2, 300), dtype); want[:, :, 4:260] = cube[:40, :2, :256]
+    assert_bits(dst.to_host(), want, "scatter [40,2,256]")
+    # row-vector operand with a short last outer axis: the ROWVEC detection is order-independent
+    if np.dtype(dtype).kind == "f":
+        rowv = D.from_host(cube[:1, :1, :512].copy())
+        want, _ = O.ewise_broadcast("+", cube[:, :, :512].copy(), cube[:1, :1, :512].copy())
+        assert_bits(v.broadcast_op("+", rowv).to_host(), want, "rowvec + strided")
