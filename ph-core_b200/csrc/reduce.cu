@@ -385,13 +385,13 @@ __global__ void __launch_bounds__(RED_THREADS) ext_partial_kernel(const T* __res
 
 // ---------------------------------------------------------------- per-axis: [outer, K, inner]
 // inner > 1: threads run along `inner` (coalesced), each folds its column over k = 0..K-1 in order.
-template <typename T, int E, int RED>
+// UNROLL groups are in flight per thread; the block size is the launch's (64..256).
+template <typename T, int E, int RED, int UNROLL>
 __global__ void __launch_bounds__(RED_THREADS) axis_strip_kernel(const T* __restrict__ x, void* __restrict__ out,
                                                                  int64_t outer, int64_t K, int64_t inner,
                                                                  uint32_t* __restrict__ flags) {
-  constexpr int UNROLL = 4;
   const int64_t groups = inner / E;                         // inner % E == 0 by dispatch
-  const int64_t gid = (int64_t)blockIdx.x * RED_THREADS + threadIdx.x;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= outer * groups) return;
   const int64_t o = gid / groups;
   const int64_t c = (gid - o * groups) * E;
@@ -822,17 +822,47 @@ static int32_t reduce_axis_launch(const T* x, void* out, int64_t outer, int64_t 
     const uintptr_t xa = (uintptr_t)x, oa = (uintptr_t)out;
     const bool can32 = inner % E32 == 0 && xa % 32 == 0 && (ARG || oa % 32 == 0);
     const bool can16 = inner % E16 == 0 && xa % 16 == 0 && (ARG || oa % 16 == 0);
-    // widest group that still leaves >= 512 threads per SM in flight
-    const int64_t want_threads = (int64_t)r.sm_count * 512;
-    int e = 1;
-    if (can32 && E32 > 1 && outer * (inner / E32) >= want_threads) e = E32;
-    else if (can16 && E16 > 1 && outer * (inner / E16) >= want_threads) e = E16;
-    const int64_t threads = outer * (inner / e);
-    const int64_t blocks = ceil_div(threads, RED_THREADS);
+    // Plan = (group width E, groups in flight per thread U, block size), measured on the axis-0
+    // shards of the 1e9-element f32 array ([1000/N, 1000, 1000], benchmarks/probe_axis.py):
+    //   * outer == 1 (the reduced axis is the leading one; consecutive k are `inner` apart): the widest
+    //     group with 4 in flight streams at 6.4-7.1 TB/s down to [125, 1000, 1000];
+    //   * outer > 1 (a middle axis: every `outer` index is its own K x inner panel): with many columns the
+    //     widest group wins, 8 in flight in 128-thread blocks (6.8 TB/s, argmax 6.5 -> 6.75); with few
+    //     columns only MORE THREADS keep the memory system busy -- 32-byte groups leave 15 625 threads on
+    //     [125, 1000, 1000] and reach 2.1 TB/s however deep the unrolling, scalar columns 5.4 TB/s.
+    const int64_t cols = outer * inner;
+    const int64_t col_bytes = cols * (int64_t)sizeof(T);
+    int e = 1, u = 4, block = RED_THREADS;
+    if (outer == 1) {
+      if (can32 && E32 > 1 && cols / E32 >= (int64_t)r.sm_count * 64) e = E32;
+      else if (can16 && E16 > 1 && cols / E16 >= (int64_t)r.sm_count * 64) e = E16;
+      u = col_bytes * 4 >= (6LL << 20) ? 4 : 16;
+    } else if (col_bytes >= (3LL << 20) && can32 && E32 > 1) {
+      e = E32; u = 8; block = 128;
+    } else if (col_bytes >= (3LL << 19) && can32 && E32 > 1) {
+      e = E32; u = 4;
+    } else if (ARG && col_bytes >= (3LL << 18) && can16 && E16 > 1) {
+      e = E16; u = 8;
+    } else {
+      e = 1; u = (!ARG && col_bytes >= (3LL << 18)) ? 4 : 16;
+    }
+    static const int force_e = getenv("PH_AXIS_E") ? atoi(getenv("PH_AXIS_E")) : 0;       // tuning knobs
+    static const int force_u = getenv("PH_AXIS_U") ? atoi(getenv("PH_AXIS_U")) : 0;
+    static const int force_b = getenv("PH_AXIS_BLOCK") ? atoi(getenv("PH_AXIS_BLOCK")) : 0;
+    if (force_e == 32 && can32 && E32 > 1) e = E32;
+    else if (force_e == 16 && can16 && E16 > 1) e = E16;
+    else if (force_e == 1) e = 1;
+    if (force_u) u = force_u;
+    if (sizeof(T) < 4 && u > 8) u = 8;                       // 32 one-byte accumulators + 16 groups would spill
+    const int64_t threads = cols / e;
+    if (force_b) block = force_b;
+    const int64_t blocks = ceil_div(threads, (int64_t)block);
     if (blocks > 0x7fffffffLL) return set_error(PH_ERR_INVALID, "array too large for one launch");
-    if (e == E32 && E32 > 1) axis_strip_kernel<T, E32, RED><<<(unsigned)blocks, RED_THREADS, 0, r.stream>>>(x, out, outer, K, inner, r.d_flags);
-    else if (e == E16 && E16 > 1) axis_strip_kernel<T, E16, RED><<<(unsigned)blocks, RED_THREADS, 0, r.stream>>>(x, out, outer, K, inner, r.d_flags);
-    else axis_strip_kernel<T, 1, RED><<<(unsigned)blocks, RED_THREADS, 0, r.stream>>>(x, out, outer, K, inner, r.d_flags);
+#define PH_STRIP(EE, UU) axis_strip_kernel<T, EE, RED, UU><<<(unsigned)blocks, block, 0, r.stream>>>(x, out, outer, K, inner, r.d_flags)
+    if (e == E32 && E32 > 1) { if (u >= 16) PH_STRIP(E32, 16); else if (u >= 8) PH_STRIP(E32, 8); else PH_STRIP(E32, 4); }
+    else if (e == E16 && E16 > 1) { if (u >= 8) PH_STRIP(E16, 8); else PH_STRIP(E16, 4); }
+    else { if (u >= 16) PH_STRIP(1, 16); else PH_STRIP(1, 4); }
+#undef PH_STRIP
     PH_LAUNCH_CHECK("axis_strip_kernel");
     return PH_OK;
   }
