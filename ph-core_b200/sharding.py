@@ -140,33 +140,22 @@ def reduce_full_sharded(local, name: str, row_offset_elems: int = 0):
         check(lib.ph_d2h(out.ctypes.data, res.ptr, dt.itemsize))
         DeviceNArray.raise_pending()
         return out[0]
+    # one 32-byte record per rank: value @0, local flat index @16, elements owned by lower ranks @24
+    # (the offset rides in the same allgather: no second collective, one D2H)
+    off = np.array([int(row_offset_elems)], dtype=np.int64)
+    check(lib.ph_h2d(res.ptr + 24, off.ctypes.data, 8))      # pageable source: staged before the call returns
     gathered = _Buffer(32 * world)
     check(lib.ph_allgather(res.ptr, gathered.ptr, 32))
     raw = np.zeros(32 * world, dtype=np.uint8)
     check(lib.ph_d2h(raw.ctypes.data, gathered.ptr, raw.nbytes))
     DeviceNArray.raise_pending()
     vals, idxs = [], []
-    offs = _allgather_host_int(row_offset_elems)
     for r in range(world):
         chunk = raw[32 * r: 32 * (r + 1)]
         vals.append(chunk[:dt.itemsize].view(dt)[0])
         i = int(chunk[16:24].view(np.int64)[0])
-        idxs.append(i + offs[r] if i >= 0 else -1)
+        idxs.append(i + int(chunk[24:32].view(np.int64)[0]) if i >= 0 else -1)
     return combine_extremum(vals, idxs, is_max=(name == "argmax"))
-
-
-def _allgather_host_int(v: int) -> List[int]:
-    world, rank = world_rank()
-    if world == 1:
-        return [int(v)]
-    import torch
-    import torch.distributed as dist
-    t = torch.tensor([int(v)], dtype=torch.int64)
-    if dist.get_backend() == "nccl":
-        t = t.cuda()
-    outs = [torch.zeros_like(t) for _ in range(world)]
-    dist.all_gather(outs, t)
-    return [int(o.item()) for o in outs]
 
 
 def heat_run_sharded(slab, other, coeff, steps: int, ghost: int = 1):
@@ -300,6 +289,19 @@ class ShardedNArray:
         for q in range(self.world):
             k0, k1 = plan["send"][q]
             n_send = int(np.prod(plan["send_shape"][q], dtype=np.int64))
+            if q == self.rank:
+                # my own block never leaves the GPU: one permuting copy straight into the result
+                # (a transposed view scattered into a region) instead of gather + self-send + scatter
+                if n_send:
+                    lit = [ALL] * nd
+                    lit[k] = rng(k0, k1 - 1)
+                    p0, p1 = plan["recv"][q]
+                    dst = [ALL] * nd
+                    dst[j] = rng(p0, p1 - 1)
+                    out.set_chunk(dst, self.local.view(*lit).permute(*pat))
+                sends.append(None)
+                recvs.append(None)
+                continue
             if n_send:
                 lit = [ALL] * nd
                 lit[k] = rng(k0, k1 - 1)
