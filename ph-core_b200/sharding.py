@@ -95,6 +95,33 @@ def combine_extremum(values: Sequence, indices: Sequence[int], is_max: bool = Tr
 _comm = {"world": 1, "rank": 0, "ready": False}
 
 
+EXTREMUM_RECORD_BYTES = 32
+
+
+def pack_extremum_record(value, local_index: int, row_offset_elems: int, dtype) -> np.ndarray:
+    """Host twin of the 32-byte record a rank contributes to the argmax / argmin allgather:
+    value @0 (<= 8 bytes), local flat index @16 (int64, -1 = empty shard), elements owned by lower
+    ranks @24 (int64).  The device fills @0 and @16 (ph_reduce_full_dev), the host @24."""
+    rec = np.zeros(EXTREMUM_RECORD_BYTES, dtype=np.uint8)
+    dt = np.dtype(dtype)
+    rec[:dt.itemsize] = np.array([value], dtype=dt).view(np.uint8)
+    rec[16:24] = np.array([local_index], dtype=np.int64).view(np.uint8)
+    rec[24:32] = np.array([row_offset_elems], dtype=np.int64).view(np.uint8)
+    return rec
+
+
+def parse_extremum_records(raw: np.ndarray, dtype, world: int):
+    """The gathered records -> (values, GLOBAL flat indices) per rank; an empty shard keeps -1."""
+    dt = np.dtype(dtype)
+    vals, idxs = [], []
+    for r in range(world):
+        chunk = raw[EXTREMUM_RECORD_BYTES * r: EXTREMUM_RECORD_BYTES * (r + 1)]
+        vals.append(chunk[:dt.itemsize].view(dt)[0])
+        i = int(chunk[16:24].view(np.int64)[0])
+        idxs.append(i + int(chunk[24:32].view(np.int64)[0]) if i >= 0 else -1)
+    return vals, idxs
+
+
 def comm_init(dist=None) -> Tuple[int, int]:
     """Create libphgpu's communicator: rank 0 makes the NCCL unique id, `torch.distributed`
     (any backend) only carries those 128 bytes to the other ranks."""
@@ -149,12 +176,7 @@ def reduce_full_sharded(local, name: str, row_offset_elems: int = 0):
     raw = np.zeros(32 * world, dtype=np.uint8)
     check(lib.ph_d2h(raw.ctypes.data, gathered.ptr, raw.nbytes))
     DeviceNArray.raise_pending()
-    vals, idxs = [], []
-    for r in range(world):
-        chunk = raw[32 * r: 32 * (r + 1)]
-        vals.append(chunk[:dt.itemsize].view(dt)[0])
-        i = int(chunk[16:24].view(np.int64)[0])
-        idxs.append(i + int(chunk[24:32].view(np.int64)[0]) if i >= 0 else -1)
+    vals, idxs = parse_extremum_records(raw, dt, world)
     return combine_extremum(vals, idxs, is_max=(name == "argmax"))
 
 

@@ -126,9 +126,12 @@ def _worker(rank, world, port, out_dir):
     part = torch.tensor([float(local.sum(dtype=np.float64))], dtype=torch.float64)
     dist.all_reduce(part)
     v, i = O.reduce_argmax(local)
-    pairs = [None] * world
-    dist.all_gather_object(pairs, (float(v), int(i + a * data.shape[1])))
-    best = S.combine_extremum([p[0] for p in pairs], [p[1] for p in pairs], True)
+    # the same 32-byte record the GPU path allgathers (value @0, LOCAL index @16, row offset @24)
+    rec = torch.from_numpy(S.pack_extremum_record(v, int(i), a * data.shape[1], np.float32))
+    recs = [torch.zeros_like(rec) for _ in range(world)]
+    dist.all_gather(recs, rec)
+    vals, idxs = S.parse_extremum_records(np.concatenate([r.numpy() for r in recs]), np.float32, world)
+    best = S.combine_extremum(vals, idxs, True)
     axis0 = torch.from_numpy(O.reduce_axis(local, 0, "sum").astype(np.float64))
     dist.all_reduce(axis0)
     np.save(os.path.join(out_dir, f"red_{rank}.npy"), np.array([part.item(), best[0], best[1]] + axis0.tolist()))
@@ -178,6 +181,11 @@ def test_shard_ranges_cover_exactly():
     assert S.combine_extremum([3.0, 9.0, 9.0], [5, 40, 12], True) == (9.0, 12)
     assert S.combine_extremum([3.0, 1.0, 1.0], [5, 40, 12], False) == (1.0, 12)
     assert S.combine_extremum([3.0, 0.0], [5, -1], True) == (3.0, 5)    # empty shard ignored
+    raw = np.concatenate([S.pack_extremum_record(7, 11, 0, np.int64), S.pack_extremum_record(0, -1, 40, np.int64),
+                          S.pack_extremum_record(7, 2, 40, np.int64)])
+    vals, idxs = S.parse_extremum_records(raw, np.int64, 3)
+    assert [int(v) for v in vals] == [7, 0, 7] and idxs == [11, -1, 42]
+    assert S.combine_extremum(vals, idxs, True) == (7, 11)
 
 
 def test_transpose_plan_covers_every_element_once():
