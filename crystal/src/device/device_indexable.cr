@@ -93,7 +93,8 @@ module Phase
     def unsafe_set_chunk(region : IndexRegion, src : DeviceIndexable(T))
       dst = region.to_descriptor(desc)
       return if Descriptor.count(dst) == 0
-      region_shape = Array(Int64).new(dst.rank) { |i| dst.extent[i] }
+      dst_extent = dst.extent
+      region_shape = Array(Int64).new(dst.rank) { |i| dst_extent[i] }
       # `compatible_shapes?` lets trailing ones differ: view the source with the region's extents
       if folded = Descriptor.reshape(src.desc, region_shape)
         src_desc = folded
@@ -372,7 +373,8 @@ module Phase
     end
 
     private def shape_without(axis : Int32) : Array(Int32)
-      rest = shape_internal.reject_with_index { |_, i| i == axis }
+      rest = [] of Int32
+      shape_internal.each_with_index { |n, i| rest << n unless i == axis }
       rest.empty? ? [1] : rest
     end
 
@@ -415,21 +417,9 @@ module Phase
       counts = counts.to_a
       raise DimensionError.new("Cannot tile: #{counts.size} counts for #{shape_internal.size} dimensions.") if counts.size != shape_internal.size
       raise ShapeError.new("Cannot tile on the device path beyond #{LibPhGpu::MAX_RANK // 2} dimensions.") if 2 * counts.size > LibPhGpu::MAX_RANK
-      mine = desc
-      src = LibPhGpu::Desc.new
-      src.rank = 2 * counts.size
-      src.offset = mine.offset
-      doubled = [] of Int64
-      counts.each_with_index do |c, i|
-        src.extent[2 * i] = c.to_i64
-        src.stride[2 * i] = 0_i64
-        src.extent[2 * i + 1] = mine.extent[i]
-        src.stride[2 * i + 1] = mine.stride[i]
-        doubled << c.to_i64 << mine.extent[i]
-      end
+      src, dst = Descriptor.tile(desc, counts)
       result = DeviceNArray(T).new(shape_internal.map_with_index { |n, i| n * counts[i].to_i32 })
       if result.size > 0
-        dst = Descriptor.contiguous(doubled)
         Device.check LibPhGpu.ph_copy_strided(elem_size, dev.ptr, pointerof(src), result.dev.ptr, pointerof(dst))
       end
       result

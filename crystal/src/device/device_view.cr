@@ -75,7 +75,8 @@ module Phase
         raise IndexError.new("Could not use pattern #{order} to permute: Axis #{bad_axis} is not present in a #{dimensions}-dimensional MultiIndexable")
       end
       @desc = Descriptor.permute(@desc, order.try &.to_a)
-      @shape = Array(Int32).new(@desc.rank) { |i| @desc.extent[i].to_i32 }
+      extent = @desc.extent
+      @shape = Array(Int32).new(@desc.rank) { |i| extent[i].to_i32 }
       self
     end
 
