@@ -184,7 +184,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rows = 1024                                            # 1/8 of the workload per step (~0.12 s)
+    # a bounded sample per step, sized so that the whole --steps K run ends within about a minute:
+    # 1/8 of the workload (~0.13 s on one core) for K <= 100, 1/32 for K <= 2000 (the driver may pass
+    # our own default K = 1000), 1/128 beyond
+    rows = 1024 if args.steps <= 100 else (256 if args.steps <= 2000 else 64)
     from oracle import c_oracle as CO
     a, b, c = make_inputs(0, rows)
     for _ in range(max(1, min(args.warmup, 3))):
