@@ -103,6 +103,14 @@ static void host_specs() {
     IndexRegion rev = two;
     rev.reverse();
     EXPECT(rev.r.first[1] == 4 && rev.r.last[1] == 0 && rev.r.step[1] == -2 && rev.shape() == two.shape());
+    // multidimensional goldens (index_region_spec.cr:64-77, 300-305)
+    IndexRegion md({range(0, 2, 8), range(nil, -1, nil)}, {10, 4});
+    EXPECT(md.shape() == Shape({5, 4}) && md.r.first[0] == 0 && md.r.first[1] == 3 && md.r.last[0] == 8 && md.r.last[1] == 0 &&
+           md.r.step[0] == 2 && md.r.step[1] == -1);
+    EXPECT_RAISES(IndexError, IndexRegion({range(0, 3), range(0, 2, 8)}, {10, 4}));
+    IndexRegion big = IndexRegion::cover({20, 20});
+    big.trim({10, 4});
+    EXPECT(big.fits_in({10, 4}) && !big.fits_in({4, 10}));
     IndexRegion cov = IndexRegion::cover({4, 0, 2});
     EXPECT(cov.shape() == Shape({4, 0, 2}) && cov.size() == 0);
     EXPECT(shape_to_size({}) == 0 && shape_to_size({3, 4}) == 12);
