@@ -194,8 +194,15 @@ if cube is not None:
     s1 = [slice_descs(1, j) for j in range(0, cube.shape[1], step1)][:64]
     row("each_slice(axis=1)[::%d] of the same f64 (strided gathers)" % step1, 2 * 64 * 64 * 1024 * 8,
         lambda: run_slices(s1), reps=5, inner=1, note="f-2: 64 slices of [64,1024] (1 KiB rows, 32 MiB apart), 512 KiB per launch: launch-bound")
+    perm_src = cube.view().permute(1, 0, 2)
+    perm_out = D(perm_src.shape, np.float64)
+    psd, pod = perm_src.desc(), perm_out.desc()
+    row("slices(axis=1), all %d at once: ONE permuting copy [64,%d,1024] -> [%d,64,1024] f64" % (cube.shape[1], cube.shape[1], cube.shape[1]),
+        2 * ncube * 8, lambda: ph.check(lib.ph_copy_strided(8, cube.ptr, C.byref(psd), perm_out.ptr, C.byref(pod))), reps=5,
+        note="f-2: what DeviceNArray#slices does now; the per-index gathers above are the reference's structure")
+    del perm_out
     row("slices(axis=0) through the Python mirror", 2 * ncube * 8, lambda: cube.slices(0), reps=5, inner=1,
-        note="same kernels + region parse, descriptor compile and allocation per slice in Python: host-bound")
+        note="one copy + 64 Python objects")
     del sl_out
 # ---- f-4: binary dump / load of a device array (host file system either side of the path)
 import tempfile, time as _time

@@ -179,9 +179,16 @@ class DeviceBuffer {
     Device::ensure_init();
     Device::check(ph_alloc(nbytes, &ptr));
   }
-  ~DeviceBuffer() { if (ptr) ph_free(ptr); }
+  // A byte range of another buffer (one slice of a batched `slices` copy): keeps the parent alive and
+  // never frees; the parent releases the whole allocation when the last range dies.
+  DeviceBuffer(std::shared_ptr<DeviceBuffer> parent, size_t byte_offset, size_t n)
+      : ptr(static_cast<char*>(parent->ptr) + byte_offset), nbytes(n), parent_(std::move(parent)) {}
+  ~DeviceBuffer() { if (ptr && !parent_) ph_free(ptr); }
   DeviceBuffer(const DeviceBuffer&) = delete;
   DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+
+ private:
+  std::shared_ptr<DeviceBuffer> parent_;
 };
 
 template <class T> class DeviceNArray;
@@ -553,15 +560,29 @@ template <class T> DeviceView<T> MultiIndexable<T>::view(const RegionLiteral& li
 template <class T> DeviceView<T> MultiIndexable<T>::mutable_view() const { return view(); }
 template <class T> DeviceView<T> MultiIndexable<T>::mutable_view(const RegionLiteral& lits, bool drop) const { return view(lits, drop); }
 
+// The reference gathers the slices one by one (ChunkIterator -> unsafe_fetch_chunk per index): on the
+// device one launch per slice, launch-bound for every axis but the leading one.  All slices along `axis`
+// together ARE the array with `axis` moved to the front, so ONE permuting copy produces them and they are
+// handed out as consecutive ranges of its buffer (disjoint, so still independent arrays).
 template <class T>
 std::vector<DeviceNArray<T>> MultiIndexable<T>::slices(int32_t axis) const {
   if (axis < 0 || axis >= dimensions()) throw IndexError("axis " + std::to_string(axis) + " is out of range for shape " + shape_str(shape_));
+  const int64_t n = shape_[axis];
+  Shape rest;
+  for (int32_t i = 0; i < dimensions(); i++) if (i != axis) rest.push_back(shape_[i]);
+  if (rest.empty()) rest.push_back(1);
   std::vector<DeviceNArray<T>> out;
-  for (int64_t i = 0; i < shape_[axis]; i++) {
-    RegionLiteral lit(shape_.size(), all);
-    lit[axis] = Lit(i);
-    out.push_back(get_chunk(lit));
+  out.reserve((size_t)n);
+  if (n == 0 || size() == 0) {
+    for (int64_t i = 0; i < n; i++) out.emplace_back(rest);
+    return out;
   }
+  std::vector<int32_t> order{axis};
+  for (int32_t i = 0; i < dimensions(); i++) if (i != axis) order.push_back(i);
+  DeviceNArray<T> moved = view().permute(order).to_narr();   // one launch
+  const size_t step = (size_t)(size() / n) * sizeof(T);
+  for (int64_t i = 0; i < n; i++)
+    out.emplace_back(rest, std::make_shared<DeviceBuffer>(moved.buffer_owner(), (size_t)i * step, step));
   return out;
 }
 

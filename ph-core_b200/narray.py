@@ -127,6 +127,16 @@ class _Buffer:
             pass
 
 
+class _SubBuffer:
+    """A byte range of another buffer (one slice of a batched `slices` copy).  Keeps its parent
+    alive and never frees: the parent releases the whole allocation when the last slice dies."""
+
+    def __init__(self, parent, byte_offset: int, nbytes: int):
+        self.parent = parent
+        self.nbytes = int(nbytes)
+        self.ptr = parent.ptr + int(byte_offset)
+
+
 _BIN = {"+": "PH_ADD", "-": "PH_SUB", "*": "PH_MUL", "/": "PH_DIV", "//": "PH_FLOORDIV", "%": "PH_MOD",
         "**": "PH_POW", "&+": "PH_WADD", "&-": "PH_WSUB", "&*": "PH_WMUL", "&**": "PH_WPOW",
         "&": "PH_AND", "|": "PH_OR", "^": "PH_XOR"}
@@ -372,14 +382,29 @@ class _Indexable:
         return out
 
     # ---- slices / tile (src/multi_indexable.cr:742-786, 818-843) ----------------------------
-    def each_slice(self, axis: int = 0):
-        for i in range(self.shape[axis]):
-            lit = [_region.ALL] * len(self.shape)
-            lit[axis] = i
-            yield self.get_chunk(lit)
+    def slices(self, axis: int = 0) -> List["DeviceNArray"]:
+        """MultiIndexable#slices (:776-786): the chunks `self[.., i, ..]` for every index i of `axis`,
+        each an independent array without that axis.  The reference gathers them one by one
+        (ChunkIterator -> unsafe_fetch_chunk per index); on the device that is one launch per slice
+        and launch-bound for every axis but the leading one.  All slices along `axis` together ARE
+        the array with `axis` moved to the front, so they are produced by ONE permuting copy and
+        handed out as consecutive ranges of its buffer (disjoint, so still independent arrays)."""
+        nd = len(self.shape)
+        if not 0 <= axis < nd:
+            raise CrIndexError(f"axis {axis} is not present in a {nd}-dimensional MultiIndexable")
+        n = self.shape[axis]
+        if n == 0 or self.size == 0:
+            rest = [s for i, s in enumerate(self.shape) if i != axis] or [1]
+            return [DeviceNArray(rest, self.dtype) for _ in range(n)]
+        order = [axis] + [i for i in range(nd) if i != axis]
+        moved = self.view().permute(*order).to_narr()                  # one launch
+        rest = moved.shape[1:] or [1]
+        step = self.size // n * self.dtype.itemsize
+        return [DeviceNArray(rest, self.dtype, _SubBuffer(moved._buf, i * step, step)) for i in range(n)]
 
-    def slices(self, axis: int = 0):
-        return list(self.each_slice(axis))
+    def each_slice(self, axis: int = 0):
+        """MultiIndexable#each_slice (:742-748)."""
+        return iter(self.slices(axis))
 
     def tile(self, counts: Sequence[int]) -> "DeviceNArray":
         """MultiIndexable#tile (:818-827): out[c] = self[c % shape]; as a descriptor every axis

@@ -294,6 +294,18 @@ int main(int argc, char** argv) {
     EXPECT(b.sum() == 36 && b.min() == 0 && b.max() == 12);
     auto sl = b.slices(1);
     EXPECT(sl.size() == 3 && sl[0].to_host() == V<int32_t>({0, 10}) && sl[2].to_host() == V<int32_t>({2, 12}));
+    {   // all slices along an axis come from ONE permuting copy and stay independent arrays
+      V<int32_t> v(2 * 3 * 4);
+      for (int i = 0; i < 24; i++) v[i] = i;
+      auto cube = narr<int32_t>({2, 3, 4}, v);
+      long long before = ph_launch_count();
+      auto mid = cube.slices(1);
+      EXPECT(ph_launch_count() - before == 1 && mid.size() == 3 && mid[1].shape() == Shape({2, 4}));
+      EXPECT(mid[1].to_host() == V<int32_t>({4, 5, 6, 7, 16, 17, 18, 19}) && mid[2].get({1, 3}) == 23);
+      mid[1].set_chunk({all, all}, -1);
+      EXPECT(mid[0].to_host() == V<int32_t>({0, 1, 2, 3, 12, 13, 14, 15}) && cube.get({0, 1, 0}) == 4);
+      EXPECT_RAISES(IndexError, cube.slices(3));
+    }
     EXPECT(b.sum(0).to_host() == V<int32_t>({10, 12, 14}) && b.sum(1).to_host() == V<int32_t>({3, 33}));
     EXPECT(b.argmax(1).to_host() == V<int64_t>({2, 2}) && b.max(0).to_host() == V<int32_t>({10, 11, 12}));
     auto ties = narr<float>({2, 4}, {1, 7, 7, 0, 7, 7, 7, 7});

@@ -304,3 +304,39 @@ def test_short_last_outer_axis_is_reordered(dtype):
         rowv = D.from_host(cube[:1, :1, :512].copy())
         want, _ = O.ewise_broadcast("+", cube[:, :, :512].copy(), cube[:1, :1, :512].copy())
         assert_bits(v.broadcast_op("+", rowv).to_host(), want, "rowvec + strided")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.uint8])
+def test_slices_along_every_axis_are_one_batched_copy(dtype):
+    """MultiIndexable#slices (src/multi_indexable.cr:776-786): per index the chunk self[.., i, ..]; the device
+    produces all of them with ONE permuting copy and hands out ranges of its buffer.  They must equal the
+    oracle's each_slice, be independent of each other and of the source, and cost one launch."""
+    rs = np.random.RandomState(21)
+    host = (rs.rand(5, 36, 130) * 200).astype(dtype)
+    d = D.from_host(host)
+    for axis in range(3):
+        before = ph.load().ph_launch_count()
+        got = d.slices(axis)
+        assert ph.load().ph_launch_count() - before == 1
+        want = list(O.each_slice(host, axis))
+        assert len(got) == len(want) == host.shape[axis]
+        for g, w in zip(got, want):
+            assert g.shape == list(w.shape)
+            assert_bits(g.to_host(), w, f"slice along {axis}")
+    sl = d.slices(1)
+    sl[3][rng(None, None), rng(None, None)] = 7                      # writing one slice ...
+    assert_bits(sl[2].to_host(), host[:, 2, :], "neighbour slice untouched")
+    assert_bits(sl[4].to_host(), host[:, 4, :], "neighbour slice untouched")
+    assert_bits(d.to_host(), host, "source untouched")               # ... touches neither its neighbours nor the source
+    assert (sl[3].to_host() == 7).all()
+    keep = sl[5]
+    del sl, got                                                      # the shared buffer lives as long as any slice does
+    assert_bits(keep.clone().to_host(), host[:, 5, :], "slice outlives its siblings")
+    one_d = D.from_host(np.arange(4, dtype=dtype))
+    assert [s.to_host().tolist() for s in one_d.slices()] == [[0], [1], [2], [3]]       # all axes dropped -> [1]
+    assert [s.shape for s in D.fill([3, 0, 2], 1, dtype).slices(0)] == [[0, 2]] * 3 and D.fill([3, 0, 2], 1, dtype).slices(1) == []
+    with pytest.raises(ph.CrIndexError):
+        d.slices(3)
+    strided = d.view(rng(None, None), rng(0, None, 5), rng(None, None, -1))         # slices of a VIEW
+    for g, w in zip(strided.slices(2), O.each_slice(np.ascontiguousarray(host[:, ::5, ::-1]), 2)):
+        assert_bits(g.to_host(), w, "slices of a strided view")
