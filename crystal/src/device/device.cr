@@ -89,6 +89,7 @@ module Phase
   class DeviceBuffer
     getter ptr : Void*
     getter bytesize : Int64
+    @parent : DeviceBuffer? = nil
 
     def initialize(@bytesize : Int64)
       Device.ensure_init
@@ -96,9 +97,16 @@ module Phase
       Device.check LibPhGpu.ph_alloc(LibC::SizeT.new({@bytesize, 1_i64}.max), pointerof(@ptr))
     end
 
+    # A byte range of another buffer (one slice of a batched `slices` copy). It keeps its parent
+    # alive and never frees: the parent releases the whole allocation when the last range is gone.
+    def initialize(parent : DeviceBuffer, byte_offset : Int64, @bytesize : Int64)
+      @parent = parent
+      @ptr = (parent.ptr.as(UInt8*) + byte_offset).as(Void*)
+    end
+
     # Eager release; the finalizer is only the safety net.
     def free : Nil
-      return if @ptr.null?
+      return if @ptr.null? || @parent
       LibPhGpu.ph_free(@ptr)
       @ptr = Pointer(Void).null
     end

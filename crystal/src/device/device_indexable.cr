@@ -400,10 +400,24 @@ module Phase
     end
 
     # ---- slices / tile ---------------------------------------------------------------------------
+    # The reference gathers one chunk per index (ChunkIterator -> unsafe_fetch_chunk); on the device that
+    # is one launch per slice and launch-bound for every axis but the leading one. All slices along
+    # `axis` together ARE the array with `axis` moved to the front, so ONE permuting copy produces them
+    # and they are handed out as consecutive ranges of its buffer (disjoint: still independent arrays).
     def slices(axis = 0) : Array(DeviceNArray(T))
-      Array(DeviceNArray(T)).new(shape_internal[axis]) do |i|
-        literal = Array(Int32 | Range(Nil, Nil)).new(shape_internal.size) { |k| k == axis ? i : Range.new(nil, nil) }
-        unsafe_fetch_chunk(IndexRegion.new(literal, shape_internal))
+      unless 0 <= axis < shape_internal.size
+        raise IndexError.new("Axis #{axis} is not present in a #{shape_internal.size}-dimensional MultiIndexable.")
+      end
+      count = shape_internal[axis]
+      rest = shape_without(axis)
+      if count == 0 || size == 0
+        return Array(DeviceNArray(T)).new(count) { DeviceNArray(T).new(rest) }
+      end
+      order = [axis] + (0...shape_internal.size).reject { |i| i == axis }
+      moved = view.permute(order).to_narr # one launch
+      step = size // count * sizeof(T)
+      Array(DeviceNArray(T)).new(count) do |i|
+        DeviceNArray(T).new(rest, DeviceBuffer.new(moved.dev, i.to_i64 * step, step))
       end
     end
 
