@@ -4,7 +4,7 @@ include/ph_gpu.h); this Python package is the thin host mirror used by tests and
 There is no CPU fallback: importing works anywhere, computing needs the GPU library."""
 from . import _lib
 from ._lib import PhDesc, PhError, init, load, check, K
-from .narray import (DeviceNArray, DeviceView, make_region, ShapeError, DimensionError, CrIndexError, CrOverflowError,
+from .narray import (DeviceNArray, DeviceView, make_region, cover_region, ShapeError, DimensionError, CrIndexError, CrOverflowError,
                      CrDivisionByZeroError, CrArgumentError, CrEmptyError, DeviceBlockError)
 
 from .region import R, Step, rng, ALL
@@ -12,6 +12,6 @@ from . import heat
 from . import io
 from . import sharding
 
-__all__ = ["DeviceNArray", "DeviceView", "make_region", "R", "Step", "rng", "ALL", "heat", "io", "sharding", "PhDesc", "PhError", "init", "load", "check", "K", "ShapeError", "DimensionError",
+__all__ = ["DeviceNArray", "DeviceView", "make_region", "cover_region", "R", "Step", "rng", "ALL", "heat", "io", "sharding", "PhDesc", "PhError", "init", "load", "check", "K", "ShapeError", "DimensionError",
            "CrIndexError", "CrOverflowError", "CrDivisionByZeroError", "CrArgumentError", "CrEmptyError",
            "DeviceBlockError"]

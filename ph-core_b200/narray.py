@@ -107,6 +107,14 @@ def make_region(literal: Sequence, bound_shape: Sequence[int], drop: bool = True
     return out
 
 
+def cover_region(bound_shape: Sequence[int], drop: bool = True) -> PhRegion:
+    """IndexRegion.cover(bound_shape) (src/index_region.cr:232-238): the whole array, also when an axis is
+    empty (a literal `..` on a zero-length axis raises IndexError in the reference, range_syntax.cr:120-122)."""
+    out = PhRegion()
+    host_check(_lib.load().ph_region_cover(_i64(bound_shape), len(bound_shape), int(drop), C.byref(out)))
+    return out
+
+
 class _Buffer:
     """Ref-counted owner of one device allocation (reshape aliases the buffer,
     src/n_array.cr:429-433; views keep their source alive, src/view.cr:7)."""

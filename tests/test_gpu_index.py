@@ -340,3 +340,67 @@ def test_slices_along_every_axis_are_one_batched_copy(dtype):
     strided = d.view(rng(None, None), rng(0, None, 5), rng(None, None, -1))         # slices of a VIEW
     for g, w in zip(strided.slices(2), O.each_slice(np.ascontiguousarray(host[:, ::5, ::-1]), 2)):
         assert_bits(g.to_host(), w, "slices of a strided view")
+
+
+@pytest.mark.parametrize("shape", [[0], [5, 0, 2], [3, 0, 0, 1]])
+def test_empty_arrays_through_every_entry_point(shape):
+    """The reference's empties (spec/multi_indexable_spec.cr: shapes [0], [5,0,2], [3,0,0,1]): every entry point
+    accepts a zero-element array, launches nothing that could fault, and keeps the shape rules."""
+    host = np.zeros(shape, np.float32)
+    failures = []
+
+    def check(name, fn):
+        try:
+            assert fn(), "returned False"
+        except Exception as e:                                           # collect, report all at once
+            failures.append(f"{name}: {type(e).__name__}: {e}")
+
+    d = D.from_host(host)
+    check("size/empty", lambda: d.size == 0 and d.empty() and not d.scalar())
+    check("to_host", lambda: d.to_host().shape == tuple(shape))
+    check("clone", lambda: d.clone().shape == shape)
+    check("binary", lambda: (d * d + d).shape == shape)
+    check("scalar both sides", lambda: (2 * d - 1).shape == shape)
+    check("unary", lambda: (-d).shape == shape)
+    check("compare", lambda: (d > d).shape == shape and (d > d).dtype == np.dtype(np.bool_) and d.eq(0).shape == shape)
+    check("equals", lambda: d.equals(D.from_host(host)))
+    check("mask store", lambda: (d.set_mask(d > d, 1.0) or True) and (d.set_mask(d > d, d) or True))
+    # a literal `..` on a zero-length axis raises IndexError in the reference too (range_syntax.cr:120-122:
+    # last = bound - 1 = -1); the whole of an empty array is IndexRegion.cover (index_region.cr:232-238)
+    check("`..` on an empty axis raises IndexError", lambda: _raises(ph.CrIndexError, lambda: d.get_chunk([ph.ALL] * len(shape))))
+    cover = ph.cover_region(shape)
+    check("cover gather", lambda: d.unsafe_fetch_chunk(cover).shape == shape)
+    check("fill region", lambda: (d.unsafe_set_chunk(cover, 3.0) or True))
+    check("scatter", lambda: (d.unsafe_set_chunk(cover, D.from_host(host)) or True))
+    check("view chain", lambda: d.view().permute().reverse().to_narr().shape == shape[::-1])
+    check("reshape", lambda: d.reshape([0]).shape == [0] and d.flatten().shape == [0])
+    check("sum is zero", lambda: d.sum() == 0)
+    for name in ("min", "max", "argmax"):
+        def raises(name=name):
+            try:
+                getattr(d, name)()
+            except ph.CrEmptyError:
+                return True
+            return False
+        check(f"{name} raises EmptyError", raises)
+    check("first raises ShapeError", lambda: _raises(ph.ShapeError, d.first))
+    check("tile", lambda: d.tile([2] * len(shape)).shape == [2 * s for s in shape])
+    check("slices", lambda: [s.shape for s in d.slices(0)] == [shape[1:] or [1]] * shape[0])
+    check("fused mul_add", lambda: d.mul_add(d, d).shape == shape)
+    if len(shape) > 1:
+        ax = shape.index(0)
+        check("axis sum over the empty axis", lambda: (d.sum(axis=ax).to_host() == 0).all()
+              and d.sum(axis=ax).shape == ([s for i, s in enumerate(shape) if i != ax] or [1]))
+        check("axis max over the empty axis raises", lambda: _raises(ph.CrEmptyError, lambda: d.max(axis=ax)))
+        other = 0 if ax != 0 else len(shape) - 1
+        check("axis sum over another axis", lambda: d.sum(axis=other).size == 0)
+    check("no arithmetic flags", lambda: D.take_flags() == 0)
+    assert failures == [], "\\n".join(failures)
+
+
+def _raises(exc, fn):
+    try:
+        fn()
+    except exc:
+        return True
+    return False
