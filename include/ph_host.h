@@ -96,6 +96,51 @@ int32_t ph_desc_broadcast(const ph_desc* src, const int64_t* shape, int32_t rank
 /* buffer offset of one coordinate (Buffered.coord_to_index_fast, buffered.cr:44-52) */
 int32_t ph_desc_offset_of(const ph_desc* d, const int64_t* coord, int32_t ncoord, int64_t* out);
 
+/* ---- partitioning across one process per GPU.  ph-core is single-process, so
+ * these have no reference counterpart; they are the host plans the sharded operations of the path run on
+ * (ph_allreduce / ph_allgather / ph_alltoallv / ph_heat_run_sharded in ph_gpu.h do the data movement). */
+
+/* Contiguous split of `n` leading-axis indices over `world` ranks: the first n % world ranks get one extra. */
+int32_t ph_shard_range(int64_t n, int32_t world, int32_t rank, int64_t* start, int64_t* stop);
+
+/* Slab of a grid split along axis 0: the owned planes [start, stop) live at local planes
+ * [ghost, ghost + count); `ghost` planes on either side are ghosts (1: one time step per halo exchange,
+ * 2: two, for the temporally blocked stencil).  lo_rank / hi_rank = neighbour ranks or -1 at the ends of the
+ * grid, where the first / last owned plane is the fixed global boundary. */
+typedef struct ph_slab {
+  int64_t start, stop, count, local_planes;
+  int32_t ghost, lo_rank, hi_rank, _pad;
+} ph_slab;
+int32_t ph_slab_layout(int64_t n0, int32_t world, int32_t rank, int32_t ghost, ph_slab* out);
+
+/* Plan of `permute(pattern)` (PermuteTransform, transforms.cr:224-271) on an array sharded along axis 0
+ * whose result is sharded along ITS axis 0 (= old axis k = pattern[0]).  For every peer q (peers[q]):
+ *   send0..send1: the slice of old axis k this rank cuts out of its rows for q; the block travels already
+ *                 permuted, shape send_shape;
+ *   recv0..recv1: the old-axis-0 rows q owns; its block lands at those positions of new axis j (where old
+ *                 axis 0 ends up), shape recv_shape.
+ * local != 0 (pattern[0] == 0): no exchange, every rank permutes its own shard.  A pattern that is not a
+ * permutation of the axes -> IndexError. */
+typedef struct ph_transpose_peer {
+  int64_t send0, send1, recv0, recv1;
+  int64_t send_shape[PH_MAX_RANK], recv_shape[PH_MAX_RANK];
+} ph_transpose_peer;
+typedef struct ph_transpose_plan {
+  int32_t local, dims, k, j;
+  int64_t new_shape[PH_MAX_RANK];
+  int64_t my_rows[2], my_new_rows[2];
+} ph_transpose_plan;
+int32_t ph_transpose_plan_of(const int64_t* shape, int32_t dims, const int32_t* pattern, int32_t world,
+                             int32_t rank, ph_transpose_plan* plan, ph_transpose_peer* peers /* world entries */);
+
+/* The sharded argmax / argmin: every rank contributes one 32-byte record to ph_allgather --
+ * value @0 (one element of dtype, <= 8 bytes), LOCAL flat index of its first extremum @16 (int64, -1 = empty
+ * shard), elements owned by lower ranks @24 (int64).  Picks the best value, then the lowest GLOBAL index
+ * (README.md:56-61 across shards).  *winner_rank = -1 when every shard is empty. */
+#define PH_EXTREMUM_RECORD_BYTES 32
+int32_t ph_combine_extremum_records(const uint8_t* records, int32_t world, int32_t dtype, int32_t is_max,
+                                    int32_t* winner_rank, int64_t* global_index);
+
 const char* ph_host_last_error(void);
 
 #ifdef __cplusplus

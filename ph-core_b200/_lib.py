@@ -60,6 +60,24 @@ class PhRegion(C.Structure):
         return [int(self.reduced_shape[i]) for i in range(self.reduced_rank)]
 
 
+class PhSlab(C.Structure):
+    """struct ph_slab (include/ph_host.h)"""
+    _fields_ = [("start", C.c_int64), ("stop", C.c_int64), ("count", C.c_int64), ("local_planes", C.c_int64),
+                ("ghost", C.c_int32), ("lo_rank", C.c_int32), ("hi_rank", C.c_int32), ("_pad", C.c_int32)]
+
+
+class PhTransposePeer(C.Structure):
+    """struct ph_transpose_peer (include/ph_host.h)"""
+    _fields_ = [("send0", C.c_int64), ("send1", C.c_int64), ("recv0", C.c_int64), ("recv1", C.c_int64),
+                ("send_shape", C.c_int64 * PH_MAX_RANK), ("recv_shape", C.c_int64 * PH_MAX_RANK)]
+
+
+class PhTransposePlan(C.Structure):
+    """struct ph_transpose_plan (include/ph_host.h)"""
+    _fields_ = [("local", C.c_int32), ("dims", C.c_int32), ("k", C.c_int32), ("j", C.c_int32),
+                ("new_shape", C.c_int64 * PH_MAX_RANK), ("my_rows", C.c_int64 * 2), ("my_new_rows", C.c_int64 * 2)]
+
+
 HOST_HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "ph_host.h")
 
 
@@ -157,6 +175,10 @@ def load() -> C.CDLL:
         "ph_desc_permute": [dp, i32p, i32, dp], "ph_desc_reverse": [dp, dp],
         "ph_desc_reshape": [dp, i64p, i32, dp], "ph_desc_broadcast": [dp, i64p, i32, dp],
         "ph_desc_offset_of": [dp, i64p, i32, i64p],
+        "ph_shard_range": [i64, i32, i32, i64p, i64p],
+        "ph_slab_layout": [i64, i32, i32, i32, C.POINTER(PhSlab)],
+        "ph_transpose_plan_of": [i64p, i32, i32p, i32, i32, C.POINTER(PhTransposePlan), C.POINTER(PhTransposePeer)],
+        "ph_combine_extremum_records": [vp, i32, i32, i32, i32p, i64p],
     })
     for name, args in sig.items():
         if hasattr(lib, name):

@@ -86,6 +86,24 @@ void finish_region(ph_region& r) {
 
 }  // namespace
 
+namespace {
+// extremum records are compared in the value's own type (exact for int64 / uint64 too)
+template <typename T>
+bool better(const uint8_t* a, const uint8_t* b, bool is_max) {
+  T x, y;
+  memcpy(&x, a, sizeof(T));
+  memcpy(&y, b, sizeof(T));
+  return is_max ? x > y : x < y;
+}
+template <typename T>
+bool same(const uint8_t* a, const uint8_t* b) {
+  T x, y;
+  memcpy(&x, a, sizeof(T));
+  memcpy(&y, b, sizeof(T));
+  return x == y;
+}
+}  // namespace
+
 extern "C" {
 
 const char* ph_host_last_error(void) { return g_err; }
@@ -401,6 +419,97 @@ int32_t ph_desc_offset_of(const ph_desc* d, const int64_t* coord, int32_t ncoord
   int64_t off = d->offset;
   for (int i = 0; i < ncoord; i++) off += coord[i] * d->stride[i];
   *out = off;
+  return PH_HOST_OK;
+}
+
+// ------------------------------------------------------------------ partitioning plans (one process per GPU)
+int32_t ph_shard_range(int64_t n, int32_t world, int32_t rank, int64_t* start, int64_t* stop) {
+  if (!start || !stop || world <= 0 || rank < 0 || rank >= world || n < 0) return fail(PH_HOST_INVALID, "bad argument to ph_shard_range");
+  const int64_t base = n / world, extra = n % world;
+  *start = rank * base + std::min<int64_t>(rank, extra);
+  *stop = *start + base + (rank < extra ? 1 : 0);
+  return PH_HOST_OK;
+}
+
+int32_t ph_slab_layout(int64_t n0, int32_t world, int32_t rank, int32_t ghost, ph_slab* out) {
+  if (!out || ghost < 0) return fail(PH_HOST_INVALID, "bad argument to ph_slab_layout");
+  memset(out, 0, sizeof(*out));
+  int32_t st = ph_shard_range(n0, world, rank, &out->start, &out->stop);
+  if (st != PH_HOST_OK) return st;
+  out->count = out->stop - out->start;
+  out->ghost = ghost;
+  out->local_planes = out->count + 2 * (int64_t)ghost;
+  out->lo_rank = rank > 0 ? rank - 1 : -1;
+  out->hi_rank = rank < world - 1 ? rank + 1 : -1;
+  return PH_HOST_OK;
+}
+
+int32_t ph_transpose_plan_of(const int64_t* shape, int32_t dims, const int32_t* pattern, int32_t world,
+                             int32_t rank, ph_transpose_plan* plan, ph_transpose_peer* peers) {
+  if (!shape || !pattern || !plan || dims <= 0 || dims > PH_MAX_RANK || world <= 0 || rank < 0 || rank >= world)
+    return fail(PH_HOST_INVALID, "bad argument to ph_transpose_plan_of");
+  bool seen[PH_MAX_RANK] = {false};
+  for (int i = 0; i < dims; i++) {
+    if (pattern[i] < 0 || pattern[i] >= dims || seen[pattern[i]])
+      return fail(PH_HOST_INDEX_ERROR, "permute pattern is not a permutation of the axes of a rank-%d array", dims);
+    seen[pattern[i]] = true;
+  }
+  memset(plan, 0, sizeof(*plan));
+  plan->dims = dims;
+  for (int i = 0; i < dims; i++) plan->new_shape[i] = shape[pattern[i]];
+  if (pattern[0] == 0) { plan->local = 1; return PH_HOST_OK; }
+  if (!peers) return fail(PH_HOST_INVALID, "ph_transpose_plan_of needs `world` peer entries for an exchanging plan");
+  const int k = pattern[0];
+  int j = 0;
+  for (int i = 0; i < dims; i++) if (pattern[i] == 0) j = i;
+  plan->k = k;
+  plan->j = j;
+  ph_shard_range(shape[0], world, rank, &plan->my_rows[0], &plan->my_rows[1]);
+  ph_shard_range(shape[k], world, rank, &plan->my_new_rows[0], &plan->my_new_rows[1]);
+  for (int q = 0; q < world; q++) {
+    ph_transpose_peer& p = peers[q];
+    memset(&p, 0, sizeof(p));
+    ph_shard_range(shape[k], world, q, &p.send0, &p.send1);
+    ph_shard_range(shape[0], world, q, &p.recv0, &p.recv1);
+    for (int i = 0; i < dims; i++) { p.send_shape[i] = plan->new_shape[i]; p.recv_shape[i] = plan->new_shape[i]; }
+    p.send_shape[0] = p.send1 - p.send0;
+    p.send_shape[j] = plan->my_rows[1] - plan->my_rows[0];
+    p.recv_shape[0] = plan->my_new_rows[1] - plan->my_new_rows[0];
+    p.recv_shape[j] = p.recv1 - p.recv0;
+  }
+  return PH_HOST_OK;
+}
+
+int32_t ph_combine_extremum_records(const uint8_t* records, int32_t world, int32_t dtype, int32_t is_max,
+                                    int32_t* winner_rank, int64_t* global_index) {
+  if (!records || !winner_rank || !global_index || world <= 0) return fail(PH_HOST_INVALID, "bad argument to ph_combine_extremum_records");
+  int best = -1;
+  int64_t best_index = -1;
+  for (int r = 0; r < world; r++) {
+    const uint8_t* rec = records + (size_t)r * PH_EXTREMUM_RECORD_BYTES;
+    int64_t local, offset;
+    memcpy(&local, rec + 16, 8);
+    memcpy(&offset, rec + 24, 8);
+    if (local < 0) continue;                       // empty shard
+    const int64_t gidx = local + offset;
+    bool take = best < 0;
+    if (!take) {
+      const uint8_t* cur = records + (size_t)best * PH_EXTREMUM_RECORD_BYTES;
+      bool gt = false, eq = false;
+#define PH_CASE(code, T) case code: gt = better<T>(rec, cur, is_max != 0); eq = same<T>(rec, cur); break;
+      switch (dtype) {
+        PH_CASE(PH_F32, float) PH_CASE(PH_F64, double) PH_CASE(PH_I32, int32_t) PH_CASE(PH_I64, int64_t)
+        PH_CASE(PH_U8, uint8_t) PH_CASE(PH_I8, int8_t) PH_CASE(PH_I16, int16_t) PH_CASE(PH_U16, uint16_t)
+        PH_CASE(PH_U32, uint32_t) PH_CASE(PH_U64, uint64_t)
+        default: return fail(PH_HOST_INVALID, "unknown dtype %d", dtype);
+      }
+#undef PH_CASE
+      take = gt || (eq && gidx < best_index);
+    }
+    if (take) { best = r; best_index = gidx; }
+  }
+  *winner_rank = best;
+  *global_index = best_index;
   return PH_HOST_OK;
 }
 

@@ -18,22 +18,28 @@ from . import _lib
 from ._lib import K, check
 
 
+def _host_check(status: int) -> None:
+    from .narray import host_check
+    host_check(status)
+
+
 def shard_range(n: int, world: int, rank: int) -> Tuple[int, int]:
-    """Contiguous split of `n` leading-axis indices: the first n % world ranks get one extra."""
-    base, extra = divmod(int(n), int(world))
-    start = rank * base + min(rank, extra)
-    return start, start + base + (1 if rank < extra else 0)
+    """Contiguous split of `n` leading-axis indices: the first n % world ranks get one extra
+    (ph_shard_range, include/ph_host.h -- the plans below are C++ host code; this file marshals)."""
+    a, b = C.c_int64(), C.c_int64()
+    _host_check(_lib.load().ph_shard_range(int(n), int(world), int(rank), C.byref(a), C.byref(b)))
+    return a.value, b.value
 
 
 def slab_layout(n0: int, world: int, rank: int, ghost: int = 1) -> dict:
-    """Slab of a grid split along axis 0: owned planes [start, stop) live at local planes
+    """Slab of a grid split along axis 0 (ph_slab_layout): owned planes [start, stop) live at local planes
     [ghost, ghost + count); `ghost` planes on either side are ghosts (1: one time step per halo
     exchange; 2: two, for the temporally blocked stencil).  A rank at either end of the grid has
     no neighbour there: its first / last owned plane is the fixed global boundary."""
-    start, stop = shard_range(n0, world, rank)
-    return {"start": start, "stop": stop, "count": stop - start, "ghost": ghost,
-            "local_planes": stop - start + 2 * ghost,
-            "lo_rank": rank - 1 if rank > 0 else -1, "hi_rank": rank + 1 if rank < world - 1 else -1}
+    out = _lib.PhSlab()
+    _host_check(_lib.load().ph_slab_layout(int(n0), int(world), int(rank), int(ghost), C.byref(out)))
+    return {"start": out.start, "stop": out.stop, "count": out.count, "ghost": out.ghost,
+            "local_planes": out.local_planes, "lo_rank": out.lo_rank, "hi_rank": out.hi_rank}
 
 
 def slab_from_global(field: np.ndarray, world: int, rank: int, ghost: int = 1) -> np.ndarray:
@@ -59,23 +65,27 @@ def transpose_plan(shape: Sequence[int], pattern: Sequence[int], world: int, ran
     pattern[0] == 0 needs no exchange (`local` = True)."""
     shape = [int(v) for v in shape]
     pattern = [int(v) for v in pattern]
-    if sorted(pattern) != list(range(len(shape))):
+    if len(pattern) != len(shape):
         raise IndexError(f"permute pattern {pattern} is not a permutation of the axes of a rank-{len(shape)} array")
-    new_shape = [shape[a] for a in pattern]
-    if pattern[0] == 0:
+    plan_c = _lib.PhTransposePlan()
+    peers = (_lib.PhTransposePeer * max(1, int(world)))()
+    st = _lib.load().ph_transpose_plan_of((C.c_int64 * len(shape))(*shape), len(shape), (C.c_int32 * len(pattern))(*pattern),
+                                          int(world), int(rank), C.byref(plan_c), peers)
+    if st == K["PH_HOST_INDEX_ERROR"]:
+        raise IndexError(f"permute pattern {pattern} is not a permutation of the axes of a rank-{len(shape)} array")
+    _host_check(st)
+    nd = len(shape)
+    new_shape = [int(plan_c.new_shape[i]) for i in range(nd)]
+    if plan_c.local:
         return {"local": True, "new_shape": new_shape}
-    k, j = pattern[0], pattern.index(0)
-    r0, r1 = shard_range(shape[0], world, rank)
-    m0, m1 = shard_range(shape[k], world, rank)
-    plan = {"local": False, "new_shape": new_shape, "k": k, "j": j, "my_rows": (r0, r1), "my_new_rows": (m0, m1),
+    plan = {"local": False, "new_shape": new_shape, "k": plan_c.k, "j": plan_c.j,
+            "my_rows": (plan_c.my_rows[0], plan_c.my_rows[1]), "my_new_rows": (plan_c.my_new_rows[0], plan_c.my_new_rows[1]),
             "send": [], "recv": [], "send_shape": [], "recv_shape": []}
     for q in range(world):
-        k0, k1 = shard_range(shape[k], world, q)
-        p0, p1 = shard_range(shape[0], world, q)
-        ss = list(new_shape); ss[0] = k1 - k0; ss[j] = r1 - r0
-        rs = list(new_shape); rs[0] = m1 - m0; rs[j] = p1 - p0
-        plan["send"].append((k0, k1)); plan["recv"].append((p0, p1))
-        plan["send_shape"].append(ss); plan["recv_shape"].append(rs)
+        p = peers[q]
+        plan["send"].append((p.send0, p.send1)); plan["recv"].append((p.recv0, p.recv1))
+        plan["send_shape"].append([int(p.send_shape[i]) for i in range(nd)])
+        plan["recv_shape"].append([int(p.recv_shape[i]) for i in range(nd)])
     return plan
 
 
@@ -120,6 +130,21 @@ def parse_extremum_records(raw: np.ndarray, dtype, world: int):
         i = int(chunk[16:24].view(np.int64)[0])
         idxs.append(i + int(chunk[24:32].view(np.int64)[0]) if i >= 0 else -1)
     return vals, idxs
+
+
+def combine_extremum_records(raw: np.ndarray, dtype, world: int, is_max: bool = True):
+    """The gathered 32-byte records -> (value, GLOBAL flat index) of the FIRST extremum: best value, then the
+    lowest global index (ph_combine_extremum_records, include/ph_host.h).  (None, None) if every shard is empty."""
+    from .narray import dtype_code
+    dt = np.dtype(dtype)
+    raw = np.ascontiguousarray(raw, dtype=np.uint8)
+    winner, gidx = C.c_int32(-1), C.c_int64(-1)
+    _host_check(_lib.load().ph_combine_extremum_records(raw.ctypes.data, int(world), dtype_code(dt), int(bool(is_max)),
+                                                        C.byref(winner), C.byref(gidx)))
+    if winner.value < 0:
+        return None, None
+    rec = raw[EXTREMUM_RECORD_BYTES * winner.value: EXTREMUM_RECORD_BYTES * (winner.value + 1)]
+    return rec[:dt.itemsize].view(dt)[0], gidx.value
 
 
 def comm_init(dist=None) -> Tuple[int, int]:
@@ -176,8 +201,7 @@ def reduce_full_sharded(local, name: str, row_offset_elems: int = 0):
     raw = np.zeros(32 * world, dtype=np.uint8)
     check(lib.ph_d2h(raw.ctypes.data, gathered.ptr, raw.nbytes))
     DeviceNArray.raise_pending()
-    vals, idxs = parse_extremum_records(raw, dt, world)
-    return combine_extremum(vals, idxs, is_max=(name == "argmax"))
+    return combine_extremum_records(raw, dt, world, is_max=(name == "argmax"))
 
 
 def heat_run_sharded(slab, other, coeff, steps: int, ghost: int = 1):

@@ -225,3 +225,87 @@ def test_transpose_plan_covers_every_element_once():
         assert got.tobytes() == want.tobytes(), (shape, pat, world)
     with pytest.raises(IndexError):
         S.transpose_plan([3, 4], [0, 0], 2, 0)
+
+
+# ---- the partition plans are C++ host code (include/ph_host.h); independent Python restatements check them
+def _py_shard_range(n, world, rank):
+    base, extra = divmod(n, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def _py_transpose_plan(shape, pattern, world, rank):
+    new_shape = [shape[a] for a in pattern]
+    if pattern[0] == 0:
+        return {"local": True, "new_shape": new_shape}
+    k, j = pattern[0], pattern.index(0)
+    r0, r1 = _py_shard_range(shape[0], world, rank)
+    m0, m1 = _py_shard_range(shape[k], world, rank)
+    plan = {"local": False, "new_shape": new_shape, "k": k, "j": j, "my_rows": (r0, r1), "my_new_rows": (m0, m1),
+            "send": [], "recv": [], "send_shape": [], "recv_shape": []}
+    for q in range(world):
+        k0, k1 = _py_shard_range(shape[k], world, q)
+        p0, p1 = _py_shard_range(shape[0], world, q)
+        ss = list(new_shape); ss[0] = k1 - k0; ss[j] = r1 - r0
+        rs = list(new_shape); rs[0] = m1 - m0; rs[j] = p1 - p0
+        plan["send"].append((k0, k1)); plan["recv"].append((p0, p1))
+        plan["send_shape"].append(ss); plan["recv_shape"].append(rs)
+    return plan
+
+
+def test_cpp_partition_plans_match_their_restatement():
+    from ph_core_b200 import sharding as S
+    rs = np.random.RandomState(5)
+    for _ in range(400):
+        world = int(rs.randint(1, 9))
+        n = int(rs.randint(0, 50))
+        for rank in range(world):
+            assert S.shard_range(n, world, rank) == _py_shard_range(n, world, rank)
+            ghost = int(rs.randint(1, 3))
+            lay = S.slab_layout(n, world, rank, ghost)
+            a, b = _py_shard_range(n, world, rank)
+            assert lay == {"start": a, "stop": b, "count": b - a, "ghost": ghost, "local_planes": b - a + 2 * ghost,
+                           "lo_rank": rank - 1 if rank > 0 else -1, "hi_rank": rank + 1 if rank < world - 1 else -1}
+    for _ in range(300):
+        nd = int(rs.randint(1, 5))
+        shape = [int(v) for v in rs.randint(0, 12, size=nd)]
+        pattern = [int(v) for v in rs.permutation(nd)]
+        world = int(rs.randint(1, 9))
+        for rank in range(world):
+            assert S.transpose_plan(shape, pattern, world, rank) == _py_transpose_plan(shape, pattern, world, rank)
+    for bad in ([0, 0], [0, 2], [1], [0, 1, 2]):
+        with pytest.raises(IndexError):
+            S.transpose_plan([4, 5], bad, 2, 0)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int8, np.int16, np.int32, np.int64,
+                                   np.uint8, np.uint16, np.uint32, np.uint64])
+def test_cpp_extremum_combine_matches_the_python_fold(dtype):
+    from ph_core_b200 import sharding as S
+    rs = np.random.RandomState(9)
+    info = np.iinfo(dtype) if np.dtype(dtype).kind in "iu" else None
+    for trial in range(200):
+        world = int(rs.randint(1, 9))
+        recs, vals, idxs = [], [], []
+        offset = 0
+        for r in range(world):
+            count = int(rs.randint(0, 6))                          # elements this shard owns (0 = empty shard)
+            if info is not None:
+                pool = [info.min, info.max, 0, 1] if trial % 3 == 0 else [3, 5, 7]
+                v = dtype(pool[rs.randint(len(pool))])
+            else:
+                v = dtype([-0.0, 0.0, 1.5, -2.5, np.inf][rs.randint(5)])
+            local = int(rs.randint(0, count)) if count else -1
+            recs.append(S.pack_extremum_record(v, local, offset, dtype))
+            vals.append(v); idxs.append(local + offset if local >= 0 else -1)
+            offset += count
+        raw = np.concatenate(recs)
+        for is_max in (True, False):
+            want = S.combine_extremum(vals, idxs, is_max)
+            got = S.combine_extremum_records(raw, dtype, world, is_max)
+            if want[0] is None:
+                assert got == (None, None)
+            else:
+                assert got[1] == want[1] and got[0] == want[0] and np.signbit(np.float64(got[0])) == np.signbit(np.float64(want[0]))
+        pv, pi = S.parse_extremum_records(raw, dtype, world)
+        assert pi == idxs and all(a == b for a, b in zip(pv, vals))
