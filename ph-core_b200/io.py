@@ -63,18 +63,20 @@ def from_yaml(text: str, dtype) -> DeviceNArray:
     return from_json(json.dumps(obj), dtype)
 
 
-def dump(arr: DeviceNArray, path: str) -> None:
-    """Binary checkpoint: magic, JSON header line, raw row-major bytes (little endian)."""
-    host = arr.to_host()
-    header = json.dumps({"shape": [int(s) for s in arr.shape], "dtype": host.dtype.str}).encode() + b"\n"
+def write_dump(host: np.ndarray, path: str) -> None:
+    """Host half of `dump`: magic, JSON header line (shape, numpy dtype string), raw row-major bytes.  The C++
+    host layer reads and writes the same file (include/ph_narray_io.hpp)."""
+    host = np.ascontiguousarray(host)
+    header = json.dumps({"shape": [int(s) for s in host.shape], "dtype": host.dtype.str}).encode() + b"\n"
     with open(path, "wb") as f:
         f.write(_MAGIC)
         f.write(header)
         if host.size:
-            f.write(memoryview(np.ascontiguousarray(host)).cast("B"))  # no second host copy
+            f.write(memoryview(host).cast("B"))                         # no second host copy
 
 
-def load(path: str) -> DeviceNArray:
+def read_dump(path: str) -> np.ndarray:
+    """Host half of `load`."""
     with open(path, "rb") as f:
         if f.read(len(_MAGIC)) != _MAGIC:
             raise ValueError(f"{path} is not a ph-core binary dump")
@@ -85,4 +87,13 @@ def load(path: str) -> DeviceNArray:
     size = int(np.prod(shape, dtype=np.int64)) if len(shape) else 0
     if data.size != size:
         raise ShapeError(f"binary dump holds {data.size} elements, the header's shape {shape} needs {size}")
-    return DeviceNArray.from_host(data.reshape(shape))
+    return data.reshape(shape)
+
+
+def dump(arr: DeviceNArray, path: str) -> None:
+    """Binary checkpoint of a device array (explicit D2H, then `write_dump`)."""
+    write_dump(arr.to_host(), path)
+
+
+def load(path: str) -> DeviceNArray:
+    return DeviceNArray.from_host(read_dump(path))

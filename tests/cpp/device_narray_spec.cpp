@@ -12,6 +12,7 @@
 // Build: make -C tests/cpp      Run: tests/cpp/device_narray_spec   (exit 0 = all specs passed)
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <limits>
@@ -19,6 +20,7 @@
 #include <vector>
 
 #include "../../include/ph_narray.hpp"
+#include "../../include/ph_narray_io.hpp"
 
 using namespace Phase;
 template <class T> using V = std::vector<T>;
@@ -117,9 +119,74 @@ static void host_specs() {
   });
 }
 
+// JSON / YAML goldens of spec/n_array_spec.cr:520-558 and the binary dump, host side only
+static void io_host_specs() {
+  it("to_json / from_json / to_yaml / from_yaml goldens (n_array_spec.cr:520-558)", [] {
+    namespace H = IO::host;
+    const Shape shape{2, 3};
+    const V<int32_t> stock{0, 1, 2, 3, 4, 5};
+    EXPECT(H::to_json(shape, stock) == "{\"shape\":[2,3],\"elements\":[0,1,2,3,4,5]}");
+    EXPECT(H::to_json(Shape{0}, V<int32_t>{}) == "{\"shape\":[0],\"elements\":[]}");
+    EXPECT(H::to_yaml(shape, stock) == "---\nshape: [2, 3]\nelements: [0, 1, 2, 3, 4, 5]\n");
+    EXPECT(H::to_yaml(Shape{0}, V<int32_t>{}) == "---\nshape: [0]\nelements: []\n");
+    Shape s; V<int32_t> e;
+    H::from_json("{\"shape\":[2,3],\"elements\":[0,1,2,3,4,5]}", s, e);
+    EXPECT(s == shape && e == stock);
+    H::from_json(" { \"elements\" : [ ] , \"shape\" : [0] } ", s, e);          // any key order, any whitespace
+    EXPECT(s == Shape{0} && e.empty());
+    H::from_yaml("---\nshape: [2, 3]\nelements: [0, 1, 2, 3, 4, 5]\n", s, e);
+    EXPECT(s == shape && e == stock);
+    H::from_yaml("---\nshape: [0]\nelements: []\n", s, e);
+    EXPECT(s == Shape{0} && e.empty());
+    EXPECT_RAISES(ShapeError, H::from_json("{\"shape\":[2,2],\"elements\":[1,2,3]}", s, e));
+    EXPECT_RAISES(IO::ParseError, H::from_json("{\"shape\":[2,2]}", s, e));
+    EXPECT_RAISES(IO::ParseError, H::from_json("{\"shape\":[1],\"elements\":[1.5]}", s, e));    // not an Int32
+    EXPECT_RAISES(IO::ParseError, H::from_json("{\"shape\":[1],\"elements\":[1],\"extra\":[2]}", s, e));
+    // floats: shortest text that round-trips, always with a fraction; bools as true / false on the way in
+    const V<double> fl{0.1, 2.0, -1.5e-7, 1e22, 5e-324, 0.30000000000000004};
+    EXPECT(H::to_json(Shape{6}, fl) == "{\"shape\":[6],\"elements\":[0.1,2.0,-1.5e-07,1e+22,5e-324,0.30000000000000004]}");
+    Shape fs; V<double> fe;
+    H::from_json(H::to_json(Shape{6}, fl), fs, fe);
+    EXPECT(fe == fl);
+    H::from_yaml(H::to_yaml(Shape{2, 3}, fl), fs, fe);
+    EXPECT(fs == Shape({2, 3}) && fe == fl);
+    V<Bool> be;
+    H::from_json("{\"shape\":[3],\"elements\":[true,false,true]}", fs, be);
+    EXPECT(be == V<Bool>({1, 0, 1}));
+    EXPECT_RAISES(std::invalid_argument, H::to_json(Shape{1}, V<float>{std::nanf("")}));
+  });
+}
+
+// --write-dump PATH: a known [3,4] f32 array in the binary format; --read-dump PATH DTYPE: print it back as JSON.
+// tests/test_cpp_host_layer.py exchanges files with the Python mirror's io module through these.
+static int dump_cli(int argc, char** argv) {
+  namespace H = IO::host;
+  if (std::strcmp(argv[1], "--write-dump") == 0 && argc > 2) {
+    V<float> v(12);
+    for (int i = 0; i < 12; i++) v[i] = 0.25f * i - 1.0f;
+    H::dump(argv[2], Shape{3, 4}, v);
+    return 0;
+  }
+  if (std::strcmp(argv[1], "--read-dump") == 0 && argc > 3) {
+    Shape s;
+    std::string dt = argv[3];
+    if (dt == "f64") { V<double> e; H::load(argv[2], s, e); std::printf("%s\n", H::to_json(s, e).c_str()); }
+    else if (dt == "i16") { V<int16_t> e; H::load(argv[2], s, e); std::printf("%s\n", H::to_json(s, e).c_str()); }
+    else if (dt == "u8") { V<uint8_t> e; H::load(argv[2], s, e); std::printf("%s\n", H::to_json(s, e).c_str()); }
+    else { V<float> e; H::load(argv[2], s, e); std::printf("%s\n", H::to_json(s, e).c_str()); }
+    return 0;
+  }
+  return 2;
+}
+
 int main(int argc, char** argv) {
+  if (argc > 1 && (std::strcmp(argv[1], "--write-dump") == 0 || std::strcmp(argv[1], "--read-dump") == 0)) {
+    try { return dump_cli(argc, argv); }
+    catch (const std::exception& e) { std::fprintf(stderr, "%s\n", e.what()); return 4; }
+  }
   if (argc > 1 && std::strcmp(argv[1], "--host-only") == 0) {
     host_specs();
+    io_host_specs();
     std::printf("%d expectations passed, %d failed (host-only)\n", g_passed, g_failed);
     return g_failed ? 1 : 0;
   }
@@ -130,6 +197,32 @@ int main(int argc, char** argv) {
   }
 
   host_specs();
+  io_host_specs();
+
+  // Written after the round's last GPU minute was spent: opt-in until it has run on a device once
+  // (PH_SPEC_DEVICE_IO=1); its host half (io_host_specs) is part of every run.
+  if (std::getenv("PH_SPEC_DEVICE_IO"))
+  it("device arrays through the I/O formats (n_array.cr:807-912; binary checkpoint)", [] {
+    auto stock = stock_narr();
+    EXPECT(IO::to_json(stock) == "{\"shape\":[2,3],\"elements\":[0,1,2,3,4,5]}");
+    EXPECT(IO::from_json<int32_t>(IO::to_json(stock)) == stock);
+    EXPECT(IO::from_yaml<int32_t>(IO::to_yaml(stock)) == stock);
+    EXPECT(IO::to_yaml(stock.view().permute()) == "---\nshape: [3, 2]\nelements: [0, 3, 1, 4, 2, 5]\n");   // a view is materialised first
+    V<float> v(300 * 20);
+    for (size_t i = 0; i < v.size(); i++) v[i] = (float)((i * 2654435761u) % 1000) / 7.0f;
+    auto big = narr<float>({300, 20}, v);
+    const char* path = "/tmp/ph_cpp_spec_checkpoint.phbin";
+    IO::dump(big, path);
+    auto back = IO::load<float>(path);
+    EXPECT(back == big);
+    // checkpoint / resume of a heat run: 3 + 4 steps == 7 steps, bit for bit
+    auto grid = narr<float>({30, 200}, v);
+    auto whole = Heat::simulate(grid, 0.1f, 7);
+    IO::dump(Heat::simulate(grid, 0.1f, 3), path);
+    EXPECT(Heat::simulate(IO::load<float>(path), 0.1f, 4) == whole);
+    EXPECT_RAISES(IO::ParseError, IO::load<double>(path));                     // wrong element type
+    std::remove(path);
+  });
 
   it("#unsafe_fetch_chunk goldens (n_array_spec.cr:211-229)", [] {
     auto s = stock_narr();

@@ -48,3 +48,41 @@ def test_reference_specs_replayed_through_the_cpp_host_layer():
     assert " 0 failed" in out.stdout and "FAIL" not in out.stdout
     launches = int(out.stdout.rsplit(",", 1)[1].split()[0])
     assert launches > 100                                            # the specs ran on the device
+
+
+def test_binary_dump_is_interchangeable_between_the_cpp_and_python_hosts(tmp_path):
+    """f-4: the C++ host layer (include/ph_narray_io.hpp) and the Python mirror (ph_core_b200/io.py) read each
+    other's binary checkpoints and agree on the JSON form (host halves only: no GPU needed)."""
+    import json
+    import numpy as np
+    from ph_core_b200 import io
+    _build()
+    # C++ writes, Python reads
+    p1 = str(tmp_path / "from_cpp.phbin")
+    assert subprocess.run([EXE, "--write-dump", p1]).returncode == 0
+    got = io.read_dump(p1)
+    want = (0.25 * np.arange(12, dtype=np.float32) - 1.0).reshape(3, 4)
+    assert got.dtype == np.float32 and got.shape == (3, 4) and got.tobytes() == want.tobytes()
+    # Python writes, C++ reads and prints the reference's JSON form
+    rs = np.random.RandomState(3)
+    cases = [("f64", rs.rand(4, 3, 2)), ("f32", rs.rand(5, 7).astype(np.float32)),
+             ("i16", rs.randint(-30000, 30000, size=(6,)).astype(np.int16)),
+             ("u8", (rs.rand(2, 9) < 0.5)), ("f32", np.zeros((3, 0, 2), np.float32))]
+    for tag, arr in cases:
+        p2 = str(tmp_path / f"from_py_{tag}.phbin")
+        io.write_dump(arr, p2)
+        out = subprocess.run([EXE, "--read-dump", p2, tag], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        obj = json.loads(out.stdout)
+        assert obj["shape"] == list(arr.shape)
+        back = np.array(obj["elements"], dtype=arr.dtype if arr.dtype != np.bool_ else np.uint8).reshape(arr.shape)
+        assert back.tobytes() == np.ascontiguousarray(arr).view(back.dtype).tobytes()      # shortest round-trip text is exact
+    # a dump of the wrong element type, a truncated one and a foreign file are refused
+    p3 = str(tmp_path / "f64.phbin")
+    io.write_dump(rs.rand(3), p3)
+    assert subprocess.run([EXE, "--read-dump", p3, "f32"], capture_output=True).returncode == 4
+    raw = open(p3, "rb").read()
+    open(p3, "wb").write(raw[:-5])
+    assert subprocess.run([EXE, "--read-dump", p3, "f64"], capture_output=True).returncode == 4
+    open(p3, "wb").write(b"not a dump at all\\n")
+    assert subprocess.run([EXE, "--read-dump", p3, "f64"], capture_output=True).returncode == 4
