@@ -1,930 +1,13 @@
-// reduce.cu -- full and per-axis reductions (K7, K8 of SURVEY.md 2.3).
-//
-// Replaces Crystal's Enumerable#sum/min/max folded over NArray#each
-// (src/n_array.cr:556-564, block form src/multi_indexable.cr:788-793) and the README's
-// argmax idiom (README.md:56-61).  Semantics kept from the reference:
-//   * max/min/argmax/argmin: strict > / < from the left, so the FIRST extremum wins (this
-//     also decides between -0.0 and +0.0); NaN -> PH_FLAG_NAN (host raises ArgumentError).
-//   * integer sum: OverflowError when ANY prefix of the lexicographic fold leaves T.  A
-//     commutative pre-filter (sum of positives / of negatives fit in T => no prefix can
-//     overflow) decides almost always; otherwise an ordered (sum, max-prefix, min-prefix)
-//     monoid pass decides exactly.
-//   * float sum: per-block tree in T, then the last block to finish folds the partials in a
-//     fixed order inside the same launch (deterministic for a given shape), tolerance-checked.
-// Per-axis reductions are defined as the fold of each_slice(axis) in increasing index
-// (src/multi_indexable.cr:742-748); the column-strip kernel keeps exactly that order.
-#include "map_kernels.cuh"
-#include "ops.cuh"
-#include <limits>
+// reduce.cu -- C-ABI entry points of the reductions (ph_reduce_full, ph_reduce_full_dev, ph_reduce_axis).
+// The kernels and per-dtype launchers live in reduce_impl.cuh and are instantiated one element type per
+// translation unit (reduce_<dtype>.cu); here the two launcher templates are only declared.
+#include "ph_common.cuh"
 
 namespace ph {
-
-constexpr int RED_THREADS = 256;
-
-// ---------------------------------------------------------------- helpers
-template <typename T> struct Acc { using type = T; };             // sum accumulator
-template <> struct Acc<int32_t> { using type = int64_t; };
-template <> struct Acc<int64_t> { using type = __int128; };
-template <> struct Acc<uint8_t> { using type = int64_t; };
-template <> struct Acc<int8_t> { using type = int64_t; };
-template <> struct Acc<int16_t> { using type = int64_t; };
-template <> struct Acc<uint16_t> { using type = int64_t; };
-template <> struct Acc<uint32_t> { using type = int64_t; };
-template <> struct Acc<uint64_t> { using type = __int128; };
-
-template <typename T> __device__ __forceinline__ T shfl_down_t(T v, int off) {
-  if constexpr (sizeof(T) == 16) {
-    uint64_t lo = (uint64_t)v, hi = (uint64_t)((unsigned __int128)v >> 64);
-    lo = __shfl_down_sync(0xffffffffu, lo, off);
-    hi = __shfl_down_sync(0xffffffffu, hi, off);
-    return (T)(((unsigned __int128)hi << 64) | lo);
-  } else {
-    return __shfl_down_sync(0xffffffffu, v, off);
-  }
-}
-
-template <typename T> __device__ __forceinline__ T shfl_xor_t(T v, int off) {
-  if constexpr (sizeof(T) == 16) {
-    uint64_t lo = (uint64_t)v, hi = (uint64_t)((unsigned __int128)v >> 64);
-    lo = __shfl_xor_sync(0xffffffffu, lo, off);
-    hi = __shfl_xor_sync(0xffffffffu, hi, off);
-    return (T)(((unsigned __int128)hi << 64) | lo);
-  } else {
-    return __shfl_xor_sync(0xffffffffu, v, off);
-  }
-}
-
-// read a value another block of this launch wrote (L2, never a stale L1 line)
-template <typename T> __device__ __forceinline__ T ld_cg(const T* p) {
-  if constexpr (sizeof(T) == 16) {
-    const unsigned long long* q = reinterpret_cast<const unsigned long long*>(p);
-    const unsigned long long lo = __ldcg(q), hi = __ldcg(q + 1);
-    return (T)(((unsigned __int128)hi << 64) | lo);
-  } else if constexpr (sizeof(T) == 8) {
-    const unsigned long long v = __ldcg(reinterpret_cast<const unsigned long long*>(p));
-    T r; memcpy(&r, &v, 8); return r;
-  } else if constexpr (sizeof(T) == 4) {
-    const unsigned int v = __ldcg(reinterpret_cast<const unsigned int*>(p));
-    T r; memcpy(&r, &v, 4); return r;
-  } else {
-    return *reinterpret_cast<const volatile T*>(p);
-  }
-}
-
-template <typename T> __device__ __forceinline__ T lowest_of() {
-  if constexpr (std::is_same<T, float>::value) return -__int_as_float(0x7f800000);
-  else if constexpr (std::is_same<T, double>::value) return -__longlong_as_double(0x7ff0000000000000LL);
-  else return std::numeric_limits<T>::lowest();
-}
-template <typename T> __device__ __forceinline__ T highest_of() {
-  if constexpr (std::is_same<T, float>::value) return __int_as_float(0x7f800000);
-  else if constexpr (std::is_same<T, double>::value) return __longlong_as_double(0x7ff0000000000000LL);
-  else return std::numeric_limits<T>::max();
-}
-
-// (value, index) candidate for first-extremum selection
-template <typename T> struct Cand { T v; int64_t i; };
-template <typename T, bool IS_MAX>
-__device__ __forceinline__ Cand<T> better(const Cand<T>& a, const Cand<T>& b) {
-  // strictly better value wins; equal values -> lower index (the first one met in lex order)
-  const bool b_wins = IS_MAX ? (b.v > a.v || (b.v == a.v && b.i < a.i))
-                             : (b.v < a.v || (b.v == a.v && b.i < a.i));
-  return b_wins ? b : a;
-}
-
-__global__ void set_flag_kernel(uint32_t* flags, uint32_t bits) { atomicOr(flags, bits); }
-
-// ---------------------------------------------------------------- full sum (floats; ints: S, P, N)
-template <typename T> struct SumState {
-  using A = typename Acc<T>::type;
-  A s, pos, neg;
-};
-
-// The block that finishes LAST (atomic ticket) folds the per-block partials: no second launch, and
-// the fold order is fixed (thread j takes partials j, j+256, ... in order, then a fixed tree), so
-// the result is deterministic for a given grid.  out_value = the sum in T; status = 0 ok /
-// 1 definitely-overflow / 2 need the exact ordered pass (integers only).
-template <typename T, int E>
-__global__ void __launch_bounds__(RED_THREADS) sum_partial_kernel(const T* __restrict__ x, int64_t n,
-                                                                  SumState<T>* __restrict__ partials,
-                                                                  T* __restrict__ out_value, int* __restrict__ status,
-                                                                  unsigned int* __restrict__ ticket) {
-  using A = typename Acc<T>::type;
-  constexpr bool IS_INT = !is_float_t<T>::value;
-  constexpr int UNROLL = 4;
-  A acc[E];
-  A pos = 0, neg = 0;
-#pragma unroll
-  for (int i = 0; i < E; i++) acc[i] = 0;
-  const int64_t tile = (int64_t)RED_THREADS * E * UNROLL;
-  const int64_t ntiles = n / tile;
-  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int64_t base = t * tile + (int64_t)threadIdx.x * E;
-    Group<T, E> g[UNROLL];
-#pragma unroll
-    for (int u = 0; u < UNROLL; u++) g[u] = load_group<T, E>(x + base + (int64_t)u * RED_THREADS * E);
-#pragma unroll
-    for (int u = 0; u < UNROLL; u++)
-#pragma unroll
-      for (int i = 0; i < E; i++) {
-        if constexpr (IS_INT) {
-          const A v = (A)g[u].v[i];
-          acc[i] += v;
-          if (v > 0) pos += v; else neg += v;
-        } else {
-          acc[i] = f_add(acc[i], g[u].v[i]);
-        }
-      }
-  }
-  // tail (< one tile): spread over the first block
-  if (blockIdx.x == 0) {
-    for (int64_t i = ntiles * tile + threadIdx.x; i < n; i += RED_THREADS) {
-      if constexpr (IS_INT) {
-        const A v = (A)x[i];
-        acc[0] += v;
-        if (v > 0) pos += v; else neg += v;
-      } else {
-        acc[0] = f_add(acc[0], x[i]);
-      }
-    }
-  }
-  A s = acc[0];
-#pragma unroll
-  for (int i = 1; i < E; i++) {
-    if constexpr (IS_INT) s += acc[i]; else s = f_add(s, acc[i]);
-  }
-  __shared__ A sh_s[RED_THREADS / 32], sh_p[RED_THREADS / 32], sh_n[RED_THREADS / 32];
-  __shared__ bool is_last;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // warp then block tree (fixed order => deterministic); thread 0 ends up with the block totals
-  auto block_fold = [&](A& ts, A& tp, A& tn) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      if constexpr (IS_INT) {
-        ts += shfl_down_t<A>(ts, off); tp += shfl_down_t<A>(tp, off); tn += shfl_down_t<A>(tn, off);
-      } else {
-        ts = f_add(ts, shfl_down_t<A>(ts, off));
-      }
-    }
-    if (lane == 0) { sh_s[warp] = ts; sh_p[warp] = tp; sh_n[warp] = tn; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      ts = sh_s[0]; tp = sh_p[0]; tn = sh_n[0];
-      for (int w = 1; w < RED_THREADS / 32; w++) {
-        if constexpr (IS_INT) { ts += sh_s[w]; tp += sh_p[w]; tn += sh_n[w]; }
-        else ts = f_add(ts, sh_s[w]);
-      }
-    }
-  };
-  block_fold(s, pos, neg);
-  if (threadIdx.x == 0) {
-    partials[blockIdx.x].s = s; partials[blockIdx.x].pos = pos; partials[blockIdx.x].neg = neg;
-    __threadfence();
-    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
-  }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  A fs = 0, fp = 0, fn = 0;
-  for (int i = threadIdx.x; i < (int)gridDim.x; i += RED_THREADS) {
-    const SumState<T>* q = partials + i;
-    if constexpr (IS_INT) { fs += ld_cg(&q->s); fp += ld_cg(&q->pos); fn += ld_cg(&q->neg); }
-    else fs = f_add(fs, ld_cg(&q->s));
-  }
-  __syncthreads();                                   // sh_* are reused
-  block_fold(fs, fp, fn);
-  if (threadIdx.x == 0) {
-    if constexpr (IS_INT) {
-      const A hi = (A)std::numeric_limits<T>::max(), lo = (A)std::numeric_limits<T>::lowest();
-      int st = 0;
-      if (fs > hi || fs < lo) st = 1;                // the final prefix itself overflows
-      else if (fp > hi || fn < lo) st = 2;           // some prefix MIGHT overflow: decide exactly
-      *status = st;
-      *out_value = (T)fs;
-    } else {
-      *status = 0;
-      *out_value = fs;
-    }
-    *ticket = 0;                                     // ready for the next launch on this stream
-  }
-}
-
-// Exact ordered pass for integer sums: monoid (sum, max prefix, min prefix) combined in lex order.
-template <typename T> struct Prefix {
-  using A = typename Acc<T>::type;
-  A s, mx, mn;
-};
 template <typename T>
-__device__ __forceinline__ Prefix<T> pcombine(const Prefix<T>& l, const Prefix<T>& r) {
-  Prefix<T> o;
-  o.s = l.s + r.s;
-  const typename Prefix<T>::A a = l.s + r.mx, b = l.s + r.mn;
-  o.mx = l.mx > a ? l.mx : a;
-  o.mn = l.mn < b ? l.mn : b;
-  return o;
-}
-// each block owns a CONTIGUOUS range; each thread a contiguous sub-range (uncoalesced but exact;
-// this kernel only runs when the commutative filter could not decide).
+int32_t reduce_full_t(int32_t red, const void* a, const ph_desc* d, void* out_value_dev, int64_t* out_index_dev);
 template <typename T>
-__global__ void __launch_bounds__(RED_THREADS) sum_exact_kernel(const T* __restrict__ x, int64_t n,
-                                                                Prefix<T>* __restrict__ partials) {
-  using A = typename Acc<T>::type;
-  const int64_t nthreads = (int64_t)gridDim.x * RED_THREADS;
-  const int64_t per = (n + nthreads - 1) / nthreads;
-  const int64_t gid = (int64_t)blockIdx.x * RED_THREADS + threadIdx.x;
-  int64_t b = gid * per, e = b + per;
-  if (b > n) b = n;
-  if (e > n) e = n;
-  Prefix<T> st; st.s = 0; st.mx = 0; st.mn = 0;     // prefixes include the empty prefix (acc = 0)
-  for (int64_t i = b; i < e; i++) {
-    st.s += (A)x[i];
-    if (st.s > st.mx) st.mx = st.s;
-    if (st.s < st.mn) st.mn = st.s;
-  }
-  __shared__ Prefix<T> sh[RED_THREADS];
-  sh[threadIdx.x] = st;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    Prefix<T> acc = sh[0];
-    for (int t = 1; t < RED_THREADS; t++) acc = pcombine<T>(acc, sh[t]);
-    partials[blockIdx.x] = acc;
-  }
-}
-template <typename T>
-__global__ void sum_exact_final_kernel(const Prefix<T>* __restrict__ partials, int nparts, int* __restrict__ status) {
-  using A = typename Acc<T>::type;
-  if (threadIdx.x != 0) return;
-  Prefix<T> acc = partials[0];
-  for (int i = 1; i < nparts; i++) acc = pcombine<T>(acc, partials[i]);
-  const A hi = (A)std::numeric_limits<T>::max(), lo = (A)std::numeric_limits<T>::lowest();
-  *status = (acc.mx > hi || acc.mn < lo) ? 1 : 0;
-}
-
-// ---------------------------------------------------------------- full min / max / argmin / argmax
-// Running extremum of a register tile.  f32 uses max.NaN / min.NaN (one instruction that also
-// propagates NaN, so NaN detection is free); other types compare + select and test NaN apart.
-template <typename T, bool IS_MAX>
-__device__ __forceinline__ T ext2(T a, T b, bool& nan) {
-  if constexpr (std::is_same<T, float>::value) {
-    float r;
-    if (IS_MAX) asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
-    else asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
-    return r;
-  } else {
-    if constexpr (is_float_t<T>::value) nan |= (b != b);
-    return IS_MAX ? (b > a ? b : a) : (b < a ? b : a);
-  }
-}
-
-// Hot loop: 4 x 32-byte loads, the extremum of the 32 register values, and -- only when a tile
-// strictly improves on the running extremum -- the tile NUMBER.  The first index inside the
-// winning tile is searched once per thread after the loop (the tile is re-read, 128 bytes), so
-// the loop carries no index arithmetic and few registers.  Tiles are visited in increasing
-// index order, so "strictly improves" keeps the FIRST extremum.  The last block to finish
-// (atomic ticket) folds the per-block candidates: no second launch.
-template <typename T, int E, bool IS_MAX>
-__global__ void __launch_bounds__(RED_THREADS) ext_partial_kernel(const T* __restrict__ x, int64_t n,
-                                                                  Cand<T>* __restrict__ partials,
-                                                                  uint32_t* __restrict__ flags,
-                                                                  T* __restrict__ out_value,
-                                                                  int64_t* __restrict__ out_index,
-                                                                  unsigned int* __restrict__ ticket) {
-  constexpr int UNROLL = 4;
-  T best_v = IS_MAX ? lowest_of<T>() : highest_of<T>();
-  int64_t best_t = -1;
-  bool nan = false;
-  const int64_t tile = (int64_t)RED_THREADS * E * UNROLL;
-  const int64_t ntiles = n / tile;
-  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int64_t base = t * tile + (int64_t)threadIdx.x * E;
-    Group<T, E> g[UNROLL];
-#pragma unroll
-    for (int u = 0; u < UNROLL; u++) g[u] = load_group<T, E>(x + base + (int64_t)u * RED_THREADS * E);
-    T m = g[0].v[0];
-    if constexpr (is_float_t<T>::value && !std::is_same<T, float>::value) nan |= (m != m);
-#pragma unroll
-    for (int u = 0; u < UNROLL; u++)
-#pragma unroll
-      for (int i = 0; i < E; i++)
-        if (u || i) m = ext2<T, IS_MAX>(m, g[u].v[i], nan);
-    if constexpr (std::is_same<T, float>::value) nan |= (m != m);
-    const bool improves = IS_MAX ? (m > best_v) : (m < best_v);
-    if (improves || (best_t < 0 && m == best_v)) { best_v = m; best_t = t; }
-  }
-  Cand<T> best;
-  best.v = best_v;
-  best.i = INT64_MAX;
-  if (best_t >= 0) {                                 // first register of the winning tile holding the extremum
-    const int64_t base = best_t * tile + (int64_t)threadIdx.x * E;
-    bool found = false;
-#pragma unroll
-    for (int u = 0; u < UNROLL; u++) {
-      const Group<T, E> g = load_group_plain<T, E>(x + base + (int64_t)u * RED_THREADS * E);
-#pragma unroll
-      for (int i = 0; i < E; i++)
-        if (!found && g.v[i] == best_v) {
-          found = true;
-          best.v = g.v[i];                           // the element itself (keeps the sign of a zero)
-          best.i = base + (int64_t)u * RED_THREADS * E + i;
-        }
-    }
-  }
-  if (blockIdx.x == 0) {
-    for (int64_t i = ntiles * tile + threadIdx.x; i < n; i += RED_THREADS) {
-      const T v = x[i];
-      if constexpr (is_float_t<T>::value) nan |= (v != v);
-      Cand<T> c; c.v = v; c.i = i;
-      best = better<T, IS_MAX>(best, c);
-    }
-  }
-  __shared__ Cand<T> sh[RED_THREADS / 32];
-  __shared__ bool is_last;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  auto block_fold = [&](Cand<T>& b) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      Cand<T> o;
-      o.v = __shfl_down_sync(0xffffffffu, b.v, off);
-      o.i = __shfl_down_sync(0xffffffffu, b.i, off);
-      b = better<T, IS_MAX>(b, o);
-    }
-    if (lane == 0) sh[warp] = b;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      b = sh[0];
-      for (int w = 1; w < RED_THREADS / 32; w++) b = better<T, IS_MAX>(b, sh[w]);
-    }
-  };
-  block_fold(best);
-  if (nan) atomicOr(flags, (uint32_t)PH_FLAG_NAN);
-  if (threadIdx.x == 0) {
-    partials[blockIdx.x] = best;
-    __threadfence();
-    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
-  }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  Cand<T> fin;
-  fin.v = IS_MAX ? lowest_of<T>() : highest_of<T>();
-  fin.i = INT64_MAX;
-  for (int i = threadIdx.x; i < (int)gridDim.x; i += RED_THREADS) {
-    Cand<T> c;
-    c.v = ld_cg(&partials[i].v);
-    c.i = ld_cg(&partials[i].i);
-    fin = better<T, IS_MAX>(fin, c);
-  }
-  __syncthreads();                                   // sh is reused
-  block_fold(fin);
-  if (threadIdx.x == 0) {
-    *out_value = fin.v;
-    if (out_index) *out_index = fin.i;
-    *ticket = 0;
-  }
-}
-
-// ---------------------------------------------------------------- per-axis: [outer, K, inner]
-// inner > 1: threads run along `inner` (coalesced), each folds its column over k = 0..K-1 in order.
-// UNROLL groups are in flight per thread; the block size is the launch's (64..256).
-template <typename T, int E, int RED, int UNROLL>
-__global__ void __launch_bounds__(RED_THREADS) axis_strip_kernel(const T* __restrict__ x, void* __restrict__ out,
-                                                                 int64_t outer, int64_t K, int64_t inner,
-                                                                 uint32_t* __restrict__ flags) {
-  const int64_t groups = inner / E;                         // inner % E == 0 by dispatch
-  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= outer * groups) return;
-  const int64_t o = gid / groups;
-  const int64_t c = (gid - o * groups) * E;
-  const T* p = x + o * K * inner + c;
-  uint32_t err = 0;
-  bool nan = false;
-  T acc[E];
-  int32_t arg[E];                                           // an axis extent always fits Int32
-#pragma unroll
-  for (int i = 0; i < E; i++) { acc[i] = (RED == PH_SUM) ? (T)0 : p[i]; arg[i] = 0; }
-  int64_t k = (RED == PH_SUM) ? 0 : 1;
-  if constexpr (RED != PH_SUM && is_float_t<T>::value) {
-#pragma unroll
-    for (int i = 0; i < E; i++) nan |= (acc[i] != acc[i]);
-  }
-  auto fold = [&](const Group<T, E>& g, int32_t kk) {
-#pragma unroll
-    for (int i = 0; i < E; i++) {
-      const T v = g.v[i];
-      if constexpr (RED == PH_SUM) {
-        if constexpr (is_float_t<T>::value) acc[i] = f_add(acc[i], v);
-        else acc[i] = i_add<T>(acc[i], v, true, err);
-      } else {
-        if constexpr (is_float_t<T>::value) nan |= (v != v);
-        const bool take = (RED == PH_MAX || RED == PH_ARGMAX) ? (v > acc[i]) : (v < acc[i]);
-        if (take) { acc[i] = v; arg[i] = kk; }
-      }
-    }
-  };
-  for (; k + UNROLL <= K; k += UNROLL) {
-    Group<T, E> g[UNROLL];
-#pragma unroll
-    for (int u = 0; u < UNROLL; u++) g[u] = load_group<T, E>(p + (k + u) * inner);
-#pragma unroll
-    for (int u = 0; u < UNROLL; u++) fold(g[u], (int32_t)(k + u));
-  }
-  for (; k < K; k++) fold(load_group<T, E>(p + k * inner), (int32_t)k);
-  if constexpr (RED == PH_ARGMAX || RED == PH_ARGMIN) {
-    int64_t* q = reinterpret_cast<int64_t*>(out) + o * inner + c;
-#pragma unroll
-    for (int i = 0; i < E; i++) q[i] = (int64_t)arg[i];
-  } else {
-    Group<T, E> r;
-#pragma unroll
-    for (int i = 0; i < E; i++) r.v[i] = acc[i];
-    store_group<T, E>(reinterpret_cast<T*>(out) + o * inner + c, r);
-  }
-  if (err) atomicOr(flags, err);
-  if (nan) atomicOr(flags, (uint32_t)PH_FLAG_NAN);
-}
-
-// inner == 1: each row of K contiguous elements is reduced by TX cooperating threads (TX a
-// power of two; <= 32 combines with shuffles, larger through shared memory).  Lanes read
-// consecutive 32-byte groups (E elements), UNROLL groups in flight per lane.
-// min/max/arg*: pass 1 finds the row extremum M (one max.NaN per element for f32); the index of
-// its FIRST occurrence -- needed for arg*, and for max/min only when M is a zero whose sign
-// depends on which zero came first -- is found by a second pass over the L1/L2-resident row.
-template <typename T, int E, int RED>
-__global__ void __launch_bounds__(RED_THREADS) axis_row_kernel(const T* __restrict__ x, void* __restrict__ out,
-                                                               int64_t rows, int64_t K, int tx, int tx_log2,
-                                                               uint32_t* __restrict__ flags) {
-  constexpr bool IS_MAXLIKE = (RED == PH_MAX || RED == PH_ARGMAX);
-  constexpr bool IS_ARG = (RED == PH_ARGMAX || RED == PH_ARGMIN);
-  constexpr int UNROLL = 4;
-  using A = typename Acc<T>::type;
-  __shared__ A sh_s[RED_THREADS], sh_p[RED_THREADS], sh_n[RED_THREADS];
-  __shared__ T sh_m[RED_THREADS];
-  __shared__ int32_t sh_i[RED_THREADS];
-  const int lane = threadIdx.x & (tx - 1);
-  const int ty = threadIdx.x >> tx_log2;
-  const int TY = RED_THREADS >> tx_log2;
-  const int b0 = ty << tx_log2;
-  const int64_t row = (int64_t)blockIdx.x * TY + ty;
-  const bool live = row < rows;
-  const T* p = x + (live ? row : 0) * K;
-  const int64_t groups = K / E;                   // K % E == 0 by dispatch (E == 1 otherwise)
-  bool nan = false;
-  uint32_t err = 0;
-
-  if constexpr (RED == PH_SUM) {
-    A s = 0, pos = 0, neg = 0;
-    auto fold = [&](const Group<T, E>& g) {
-#pragma unroll
-      for (int i = 0; i < E; i++) {
-        const T v = g.v[i];
-        if constexpr (is_float_t<T>::value) s = f_add(s, v);
-        else { s += (A)v; if (v > 0) pos += (A)v; else neg += (A)v; }
-      }
-    };
-    if (live) {
-      int64_t g0 = lane;
-      for (; g0 + (int64_t)(UNROLL - 1) * tx < groups; g0 += (int64_t)UNROLL * tx) {
-        Group<T, E> g[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) g[u] = load_group<T, E>(p + (g0 + (int64_t)u * tx) * E);
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) fold(g[u]);
-      }
-      for (; g0 < groups; g0 += tx) fold(load_group<T, E>(p + g0 * E));
-    }
-    if (tx <= 32) {
-      for (int off = tx >> 1; off > 0; off >>= 1) {
-        if constexpr (is_float_t<T>::value) s = f_add(s, shfl_xor_t<A>(s, off));
-        else { s += shfl_xor_t<A>(s, off); pos += shfl_xor_t<A>(pos, off); neg += shfl_xor_t<A>(neg, off); }
-      }
-    } else {
-      sh_s[threadIdx.x] = s; sh_p[threadIdx.x] = pos; sh_n[threadIdx.x] = neg;
-      __syncthreads();
-      if (lane == 0)
-        for (int j = 1; j < tx; j++) {
-          if constexpr (is_float_t<T>::value) s = f_add(s, sh_s[b0 + j]);
-          else { s += sh_s[b0 + j]; pos += sh_p[b0 + j]; neg += sh_n[b0 + j]; }
-        }
-    }
-    if (lane == 0 && live) {
-      if constexpr (!is_float_t<T>::value) {
-        // checked fold: overflow at ANY prefix raises.  sum(positives) / sum(negatives) inside T
-        // proves no prefix can leave T; otherwise lane 0 replays the row in order (rare).
-        const A hi = (A)std::numeric_limits<T>::max(), lo = (A)std::numeric_limits<T>::lowest();
-        if (pos > hi || neg < lo) {
-          A run = 0;
-          for (int64_t k = 0; k < K; k++) { run += (A)p[k]; if (run > hi || run < lo) { err |= PH_FLAG_OVERFLOW; break; } }
-        }
-      }
-      reinterpret_cast<T*>(out)[row] = (T)s;
-    }
-  } else {
-    // ---- pass 1: row extremum
-    T m = IS_MAXLIKE ? lowest_of<T>() : highest_of<T>();
-    auto fold = [&](const Group<T, E>& g) {
-#pragma unroll
-      for (int i = 0; i < E; i++) m = ext2<T, IS_MAXLIKE>(m, g.v[i], nan);
-    };
-    if (live) {
-      int64_t g0 = lane;
-      for (; g0 + (int64_t)(UNROLL - 1) * tx < groups; g0 += (int64_t)UNROLL * tx) {
-        Group<T, E> g[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) g[u] = load_group_plain<T, E>(p + (g0 + (int64_t)u * tx) * E);
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) fold(g[u]);
-      }
-      for (; g0 < groups; g0 += tx) fold(load_group_plain<T, E>(p + g0 * E));
-    }
-    if (tx <= 32) {
-      for (int off = tx >> 1; off > 0; off >>= 1) m = ext2<T, IS_MAXLIKE>(m, __shfl_xor_sync(0xffffffffu, m, off), nan);
-    } else {
-      sh_m[threadIdx.x] = m;
-      __syncthreads();
-      m = sh_m[b0];
-      for (int j = 1; j < tx; j++) m = ext2<T, IS_MAXLIKE>(m, sh_m[b0 + j], nan);
-    }
-    if constexpr (std::is_same<T, float>::value) nan |= (m != m);
-    // ---- pass 2: index of the first element equal to M (arg*, or a zero extremum)
-    int32_t bi = INT32_MAX;
-    const bool need_index = IS_ARG || (is_float_t<T>::value && m == (T)0);
-    if (live && need_index && !nan) {
-      for (int64_t g0 = lane; g0 < groups; g0 += tx) {
-        if (bi != INT32_MAX) break;               // k grows inside a lane: the first hit is the lane's first
-        const Group<T, E> g = load_group_plain<T, E>(p + g0 * E);
-#pragma unroll
-        for (int i = 0; i < E; i++)
-          if (bi == INT32_MAX && g.v[i] == m) bi = (int32_t)(g0 * E) + i;
-      }
-    }
-    if (tx <= 32) {
-      for (int off = tx >> 1; off > 0; off >>= 1) {
-        const int32_t o = __shfl_xor_sync(0xffffffffu, bi, off);
-        bi = o < bi ? o : bi;
-      }
-    } else {
-      __syncthreads();
-      sh_i[threadIdx.x] = bi;
-      __syncthreads();
-      if (lane == 0)
-        for (int j = 1; j < tx; j++) bi = sh_i[b0 + j] < bi ? sh_i[b0 + j] : bi;
-    }
-    if (lane == 0 && live) {
-      if constexpr (IS_ARG) reinterpret_cast<int64_t*>(out)[row] = (bi == INT32_MAX) ? 0 : (int64_t)bi;
-      else reinterpret_cast<T*>(out)[row] = (need_index && bi != INT32_MAX) ? p[bi] : m;   // keeps the first zero's sign
-    }
-  }
-  if (err) atomicOr(flags, err);
-  if (nan) atomicOr(flags, (uint32_t)PH_FLAG_NAN);
-}
-
-// inner == 1, short rows (K <= 32 lanes x G groups x E elements): the whole row lives in the
-// registers of TX <= 32 lanes of ONE warp.  Every lane issues all of its G 32-byte loads before
-// the first use (no loop, no trip-count arithmetic: the looped kernel above spent ~7 instructions
-// per element and was latency-bound at 0.87 of the copy peak), folds them, and the lanes combine
-// with shuffles.  arg* / a zero extremum: only lanes whose own extremum equals the row's search
-// their registers for the first match (no second pass over memory).
-template <typename T, int E, int G, int RED>
-__global__ void __launch_bounds__(RED_THREADS) axis_rowreg_kernel(const T* __restrict__ x, void* __restrict__ out,
-                                                                  int64_t rows, int64_t K, int tx_log2,
-                                                                  uint32_t* __restrict__ flags) {
-  constexpr bool IS_MAXLIKE = (RED == PH_MAX || RED == PH_ARGMAX);
-  constexpr bool IS_ARG = (RED == PH_ARGMAX || RED == PH_ARGMIN);
-  using A = typename Acc<T>::type;
-  const int tx = 1 << tx_log2;
-  const int lane = threadIdx.x & (tx - 1);
-  const int64_t row = (int64_t)blockIdx.x * (RED_THREADS >> tx_log2) + (threadIdx.x >> tx_log2);
-  const bool live = row < rows;
-  const T* p = x + (live ? row : 0) * K;
-  const int groups = (int)(K / E);                // K % E == 0 and groups <= 32 * G by dispatch
-  Group<T, E> g[G];
-  bool has[G];
-#pragma unroll
-  for (int u = 0; u < G; u++) {
-    const int gi = lane + u * tx;
-    has[u] = live && gi < groups;
-    if (has[u]) g[u] = load_group<T, E>(p + (int64_t)gi * E);
-  }
-  bool nan = false;
-  uint32_t err = 0;
-  if constexpr (RED == PH_SUM) {
-    A s = 0, pos = 0, neg = 0;
-    if constexpr (is_float_t<T>::value) {
-      A acc[E];
-#pragma unroll
-      for (int i = 0; i < E; i++) acc[i] = has[0] ? g[0].v[i] : (T)0;
-#pragma unroll
-      for (int u = 1; u < G; u++)
-        if (has[u]) {
-#pragma unroll
-          for (int i = 0; i < E; i++) acc[i] = f_add(acc[i], g[u].v[i]);
-        }
-#pragma unroll
-      for (int w = E / 2; w > 0; w >>= 1)
-#pragma unroll
-        for (int i = 0; i < w; i++) acc[i] = f_add(acc[i], acc[i + w]);
-      s = acc[0];
-    } else {
-#pragma unroll
-      for (int u = 0; u < G; u++)
-        if (has[u]) {
-#pragma unroll
-          for (int i = 0; i < E; i++) { const A v = (A)g[u].v[i]; s += v; if (v > 0) pos += v; else neg += v; }
-        }
-    }
-    for (int off = tx >> 1; off > 0; off >>= 1) {
-      if constexpr (is_float_t<T>::value) s = f_add(s, shfl_xor_t<A>(s, off));
-      else { s += shfl_xor_t<A>(s, off); pos += shfl_xor_t<A>(pos, off); neg += shfl_xor_t<A>(neg, off); }
-    }
-    if (lane == 0 && live) {
-      if constexpr (!is_float_t<T>::value) {
-        const A hi = (A)std::numeric_limits<T>::max(), lo = (A)std::numeric_limits<T>::lowest();
-        if (pos > hi || neg < lo) {               // some prefix might leave T: replay the row in order (rare)
-          A run = 0;
-          for (int64_t k = 0; k < K; k++) { run += (A)p[k]; if (run > hi || run < lo) { err |= PH_FLAG_OVERFLOW; break; } }
-        }
-      }
-      reinterpret_cast<T*>(out)[row] = (T)s;
-    }
-  } else {
-    T m = IS_MAXLIKE ? lowest_of<T>() : highest_of<T>();
-#pragma unroll
-    for (int u = 0; u < G; u++)
-      if (has[u]) {
-#pragma unroll
-        for (int i = 0; i < E; i++) m = ext2<T, IS_MAXLIKE>(m, g[u].v[i], nan);
-      }
-    T M = m;
-    for (int off = tx >> 1; off > 0; off >>= 1) M = ext2<T, IS_MAXLIKE>(M, __shfl_xor_sync(0xffffffffu, M, off), nan);
-    if constexpr (std::is_same<T, float>::value) nan |= (M != M);
-    int32_t bi = INT32_MAX;
-    T zv = M;
-    const bool need_index = IS_ARG || (is_float_t<T>::value && M == (T)0);
-    // rows sharing a warp (TX < 32) may disagree on need_index: branch on a warp-uniform vote so
-    // the shuffles below are executed by all 32 lanes
-    const bool warp_need = IS_ARG ? true : (__any_sync(0xffffffffu, need_index) != 0);
-    if (warp_need) {
-      if (need_index && m == M) {                 // NaN rows never match
-#pragma unroll
-        for (int u = 0; u < G; u++)
-#pragma unroll
-          for (int i = 0; i < E; i++)
-            if (has[u] && bi == INT32_MAX && g[u].v[i] == M) { bi = (lane + u * tx) * E + i; zv = g[u].v[i]; }
-      }
-      for (int off = tx >> 1; off > 0; off >>= 1) {
-        const int32_t ob = __shfl_xor_sync(0xffffffffu, bi, off);
-        const T oz = __shfl_xor_sync(0xffffffffu, zv, off);
-        if (ob < bi) { bi = ob; zv = oz; }
-      }
-    }
-    if (lane == 0 && live) {
-      if constexpr (IS_ARG) reinterpret_cast<int64_t*>(out)[row] = (bi == INT32_MAX) ? 0 : (int64_t)bi;
-      else reinterpret_cast<T*>(out)[row] = (need_index && bi != INT32_MAX) ? zv : M;   // keeps the first zero's sign
-    }
-  }
-  if (err) atomicOr(flags, err);
-  if (nan) atomicOr(flags, (uint32_t)PH_FLAG_NAN);
-}
-
-// ---------------------------------------------------------------- host side
-static bool desc_is_contiguous(const ph_desc* d, int64_t& total) {
-  total = 1;
-  int64_t expect = 1;
-  bool ok = true;
-  for (int i = d->rank - 1; i >= 0; i--) {
-    if (d->extent[i] != 1 && d->stride[i] != expect) ok = false;
-    expect *= d->extent[i];
-    total *= d->extent[i];
-  }
-  if (d->rank == 0) total = 0;
-  return ok;
-}
-
-// returns a contiguous device pointer holding the described region (gathers if needed)
-template <typename T>
-static int32_t contiguous_input(const void* a, const ph_desc* d, const T** out_ptr, void** temp, int64_t& total) {
-  *temp = nullptr;
-  if (desc_is_contiguous(d, total)) {
-    *out_ptr = reinterpret_cast<const T*>(a) + d->offset;
-    return PH_OK;
-  }
-  if (total == 0) { *out_ptr = reinterpret_cast<const T*>(a); return PH_OK; }
-  PH_CUDA(cudaMallocAsync(temp, (size_t)total * sizeof(T), rt().stream));
-  ph_desc cd;
-  memset(&cd, 0, sizeof(cd));
-  cd.rank = d->rank;
-  int64_t acc = 1;
-  for (int i = d->rank - 1; i >= 0; i--) { cd.extent[i] = d->extent[i]; cd.stride[i] = acc; acc *= d->extent[i]; }
-  int32_t st = ph_copy_strided((int32_t)sizeof(T), a, d, *temp, &cd);
-  if (st != PH_OK) return st;
-  *out_ptr = reinterpret_cast<const T*>(*temp);
-  return PH_OK;
-}
-
-// one zero-initialised device word (allocated with the flag word by ph_init, so it follows the
-// device); the last block of every fused reduction resets it
-static unsigned int* reduce_ticket() { return rt().d_flags ? rt().d_flags + 8 : nullptr; }
-
-template <typename T>
-static int32_t reduce_full_t(int32_t red, const void* a, const ph_desc* d, void* out_value_dev,
-                             int64_t* out_index_dev) {
-  Runtime& r = rt();
-  const T* x;
-  void* temp;
-  int64_t n;
-  int32_t st = contiguous_input<T>(a, d, &x, &temp, n);
-  if (st != PH_OK) return st;
-  // persistent grid: exactly the blocks that are resident at once (a partial second wave would
-  // leave the GPU mostly idle while it runs), fewer for small inputs
-  static int resident_sum = 0, resident_ext = 0, resident_dev = -1;
-  if (resident_dev != r.device) {
-    resident_dev = r.device;
-    int a = 0, b = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sum_partial_kernel<T, 32 / (int)sizeof(T)>, RED_THREADS, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ext_partial_kernel<T, 32 / (int)sizeof(T), true>, RED_THREADS, 0);
-    resident_sum = std::max(1, a);
-    resident_ext = std::max(1, b);
-  }
-  const int per_sm = (red == PH_SUM) ? resident_sum : resident_ext;
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)r.sm_count * per_sm,
-                                                               ceil_div(n, (int64_t)RED_THREADS * 32)));
-  st = ensure_scratch((size_t)grid * 64 + 256);
-  if (st != PH_OK) return st;
-  int* status = reinterpret_cast<int*>(reinterpret_cast<char*>(r.d_scratch) + (size_t)grid * 64);
-  unsigned int* ticket = reduce_ticket();
-  if (!ticket) return set_error(PH_ERR_CUDA, "cannot allocate the reduction ticket");
-  constexpr int E32 = 32 / (int)sizeof(T);
-  const bool al32 = ((uintptr_t)x % 32) == 0;
-  if (red == PH_SUM) {
-    if (n == 0) {                                         // Enumerable#sum of nothing is T.zero
-      PH_CUDA(cudaMemsetAsync(out_value_dev, 0, sizeof(T), r.stream));
-    } else {
-      SumState<T>* parts = reinterpret_cast<SumState<T>*>(r.d_scratch);
-      static_assert(sizeof(SumState<T>) <= 64, "partial too large");
-      T* ov = reinterpret_cast<T*>(out_value_dev);
-      if (al32) sum_partial_kernel<T, E32><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, ov, status, ticket);
-      else sum_partial_kernel<T, 1><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, ov, status, ticket);
-      PH_LAUNCH_CHECK("sum_partial_kernel");
-      if constexpr (!is_float_t<T>::value) {
-        int* h = reinterpret_cast<int*>(r.h_scratch);
-        PH_CUDA(cudaMemcpyAsync(h, status, sizeof(int), cudaMemcpyDeviceToHost, r.stream));
-        PH_CUDA(cudaStreamSynchronize(r.stream));
-        int code = *h;
-        if (code == 2) {                                  // the filter could not decide: exact ordered pass
-          Prefix<T>* pp = reinterpret_cast<Prefix<T>*>(r.d_scratch);
-          static_assert(sizeof(Prefix<T>) <= 64, "partial too large");
-          sum_exact_kernel<T><<<grid, RED_THREADS, 0, r.stream>>>(x, n, pp);
-          PH_LAUNCH_CHECK("sum_exact_kernel");
-          sum_exact_final_kernel<T><<<1, 32, 0, r.stream>>>(pp, grid, status);
-          PH_LAUNCH_CHECK("sum_exact_final_kernel");
-          PH_CUDA(cudaMemcpyAsync(h, status, sizeof(int), cudaMemcpyDeviceToHost, r.stream));
-          PH_CUDA(cudaStreamSynchronize(r.stream));
-          code = *h;
-        }
-        if (code == 1) {
-          set_flag_kernel<<<1, 1, 0, r.stream>>>(r.d_flags, (uint32_t)PH_FLAG_OVERFLOW);
-          PH_LAUNCH_CHECK("set_flag_kernel");
-        }
-      }
-    }
-    if (out_index_dev) PH_CUDA(cudaMemsetAsync(out_index_dev, 0, 8, r.stream));
-  } else if (red == PH_MIN || red == PH_MAX || red == PH_ARGMIN || red == PH_ARGMAX) {
-    if (n == 0) {                                         // host raises Enumerable::EmptyError
-      PH_CUDA(cudaMemsetAsync(out_value_dev, 0, sizeof(T), r.stream));
-      if (out_index_dev) PH_CUDA(cudaMemsetAsync(out_index_dev, 0xff, 8, r.stream));
-    } else {
-      Cand<T>* parts = reinterpret_cast<Cand<T>*>(r.d_scratch);
-      const bool is_max = (red == PH_MAX || red == PH_ARGMAX);
-      T* ov = reinterpret_cast<T*>(out_value_dev);
-      if (is_max) {
-        if (al32) ext_partial_kernel<T, E32, true><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags, ov, out_index_dev, ticket);
-        else ext_partial_kernel<T, 1, true><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags, ov, out_index_dev, ticket);
-      } else {
-        if (al32) ext_partial_kernel<T, E32, false><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags, ov, out_index_dev, ticket);
-        else ext_partial_kernel<T, 1, false><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags, ov, out_index_dev, ticket);
-      }
-      PH_LAUNCH_CHECK("ext_partial_kernel");
-    }
-  } else {
-    if (temp) cudaFreeAsync(temp, r.stream);
-    return set_error(PH_ERR_INVALID, "unknown reduction %d", red);
-  }
-  if (temp) PH_CUDA(cudaFreeAsync(temp, r.stream));
-  return PH_OK;
-}
-
-template <typename T, int RED>
-static int32_t reduce_axis_launch(const T* x, void* out, int64_t outer, int64_t K, int64_t inner) {
-  Runtime& r = rt();
-  if (inner > 1) {
-    constexpr int E32 = 32 / (int)sizeof(T), E16 = 16 / (int)sizeof(T);
-    constexpr bool ARG = (RED == PH_ARGMAX || RED == PH_ARGMIN);
-    const uintptr_t xa = (uintptr_t)x, oa = (uintptr_t)out;
-    const bool can32 = inner % E32 == 0 && xa % 32 == 0 && (ARG || oa % 32 == 0);
-    const bool can16 = inner % E16 == 0 && xa % 16 == 0 && (ARG || oa % 16 == 0);
-    // Plan = (group width E, groups in flight per thread U, block size), measured on the axis-0
-    // shards of the 1e9-element f32 array ([1000/N, 1000, 1000], benchmarks/probe_axis.py):
-    //   * outer == 1 (the reduced axis is the leading one; consecutive k are `inner` apart): the widest
-    //     group with 4 in flight streams at 6.4-7.1 TB/s down to [125, 1000, 1000];
-    //   * outer > 1 (a middle axis: every `outer` index is its own K x inner panel): with many columns the
-    //     widest group wins, 8 in flight in 128-thread blocks (6.8 TB/s, argmax 6.5 -> 6.75); with few
-    //     columns only MORE THREADS keep the memory system busy -- 32-byte groups leave 15 625 threads on
-    //     [125, 1000, 1000] and reach 2.1 TB/s however deep the unrolling, scalar columns 5.4 TB/s.
-    const int64_t cols = outer * inner;
-    const int64_t col_bytes = cols * (int64_t)sizeof(T);
-    int e = 1, u = 4, block = RED_THREADS;
-    if (outer == 1) {
-      if (can32 && E32 > 1 && cols / E32 >= (int64_t)r.sm_count * 64) e = E32;
-      else if (can16 && E16 > 1 && cols / E16 >= (int64_t)r.sm_count * 64) e = E16;
-      u = col_bytes * 4 >= (6LL << 20) ? 4 : 16;
-    } else if (col_bytes >= (3LL << 20) && can32 && E32 > 1) {
-      e = E32; u = 8; block = 128;
-    } else if (col_bytes >= (3LL << 19) && can32 && E32 > 1) {
-      e = E32; u = 4;
-    } else if (ARG && col_bytes >= (3LL << 18) && can16 && E16 > 1) {
-      e = E16; u = 8;
-    } else {
-      e = 1; u = (!ARG && col_bytes >= (3LL << 18)) ? 4 : 16;
-    }
-    static const int force_e = getenv("PH_AXIS_E") ? atoi(getenv("PH_AXIS_E")) : 0;       // tuning knobs
-    static const int force_u = getenv("PH_AXIS_U") ? atoi(getenv("PH_AXIS_U")) : 0;
-    static const int force_b = getenv("PH_AXIS_BLOCK") ? atoi(getenv("PH_AXIS_BLOCK")) : 0;
-    if (force_e == 32 && can32 && E32 > 1) e = E32;
-    else if (force_e == 16 && can16 && E16 > 1) e = E16;
-    else if (force_e == 1) e = 1;
-    if (force_u) u = force_u;
-    if (sizeof(T) < 4 && u > 8) u = 8;                       // 32 one-byte accumulators + 16 groups would spill
-    const int64_t threads = cols / e;
-    if (force_b) block = force_b;
-    const int64_t blocks = ceil_div(threads, (int64_t)block);
-    if (blocks > 0x7fffffffLL) return set_error(PH_ERR_INVALID, "array too large for one launch");
-#define PH_STRIP(EE, UU) axis_strip_kernel<T, EE, RED, UU><<<(unsigned)blocks, block, 0, r.stream>>>(x, out, outer, K, inner, r.d_flags)
-    if (e == E32 && E32 > 1) { if (u >= 16) PH_STRIP(E32, 16); else if (u >= 8) PH_STRIP(E32, 8); else PH_STRIP(E32, 4); }
-    else if (e == E16 && E16 > 1) { if (u >= 8) PH_STRIP(E16, 8); else PH_STRIP(E16, 4); }
-    else { if (u >= 16) PH_STRIP(1, 16); else PH_STRIP(1, 4); }
-#undef PH_STRIP
-    PH_LAUNCH_CHECK("axis_strip_kernel");
-    return PH_OK;
-  }
-  // last axis: rows of K contiguous elements
-  constexpr int E32 = 32 / (int)sizeof(T);
-  const bool vec = E32 > 1 && K % E32 == 0 && ((uintptr_t)x % 32) == 0;
-  const int e = vec ? E32 : 1;
-  const int64_t groups = K / e;
-  if (vec && groups <= 32 * 8) {                  // the row fits the registers of one warp
-    const int G = groups <= 32 * 4 ? 4 : 8;
-    int tx = 1, lg = 0;
-    while (tx < 32 && (int64_t)tx * G < groups) { tx <<= 1; lg++; }
-    const int64_t blocks = ceil_div(outer, (int64_t)(RED_THREADS / tx));
-    if (blocks > 0x7fffffffLL) return set_error(PH_ERR_INVALID, "array too large for one launch");
-    if (G == 4) axis_rowreg_kernel<T, E32, 4, RED><<<(unsigned)blocks, RED_THREADS, 0, r.stream>>>(x, out, outer, K, lg, r.d_flags);
-    else axis_rowreg_kernel<T, E32, 8, RED><<<(unsigned)blocks, RED_THREADS, 0, r.stream>>>(x, out, outer, K, lg, r.d_flags);
-    PH_LAUNCH_CHECK("axis_rowreg_kernel");
-    return PH_OK;
-  }
-  int tx = 1, lg = 0;
-  while (tx < RED_THREADS && (int64_t)tx * 8 < groups) { tx <<= 1; lg++; }   // <= 8 groups per lane
-  const int ty = RED_THREADS / tx;
-  const int64_t blocks = ceil_div(outer, ty);
-  if (blocks > 0x7fffffffLL) return set_error(PH_ERR_INVALID, "array too large for one launch");
-  if (vec) axis_row_kernel<T, E32, RED><<<(unsigned)blocks, RED_THREADS, 0, r.stream>>>(x, out, outer, K, tx, lg, r.d_flags);
-  else axis_row_kernel<T, 1, RED><<<(unsigned)blocks, RED_THREADS, 0, r.stream>>>(x, out, outer, K, tx, lg, r.d_flags);
-  PH_LAUNCH_CHECK("axis_row_kernel");
-  return PH_OK;
-}
-
-template <typename T>
-static int32_t reduce_axis_t(int32_t red, const void* a, const ph_desc* d, int32_t axis, void* out,
-                             const ph_desc* od) {
-  Runtime& r = rt();
-  if (axis < 0 || axis >= d->rank) return set_error(PH_ERR_INVALID, "axis %d out of range for rank %d", axis, d->rank);
-  int64_t ototal;
-  if (!od || !desc_is_contiguous(od, ototal) )
-    return set_error(PH_ERR_UNSUPPORTED, "ph_reduce_axis writes a contiguous output");
-  const T* x;
-  void* temp;
-  int64_t n;
-  int32_t st = contiguous_input<T>(a, d, &x, &temp, n);
-  if (st != PH_OK) return st;
-  int64_t outer = 1, inner = 1;
-  const int64_t K = d->extent[axis];
-  for (int i = 0; i < axis; i++) outer *= d->extent[i];
-  for (int i = axis + 1; i < d->rank; i++) inner *= d->extent[i];
-  if (outer * inner == 0 || K == 0) { if (temp) cudaFreeAsync(temp, r.stream); return PH_OK; }
-  const bool arg = (red == PH_ARGMAX || red == PH_ARGMIN);
-  void* o = arg ? (void*)(reinterpret_cast<int64_t*>(out) + od->offset) : (void*)(reinterpret_cast<T*>(out) + od->offset);
-  switch (red) {
-    case PH_SUM: st = reduce_axis_launch<T, PH_SUM>(x, o, outer, K, inner); break;
-    case PH_MIN: st = reduce_axis_launch<T, PH_MIN>(x, o, outer, K, inner); break;
-    case PH_MAX: st = reduce_axis_launch<T, PH_MAX>(x, o, outer, K, inner); break;
-    case PH_ARGMAX: st = reduce_axis_launch<T, PH_ARGMAX>(x, o, outer, K, inner); break;
-    case PH_ARGMIN: st = reduce_axis_launch<T, PH_ARGMIN>(x, o, outer, K, inner); break;
-    default: st = set_error(PH_ERR_INVALID, "unknown reduction %d", red);
-  }
-  if (temp) cudaFreeAsync(temp, r.stream);
-  return st;
-}
-
+int32_t reduce_axis_t(int32_t red, const void* a, const ph_desc* d, int32_t axis, void* out, const ph_desc* od);
 }  // namespace ph
 
 using namespace ph;
