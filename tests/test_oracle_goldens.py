@@ -544,3 +544,38 @@ def test_c_port_heat_and_sum_match_the_numpy_oracle():
         acc = np.float32(acc + v)                                    # Enumerable#sum: left fold in T
     assert CO.ref_sum_f32(x[:2000].copy()) == acc
     assert abs(CO.flat_sum_f32(x) - float(x.astype(np.float64).sum())) < 1e-6 * x.size
+
+
+def test_powi_is_pinned_to_an_independent_runtime_implementation(tmp_path):
+    """`Float ** Int32` lowers to llvm.powi, i.e. compiler-rt's __powisf2 / __powidf2.  Neither
+    Crystal nor compiler-rt is in this image; libgcc's __powisf2 / __powidf2 (reached through gcc's
+    __builtin_powi) are an INDEPENDENT implementation of the same published square-and-multiply order
+    (odd exponent bits multiply the running square into the result, 1 / r at the end for n < 0).  The
+    oracle's restatement must agree with it bit for bit."""
+    import ctypes
+    import subprocess
+    src = tmp_path / "powi_ref.c"
+    src.write_text("double powi_f64(double x, int n) { return __builtin_powi(x, n); }\n"
+                   "float powi_f32(float x, int n) { return __builtin_powif(x, n); }\n")
+    lib_path = tmp_path / "libpowi_ref.so"
+    subprocess.run(["gcc", "-O1", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC", "-o", str(lib_path), str(src)], check=True)
+    nm = subprocess.run(["nm", str(lib_path)], capture_output=True, text=True).stdout         # libgcc.a links them statically
+    assert "__powidf2" in nm and "__powisf2" in nm                 # really the runtime routine, not an inlined pow()
+    lib = ctypes.CDLL(str(lib_path))
+    lib.powi_f64.restype, lib.powi_f64.argtypes = ctypes.c_double, [ctypes.c_double, ctypes.c_int]
+    lib.powi_f32.restype, lib.powi_f32.argtypes = ctypes.c_float, [ctypes.c_float, ctypes.c_int]
+    rs = np.random.RandomState(31)
+    xs64 = np.concatenate([rs.randn(200) * 3, [0.0, -0.0, 1.0, -1.0, 0.05, 1e-160, -1e160, 5e-324, np.inf, -np.inf, np.nan]])
+    exps = [0, 1, 2, 3, 4, 5, 7, 10, 13, 31, 64, 255, 1000, -1, -2, -3, -7, -64, 2 ** 31 - 1, -(2 ** 31) + 1]
+    for n in exps:
+        got64 = O._powi(xs64.astype(np.float64), n)
+        want64 = np.array([lib.powi_f64(float(x), n) for x in xs64], dtype=np.float64)
+        assert np.array_equal(np.isnan(got64), np.isnan(want64))
+        assert got64[~np.isnan(got64)].tobytes() == want64[~np.isnan(want64)].tobytes(), f"f64 ** {n}"
+        xs32 = xs64.astype(np.float32)
+        got32 = O._powi(xs32, n)
+        want32 = np.array([lib.powi_f32(float(x), n) for x in xs32], dtype=np.float32)
+        assert np.array_equal(np.isnan(got32), np.isnan(want32))
+        assert got32[~np.isnan(got32)].tobytes() == want32[~np.isnan(want32)].tobytes(), f"f32 ** {n}"
+    # the example's constant: SPACING ** 2 with Float64 ** Int32 (examples/heat_equation.cr:20)
+    assert lib.powi_f64(0.05, 2) == 0.05 * 0.05 == float(O._powi(np.array(0.05), 2))
