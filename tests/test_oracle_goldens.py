@@ -579,3 +579,75 @@ def test_powi_is_pinned_to_an_independent_runtime_implementation(tmp_path):
         assert got32[~np.isnan(got32)].tobytes() == want32[~np.isnan(want32)].tobytes(), f"f32 ** {n}"
     # the example's constant: SPACING ** 2 with Float64 ** Int32 (examples/heat_equation.cr:20)
     assert lib.powi_f64(0.05, 2) == 0.05 * 0.05 == float(O._powi(np.array(0.05), 2))
+
+
+@pytest.mark.parametrize("dtype", [np.int8, np.int16, np.int32, np.int64, np.uint8, np.uint16, np.uint32, np.uint64])
+def test_integer_semantics_against_exact_arithmetic(dtype):
+    """Crystal's integer operators restated INDEPENDENTLY with Python's unbounded integers: `+ - *` are exact
+    or raise OverflowError; `&+ &- &*` wrap modulo 2^bits; `//` and `%` are floored (the sign of the divisor),
+    x // 0 and x % 0 raise DivisionByZeroError, MIN // -1 raises ArgumentError; `**` is exact or overflows,
+    `&**` wraps, a negative exponent raises ArgumentError.  The oracle's numpy restatement must agree
+    element by element: value (as wrapped) and the set of errors."""
+    info = np.iinfo(dtype)
+    bits = info.bits
+    lo, hi = int(info.min), int(info.max)
+
+    def wrap(v):
+        v &= (1 << bits) - 1
+        return v - (1 << bits) if (lo < 0 and v > hi) else v
+
+    rs = np.random.RandomState(bits + (1 if lo < 0 else 0))
+    edge = [lo, lo + 1, hi, hi - 1, 0, 1, 2, 3, 7, hi // 2, hi // 2 + 1] + ([-1, -2, -3, lo // 2] if lo < 0 else [])
+    pool = edge + [int(v) for v in rs.randint(max(lo, -1000), min(hi, 1000) + 1, size=40)]
+    pairs = [(x, y) for x in pool for y in edge + pool[-8:]]
+
+    def check(op, model):
+        # one element at a time so the error set is per element
+        for (x, y) in pairs[:: max(1, len(pairs) // 400)]:
+            r, flags = O.ewise(op, np.array([x], dtype), np.array([y], dtype))
+            want_v, want_f = model(x, y)
+            assert flags == want_f, f"{np.dtype(dtype)} {x} {op} {y}: flags {flags} != {want_f}"
+            if want_v is not None and not want_f:
+                assert int(r[0]) == want_v, f"{np.dtype(dtype)} {x} {op} {y}: {int(r[0])} != {want_v}"
+
+    def exact(fn):
+        def model(x, y):
+            v = fn(x, y)
+            return (v, set()) if lo <= v <= hi else (None, {"overflow"})
+        return model
+
+    check("+", exact(lambda x, y: x + y))
+    check("-", exact(lambda x, y: x - y))
+    check("*", exact(lambda x, y: x * y))
+    check("&+", lambda x, y: (wrap(x + y), set()))
+    check("&-", lambda x, y: (wrap(x - y), set()))
+    check("&*", lambda x, y: (wrap(x * y), set()))
+
+    def floordiv(x, y):
+        if y == 0:
+            return None, {"div0"}
+        if lo < 0 and x == lo and y == -1:
+            return None, {"argument"}
+        return x // y, set()
+
+    def mod(x, y):
+        if y == 0:
+            return None, {"div0"}
+        return x % y, set()                                            # Python's % is floored, like Crystal's
+
+    check("//", floordiv)
+    check("%", mod)
+    for base in [0, 1, 2, 3, 7, 10] + ([-1, -2, -3] if lo < 0 else []):
+        for e in [0, 1, 2, 3, 5, 7, 8, 15, 16, 31, 32, 63, 64] + ([-1] if lo < 0 else []):
+            if not (lo <= e <= hi):
+                continue
+            r, flags = O.ewise("**", np.array([base], dtype), np.array([e], dtype))
+            if e < 0:
+                assert flags == {"argument"}
+                continue
+            v = base ** e
+            assert flags == (set() if lo <= v <= hi else {"overflow"}), f"{base} ** {e}"
+            if not flags:
+                assert int(r[0]) == v
+            r, flags = O.ewise("&**", np.array([base], dtype), np.array([e], dtype))
+            assert not flags and int(r[0]) == wrap(v), f"{base} &** {e}"
