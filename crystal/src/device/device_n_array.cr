@@ -96,8 +96,8 @@ module Phase
       DeviceNArray(T).new(new_shape, @dev)
     end
 
-    def reshape(*new_shape : Int) : self
-      reshape(new_shape)
+    def reshape(first : Int, *rest : Int) : self
+      reshape([first.to_i32] + rest.map(&.to_i32).to_a)
     end
 
     def flatten : self
@@ -109,8 +109,8 @@ module Phase
       view.permute(order).to_narr
     end
 
-    def permute(*order : Int) : DeviceNArray(T)
-      permute(order)
+    def permute(first : Int, *rest : Int) : DeviceNArray(T)
+      permute([first.to_i32] + rest.map(&.to_i32).to_a)
     end
 
     def reverse : DeviceNArray(T)

@@ -84,9 +84,11 @@ module Phase
       clone.permute!(order)
     end
 
+    # Splat forms (`view.permute(1, 0, 2)`); at least one argument, so that a bare `permute`
+    # always means "reverse the axes".
     {% for name in {"permute", "permute!", "reshape", "reshape!"} %}
-      def {{name.id}}(*args : Int)
-        {{name.id}}(args)
+      def {{name.id}}(first : Int, *rest : Int)
+        {{name.id}}([first.to_i32] + rest.map(&.to_i32).to_a)
       end
     {% end %}
 
