@@ -149,16 +149,16 @@ module Phase
       region ? v.view(region) : v
     end
 
-    def view(*region) : DeviceView(T)
-      view(region.to_a)
+    def view(first, *rest) : DeviceView(T)
+      view([first] + rest.to_a)
     end
 
     def mutable_view(region = nil) : DeviceView(T)
       view(region)
     end
 
-    def mutable_view(*region) : DeviceView(T)
-      view(region.to_a)
+    def mutable_view(first, *rest) : DeviceView(T)
+      view([first] + rest.to_a)
     end
 
     # ---- elementwise operators: the same list as MultiIndexable's def_elementwise_binary ----
