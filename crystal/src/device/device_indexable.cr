@@ -149,7 +149,7 @@ module Phase
       region ? v.view(region) : v
     end
 
-    def view(first, *rest) : DeviceView(T)
+    def view(first : Int | Range, *rest) : DeviceView(T)
       view([first] + rest.to_a)
     end
 
@@ -157,7 +157,7 @@ module Phase
       view(region)
     end
 
-    def mutable_view(first, *rest) : DeviceView(T)
+    def mutable_view(first : Int | Range, *rest) : DeviceView(T)
       view([first] + rest.to_a)
     end
 
