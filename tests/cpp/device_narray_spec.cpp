@@ -119,6 +119,46 @@ static void host_specs() {
   });
 }
 
+// The partition plans of the multi-GPU path, called from a compiled host (ph_host.h); no reference counterpart.
+static void partition_host_specs() {
+  it("shard ranges, slab layout, cross-shard transpose plan, extremum records (SURVEY.md 8(e), f-3)", [] {
+    int64_t a = 0, b = 0, covered = 0;
+    for (int r = 0; r < 3; r++) {                       // 10 rows over 3 ranks: 4 + 3 + 3, contiguous
+      EXPECT(ph_shard_range(10, 3, r, &a, &b) == PH_HOST_OK && a == covered && b - a == (r == 0 ? 4 : 3));
+      covered = b;
+    }
+    EXPECT(covered == 10);
+    ph_slab slab;
+    EXPECT(ph_slab_layout(2048, 8, 0, 2, &slab) == PH_HOST_OK && slab.count == 256 && slab.local_planes == 260 &&
+           slab.lo_rank == -1 && slab.hi_rank == 1);
+    EXPECT(ph_slab_layout(2048, 8, 7, 2, &slab) == PH_HOST_OK && slab.start == 1792 && slab.lo_rank == 6 && slab.hi_rank == -1);
+    // [6, 4] transposed over 2 ranks: rank 0 owns rows 0..2, keeps new rows 0..1
+    const int64_t shape[2] = {6, 4};
+    const int32_t pattern[2] = {1, 0};
+    ph_transpose_plan plan;
+    ph_transpose_peer peers[2];
+    EXPECT(ph_transpose_plan_of(shape, 2, pattern, 2, 0, &plan, peers) == PH_HOST_OK && !plan.local && plan.k == 1 && plan.j == 1);
+    EXPECT(plan.new_shape[0] == 4 && plan.new_shape[1] == 6 && plan.my_rows[1] == 3 && plan.my_new_rows[1] == 2);
+    EXPECT(peers[1].send0 == 2 && peers[1].send1 == 4 && peers[1].send_shape[0] == 2 && peers[1].send_shape[1] == 3);
+    EXPECT(peers[1].recv0 == 3 && peers[1].recv1 == 6 && peers[1].recv_shape[0] == 2 && peers[1].recv_shape[1] == 3);
+    const int32_t same[2] = {0, 1}, bad[2] = {1, 1};
+    EXPECT(ph_transpose_plan_of(shape, 2, same, 2, 0, &plan, peers) == PH_HOST_OK && plan.local);
+    EXPECT(ph_transpose_plan_of(shape, 2, bad, 2, 0, &plan, peers) == PH_HOST_INDEX_ERROR);
+    // three shards: a tie between ranks 0 and 2 goes to the lower GLOBAL index, an empty shard is skipped
+    uint8_t recs[3 * PH_EXTREMUM_RECORD_BYTES] = {0};
+    auto put = [&](int r, float v, int64_t local, int64_t offset) {
+      std::memcpy(recs + r * PH_EXTREMUM_RECORD_BYTES, &v, 4);
+      std::memcpy(recs + r * PH_EXTREMUM_RECORD_BYTES + 16, &local, 8);
+      std::memcpy(recs + r * PH_EXTREMUM_RECORD_BYTES + 24, &offset, 8);
+    };
+    put(0, 9.0f, 7, 0); put(1, 99.0f, -1, 10); put(2, 9.0f, 1, 10);
+    int32_t winner = -5; int64_t gidx = -5;
+    EXPECT(ph_combine_extremum_records(recs, 3, PH_F32, 1, &winner, &gidx) == PH_HOST_OK && winner == 0 && gidx == 7);
+    put(0, 9.0f, 12, 0);
+    EXPECT(ph_combine_extremum_records(recs, 3, PH_F32, 1, &winner, &gidx) == PH_HOST_OK && winner == 2 && gidx == 11);
+  });
+}
+
 // JSON / YAML goldens of spec/n_array_spec.cr:520-558 and the binary dump, host side only
 static void io_host_specs() {
   it("to_json / from_json / to_yaml / from_yaml goldens (n_array_spec.cr:520-558)", [] {
@@ -187,6 +227,7 @@ int main(int argc, char** argv) {
   if (argc > 1 && std::strcmp(argv[1], "--host-only") == 0) {
     host_specs();
     io_host_specs();
+    partition_host_specs();
     std::printf("%d expectations passed, %d failed (host-only)\n", g_passed, g_failed);
     return g_failed ? 1 : 0;
   }
@@ -198,6 +239,7 @@ int main(int argc, char** argv) {
 
   host_specs();
   io_host_specs();
+  partition_host_specs();
 
   // Written after the round's last GPU minute was spent: opt-in until it has run on a device once
   // (PH_SPEC_DEVICE_IO=1); its host half (io_host_specs) is part of every run.
