@@ -7,6 +7,9 @@ module Phase
   # the chain folds into (offset, extent[], stride[]) as it is built and a read is one gather, a
   # write one scatter. Reshape folds when strides can express it and materialises otherwise.
   # It is both `View` and `MutableView`: writes go through to the source.
+  #
+  # Every transform is a pure function from one (buffer, descriptor, shape) triple to the next;
+  # the `!` forms of the reference's API adopt the transformed triple in place.
   class DeviceView(T)
     include DeviceIndexable(T) # brings MultiIndexable::Mutable(T) with it
 
@@ -21,67 +24,80 @@ module Phase
       @shape
     end
 
-    def clone : self
-      DeviceView(T).new(@dev, @desc, @shape.clone)
+    private def derive(desc : LibPhGpu::Desc, shape : Array(Int32), dev : DeviceBuffer = @dev) : DeviceView(T)
+      DeviceView(T).new(dev, desc, shape)
     end
 
+    protected def adopt(other : DeviceView(T)) : self
+      @dev, @desc, @shape = other.dev, other.desc, other.shape_internal
+      self
+    end
+
+    def clone : self
+      derive(@desc, @shape.dup)
+    end
+
+    # ---- restriction to a region (`View#view`, `RegionTransform`)
     def view(region = nil) : DeviceView(T)
-      new_view = clone
-      new_view.restrict_to(region) if region
-      new_view
+      case region
+      when Nil         then clone
+      when IndexRegion then derive(region.to_descriptor(@desc), region.shape)
+      else
+        canonical = IndexRegion.new(region, @shape)
+        derive(canonical.to_descriptor(@desc), canonical.shape)
+      end
     end
 
     def mutable_view(region = nil) : DeviceView(T)
       view(region)
     end
 
-    protected def restrict_to(region : Enumerable) : self
-      restrict_to(IndexRegion.new(region, @shape))
-    end
-
-    protected def restrict_to(region : IndexRegion) : self
-      @desc = region.to_descriptor(@desc)
-      @shape = region.shape
-      self
-    end
-
-    # A chunk of a view is a view, like `View#unsafe_fetch_chunk`.
+    # A chunk of a view is again a view (`View#unsafe_fetch_chunk`), nothing is copied.
     def unsafe_fetch_chunk(region : IndexRegion) : DeviceView(T)
       view(region)
     end
 
-    def reshape!(new_shape) : self
-      new_shape = new_shape.map(&.to_i32).to_a
-      if ShapeUtil.shape_to_size(new_shape) != size
-        raise ShapeError.new("Cannot change shape from #{@shape.join('x')} (#{size} elements) to #{new_shape.join('x')} (#{ShapeUtil.shape_to_size(new_shape)} elements) because reshape cannot add or remove elements.")
+    # ---- `PermuteTransform`: output axis i is source axis order[i]; no order = reversed axes
+    def permute(order : Enumerable? = nil) : DeviceView(T)
+      axes = order.try &.map(&.to_i32).to_a
+      if axes && (stray = axes.find { |axis| !(0 <= axis < @shape.size) })
+        raise IndexError.new("Could not use pattern #{axes} to permute: Axis #{stray} is not present in a #{dimensions}-dimensional MultiIndexable")
       end
-      if folded = Descriptor.reshape(@desc, new_shape)
-        @desc = folded
-      else
-        copy = to_narr # not expressible in strides: materialise, then reshape the copy
-        @dev = copy.dev
-        @desc = Descriptor.contiguous(new_shape)
-      end
-      @shape = new_shape
-      self
-    end
-
-    def reshape(new_shape) : self
-      clone.reshape!(new_shape)
+      moved = Descriptor.permute(@desc, axes)
+      extents = moved.extent
+      derive(moved, Array(Int32).new(moved.rank) { |i| extents[i].to_i32 })
     end
 
     def permute!(order : Enumerable? = nil) : self
-      if order && (bad_axis = order.find { |axis| axis < 0 || axis >= @shape.size })
-        raise IndexError.new("Could not use pattern #{order} to permute: Axis #{bad_axis} is not present in a #{dimensions}-dimensional MultiIndexable")
-      end
-      @desc = Descriptor.permute(@desc, order.try &.to_a)
-      extent = @desc.extent
-      @shape = Array(Int32).new(@desc.rank) { |i| extent[i].to_i32 }
-      self
+      adopt permute(order)
     end
 
-    def permute(order : Enumerable? = nil) : self
-      clone.permute!(order)
+    # ---- `ReverseTransform`: every axis flipped
+    def reverse : DeviceView(T)
+      derive(Descriptor.reverse(@desc), @shape.dup)
+    end
+
+    def reverse! : self
+      adopt reverse
+    end
+
+    # ---- `ReshapeTransform`: in strides when the new axes subdivide contiguous runs, else through a copy
+    def reshape(new_shape : Enumerable) : DeviceView(T)
+      target = new_shape.map(&.to_i32).to_a
+      wanted = Descriptor.element_count(target)
+      if wanted != size
+        raise ShapeError.new("Cannot change shape from #{@shape.join('x')} (#{size} elements) to #{target.join('x')} (#{wanted} elements) because reshape cannot add or remove elements.")
+      end
+      if folded = Descriptor.reshape(@desc, target)
+        derive(folded, target)
+      else
+        copy = to_narr
+        derive(Descriptor.contiguous(target), target, copy.dev)
+      end
+    end
+
+    def reshape!(new_shape : Enumerable) : self
+      adopt reshape(new_shape)
     end
 
     # Splat forms (`view.permute(1, 0, 2)`); at least one argument, so that a bare `permute`
@@ -91,14 +107,5 @@ module Phase
         {{name.id}}([first.to_i32] + rest.map(&.to_i32).to_a)
       end
     {% end %}
-
-    def reverse! : self
-      @desc = Descriptor.reverse(@desc)
-      self
-    end
-
-    def reverse : self
-      clone.reverse!
-    end
   end
 end
