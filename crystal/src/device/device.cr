@@ -35,8 +35,22 @@ module Phase
       raise RuntimeError.new("libphgpu status #{status}: #{String.new(LibPhGpu.ph_last_error_string)}")
     end
 
+    # Wait for every launched operator. A guaranteed raise point: the flag word comes back in the
+    # same synchronisation (`ph_d2h_flags` with nothing to copy).
     def self.sync : Nil
+      read_checked(Pointer(Void).null, Pointer(Void).null, LibC::SizeT.new(0))
+    end
+
+    # Internal wait that never raises (keeps a host temporary alive until it is copied).
+    def self.wait : Nil
       check LibPhGpu.ph_sync
+    end
+
+    # Every synchronising READ is a raise point: `(a + b).to_host` raises OverflowError like
+    # `a + b` does on the CPU path (`Int32#+`), without an explicit `raise_pending`.
+    def self.read_checked(dst_host : Void*, src_dev : Void*, nbytes : LibC::SizeT) : Nil
+      check LibPhGpu.ph_d2h_flags(dst_host, src_dev, nbytes, out flags)
+      raise_for(flags)
     end
 
     def self.take_flags : UInt32
@@ -48,7 +62,10 @@ module Phase
     # clears it and raises the class the CPU path would have raised at the offending element
     # (Int32#+ -> OverflowError, Int#// -> DivisionByZeroError, Enumerable#max on NaN -> ArgumentError).
     def self.raise_pending : Nil
-      flags = take_flags
+      raise_for(take_flags)
+    end
+
+    def self.raise_for(flags : UInt32) : Nil
       raise DivisionByZeroError.new if flags & LibPhGpu::FLAG_DIV0 != 0
       raise OverflowError.new if flags & LibPhGpu::FLAG_OVERFLOW != 0
       raise ArgumentError.new("Overflow: Int::MIN // -1, or a negative integer exponent") if flags & LibPhGpu::FLAG_ARGUMENT != 0

@@ -51,14 +51,14 @@ module Phase
     def unsafe_fetch_element(coord : Indexable) : T
       value = uninitialized T
       offset = Descriptor.offset_of(desc, coord)
-      Device.check LibPhGpu.ph_d2h(pointerof(value).as(Void*), (dev.ptr.as(T*) + offset).as(Void*), LibC::SizeT.new(sizeof(T)))
+      Device.read_checked(pointerof(value).as(Void*), (dev.ptr.as(T*) + offset).as(Void*), LibC::SizeT.new(sizeof(T)))
       value
     end
 
     def unsafe_set_element(coord : Indexable, value : T)
       offset = Descriptor.offset_of(desc, coord)
       Device.check LibPhGpu.ph_h2d((dev.ptr.as(T*) + offset).as(Void*), pointerof(value).as(Void*), LibC::SizeT.new(sizeof(T)))
-      Device.sync # `value` lives on this stack frame
+      Device.wait # `value` lives on this stack frame
     end
 
     # ---- gather: one launch ---------------------------------------------------------------
@@ -85,7 +85,7 @@ module Phase
     def to_host : NArray(T)
       flat = to_narr
       slice = Slice(T).new(flat.size.to_i32) # NArray counts in Int32: raises OverflowError beyond that
-      Device.check LibPhGpu.ph_d2h(slice.to_unsafe.as(Void*), flat.dev.ptr, LibC::SizeT.new(slice.bytesize)) if slice.size > 0
+      Device.read_checked(slice.to_unsafe.as(Void*), flat.dev.ptr, LibC::SizeT.new(slice.bytesize)) # a raise point
       NArray.of_buffer(shape_internal.clone, slice)
     end
 

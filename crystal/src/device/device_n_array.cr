@@ -49,7 +49,7 @@ module Phase
       result = new(src.shape)
       if result.size > 0
         Device.check LibPhGpu.ph_h2d(result.dev.ptr, src.buffer.to_unsafe.as(Void*), LibC::SizeT.new(src.buffer.bytesize))
-        Device.sync # the GC may free `src` as soon as we return
+        Device.wait # the GC may free `src` as soon as we return
       end
       result
     end

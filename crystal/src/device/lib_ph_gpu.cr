@@ -98,6 +98,7 @@ lib LibPhGpu
   fun ph_free(dev : Void*) : Int32
   fun ph_h2d(dst_dev : Void*, src_host : Void*, nbytes : LibC::SizeT) : Int32
   fun ph_d2h(dst_host : Void*, src_dev : Void*, nbytes : LibC::SizeT) : Int32
+  fun ph_d2h_flags(dst_host : Void*, src_dev : Void*, nbytes : LibC::SizeT, out_flags : UInt32*) : Int32
   fun ph_d2h_async(dst_host : Void*, src_dev : Void*, nbytes : LibC::SizeT) : Int32
   fun ph_d2d(dst_dev : Void*, src_dev : Void*, nbytes : LibC::SizeT) : Int32
   fun ph_host_alloc(nbytes : LibC::SizeT, out_host : Void**) : Int32

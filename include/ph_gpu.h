@@ -119,6 +119,10 @@ int32_t ph_alloc(size_t nbytes, void** out_dev);     /* stream-ordered pool allo
 int32_t ph_free(void* dev);
 int32_t ph_h2d(void* dst_dev, const void* src_host, size_t nbytes);
 int32_t ph_d2h(void* dst_host, const void* src_dev, size_t nbytes);   /* synchronises */
+/* ph_d2h + ph_take_arith_flags in one synchronisation: what `to_host` / `get` call, so an
+ * OverflowError / DivisionByZeroError of any earlier operator is raised by the read that would
+ * hand its result to the caller (the reference raises at the operator itself). */
+int32_t ph_d2h_flags(void* dst_host, const void* src_dev, size_t nbytes, uint32_t* out_flags);
 int32_t ph_d2h_async(void* dst_host, const void* src_dev, size_t nbytes); /* pinned dst; ph_sync before reading */
 int32_t ph_d2d(void* dst_dev, const void* src_dev, size_t nbytes);    /* NArray#clone */
 int32_t ph_host_alloc(size_t nbytes, void** out_host);  /* pinned staging memory */

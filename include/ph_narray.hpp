@@ -90,17 +90,25 @@ inline bool& initialised() { static bool v = false; return v; }
 inline void init(int32_t device = 0) { check(ph_init(device)); initialised() = true; }
 inline void ensure_init() { if (!initialised()) init(0); }
 inline void shutdown() { if (initialised()) { ph_shutdown(); initialised() = false; } }
-inline void sync() { check(ph_sync()); }
+inline void wait() { check(ph_sync()); }    // internal: keep a host temporary alive until it is copied; never raises
 inline uint32_t take_flags() { uint32_t f = 0; check(ph_take_arith_flags(&f)); return f; }
 // Data-dependent errors come back as a flag word after the stream sync and are re-raised as
 // the classes the CPU path raises.
-inline void raise_pending() {
-  uint32_t f = take_flags();
+inline void raise_for(uint32_t f) {
   if (f & PH_FLAG_DIV0) throw DivisionByZeroError("Division by 0");
   if (f & PH_FLAG_OVERFLOW) throw OverflowError("Arithmetic overflow");
   if (f & PH_FLAG_ARGUMENT) throw ArgumentError("invalid integer argument (MIN // -1 or negative exponent)");
   if (f & PH_FLAG_NAN) throw ArgumentError("Comparison of NaN failed");
 }
+inline void raise_pending() { raise_for(take_flags()); }
+// Every synchronising READ is a raise point: the copy and the flag word come back in one
+// synchronisation (ph_d2h_flags), so `(a + b).to_host()` raises OverflowError like `a + b` does on the CPU.
+inline void read_checked(void* dst_host, const void* src_dev, size_t nbytes) {
+  uint32_t f = 0;
+  check(ph_d2h_flags(dst_host, src_dev, nbytes, &f));
+  raise_for(f);
+}
+inline void sync() { read_checked(nullptr, nullptr, 0); }
 }  // namespace Device
 
 // ---- region literals (range_syntax.cr:41-69).  Crystal writes a..b, a...b, a..s..b, `..`; here:
@@ -276,7 +284,7 @@ class MultiIndexable {
   // one element; legal but slow (one tiny D2H) -- the conformance tester enumerates coordinates
   T get(const Coord& coord) const {                                                     // :567-575
     T out;
-    Device::check(ph_d2h(&out, data() + offset_of(coord), sizeof(T)));
+    Device::read_checked(&out, data() + offset_of(coord), sizeof(T));
     return out;
   }
   T get_element(const Coord& coord) const { return get(coord); }
@@ -288,7 +296,7 @@ class MultiIndexable {
   // ---- scatter / fill (multi_writable.cr:55-84 -> n_array.cr:484-500) ------------------------
   void set_element(const Coord& coord, T value) {
     Device::check(ph_h2d(data() + offset_of(coord), &value, sizeof(T)));
-    Device::sync();   // `value` is a stack temporary
+    Device::wait();   // `value` is a stack temporary
   }
   void set_chunk(const RegionLiteral& lits, const MultiIndexable<T>& src) { set_chunk(IndexRegion(lits, shape_), src); }
   void set_chunk(const RegionLiteral& lits, type_identity_t<T> value) { unsafe_set_chunk(IndexRegion(lits, shape_), value); }
@@ -439,7 +447,7 @@ class DeviceNArray : public MultiIndexable<T> {
     DeviceNArray out(shape);
     if (out.size()) {
       Device::check(ph_h2d(out.data(), host, (size_t)out.size() * sizeof(T)));
-      Device::sync();   // a pageable source must stay alive until copied
+      Device::wait();   // a pageable source must stay alive until copied
     }
     return out;
   }
@@ -551,7 +559,7 @@ template <class T>
 std::vector<T> MultiIndexable<T>::to_host() const {
   DeviceNArray<T> flat = to_narr();   // one gather; a whole contiguous array takes the flat copy kernel
   std::vector<T> out((size_t)flat.size());
-  if (!out.empty()) Device::check(ph_d2h(out.data(), flat.data(), out.size() * sizeof(T)));
+  Device::read_checked(out.empty() ? nullptr : out.data(), flat.data(), out.size() * sizeof(T));   // a raise point
   return out;
 }
 

@@ -41,11 +41,29 @@ template <class T>
 inline std::string format_element(T v) {
   char buf[64];
   if constexpr (std::is_floating_point<T>::value) {
+    // Crystal's Float#to_s (Float::Printer, Crystal 1.0.0 stdlib; restated, the Python mirror's io.format_float
+    // applies the same rule): shortest digits that round-trip in T's own width; positional while the decimal
+    // point sits in [-3, 15], otherwise d.ddde+X with at least one fraction digit and an unpadded exponent.
     if (!std::isfinite(v)) throw std::invalid_argument("NaN and Infinity cannot be written as JSON / YAML numbers");
-    auto r = std::to_chars(buf, buf + sizeof(buf), v);
-    std::string s(buf, r.ptr);
-    if (s.find_first_of(".e") == std::string::npos) s += ".0";
-    return s;
+    auto r = std::to_chars(buf, buf + sizeof(buf), v, std::chars_format::scientific);   // shortest, "d.ddde[+-]XX"
+    std::string sci(buf, r.ptr);
+    const size_t epos = sci.find('e');
+    std::string mant = sci.substr(0, epos);
+    const int exp10 = std::stoi(sci.substr(epos + 1));
+    std::string sign;
+    if (!mant.empty() && mant[0] == '-') { sign = "-"; mant.erase(0, 1); }
+    std::string digits;
+    for (char c : mant) if (c != '.') digits += c;
+    while (digits.size() > 1 && digits.back() == '0') digits.pop_back();
+    if (digits == "0") return sign + "0.0";
+    const int point = exp10 + 1, n = (int)digits.size();                 // value = 0.DIGITS x 10^point
+    if (point > 15 || point < -3) {
+      const int e = point - 1;
+      return sign + digits.substr(0, 1) + "." + (n > 1 ? digits.substr(1) : std::string("0")) + "e" + (e > 0 ? "+" : "") + std::to_string(e);
+    }
+    if (point <= 0) return sign + "0." + std::string((size_t)(-point), '0') + digits;
+    if (point >= n) return sign + digits + std::string((size_t)(point - n), '0') + ".0";
+    return sign + digits.substr(0, (size_t)point) + "." + digits.substr((size_t)point);
   } else {
     auto r = std::to_chars(buf, buf + sizeof(buf), (typename std::conditional<std::is_signed<T>::value, long long, unsigned long long>::type)v);
     return std::string(buf, r.ptr);

@@ -133,7 +133,8 @@ def load() -> C.CDLL:
     sig = {
         "ph_init": [i32], "ph_shutdown": [], "ph_device_count": [C.POINTER(i32)], "ph_sm_count": [C.POINTER(i32)],
         "ph_alloc": [C.c_size_t, C.POINTER(vp)], "ph_free": [vp],
-        "ph_h2d": [vp, vp, C.c_size_t], "ph_d2h": [vp, vp, C.c_size_t], "ph_d2h_async": [vp, vp, C.c_size_t], "ph_d2d": [vp, vp, C.c_size_t],
+        "ph_h2d": [vp, vp, C.c_size_t], "ph_d2h": [vp, vp, C.c_size_t], "ph_d2h_async": [vp, vp, C.c_size_t],
+        "ph_d2h_flags": [vp, vp, C.c_size_t, C.POINTER(C.c_uint32)], "ph_d2d": [vp, vp, C.c_size_t],
         "ph_host_alloc": [C.c_size_t, C.POINTER(vp)], "ph_host_free": [vp],
         "ph_sync": [], "ph_set_stream": [vp], "ph_take_arith_flags": [C.POINTER(C.c_uint32)],
         "ph_timer_start": [], "ph_timer_stop": [C.POINTER(C.c_float)],

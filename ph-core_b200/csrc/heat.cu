@@ -569,9 +569,19 @@ static int32_t heat_slab_t(int rank, const int64_t* ext, const void* coeff_host,
   const int64_t lo = has_lo ? g : g + 1;
   const int64_t hi = has_hi ? n0 - g : n0 - g - 1;
   const int64_t b = std::max<int64_t>(p_begin, lo), e = std::min<int64_t>(p_end, hi);
-  for (int i = 1; i < rank; i++) if (ext[i] < 3) return PH_OK;
   const T* in = reinterpret_cast<const T*>(in_v);
   T* out = reinterpret_cast<T*>(out_v);
+  for (int i = 1; i < rank; i++)
+    if (ext[i] < 3) {
+      // a thin grid has no interior: every cell is a held boundary cell, a step is `nxt = s.clone`
+      // (heat_step_t does the same for the undivided grid) -- the caller flips buffers after every pass
+      int64_t plane = 1;
+      for (int j = 1; j < rank; j++) plane *= ext[j];
+      if (p_end > p_begin && plane > 0)
+        PH_CUDA(cudaMemcpyAsync(out + p_begin * plane, in + p_begin * plane, (size_t)((p_end - p_begin) * plane) * sizeof(T),
+                                cudaMemcpyDeviceToDevice, stream));
+      return PH_OK;
+    }
   if (two_step) {
     if (g < 2) return set_error(PH_ERR_INVALID, "two-step slab update needs 2 ghost planes");
     bool used = false;

@@ -205,6 +205,24 @@ int32_t ph_d2h(void* dst_host, const void* src_dev, size_t nbytes) {
   return PH_OK;
 }
 
+// ph_d2h plus the arithmetic flag word in the SAME synchronisation: the read a host layer uses for
+// `to_host` / `get`, so that a data-dependent error of any earlier launch surfaces at the read that
+// would hand its result to the caller (the reference raises at the offending operator).
+int32_t ph_d2h_flags(void* dst_host, const void* src_dev, size_t nbytes, uint32_t* out_flags) {
+  PH_REQUIRE_INIT();
+  if (!out_flags) return set_error(PH_ERR_INVALID, "null out_flags");
+  Runtime& r = rt();
+  if (nbytes) {
+    if (!dst_host || !src_dev) return set_error(PH_ERR_INVALID, "null pointer in ph_d2h_flags");
+    PH_CUDA(cudaMemcpyAsync(dst_host, src_dev, nbytes, cudaMemcpyDeviceToHost, r.stream));
+  }
+  PH_CUDA(cudaMemcpyAsync(r.h_flags, r.d_flags, 4, cudaMemcpyDeviceToHost, r.stream));
+  PH_CUDA(cudaMemsetAsync(r.d_flags, 0, 4, r.stream));
+  PH_CUDA(cudaStreamSynchronize(r.stream));
+  *out_flags = *r.h_flags;
+  return PH_OK;
+}
+
 int32_t ph_d2h_async(void* dst_host, const void* src_dev, size_t nbytes) {
   PH_REQUIRE_INIT();
   if (nbytes == 0) return PH_OK;

@@ -18,19 +18,80 @@ from .narray import DeviceNArray, ShapeError
 _MAGIC = b"PHNARR1\n"
 
 
-def _elements(host: np.ndarray) -> list:
+def format_float(v) -> str:
+    """Crystal's Float#to_s for a Float32 / Float64 element, which is what `NArray#to_json` / `#to_yaml`
+    write (JSON::Builder#number / YAML scalar -> Float::Printer, Crystal 1.0.0 stdlib -- not vendored in
+    the reference, restated: the SHORTEST digits that round-trip in the element's own width, positional
+    for decimal points in [-3, 15], otherwise `d.ddde+X` with at least one fraction digit and an
+    unpadded exponent: 0.1, 100000000000000.0, 1.0e+15, 1.0e-5).  include/ph_narray_io.hpp's
+    format_element applies the same rule, so the two hosts write identical text.  NaN and the
+    infinities are not JSON numbers: both hosts raise, like JSON::Builder does."""
+    v = v if isinstance(v, np.floating) else np.float64(v)
+    if not np.isfinite(v):
+        raise ValueError("NaN and Infinity cannot be written as JSON / YAML numbers")
+    sci = np.format_float_scientific(v, unique=True, trim="-")           # shortest round trip in v's own width
+    mant, exp10 = sci.split("e")
+    sign = "-" if mant.startswith("-") else ""
+    digits = mant.lstrip("-").replace(".", "")
+    if digits.strip("0") == "":
+        return sign + "0.0"
+    digits = digits.rstrip("0") or "0"
+    point = int(exp10) + 1                                               # value = 0.DIGITS x 10^point
+    n = len(digits)
+    if point > 15 or point < -3:                                         # exponent form
+        frac = digits[1:] or "0"
+        e = point - 1
+        return f"{sign}{digits[0]}.{frac}e{'+' if e > 0 else ''}{e}"
+    if point <= 0:
+        return f"{sign}0.{'0' * (-point)}{digits}"
+    if point >= n:
+        return f"{sign}{digits}{'0' * (point - n)}.0"
+    return f"{sign}{digits[:point]}.{digits[point:]}"
+
+
+def _element_text(host: np.ndarray) -> list:
     flat = host.reshape(-1)
     if host.dtype == np.bool_:
-        return [bool(v) for v in flat]
+        return ["true" if v else "false" for v in flat]
     if host.dtype.kind in "iu":
-        return [int(v) for v in flat]
-    return [float(v) for v in flat]
+        return [str(int(v)) for v in flat]
+    return [format_float(v) for v in flat]
+
+
+def host_to_json(host: np.ndarray) -> str:
+    """The text half of `to_json` on a host array (what the C++ layer's IO::host::to_json writes)."""
+    shape = ",".join(str(int(s)) for s in host.shape)
+    return '{"shape":[' + shape + '],"elements":[' + ",".join(_element_text(host)) + "]}"
+
+
+def host_to_yaml(host: np.ndarray) -> str:
+    shape = ", ".join(str(int(s)) for s in host.shape)
+    return f"---\nshape: [{shape}]\nelements: [{', '.join(_element_text(host))}]\n"
 
 
 def to_json(arr: DeviceNArray) -> str:
     """NArray#to_json (src/n_array.cr:807-818): compact separators, flat lex order."""
-    return json.dumps({"shape": [int(s) for s in arr.shape], "elements": _elements(arr.to_host())},
-                      separators=(",", ":"))
+    return host_to_json(arr.to_host())
+
+
+def _typed_elements(elements, dtype: np.dtype, what: str) -> np.ndarray:
+    """Elements of a parsed document as `dtype`, WITHOUT numpy's silent coercions: the reference's
+    `T.new(pull)` (src/n_array.cr:838-841) raises when a JSON value is not a T."""
+    dtype = np.dtype(dtype)
+    for v in elements:
+        if dtype == np.bool_:
+            ok = isinstance(v, bool)
+        elif dtype.kind in "iu":
+            ok = isinstance(v, int) and not isinstance(v, bool)
+        else:
+            ok = isinstance(v, (int, float)) and not isinstance(v, bool)
+        if not ok:
+            raise ValueError(f"Could not read NArray from {what}: element {v!r} is not a {dtype}")
+    if dtype.kind in "iu" and len(elements):
+        info = np.iinfo(dtype)
+        if min(elements) < info.min or max(elements) > info.max:
+            raise ValueError(f"Could not read NArray from {what}: an element does not fit {dtype}")
+    return np.array(elements, dtype=dtype)
 
 
 def from_json(text: str, dtype) -> DeviceNArray:
@@ -43,15 +104,12 @@ def from_json(text: str, dtype) -> DeviceNArray:
     size = int(np.prod(shape, dtype=np.int64)) if shape else 0
     if size != len(elements):
         raise ShapeError(f"Could not read NArray from JSON: wrong number of elements for shape {shape}")
-    return DeviceNArray.from_host(np.array(elements, dtype=dtype).reshape(shape))
+    return DeviceNArray.from_host(_typed_elements(elements, dtype, "JSON").reshape(shape))
 
 
 def to_yaml(arr: DeviceNArray) -> str:
     """NArray#to_yaml (src/n_array.cr:853-869): flow sequences, document start marker."""
-    fmt = lambda v: ("true" if v else "false") if isinstance(v, bool) else repr(v) if isinstance(v, float) else str(v)
-    shape = ", ".join(str(int(s)) for s in arr.shape)
-    elems = ", ".join(fmt(v) for v in _elements(arr.to_host()))
-    return f"---\nshape: [{shape}]\nelements: [{elems}]\n"
+    return host_to_yaml(arr.to_host())
 
 
 def from_yaml(text: str, dtype) -> DeviceNArray:

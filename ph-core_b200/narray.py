@@ -115,6 +115,52 @@ def cover_region(bound_shape: Sequence[int], drop: bool = True) -> PhRegion:
     return out
 
 
+def _checked_d2h(dst_host, src_dev, nbytes: int) -> None:
+    """ph_d2h_flags: the copy and the arithmetic flag word in one synchronisation; raises the
+    reference's exception class when any earlier launch flagged one."""
+    flags = C.c_uint32(0)
+    check(_lib.load().ph_d2h_flags(dst_host, src_dev, int(nbytes), C.byref(flags)))
+    raise_for_flags(flags.value)
+
+
+def sync() -> None:
+    """Device.sync: wait for every launched operator; a guaranteed raise point for data-dependent errors."""
+    flags = C.c_uint32(0)
+    check(_lib.load().ph_d2h_flags(None, None, 0, C.byref(flags)))
+    raise_for_flags(flags.value)
+
+
+def _scalar_of(value, dtype: np.dtype, what: str) -> np.ndarray:
+    """A scalar operand as ONE element of the array's dtype.  The device path computes in the
+    array's element type only (same-dtype operands): a scalar that the type cannot
+    hold exactly (`int_arr * 2.5`, `u8_arr + 300`, `int_arr < 2.5`) would silently change the
+    result, so it is rejected; the reference would promote (Int32 * Float64 -> Float64)."""
+    if isinstance(value, np.generic) or (isinstance(value, np.ndarray) and value.ndim == 0):
+        value = value.item()
+    if isinstance(value, (bool, np.bool_)):
+        value = int(value) if dtype.kind != "b" else bool(value)
+    if dtype.kind == "f":
+        if isinstance(value, (int, float, np.integer, np.floating)):
+            return np.array(value, dtype=dtype)           # Float32 arrays take any real (rounded like a Float32 literal)
+        raise TypeError(f"device path: {what} needs a real scalar for a {dtype} array, got {type(value).__name__}")
+    if dtype.kind in "iub":
+        if isinstance(value, (float, np.floating)):
+            if not float(value).is_integer():
+                raise TypeError(f"device path: scalar {value!r} is not representable in {dtype} ({what}); "
+                                "mixed Int/Float arithmetic is off the device path -- convert the array first")
+            value = int(value)
+        if isinstance(value, (int, np.integer)):
+            if dtype.kind == "b":
+                if int(value) not in (0, 1):
+                    raise TypeError(f"device path: scalar {value!r} is not a Bool ({what})")
+                return np.array(bool(value), dtype=dtype)
+            info = np.iinfo(dtype)
+            if not info.min <= int(value) <= info.max:
+                raise TypeError(f"device path: scalar {value!r} does not fit {dtype} ({what})")
+            return np.array(int(value), dtype=dtype)
+    raise TypeError(f"device path: {what} cannot take a {type(value).__name__} scalar for a {dtype} array")
+
+
 class _Buffer:
     """Ref-counted owner of one device allocation (reshape aliases the buffer,
     src/n_array.cr:429-433; views keep their source alive, src/view.cr:7)."""
@@ -295,7 +341,7 @@ class _Indexable:
         off = C.c_int64()
         host_check(_lib.load().ph_desc_offset_of(C.byref(self.desc()), canon, len(coord), C.byref(off)))
         out = np.empty(1, dtype=self.dtype)
-        check(_lib.load().ph_d2h(out.ctypes.data, self.ptr + off.value * self.dtype.itemsize, self.dtype.itemsize))
+        _checked_d2h(out.ctypes.data, self.ptr + off.value * self.dtype.itemsize, self.dtype.itemsize)
         return out[0]
 
     get_element = get
@@ -306,7 +352,7 @@ class _Indexable:
         host_check(_lib.load().ph_canonicalize_coord(_i64(coord), len(coord), _i64(self.shape), len(self.shape), canon))
         off = C.c_int64()
         host_check(_lib.load().ph_desc_offset_of(C.byref(self.desc()), canon, len(coord), C.byref(off)))
-        v = np.array([value], dtype=self.dtype)
+        v = _scalar_of(value, self.dtype, "set_element").reshape(1)
         check(_lib.load().ph_h2d(self.ptr + off.value * self.dtype.itemsize, v.ctypes.data, self.dtype.itemsize))
         check(_lib.load().ph_sync())
 
@@ -345,7 +391,7 @@ class _Indexable:
             host_check(st)
             check(lib.ph_copy_strided(self.dtype.itemsize, value.ptr, C.byref(sdesc), self.ptr, C.byref(dst)))
         else:
-            v = np.array(value, dtype=self.dtype)
+            v = _scalar_of(value, self.dtype, "[]=")
             check(lib.ph_fill_region(self.dtype.itemsize, self.ptr, C.byref(dst), v.ctypes.data))
 
     def set_mask(self, mask: "_Indexable", value) -> None:
@@ -358,10 +404,11 @@ class _Indexable:
         if isinstance(value, _Indexable):
             if list(value.shape) != list(self.shape):
                 raise DimensionError("Cannot perform masking: value shape does not match array shape.")
+            self._same_dtype(value, "masked store")
             check(lib.ph_mask_set_array(self.dtype.itemsize, self.ptr, C.byref(self.desc()), mask.ptr,
                                         C.byref(mask.desc()), value.ptr, C.byref(value.desc())))
         else:
-            v = np.array(value, dtype=self.dtype)
+            v = _scalar_of(value, self.dtype, "masked store")
             check(lib.ph_mask_set_scalar(self.dtype.itemsize, self.ptr, C.byref(self.desc()), mask.ptr,
                                          C.byref(mask.desc()), v.ctypes.data))
 
@@ -381,11 +428,17 @@ class _Indexable:
                                               C.byref(out.desc())))
         return out
 
-    def to_host(self) -> np.ndarray:
-        """Explicit device -> host transfer of the (materialised) contents."""
+    def to_host(self, check_flags: bool = True) -> np.ndarray:
+        """Explicit device -> host transfer of the (materialised) contents.  A guaranteed raise point:
+        OverflowError / DivisionByZeroError / ArgumentError of ANY operator launched before it is raised
+        here, in the same synchronisation as the copy (the reference raises at the operator; on the device
+        path the error surfaces at the first read of a result, INTEGRATION.md "raise points").
+        `check_flags=False` is the raw read the parity tests use to compare wrapped values AND flags."""
         src = self if isinstance(self, DeviceNArray) else self.to_narr()
         out = np.empty(src.shape, dtype=src.dtype)
-        if out.size:
+        if check_flags:
+            _checked_d2h(out.ctypes.data if out.size else None, src.ptr, out.nbytes if out.size else 0)
+        elif out.size:
             check(_lib.load().ph_d2h(out.ctypes.data, src.ptr, out.nbytes))
         return out
 
@@ -439,13 +492,21 @@ class _Indexable:
             return np.dtype(np.float64)
         return self.dtype
 
+    def _same_dtype(self, other: "_Indexable", what: str) -> None:
+        """Kernels are typed by ONE element type: a second operand of another dtype would be read with
+        the wrong element size (past its allocation).  The Crystal and C++ layers reject this at compile
+        time (both operands are DeviceIndexable(T)); here it is a TypeError before any launch."""
+        a = np.dtype(np.uint8) if self.dtype == np.dtype(np.bool_) else self.dtype
+        b = np.dtype(np.uint8) if other.dtype == np.dtype(np.bool_) else other.dtype
+        if a != b:
+            raise TypeError(f"device path: {what} needs operands of one dtype, got {self.dtype} and {other.dtype}")
+
     def _binary(self, op: str, other, reflected: bool = False) -> "DeviceNArray":
         lib = _lib.load()
         code = K[_BIN[op]]
         dt = dtype_code(self.dtype)
         if isinstance(other, _Indexable):
-            if other.dtype != self.dtype:
-                raise TypeError("device path: operands must share a dtype")
+            self._same_dtype(other, f"'{op}'")
             a, b = (other, self) if reflected else (self, other)
             if list(a.shape) != list(b.shape):                # multi_indexable.cr:935-940
                 raise ShapeError(f"The shape of this MultiIndexable ({a.shape}) does not match the shape of "
@@ -460,7 +521,7 @@ class _Indexable:
             s = np.array(other, dtype=np.int32)
             code = K["PH_POWI"]
         else:
-            s = np.array(other, dtype=self.dtype)
+            s = _scalar_of(other, self.dtype, f"'{op}'")
         check(lib.ph_ewise_scalar(code, dt, self.ptr, C.byref(self.desc()), s.ctypes.data, int(reflected), out.ptr,
                                   C.byref(out.desc())))
         return out
@@ -474,6 +535,7 @@ class _Indexable:
         """NEW (ShapeUtil.broadcast_shapes): equal rank, size-1 axes stretch."""
         if len(self.shape) != len(other.shape):
             raise ShapeError("broadcast requires equal rank")
+        self._same_dtype(other, f"broadcast '{op}'")
         shape = (C.c_int64 * max(1, len(self.shape)))()
         host_check(_lib.load().ph_broadcast_shapes(_i64(self.shape), _i64(other.shape), len(self.shape), shape))
         shape = [int(shape[i]) for i in range(len(self.shape))]
@@ -485,6 +547,8 @@ class _Indexable:
 
     def mul_add(self, b: "_Indexable", c: "_Indexable") -> "DeviceNArray":
         """Fused (self * b) + c with two roundings; b and c may broadcast."""
+        self._same_dtype(b, "mul_add")
+        self._same_dtype(c, "mul_add")
         out = DeviceNArray(self.shape, self.dtype)
         da, db, dc = self.desc(), b.bcast_desc(self.shape), c.bcast_desc(self.shape)
         check(_lib.load().ph_ewise_mul_add(dtype_code(self.dtype), self.ptr, C.byref(da), b.ptr, C.byref(db),
@@ -532,10 +596,11 @@ class _Indexable:
                 if eq_style:                                    # multi_indexable.cr:900-902
                     raise DimensionError("Cannot compute the element-wise equality: shapes differ")
                 raise ShapeError("shapes differ")               # :935-940
+            self._same_dtype(other, f"'{op}'")
             check(lib.ph_compare(K[_CMP[op]], dt, self.ptr, C.byref(self.desc()), other.ptr, C.byref(other.desc()),
                                  out.ptr, C.byref(out.desc())))
         else:
-            s = np.array(other, dtype=self.dtype)
+            s = _scalar_of(other, self.dtype, f"'{op}'")
             check(lib.ph_compare_scalar(K[_CMP[op]], dt, self.ptr, C.byref(self.desc()), s.ctypes.data, int(reflected),
                                         out.ptr, C.byref(out.desc())))
         return out
@@ -663,7 +728,7 @@ class DeviceNArray(_Indexable):
         """NArray.fill (src/n_array.cr:230-232)."""
         out = cls(shape, dtype)
         if out.size:
-            v = np.array(value, dtype=out.dtype)
+            v = _scalar_of(value, out.dtype, "fill")
             check(_lib.load().ph_fill_region(out.dtype.itemsize, out.ptr, C.byref(out.desc()), v.ctypes.data))
         return out
 

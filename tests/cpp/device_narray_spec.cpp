@@ -182,9 +182,12 @@ static void io_host_specs() {
     EXPECT_RAISES(IO::ParseError, H::from_json("{\"shape\":[2,2]}", s, e));
     EXPECT_RAISES(IO::ParseError, H::from_json("{\"shape\":[1],\"elements\":[1.5]}", s, e));    // not an Int32
     EXPECT_RAISES(IO::ParseError, H::from_json("{\"shape\":[1],\"elements\":[1],\"extra\":[2]}", s, e));
-    // floats: shortest text that round-trips, always with a fraction; bools as true / false on the way in
+    // floats as Crystal's Float#to_s writes them: shortest text that round-trips, always with a fraction,
+    // positional up to 1e15, d.de+X beyond (unpadded exponent); bools as true / false on the way in
     const V<double> fl{0.1, 2.0, -1.5e-7, 1e22, 5e-324, 0.30000000000000004};
-    EXPECT(H::to_json(Shape{6}, fl) == "{\"shape\":[6],\"elements\":[0.1,2.0,-1.5e-07,1e+22,5e-324,0.30000000000000004]}");
+    EXPECT(H::to_json(Shape{6}, fl) == "{\"shape\":[6],\"elements\":[0.1,2.0,-1.5e-7,1.0e+22,5.0e-324,0.30000000000000004]}");
+    EXPECT(H::to_json(Shape{5}, V<double>{1e14, 1e15, 0.0001, 0.00001, -0.0}) == "{\"shape\":[5],\"elements\":[100000000000000.0,1.0e+15,0.0001,1.0e-5,-0.0]}");
+    EXPECT(H::to_json(Shape{2}, V<float>{0.1f, 16777216.0f}) == "{\"shape\":[2],\"elements\":[0.1,16777216.0]}");   // Float32 digits, not the widened double's
     Shape fs; V<double> fe;
     H::from_json(H::to_json(Shape{6}, fl), fs, fe);
     EXPECT(fe == fl);

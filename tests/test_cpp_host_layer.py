@@ -65,7 +65,9 @@ def test_binary_dump_is_interchangeable_between_the_cpp_and_python_hosts(tmp_pat
     assert got.dtype == np.float32 and got.shape == (3, 4) and got.tobytes() == want.tobytes()
     # Python writes, C++ reads and prints the reference's JSON form
     rs = np.random.RandomState(3)
+    edge = [0.1, 2.0, -1.5e-7, 1e22, 5e-324, 0.30000000000000004, 1e14, 1e15, 1e16, 1e-4, 1e-5, -0.0, 123456.789e3]
     cases = [("f64", rs.rand(4, 3, 2)), ("f32", rs.rand(5, 7).astype(np.float32)),
+             ("f64", np.array(edge)), ("f32", np.array([0.1, 3.4e38, 1e-38, 16777216.0, 1e16, -2.5e-7], np.float32)),
              ("i16", rs.randint(-30000, 30000, size=(6,)).astype(np.int16)),
              ("u8", (rs.rand(2, 9) < 0.5)), ("f32", np.zeros((3, 0, 2), np.float32))]
     for tag, arr in cases:
@@ -75,6 +77,8 @@ def test_binary_dump_is_interchangeable_between_the_cpp_and_python_hosts(tmp_pat
         assert out.returncode == 0, out.stderr
         obj = json.loads(out.stdout)
         assert obj["shape"] == list(arr.shape)
+        if tag != "u8":                                   # (Bool arrays are read back as UInt8 by the CLI)
+            assert out.stdout.strip() == io.host_to_json(arr), "the two hosts write different text"
         back = np.array(obj["elements"], dtype=arr.dtype if arr.dtype != np.bool_ else np.uint8).reshape(arr.shape)
         assert back.tobytes() == np.ascontiguousarray(arr).view(back.dtype).tobytes()      # shortest round-trip text is exact
     # a dump of the wrong element type, a truncated one and a foreign file are refused

@@ -50,7 +50,11 @@ def test_config2_views_16384_f64():
     # (i) rows 0,2,4..: element [i, j] must be (2i)*n + j
     g = src[rng(0, None, 2), rng(None, -1)]
     assert g.shape == [n // 2, n] and g.get(3, 9) == 6 * n + 9 and g.get(n // 2 - 1, n - 1) == (n - 2) * n + n - 1
-    assert float(g.sum(axis=1).sum()) == sum(((2 * i) * n) * n + n * (n - 1) / 2 for i in range(0, n // 2, n // 64)) or True
+    # row i of g holds (2i)*n + j: its sum is 2i*n^2 + n(n-1)/2, an integer < 2^42, and every partial sum of
+    # the row sums is a multiple of 2^13 below 2^55 -- all exact in f64 whatever the fold order
+    half = n // 2
+    assert float(g.sum(axis=1).sum()) == float(n * n * half * (half - 1) + half * (n * (n - 1) // 2))
+    assert g.sum(axis=1).get(half - 1) == float(2 * (half - 1) * n * n + n * (n - 1) // 2)
     # (ii) columns 0,2,4..
     g2 = src[rng(None, None), rng(0, None, 2)]
     assert g2.shape == [n, n // 2] and g2.get(11, 5) == 11 * n + 10

@@ -176,7 +176,9 @@ def test_axis_int_overflow_and_errors():
     a = np.array([[2**31 - 1, 1], [1, 1], [-5, 1]], np.int32)
     with pytest.raises(ph.CrOverflowError):
         D.from_host(a).sum(axis=0)
-    assert D.from_host(a).sum(axis=1).to_host().tolist() if False else True
+    with pytest.raises(ph.CrOverflowError):
+        D.from_host(a).sum(axis=1)                                              # row 0: Int32::MAX + 1
+    assert D.from_host(a[1:]).sum(axis=1).to_host().tolist() == [2, -4]
     with pytest.raises(ph.CrOverflowError):
         D.from_host(np.array([[2**31 - 1, 1, -5]], np.int32)).sum(axis=1)       # prefix along the row
     assert D.from_host(np.array([[2**31 - 1, -5, 1]], np.int32)).sum(axis=1).to_host().tolist() == [2**31 - 5]

@@ -312,3 +312,31 @@ def test_trimmed_regions_match_oracle():
                 assert (reg.first[i], reg.step[i], reg.last[i]) == (oreg.first[i], oreg.step[i], oreg.last[i]), (lit, shape)
         ok += 1
     assert ok > 500
+
+
+def test_float_text_follows_crystal_float_to_s():
+    """f-4 / ADVICE r1: io.format_float restates Crystal 1.0's Float#to_s (shortest round-trip digits in the
+    element's own width; positional for decimal points in [-3, 15], else d.de+X with an unpadded exponent);
+    NaN / Infinity are refused like JSON::Builder#number does; from_json does not coerce element types."""
+    import numpy as np
+    import pytest
+    from ph_core_b200 import io
+    cases = {0.1: "0.1", 2.0: "2.0", -1.5e-7: "-1.5e-7", 1e22: "1.0e+22", 5e-324: "5.0e-324", 1e14: "100000000000000.0",
+             1e15: "1.0e+15", 1e-4: "0.0001", 1e-5: "1.0e-5", -0.0: "-0.0", 0.30000000000000004: "0.30000000000000004",
+             123.456: "123.456"}
+    for v, text in cases.items():
+        assert io.format_float(np.float64(v)) == text
+        assert float(io.format_float(np.float64(v))) == v
+    assert io.format_float(np.float32(0.1)) == "0.1" and io.format_float(np.float32(16777216.0)) == "16777216.0"
+    assert io.host_to_json(np.array([[0.5, 1e16]], np.float32)) == '{"shape":[1,2],"elements":[0.5,1.0e+16]}'
+    assert io.host_to_yaml(np.array([True, False])) == "---\nshape: [2]\nelements: [true, false]\n"
+    for bad in (np.nan, np.inf, -np.inf):
+        with pytest.raises(ValueError):
+            io.format_float(np.float64(bad))
+    with pytest.raises(ValueError):
+        io._typed_elements([1, 2.5], np.int32, "JSON")
+    with pytest.raises(ValueError):
+        io._typed_elements([1, 300], np.uint8, "JSON")
+    with pytest.raises(ValueError):
+        io._typed_elements([1, True], np.int32, "JSON")
+    assert io._typed_elements([1, 2], np.float32, "JSON").tolist() == [1.0, 2.0]
