@@ -13,8 +13,10 @@ N > 1 is launched by torchrun, one rank per GPU; elementwise work shards along t
 axis with no data-path collective (weak scaling: every rank owns an 8192x8192 shard).
 
 Prints ONE JSON line (rank 0).  `value` = whole-job GB/s with inputs resident in HBM (two CUDA
-events around the K steps); `e2e` = the same metric through the public API with HOST buffers
-(pinned H2D of a, b, c and D2H of the result inside the timed region); `roofline` describes the
+events around the K steps); `e2e` = the same metric through the public ARRAY API with HOST buffers
+(ph_core_b200.pipeline.RowPipeline: from_host_async of a, b, c, the two operators, to_host_async of the
+result, chunked over the library's streams; `e2e.naive` = plain from_host -> operators -> to_host beside it,
+`e2e.host_link_ceiling` = the measured rate of moving the same bytes with no kernels at all); `roofline` describes the
 dominant kernel (its own duration from events on every 8th step of the same timed region, DRAM
 traffic from the committed ncu capture); `cpu_baseline` = the oracle's C port of the REFERENCE'S
 structure (single thread: ph-core has no threads) timed on this box, with the flat OpenMP loop on
@@ -184,10 +186,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # a bounded sample per step, sized so that the whole --steps K run ends within about a minute:
-    # 1/8 of the workload (~0.13 s on one core) for K <= 100, 1/32 for K <= 2000 (the driver may pass
-    # our own default K = 1000), 1/128 beyond
-    rows = 1024 if args.steps <= 100 else (256 if args.steps <= 2000 else 64)
+    # One step = the WHOLE workload (8192 rows, ~1 s on one core) whenever the run then ends within a few
+    # minutes (K <= 32; the driver passes K = 20); beyond that a bounded sample of rows per step, stated in
+    # config.sample, and ms_per_step is the time of what was actually run -- never a scaled figure.
+    rows = ROWS if args.steps <= 32 else (1024 if args.steps <= 200 else (256 if args.steps <= 2000 else 64))
     from oracle import c_oracle as CO
     a, b, c = make_inputs(0, rows)
     for _ in range(max(1, min(args.warmup, 3))):
@@ -198,11 +200,14 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     gbs = (BYTES_STEP * rows / ROWS) * args.steps / dt / 1e9
     flat_gbs, flat_cores, _ = cpu_flat_sample(2048, 5)
+    sample = ("the full workload per step" if rows == ROWS else
+              f"{rows} of {ROWS} rows per step (value = GB/s of the rows run; ms_per_step = time of those rows)")
     line = {
         "impl": "reference", "metric": METRIC, "value": round(gbs, 4), "unit": "GB/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3 * ROWS / rows, 3),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{rows} of {ROWS} rows per step (ms_per_step scaled to the full workload)"},
+        "config": {"workload": WORKLOAD, "shape_per_gpu": [rows, COLS], "bytes_per_step_per_gpu": int(BYTES_STEP * rows / ROWS),
+                   "sample": sample, "seed": SEED},
         "cpu_baseline": {"value": round(gbs, 4), "unit": "GB/s", "cores": 1, "kind": "port",
                          "sample": f"{rows}x{COLS} f32 rows per step; C port of the reference's structure "
                                    "(tile + two per-element map_with passes), single thread like the reference",
@@ -308,64 +313,69 @@ def run_ours(args):
     barrier()
     fused_ms = e0.elapsed_time(e1) / args.steps
 
-    # ---- end to end through the public API with HOST buffers (pinned), copies timed
-    pin = {}
-    for name, arr in (("a", a_h), ("b", b_h), ("c", c_h), ("out", np.empty_like(a_h))):
-        p = C.c_void_p()
-        ph.check(lib.ph_host_alloc(arr.nbytes, C.byref(p)))
-        view = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(arr.size,)).reshape(arr.shape)
-        if name != "out":
-            view[...] = arr
-        pin[name] = (p, view)
-
-    # The user-level call sequence: explicit H2D of the operands, the two operators, explicit
-    # D2H of the result.  Rows are processed in chunks on three streams so the upload of chunk
-    # i+1, the kernels of chunk i and the download of chunk i-1 overlap (PCIe is full duplex).
-    CH = 8
-    rows_per = ROWS // CH
-    streams = [torch.cuda.Stream(device=torch.device("cuda", local)) for _ in range(3)]
-    isz = 4
+    # ---- end to end through the public ARRAY API with HOST buffers: every step uploads a, b, c from pinned
+    # host memory, runs the two operators and downloads the result (all inside the timed region).
+    # RowPipeline cuts the rows into chunks on the library's own streams so upload, kernels and download
+    # overlap; the expression is written with the array API (no hand-built descriptors, no torch streams).
+    a_pin, b_pin, c_pin = ph.pinned_from(a_h), ph.pinned_from(b_h), ph.pinned_from(c_h)
+    out_pin = ph.pinned_empty(a_h.shape, np.float32)
+    pipe = ph.pipeline.RowPipeline(chunks=8, streams=3)
+    expr = lambda x, z, y: x.broadcast_op("*", y) + z          # (a * b) + c, b the [1, COLS] row vector
 
     def e2e_step():
-        ph.check(lib.ph_set_stream(streams[0].cuda_stream))
-        ph.check(lib.ph_h2d(b.ptr, pin["b"][0], b_h.nbytes))
-        b_ready = torch.cuda.Event()
-        b_ready.record(streams[0])
-        for k in range(CH):
-            st = streams[k % 3]
-            st.wait_event(b_ready)
-            ph.check(lib.ph_set_stream(st.cuda_stream))
-            off = k * rows_per * COLS * isz
-            nb = rows_per * COLS * isz
-            ph.check(lib.ph_h2d(a.ptr + off, pin["a"][0].value + off, nb))
-            ph.check(lib.ph_h2d(c.ptr + off, pin["c"][0].value + off, nb))
-            dk = ph.PhDesc.make([rows_per, COLS], [COLS, 1], k * rows_per * COLS)
-            dbk = ph.PhDesc.make([rows_per, COLS], [0, 1], 0)
-            ph.check(lib.ph_ewise_binary(MUL, F32, a.ptr, C.byref(dk), b.ptr, C.byref(dbk), t.ptr, C.byref(dk)))
-            ph.check(lib.ph_ewise_binary(ADD, F32, t.ptr, C.byref(dk), c.ptr, C.byref(dk), out.ptr, C.byref(dk)))
-            ph.check(lib.ph_d2h_async(pin["out"][0].value + off, out.ptr + off, nb))
-        for st in streams:
-            stream.wait_stream(st)
-        ph.check(lib.ph_set_stream(None))
+        pipe.map_rows(expr, rows=[a_pin, c_pin], out=out_pin, shared=[b_pin], wait=False)
 
     e2e_steps = max(2, min(args.steps, 5))
     e2e_step()
+    ph.sync()
     barrier()
     with torch.cuda.stream(stream):
         e0.record(stream)
         for _ in range(e2e_steps):
-            for st in streams:
-                st.wait_stream(stream)
             e2e_step()
         e1.record(stream)
     barrier()
+    ph.sync()
     e2e_ms = e0.elapsed_time(e1) / e2e_steps
+    e2e_out = out_pin.copy()
+
+    # the same through the plainest calls a user can make: pageable numpy in, numpy out, one stream
+    def naive_step():
+        return (D.from_host(a_h).broadcast_op("*", D.from_host(b_h)) + D.from_host(c_h)).to_host()
+    naive_step()
+    barrier()
+    t0 = time.perf_counter()
+    naive_out = naive_step()
+    naive_ms = (time.perf_counter() - t0) * 1e3
+    naive_ok = bool(naive_out.tobytes() == e2e_out.tobytes())
+
+    # what the host link alone allows, measured with every rank active at once: the step's uploads on one
+    # stream and its download on another, no kernels -- the ceiling the e2e figure is judged against
+    s_up, s_dn = ph.Stream(), ph.Stream()
+    def link_step():
+        s_up.wait(None); s_dn.wait(None)
+        with s_up:
+            ph.check(lib.ph_h2d(a.ptr, a_pin.ctypes.data, a_pin.nbytes))
+            ph.check(lib.ph_h2d(c.ptr, c_pin.ctypes.data, c_pin.nbytes))
+            ph.check(lib.ph_h2d(b.ptr, b_pin.ctypes.data, b_pin.nbytes))
+        with s_dn:
+            ph.check(lib.ph_d2h_async(out_pin.ctypes.data, out.ptr, out_pin.nbytes))
+        ph.narray.main_stream_wait(s_up); ph.narray.main_stream_wait(s_dn)
+    link_step()
+    barrier()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(3):
+            link_step()
+        e1.record(stream)
+    barrier()
+    link_ms = e0.elapsed_time(e1) / 3
     if dist is not None:
-        tt = torch.tensor([e2e_ms], device="cuda")
+        tt = torch.tensor([e2e_ms, link_ms, naive_ms], device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_ms = float(tt.item())
+        e2e_ms, link_ms, naive_ms = [float(v) for v in tt.tolist()]
     e2e_value = BYTES_STEP * world / (e2e_ms * 1e-3) / 1e9
-    e2e_out = pin["out"][1].copy()
+    link_ceiling = BYTES_STEP * world / (link_ms * 1e-3) / 1e9
     clocks = sampler.stop()          # sampled across the headline, fused and e2e timed regions
 
     # ---- parity spot check of the timed result (oracle = checker only)
@@ -378,7 +388,7 @@ def run_ours(args):
     extras = None
     if not args.no_extras:
         try:
-            extras = run_extras(ph, lib, dist, world, rank, torch)
+            extras = run_extras(ph, lib, dist, world, rank, torch, stream)
         except Exception as e:                       # extras never invalidate the headline
             extras = {"error": repr(e)}
 
@@ -426,7 +436,14 @@ def run_ours(args):
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": round(e2e_value, 3), "unit": "GB/s", "ms_per_step": round(e2e_ms, 4),
                     "h2d_bytes_per_step": int(a_h.nbytes + b_h.nbytes + c_h.nbytes), "d2h_bytes_per_step": int(a_h.nbytes),
-                    "steps": e2e_steps, "how": "pinned host buffers; 8 row-chunks on 3 streams so H2D, kernels and D2H overlap",
+                    "steps": e2e_steps,
+                    "how": "array API: pipeline.RowPipeline.map_rows (from_host_async of pinned a, b, c -> a.broadcast_op('*', b) + c "
+                           "-> to_host_async), 8 row chunks on 3 library streams so H2D, kernels and D2H overlap",
+                    "naive": {"value": round(BYTES_STEP * world / (naive_ms * 1e-3) / 1e9, 3), "ms_per_step": round(naive_ms, 3),
+                              "how": "from_host(pageable numpy) x3 -> operators -> to_host, one stream, wall clock", "same_result": naive_ok},
+                    "host_link_ceiling": {"value": round(link_ceiling, 3), "unit": "GB/s", "ms_per_step": round(link_ms, 4),
+                                          "how": "the step's 537 MB up and 268 MB down on two streams at once, no kernels, all ranks concurrently"},
+                    "frac_of_host_link_ceiling": round(e2e_value / link_ceiling, 4),
                     "host_buffers_numa_local": numa_bound},
             "gpu_launches": int(launches), "clocks": clocks, "parity_spot_check": parity_ok,
             "extras": extras,
@@ -436,48 +453,114 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def run_extras(ph, lib, dist, world, rank, torch):
-    """Secondary BASELINE.json configs reported beside the headline (same JSON line, key
-    `extras`): the 2048^3 f32 heat stencil slab-decomposed over the N ranks with NCCL halo
-    exchange (STRONG scaling: the grid is fixed), and the full sum of a 1e9-element f32 array
-    sharded along axis 0 with an NCCL allreduce of the per-GPU partials."""
+def _gather_objects(dist, world, obj):
+    if dist is None:
+        return [obj]
+    out = [None] * world
+    dist.all_gather_object(out, obj)
+    return out
+
+
+def run_extras(ph, lib, dist, world, rank, torch, stream):
+    """Secondary BASELINE.json configs reported beside the headline (same JSON line, key `extras`), each
+    SELF-VERIFYING so that the driver's N = 1/2/4/8 runs check the multi-GPU paths:
+      * heat3d_2048_f32: 2048^3 f32 stencil, slab-decomposed over the N ranks (STRONG scaling).  Seeded
+        non-constant field (analytic bump + per-plane Philox noise, identical for every N), 10 warm-up +
+        100 timed steps; `subcube_vs_oracle` = a 48^3 crop straddling the slab boundary at plane 1024
+        replayed through the oracle for the first 2 steps, bit for bit; `field_hash` = position-weighted
+        64-bit checksum of the final field -- equal at N = 1/2/4/8 iff the fields are bit-identical.
+      * reduce_sum_1e9_f32 / reduce_argmax_1e9_f32: full reductions of [1000,1000,1000] f32 sharded along
+        axis 0; integer-valued data (every partial sum exact => the result must EQUAL the exact total) with
+        a planted maximum and a planted tie in another shard (argmax must return the lower global index).
+      * sharded_permute_16384_f64 (N > 1): transpose across shards, compared with the closed form."""
+    import math
     from ph_core_b200 import DeviceNArray as D, sharding as S, heat
+    from oracle import ph_oracle as O
     out = {}
     S.comm_init(dist)
-    # ---- heat 3-D 2048^3
-    G = 2048
-    lay = S.slab_layout(G, world, rank, ghost=2)
-    one = np.array(1.0, np.float32)
-    coeff = np.array(0.1, np.float32)
-    steps = 10
+    p2p = S.p2p_ready()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ms = C.c_float()
+
+    def max_over_ranks(v):
+        t = torch.tensor([v], device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------------------------------------------------------- heat 3-D 2048^3
+    G, GH, COEFF, WARM, STEPS = 2048, 2, 0.1, 10, 100
+    lay = S.slab_layout(G, world, rank, ghost=GH)
+    pbytes = G * G * 4
     if world == 1:
         a, b = D([G, G, G], np.float32), D([G, G, G], np.float32)
-        ph.check(lib.ph_fill_region(4, a.ptr, C.byref(a.desc()), one.ctypes.data))
-        run = lambda n: heat.simulate(a, 0.1, n)
+        first_local, own0, own1 = 0, 0, G                       # local plane of global plane 0; owned global planes
+        run = lambda x, y, n: heat.simulate_into(x, y, COEFF, n)
     else:
         shape = [lay["local_planes"], G, G]
-        a, b = D(shape, np.float32), D(shape, np.float32)
-        ph.check(lib.ph_fill_region(4, a.ptr, C.byref(a.desc()), one.ctypes.data))
-        ph.check(lib.ph_fill_region(4, b.ptr, C.byref(b.desc()), one.ctypes.data))
-        run = lambda n: S.heat_run_sharded(a, b, 0.1, n, ghost=2)
-    run(2)
+        a, b = S.symm_empty(shape, np.float32), S.symm_empty(shape, np.float32)     # peer-mapped when P2P is up
+        first_local, own0, own1 = GH - lay["start"], lay["start"], lay["stop"]
+        run = lambda x, y, n: S.heat_run_sharded(x, y, COEFF, n, ghost=GH)
+    # field: plane z = 100 * g(z) * g(y) g(x) + U[0,1) noise seeded by z alone (so every N builds the same grid)
+    with torch.cuda.stream(stream):
+        idx = torch.arange(G, device=dev, dtype=torch.float32)
+        cen, sig = (G - 1) / 2.0, G / 6.0
+        g1 = torch.exp(-((idx - cen) ** 2) / (2 * sig * sig))
+        bump_xy = 100.0 * g1[:, None] * g1[None, :]
+        gen = torch.Generator(device=dev)
+        for z in range(own0, own1):
+            gen.manual_seed(SEED * 4096 + z)
+            plane = bump_xy * float(np.float32(math.exp(-((z - cen) ** 2) / (2 * sig * sig)))) + \
+                torch.rand(G, G, generator=gen, device=dev, dtype=torch.float32)
+            ph.check(lib.ph_d2d(a.ptr + (z + first_local) * pbytes, plane.data_ptr(), pbytes))
+        del plane
+    torch.cuda.synchronize()
+
+    CZ, CY, CX, CN = G // 2 - 24, 700, 1100, 48                # crop straddles plane 1024: a slab boundary at N = 2, 4, 8
+    def crop_of(x):
+        z0, z1 = max(CZ, own0), min(CZ + CN, own1)
+        if z0 >= z1:
+            return None
+        part = x[ph.rng(z0 + first_local, z1 - 1 + first_local), ph.rng(CY, CY + CN - 1), ph.rng(CX, CX + CN - 1)].to_host()
+        return (z0, part)
+    def gather_crop(x):
+        parts = [p for p in _gather_objects(dist, world, crop_of(x)) if p is not None]
+        return np.concatenate([p[1] for p in sorted(parts, key=lambda t: t[0])], axis=0)
+
+    crop0 = gather_crop(a)
+    cur = run(a, b, 2)
+    crop2 = gather_crop(cur)
+    want = crop0
+    for _ in range(2):
+        want = O.heat_step_nd(want, np.float32(COEFF))
+    # cells at distance >= 2 from the crop's faces depend only on cells inside the crop
+    subcube_ok = bool(crop2.shape == (CN, CN, CN) and crop2[2:-2, 2:-2, 2:-2].tobytes() == want[2:-2, 2:-2, 2:-2].tobytes()
+                      and not np.array_equal(crop2, crop0))
+    other = b if cur is a else a
+    cur2 = run(cur, other, WARM - 2)
+    other = cur if cur2 is not cur else other
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
-    ms = C.c_float()
     ph.check(lib.ph_timer_start())
-    run(steps)
+    fin = run(cur2, other, STEPS)
     ph.check(lib.ph_timer_stop(C.byref(ms)))
-    t = torch.tensor([ms.value], device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    heat_ms = float(t.item()) / steps
-    out["heat3d_2048_f32"] = {"gcell_updates_per_s": round(G ** 3 / (heat_ms * 1e-3) / 1e9, 2), "ms_per_step": round(heat_ms, 4),
-                              "grid": [G, G, G], "steps": steps, "scaling": "strong",
-                              "decomposition": f"axis-0 slabs x{world}, two time steps per pass over HBM (temporal blocking, bit-identical); "
-                                               "2-plane NCCL send/recv halos every 2 steps, overlapped with the interior",
-                              "algorithmic_bytes_per_cell_update": 8,
-                              "hbm_gbs_per_gpu": round(8 * G ** 3 / world / (heat_ms * 1e-3) / 1e9, 1)}
+    heat_ms = max_over_ranks(ms.value) / STEPS
+    h = C.c_uint64(0)
+    ph.check(lib.ph_checksum64(fin.ptr + (own0 + first_local) * pbytes, (own1 - own0) * pbytes, own0 * (pbytes // 8), C.byref(h)))
+    field_hash = sum(_gather_objects(dist, world, int(h.value))) % (1 << 64)
+    out["heat3d_2048_f32"] = {
+        "gcell_updates_per_s": round(G ** 3 / (heat_ms * 1e-3) / 1e9, 2), "ms_per_step": round(heat_ms, 4),
+        "grid": [G, G, G], "steps": STEPS, "warmup": WARM, "scaling": "strong",
+        "field": "100 * gaussian bump + U[0,1) noise (torch Philox seeded per global plane), fixed boundary, C = 0.1",
+        "field_hash": f"{field_hash:016x}", "field_hash_steps": WARM + STEPS, "subcube_vs_oracle": subcube_ok,
+        "subcube": f"48^3 crop at [{CZ},{CY},{CX}] (straddles plane 1024), first 2 steps replayed by oracle.heat_step_nd, inner 44^3 bit-exact",
+        "halo": ("none (1 GPU)" if world == 1 else
+                 ("in-kernel P2P: the stencil kernel stores its edge planes into the neighbours' ghost planes (peer-mapped slabs), "
+                  "flag words + stream waits, no NCCL" if p2p else "NCCL send/recv of 2-plane halos every 2 steps, overlapped with the interior")),
+        "decomposition": f"axis-0 slabs x{world}, two time steps per pass over HBM (temporal blocking, bit-identical)",
+        "algorithmic_bytes_per_cell_update": 8,
+        "hbm_gbs_per_gpu": round(8 * G ** 3 / world / (heat_ms * 1e-3) / 1e9, 1)}
     if world == 1:
         # the reference's CPU path beside it: the slice-arithmetic step through ph-core's operator
         # structure (C port, one thread) on a 160^3 sample, and the flat OpenMP loop nest on 512^3
@@ -499,26 +582,54 @@ def run_extras(ph, lib, dist, world, rank, torch):
             "flat_openmp_all_cores": {"value": round(mid.size / dt_flat / 1e9, 3), "cores": CO.num_threads(),
                                       "sample": "512^3 f32, flat loop nest + OpenMP, mean of 3"}}
         del small, mid, tmp
-    del a, b
-    # ---- full sum of 1e9 f32 sharded along axis 0
-    n_total = 1000 * 1000 * 1000
-    r0, r1 = S.shard_range(1000, world, rank)
-    x = D([r1 - r0, 1000, 1000], np.float32)
-    ph.check(lib.ph_fill_region(4, x.ptr, C.byref(x.desc()), one.ctypes.data))
-    S.reduce_full_sharded(x, "sum")
+    if world > 1:
+        a._buf.free(); b._buf.free()
+    del a, b, cur, cur2, fin, other
+
+    # ---------------------------------------------------------------- full reductions of 1e9 f32 sharded along axis 0
+    R0, INNER = 1000, 1000 * 1000
+    n_total = R0 * INNER
+    r0, r1 = S.shard_range(R0, world, rank)
+    x = D([max(r1 - r0, 0), 1000, 1000], np.float32)
+    P1, P2 = 123_456_789, 876_543_210                        # planted maximum and its tie (another shard at N >= 2)
+    exact = torch.zeros((), dtype=torch.int64, device=dev)
+    with torch.cuda.stream(stream):
+        gen = torch.Generator(device=dev)
+        for i in range(r0, r1):
+            gen.manual_seed(SEED * 8192 + i)
+            row = torch.randint(-8, 9, (INNER,), generator=gen, device=dev, dtype=torch.int32)
+            for p in (P1, P2):
+                if p // INNER == i:
+                    row[p % INNER] = 99
+            exact += row.sum(dtype=torch.int64)
+            rowf = row.to(torch.float32)
+            ph.check(lib.ph_d2d(x.ptr + (i - r0) * INNER * 4, rowf.data_ptr(), INNER * 4))
+        del row, rowf
     torch.cuda.synchronize()
-    reps = 10
-    ph.check(lib.ph_timer_start())
-    for _ in range(reps):
-        total = S.reduce_full_sharded(x, "sum")
-    ph.check(lib.ph_timer_stop(C.byref(ms)))
-    t = torch.tensor([ms.value], device="cuda")
     if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    red_ms = float(t.item()) / reps
-    out["reduce_sum_1e9_f32"] = {"gbs": round(4 * n_total / (red_ms * 1e-3) / 1e9, 1), "ms": round(red_ms, 4),
-                                 "result_ok": bool(abs(float(total) - n_total) <= 1e-4 * n_total),
-                                 "collective": "ncclAllReduce of one f32 partial per GPU" if world > 1 else "none"}
+        dist.all_reduce(exact)
+    exact = int(exact.item())
+    off = r0 * INNER
+    reps = 20
+    for name, key in (("sum", "reduce_sum_1e9_f32"), ("argmax", "reduce_argmax_1e9_f32")):
+        got = S.reduce_full_sharded(x, name, off)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ph.check(lib.ph_timer_start())
+        for _ in range(reps):
+            got = S.reduce_full_sharded(x, name, off)
+        ph.check(lib.ph_timer_stop(C.byref(ms)))
+        red_ms = max_over_ranks(ms.value) / reps
+        ok = (float(got) == float(exact)) if name == "sum" else (float(got[0]) == 99.0 and int(got[1]) == P1)
+        ok = all(_gather_objects(dist, world, bool(ok)))
+        out[key] = {"gbs": round(4 * n_total / (red_ms * 1e-3) / 1e9, 1), "ms": round(red_ms, 4), "result_ok": ok,
+                    "check": ("integers in {-8..8} (+ two planted 99s): every partial sum is exact in f32, the result must equal the exact total"
+                              if name == "sum" else "planted maximum 99 at two global indices in different shards: argmax must return the lower one"),
+                    "collective": ("none (1 GPU)" if world == 1 else
+                                   ("in-kernel one-shot combine over peer-mapped slots (no NCCL, one launch, one sync)" if p2p
+                                    else "ncclAllGather of one 64-byte record per GPU + a combine launch")),
+                    "reps": reps}
     if world == 1:
         from oracle import c_oracle as CO
         xs = np.random.RandomState(2).rand(200_000_000).astype(np.float32)
@@ -531,6 +642,34 @@ def run_extras(ph, lib, dist, world, rank, torch):
             "sample": f"2e8 of 1e9 elements, Enumerable#sum as a sequential f32 left fold ({dt_ref:.2f} s)",
             "flat_openmp_all_cores": {"value": round(xs.nbytes / dt_flat / 1e9, 2), "cores": CO.num_threads(),
                                       "sample": "2e8 elements, OpenMP reduction in f64"}}
+        del xs
+    del x
+
+    # ---------------------------------------------------------------- transpose across shards (f-3), N > 1
+    if world > 1:
+        n = 16384
+        q0, q1 = S.shard_range(n, world, rank)
+        rows_v = D.from_host((np.arange(q0, q1, dtype=np.float64) * n).reshape(q1 - q0, 1))
+        cols_v = D.from_host(np.arange(n, dtype=np.float64).reshape(1, n))
+        src = S.ShardedNArray([n, n], rows_v.broadcast_op("+", cols_v))          # value = flat index
+        t = src.permute()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        preps = 3
+        ph.check(lib.ph_timer_start())
+        for _ in range(preps):
+            t = src.permute()
+        ph.check(lib.ph_timer_stop(C.byref(ms)))
+        perm_ms = max_over_ranks(ms.value) / preps
+        # transposed[i, j] = j * n + i on my rows i in [q0, q1)
+        expect = D.from_host(np.arange(q0, q1, dtype=np.float64).reshape(q1 - q0, 1)).broadcast_op(
+            "+", D.from_host((np.arange(n, dtype=np.float64) * n).reshape(1, n)))
+        ok = all(_gather_objects(dist, world, bool(t.local.equals(expect))))
+        hsum = sum(_gather_objects(dist, world, t.local.checksum64(q0 * n))) % (1 << 64)
+        out["sharded_permute_16384_f64"] = {"ms": round(perm_ms, 4), "gbs_aggregate": round(2 * n * n * 8 / (perm_ms * 1e-3) / 1e9, 1),
+                                            "result_ok": ok, "checksum": f"{hsum:016x}",
+                                            "how": "ShardedNArray.permute: per-peer permuting gathers, all-to-all, scatters"}
     return out
 
 

@@ -106,6 +106,12 @@ lib LibPhGpu
   fun ph_sync : Int32
   fun ph_stream : Void*
   fun ph_set_stream(cuda_stream : Void*) : Int32
+  fun ph_stream_create(out_stream : Void**) : Int32
+  fun ph_stream_destroy(stream : Void*) : Int32
+  fun ph_stream_wait(waiter_stream : Void*, signaler_stream : Void*) : Int32
+  fun ph_stream_sync(stream : Void*) : Int32
+  fun ph_free_on(dev : Void*, stream : Void*) : Int32
+  fun ph_checksum64(dev : Void*, nbytes : LibC::SizeT, word_offset : UInt64, out_host : UInt64*) : Int32
   fun ph_last_error_string : LibC::Char*
   fun ph_take_arith_flags(out_flags : UInt32*) : Int32
   fun ph_timer_start : Int32
@@ -124,6 +130,9 @@ lib LibPhGpu
                  out : UInt8*, out_desc : Desc*) : Int32
   fun ph_compare_scalar(cmp : Int32, dtype : Int32, a : Void*, a_desc : Desc*, scalar_host : Void*,
                         scalar_on_left : Int32, out : UInt8*, out_desc : Desc*) : Int32
+  fun ph_compare3(dtype : Int32, a : Void*, a_desc : Desc*, b : Void*, b_desc : Desc*, out : Int32*, out_desc : Desc*) : Int32
+  fun ph_compare3_scalar(dtype : Int32, a : Void*, a_desc : Desc*, scalar_host : Void*, scalar_on_left : Int32,
+                         out : Int32*, out_desc : Desc*) : Int32
   fun ph_mask_set_scalar(elem_size : Int32, dst : Void*, dst_desc : Desc*, mask : UInt8*, mask_desc : Desc*,
                          scalar_host : Void*) : Int32
   fun ph_mask_set_array(elem_size : Int32, dst : Void*, dst_desc : Desc*, mask : UInt8*, mask_desc : Desc*,
@@ -157,6 +166,12 @@ lib LibPhGpu
   fun ph_comm_unique_id(out128 : UInt8*) : Int32
   fun ph_comm_init(nranks : Int32, rank : Int32, id128 : UInt8*) : Int32
   fun ph_comm_destroy : Int32
+  fun ph_comm_p2p_ready(out_ready : Int32*) : Int32
+  fun ph_symm_alloc(nbytes : LibC::SizeT, out_dev : Void**) : Int32
+  fun ph_symm_free(dev : Void*) : Int32
+  fun ph_symm_peer(local_dev : Void*, peer_rank : Int32, out_peer_dev : Void**) : Int32
+  fun ph_reduce_full_sharded(red : Int32, dtype : Int32, a : Void*, a_desc : Desc*, elems_before : Int64,
+                             out_value_host : Void*, out_index_host : Int64*, out_flags : UInt32*) : Int32
   fun ph_allreduce(red : Int32, dtype : Int32, buf_dev : Void*, count : Int64) : Int32
   fun ph_allgather(send_dev : Void*, recv_dev : Void*, nbytes_per_rank : Int64) : Int32
   fun ph_alltoallv(send_dev : Void**, send_bytes : Int64*, recv_dev : Void**, recv_bytes : Int64*) : Int32

@@ -130,6 +130,20 @@ int32_t ph_host_free(void* host);
 int32_t ph_sync(void);
 void*   ph_stream(void);                      /* the cudaStream_t launches go to */
 int32_t ph_set_stream(void* cuda_stream);     /* adopt a caller-owned stream (0 = own) */
+/* Caller-visible streams, for chunked host <-> device pipelines written with the array API (upload of
+ * chunk i+1, the operators of chunk i and the download of chunk i-1 overlap: PCIe is full duplex).
+ * ph_set_stream(s) makes `s` the stream every later call launches on; ph_stream_wait orders two streams;
+ * ph_free_on releases a block on the stream it was used on.  ph_h2d / ph_d2h_async are asynchronous when
+ * the host side is pinned (ph_host_alloc). */
+int32_t ph_stream_create(void** out_stream);
+int32_t ph_stream_destroy(void* stream);
+int32_t ph_stream_wait(void* waiter_stream, void* signaler_stream);   /* NULL = the library's own stream */
+int32_t ph_stream_sync(void* stream);
+int32_t ph_free_on(void* dev, void* stream);
+/* Position-weighted 64-bit checksum of a device buffer: sum of word_i * (2 * (i + word_offset) + 1) mod 2^64
+ * over its 8-byte words.  Independent of grid and sharding (ranks pass the GLOBAL index of their first word
+ * and add their values), sensitive to where every word sits.  Verification aid (bench.py field_hash). */
+int32_t ph_checksum64(const void* dev, size_t nbytes, uint64_t word_offset, uint64_t* out_host);
 const char* ph_last_error_string(void);
 int32_t ph_take_arith_flags(uint32_t* out_flags);    /* read + clear; synchronises */
 int32_t ph_timer_start(void);                 /* CUDA event on ph_stream */
@@ -172,6 +186,17 @@ int32_t ph_compare_scalar(int32_t cmp, int32_t dtype,
                           const void* a, const ph_desc* a_desc,
                           const void* scalar_host, int32_t scalar_on_left,
                           uint8_t* out, const ph_desc* out_desc);
+
+/* `<=>` of the operator list (src/multi_indexable.cr:960-981): -1 / 0 / 1 as Int32, INTEGER element
+ * types only (Float#<=> is Int32?, nil against NaN: PH_ERR_UNSUPPORTED). */
+int32_t ph_compare3(int32_t dtype,
+                    const void* a, const ph_desc* a_desc,
+                    const void* b, const ph_desc* b_desc,
+                    int32_t* out, const ph_desc* out_desc);
+int32_t ph_compare3_scalar(int32_t dtype,
+                           const void* a, const ph_desc* a_desc,
+                           const void* scalar_host, int32_t scalar_on_left,
+                           int32_t* out, const ph_desc* out_desc);
 
 /* ---- masked store (K4): NArray#[]=(mask, value) src/n_array.cr:510-551,
  *      MultiWritable#set_mask src/multi_writable.cr:154-172 ------------------- */
@@ -254,6 +279,30 @@ int32_t ph_heat_pass_slab(int32_t dtype, int32_t rank, const int64_t* extents,
 int32_t ph_comm_unique_id(uint8_t* out128);                 /* rank 0; broadcast by the host */
 int32_t ph_comm_init(int32_t nranks, int32_t rank, const uint8_t* id128);
 int32_t ph_comm_destroy(void);
+/* 1 when every rank has mapped its peers' memory (CUDA IPC over NVLink / NVSwitch): sharded reductions then
+ * combine inside the reduction kernel and the stencil delivers its own halos (no NCCL on either path).
+ * 0 (IPC refused, PH_NO_P2P=1, a single rank): the NCCL forms of the same entry points run instead. */
+int32_t ph_comm_p2p_ready(int32_t* out);
+/* Peer-mapped device memory for arrays whose kernels write into a neighbour rank (heat slabs).
+ * COLLECTIVE: every rank calls ph_symm_alloc / ph_symm_free in the same order.  Works (as a plain
+ * allocation) without P2P too.  ph_symm_peer: the address of `local_dev` (any address inside a
+ * ph_symm_alloc block) in rank `peer_rank`'s copy of that block, NULL when not mapped. */
+int32_t ph_symm_alloc(size_t nbytes, void** out_dev);
+int32_t ph_symm_free(void* dev);
+int32_t ph_symm_peer(const void* local_dev, int32_t peer_rank, void** out_peer_dev);
+/* Full reduction of an array sharded along axis 0 (Enumerable#sum/min/max and the argmax idiom over the
+ * whole distributed array; src/n_array.cr:556-564, README.md:56-61).  COLLECTIVE: every rank passes its
+ * shard (possibly EMPTY: it contributes the identity) and `elems_before` = the number of elements owned by
+ * lower ranks.  Every rank receives the same result: value in `out_value_host`, for ARG* the GLOBAL flat
+ * index of the first extremum in `out_index_host` (-1: every shard is empty -> the host raises EmptyError
+ * for min/max).  Integer SUM is overflow-checked over the lexicographic fold of the GLOBAL array.
+ * `out_flags` receives the arithmetic flags of every rank, read and cleared (PH_FLAG_*).
+ * One kernel launch per rank and one synchronisation: the last block stores the rank's partial into every
+ * peer's slot over NVLink and folds the N slots in rank order (deterministic); NCCL allgather of the
+ * records + a second tiny launch when peers are not mapped (or PH_REDUCE_NCCL=1). */
+int32_t ph_reduce_full_sharded(int32_t red, int32_t dtype, const void* a, const ph_desc* a_desc,
+                               int64_t elems_before, void* out_value_host, int64_t* out_index_host,
+                               uint32_t* out_flags);
 int32_t ph_allreduce(int32_t red, int32_t dtype, void* buf_dev, int64_t count); /* SUM/MIN/MAX in place */
 int32_t ph_allgather(const void* send_dev, void* recv_dev, int64_t nbytes_per_rank);
 /* personalised all-to-all (the exchange step of a transpose across axis-0 shards): arrays of
@@ -270,7 +319,10 @@ int32_t ph_halo_exchange(const void* send_lo, void* recv_lo, int32_t lo_rank,
  * holds `ghost_planes` (1 or 2) ghost planes on either side of its owned planes
  * (local_extents[0] = owned + 2 * ghost_planes).  With 2 ghost planes a rank-3 grid advances
  * two time steps per pass over HBM and per exchange (bit-identical to single steps).
- * *final_is_b (may be NULL) = 1 when the final state is in buf_b. */
+ * *final_is_b (may be NULL) = 1 when the final state is in buf_b.
+ * When both slabs come from ph_symm_alloc and peers are mapped, a pass is ONE launch: the stencil kernel
+ * stores the planes its neighbours need straight into their ghost planes and releases their flag words
+ * (compute + halo in one kernel, no ncclSend/ncclRecv; PH_HEAT_NCCL=1 forces the NCCL form for A/B). */
 int32_t ph_heat_run_sharded(int32_t dtype, int32_t rank, const int64_t* local_extents,
                             const void* coeff_host, int32_t ghost_planes, void* buf_a, void* buf_b,
                             int64_t steps, int32_t* final_is_b);

@@ -8,10 +8,12 @@ from .narray import (DeviceNArray, DeviceView, make_region, cover_region, ShapeE
                      CrDivisionByZeroError, CrArgumentError, CrEmptyError, DeviceBlockError)
 
 from .region import R, Step, rng, ALL
+from .narray import Stream, pinned_empty, pinned_from, sync
 from . import heat
 from . import io
 from . import sharding
+from . import pipeline
 
-__all__ = ["DeviceNArray", "DeviceView", "make_region", "cover_region", "R", "Step", "rng", "ALL", "heat", "io", "sharding", "PhDesc", "PhError", "init", "load", "check", "K", "ShapeError", "DimensionError",
+__all__ = ["Stream", "pinned_empty", "pinned_from", "sync", "pipeline", "DeviceNArray", "DeviceView", "make_region", "cover_region", "R", "Step", "rng", "ALL", "heat", "io", "sharding", "PhDesc", "PhError", "init", "load", "check", "K", "ShapeError", "DimensionError",
            "CrIndexError", "CrOverflowError", "CrDivisionByZeroError", "CrArgumentError", "CrEmptyError",
            "DeviceBlockError"]

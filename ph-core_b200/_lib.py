@@ -136,7 +136,10 @@ def load() -> C.CDLL:
         "ph_h2d": [vp, vp, C.c_size_t], "ph_d2h": [vp, vp, C.c_size_t], "ph_d2h_async": [vp, vp, C.c_size_t],
         "ph_d2h_flags": [vp, vp, C.c_size_t, C.POINTER(C.c_uint32)], "ph_d2d": [vp, vp, C.c_size_t],
         "ph_host_alloc": [C.c_size_t, C.POINTER(vp)], "ph_host_free": [vp],
-        "ph_sync": [], "ph_set_stream": [vp], "ph_take_arith_flags": [C.POINTER(C.c_uint32)],
+        "ph_sync": [], "ph_set_stream": [vp], "ph_stream_create": [C.POINTER(vp)], "ph_stream_destroy": [vp],
+        "ph_stream_wait": [vp, vp], "ph_stream_sync": [vp], "ph_free_on": [vp, vp],
+        "ph_checksum64": [vp, C.c_size_t, C.c_uint64, C.POINTER(C.c_uint64)],
+        "ph_compare3": [i32, vp, dp, vp, dp, vp, dp], "ph_compare3_scalar": [i32, vp, dp, vp, i32, vp, dp], "ph_take_arith_flags": [C.POINTER(C.c_uint32)],
         "ph_timer_start": [], "ph_timer_stop": [C.POINTER(C.c_float)],
         "ph_ewise_binary": [i32, i32, vp, dp, vp, dp, vp, dp],
         "ph_ewise_scalar": [i32, i32, vp, dp, vp, i32, vp, dp],
@@ -157,6 +160,9 @@ def load() -> C.CDLL:
         "ph_heat_pass_slab": [i32, i32, C.POINTER(i64), vp, i32, i32, i32, i32, i64, i64, vp, vp, vp],
         "ph_comm_unique_id": [vp], "ph_comm_init": [i32, i32, vp], "ph_comm_destroy": [],
         "ph_allreduce": [i32, i32, vp, i64], "ph_allgather": [vp, vp, i64],
+        "ph_comm_p2p_ready": [C.POINTER(i32)], "ph_symm_alloc": [C.c_size_t, C.POINTER(vp)], "ph_symm_free": [vp],
+        "ph_symm_peer": [vp, i32, C.POINTER(vp)],
+        "ph_reduce_full_sharded": [i32, i32, vp, dp, i64, vp, C.POINTER(i64), C.POINTER(C.c_uint32)],
         "ph_alltoallv": [C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), C.POINTER(i64)],
         "ph_halo_exchange": [vp, vp, i32, vp, vp, i32, i64, vp],
         "ph_heat_run_sharded": [i32, i32, C.POINTER(i64), vp, i32, vp, vp, i64, C.POINTER(i32)],

@@ -6,8 +6,12 @@
 // exchanged by grouped ncclSend/ncclRecv on a side stream while the interior planes are
 // being updated on the main stream.
 #include "ph_common.cuh"
+#include "comm.cuh"
+#include <cuda.h>
 #include <stdlib.h>
 #include <dlfcn.h>
+#include <vector>
+#include <algorithm>
 #include <nccl.h>   // types only: the library is resolved at run time (see nccl_api)
 
 namespace ph {
@@ -79,8 +83,254 @@ static int32_t check_nccl(ncclResult_t r, const char* what) {
 
 int32_t heat_slab_dispatch(int32_t dtype, int rank, const int64_t* ext, const void* coeff_host, int ghost, int has_lo,
                            int has_hi, int64_t p_begin, int64_t p_end, const void* in, void* out,
-                           cudaStream_t stream, bool two_step);
+                           cudaStream_t stream, bool two_step, const HeatMirror* mir, bool* mirrored);
 bool heat_two_step_usable(int32_t dtype, int rank, const int64_t* ext);
+
+// ---------------------------------------------------------------- peer-mapped memory (CUDA IPC over NVLink)
+PeerInfo& peers() {
+  static PeerInfo p;
+  return p;
+}
+bool comm_is_multi() { return cm().inited && cm().nranks > 1; }
+
+struct SymmAlloc {
+  char* local = nullptr;
+  size_t nbytes = 0;
+  bool mapped = false;
+  char* peer[PH_MAX_PEERS] = {nullptr};
+};
+static std::vector<SymmAlloc>& symm_table() {
+  static std::vector<SymmAlloc> t;
+  return t;
+}
+static const SymmAlloc* symm_find(const void* p) {
+  const char* q = reinterpret_cast<const char*>(p);
+  for (const SymmAlloc& a : symm_table())
+    if (q >= a.local && q < a.local + a.nbytes) return &a;
+  return nullptr;
+}
+
+static int32_t ensure_exchange_buffers() {
+  PeerInfo& p = peers();
+  if (!p.gather_send) {
+    PH_CUDA(cudaMalloc((void**)&p.gather_send, sizeof(ReduceSlot) * PH_MAX_PEERS));
+    PH_CUDA(cudaMalloc((void**)&p.gather_recv, sizeof(ReduceSlot) * PH_MAX_PEERS));
+    PH_CUDA(cudaMemset(p.gather_send, 0, sizeof(ReduceSlot) * PH_MAX_PEERS));
+    PH_CUDA(cudaMemset(p.gather_recv, 0, sizeof(ReduceSlot) * PH_MAX_PEERS));
+  }
+  if (!p.host_result) {
+    PH_CUDA(cudaHostAlloc((void**)&p.host_result, 64, cudaHostAllocMapped));
+    memset(p.host_result, 0, 64);
+    PH_CUDA(cudaHostGetDevicePointer((void**)&p.host_result_dev, p.host_result, 0));
+  }
+  return PH_OK;
+}
+
+int32_t comm_allgather_records(cudaStream_t s) {
+  Comm& c = cm();
+  PeerInfo& p = peers();
+  if (c.nranks == 1) {
+    PH_CUDA(cudaMemcpyAsync(p.gather_recv, p.gather_send, sizeof(ReduceSlot), cudaMemcpyDeviceToDevice, s));
+    return PH_OK;
+  }
+  PH_NCCL(nccl().AllGather(p.gather_send + c.rank, p.gather_recv, sizeof(ReduceSlot), ncclUint8, c.comm, s));
+  return PH_OK;
+}
+
+// 64 bytes from every rank to every rank through the host (set-up paths only)
+static int32_t exchange64(const void* mine, void* all /* nranks x 64 */) {
+  Comm& c = cm();
+  PeerInfo& p = peers();
+  cudaStream_t s = rt().stream;
+  PH_CUDA(cudaMemcpyAsync(p.gather_send + c.rank, mine, 64, cudaMemcpyHostToDevice, s));
+  int32_t st = comm_allgather_records(s);
+  if (st != PH_OK) return st;
+  PH_CUDA(cudaMemcpyAsync(all, p.gather_recv, (size_t)64 * c.nranks, cudaMemcpyDeviceToHost, s));
+  PH_CUDA(cudaStreamSynchronize(s));
+  return PH_OK;
+}
+
+// every rank reports `ok`; true only when all did (so that all ranks take the same path afterwards)
+static int32_t all_agree(bool ok, bool* all_ok) {
+  uint64_t mine[8] = {ok ? 1ull : 0ull, 0, 0, 0, 0, 0, 0, 0};
+  uint64_t all[8 * PH_MAX_PEERS];
+  int32_t st = exchange64(mine, all);
+  if (st != PH_OK) return st;
+  *all_ok = true;
+  for (int r = 0; r < cm().nranks; r++) if (all[8 * r] != 1ull) *all_ok = false;
+  return PH_OK;
+}
+
+// export `local`, import everybody else's: peer[r] = rank r's allocation mapped into this process
+static int32_t map_peers(void* local, char** peer, bool* mapped) {
+  Comm& c = cm();
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "an IPC handle travels as one 64-byte record");
+  cudaIpcMemHandle_t mine, all[PH_MAX_PEERS];
+  memset(&mine, 0, sizeof(mine));
+  bool ok = cudaIpcGetMemHandle(&mine, local) == cudaSuccess;
+  if (!ok) cudaGetLastError();
+  int32_t st = exchange64(&mine, all);
+  if (st != PH_OK) return st;
+  bool all_exported = false;
+  if ((st = all_agree(ok, &all_exported)) != PH_OK) return st;
+  for (int r = 0; r < c.nranks; r++) peer[r] = nullptr;
+  peer[c.rank] = reinterpret_cast<char*>(local);
+  if (all_exported) {
+    for (int r = 0; r < c.nranks && ok; r++) {
+      if (r == c.rank) continue;
+      void* q = nullptr;
+      if (cudaIpcOpenMemHandle(&q, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; }
+      else peer[r] = reinterpret_cast<char*>(q);
+    }
+  }
+  bool all_mapped = false;
+  if ((st = all_agree(ok && all_exported, &all_mapped)) != PH_OK) return st;
+  if (!all_mapped)
+    for (int r = 0; r < c.nranks; r++)
+      if (r != c.rank && peer[r]) { cudaIpcCloseMemHandle(peer[r]); peer[r] = nullptr; }
+  *mapped = all_mapped;
+  return PH_OK;
+}
+
+static void p2p_teardown() {
+  PeerInfo& p = peers();
+  for (SymmAlloc& a : symm_table()) {
+    for (int r = 0; r < PH_MAX_PEERS; r++)
+      if (a.mapped && a.peer[r] && a.peer[r] != a.local) cudaIpcCloseMemHandle(a.peer[r]);
+    if (a.local) cudaFree(a.local);
+  }
+  symm_table().clear();
+  for (int r = 0; r < PH_MAX_PEERS; r++)
+    if (p.ctrl[r] && r != p.rank) cudaIpcCloseMemHandle(p.ctrl[r]);
+  if (p.ctrl[p.rank]) cudaFree(p.ctrl[p.rank]);
+  if (p.gather_send) cudaFree(p.gather_send);
+  if (p.gather_recv) cudaFree(p.gather_recv);
+  if (p.host_result) cudaFreeHost(p.host_result);
+  cudaGetLastError();
+  p = PeerInfo();
+}
+
+// Map every peer's control block.  Failure is not an error: the NCCL paths remain (PH_NO_P2P=1 forces that).
+static int32_t p2p_setup() {
+  Comm& c = cm();
+  PeerInfo& p = peers();
+  p.nranks = c.nranks;
+  p.rank = c.rank;
+  int32_t st = ensure_exchange_buffers();
+  if (st != PH_OK) return st;
+  if (c.nranks == 1 || c.nranks > PH_MAX_PEERS || getenv("PH_NO_P2P")) return PH_OK;
+  CtrlBlock* mine = nullptr;
+  const size_t bytes = std::max<size_t>(sizeof(CtrlBlock), (size_t)2 << 20);     // its own 2 MiB granule
+  PH_CUDA(cudaMalloc((void**)&mine, bytes));
+  PH_CUDA(cudaMemset(mine, 0, bytes));
+  PH_CUDA(cudaDeviceSynchronize());
+  char* peer[PH_MAX_PEERS];
+  bool mapped = false;
+  if ((st = map_peers(mine, peer, &mapped)) != PH_OK) return st;
+  if (!mapped) { cudaFree(mine); return PH_OK; }
+  for (int r = 0; r < c.nranks; r++) p.ctrl[r] = reinterpret_cast<CtrlBlock*>(peer[r]);
+  p.ready = true;
+  return PH_OK;
+}
+
+int32_t comm_combine_args(CombineArgs* out, int64_t elems_before) {
+  Comm& c = cm();
+  PeerInfo& p = peers();
+  if (!c.inited) return set_error(PH_ERR_NOT_INIT, "ph_comm_init was not called");
+  int32_t st = ensure_exchange_buffers();
+  if (st != PH_OK) return st;
+  CombineArgs a;
+  a.nranks = c.nranks;
+  a.rank = c.rank;
+  a.seq = ++p.reduce_seq;
+  a.elems_before = elems_before;
+  a.host_out = p.host_result_dev;
+  static const bool force_nccl = getenv("PH_REDUCE_NCCL") != nullptr;       // A/B knob: NCCL transport of the records
+  if (c.nranks > 1) {
+    if (p.ready && !force_nccl) {
+      const int parity = (int)(a.seq & 1u);
+      a.my_slots = &p.ctrl[c.rank]->slot[parity][0];
+      for (int r = 0; r < c.nranks; r++) a.peer_slots[r] = &p.ctrl[r]->slot[parity][0];
+    } else {
+      a.my_slots = p.gather_send;
+      a.peer_slots[0] = nullptr;
+    }
+  }
+  *out = a;
+  return PH_OK;
+}
+
+// ---- stream-ordered signal / wait on flag words in the control blocks
+typedef CUresult (*StreamWaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static StreamWaitValue32Fn stream_wait_fn() {
+  static StreamWaitValue32Fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    if (!getenv("PH_P2P_SPIN_WAIT")) {
+      void* q = nullptr;
+      cudaDriverEntryPointQueryResult res;
+      if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &q, cudaEnableDefault, &res) == cudaSuccess &&
+          res == cudaDriverEntryPointSuccess)
+        fn = (StreamWaitValue32Fn)q;
+      else
+        cudaGetLastError();
+    }
+  }
+  return fn;
+}
+static __global__ void wait_flag_kernel(const volatile uint32_t* flag, uint32_t value, uint32_t* err_flags) {
+  const long long t0 = clock64();
+  while ((int32_t)(*flag - value) < 0) {
+    if (clock64() - t0 > 20000000000LL) { atomicOr(err_flags + 1, 1u); break; }     // ~10 s: a neighbour died
+  }
+  __threadfence_system();
+}
+int32_t stream_wait_geq(cudaStream_t s, uint32_t* flag_dev, uint32_t value) {
+  if (StreamWaitValue32Fn fn = stream_wait_fn()) {
+    CUresult r = fn((CUstream)s, (CUdeviceptr)flag_dev, value, CU_STREAM_WAIT_VALUE_GEQ);
+    if (r != CUDA_SUCCESS) return set_error(PH_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", (int)r);
+    return PH_OK;
+  }
+  wait_flag_kernel<<<1, 1, 0, s>>>(flag_dev, value, rt().d_flags);
+  PH_LAUNCH_CHECK("wait_flag_kernel");
+  return PH_OK;
+}
+
+static __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// "I have reached the start of run `event`, my slab has `my_planes` planes": everything this rank launched
+// before is complete (stream order), so the neighbours may write into its ghost planes again
+static __global__ void halo_hello_kernel(uint32_t* flag_lo, uint32_t* flag_hi, int64_t* planes_lo, int64_t* planes_hi,
+                                         int64_t my_planes, uint32_t event) {
+  if (planes_lo) *reinterpret_cast<volatile int64_t*>(planes_lo) = my_planes;
+  if (planes_hi) *reinterpret_cast<volatile int64_t*>(planes_hi) = my_planes;
+  __threadfence_system();
+  if (flag_lo) st_release_sys(flag_lo, event);
+  if (flag_hi) st_release_sys(flag_hi, event);
+}
+// copy my edge planes into the neighbours' ghost planes (peer stores), then release their flags
+static __global__ void __launch_bounds__(256) halo_push_kernel(const uint4* __restrict__ src_lo, uint4* __restrict__ dst_lo,
+                                                               const uint4* __restrict__ src_hi, uint4* __restrict__ dst_hi,
+                                                               int64_t n16, uint32_t* ticket, uint32_t* flag_lo,
+                                                               uint32_t* flag_hi, uint32_t event) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    if (dst_lo) dst_lo[i] = src_lo[i];
+    if (dst_hi) dst_hi[i] = src_hi[i];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+      *ticket = 0;
+      __threadfence_system();
+      if (flag_lo) st_release_sys(flag_lo, event);
+      if (flag_hi) st_release_sys(flag_hi, event);
+    }
+  }
+}
 
 static int32_t nccl_type(int32_t dtype, ncclDataType_t* t) {
   switch (dtype) {
@@ -136,21 +386,77 @@ int32_t ph_comm_init(int32_t nranks, int32_t rank, const uint8_t* id128) {
   if (c.inited) ph_comm_destroy();
   if (nranks < 1 || rank < 0 || rank >= nranks) return set_error(PH_ERR_INVALID, "bad rank %d of %d", rank, nranks);
   c.nranks = nranks; c.rank = rank;
-  if (nranks == 1) { c.inited = true; c.comm = nullptr; return PH_OK; }
+  if (nranks == 1) { c.inited = true; c.comm = nullptr; return p2p_setup(); }
   if (!id128) return set_error(PH_ERR_INVALID, "null unique id");
   PH_NCCL_LOAD();
   ncclUniqueId id;
   memcpy(&id, id128, 128);
   PH_NCCL(nccl().CommInitRank(&c.comm, nranks, id, rank));
   c.inited = true;
+  return p2p_setup();     // map the peers' control blocks (CUDA IPC); the NCCL paths remain when that is impossible
+}
+
+int32_t ph_comm_p2p_ready(int32_t* out) {
+  if (!out) return set_error(PH_ERR_INVALID, "null out");
+  *out = peers().ready ? 1 : 0;
+  return PH_OK;
+}
+
+int32_t ph_symm_alloc(size_t nbytes, void** out_dev) {
+  PH_REQUIRE_INIT();
+  Comm& c = cm();
+  if (!c.inited) return set_error(PH_ERR_NOT_INIT, "ph_comm_init was not called");
+  if (!out_dev) return set_error(PH_ERR_INVALID, "null out_dev");
+  *out_dev = nullptr;
+  SymmAlloc a;
+  a.nbytes = nbytes ? nbytes : 1;
+  PH_CUDA(cudaMalloc((void**)&a.local, a.nbytes));
+  if (peers().ready) {
+    int32_t st = map_peers(a.local, a.peer, &a.mapped);
+    if (st != PH_OK) { cudaFree(a.local); return st; }
+  }
+  symm_table().push_back(a);
+  *out_dev = a.local;
+  return PH_OK;
+}
+
+int32_t ph_symm_free(void* dev) {
+  PH_REQUIRE_INIT();
+  if (!dev) return PH_OK;
+  std::vector<SymmAlloc>& t = symm_table();
+  for (size_t i = 0; i < t.size(); i++) {
+    if (t[i].local != dev) continue;
+    PH_CUDA(cudaDeviceSynchronize());
+    if (t[i].mapped) {
+      bool dummy;
+      int32_t st = all_agree(true, &dummy);        // nobody unmaps while a peer may still be writing
+      if (st != PH_OK) return st;
+      for (int r = 0; r < cm().nranks; r++)
+        if (t[i].peer[r] && t[i].peer[r] != t[i].local) cudaIpcCloseMemHandle(t[i].peer[r]);
+      if ((st = all_agree(true, &dummy)) != PH_OK) return st;     // every importer has let go before the owner frees
+    }
+    PH_CUDA(cudaFree(t[i].local));
+    t.erase(t.begin() + (long)i);
+    return PH_OK;
+  }
+  return set_error(PH_ERR_INVALID, "ph_symm_free: not a ph_symm_alloc pointer");
+}
+
+int32_t ph_symm_peer(const void* local_dev, int32_t peer_rank, void** out_peer_dev) {
+  if (!out_peer_dev) return set_error(PH_ERR_INVALID, "null out_peer_dev");
+  *out_peer_dev = nullptr;
+  const SymmAlloc* a = symm_find(local_dev);
+  if (!a || !a->mapped || peer_rank < 0 || peer_rank >= cm().nranks) return PH_OK;
+  *out_peer_dev = a->peer[peer_rank] + (reinterpret_cast<const char*>(local_dev) - a->local);
   return PH_OK;
 }
 
 int32_t ph_comm_destroy(void) {
   Comm& c = cm();
-  if (c.inited && c.comm) {
+  if (c.inited) {
     cudaDeviceSynchronize();
-    nccl().CommDestroy(c.comm);
+    p2p_teardown();
+    if (c.comm) nccl().CommDestroy(c.comm);
   }
   c = Comm();
   return PH_OK;
@@ -255,6 +561,103 @@ int32_t ph_heat_run_sharded(int32_t dtype, int32_t rank, const int64_t* local_ex
   *final_is_b = 0;
   const bool can_two = g == 2 && heat_two_step_usable(dtype, rank, local_extents);
 
+  const int64_t own_b = g, own_e = n0 - g;
+
+  // ---- P2P path: both slabs live in peer-mapped memory (ph_symm_alloc) -> no NCCL, no side stream.
+  // A pass is ONE launch over all owned planes: the marches at either end of the slab are dispatched first
+  // and store the planes the neighbours need straight into their ghost planes (compute + halo in one
+  // kernel); the last of those blocks releases the neighbour's flag word, and the neighbour's next pass is
+  // stream-ordered behind a wait on it.  Events are numbered identically on every rank (same calls, same
+  // step counts): hello, initial ghosts, then one per pass.
+  {
+    PeerInfo& P = peers();
+    static const bool force_nccl = getenv("PH_HEAT_NCCL") != nullptr;           // A/B knob
+    void *pa_lo = nullptr, *pb_lo = nullptr, *pa_hi = nullptr, *pb_hi = nullptr;
+    bool p2p = P.ready && !force_nccl && c.nranks > 1 && (g * pbytes) % 16 == 0 && ((uintptr_t)buf_a % 16) == 0 &&
+               ((uintptr_t)buf_b % 16) == 0;
+    if (p2p) {
+      if (has_lo) { ph_symm_peer(buf_a, lo, &pa_lo); ph_symm_peer(buf_b, lo, &pb_lo); p2p = p2p && pa_lo && pb_lo; }
+      if (has_hi) { ph_symm_peer(buf_a, hi, &pa_hi); ph_symm_peer(buf_b, hi, &pb_hi); p2p = p2p && pa_hi && pb_hi; }
+      if (!symm_find(buf_a) || !symm_find(buf_b)) p2p = false;
+    }
+    if (p2p) {
+      cudaStream_t s = r.stream;
+      CtrlBlock* me = P.ctrl[c.rank];
+      uint32_t* nbr_flag_lo = has_lo ? &P.ctrl[lo]->halo_flag[1] : nullptr;    // I am lo's HI neighbour
+      uint32_t* nbr_flag_hi = has_hi ? &P.ctrl[hi]->halo_flag[0] : nullptr;
+      auto wait_nbrs = [&](uint32_t ev) -> int32_t {
+        int32_t w = PH_OK;
+        if (has_lo && (w = stream_wait_geq(s, &me->halo_flag[0], ev)) != PH_OK) return w;
+        if (has_hi && (w = stream_wait_geq(s, &me->halo_flag[1], ev)) != PH_OK) return w;
+        return PH_OK;
+      };
+      // hello: my earlier work is complete (stream order) and this is my plane count
+      uint32_t ev = ++P.halo_event;
+      halo_hello_kernel<<<1, 1, 0, s>>>(nbr_flag_lo, nbr_flag_hi, has_lo ? &P.ctrl[lo]->nbr_planes[1] : nullptr,
+                                        has_hi ? &P.ctrl[hi]->nbr_planes[0] : nullptr, n0, ev);
+      PH_LAUNCH_CHECK("halo_hello_kernel");
+      int32_t st = wait_nbrs(ev);
+      if (st != PH_OK) return st;
+      int64_t nbr_planes[2] = {0, 0};
+      PH_CUDA(cudaMemcpyAsync(nbr_planes, me->nbr_planes, sizeof(nbr_planes), cudaMemcpyDeviceToHost, s));
+      PH_CUDA(cudaStreamSynchronize(s));
+      const int64_t n0_lo = nbr_planes[0];
+      char* peer_bufs_lo[2] = {reinterpret_cast<char*>(pa_lo), reinterpret_cast<char*>(pb_lo)};
+      char* peer_bufs_hi[2] = {reinterpret_cast<char*>(pa_hi), reinterpret_cast<char*>(pb_hi)};
+      // my g lowest owned planes -> lo's upper ghosts [n0_lo - g, n0_lo); my g highest -> hi's lower ghosts [0, g)
+      auto push = [&](int which, uint32_t event) -> int32_t {
+        const int64_t n16 = g * pbytes / 16;
+        const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)r.sm_count * 4, ceil_div(n16, (int64_t)256 * 4)));
+        halo_push_kernel<<<blocks, 256, 0, s>>>(
+            reinterpret_cast<const uint4*>(bufs[which] + own_b * pbytes),
+            has_lo ? reinterpret_cast<uint4*>(peer_bufs_lo[which] + (n0_lo - g) * pbytes) : nullptr,
+            reinterpret_cast<const uint4*>(bufs[which] + (own_e - g) * pbytes),
+            has_hi ? reinterpret_cast<uint4*>(peer_bufs_hi[which]) : nullptr, n16, &me->halo_ticket[2], nbr_flag_lo,
+            nbr_flag_hi, event);
+        PH_LAUNCH_CHECK("halo_push_kernel");
+        return PH_OK;
+      };
+      ev = ++P.halo_event;
+      if ((st = push(0, ev)) != PH_OK) return st;
+      if (!has_lo) PH_CUDA(cudaMemcpyAsync(bufs[1] + g * pbytes, bufs[0] + g * pbytes, pbytes, cudaMemcpyDeviceToDevice, s));
+      if (!has_hi) PH_CUDA(cudaMemcpyAsync(bufs[1] + (n0 - g - 1) * pbytes, bufs[0] + (n0 - g - 1) * pbytes, pbytes,
+                                           cudaMemcpyDeviceToDevice, s));
+      int cur = 0;
+      int64_t left = steps;
+      while (left > 0) {
+        const bool two = can_two && left >= 2;
+        if ((st = wait_nbrs(ev)) != PH_OK) return st;        // my ghosts of `in` are complete; theirs of `out` are free
+        ev = ++P.halo_event;
+        const char* in = bufs[cur];
+        char* out = bufs[cur ^ 1];
+        HeatMirror mir;
+        if (has_lo) {
+          mir.lo_end = own_b + g;
+          mir.delta_lo = (peer_bufs_lo[cur ^ 1] - out) + (n0_lo - g - own_b) * pbytes;
+          mir.flag_lo = nbr_flag_lo;
+        }
+        if (has_hi) {
+          mir.hi_begin = own_e - g;
+          mir.delta_hi = (peer_bufs_hi[cur ^ 1] - out) - (own_e - g) * pbytes;
+          mir.flag_hi = nbr_flag_hi;
+        }
+        mir.ticket = me->halo_ticket;
+        mir.event = ev;
+        bool mirrored = false;
+        st = heat_slab_dispatch(dtype, rank, local_extents, coeff_host, g, has_lo, has_hi, own_b, own_e, in, out, s, two,
+                                two ? &mir : nullptr, &mirrored);
+        if (st != PH_OK) return st;
+        if (!mirrored && (st = push(cur ^ 1, ev)) != PH_OK) return st;
+        cur ^= 1;
+        left -= two ? 2 : 1;
+      }
+      if ((st = wait_nbrs(ev)) != PH_OK) return st;          // the ghosts of the final state have arrived
+      *final_is_b = cur;
+      return PH_OK;
+    }
+  }
+
+  // ---- NCCL path
   // g lowest owned planes -> lo neighbour's upper ghosts, g highest owned planes -> hi neighbour's lower ghosts
   auto exchange = [&](char* buf, cudaStream_t s) {
     return halo_exchange_impl(buf + g * pbytes, buf, lo, buf + (n0 - 2 * g) * pbytes, buf + (n0 - g) * pbytes, hi,
@@ -274,7 +677,6 @@ int32_t ph_heat_run_sharded(int32_t dtype, int32_t rank, const int64_t* local_ex
   //   edges(k)    <- exchange(k-1) [same stream], interior(k-1) [ev_a: main -> side]
   //   interior(k) <- edges(k-1)                  [ev_b: side -> main]
   static const bool no_overlap = getenv("PH_HEAT_NO_OVERLAP") != nullptr;    // measurement knob
-  const int64_t own_b = g, own_e = n0 - g;
   const bool split = own_e - own_b > 2 * g && c.nranks > 1 && !no_overlap;
   cudaStream_t side = r.aux_stream;
   if (split) {
@@ -289,7 +691,7 @@ int32_t ph_heat_run_sharded(int32_t dtype, int32_t rank, const int64_t* local_ex
     const char* in = bufs[cur];
     char* out = bufs[cur ^ 1];
     auto update = [&](int64_t b, int64_t e, cudaStream_t s) {
-      return heat_slab_dispatch(dtype, rank, local_extents, coeff_host, g, has_lo, has_hi, b, e, in, out, s, two);
+      return heat_slab_dispatch(dtype, rank, local_extents, coeff_host, g, has_lo, has_hi, b, e, in, out, s, two, nullptr, nullptr);
     };
     if (split) {
       PH_CUDA(cudaStreamWaitEvent(side, r.ev_a, 0));           // previous interior

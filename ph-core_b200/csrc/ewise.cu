@@ -10,6 +10,8 @@ namespace ph {
                            const ph_desc*, bool, uint64_t, bool, uint64_t);                                \
   int32_t compare_##S(int32_t, const void*, const ph_desc*, const void*, const ph_desc*, void*,           \
                       const ph_desc*, bool, uint64_t, bool, uint64_t);                                     \
+  int32_t compare3_##S(const void*, const ph_desc*, const void*, const ph_desc*, void*, const ph_desc*,   \
+                       bool, uint64_t, bool, uint64_t);                                                    \
   int32_t unary_##S(int32_t, const void*, const ph_desc*, void*, const ph_desc*);                          \
   int32_t mul_add_##S(const void*, const ph_desc*, const void*, const ph_desc*, const void*,              \
                       const ph_desc*, void*, const ph_desc*);
@@ -110,6 +112,30 @@ int32_t ph_compare_scalar(int32_t cmp, int32_t dtype, const void* a, const ph_de
 #undef CALL
   } else {
 #define CALL(S) compare_##S(cmp, a, a_desc, nullptr, nullptr, out, out_desc, false, 0, true, bits)
+    PH_DTYPE_SWITCH(dtype, CALL)
+#undef CALL
+  }
+}
+
+int32_t ph_compare3(int32_t dtype, const void* a, const ph_desc* a_desc, const void* b, const ph_desc* b_desc,
+                    int32_t* out, const ph_desc* out_desc) {
+  PH_REQUIRE_INIT();
+#define CALL(S) compare3_##S(a, a_desc, b, b_desc, out, out_desc, false, 0, false, 0)
+  PH_DTYPE_SWITCH(dtype, CALL)
+#undef CALL
+}
+
+int32_t ph_compare3_scalar(int32_t dtype, const void* a, const ph_desc* a_desc, const void* scalar_host,
+                           int32_t scalar_on_left, int32_t* out, const ph_desc* out_desc) {
+  PH_REQUIRE_INIT();
+  if (!scalar_host) return set_error(PH_ERR_INVALID, "null scalar");
+  const uint64_t bits = host_scalar_bits(scalar_host, dtype_size(dtype));
+  if (scalar_on_left) {
+#define CALL(S) compare3_##S(nullptr, nullptr, a, a_desc, out, out_desc, true, bits, false, 0)
+    PH_DTYPE_SWITCH(dtype, CALL)
+#undef CALL
+  } else {
+#define CALL(S) compare3_##S(a, a_desc, nullptr, nullptr, out, out_desc, false, 0, true, bits)
     PH_DTYPE_SWITCH(dtype, CALL)
 #undef CALL
   }

@@ -62,6 +62,20 @@ int32_t compare_t(int32_t cmp, const void* a, const ph_desc* ad, const void* b, 
 }
 
 template <typename T>
+int32_t compare3_t(const void* a, const ph_desc* ad, const void* b, const ph_desc* bd, void* out, const ph_desc* od,
+                   bool a_param, uint64_t a_bits, bool b_param, uint64_t b_bits) {
+  if constexpr (is_float_t<T>::value) {
+    return set_error(PH_ERR_UNSUPPORTED, "<=> on floats yields Int32? (nil against NaN): not on the device path");
+  } else {
+    MapOperand ops[2];
+    fill_operands2<T>(ops, a, ad, b, bd);
+    ops[0].is_param = a_param; ops[0].param = a_bits;
+    ops[1].is_param = b_param; ops[1].param = b_bits;
+    return launch_map<SpaceshipOp<T>>(ops, out, od);
+  }
+}
+
+template <typename T>
 int32_t unary_t(int32_t op, const void* a, const ph_desc* ad, void* out, const ph_desc* od) {
   MapOperand ops[1];
   ops[0].base = a; ops[0].desc = ad;
@@ -100,6 +114,10 @@ int32_t PH_CONCAT(compare_, PH_SUFFIX)(int32_t cmp, const void* a, const ph_desc
                                        const ph_desc* bd, void* out, const ph_desc* od, bool ap,
                                        uint64_t abits, bool bp, uint64_t bbits) {
   return compare_t<PH_T>(cmp, a, ad, b, bd, out, od, ap, abits, bp, bbits);
+}
+int32_t PH_CONCAT(compare3_, PH_SUFFIX)(const void* a, const ph_desc* ad, const void* b, const ph_desc* bd, void* out,
+                                        const ph_desc* od, bool ap, uint64_t abits, bool bp, uint64_t bbits) {
+  return compare3_t<PH_T>(a, ad, b, bd, out, od, ap, abits, bp, bbits);
 }
 int32_t PH_CONCAT(unary_, PH_SUFFIX)(int32_t op, const void* a, const ph_desc* ad, void* out,
                                      const ph_desc* od) {

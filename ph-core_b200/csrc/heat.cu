@@ -22,6 +22,7 @@
 // halo is re-read (L2 hits).  Slabs for multi-GPU runs are split along axis 0, so halo
 // planes are contiguous and need no packing.
 #include "ph_common.cuh"
+#include "comm.cuh"
 #include "ops.cuh"
 #include <algorithm>
 #include <type_traits>
@@ -452,7 +453,8 @@ int32_t heat_tma_planes(const T* in, T* out, int64_t n0, int64_t n1, int64_t n2,
 
 template <typename T>
 int32_t heat_tma2_planes(const T* in, T* out, int64_t n0, int64_t n1, int64_t n2, T coeff, int64_t z_begin,
-                         int64_t z_end, int64_t fixed_lo, int64_t fixed_hi, cudaStream_t stream, bool* used);
+                         int64_t z_end, int64_t fixed_lo, int64_t fixed_hi, cudaStream_t stream, bool* used,
+                         const HeatMirror* mir);
 
 template <typename T>
 bool heat_tma2_usable(int64_t n1, int64_t n2);
@@ -534,7 +536,7 @@ static int32_t heat_run_t(int rank, const int64_t* ext, const void* coeff_host, 
           bool used = false;
           int32_t st = rank == 3
               ? heat_tma2_planes<T>(bufs[cur], bufs[cur ^ 1], ext[0], ext[1], ext[2], coeff, 1, ext[0] - 1, 0,
-                                    ext[0] - 1, r.stream, &used)
+                                    ext[0] - 1, r.stream, &used, nullptr)
               : heat2d_tb_planes<T>(bufs[cur], bufs[cur ^ 1], ext[0], ext[1], coeff, 1, ext[0] - 1, 0, ext[0] - 1,
                                     r.stream, &used);
           if (st != PH_OK) return st;
@@ -562,7 +564,8 @@ static int32_t heat_run_t(int rank, const int64_t* ext, const void* coeff_host, 
 template <typename T>
 static int32_t heat_slab_t(int rank, const int64_t* ext, const void* coeff_host, int g, int has_lo, int has_hi,
                            int64_t p_begin, int64_t p_end, const void* in_v, void* out_v, cudaStream_t stream,
-                           bool two_step) {
+                           bool two_step, const HeatMirror* mir, bool* mirrored) {
+  if (mirrored) *mirrored = false;
   T coeff;
   memcpy(&coeff, coeff_host, sizeof(T));
   const int64_t n0 = ext[0];
@@ -586,9 +589,10 @@ static int32_t heat_slab_t(int rank, const int64_t* ext, const void* coeff_host,
     if (g < 2) return set_error(PH_ERR_INVALID, "two-step slab update needs 2 ghost planes");
     bool used = false;
     const int64_t flo = has_lo ? -1 : g, fhi = has_hi ? n0 : n0 - g - 1;
-    int32_t st = rank == 3 ? heat_tma2_planes<T>(in, out, n0, ext[1], ext[2], coeff, b, e, flo, fhi, stream, &used)
+    int32_t st = rank == 3 ? heat_tma2_planes<T>(in, out, n0, ext[1], ext[2], coeff, b, e, flo, fhi, stream, &used, mir)
                            : heat2d_tb_planes<T>(in, out, n0, ext[1], coeff, b, e, flo, fhi, stream, &used);
     if (st != PH_OK) return st;
+    if (mirrored) *mirrored = used && rank == 3 && mir != nullptr;     // the kernel delivered the halo itself
     if (!used) return set_error(PH_ERR_INVALID, "two-step slab update: buffers must be 32-byte aligned");
     return PH_OK;
   }
@@ -598,10 +602,10 @@ static int32_t heat_slab_t(int rank, const int64_t* ext, const void* coeff_host,
 // exported to comm.cu
 int32_t heat_slab_dispatch(int32_t dtype, int rank, const int64_t* ext, const void* coeff_host, int ghost, int has_lo,
                            int has_hi, int64_t p_begin, int64_t p_end, const void* in, void* out,
-                           cudaStream_t stream, bool two_step) {
+                           cudaStream_t stream, bool two_step, const HeatMirror* mir, bool* mirrored) {
   if (rank < 2 || rank > 3) return set_error(PH_ERR_UNSUPPORTED, "slab stencil needs rank 2 or 3 (got %d)", rank);
-  if (dtype == PH_F32) return heat_slab_t<float>(rank, ext, coeff_host, ghost, has_lo, has_hi, p_begin, p_end, in, out, stream, two_step);
-  if (dtype == PH_F64) return heat_slab_t<double>(rank, ext, coeff_host, ghost, has_lo, has_hi, p_begin, p_end, in, out, stream, two_step);
+  if (dtype == PH_F32) return heat_slab_t<float>(rank, ext, coeff_host, ghost, has_lo, has_hi, p_begin, p_end, in, out, stream, two_step, mir, mirrored);
+  if (dtype == PH_F64) return heat_slab_t<double>(rank, ext, coeff_host, ghost, has_lo, has_hi, p_begin, p_end, in, out, stream, two_step, mir, mirrored);
   return set_error(PH_ERR_UNSUPPORTED, "the heat stencil is defined for F32 / F64");
 }
 
@@ -648,7 +652,7 @@ int32_t ph_heat_step_slab(int32_t dtype, int32_t rank, const int64_t* extents, c
   PH_REQUIRE_INIT();
   if (!extents || !coeff_host || !in || !out) return set_error(PH_ERR_INVALID, "null argument to ph_heat_step_slab");
   cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : rt().stream;
-  return heat_slab_dispatch(dtype, rank, extents, coeff_host, 1, has_lo, has_hi, p_begin, p_end, in, out, s, false);
+  return heat_slab_dispatch(dtype, rank, extents, coeff_host, 1, has_lo, has_hi, p_begin, p_end, in, out, s, false, nullptr, nullptr);
 }
 
 int32_t ph_heat_pass_slab(int32_t dtype, int32_t rank, const int64_t* extents, const void* coeff_host,
@@ -661,7 +665,7 @@ int32_t ph_heat_pass_slab(int32_t dtype, int32_t rank, const int64_t* extents, c
     return set_error(PH_ERR_UNSUPPORTED, "the two-steps-per-pass kernels cannot take this grid (rank 2 / 3, x extent a multiple of 32 / 16 bytes)");
   cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : rt().stream;
   return heat_slab_dispatch(dtype, rank, extents, coeff_host, ghost_planes, has_lo, has_hi, p_begin, p_end, in, out, s,
-                            two_steps != 0);
+                            two_steps != 0, nullptr, nullptr);
 }
 
 }  // extern "C"

@@ -12,6 +12,7 @@
 // Same arithmetic, same association order, same bit-exact results as heat.cu
 // (examples/heat_equation.cr:38-51 generalised by SURVEY.md 8(a) a-9).
 #include "ph_common.cuh"
+#include "comm.cuh"
 #include "ops.cuh"
 #include <cuda.h>
 #include <algorithm>
@@ -28,6 +29,10 @@ namespace ph {
 #define PH_HEAT_F32X2 0
 #endif
 constexpr int TMA_STAGES = 6;       // planes resident in shared memory (3 in use + 3 in flight)
+
+__device__ __forceinline__ void st_flag_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 template <typename T, int TMA_TY> struct TmaTile {
   static constexpr int E = 16 / (int)sizeof(T);       // cells per thread (one 16-byte group)
@@ -194,6 +199,7 @@ struct HeatTma2Args {
   int64_t z_begin, z_end, z_chunk;
   int64_t fixed_lo, fixed_hi;        // planes <= fixed_lo or >= fixed_hi are held (global boundary planes)
   T coeff;
+  HeatMirror mir;                    // sharded runs over peer-mapped slabs: compute + halo in one kernel
 };
 
 template <typename T>
@@ -296,7 +302,11 @@ heat_tma2_kernel(const __grid_constant__ CUtensorMap in_map, const HeatTma2Args<
   const int warp = threadIdx.x >> 5;
   const int64_t tile_x = (int64_t)blockIdx.x * W;
   const int64_t tile_y = (int64_t)blockIdx.y * TY;
-  const int64_t zb = a.z_begin + (int64_t)blockIdx.z * a.z_chunk;
+  // sharded runs: the chunks at either end of the slab produce the planes the neighbours need, so they are
+  // numbered first (blocks are dispatched in blockIdx order) and the halo leaves in the first wave
+  int64_t zc = blockIdx.z;
+  if (a.mir.edges_first && gridDim.z > 2) zc = blockIdx.z == 0 ? 0 : (blockIdx.z == 1 ? (int64_t)gridDim.z - 1 : (int64_t)blockIdx.z - 1);
+  const int64_t zb = a.z_begin + zc * a.z_chunk;
   const int64_t ze = (zb + a.z_chunk < a.z_end) ? zb + a.z_chunk : a.z_end;
   if (zb >= ze) return;
   const T* const ringA = reinterpret_cast<const T*>(smem_raw);
@@ -373,9 +383,9 @@ heat_tma2_kernel(const __grid_constant__ CUtensorMap in_map, const HeatTma2Args<
     // OWN: adjacent rows (the pair shares its middle neighbours through registers) and the t+2
     // phase; !OWN: the two halo rows.  FAST: no held cell, no range test (see `fast`); the first
     // and the last plane of a march always take the general form (they may be held planes).
-    auto step = [&](auto own_t, auto fast_t, G& aP0, G& aP1, G& aC0, G& aC1, G& aN0, G& aN1, G& bP0, G& bP1, G& bC0,
-                    G& bC1, G& bN0, G& bN1) {
-      constexpr bool OWN = decltype(own_t)::value, FAST = decltype(fast_t)::value;
+    auto step = [&](auto own_t, auto fast_t, auto mir_t, G& aP0, G& aP1, G& aC0, G& aC1, G& aN0, G& aN1, G& bP0, G& bP1,
+                    G& bC0, G& bC1, G& bN0, G& bN1) {
+      constexpr bool OWN = decltype(own_t)::value, FAST = decltype(fast_t)::value, MIR = decltype(mir_t)::value;
       mbar_wait(&full[sn], par_n);               // planes land in order: p+1 here => p here
       const T* An = ringA + sn * A_ELEMS;
       const T* Ac = ringA + sc * A_ELEMS;
@@ -409,16 +419,33 @@ heat_tma2_kernel(const __grid_constant__ CUtensorMap in_map, const HeatTma2Args<
         const G up0 = *reinterpret_cast<const G*>(Bq + ob0 - PITCH);
         const G dn1 = *reinterpret_cast<const G*>(Bq + ob1 + PITCH);
         const T xl0 = Bq[ob0 - 1], xr0 = Bq[ob0 + E], xl1 = Bq[ob1 - 1], xr1 = Bq[ob1 + E];
+        // MIR: output plane q = p-1 is one of the planes a neighbour slab keeps as ghosts -> the same group
+        // also goes to that neighbour's memory over NVLink (a plain store through the peer mapping)
+        auto mirror_delta = [&]() -> int64_t {
+          return (p - 1 < a.mir.lo_end) ? a.mir.delta_lo : ((p - 1 >= a.mir.hi_begin) ? a.mir.delta_hi : 0);
+        };
         if constexpr (FAST) {
           const G res0 = heat_row<T, E, false>(bC0, bP0, bN0, up0, bC1, xl0, xr0, coeff, false, false);
           const G res1 = heat_row<T, E, false>(bC1, bP1, bN1, bC0, dn1, xl1, xr1, coeff, false, false);
           store_group<T, E>(p_out0, res0);
           store_group<T, E>(p_out1, res1);
+          if constexpr (MIR) {
+            if (const int64_t mdelta = mirror_delta()) {
+              store_group<T, E>(reinterpret_cast<T*>(reinterpret_cast<char*>(p_out0) + mdelta), res0);
+              store_group<T, E>(reinterpret_cast<T*>(reinterpret_cast<char*>(p_out1) + mdelta), res1);
+            }
+          }
         } else {
           const G t0 = heat_row<T, E, true>(bC0, bP0, bN0, up0, bC1, xl0, xr0, coeff, fix_first, fix_last);
           const G t1 = heat_row<T, E, true>(bC1, bP1, bN1, bC0, dn1, xl1, xr1, coeff, fix_first, fix_last);
           if (act0) store_group<T, E>(p_out0, rowfix0 ? bC0 : t0);
           if (act1) store_group<T, E>(p_out1, rowfix1 ? bC1 : t1);
+          if constexpr (MIR) {
+            if (const int64_t mdelta = mirror_delta()) {
+              if (act0) store_group<T, E>(reinterpret_cast<T*>(reinterpret_cast<char*>(p_out0) + mdelta), rowfix0 ? bC0 : t0);
+              if (act1) store_group<T, E>(reinterpret_cast<T*>(reinterpret_cast<char*>(p_out1) + mdelta), rowfix1 ? bC1 : t1);
+            }
+          }
         }
         p_out0 += plane; p_out1 += plane;
       }
@@ -427,30 +454,32 @@ heat_tma2_kernel(const __grid_constant__ CUtensorMap in_map, const HeatTma2Args<
 #define PH_ROT0 a0[0], a1[0], a0[1], a1[1], a0[2], a1[2], b0[0], b1[0], b0[1], b1[1], b0[2], b1[2]
 #define PH_ROT1 a0[1], a1[1], a0[2], a1[2], a0[0], a1[0], b0[1], b1[1], b0[2], b1[2], b0[0], b1[0]
 #define PH_ROT2 a0[2], a1[2], a0[0], a1[0], a0[1], a1[1], b0[2], b1[2], b0[0], b1[0], b0[1], b1[1]
-    auto run = [&](auto own_t, auto fast_t) {
+    auto run = [&](auto own_t, auto fast_t, auto mir_t) {
       const std::false_type general;
-      step(own_t, general, PH_ROT0);             // it = 0: plane zb-1 may be a held plane, no output yet
-      step(own_t, general, PH_ROT1);             // it = 1: no output yet
+      step(own_t, general, mir_t, PH_ROT0);      // it = 0: plane zb-1 may be a held plane, no output yet
+      step(own_t, general, mir_t, PH_ROT1);      // it = 1: no output yet
       while (iters - it >= 4) {
-        step(own_t, fast_t, PH_ROT2);
-        step(own_t, fast_t, PH_ROT0);
-        step(own_t, fast_t, PH_ROT1);
+        step(own_t, fast_t, mir_t, PH_ROT2);
+        step(own_t, fast_t, mir_t, PH_ROT0);
+        step(own_t, fast_t, mir_t, PH_ROT1);
       }
       const int rem = iters - it;                // 1..3 planes left (iters >= 3); the last one may be a held plane
       if (rem == 1) {
-        step(own_t, general, PH_ROT2);
+        step(own_t, general, mir_t, PH_ROT2);
       } else if (rem == 2) {
-        step(own_t, fast_t, PH_ROT2);
-        step(own_t, general, PH_ROT0);
+        step(own_t, fast_t, mir_t, PH_ROT2);
+        step(own_t, general, mir_t, PH_ROT0);
       } else {
-        step(own_t, fast_t, PH_ROT2);
-        step(own_t, fast_t, PH_ROT0);
-        step(own_t, general, PH_ROT1);
+        step(own_t, fast_t, mir_t, PH_ROT2);
+        step(own_t, fast_t, mir_t, PH_ROT0);
+        step(own_t, general, mir_t, PH_ROT1);
       }
     };
-    if (fast) run(std::true_type{}, std::true_type{});
-    else if (own) run(std::true_type{}, std::false_type{});
-    else run(std::false_type{}, std::false_type{});
+    // block-uniform: does this march produce planes that are ALSO stored into a neighbour's ghost planes?
+    const bool mirror = own && (zb < a.mir.lo_end || ze > a.mir.hi_begin);
+    if (fast) { if (mirror) run(std::true_type{}, std::true_type{}, std::true_type{}); else run(std::true_type{}, std::true_type{}, std::false_type{}); }
+    else if (own) { if (mirror) run(std::true_type{}, std::false_type{}, std::true_type{}); else run(std::true_type{}, std::false_type{}, std::false_type{}); }
+    else run(std::false_type{}, std::false_type{}, std::false_type{});
 #undef PH_ROT0
 #undef PH_ROT1
 #undef PH_ROT2
@@ -491,6 +520,31 @@ heat_tma2_kernel(const __grid_constant__ CUtensorMap in_map, const HeatTma2Args<
     if (it < iters) {
       step(e0[0], e1[0], e0[1], e1[1], e0[2], e1[2]);
       if (it < iters) step(e0[1], e1[1], e0[2], e1[2], e0[0], e1[0]);
+    }
+  }
+  // ---- halo signal: when the LAST block that stored into a neighbour's ghost planes is done, that
+  // neighbour's flag word receives this pass's event number (release at system scope after every block's
+  // own system fence), and its next pass -- stream-ordered behind a wait on that word -- may start
+  // (the march bounds are recomputed from blockIdx here rather than kept in registers across the loops)
+  int64_t zc2 = blockIdx.z;
+  if (a.mir.edges_first && gridDim.z > 2) zc2 = blockIdx.z == 0 ? 0 : (blockIdx.z == 1 ? (int64_t)gridDim.z - 1 : (int64_t)blockIdx.z - 1);
+  const int64_t zb2 = a.z_begin + zc2 * a.z_chunk;
+  const int64_t ze2 = (zb2 + a.z_chunk < a.z_end) ? zb2 + a.z_chunk : a.z_end;
+  const bool covers_lo = zb2 < a.mir.lo_end, covers_hi = ze2 > a.mir.hi_begin;
+  if (covers_lo || covers_hi) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      if (covers_lo && atomicAdd(&a.mir.ticket[0], 1u) == a.mir.lo_blocks - 1) {
+        a.mir.ticket[0] = 0;
+        __threadfence_system();
+        st_flag_sys(a.mir.flag_lo, a.mir.event);
+      }
+      if (covers_hi && atomicAdd(&a.mir.ticket[1], 1u) == a.mir.hi_blocks - 1) {
+        a.mir.ticket[1] = 0;
+        __threadfence_system();
+        st_flag_sys(a.mir.flag_hi, a.mir.event);
+      }
     }
   }
 }
@@ -565,7 +619,8 @@ static int32_t heat_tma_launch(const T* in, T* out, int64_t n0, int64_t n1, int6
 // two steps per pass; *used = false => caller runs two single steps instead
 template <typename T, int TY, int STAGES>
 static int32_t heat_tma2_launch(const T* in, T* out, int64_t n0, int64_t n1, int64_t n2, T coeff, int64_t z_begin,
-                                int64_t z_end, int64_t fixed_lo, int64_t fixed_hi, cudaStream_t stream, bool* used) {
+                                int64_t z_end, int64_t fixed_lo, int64_t fixed_hi, cudaStream_t stream, bool* used,
+                                const HeatMirror* mir) {
   using Tile = Tma2Tile<T, TY, STAGES>;
   static_assert(TY % 2 == 0 && TY + 2 <= 32, "the edge-column warp covers rows -1 .. TY with one lane each");
   EncodeTiledFn enc = encode_fn();
@@ -597,6 +652,16 @@ static int32_t heat_tma2_launch(const T* in, T* out, int64_t n0, int64_t n1, int
   a.z_chunk = ceil_div(planes, gz);
   gz = ceil_div(planes, a.z_chunk);
   if (gy > 65535 || gz > 65535) return PH_OK;
+  if (mir) {                                        // how many blocks store into each neighbour's ghost planes
+    a.mir = *mir;
+    a.mir.edges_first = 1;
+    a.mir.lo_blocks = a.mir.hi_blocks = 0;
+    for (int64_t c = 0; c < gz; c++) {
+      const int64_t zb = z_begin + c * a.z_chunk, ze = std::min(zb + a.z_chunk, z_end);
+      if (zb < a.mir.lo_end) a.mir.lo_blocks += (uint32_t)(gx * gy);
+      if (ze > a.mir.hi_begin) a.mir.hi_blocks += (uint32_t)(gx * gy);
+    }
+  }
   static int attr_dev = -1;                         // function attributes are per device
   if (attr_dev != rt().device) {
     PH_CUDA(cudaFuncSetAttribute(heat_tma2_kernel<T, TY, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tile::SMEM));
@@ -614,7 +679,8 @@ static int32_t heat_tma2_launch(const T* in, T* out, int64_t n0, int64_t n1, int
 // >= fixed_hi are held fixed, and a fixed plane ignores its neighbours).
 template <typename T>
 int32_t heat_tma2_planes(const T* in, T* out, int64_t n0, int64_t n1, int64_t n2, T coeff, int64_t z_begin,
-                         int64_t z_end, int64_t fixed_lo, int64_t fixed_hi, cudaStream_t stream, bool* used) {
+                         int64_t z_end, int64_t fixed_lo, int64_t fixed_hi, cudaStream_t stream, bool* used,
+                         const HeatMirror* mir) {
   *used = false;
   if (z_begin >= z_end) { *used = true; return PH_OK; }
   static const bool disabled = getenv("PH_HEAT_NO_TMA") != nullptr || getenv("PH_HEAT_NO_FUSE2") != nullptr;
@@ -624,11 +690,11 @@ int32_t heat_tma2_planes(const T* in, T* out, int64_t n0, int64_t n1, int64_t n2
   if (n0 > 0x7fffffff || n1 > 0x7fffffff || n2 > 0x7fffffff) return PH_OK;
   static const int cfg = getenv("PH_HEAT_TB_CFG") ? atoi(getenv("PH_HEAT_TB_CFG")) : 0;     // tuning knob
   switch (cfg) {
-    case 1: return heat_tma2_launch<T, 16, 4>(in, out, n0, n1, n2, coeff, z_begin, z_end, fixed_lo, fixed_hi, stream, used);
-    case 2: return heat_tma2_launch<T, 16, 8>(in, out, n0, n1, n2, coeff, z_begin, z_end, fixed_lo, fixed_hi, stream, used);
-    case 3: return heat_tma2_launch<T, 24, 5>(in, out, n0, n1, n2, coeff, z_begin, z_end, fixed_lo, fixed_hi, stream, used);
-    case 4: return heat_tma2_launch<T, 8, 6>(in, out, n0, n1, n2, coeff, z_begin, z_end, fixed_lo, fixed_hi, stream, used);
-    default: return heat_tma2_launch<T, 16, 6>(in, out, n0, n1, n2, coeff, z_begin, z_end, fixed_lo, fixed_hi, stream, used);
+    case 1: return heat_tma2_launch<T, 16, 4>(in, out, n0, n1, n2, coeff, z_begin, z_end, fixed_lo, fixed_hi, stream, used, mir);
+    case 2: return heat_tma2_launch<T, 16, 8>(in, out, n0, n1, n2, coeff, z_begin, z_end, fixed_lo, fixed_hi, stream, used, mir);
+    case 3: return heat_tma2_launch<T, 24, 5>(in, out, n0, n1, n2, coeff, z_begin, z_end, fixed_lo, fixed_hi, stream, used, mir);
+    case 4: return heat_tma2_launch<T, 8, 6>(in, out, n0, n1, n2, coeff, z_begin, z_end, fixed_lo, fixed_hi, stream, used, mir);
+    default: return heat_tma2_launch<T, 16, 6>(in, out, n0, n1, n2, coeff, z_begin, z_end, fixed_lo, fixed_hi, stream, used, mir);
   }
 }
 
@@ -644,9 +710,9 @@ template bool heat_tma2_usable<float>(int64_t, int64_t);
 template bool heat_tma2_usable<double>(int64_t, int64_t);
 
 template int32_t heat_tma2_planes<float>(const float*, float*, int64_t, int64_t, int64_t, float, int64_t, int64_t,
-                                         int64_t, int64_t, cudaStream_t, bool*);
+                                         int64_t, int64_t, cudaStream_t, bool*, const HeatMirror*);
 template int32_t heat_tma2_planes<double>(const double*, double*, int64_t, int64_t, int64_t, double, int64_t, int64_t,
-                                          int64_t, int64_t, cudaStream_t, bool*);
+                                          int64_t, int64_t, cudaStream_t, bool*, const HeatMirror*);
 
 template <typename T>
 int32_t heat_tma_planes(const T* in, T* out, int64_t n0, int64_t n1, int64_t n2, T coeff, int64_t z_begin,

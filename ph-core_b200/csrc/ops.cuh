@@ -235,6 +235,19 @@ struct CompareOp {
   }
 };
 
+// `<=>` (src/multi_indexable.cr:981 in the operator list): Int#<=> yields -1 / 0 / 1 as Int32.  Integer
+// element types only: Float#<=> is Int32? (nil against NaN), which has no device representation.
+template <typename T>
+struct SpaceshipOp {
+  using In = T;
+  using Out = int32_t;
+  static constexpr int NIN = 2;
+  static constexpr bool kCompact = true;
+  static __device__ __forceinline__ Out apply(const In (&x)[2], uint32_t&) {
+    return (x[0] > x[1]) - (x[0] < x[1]);
+  }
+};
+
 template <typename T, int OP>
 struct UnaryOp {
   using In = T;

@@ -2,10 +2,15 @@
 // The kernels and per-dtype launchers live in reduce_impl.cuh and are instantiated one element type per
 // translation unit (reduce_<dtype>.cu); here the two launcher templates are only declared.
 #include "ph_common.cuh"
+#include "comm.cuh"
 
 namespace ph {
 template <typename T>
-int32_t reduce_full_t(int32_t red, const void* a, const ph_desc* d, void* out_value_dev, int64_t* out_index_dev);
+int32_t reduce_full_t(int32_t red, const void* a, const ph_desc* d, void* out_value_dev, int64_t* out_index_dev,
+                      const CombineArgs* cmb);
+template <typename T>
+int32_t reduce_full_sharded_t(int32_t red, const void* a, const ph_desc* d, int64_t elems_before, void* out_value_host,
+                              int64_t* out_index_host, uint32_t* out_flags);
 template <typename T>
 int32_t reduce_axis_t(int32_t red, const void* a, const ph_desc* d, int32_t axis, void* out, const ph_desc* od);
 }  // namespace ph
@@ -33,7 +38,7 @@ int32_t ph_reduce_full_dev(int32_t red, int32_t dtype, const void* a, const ph_d
                            void* out_value_dev, int64_t* out_index_dev) {
   PH_REQUIRE_INIT();
   if (!a || !a_desc || !out_value_dev) return set_error(PH_ERR_INVALID, "null argument to ph_reduce_full_dev");
-#define CALL(T) reduce_full_t<T>(red, a, a_desc, out_value_dev, out_index_dev)
+#define CALL(T) reduce_full_t<T>(red, a, a_desc, out_value_dev, out_index_dev, nullptr)
   PH_RED_DTYPE_SWITCH(dtype, CALL)
 #undef CALL
 }
@@ -55,6 +60,16 @@ int32_t ph_reduce_full(int32_t red, int32_t dtype, const void* a, const ph_desc*
   memcpy(out_value_host, h, dtype_size(dtype));
   if (out_index_host) memcpy(out_index_host, h + 16, 8);
   return PH_OK;
+}
+
+int32_t ph_reduce_full_sharded(int32_t red, int32_t dtype, const void* a, const ph_desc* a_desc, int64_t elems_before,
+                               void* out_value_host, int64_t* out_index_host, uint32_t* out_flags) {
+  PH_REQUIRE_INIT();
+  if (!a || !a_desc || !out_value_host) return set_error(PH_ERR_INVALID, "null argument to ph_reduce_full_sharded");
+  if (red < PH_SUM || red > PH_ARGMIN) return set_error(PH_ERR_INVALID, "unknown reduction %d", red);
+#define CALL(T) reduce_full_sharded_t<T>(red, a, a_desc, elems_before, out_value_host, out_index_host, out_flags)
+  PH_RED_DTYPE_SWITCH(dtype, CALL)
+#undef CALL
 }
 
 int32_t ph_reduce_axis(int32_t red, int32_t dtype, const void* a, const ph_desc* a_desc, int32_t axis,

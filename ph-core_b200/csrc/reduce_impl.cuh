@@ -19,6 +19,7 @@
 #pragma once
 #include "map_kernels.cuh"
 #include "ops.cuh"
+#include "comm.cuh"
 #include <limits>
 
 namespace ph {
@@ -98,6 +99,145 @@ __device__ __forceinline__ Cand<T> better(const Cand<T>& a, const Cand<T>& b) {
 
 static __global__ void set_flag_kernel(uint32_t* flags, uint32_t bits) { atomicOr(flags, bits); }
 
+// ---------------------------------------------------------------- cross-rank combine (one process per GPU)
+// A sharded reduction is ONE launch per rank: the block that finishes last stores this rank's partial into
+// slot[rank] of EVERY peer's control block over NVLink (payload, system fence, then the word carrying the
+// call number), waits until all N slots of its own block carry this call's number, and folds them in rank
+// order -- every rank computes the same result from the same records in the same order (deterministic), and
+// writes it to a pinned host record.  No NCCL kernel, no second launch, no D2H copy.  Slots are double
+// buffered by call parity: a peer can only be one call ahead (it needs MY record to finish a call).
+template <typename A> __device__ __forceinline__ void pack_wide(uint64_t* w, A v) {
+  if constexpr (sizeof(A) == 16) {
+    w[0] = (uint64_t)(unsigned __int128)v;
+    w[1] = (uint64_t)((unsigned __int128)v >> 64);
+  } else {
+    uint64_t b = 0;
+    memcpy(&b, &v, sizeof(A));
+    w[0] = b;
+    w[1] = 0;
+  }
+}
+template <typename A> __device__ __forceinline__ A unpack_wide(const uint64_t* w) {
+  if constexpr (sizeof(A) == 16) {
+    return (A)(((unsigned __int128)w[1] << 64) | (unsigned __int128)w[0]);
+  } else {
+    A v;
+    const uint64_t b = w[0];
+    memcpy(&v, &b, sizeof(A));
+    return v;
+  }
+}
+
+// Called by every thread of the finishing block; `mine` is thread 0's.  Afterwards sh[r] holds rank r's
+// record for r < nranks (visible to all threads).  false = a peer never arrived (time-out, ~4 s).
+__device__ __forceinline__ bool exchange_records(const CombineArgs& c, const ReduceSlot& mine, ReduceSlot* sh) {
+  __shared__ int timed_out;
+  if (threadIdx.x == 0) { sh[PH_MAX_PEERS] = mine; timed_out = 0; }
+  __syncthreads();
+  if ((int)threadIdx.x < c.nranks) {
+    const int r = threadIdx.x;
+    volatile uint64_t* dst = reinterpret_cast<volatile uint64_t*>(c.peer_slots[r] + c.rank);
+    const uint64_t* src = sh[PH_MAX_PEERS].w;
+#pragma unroll
+    for (int i = 0; i < 7; i++) dst[i] = src[i];
+    __threadfence_system();
+    dst[7] = (src[7] & 0xffffffffull) | ((uint64_t)c.seq << 32);
+    const volatile uint64_t* mine_r = reinterpret_cast<const volatile uint64_t*>(c.my_slots + r);
+    const long long t0 = clock64();
+    uint64_t tail;
+    while ((uint32_t)((tail = mine_r[7]) >> 32) != c.seq) {
+      if (clock64() - t0 > 8000000000LL) { timed_out = 1; break; }
+    }
+    __threadfence_system();
+#pragma unroll
+    for (int i = 0; i < 7; i++) sh[r].w[i] = mine_r[i];
+    sh[r].w[7] = tail;
+  }
+  __syncthreads();
+  return timed_out == 0;
+}
+
+template <typename T> __device__ __forceinline__ void sum_finish(typename Acc<T>::type fs, typename Acc<T>::type fp,
+                                                                  typename Acc<T>::type fn, uint32_t fl, bool ok,
+                                                                  T* out_value, int* status, ReduceResult* host_out) {
+  using A = typename Acc<T>::type;
+  int st = PH_RED_OK;
+  if constexpr (!is_float_t<T>::value) {
+    const A hi = (A)std::numeric_limits<T>::max(), lo = (A)std::numeric_limits<T>::lowest();
+    if (fs > hi || fs < lo) st = PH_RED_OVERFLOW;               // the final prefix itself overflows
+    else if (fp > hi || fn < lo) st = PH_RED_NEED_EXACT;        // some prefix MIGHT overflow: decide exactly
+  }
+  if (!ok) st = PH_RED_TIMEOUT;
+  const T v = (T)fs;
+  if (status) *status = st;
+  if (out_value) *out_value = v;
+  if (host_out) {
+    uint64_t w[2];
+    pack_wide<T>(w, v);
+    host_out->value[0] = w[0]; host_out->value[1] = w[1];
+    host_out->index = 0;
+    host_out->flags = fl;
+    host_out->status = st;
+    __threadfence_system();
+  }
+}
+
+// fold of the N sum records in rank order (thread 0)
+template <typename T> __device__ __forceinline__ void sum_fold_records(const ReduceSlot* rec, int nranks, bool ok, T* out_value,
+                                                                        int* status, ReduceResult* host_out) {
+  using A = typename Acc<T>::type;
+  A fs = 0, fp = 0, fn = 0;
+  uint32_t fl = 0;
+  for (int r = 0; r < nranks; r++) {
+    if constexpr (is_float_t<T>::value) fs = f_add(fs, unpack_wide<A>(rec[r].w));
+    else { fs += unpack_wide<A>(rec[r].w); fp += unpack_wide<A>(rec[r].w + 2); fn += unpack_wide<A>(rec[r].w + 4); }
+    fl |= (uint32_t)rec[r].w[7];
+  }
+  sum_finish<T>(fs, fp, fn, fl, ok, out_value, status, host_out);
+}
+
+template <typename T> __device__ __forceinline__ void ext_finish(Cand<T> fin, uint32_t fl, bool ok, T* out_value,
+                                                                  int64_t* out_index, ReduceResult* host_out) {
+  if (out_value) *out_value = fin.v;
+  if (out_index) *out_index = fin.i;
+  if (host_out) {
+    uint64_t w[2];
+    pack_wide<T>(w, fin.v);
+    host_out->value[0] = w[0]; host_out->value[1] = w[1];
+    host_out->index = fin.i;
+    host_out->flags = fl;
+    host_out->status = !ok ? PH_RED_TIMEOUT : (fin.i == INT64_MAX ? PH_RED_EMPTY : PH_RED_OK);
+    __threadfence_system();
+  }
+}
+
+template <typename T, bool IS_MAX> __device__ __forceinline__ void ext_fold_records(const ReduceSlot* rec, int nranks, bool ok,
+                                                                                    T* out_value, int64_t* out_index,
+                                                                                    ReduceResult* host_out) {
+  Cand<T> fin;
+  fin.v = IS_MAX ? lowest_of<T>() : highest_of<T>();
+  fin.i = INT64_MAX;
+  uint32_t fl = 0;
+  for (int r = 0; r < nranks; r++) {
+    Cand<T> c;
+    c.v = unpack_wide<T>(rec[r].w);
+    c.i = (int64_t)rec[r].w[6];
+    if (c.i != INT64_MAX) fin = better<T, IS_MAX>(fin, c);      // an empty shard contributes nothing
+    fl |= (uint32_t)rec[r].w[7];
+  }
+  ext_finish<T>(fin, fl, ok, out_value, out_index, host_out);
+}
+
+// NCCL transport of the same combine: the records were allgathered between the two launches
+template <typename T> __global__ void sum_combine_kernel(const ReduceSlot* rec, int nranks, T* out_value, int* status,
+                                                         ReduceResult* host_out) {
+  if (threadIdx.x == 0) sum_fold_records<T>(rec, nranks, true, out_value, status, host_out);
+}
+template <typename T, bool IS_MAX> __global__ void ext_combine_kernel(const ReduceSlot* rec, int nranks, T* out_value,
+                                                                       int64_t* out_index, ReduceResult* host_out) {
+  if (threadIdx.x == 0) ext_fold_records<T, IS_MAX>(rec, nranks, true, out_value, out_index, host_out);
+}
+
 // ---------------------------------------------------------------- full sum (floats; ints: S, P, N)
 template <typename T> struct SumState {
   using A = typename Acc<T>::type;
@@ -112,7 +252,8 @@ template <typename T, int E>
 __global__ void __launch_bounds__(RED_THREADS) sum_partial_kernel(const T* __restrict__ x, int64_t n,
                                                                   SumState<T>* __restrict__ partials,
                                                                   T* __restrict__ out_value, int* __restrict__ status,
-                                                                  unsigned int* __restrict__ ticket) {
+                                                                  unsigned int* __restrict__ ticket,
+                                                                  uint32_t* __restrict__ flags, const CombineArgs cmb) {
   using A = typename Acc<T>::type;
   constexpr bool IS_INT = !is_float_t<T>::value;
   constexpr int UNROLL = 4;
@@ -197,20 +338,25 @@ __global__ void __launch_bounds__(RED_THREADS) sum_partial_kernel(const T* __res
   }
   __syncthreads();                                   // sh_* are reused
   block_fold(fs, fp, fn);
-  if (threadIdx.x == 0) {
-    if constexpr (IS_INT) {
-      const A hi = (A)std::numeric_limits<T>::max(), lo = (A)std::numeric_limits<T>::lowest();
-      int st = 0;
-      if (fs > hi || fs < lo) st = 1;                // the final prefix itself overflows
-      else if (fp > hi || fn < lo) st = 2;           // some prefix MIGHT overflow: decide exactly
-      *status = st;
-      *out_value = (T)fs;
-    } else {
-      *status = 0;
-      *out_value = fs;
+  if (threadIdx.x == 0) *ticket = 0;                 // ready for the next launch on this stream
+  if (cmb.nranks > 1) {                              // sharded: combine the per-GPU partials across ranks
+    __shared__ ReduceSlot sh_rec[PH_MAX_PEERS + 1];
+    ReduceSlot mine;
+    if (threadIdx.x == 0) {
+      pack_wide<A>(mine.w, fs); pack_wide<A>(mine.w + 2, fp); pack_wide<A>(mine.w + 4, fn);
+      mine.w[6] = 0;
+      mine.w[7] = atomicExch(flags, 0u);             // pending arithmetic flags travel with the record
     }
-    *ticket = 0;                                     // ready for the next launch on this stream
+    if (cmb.peer_slots[0] == nullptr) {              // NCCL transport: the allgather follows this launch
+      if (threadIdx.x == 0) { mine.w[7] |= (uint64_t)cmb.seq << 32; cmb.my_slots[cmb.rank] = mine; }
+      return;
+    }
+    const bool ok = exchange_records(cmb, mine, sh_rec);
+    if (threadIdx.x == 0) sum_fold_records<T>(sh_rec, cmb.nranks, ok, out_value, status, cmb.host_out);
+    return;
   }
+  if (threadIdx.x == 0)
+    sum_finish<T>(fs, fp, fn, cmb.host_out ? atomicExch(flags, 0u) : 0u, true, out_value, status, cmb.host_out);
 }
 
 // Exact ordered pass for integer sums: monoid (sum, max prefix, min prefix) combined in lex order.
@@ -254,14 +400,60 @@ __global__ void __launch_bounds__(RED_THREADS) sum_exact_kernel(const T* __restr
     partials[blockIdx.x] = acc;
   }
 }
+// thread 0 folds this rank's per-block prefixes in order; sharded: the per-rank (sum, max prefix, min prefix)
+// triples are exchanged like any other record and folded in RANK order -- the lexicographic order of the
+// global array -- so the overflow decision is exact across ranks too.
 template <typename T>
-__global__ void sum_exact_final_kernel(const Prefix<T>* __restrict__ partials, int nparts, int* __restrict__ status) {
+__global__ void sum_exact_final_kernel(const Prefix<T>* __restrict__ partials, int nparts, int* __restrict__ status,
+                                       const CombineArgs cmb) {
+  using A = typename Acc<T>::type;
+  Prefix<T> acc;
+  acc.s = 0; acc.mx = 0; acc.mn = 0;
+  if (threadIdx.x == 0 && nparts > 0) {
+    acc = partials[0];
+    for (int i = 1; i < nparts; i++) acc = pcombine<T>(acc, partials[i]);
+  }
+  bool ok = true;
+  if (cmb.nranks > 1) {
+    __shared__ ReduceSlot sh_rec[PH_MAX_PEERS + 1];
+    ReduceSlot mine;
+    if (threadIdx.x == 0) {
+      pack_wide<A>(mine.w, acc.s); pack_wide<A>(mine.w + 2, acc.mx); pack_wide<A>(mine.w + 4, acc.mn);
+      mine.w[6] = 0; mine.w[7] = 0;
+    }
+    const ReduceSlot* rec = sh_rec;
+    if (cmb.peer_slots[0] == nullptr) rec = cmb.my_slots;          // NCCL transport: already gathered (second launch)
+    else ok = exchange_records(cmb, mine, sh_rec);
+    if (threadIdx.x == 0) {
+      acc.s = unpack_wide<A>(rec[0].w); acc.mx = unpack_wide<A>(rec[0].w + 2); acc.mn = unpack_wide<A>(rec[0].w + 4);
+      for (int r = 1; r < cmb.nranks; r++) {
+        Prefix<T> o;
+        o.s = unpack_wide<A>(rec[r].w); o.mx = unpack_wide<A>(rec[r].w + 2); o.mn = unpack_wide<A>(rec[r].w + 4);
+        acc = pcombine<T>(acc, o);
+      }
+    }
+  }
+  if (threadIdx.x != 0) return;
+  const A hi = (A)std::numeric_limits<T>::max(), lo = (A)std::numeric_limits<T>::lowest();
+  const int st = !ok ? PH_RED_TIMEOUT : ((acc.mx > hi || acc.mn < lo) ? PH_RED_OVERFLOW : PH_RED_OK);
+  if (status) *status = st;
+  if (cmb.host_out) { cmb.host_out->status = st; __threadfence_system(); }
+}
+// NCCL transport, first launch: leave this rank's prefix triple in the gather send buffer
+template <typename T>
+__global__ void sum_exact_record_kernel(const Prefix<T>* __restrict__ partials, int nparts, const CombineArgs cmb) {
   using A = typename Acc<T>::type;
   if (threadIdx.x != 0) return;
-  Prefix<T> acc = partials[0];
-  for (int i = 1; i < nparts; i++) acc = pcombine<T>(acc, partials[i]);
-  const A hi = (A)std::numeric_limits<T>::max(), lo = (A)std::numeric_limits<T>::lowest();
-  *status = (acc.mx > hi || acc.mn < lo) ? 1 : 0;
+  Prefix<T> acc;
+  acc.s = 0; acc.mx = 0; acc.mn = 0;
+  if (nparts > 0) {
+    acc = partials[0];
+    for (int i = 1; i < nparts; i++) acc = pcombine<T>(acc, partials[i]);
+  }
+  ReduceSlot mine;
+  pack_wide<A>(mine.w, acc.s); pack_wide<A>(mine.w + 2, acc.mx); pack_wide<A>(mine.w + 4, acc.mn);
+  mine.w[6] = 0; mine.w[7] = (uint64_t)cmb.seq << 32;
+  cmb.my_slots[cmb.rank] = mine;
 }
 
 // ---------------------------------------------------------------- full min / max / argmin / argmax
@@ -292,7 +484,7 @@ __global__ void __launch_bounds__(RED_THREADS) ext_partial_kernel(const T* __res
                                                                   uint32_t* __restrict__ flags,
                                                                   T* __restrict__ out_value,
                                                                   int64_t* __restrict__ out_index,
-                                                                  unsigned int* __restrict__ ticket) {
+                                                                  unsigned int* __restrict__ ticket, const CombineArgs cmb) {
   constexpr int UNROLL = 4;
   T best_v = IS_MAX ? lowest_of<T>() : highest_of<T>();
   int64_t best_t = -1;
@@ -359,8 +551,8 @@ __global__ void __launch_bounds__(RED_THREADS) ext_partial_kernel(const T* __res
       for (int w = 1; w < RED_THREADS / 32; w++) b = better<T, IS_MAX>(b, sh[w]);
     }
   };
+  if (nan) atomicOr(flags, (uint32_t)PH_FLAG_NAN);   // before the fold's barrier: ordered ahead of thread 0's ticket
   block_fold(best);
-  if (nan) atomicOr(flags, (uint32_t)PH_FLAG_NAN);
   if (threadIdx.x == 0) {
     partials[blockIdx.x] = best;
     __threadfence();
@@ -380,11 +572,25 @@ __global__ void __launch_bounds__(RED_THREADS) ext_partial_kernel(const T* __res
   }
   __syncthreads();                                   // sh is reused
   block_fold(fin);
-  if (threadIdx.x == 0) {
-    *out_value = fin.v;
-    if (out_index) *out_index = fin.i;
-    *ticket = 0;
+  if (threadIdx.x == 0) *ticket = 0;
+  if (cmb.nranks > 1) {                              // sharded: first extremum across ranks (value, then GLOBAL index)
+    __shared__ ReduceSlot sh_rec[PH_MAX_PEERS + 1];
+    ReduceSlot mine;
+    if (threadIdx.x == 0) {
+      pack_wide<T>(mine.w, fin.v);
+      mine.w[2] = mine.w[3] = mine.w[4] = mine.w[5] = 0;
+      mine.w[6] = (uint64_t)(fin.i == INT64_MAX ? INT64_MAX : fin.i + cmb.elems_before);
+      mine.w[7] = atomicExch(flags, 0u);
+    }
+    if (cmb.peer_slots[0] == nullptr) {
+      if (threadIdx.x == 0) { mine.w[7] |= (uint64_t)cmb.seq << 32; cmb.my_slots[cmb.rank] = mine; }
+      return;
+    }
+    const bool ok = exchange_records(cmb, mine, sh_rec);
+    if (threadIdx.x == 0) ext_fold_records<T, IS_MAX>(sh_rec, cmb.nranks, ok, out_value, out_index, cmb.host_out);
+    return;
   }
+  if (threadIdx.x == 0) ext_finish<T>(fin, cmb.host_out ? atomicExch(flags, 0u) : 0u, true, out_value, out_index, cmb.host_out);
 }
 
 // ---------------------------------------------------------------- per-axis: [outer, K, inner]
@@ -729,10 +935,15 @@ static int32_t contiguous_input(const void* a, const ph_desc* d, const T** out_p
 // device); the last block of every fused reduction resets it
 static unsigned int* reduce_ticket() { return rt().d_flags ? rt().d_flags + 8 : nullptr; }
 
+// `cmb` == nullptr: single-GPU reduction, result left on the device (out_value_dev / out_index_dev).
+// `cmb` with nranks > 1: this rank's part of a sharded reduction -- the kernel also runs for an EMPTY shard
+// (one block contributing the identity), so every rank enters the combine; the result goes to cmb->host_out.
 template <typename T>
-int32_t reduce_full_t(int32_t red, const void* a, const ph_desc* d, void* out_value_dev,
-                             int64_t* out_index_dev) {
+int32_t reduce_full_t(int32_t red, const void* a, const ph_desc* d, void* out_value_dev, int64_t* out_index_dev,
+                      const CombineArgs* cmb_in) {
   Runtime& r = rt();
+  const CombineArgs cmb = cmb_in ? *cmb_in : CombineArgs();
+  const bool sharded = cmb.host_out != nullptr;       // record mode: always launch, result to the pinned host record
   const T* x;
   void* temp;
   int64_t n;
@@ -760,40 +971,42 @@ int32_t reduce_full_t(int32_t red, const void* a, const ph_desc* d, void* out_va
   constexpr int E32 = 32 / (int)sizeof(T);
   const bool al32 = ((uintptr_t)x % 32) == 0;
   if (red == PH_SUM) {
-    if (n == 0) {                                         // Enumerable#sum of nothing is T.zero
+    if (n == 0 && !sharded) {                             // Enumerable#sum of nothing is T.zero
       PH_CUDA(cudaMemsetAsync(out_value_dev, 0, sizeof(T), r.stream));
     } else {
       SumState<T>* parts = reinterpret_cast<SumState<T>*>(r.d_scratch);
       static_assert(sizeof(SumState<T>) <= 64, "partial too large");
       T* ov = reinterpret_cast<T*>(out_value_dev);
-      if (al32) sum_partial_kernel<T, E32><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, ov, status, ticket);
-      else sum_partial_kernel<T, 1><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, ov, status, ticket);
+      if (al32) sum_partial_kernel<T, E32><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, ov, status, ticket, r.d_flags, cmb);
+      else sum_partial_kernel<T, 1><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, ov, status, ticket, r.d_flags, cmb);
       PH_LAUNCH_CHECK("sum_partial_kernel");
       if constexpr (!is_float_t<T>::value) {
-        int* h = reinterpret_cast<int*>(r.h_scratch);
-        PH_CUDA(cudaMemcpyAsync(h, status, sizeof(int), cudaMemcpyDeviceToHost, r.stream));
-        PH_CUDA(cudaStreamSynchronize(r.stream));
-        int code = *h;
-        if (code == 2) {                                  // the filter could not decide: exact ordered pass
-          Prefix<T>* pp = reinterpret_cast<Prefix<T>*>(r.d_scratch);
-          static_assert(sizeof(Prefix<T>) <= 64, "partial too large");
-          sum_exact_kernel<T><<<grid, RED_THREADS, 0, r.stream>>>(x, n, pp);
-          PH_LAUNCH_CHECK("sum_exact_kernel");
-          sum_exact_final_kernel<T><<<1, 32, 0, r.stream>>>(pp, grid, status);
-          PH_LAUNCH_CHECK("sum_exact_final_kernel");
+        if (!sharded) {                                   // (sharded: the caller decides from the combined record)
+          int* h = reinterpret_cast<int*>(r.h_scratch);
           PH_CUDA(cudaMemcpyAsync(h, status, sizeof(int), cudaMemcpyDeviceToHost, r.stream));
           PH_CUDA(cudaStreamSynchronize(r.stream));
-          code = *h;
-        }
-        if (code == 1) {
-          set_flag_kernel<<<1, 1, 0, r.stream>>>(r.d_flags, (uint32_t)PH_FLAG_OVERFLOW);
-          PH_LAUNCH_CHECK("set_flag_kernel");
+          int code = *h;
+          if (code == PH_RED_NEED_EXACT) {                // the filter could not decide: exact ordered pass
+            Prefix<T>* pp = reinterpret_cast<Prefix<T>*>(r.d_scratch);
+            static_assert(sizeof(Prefix<T>) <= 64, "partial too large");
+            sum_exact_kernel<T><<<grid, RED_THREADS, 0, r.stream>>>(x, n, pp);
+            PH_LAUNCH_CHECK("sum_exact_kernel");
+            sum_exact_final_kernel<T><<<1, 32, 0, r.stream>>>(pp, grid, status, CombineArgs());
+            PH_LAUNCH_CHECK("sum_exact_final_kernel");
+            PH_CUDA(cudaMemcpyAsync(h, status, sizeof(int), cudaMemcpyDeviceToHost, r.stream));
+            PH_CUDA(cudaStreamSynchronize(r.stream));
+            code = *h;
+          }
+          if (code == PH_RED_OVERFLOW) {
+            set_flag_kernel<<<1, 1, 0, r.stream>>>(r.d_flags, (uint32_t)PH_FLAG_OVERFLOW);
+            PH_LAUNCH_CHECK("set_flag_kernel");
+          }
         }
       }
     }
     if (out_index_dev) PH_CUDA(cudaMemsetAsync(out_index_dev, 0, 8, r.stream));
   } else if (red == PH_MIN || red == PH_MAX || red == PH_ARGMIN || red == PH_ARGMAX) {
-    if (n == 0) {                                         // host raises Enumerable::EmptyError
+    if (n == 0 && !sharded) {                             // host raises Enumerable::EmptyError
       PH_CUDA(cudaMemsetAsync(out_value_dev, 0, sizeof(T), r.stream));
       if (out_index_dev) PH_CUDA(cudaMemsetAsync(out_index_dev, 0xff, 8, r.stream));
     } else {
@@ -801,11 +1014,11 @@ int32_t reduce_full_t(int32_t red, const void* a, const ph_desc* d, void* out_va
       const bool is_max = (red == PH_MAX || red == PH_ARGMAX);
       T* ov = reinterpret_cast<T*>(out_value_dev);
       if (is_max) {
-        if (al32) ext_partial_kernel<T, E32, true><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags, ov, out_index_dev, ticket);
-        else ext_partial_kernel<T, 1, true><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags, ov, out_index_dev, ticket);
+        if (al32) ext_partial_kernel<T, E32, true><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags, ov, out_index_dev, ticket, cmb);
+        else ext_partial_kernel<T, 1, true><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags, ov, out_index_dev, ticket, cmb);
       } else {
-        if (al32) ext_partial_kernel<T, E32, false><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags, ov, out_index_dev, ticket);
-        else ext_partial_kernel<T, 1, false><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags, ov, out_index_dev, ticket);
+        if (al32) ext_partial_kernel<T, E32, false><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags, ov, out_index_dev, ticket, cmb);
+        else ext_partial_kernel<T, 1, false><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags, ov, out_index_dev, ticket, cmb);
       }
       PH_LAUNCH_CHECK("ext_partial_kernel");
     }
@@ -814,6 +1027,69 @@ int32_t reduce_full_t(int32_t red, const void* a, const ph_desc* d, void* out_va
     return set_error(PH_ERR_INVALID, "unknown reduction %d", red);
   }
   if (temp) PH_CUDA(cudaFreeAsync(temp, r.stream));
+  return PH_OK;
+}
+
+// Full reduction of an array sharded along axis 0 over the ranks of the communicator (collective: every
+// rank calls it with its shard).  One launch per rank with the in-kernel combine when the peers' control
+// blocks are mapped; otherwise the records are allgathered with NCCL and folded by a second tiny launch.
+// The result (identical on every rank) is read from the pinned host record after ONE synchronisation.
+template <typename T>
+int32_t reduce_full_sharded_t(int32_t red, const void* a, const ph_desc* d, int64_t elems_before, void* out_value_host,
+                              int64_t* out_index_host, uint32_t* out_flags) {
+  Runtime& r = rt();
+  PeerInfo& pi = peers();
+  CombineArgs cmb;
+  int32_t st = comm_combine_args(&cmb, elems_before);
+  if (st != PH_OK) return st;
+  const bool nccl = cmb.peer_slots[0] == nullptr;
+  const bool is_max = (red == PH_MAX || red == PH_ARGMAX);
+  st = reduce_full_t<T>(red, a, d, nullptr, nullptr, &cmb);
+  if (st != PH_OK) return st;
+  if (nccl) {
+    if ((st = comm_allgather_records(r.stream)) != PH_OK) return st;
+    if (red == PH_SUM) sum_combine_kernel<T><<<1, 32, 0, r.stream>>>(pi.gather_recv, cmb.nranks, nullptr, nullptr, cmb.host_out);
+    else if (is_max) ext_combine_kernel<T, true><<<1, 32, 0, r.stream>>>(pi.gather_recv, cmb.nranks, nullptr, nullptr, cmb.host_out);
+    else ext_combine_kernel<T, false><<<1, 32, 0, r.stream>>>(pi.gather_recv, cmb.nranks, nullptr, nullptr, cmb.host_out);
+    PH_LAUNCH_CHECK("combine_kernel");
+  }
+  PH_CUDA(cudaStreamSynchronize(r.stream));
+  ReduceResult res = *pi.host_result;
+  if constexpr (!is_float_t<T>::value) {
+    if (red == PH_SUM && res.status == PH_RED_NEED_EXACT) {
+      // rare: some prefix of the global fold MIGHT leave T.  Every rank sees the same status, so all of them
+      // take this branch: ordered (sum, max prefix, min prefix) pass per shard, triples folded in rank order.
+      const T* x;
+      void* temp;
+      int64_t n;
+      if ((st = contiguous_input<T>(a, d, &x, &temp, n)) != PH_OK) return st;
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)r.sm_count * 4, ceil_div(n, (int64_t)RED_THREADS * 32)));
+      if ((st = ensure_scratch((size_t)grid * 64 + 256)) != PH_OK) return st;
+      Prefix<T>* pp = reinterpret_cast<Prefix<T>*>(r.d_scratch);
+      sum_exact_kernel<T><<<grid, RED_THREADS, 0, r.stream>>>(x, n, pp);
+      PH_LAUNCH_CHECK("sum_exact_kernel");
+      CombineArgs c2;
+      if ((st = comm_combine_args(&c2, elems_before)) != PH_OK) return st;
+      if (c2.peer_slots[0] == nullptr) {
+        sum_exact_record_kernel<T><<<1, 32, 0, r.stream>>>(pp, grid, c2);
+        PH_LAUNCH_CHECK("sum_exact_record_kernel");
+        if ((st = comm_allgather_records(r.stream)) != PH_OK) return st;
+        c2.my_slots = pi.gather_recv;
+      }
+      sum_exact_final_kernel<T><<<1, 32, 0, r.stream>>>(pp, grid, nullptr, c2);
+      PH_LAUNCH_CHECK("sum_exact_final_kernel");
+      if (temp) PH_CUDA(cudaFreeAsync(temp, r.stream));
+      PH_CUDA(cudaStreamSynchronize(r.stream));
+      res.status = pi.host_result->status;
+    }
+  }
+  if (res.status == PH_RED_TIMEOUT)
+    return set_error(PH_ERR_CUDA, "sharded reduction: a peer rank never delivered its partial (is every rank calling?)");
+  uint32_t fl = res.flags;
+  if (res.status == PH_RED_OVERFLOW) fl |= PH_FLAG_OVERFLOW;
+  if (out_flags) *out_flags = fl;
+  memcpy(out_value_host, res.value, sizeof(T));
+  if (out_index_host) *out_index_host = (red == PH_SUM) ? 0 : (res.index == INT64_MAX ? -1 : res.index);
   return PH_OK;
 }
 

@@ -91,11 +91,110 @@ int32_t make_plan(Plan& p, int nops, const ph_desc* const* descs) {
   return PH_OK;
 }
 
+// ---- position-weighted 64-bit checksum of a device buffer (verification aid of bench.py / tests)
+// sum over 8-byte words w_i of w_i * (2 * (i + word_offset) + 1)  (mod 2^64): wrapping adds commute, so
+// the value does not depend on the grid or on how an array is sharded over ranks (a rank passes the
+// GLOBAL word index of its first word and the per-rank values are added), but it does depend on WHERE
+// every word sits -- a misplaced plane or a stale halo changes it.
+static __global__ void __launch_bounds__(256) checksum64_kernel(const uint64_t* __restrict__ x, int64_t nwords,
+                                                                uint64_t word_offset, unsigned long long* __restrict__ out) {
+  uint64_t acc = 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < nwords; i += stride) {
+    if (i + 4 <= nwords) {
+      const RawVec<32> v = ld_stream<32>(x + i);
+#pragma unroll
+      for (int k = 0; k < 4; k++) acc += v.q[k] * (2 * ((uint64_t)(i + k) + word_offset) + 1);
+    } else {
+      for (int64_t k = i; k < nwords; k++) acc += x[k] * (2 * ((uint64_t)k + word_offset) + 1);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+  __shared__ uint64_t sh[8];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint64_t t = 0;
+    for (int w = 0; w < 8; w++) t += sh[w];
+    atomicAdd(out, (unsigned long long)t);
+  }
+}
+
 }  // namespace ph
 
 using namespace ph;
 
 extern "C" {
+
+int32_t ph_checksum64(const void* dev, size_t nbytes, uint64_t word_offset, uint64_t* out_host) {
+  PH_REQUIRE_INIT();
+  if (!out_host) return set_error(PH_ERR_INVALID, "null out_host");
+  if (nbytes % 8 || ((uintptr_t)dev % 32)) return set_error(PH_ERR_INVALID, "ph_checksum64 needs a 32-byte aligned buffer of whole 8-byte words");
+  Runtime& r = rt();
+  int32_t st = ensure_scratch(1 << 20);
+  if (st != PH_OK) return st;
+  unsigned long long* acc = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(r.d_scratch) + (1 << 20) - 128);
+  PH_CUDA(cudaMemsetAsync(acc, 0, 8, r.stream));
+  const int64_t nwords = (int64_t)(nbytes / 8);
+  if (nwords) {
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)r.sm_count * 8, ceil_div(nwords, (int64_t)256 * 4)));
+    checksum64_kernel<<<blocks, 256, 0, r.stream>>>(reinterpret_cast<const uint64_t*>(dev), nwords, word_offset, acc);
+    PH_LAUNCH_CHECK("checksum64_kernel");
+  }
+  PH_CUDA(cudaMemcpyAsync(r.h_scratch, acc, 8, cudaMemcpyDeviceToHost, r.stream));
+  PH_CUDA(cudaStreamSynchronize(r.stream));
+  memcpy(out_host, r.h_scratch, 8);
+  return PH_OK;
+}
+
+// ---- caller-visible streams: chunked host <-> device pipelines through the array API
+int32_t ph_stream_create(void** out_stream) {
+  PH_REQUIRE_INIT();
+  if (!out_stream) return set_error(PH_ERR_INVALID, "null out_stream");
+  cudaStream_t s;
+  PH_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  *out_stream = (void*)s;
+  return PH_OK;
+}
+
+int32_t ph_stream_destroy(void* stream) {
+  PH_REQUIRE_INIT();
+  if (!stream) return PH_OK;
+  if ((cudaStream_t)stream == rt().stream) rt().stream = rt().own_stream;
+  PH_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  PH_CUDA(cudaStreamDestroy((cudaStream_t)stream));
+  return PH_OK;
+}
+
+// everything queued on `waiter` AFTER this call runs after everything queued on `signaler` BEFORE it
+// (NULL = the library's own stream)
+int32_t ph_stream_wait(void* waiter, void* signaler) {
+  PH_REQUIRE_INIT();
+  Runtime& r = rt();
+  cudaStream_t w = waiter ? (cudaStream_t)waiter : r.own_stream, s = signaler ? (cudaStream_t)signaler : r.own_stream;
+  if (w == s) return PH_OK;
+  cudaEvent_t ev;
+  PH_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  PH_CUDA(cudaEventRecord(ev, s));
+  PH_CUDA(cudaStreamWaitEvent(w, ev, 0));
+  PH_CUDA(cudaEventDestroy(ev));          // released once the recorded work completes
+  return PH_OK;
+}
+
+int32_t ph_stream_sync(void* stream) {
+  PH_REQUIRE_INIT();
+  PH_CUDA(cudaStreamSynchronize(stream ? (cudaStream_t)stream : rt().own_stream));
+  return PH_OK;
+}
+
+// stream-ordered release on the stream the block was last used on (ph_free releases on the CURRENT stream)
+int32_t ph_free_on(void* dev, void* stream) {
+  PH_REQUIRE_INIT();
+  if (!dev) return PH_OK;
+  PH_CUDA(cudaFreeAsync(dev, stream ? (cudaStream_t)stream : rt().own_stream));
+  return PH_OK;
+}
 
 int32_t ph_device_count(int32_t* out) {
   if (!out) return set_error(PH_ERR_INVALID, "null out");

@@ -39,3 +39,15 @@ def simulate(state: DeviceNArray, coeff, steps: int, mode: int = FIXED) -> Devic
     check(_lib.load().ph_heat_run(dtype_code(state.dtype), len(state.shape), _ext(state.shape), c.ctypes.data,
                                   mode, state.ptr, other.ptr, int(steps), C.byref(final_is_b)))
     return other if final_is_b.value else state
+
+
+def simulate_into(state: DeviceNArray, other: DeviceNArray, coeff, steps: int, mode: int = FIXED) -> DeviceNArray:
+    """`simulate` between two caller-owned buffers (no allocation: a 2048^3 f32 grid is 34 GB per buffer);
+    returns whichever of the two holds the final state."""
+    if state.dtype.kind != "f" or other.dtype != state.dtype or list(other.shape) != list(state.shape):
+        raise TypeError("simulate_into needs two Float32 / Float64 arrays of one shape")
+    c = np.array(coeff, dtype=state.dtype)
+    final_is_b = C.c_int32(0)
+    check(_lib.load().ph_heat_run(dtype_code(state.dtype), len(state.shape), _ext(state.shape), c.ctypes.data,
+                                  mode, state.ptr, other.ptr, int(steps), C.byref(final_is_b)))
+    return other if final_is_b.value else state

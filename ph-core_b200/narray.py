@@ -130,6 +130,86 @@ def sync() -> None:
     raise_for_flags(flags.value)
 
 
+_pending = []
+
+
+def _keepalive(obj) -> None:
+    """An array whose bytes an asynchronous copy still reads stays referenced until the next sync()."""
+    _pending.append(obj)
+    if len(_pending) > 4096:
+        del _pending[:2048]
+
+
+class _PinnedOwner:
+    def __init__(self, nbytes: int):
+        p = C.c_void_p()
+        check(_lib.load().ph_host_alloc(max(1, int(nbytes)), C.byref(p)))
+        self.ptr = p.value
+        self.nbytes = int(nbytes)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                _lib.load().ph_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """An uninitialised host array in pinned memory; slices of it are pinned too (they keep it alive)."""
+    dt = np.dtype(dtype)
+    n = int(np.prod([int(s) for s in shape], dtype=np.int64)) if len(shape) else 1
+    owner = _PinnedOwner(n * dt.itemsize)
+    buf = (C.c_char * max(1, n * dt.itemsize)).from_address(owner.ptr)
+    buf._ph_owner = owner            # the array (and every slice of it) references buf, buf keeps the allocation
+    return np.frombuffer(buf, dtype=dt, count=n).reshape(shape)
+
+
+def pinned_from(arr: np.ndarray) -> np.ndarray:
+    out = pinned_empty(arr.shape, arr.dtype)
+    out[...] = arr
+    return out
+
+
+class Stream:
+    """A CUDA stream of the library (ph_stream_create).  `with Stream() as s:` makes every array operation
+    inside the block launch on it; `s.wait(other)` orders it behind what `other` has queued so far."""
+
+    def __init__(self):
+        _lib.init()
+        p = C.c_void_p()
+        check(_lib.load().ph_stream_create(C.byref(p)))
+        self.handle = p.value
+        self._saved = []
+
+    def __enter__(self):
+        lib = _lib.load()
+        self._saved.append(lib.ph_stream())
+        check(lib.ph_set_stream(self.handle))
+        return self
+
+    def __exit__(self, *exc):
+        check(_lib.load().ph_set_stream(self._saved.pop()))
+        return False
+
+    def wait(self, other: "Stream" = None) -> None:
+        check(_lib.load().ph_stream_wait(self.handle, other.handle if other is not None else None))
+
+    def synchronize(self) -> None:
+        check(_lib.load().ph_stream_sync(self.handle))
+
+    def close(self) -> None:
+        if self.handle:
+            check(_lib.load().ph_stream_destroy(self.handle))
+            self.handle = None
+
+
+def main_stream_wait(s: Stream) -> None:
+    """The library's own stream waits for everything queued so far on `s`."""
+    check(_lib.load().ph_stream_wait(None, s.handle))
+
+
 def _scalar_of(value, dtype: np.dtype, what: str) -> np.ndarray:
     """A scalar operand as ONE element of the array's dtype.  The device path computes in the
     array's element type only (same-dtype operands): a scalar that the type cannot
@@ -169,13 +249,15 @@ class _Buffer:
         _lib.init()
         self.nbytes = int(nbytes)
         p = C.c_void_p()
-        check(_lib.load().ph_alloc(self.nbytes, C.byref(p)))
+        lib = _lib.load()
+        check(lib.ph_alloc(self.nbytes, C.byref(p)))
         self.ptr = p.value
+        self.stream = lib.ph_stream()        # the pool block is released on the stream it was handed out on
 
     def __del__(self):
         try:
             if getattr(self, "ptr", None):
-                _lib.load().ph_free(self.ptr)
+                _lib.load().ph_free_on(self.ptr, self.stream)
                 self.ptr = None
         except Exception:
             pass
@@ -464,8 +546,23 @@ class _Indexable:
         return [DeviceNArray(rest, self.dtype, _SubBuffer(moved._buf, i * step, step)) for i in range(n)]
 
     def each_slice(self, axis: int = 0):
-        """MultiIndexable#each_slice (:742-748)."""
-        return iter(self.slices(axis))
+        """MultiIndexable#each_slice (:742-748): the slices `self[.., i, ..]` one after the other.  On the
+        device each one is a DeviceView over the SOURCE buffer -- a descriptor, no copy and no launch -- so
+        the reference's per-axis idiom (`each_slice(axis) { |s| acc = acc + s }`, :742-786) costs only the
+        consumer's kernel, which reads the strided slice directly.  `slices` (independent arrays, one
+        batched permuting copy) stays for callers that need owned copies."""
+        nd = len(self.shape)
+        if not 0 <= axis < nd:
+            raise CrIndexError(f"axis {axis} is not present in a {nd}-dimensional MultiIndexable")
+        base = self.view()
+        d = base.desc()
+        rest_ext = [int(d.extent[i]) for i in range(nd) if i != axis]
+        rest_str = [int(d.stride[i]) for i in range(nd) if i != axis]
+        if not rest_ext:                                         # slicing a vector: 1-element slices of shape [1]
+            rest_ext, rest_str = [1], [1]
+        step = int(d.stride[axis])
+        for i in range(self.shape[axis]):
+            yield DeviceView(self._buf, PhDesc.make(rest_ext, rest_str, int(d.offset) + i * step), rest_ext, self.dtype)
 
     def tile(self, counts: Sequence[int]) -> "DeviceNArray":
         """MultiIndexable#tile (:818-827): out[c] = self[c % shape]; as a descriptor every axis
@@ -612,6 +709,45 @@ class _Indexable:
     def eq(self, o): return self._compare("==", o, eq_style=True)   # MultiIndexable#eq (:899-913)
     def match(self, value): return self._compare("==", value)        # MultiIndexable#=~ (:916-920)
 
+    def cmp(self, other) -> "DeviceNArray":
+        """`<=>` of the operator list (src/multi_indexable.cr:960-981): -1 / 0 / 1 as an Int32 array.  Integer
+        element types only: Float#<=> is Int32? (nil against NaN), which has no device representation."""
+        lib = _lib.load()
+        if self.dtype.kind not in "iu":
+            raise TypeError("device path: <=> is defined for integer element types (Float#<=> is nilable)")
+        out = DeviceNArray(self.shape, np.int32)
+        dt = dtype_code(self.dtype)
+        if isinstance(other, _Indexable):
+            if list(other.shape) != list(self.shape):
+                raise ShapeError(f"The shape of this MultiIndexable ({self.shape}) does not match the shape of "
+                                 f"the one provided ({other.shape}), so '<=>' cannot be applied element-wise.")
+            self._same_dtype(other, "'<=>'")
+            check(lib.ph_compare3(dt, self.ptr, C.byref(self.desc()), other.ptr, C.byref(other.desc()), out.ptr,
+                                  C.byref(out.desc())))
+        else:
+            s = _scalar_of(other, self.dtype, "'<=>'")
+            check(lib.ph_compare3_scalar(dt, self.ptr, C.byref(self.desc()), s.ctypes.data, 0, out.ptr, C.byref(out.desc())))
+        return out
+
+    def checksum64(self, word_offset: int = 0) -> int:
+        """Position-weighted 64-bit checksum of a contiguous array's bytes (ph_checksum64): a verification
+        aid -- shards add up (pass the global 8-byte-word index of the shard's first word)."""
+        if not isinstance(self, DeviceNArray):
+            return self.to_narr().checksum64(word_offset)
+        out = C.c_uint64(0)
+        check(_lib.load().ph_checksum64(self.ptr, self.size * self.dtype.itemsize, int(word_offset), C.byref(out)))
+        return out.value
+
+    def to_host_async(self, out: np.ndarray) -> None:
+        """Device -> host into a PINNED array (`pinned_empty`), asynchronous: the data is valid after the
+        next `sync()` (which is also the raise point for data-dependent errors) or Stream.synchronize()."""
+        src = self if isinstance(self, DeviceNArray) else self.to_narr()
+        if list(out.shape) != list(src.shape) or out.dtype != src.dtype or not out.flags["C_CONTIGUOUS"]:
+            raise ShapeError(f"to_host_async needs a contiguous {src.dtype} destination of shape {src.shape}")
+        if out.size:
+            check(_lib.load().ph_d2h_async(out.ctypes.data, src.ptr, out.nbytes))
+        _keepalive(src)
+
     def equals(self, other: "_Indexable") -> bool:
         """NArray#== (src/n_array.cr:440-447) for two device arrays."""
         if not isinstance(other, _Indexable) or list(other.shape) != list(self.shape) or other.dtype != self.dtype:
@@ -721,6 +857,18 @@ class DeviceNArray(_Indexable):
         if arr.size:
             check(_lib.load().ph_h2d(out.ptr, arr.ctypes.data, arr.nbytes))
             check(_lib.load().ph_sync())   # pageable source: keep it alive until copied
+        return out
+
+    @classmethod
+    def from_host_async(cls, arr: np.ndarray) -> "DeviceNArray":
+        """Host -> device from a PINNED, contiguous array (`pinned_empty`): returns at once, the copy is
+        ordered on the current stream like any operator (a pageable source would make it synchronous)."""
+        _lib.init()
+        if not arr.flags["C_CONTIGUOUS"]:
+            raise ShapeError("from_host_async needs a contiguous (pinned) source")
+        out = cls(arr.shape, arr.dtype)
+        if arr.size:
+            check(_lib.load().ph_h2d(out.ptr, arr.ctypes.data, arr.nbytes))
         return out
 
     @classmethod

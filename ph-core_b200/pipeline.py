@@ -1,0 +1,67 @@
+"""Chunked host -> device -> host pipelines written with the array API.
+
+One elementwise expression over HOST-resident operands is bound by the host link, not by any kernel:
+uploading the operands, running the operators and downloading the result one after the other leaves the
+link idle two thirds of the time.  `map_rows` cuts the leading axis into chunks and runs every chunk on one
+of a few streams -- `DeviceNArray.from_host_async` (pinned source), the caller's expression on device
+arrays, `to_host_async` (pinned destination) -- so the upload of chunk i+1, the kernels of chunk i and the
+download of chunk i-1 overlap (PCIe is full duplex).  Everything goes through the public array API and the
+stream entry points of include/ph_gpu.h (ph_stream_create / ph_set_stream / ph_stream_wait); nothing here
+builds descriptors by hand.
+"""
+from __future__ import annotations
+
+from typing import Callable, Sequence
+
+import numpy as np
+
+from .narray import DeviceNArray, Stream, ShapeError, main_stream_wait, sync
+
+
+class RowPipeline:
+    """`streams` streams reused across calls (creating a stream costs more than a chunk)."""
+
+    def __init__(self, chunks: int = 8, streams: int = 3):
+        self.chunks = int(chunks)
+        self.streams = [Stream() for _ in range(int(streams))]
+
+    def map_rows(self, fn: Callable, rows: Sequence[np.ndarray], out: np.ndarray, shared: Sequence[np.ndarray] = (),
+                 wait: bool = True) -> None:
+        """out[r0:r1] = fn(*rows[k][r0:r1] as device arrays, *shared as device arrays) for every row chunk.
+        `rows` and `out` are pinned host arrays (narray.pinned_empty) with the same leading extent; `shared`
+        operands (e.g. a broadcast row vector) are uploaded once.  With wait=True the call returns when `out`
+        is complete and raises pending data-dependent errors; wait=False leaves that to the caller's sync()."""
+        n = out.shape[0]
+        for r in rows:
+            if r.shape[0] != n:
+                raise ShapeError("map_rows: every row operand needs the leading extent of the output")
+        first = self.streams[0]
+        for s in self.streams:
+            s.wait(None)                                           # behind whatever the main stream has queued
+        with first:
+            shared_dev = [DeviceNArray.from_host_async(x) for x in shared]
+        for s in self.streams[1:]:
+            s.wait(first)
+        per = -(-n // self.chunks)
+        keep = []
+        for k in range(self.chunks):
+            r0, r1 = k * per, min(n, (k + 1) * per)
+            if r0 >= r1:
+                break
+            with self.streams[k % len(self.streams)]:
+                ins = [DeviceNArray.from_host_async(r[r0:r1]) for r in rows]
+                res = fn(*ins, *shared_dev)
+                res.to_host_async(out[r0:r1])
+                keep.append((ins, res))
+                del ins, res
+        for s in self.streams:
+            main_stream_wait(s)
+        if wait:
+            sync()
+        # device temporaries are released on the streams they were used on (narray._Buffer)
+        del keep, shared_dev
+
+    def close(self) -> None:
+        for s in self.streams:
+            s.close()
+        self.streams = []

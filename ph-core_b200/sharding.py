@@ -175,33 +175,71 @@ def world_rank() -> Tuple[int, int]:
     return _comm["world"], _comm["rank"]
 
 
+def p2p_ready() -> bool:
+    """True when every rank mapped its peers' memory (CUDA IPC): sharded reductions combine inside the
+    reduction kernel and ph_heat_run_sharded delivers its own halos; False = the NCCL forms run."""
+    out = C.c_int32(0)
+    check(_lib.load().ph_comm_p2p_ready(C.byref(out)))
+    return bool(out.value)
+
+
+class _SymmBuffer:
+    """Peer-mapped device memory (ph_symm_alloc).  Allocation and release are COLLECTIVE, so release is
+    explicit (`free()`, every rank, same order) and never left to the garbage collector; whatever is
+    still allocated is released by ph_comm_destroy."""
+
+    def __init__(self, nbytes: int):
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        check(_lib.load().ph_symm_alloc(self.nbytes, C.byref(p)))
+        self.ptr = p.value
+
+    def free(self) -> None:
+        if self.ptr:
+            check(_lib.load().ph_symm_free(self.ptr))
+            self.ptr = None
+
+
+def symm_empty(shape, dtype):
+    """An uninitialised DeviceNArray in peer-mapped memory (collective: every rank calls it)."""
+    from .narray import DeviceNArray
+    dt = np.dtype(dtype)
+    n = int(np.prod([int(v) for v in shape], dtype=np.int64)) if len(shape) else 0
+    return DeviceNArray(shape, dt, _SymmBuffer(max(1, n) * dt.itemsize))
+
+
+def symm_from_host(arr: np.ndarray):
+    """`DeviceNArray.from_host` into peer-mapped memory (collective)."""
+    arr = np.ascontiguousarray(arr)
+    out = symm_empty(arr.shape, arr.dtype)
+    if arr.size:
+        check(_lib.load().ph_h2d(out.ptr, arr.ctypes.data, arr.nbytes))
+        check(_lib.load().ph_sync())
+    return out
+
+
 def reduce_full_sharded(local, name: str, row_offset_elems: int = 0):
-    """Full reduction of an array sharded along axis 0: local two-pass reduce, then
-    allreduce of the per-GPU partial (sum/min/max) or allgather of (value, index) pairs
-    (argmax/argmin).  `row_offset_elems` = number of elements owned by lower ranks."""
-    from .narray import DeviceNArray, dtype_code, _Buffer, _RED
+    """Full reduction of an array sharded along axis 0 (ph_reduce_full_sharded; collective -- every rank
+    calls it, also with an EMPTY shard, which contributes the identity).  sum / min / max return the value;
+    argmax / argmin return (value, GLOBAL flat index of the first extremum).  `row_offset_elems` = number of
+    elements owned by lower ranks.  Raises like the undivided array would: EmptyError for min / max of
+    nothing, OverflowError for an integer sum leaving T over the global lexicographic fold, ArgumentError
+    for NaN under max -- on EVERY rank (the flags travel with the partials)."""
+    from .narray import dtype_code, _RED, raise_for_flags, CrEmptyError
     lib = _lib.load()
-    world, rank = world_rank()
-    dt = local.dtype
-    res = _Buffer(64)
-    idx_ptr = res.ptr + 16
-    check(lib.ph_reduce_full_dev(K[_RED[name]], dtype_code(dt), local.ptr, C.byref(local.desc()), res.ptr, idx_ptr))
-    if name in ("sum", "min", "max"):
-        check(lib.ph_allreduce(K[_RED[name]], dtype_code(dt), res.ptr, 1))
-        out = np.zeros(1, dtype=dt)
-        check(lib.ph_d2h(out.ctypes.data, res.ptr, dt.itemsize))
-        DeviceNArray.raise_pending()
-        return out[0]
-    # one 32-byte record per rank: value @0, local flat index @16, elements owned by lower ranks @24
-    # (the offset rides in the same allgather: no second collective, one D2H)
-    off = np.array([int(row_offset_elems)], dtype=np.int64)
-    check(lib.ph_h2d(res.ptr + 24, off.ctypes.data, 8))      # pageable source: staged before the call returns
-    gathered = _Buffer(32 * world)
-    check(lib.ph_allgather(res.ptr, gathered.ptr, 32))
-    raw = np.zeros(32 * world, dtype=np.uint8)
-    check(lib.ph_d2h(raw.ctypes.data, gathered.ptr, raw.nbytes))
-    DeviceNArray.raise_pending()
-    return combine_extremum_records(raw, dt, world, is_max=(name == "argmax"))
+    dt = np.dtype(np.uint8) if local.dtype == np.dtype(np.bool_) else local.dtype
+    val = np.zeros(2, dtype=np.uint64)
+    idx = C.c_int64(-1)
+    flags = C.c_uint32(0)
+    check(lib.ph_reduce_full_sharded(K[_RED[name]], dtype_code(dt), local.ptr, C.byref(local.desc()), int(row_offset_elems),
+                                     val.ctypes.data, C.byref(idx), C.byref(flags)))
+    raise_for_flags(flags.value)
+    value = val.view(np.uint8)[:dt.itemsize].view(dt)[0]
+    if name == "sum":
+        return value
+    if idx.value < 0:
+        raise CrEmptyError("Empty enumerable")
+    return (value, idx.value) if name.startswith("arg") else value
 
 
 def heat_run_sharded(slab, other, coeff, steps: int, ghost: int = 1):
@@ -385,6 +423,14 @@ class ShardedNArray:
     def min(self, axis=None):
         return self._reduce("min", axis)
 
+    def argmin(self):
+        v, i = reduce_full_sharded(self.local, "argmin", self.row0 * self._row_elems())
+        coord = []
+        for length in reversed(self.shape):
+            coord.append(i % length)
+            i //= length
+        return v, list(reversed(coord))
+
     def argmax(self):
         v, i = reduce_full_sharded(self.local, "argmax", self.row0 * self._row_elems())
         coord = []
@@ -394,11 +440,38 @@ class ShardedNArray:
         return v, list(reversed(coord))
 
     def _reduce(self, name, axis):
-        from .narray import dtype_code, _RED
+        from .narray import dtype_code, _RED, DeviceNArray, CrEmptyError, CrIndexError, _Buffer
         if axis is None:
             return reduce_full_sharded(self.local, name, self.row0 * self._row_elems())
-        part = getattr(self.local, name)(axis=axis)
-        if axis == 0:                          # partial over my rows -> allreduce of the [inner] plane
-            check(_lib.load().ph_allreduce(K[_RED[name]], dtype_code(part.dtype), part.ptr, part.size))
-            return part                        # replicated DeviceNArray
-        return ShardedNArray([self.shape[0]] + part.shape[1:], part)   # kept axis 0: still sharded
+        if axis < 0 or axis >= len(self.shape):
+            raise CrIndexError(f"axis {axis} is not present in a {len(self.shape)}-dimensional MultiIndexable")
+        if axis != 0:
+            part = getattr(self.local, name)(axis=axis)
+            return ShardedNArray([self.shape[0]] + part.shape[1:], part)   # kept axis 0: still sharded
+        # axis 0 is the sharded one: partial over my rows, then a combine across ranks.  Every decision that
+        # can raise is taken on the GLOBAL shape first, so all ranks reach the collective (or none does).
+        if self.shape[0] == 0 and name != "sum":
+            raise CrEmptyError("Empty enumerable")
+        out_shape = self.shape[1:] or [1]
+        if self.row1 - self.row0 > 0:
+            part = getattr(self.local, name)(axis=0)
+        else:                                                            # an empty shard contributes the identity
+            dt = self.dtype
+            if name == "sum":
+                ident = 0
+            elif dt.kind == "f":
+                ident = -np.inf if name == "max" else np.inf
+            else:
+                info = np.iinfo(dt)
+                ident = info.min if name == "max" else info.max
+            part = DeviceNArray.fill(out_shape, ident, dt)
+        lib = _lib.load()
+        if name == "sum" and self.dtype.kind in "iu" and self.world > 1:
+            # integer sums are overflow-CHECKED: an ncclSum would wrap silently.  The per-rank partials
+            # ([world, inner], rank order = row order) are gathered and folded by the checked axis-0 sum.
+            nbytes = part.size * part.dtype.itemsize
+            gathered = DeviceNArray([self.world] + out_shape, part.dtype, _Buffer(max(1, nbytes * self.world)))
+            check(lib.ph_allgather(part.ptr, gathered.ptr, nbytes))
+            return gathered.sum(axis=0)
+        check(lib.ph_allreduce(K[_RED[name]], dtype_code(part.dtype), part.ptr, part.size))
+        return part                            # replicated DeviceNArray

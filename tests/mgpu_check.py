@@ -65,6 +65,31 @@ def main():
         assert fin.tobytes() == want[lay["start"]:lay["stop"]].tobytes(), \
             f"rank {rank}: 2-D heat slab (ghost {ghost}, {steps} steps) differs from oracle"
 
+    # ---- the same three heat cases with the slabs in peer-mapped memory: the stencil kernel stores the halo
+    #      planes straight into the neighbours' ghosts (no NCCL); without P2P these run the NCCL form again
+    p2p = S.p2p_ready()
+    for name, grid in (("small", field), ("big", big), ("2-D", flat2)):
+        for ghost, steps in ((1, 5), (2, 7), (2, 12), (2, 2)):
+            want = grid.copy()
+            for _ in range(steps):
+                want = O.heat_step_nd(want, np.float32(0.1))
+            lay = S.slab_layout(grid.shape[0], world, rank, ghost)
+            loc = S.slab_from_global(grid, world, rank, ghost)
+            a, b = S.symm_from_host(loc), S.symm_from_host(loc)
+            for rep in range(2):                                           # a second run re-uses the mapped slabs
+                fin = S.heat_run_sharded(a, b, 0.1, steps, ghost)
+                got = fin.to_host()
+                assert got[ghost:-ghost].tobytes() == want[lay["start"]:lay["stop"]].tobytes(), \
+                    f"rank {rank}: {name} heat slab in peer-mapped memory (ghost {ghost}, {steps} steps, p2p={p2p}) differs"
+                # the ghost planes of the final state are the neighbours' edge planes
+                if lay["lo_rank"] >= 0:
+                    assert got[:ghost].tobytes() == want[lay["start"] - ghost:lay["start"]].tobytes(), "lower ghosts stale"
+                if lay["hi_rank"] >= 0:
+                    assert got[-ghost:].tobytes() == want[lay["stop"]:lay["stop"] + ghost].tobytes(), "upper ghosts stale"
+                ph.check(ph.load().ph_h2d(a.ptr, loc.ctypes.data, loc.nbytes))          # reset for the second run
+                ph.check(ph.load().ph_sync())
+            a._buf.free(); b._buf.free()
+
     # ---- sharded reductions
     data = rs.randint(-8, 9, size=(8 * world + 1, 50, 30)).astype(np.float32)
     data[3, 2, 1] = data[-1, 4, 4] = 99.0                      # tie across shards
@@ -75,6 +100,79 @@ def main():
     assert S.reduce_full_sharded(x, "max") == data.max() and S.reduce_full_sharded(x, "min") == data.min()
     v, i = S.reduce_full_sharded(x, "argmax", off)
     assert (v, i) == (np.float32(99.0), 3 * 1500 + 2 * 30 + 1), (v, i)
+    for _ in range(5):                                          # call parity of the double-buffered slots
+        assert S.reduce_full_sharded(x, "sum") == np.float32(data.sum(dtype=np.float64))
+        assert S.reduce_full_sharded(x, "argmin", off)[0] == data.min()
+    # every Crystal number type goes through the same combine
+    for dt in (np.float64, np.int32, np.int64, np.uint8, np.int16, np.uint64):
+        dd = rs.randint(0, 7, size=(3 * world + 2, 40)).astype(dt)
+        dd[1, 5] = dd[-1, 7] = 9
+        q0, q1 = S.shard_range(dd.shape[0], world, rank)
+        xs = D.from_host(dd[q0:q1])
+        total = dd.astype(np.int64).sum() if dd.dtype.kind != "f" else dd.sum()
+        if dd.dtype.kind == "f" or total <= np.iinfo(dt).max:
+            assert S.reduce_full_sharded(xs, "sum") == dt(total)
+        else:                                                   # UInt8: the global total leaves T -> every rank raises
+            try:
+                S.reduce_full_sharded(xs, "sum")
+                raise AssertionError(f"{np.dtype(dt)} sum {total} must overflow")
+            except ph.CrOverflowError:
+                pass
+        assert S.reduce_full_sharded(xs, "argmax", q0 * 40) == (dt(9), 1 * 40 + 5)
+        assert S.reduce_full_sharded(xs, "min") == dd.min()
+    # a rank that owns NO rows contributes the identity (and still enters the collective)
+    few = (rs.rand(max(1, world - 1), 6) + 1.0).astype(np.float32)                # all positive
+    f0, f1 = S.shard_range(few.shape[0], world, rank)
+    xf = D.from_host(few[f0:f1]) if f1 > f0 else D([0, 6], np.float32)
+    assert S.reduce_full_sharded(xf, "min") == few.min() and S.reduce_full_sharded(xf, "max") == few.max()
+    assert abs(float(S.reduce_full_sharded(xf, "sum")) - float(few.sum(dtype=np.float64))) <= 1e-4 * float(few.sum(dtype=np.float64))
+    v, i = S.reduce_full_sharded(xf, "argmax", f0 * 6)
+    assert (v, i) == (few.max(), int(np.argmax(few.reshape(-1))))
+    sf = S.ShardedNArray.from_global(few)
+    assert sf.min(axis=0).to_host().tobytes() == few.min(axis=0).tobytes()
+    assert sf.max(axis=0).to_host().tobytes() == few.max(axis=0).tobytes()
+    try:
+        S.reduce_full_sharded(D([0, 6], np.float32), "max")
+        raise AssertionError("max of an array that is empty on every rank must raise")
+    except ph.CrEmptyError:
+        pass
+    assert S.reduce_full_sharded(D([0, 6], np.float32), "sum") == 0
+    # integer sums are overflow-checked over the GLOBAL lexicographic fold, on every rank
+    big32 = np.zeros((2 * world, 4), np.int32)
+    big32[:, 0] = (2**31 - 1) // world                                           # every shard fits, the total fits too
+    g0, g1 = S.shard_range(big32.shape[0], world, rank)
+    xi = D.from_host(big32[g0:g1])
+    try:
+        S.reduce_full_sharded(xi, "sum")
+        raise AssertionError("global Int32 sum overflow must raise on every rank")
+    except ph.CrOverflowError:
+        pass
+    pre = np.zeros((world, 2), np.int32)
+    pre[0] = [2**31 - 2, 0]; pre[-1] = [5, -10]                                   # a PREFIX leaves Int32, the total does not
+    xp = D.from_host(pre[rank:rank + 1])
+    try:
+        S.reduce_full_sharded(xp, "sum")
+        raise AssertionError("a prefix of the global fold leaves Int32: must raise")
+    except ph.CrOverflowError:
+        pass
+    pre[-1] = [-10, 5]                                                            # same values, no prefix leaves Int32
+    assert S.reduce_full_sharded(D.from_host(pre[rank:rank + 1]), "sum") == np.int32(2**31 - 2 - 5)
+    si = S.ShardedNArray.from_global(big32)
+    try:
+        si.sum(axis=0)
+        raise AssertionError("Int32 axis-0 sum across ranks overflows: must raise")
+    except ph.CrOverflowError:
+        pass
+    assert S.ShardedNArray.from_global(big32 // 4).sum(axis=0).to_host().tolist() == (big32 // 4).sum(axis=0).tolist()
+    # NaN under max on ONE rank raises ArgumentError on EVERY rank (the flags travel with the partials)
+    nn = np.ones((world, 8), np.float32)
+    nn[world - 1, 3] = np.nan
+    try:
+        S.reduce_full_sharded(D.from_host(nn[rank:rank + 1]), "max")
+        raise AssertionError("NaN under max must raise on every rank")
+    except ph.CrArgumentError:
+        pass
+    assert D.take_flags() == 0
     # axis-0 reduce: allreduce of the [outer*inner] partial
     part = x.sum(axis=0)
     ph.check(ph.load().ph_allreduce(ph.K["PH_SUM"], ph.K["PH_F32"], part.ptr, part.size))
@@ -103,7 +201,7 @@ def main():
     assert sg.to_global().tobytes() == np.where(g > h, np.float32(0), g).tobytes()
     dist.barrier()
     if rank == 0:
-        print(f"MGPU_OK world={world}")
+        print(f"MGPU_OK world={world} p2p={S.p2p_ready()}")
     dist.destroy_process_group()
 
 

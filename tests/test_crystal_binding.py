@@ -46,7 +46,7 @@ def _cr_kind(cr_param: str) -> str:
     ty = cr_param.split(":", 1)[1].strip()
     if ty.endswith("*"):
         return "ptr"
-    return {"LibC::SizeT": "size", "Int64": "i64", "Int32": "i32"}[ty]
+    return {"LibC::SizeT": "size", "Int64": "i64", "UInt64": "i64", "Int32": "i32"}[ty]
 
 
 def test_every_c_entry_is_bound_with_the_same_signature_shape():
