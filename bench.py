@@ -542,9 +542,12 @@ def run_extras(ph, lib, dist, world, rank, torch, stream):
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
+    heat_clocks = ClockSampler(physical_gpu_index(torch.cuda.current_device()))
+    heat_clocks.start()
     ph.check(lib.ph_timer_start())
     fin = run(cur2, other, STEPS)
     ph.check(lib.ph_timer_stop(C.byref(ms)))
+    heat_clk = heat_clocks.stop()
     heat_ms = max_over_ranks(ms.value) / STEPS
     h = C.c_uint64(0)
     ph.check(lib.ph_checksum64(fin.ptr + (own0 + first_local) * pbytes, (own1 - own0) * pbytes, own0 * (pbytes // 8), C.byref(h)))
@@ -560,7 +563,8 @@ def run_extras(ph, lib, dist, world, rank, torch, stream):
                   "flag words + stream waits, no NCCL" if p2p else "NCCL send/recv of 2-plane halos every 2 steps, overlapped with the interior")),
         "decomposition": f"axis-0 slabs x{world}, two time steps per pass over HBM (temporal blocking, bit-identical)",
         "algorithmic_bytes_per_cell_update": 8,
-        "hbm_gbs_per_gpu": round(8 * G ** 3 / world / (heat_ms * 1e-3) / 1e9, 1)}
+        "hbm_gbs_per_gpu": round(8 * G ** 3 / world / (heat_ms * 1e-3) / 1e9, 1),
+        "clocks": heat_clk}
     if world == 1:
         # the reference's CPU path beside it: the slice-arithmetic step through ph-core's operator
         # structure (C port, one thread) on a 160^3 sample, and the flat OpenMP loop nest on 512^3
@@ -624,6 +628,8 @@ def run_extras(ph, lib, dist, world, rank, torch, stream):
         ok = (float(got) == float(exact)) if name == "sum" else (float(got[0]) == 99.0 and int(got[1]) == P1)
         ok = all(_gather_objects(dist, world, bool(ok)))
         out[key] = {"gbs": round(4 * n_total / (red_ms * 1e-3) / 1e9, 1), "ms": round(red_ms, 4), "result_ok": ok,
+                    "result": (float(got) if name == "sum" else [float(got[0]), int(got[1])]),
+                    "expected": (exact if name == "sum" else [99.0, P1]),
                     "check": ("integers in {-8..8} (+ two planted 99s): every partial sum is exact in f32, the result must equal the exact total"
                               if name == "sum" else "planted maximum 99 at two global indices in different shards: argmax must return the lower one"),
                     "collective": ("none (1 GPU)" if world == 1 else

@@ -44,6 +44,26 @@ module Phase
       make(shape.size, 0_i64, extent, stride)
     end
 
+    # The slice `src[.., index, ..]` along `axis` as a descriptor over the same buffer: the axis is removed,
+    # the offset moves by index * stride (what `each_slice` hands out; a vector's slices keep shape [1]).
+    def self.drop_axis(src : Desc, axis : Int, index : Int64) : Desc
+      extent, stride = axes, axes
+      src_extent, src_stride = src.extent, src.stride
+      rank = 0
+      src.rank.times do |i|
+        next if i == axis
+        extent[rank] = src_extent[i]
+        stride[rank] = src_stride[i]
+        rank += 1
+      end
+      if rank == 0
+        extent[0] = 1_i64
+        stride[0] = 1_i64
+        rank = 1
+      end
+      make(rank, src.offset + index * src_stride[axis], extent, stride)
+    end
+
     # `ShapeUtil.shape_to_size` in Int64 (the empty shape [] has size 0).
     def self.element_count(shape : Indexable(Int)) : Int64
       shape.empty? ? 0_i64 : shape.reduce(1_i64) { |acc, n| acc * n }

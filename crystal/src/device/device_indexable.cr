@@ -269,6 +269,35 @@ module Phase
       end
     {% end %}
 
+    # `<=>` of the operator list (multi_indexable.cr:960-981): -1 / 0 / 1 as Int32. Integer element types
+    # only: `Float#<=>` is `Int32?` (nil against NaN), which has no device representation.
+    def <=>(other : DeviceIndexable(T)) : DeviceNArray(Int32)
+      {% if !(T < Int) %}
+        {% raise "<=> on the device path is defined for integer element types (Float#<=> is nilable)" %}
+      {% end %}
+      if shape_internal != other.shape_internal
+        raise ShapeError.new("The shape of this MultiIndexable (#{shape_internal}) does not match the shape of the one provided (#{other.shape_internal}), so '<=>' cannot be applied element-wise.")
+      end
+      result = DeviceNArray(Int32).new(shape_internal)
+      if result.size > 0
+        a, b = desc, other.desc
+        Device.check LibPhGpu.ph_compare3(Device.dtype(T), dev.ptr, pointerof(a), other.dev.ptr, pointerof(b), result.dev.ptr.as(Int32*), result.desc_ptr)
+      end
+      result
+    end
+
+    def <=>(other : T) : DeviceNArray(Int32)
+      {% if !(T < Int) %}
+        {% raise "<=> on the device path is defined for integer element types (Float#<=> is nilable)" %}
+      {% end %}
+      result = DeviceNArray(Int32).new(shape_internal)
+      if result.size > 0
+        a = desc
+        Device.check LibPhGpu.ph_compare3_scalar(Device.dtype(T), dev.ptr, pointerof(a), pointerof(other).as(Void*), 0, result.dev.ptr.as(Int32*), result.desc_ptr)
+      end
+      result
+    end
+
     def eq(other : DeviceIndexable(T)) : DeviceNArray(Bool)
       if shape_internal != other.shape_internal
         raise DimensionError.new("Cannot compute the element-wise equality between a MultiIndexable with shape #{other.shape_internal} and one with shape #{shape_internal}.")
@@ -421,8 +450,22 @@ module Phase
       end
     end
 
-    def each_slice(axis = 0) : Iterator(DeviceNArray(T))
-      slices(axis).each
+    # `each_slice` hands out VIEWS over this array's buffer -- descriptors only, no copy and no launch -- so
+    # the reference's per-axis idiom (`each_slice(axis) { |s| acc = acc + s }`, multi_indexable.cr:742-786)
+    # costs just the consumer's kernels, which read the strided slices directly. `slices` makes independent
+    # arrays (one batched copy) for callers that need to own them.
+    def each_slice(axis = 0) : Iterator(DeviceView(T))
+      unless 0 <= axis < shape_internal.size
+        raise IndexError.new("Axis #{axis} is not present in a #{shape_internal.size}-dimensional MultiIndexable.")
+      end
+      source = desc
+      (0...shape_internal[axis]).each.map do |i|
+        DeviceView(T).new(dev, Descriptor.drop_axis(source, axis, i.to_i64), shape_without(axis))
+      end
+    end
+
+    def each_slice(axis = 0, &block : DeviceView(T) ->)
+      each_slice(axis).each { |slice| yield slice }
     end
 
     # `out[c] = self[c % shape]`; as a descriptor every axis becomes (count, extent) with strides

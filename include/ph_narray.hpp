@@ -342,7 +342,10 @@ class MultiIndexable {
 
   // ---- slices / tile (multi_indexable.cr:742-786, 818-843) ------------------------------------
   std::vector<DeviceNArray<T>> slices(int32_t axis = 0) const;
-  std::vector<DeviceNArray<T>> each_slice(int32_t axis = 0) const { return slices(axis); }
+  // each_slice (:742-748): the slices as VIEWS over this array's buffer -- descriptors only, no copy and no
+  // launch -- so the reference's per-axis idiom (a fold over each_slice) costs just the consumer's kernels,
+  // which read the strided slices directly; `slices` makes independent arrays with one batched copy.
+  std::vector<DeviceView<T>> each_slice(int32_t axis = 0) const;
   DeviceNArray<T> tile(const Shape& counts) const;
 
   // ---- elementwise, named forms (operators are free functions below) --------------------------
@@ -374,6 +377,9 @@ class MultiIndexable {
   DeviceNArray<Bool> eq(const MultiIndexable<T>& o) const;     // :899-913
   DeviceNArray<Bool> eq(type_identity_t<T> s) const;
   DeviceNArray<Bool> match(type_identity_t<T> s) const;        // =~ :916-920
+  // <=> of the operator list (:960-981): -1 / 0 / 1 as Int32; integer element types only (Float#<=> is Int32?)
+  DeviceNArray<int32_t> cmp(const MultiIndexable<T>& other) const;
+  DeviceNArray<int32_t> cmp(type_identity_t<T> s) const;
   bool equals(const MultiIndexable<T>& other) const;                                            // NArray#== n_array.cr:440-447
 
   // ---- reductions (Enumerable over NArray#each, n_array.cr:556-564) ---------------------------
@@ -594,6 +600,28 @@ std::vector<DeviceNArray<T>> MultiIndexable<T>::slices(int32_t axis) const {
   return out;
 }
 
+template <class T>
+std::vector<DeviceView<T>> MultiIndexable<T>::each_slice(int32_t axis) const {
+  if (axis < 0 || axis >= dimensions()) throw IndexError("axis " + std::to_string(axis) + " is out of range for shape " + shape_str(shape_));
+  ph_desc d{};
+  Shape rest;
+  for (int32_t i = 0; i < dimensions(); i++) {
+    if (i == axis) continue;
+    d.extent[d.rank] = desc_.extent[i];
+    d.stride[d.rank] = desc_.stride[i];
+    d.rank++;
+    rest.push_back(shape_[i]);
+  }
+  if (rest.empty()) { d.rank = 1; d.extent[0] = 1; d.stride[0] = 1; rest.push_back(1); }   // slices of a vector have shape [1]
+  std::vector<DeviceView<T>> out;
+  out.reserve((size_t)shape_[axis]);
+  for (int64_t i = 0; i < shape_[axis]; i++) {
+    d.offset = desc_.offset + i * desc_.stride[axis];
+    out.emplace_back(buf_, d, rest);
+  }
+  return out;
+}
+
 // out[c] = self[c % shape] (multi_indexable.cr:818-827); as a descriptor every axis becomes
 // (count, extent) with strides (0, stride): no modulo on the device.
 template <class T>
@@ -706,6 +734,24 @@ template <class T>
 DeviceNArray<Bool> MultiIndexable<T>::compare(int32_t cmp, T s, bool scalar_on_left) const {
   DeviceNArray<Bool> out(shape_);
   if (out.size()) Device::check(ph_compare_scalar(cmp, DType<T>::value, buf_->ptr, &desc_, &s, scalar_on_left ? 1 : 0, out.data(), &out.desc()));
+  return out;
+}
+
+template <class T>
+DeviceNArray<int32_t> MultiIndexable<T>::cmp(const MultiIndexable<T>& other) const {
+  static_assert(std::is_integral<T>::value, "<=> on the device path is defined for integer element types (Float#<=> is nilable)");
+  if (shape_ != other.shape_)
+    throw ShapeError("The shape of this MultiIndexable (" + shape_str(shape_) + ") does not match the shape of the one provided (" +
+                     shape_str(other.shape_) + "), so '<=>' cannot be applied element-wise.");
+  DeviceNArray<int32_t> out(shape_);
+  if (out.size()) Device::check(ph_compare3(DType<T>::value, buf_->ptr, &desc_, other.buf_->ptr, &other.desc_, out.data(), &out.desc()));
+  return out;
+}
+template <class T>
+DeviceNArray<int32_t> MultiIndexable<T>::cmp(type_identity_t<T> s) const {
+  static_assert(std::is_integral<T>::value, "<=> on the device path is defined for integer element types (Float#<=> is nilable)");
+  DeviceNArray<int32_t> out(shape_);
+  if (out.size()) Device::check(ph_compare3_scalar(DType<T>::value, buf_->ptr, &desc_, &s, 0, out.data(), &out.desc()));
   return out;
 }
 

@@ -1042,7 +1042,7 @@ int32_t reduce_full_sharded_t(int32_t red, const void* a, const ph_desc* d, int6
   CombineArgs cmb;
   int32_t st = comm_combine_args(&cmb, elems_before);
   if (st != PH_OK) return st;
-  const bool nccl = cmb.peer_slots[0] == nullptr;
+  const bool nccl = cmb.nranks > 1 && cmb.peer_slots[0] == nullptr;      // records travel by NCCL allgather
   const bool is_max = (red == PH_MAX || red == PH_ARGMAX);
   st = reduce_full_t<T>(red, a, d, nullptr, nullptr, &cmb);
   if (st != PH_OK) return st;
@@ -1070,7 +1070,7 @@ int32_t reduce_full_sharded_t(int32_t red, const void* a, const ph_desc* d, int6
       PH_LAUNCH_CHECK("sum_exact_kernel");
       CombineArgs c2;
       if ((st = comm_combine_args(&c2, elems_before)) != PH_OK) return st;
-      if (c2.peer_slots[0] == nullptr) {
+      if (c2.nranks > 1 && c2.peer_slots[0] == nullptr) {
         sum_exact_record_kernel<T><<<1, 32, 0, r.stream>>>(pp, grid, c2);
         PH_LAUNCH_CHECK("sum_exact_record_kernel");
         if ((st = comm_allgather_records(r.stream)) != PH_OK) return st;

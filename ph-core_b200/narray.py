@@ -130,16 +130,6 @@ def sync() -> None:
     raise_for_flags(flags.value)
 
 
-_pending = []
-
-
-def _keepalive(obj) -> None:
-    """An array whose bytes an asynchronous copy still reads stays referenced until the next sync()."""
-    _pending.append(obj)
-    if len(_pending) > 4096:
-        del _pending[:2048]
-
-
 class _PinnedOwner:
     def __init__(self, nbytes: int):
         p = C.c_void_p()
@@ -744,9 +734,15 @@ class _Indexable:
         src = self if isinstance(self, DeviceNArray) else self.to_narr()
         if list(out.shape) != list(src.shape) or out.dtype != src.dtype or not out.flags["C_CONTIGUOUS"]:
             raise ShapeError(f"to_host_async needs a contiguous {src.dtype} destination of shape {src.shape}")
+        lib = _lib.load()
         if out.size:
-            check(_lib.load().ph_d2h_async(out.ctypes.data, src.ptr, out.nbytes))
-        _keepalive(src)
+            check(lib.ph_d2h_async(out.ctypes.data, src.ptr, out.nbytes))
+        # `src` may be a temporary: its block is released on the stream it was allocated on (stream-ordered,
+        # so behind this copy when that is the current stream; otherwise that stream is made to wait for it)
+        home = getattr(src._buf, "stream", None)
+        cur = lib.ph_stream()
+        if home is not None and home != cur:
+            check(lib.ph_stream_wait(home, cur))
 
     def equals(self, other: "_Indexable") -> bool:
         """NArray#== (src/n_array.cr:440-447) for two device arrays."""

@@ -119,8 +119,7 @@ def test_config3_reductions_1e9_f32():
 
 
 def test_config5_heat_large_locality():
-    """3-D heat at 1024x1024x1024 f32 (the 2048^3 grid is covered by the N-GPU agreement test and
-    the bench): after k steps a cell depends only on cells within distance k, so a sub-cube
+    """3-D heat at 1024x1024x1024 f32 (the 2048^3 grid has its own test below): after k steps a cell depends only on cells within distance k, so a sub-cube
     compared with the oracle run on a cropped domain must match bit for bit."""
     n, k = 1024, 4
     rs = np.random.RandomState(11)
@@ -145,6 +144,39 @@ def test_config5_heat_large_locality():
         # faces of the crop that are NOT grid boundaries received wrong (held) data: trim k cells there
         sl = tuple(slice(0 if lo == 0 else k, None if hi == n else -k) for lo, hi in ((z0, z1), (y0, y1), (x0, x1)))
         assert_bits(got[sl], want[sl], f"crop {(z0, y0, x0)}")
+
+
+def test_config5_heat_2048_cubed_crops_vs_oracle():
+    """BASELINE configs[4] at its FULL size on one GPU (2 x 34.4 GB): 3-D heat on 2048^3 f32 with a
+    non-constant field (a constant one is a fixed point of the stencil and could not tell a wrong kernel from
+    a right one).  After k steps a cell depends only on cells within distance k, so crops replayed by the
+    oracle must match bit for bit: a corner touching three fixed faces, an interior block that straddles the
+    128-plane march boundary at plane 129 and tile boundaries in y / x, and the far corner.  k = 5 exercises
+    two two-step passes plus the odd single step."""
+    n, k = 2048, 5
+    lib = _lib.load()
+    tile = (np.random.RandomState(21).rand(1 << 22) * 100).astype(np.float32)      # 16 MiB, not a divisor of a plane row count
+    t = D.from_host(tile)
+    g, other = D([n, n, n], np.float32), D([n, n, n], np.float32)
+    total = n ** 3
+    step = tile.size - 4099 * 4                                                       # shifted copies: no two planes alike
+    pos, k0 = 0, 0
+    while pos < total:
+        m = min(step, total - pos)
+        ph.check(lib.ph_d2d(g.ptr + pos * 4, t.ptr + ((k0 * 52) % 4099) * 16, m * 4))
+        pos += m
+        k0 += 1
+    crops = [(0, 40, 0, 48, 0, 160), (110, 150, 1000, 1048, 1900, 2048), (2008, 2048, 2000, 2048, 0, 136)]
+    before = [g[rng(z0, z1 - 1), rng(y0, y1 - 1), rng(x0, x1 - 1)].to_host() for z0, z1, y0, y1, x0, x1 in crops]
+    fin = heat.simulate_into(g, other, 0.1, k)
+    for (z0, z1, y0, y1, x0, x1), b in zip(crops, before):
+        want = b.copy()
+        for _ in range(k):
+            want = O.heat_step_nd(want, np.float32(0.1))
+        got = fin[rng(z0, z1 - 1), rng(y0, y1 - 1), rng(x0, x1 - 1)].to_host()
+        sl = tuple(slice(0 if lo == 0 else k, None if hi == n else -k) for lo, hi in ((z0, z1), (y0, y1), (x0, x1)))
+        assert not np.array_equal(got[sl], b[sl])                                     # the field did move
+        assert_bits(got[sl], want[sl], f"2048^3 crop {(z0, y0, x0)}")
 
 
 def test_two_steps_per_pass_equal_single_steps_at_scale():

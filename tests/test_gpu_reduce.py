@@ -193,3 +193,30 @@ def test_reduce_strided_view():
     want = n[::-1, 1:10:2]
     assert v.sum() == want.sum()
     assert v.argmax() == (want.max(), [0, 4])
+
+
+def test_sharded_entry_on_one_rank_equals_the_plain_reduction():
+    """ph_reduce_full_sharded with a single-rank communicator: the same kernels in record mode (result in the
+    pinned host record, flags returned with it); also the empty-shard and integer-overflow decisions."""
+    from ph_core_b200 import sharding as S
+    S.comm_init(None)
+    rs = np.random.RandomState(4)
+    a = rs.randint(-8, 9, size=(37, 1000)).astype(np.float32)
+    a[5, 7] = a[20, 1] = 99.0
+    d = D.from_host(a)
+    assert S.reduce_full_sharded(d, "sum") == d.sum() == np.float32(a.sum(dtype=np.float64))
+    assert S.reduce_full_sharded(d, "max") == 99.0 and S.reduce_full_sharded(d, "min") == a.min()
+    assert S.reduce_full_sharded(d, "argmax") == (np.float32(99.0), 5 * 1000 + 7)
+    assert S.reduce_full_sharded(d, "argmin")[1] == int(np.argmin(a.reshape(-1)))
+    e = D([0, 4], np.float32)
+    assert S.reduce_full_sharded(e, "sum") == 0
+    with pytest.raises(ph.CrEmptyError):
+        S.reduce_full_sharded(e, "min")
+    i = D.from_host(np.array([2**31 - 1, 1, -5], np.int32))
+    with pytest.raises(ph.CrOverflowError):                     # a prefix leaves Int32 (exact ordered pass)
+        S.reduce_full_sharded(i, "sum")
+    assert S.reduce_full_sharded(D.from_host(np.array([2**31 - 1, -5, 1], np.int32)), "sum") == 2**31 - 5
+    n = D.from_host(np.array([1.0, np.nan, 3.0], np.float64))
+    with pytest.raises(ph.CrArgumentError):
+        S.reduce_full_sharded(n, "max")
+    assert take_flags() == set()

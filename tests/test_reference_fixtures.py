@@ -1,0 +1,207 @@
+"""Reference-anchored golden vectors for the floating-point half of the path.
+
+The reference's own specs pin integer results only; float elementwise results, Enumerable
+reductions and the stencil are "parity unpinned".  oracle/fixtures/gen_fixtures.cr and gen_heat_fixtures.cr
+(pure ph-core + Crystal stdlib) emit those vectors as tests/golden/ref_fixtures.json and
+ref_heat_fixtures.json on any machine with a Crystal toolchain.  There is none in this image, so until
+somebody commits the two files these tests report `xfail: no Crystal toolchain`; once the files exist they
+run -- the oracle on the CPU, the CUDA path under `-m gpu` -- and close the gap.
+Floats travel as decimal strings of their bit patterns; a raised exception as its class name."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ph_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FIX = os.path.join(GOLDEN, "ref_fixtures.json")
+HEAT = os.path.join(GOLDEN, "ref_heat_fixtures.json")
+WHY = ("no Crystal toolchain in the image: run oracle/fixtures/gen_fixtures.cr / gen_heat_fixtures.cr inside a "
+       "ph-core checkout and commit tests/golden/ref_*.json")
+needs_fix = pytest.mark.xfail(not os.path.exists(FIX), reason=WHY, strict=False)
+needs_heat = pytest.mark.xfail(not os.path.exists(HEAT), reason=WHY, strict=False)
+RAISES = {"OverflowError": "overflow", "DivisionByZeroError": "div0", "ArgumentError": "argument",
+          "Enumerable::EmptyError": "empty"}
+UINT = {np.dtype(np.float32): np.uint32, np.dtype(np.float64): np.uint64}
+
+
+def _load(path):
+    if not os.path.exists(path):
+        pytest.fail("fixture file absent")          # reported as xfail (see the marks)
+    return json.load(open(path))
+
+
+def _floats(bit_strings, dtype):
+    dt = np.dtype(dtype)
+    return np.array([int(b) for b in bit_strings], dtype=UINT[dt]).view(dt)
+
+
+def _same(got, want_text, dtype, what, tol=None):
+    """`want_text` is either an exception class name or the bit pattern of the result."""
+    dt = np.dtype(dtype)
+    if dt.kind == "f":
+        want = _floats([want_text], dt)[0]
+        if np.isnan(want):
+            assert np.isnan(got), what
+        elif tol is not None and np.isfinite(want):
+            assert abs(float(got) - float(want)) <= tol * abs(float(want)), what
+        else:
+            assert np.array([got], dt).tobytes() == np.array([want], dt).tobytes(), (what, got, want)
+    else:
+        assert int(got) == int(want_text), (what, got, want_text)
+
+
+def _check_table(table, pairs, dtype, run):
+    """run(op, x, y) -> (value, set of raised names)"""
+    for op, outcomes in table.items():
+        assert len(outcomes) == len(pairs)
+        for (x, y), want in zip(pairs, outcomes):
+            value, raised = run(op, x, y)
+            what = f"{x!r} {op} {y!r}"
+            if want in RAISES:
+                assert RAISES[want] in raised, (what, want, raised)
+            else:
+                assert not raised, (what, raised)
+                out_dt = np.float64 if (op == "/" and np.dtype(dtype).kind == "i") else (np.int32 if op == "<=>" else dtype)
+                _same(value, want, out_dt, what, tol=(1e-6 if np.dtype(dtype) == np.float64 else 1e-5) if op == "**" and np.dtype(dtype).kind == "f" else None)
+
+
+def _oracle_run(dtype):
+    def run(op, x, y):
+        a, b = np.array([x], dtype), np.array([y], dtype)
+        if op == "<=>":
+            return np.int32((a[0] > b[0]) - (a[0] < b[0])), set()
+        res, flags = O.ewise(op, a, b)
+        return res[0], set(flags)
+    return run
+
+
+def _pairs(values):
+    return [(x, y) for x in values for y in values]
+
+
+@needs_fix
+@pytest.mark.parametrize("key,dtype", [("f64", np.float64), ("f32", np.float32)])
+def test_oracle_float_elementwise_matches_the_reference(key, dtype):
+    fx = _load(FIX)
+    vals = _floats(fx[f"{key}_specials"], dtype)
+    _check_table(fx[f"ewise_{key}"], _pairs(list(vals)), dtype, _oracle_run(dtype))
+    for base, row in zip(vals, fx[f"{key}_powi"]):
+        for n, want in zip(fx["powi_exps"], row):
+            res, _ = O.ewise("**", np.array([base], dtype), np.int32(n))
+            _same(res[0], want, dtype, f"{base!r} ** {n}")
+
+
+@needs_fix
+def test_oracle_int32_elementwise_matches_the_reference():
+    fx = _load(FIX)
+    vals = [np.int32(v) for v in fx["i32_specials"]]
+    _check_table(fx["ewise_i32"], _pairs(vals), np.int32, _oracle_run(np.int32))
+    _check_table({"/": fx["i32_div"]}, _pairs(vals), np.int32, _oracle_run(np.int32))
+    for base, row in zip(vals, fx["i32_pow"]):
+        for e, want in zip(fx["pow_exps"], row):
+            res, flags = O.ewise("**", np.array([base], np.int32), np.array([e], np.int32))
+            if want in RAISES:
+                assert RAISES[want] in flags, (base, e, want)
+            else:
+                assert not flags and int(res[0]) == int(want), (base, e)
+
+
+@needs_fix
+def test_oracle_whole_array_operators_and_reductions_match_the_reference():
+    fx = _load(FIX)
+    w = fx["whole_f64"]
+    a, b = _floats(w["a"], np.float64).reshape(4, 5), _floats(w["b"], np.float64).reshape(4, 5)
+    for op in ["+", "*", "/", "//", "%"]:
+        assert O.ewise(op, a, b)[0].tobytes() == _floats(w[op], np.float64).tobytes(), op
+    t = O.ewise("*", a, b)[0]
+    assert O.ewise("+", t, a)[0].tobytes() == _floats(w["a*b+a"], np.float64).tobytes()
+    assert O.ewise("-", np.float64(2.0), a)[0].tobytes() == _floats(w["2-a"], np.float64).tobytes()
+    assert [str(int(v)) for v in O.compare(">", a, b).reshape(-1)] == w["a>b"]
+    for name, case in fx["reductions"].items():
+        dt = {"f32": np.float32, "f64": np.float64, "i32": np.int32}[name[:3]]
+        data = _floats(case["in"], dt) if np.dtype(dt).kind == "f" else np.array([int(v) for v in case["in"]], dt)
+        for which, fold in (("sum", O.reduce_sum_sequential), ("min", lambda d: O.reduce_minmax(d, "min")),
+                            ("max", lambda d: O.reduce_minmax(d, "max"))):
+            want = case[which]
+            try:
+                got = fold(data)
+            except (O.CrOverflowError, O.CrArgumentError, O.CrEmptyError) as e:
+                assert want in RAISES and {"CrOverflowError": "overflow", "CrArgumentError": "argument",
+                                           "CrEmptyError": "empty"}[type(e).__name__] == RAISES[want], (name, which)
+                continue
+            assert want not in RAISES, (name, which, want)
+            _same(got, want, dt, f"{name}.{which}")
+    am = fx["argmax_first"]
+    vals = _floats(am["values"], np.float32).reshape(am["shape"])
+    v, i = O.reduce_argmax(vals, "max")
+    assert np.float32(v).tobytes() == _floats([am["max"]], np.float32).tobytes() and O.index_to_coord(i, am["shape"]) == am["coord"]
+
+
+@needs_fix
+def test_float_text_matches_crystal_float_to_s():
+    from ph_core_b200 import io
+    fx = _load(FIX)
+    for key, dt in (("float_text_f64", np.float64), ("float_text_f32", np.float32)):
+        for b, text in fx[key]:
+            assert io.format_float(_floats([b], dt)[0]) == text
+    six = _floats([b for b, _ in fx["float_text_f64"][:6]], np.float64)
+    assert io.host_to_json(six) == fx["to_json_f64"]
+    assert io.host_to_yaml(six) == fx["to_yaml_f64"]
+
+
+@needs_heat
+def test_oracle_stencil_matches_the_reference():
+    fx = _load(HEAT)
+    coeff = _floats([fx["coeff"]], np.float64)[0]
+    assert np.float64(O.heat_example_coeff()).tobytes() == np.float64(coeff).tobytes()
+    s = _floats(fx["heat1d_initial"], np.float64)
+    one = O.heat_step_1d_example(s, coeff)
+    assert one.tobytes() == _floats(fx["heat1d_after_1"], np.float64).tobytes()
+    for _ in range(99):
+        one = O.heat_step_1d_example(one, coeff)
+    assert one.tobytes() == _floats(fx["heat1d_after_100"], np.float64).tobytes()
+    assert O.heat_simulate_1d_example().tobytes() == _floats(fx["heat1d_final"], np.float64).tobytes()
+    for key in ("heat2d", "heat3d"):
+        g = _floats(fx[key]["in"], np.float32).reshape(fx[key]["shape"])
+        s1 = O.heat_step_nd(g, np.float32(0.1))
+        assert s1.tobytes() == _floats(fx[key]["step1"], np.float32).tobytes(), key
+        assert O.heat_step_nd(s1, np.float32(0.1)).tobytes() == _floats(fx[key]["step2"], np.float32).tobytes(), key
+
+
+# ---------------------------------------------------------------- the CUDA path against the same vectors
+@pytest.mark.gpu
+@needs_fix
+@pytest.mark.parametrize("key,dtype", [("f64", np.float64), ("f32", np.float32), ("i32", np.int32)])
+def test_device_elementwise_matches_the_reference(key, dtype):
+    import ph_core_b200 as ph
+    from ph_core_b200 import DeviceNArray as D
+    from gpu_util import take_flags
+    fx = _load(FIX)
+    vals = (list(_floats(fx[f"{key}_specials"], dtype)) if key != "i32" else [np.int32(v) for v in fx["i32_specials"]])
+    ops = {"+": lambda x, y: x + y, "-": lambda x, y: x - y, "*": lambda x, y: x * y, "/": lambda x, y: x / y,
+           "//": lambda x, y: x // y, "%": lambda x, y: x % y, "**": lambda x, y: x ** y, "&": lambda x, y: x & y,
+           "|": lambda x, y: x | y, "^": lambda x, y: x ^ y, "&+": lambda x, y: x.wrapping_add(y),
+           "&-": lambda x, y: x.wrapping_sub(y), "&*": lambda x, y: x.wrapping_mul(y), "<=>": lambda x, y: x.cmp(y)}
+
+    def run(op, x, y):
+        res = ops[op](D.from_host(np.array([x], dtype)), D.from_host(np.array([y], dtype))).to_host(False)
+        return res[0], take_flags()
+    _check_table(fx[f"ewise_{key}"], _pairs(vals), dtype, run)
+
+
+@pytest.mark.gpu
+@needs_heat
+def test_device_stencil_matches_the_reference():
+    from ph_core_b200 import DeviceNArray as D, heat
+    fx = _load(HEAT)
+    coeff = _floats([fx["coeff"]], np.float64)[0]
+    s = _floats(fx["heat1d_initial"], np.float64)
+    got = heat.simulate(D.from_host(s), coeff, 10001, heat.EXAMPLE1D).to_host()
+    assert got.tobytes() == _floats(fx["heat1d_final"], np.float64).tobytes()
+    for key in ("heat2d", "heat3d"):
+        g = _floats(fx[key]["in"], np.float32).reshape(fx[key]["shape"])
+        assert heat.update_temp(D.from_host(g), 0.1).to_host().tobytes() == _floats(fx[key]["step1"], np.float32).tobytes(), key
+        assert heat.simulate(D.from_host(g), 0.1, 2).to_host().tobytes() == _floats(fx[key]["step2"], np.float32).tobytes(), key
