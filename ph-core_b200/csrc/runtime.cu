@@ -5,6 +5,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <algorithm>
+#include <vector>
 
 namespace ph {
 
@@ -149,11 +150,27 @@ int32_t ph_checksum64(const void* dev, size_t nbytes, uint64_t word_offset, uint
 }
 
 // ---- caller-visible streams: chunked host <-> device pipelines through the array API
+static std::vector<cudaStream_t>& live_streams() {
+  static std::vector<cudaStream_t> v;
+  return v;
+}
+static std::vector<cudaStream_t>& adopted_streams() {      // caller-owned streams seen by ph_set_stream
+  static std::vector<cudaStream_t> v;
+  return v;
+}
+static bool stream_is_live(cudaStream_t s) {
+  if (s == rt().own_stream || s == rt().aux_stream) return true;
+  for (cudaStream_t t : live_streams()) if (t == s) return true;
+  for (cudaStream_t t : adopted_streams()) if (t == s) return true;      // the caller keeps those alive
+  return false;
+}
+
 int32_t ph_stream_create(void** out_stream) {
   PH_REQUIRE_INIT();
   if (!out_stream) return set_error(PH_ERR_INVALID, "null out_stream");
   cudaStream_t s;
   PH_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  live_streams().push_back(s);
   *out_stream = (void*)s;
   return PH_OK;
 }
@@ -161,9 +178,14 @@ int32_t ph_stream_create(void** out_stream) {
 int32_t ph_stream_destroy(void* stream) {
   PH_REQUIRE_INIT();
   if (!stream) return PH_OK;
-  if ((cudaStream_t)stream == rt().stream) rt().stream = rt().own_stream;
-  PH_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-  PH_CUDA(cudaStreamDestroy((cudaStream_t)stream));
+  cudaStream_t s = (cudaStream_t)stream;
+  std::vector<cudaStream_t>& v = live_streams();
+  auto it = std::find(v.begin(), v.end(), s);
+  if (it == v.end()) return set_error(PH_ERR_INVALID, "ph_stream_destroy: not a live ph_stream_create stream");
+  if (s == rt().stream) rt().stream = rt().own_stream;
+  PH_CUDA(cudaStreamSynchronize(s));
+  v.erase(it);
+  PH_CUDA(cudaStreamDestroy(s));
   return PH_OK;
 }
 
@@ -192,7 +214,12 @@ int32_t ph_stream_sync(void* stream) {
 int32_t ph_free_on(void* dev, void* stream) {
   PH_REQUIRE_INIT();
   if (!dev) return PH_OK;
-  PH_CUDA(cudaFreeAsync(dev, stream ? (cudaStream_t)stream : rt().own_stream));
+  // a block may outlive the stream it was used on: that stream was synchronised when it was destroyed (or
+  // was a caller-owned stream adopted with ph_set_stream and is unknown here), so the library's own stream is
+  // as good an order as any
+  cudaStream_t s = stream ? (cudaStream_t)stream : rt().own_stream;
+  if (!stream_is_live(s)) s = rt().own_stream;
+  PH_CUDA(cudaFreeAsync(dev, s));
   return PH_OK;
 }
 
@@ -360,7 +387,9 @@ void* ph_stream(void) { return (void*)rt().stream; }
 
 int32_t ph_set_stream(void* cuda_stream) {
   PH_REQUIRE_INIT();
-  rt().stream = cuda_stream ? (cudaStream_t)cuda_stream : rt().own_stream;
+  cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : rt().own_stream;
+  if (!stream_is_live(s)) adopted_streams().push_back(s);
+  rt().stream = s;
   return PH_OK;
 }
 

@@ -2,10 +2,10 @@
 
 One elementwise expression over HOST-resident operands is bound by the host link, not by any kernel:
 uploading the operands, running the operators and downloading the result one after the other leaves the
-link idle two thirds of the time.  `map_rows` cuts the leading axis into chunks and runs every chunk on one
-of a few streams -- `DeviceNArray.from_host_async` (pinned source), the caller's expression on device
-arrays, `to_host_async` (pinned destination) -- so the upload of chunk i+1, the kernels of chunk i and the
-download of chunk i-1 overlap (PCIe is full duplex).  Everything goes through the public array API and the
+link idle two thirds of the time.  `map_rows` cuts the leading axis into chunks and runs them through an
+upload stream (`DeviceNArray.from_host_async`, pinned source), a compute stream (the caller's expression on
+device arrays) and a download stream (`to_host_async`, pinned destination), so the upload of chunk i+1, the
+kernels of chunk i and the download of chunk i-1 overlap (PCIe is full duplex).  Everything goes through the public array API and the
 stream entry points of include/ph_gpu.h (ph_stream_create / ph_set_stream / ph_stream_wait); nothing here
 builds descriptors by hand.
 """
@@ -19,11 +19,14 @@ from .narray import DeviceNArray, Stream, ShapeError, main_stream_wait, sync
 
 
 class RowPipeline:
-    """`streams` streams reused across calls (creating a stream costs more than a chunk)."""
+    """Three streams by ROLE, reused across calls: one uploads, one computes, one downloads.  Uploads of all
+    chunks are queued back to back (the host-to-device engine never waits for a kernel or a download of an
+    earlier chunk); chunk k's operators wait for its upload, its download for its operators."""
 
-    def __init__(self, chunks: int = 8, streams: int = 3):
+    def __init__(self, chunks: int = 16, streams: int = 3):
         self.chunks = int(chunks)
-        self.streams = [Stream() for _ in range(int(streams))]
+        self.up, self.comp, self.down = Stream(), Stream(), Stream()
+        self.streams = [self.up, self.comp, self.down]
 
     def map_rows(self, fn: Callable, rows: Sequence[np.ndarray], out: np.ndarray, shared: Sequence[np.ndarray] = (),
                  wait: bool = True) -> None:
@@ -35,31 +38,35 @@ class RowPipeline:
         for r in rows:
             if r.shape[0] != n:
                 raise ShapeError("map_rows: every row operand needs the leading extent of the output")
-        first = self.streams[0]
+        up, comp, down = self.up, self.comp, self.down
         for s in self.streams:
             s.wait(None)                                           # behind whatever the main stream has queued
-        with first:
+        with up:
             shared_dev = [DeviceNArray.from_host_async(x) for x in shared]
-        for s in self.streams[1:]:
-            s.wait(first)
         per = -(-n // self.chunks)
         keep = []
         for k in range(self.chunks):
             r0, r1 = k * per, min(n, (k + 1) * per)
             if r0 >= r1:
                 break
-            with self.streams[k % len(self.streams)]:
+            with up:
                 ins = [DeviceNArray.from_host_async(r[r0:r1]) for r in rows]
+            comp.wait(up)                                          # chunk k's operands (and the shared ones) have landed
+            with comp:
                 res = fn(*ins, *shared_dev)
+            down.wait(comp)
+            with down:
                 res.to_host_async(out[r0:r1])
-                keep.append((ins, res))
-                del ins, res
+            keep.append((ins, res))
+            del ins, res
+        # device temporaries are released on the streams they were allocated on: order each of those behind
+        # every consumer before letting go, then join the main stream
+        up.wait(comp); up.wait(down); comp.wait(down)
         for s in self.streams:
             main_stream_wait(s)
+        del keep, shared_dev
         if wait:
             sync()
-        # device temporaries are released on the streams they were used on (narray._Buffer)
-        del keep, shared_dev
 
     def close(self) -> None:
         for s in self.streams:
