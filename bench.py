@@ -664,8 +664,9 @@ def run_extras(ph, lib, dist, world, rank, torch, stream):
         torch.cuda.synchronize()
         preps = 3
         ph.check(lib.ph_timer_start())
+        p2p_perm = S.p2p_ready() and not os.environ.get("PH_PERMUTE_NCCL")
         for _ in range(preps):
-            t = src.permute()
+            t = src.permute(out=t) if p2p_perm else src.permute()
         ph.check(lib.ph_timer_stop(C.byref(ms)))
         perm_ms = max_over_ranks(ms.value) / preps
         # transposed[i, j] = j * n + i on my rows i in [q0, q1)
@@ -675,7 +676,10 @@ def run_extras(ph, lib, dist, world, rank, torch, stream):
         hsum = sum(_gather_objects(dist, world, t.local.checksum64(q0 * n))) % (1 << 64)
         out["sharded_permute_16384_f64"] = {"ms": round(perm_ms, 4), "gbs_aggregate": round(2 * n * n * 8 / (perm_ms * 1e-3) / 1e9, 1),
                                             "result_ok": ok, "checksum": f"{hsum:016x}",
-                                            "how": "ShardedNArray.permute: per-peer permuting gathers, all-to-all, scatters"}
+                                            "how": ("ShardedNArray.permute: ONE pass of peer stores -- the transpose kernel writes every block "
+                                                    "straight into its owner's shard over NVLink (ph_alltoall_strided), result buffer reused"
+                                                    if p2p_perm else
+                                                    "ShardedNArray.permute: per-peer permuting gathers, ncclSend/ncclRecv all-to-all, scatters")}
     return out
 
 

@@ -174,6 +174,22 @@ row("transposed scatter mutable_view.permute[..]=src f64", 2 * NS * 8,
     lambda: dst.mutable_view().permute().set_chunk([], src))
 row("clone (contiguous copy) f64", 2 * NS * 8, lambda: src.clone())
 del dst
+# ---- reductions over VIEWS of the same array, read in place (no gather into a temporary; PH_REDUCE_GATHER=1
+#      restores the gather-first form for A/B): bytes = the bytes of the view (+ the per-axis output)
+v_rows = src.view(rng(0, None, 2), ph.ALL)
+row("view reduce narr[0..2.., ..].sum f64 (row-strided, in place)", (NS // 2) * 8, lambda: v_rows.sum(), reps=10)
+row("view reduce narr[0..2.., ..].max f64 (row-strided, in place)", (NS // 2) * 8, lambda: v_rows.max(), reps=10)
+v_rev = src.view().reverse()
+row("view reduce view.reverse.max(axis: 1) f64 (reversed rows, in place)", NS * 8 + S * 8, lambda: v_rev.max(axis=1), reps=10)
+row("view reduce view.reverse.sum(axis: 0) f64 (reversed rows, in place)", NS * 8 + S * 8, lambda: v_rev.sum(axis=0), reps=10)
+row("view reduce view.reverse.argmax(axis: 1) f64 (reversed rows, in place)", NS * 8 + S * 8, lambda: v_rev.argmax(axis=1), reps=10)
+del v_rows, v_rev
+# ---- a 2-D matrix folded down its columns has FEW columns (16384): the cp.async-staged strip kernel
+#      (PH_AXIS_STAGED=0 restores one thread per column); long rows: the one-pass row kernel
+for name in ["sum", "max", "argmax"]:
+    row(f"reduce axis=0 {name} f64 [{S},{S}] (few columns: staged strips)", NS * 8 + S * 8, lambda name=name: getattr(src, name)(axis=0), reps=10)
+for name in ["sum", "max", "argmax"]:
+    row(f"reduce axis=1 {name} f64 [{S},{S}] (128 KiB rows)", NS * 8 + S * 8, lambda name=name: getattr(src, name)(axis=1), reps=10)
 # ---- f-2: each_slice on a rank-3 view of the same buffer (one gather launch per slice)
 cube = D([64, S // 64 * S // 1024, 1024], np.float64, src._buf) if S % 64 == 0 else None
 if cube is not None:

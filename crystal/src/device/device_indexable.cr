@@ -343,12 +343,16 @@ module Phase
     # ---- reductions: Enumerable's folds, one launch each ------------------------------------------
     private def reduce_full(red : LibPhGpu::Red) : {T, Int64}
       raise Enumerable::EmptyError.new if size == 0
-      value = uninitialized T
+      # record mode (the sharded entry on one process exchanges nothing): one launch, the finishing block writes
+      # value, index and the pending flags into a pinned host record -- no copy, no second read for the flags
+      cell = StaticArray(UInt64, 2).new(0_u64)
       index = -1_i64
+      flags = 0_u32
       a = desc
-      Device.check LibPhGpu.ph_reduce_full(red.value, Device.dtype(T), dev.ptr, pointerof(a), pointerof(value).as(Void*), pointerof(index))
-      Device.raise_pending
-      {value, index}
+      Device.check LibPhGpu.ph_reduce_full_sharded(red.value, Device.dtype(T), dev.ptr, pointerof(a), 0_i64,
+        cell.to_unsafe.as(Void*), pointerof(index), pointerof(flags))
+      Device.raise_for(flags)
+      {cell.to_unsafe.as(T*).value, index}
     end
 
     def sum : T

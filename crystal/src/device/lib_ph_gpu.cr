@@ -175,6 +175,7 @@ lib LibPhGpu
   fun ph_allreduce(red : Int32, dtype : Int32, buf_dev : Void*, count : Int64) : Int32
   fun ph_allgather(send_dev : Void*, recv_dev : Void*, nbytes_per_rank : Int64) : Int32
   fun ph_alltoallv(send_dev : Void**, send_bytes : Int64*, recv_dev : Void**, recv_bytes : Int64*) : Int32
+  fun ph_alltoall_strided(elem_size : Int32, src_dev : Void*, src_descs : Desc*, dst_symm : Void*, dst_descs : Desc*) : Int32
   fun ph_halo_exchange(send_lo : Void*, recv_lo : Void*, lo_rank : Int32, send_hi : Void*, recv_hi : Void*,
                        hi_rank : Int32, nbytes : Int64, cuda_stream : Void*) : Int32
   fun ph_heat_run_sharded(dtype : Int32, rank : Int32, local_extents : Int64*, coeff_host : Void*,

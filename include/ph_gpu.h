@@ -299,7 +299,11 @@ int32_t ph_symm_peer(const void* local_dev, int32_t peer_rank, void** out_peer_d
  * `out_flags` receives the arithmetic flags of every rank, read and cleared (PH_FLAG_*).
  * One kernel launch per rank and one synchronisation: the last block stores the rank's partial into every
  * peer's slot over NVLink and folds the N slots in rank order (deterministic); NCCL allgather of the
- * records + a second tiny launch when peers are not mapped (or PH_REDUCE_NCCL=1). */
+ * records + a second tiny launch when peers are not mapped (or PH_REDUCE_NCCL=1).
+ * WITHOUT a communicator (ph_comm_init never called) this is the single-process full reduction in "record
+ * mode": one launch, the finishing block writes value / index / flags into a pinned host record the call
+ * polls -- no device-to-host copy, no stream synchronisation, no second read for the flags.  The host layers
+ * use it for every `sum` / `min` / `max` / argmax (ph_reduce_full + ph_d2h_flags is the two-read form). */
 int32_t ph_reduce_full_sharded(int32_t red, int32_t dtype, const void* a, const ph_desc* a_desc,
                                int64_t elems_before, void* out_value_host, int64_t* out_index_host,
                                uint32_t* out_flags);
@@ -310,6 +314,15 @@ int32_t ph_allgather(const void* send_dev, void* recv_dev, int64_t nbytes_per_ra
  * rank p; byte counts may be 0.  No reference counterpart (ph-core is single-process): SURVEY.md 8(f) f-3. */
 int32_t ph_alltoallv(const void* const* send_dev, const int64_t* send_bytes,
                      void* const* recv_dev, const int64_t* recv_bytes);
+/* The same exchange as ONE pass of peer stores (needs ph_comm_p2p_ready): block q of `src_dev` -- src_descs[q],
+ * a strided view already in the DESTINATION's axis order -- is copied by the gather / transpose kernels straight
+ * into rank q's copy of the symmetric block `dst_symm` (from ph_symm_alloc, same call order on every rank) at
+ * dst_descs[q] (element offsets relative to dst_symm).  The permuting copy is the transfer: no staging buffers,
+ * no ncclSend/ncclRecv, no scatter.  COLLECTIVE; stream-ordered (returns without blocking the host): two flag
+ * rounds over the peer-mapped control blocks bracket the copies.  Blocks with no elements are skipped.
+ * PH_ERR_UNSUPPORTED when peers are not mapped -- the caller falls back to ph_alltoallv. */
+int32_t ph_alltoall_strided(int32_t elem_size, const void* src_dev, const ph_desc* src_descs,
+                            void* dst_symm, const ph_desc* dst_descs);
 /* exchange one plane with each neighbour rank (lo = rank-1, hi = rank+1; -1 = none):
  * sends send_lo -> lo, send_hi -> hi; receives recv_lo <- lo, recv_hi <- hi. */
 int32_t ph_halo_exchange(const void* send_lo, void* recv_lo, int32_t lo_rank,

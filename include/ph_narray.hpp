@@ -35,6 +35,7 @@
 #include <string>
 #include <type_traits>
 #include <utility>
+#include <cstring>
 #include <vector>
 
 #include "ph_gpu.h"
@@ -191,12 +192,23 @@ class DeviceBuffer {
   // never frees; the parent releases the whole allocation when the last range dies.
   DeviceBuffer(std::shared_ptr<DeviceBuffer> parent, size_t byte_offset, size_t n)
       : ptr(static_cast<char*>(parent->ptr) + byte_offset), nbytes(n), parent_(std::move(parent)) {}
-  ~DeviceBuffer() { if (ptr && !parent_) ph_free(ptr); }
+  // Storage this layer does not release (peer-mapped blocks from ph_symm_alloc, whose release is collective:
+  // ph_symm_free on every rank, or ph_comm_destroy)
+  static std::shared_ptr<DeviceBuffer> adopt(void* external, size_t n) {
+    std::shared_ptr<DeviceBuffer> b(new DeviceBuffer());
+    b->ptr = external;
+    b->nbytes = n;
+    b->adopted_ = true;
+    return b;
+  }
+  ~DeviceBuffer() { if (ptr && !parent_ && !adopted_) ph_free(ptr); }
   DeviceBuffer(const DeviceBuffer&) = delete;
   DeviceBuffer& operator=(const DeviceBuffer&) = delete;
 
  private:
+  DeviceBuffer() = default;
   std::shared_ptr<DeviceBuffer> parent_;
+  bool adopted_ = false;
 };
 
 template <class T> class DeviceNArray;
@@ -429,8 +441,13 @@ class MultiIndexable {
     if (size() == 0) throw EmptyError("Empty enumerable");
     T val{};
     int64_t idx = -1;
-    Device::check(ph_reduce_full(red, DType<T>::value, buf_->ptr, &desc_, &val, &idx));
-    Device::raise_pending();
+    // record mode (the sharded entry on one process exchanges nothing): one launch, the finishing block writes
+    // value, index and the pending flags into a pinned host record -- no copy, no second read for the flags
+    alignas(16) unsigned char cell[16] = {0};
+    uint32_t flags = 0;
+    Device::check(ph_reduce_full_sharded(red, DType<T>::value, buf_->ptr, &desc_, 0, cell, &idx, &flags));
+    Device::raise_for(flags);
+    std::memcpy(&val, cell, sizeof(T));
     return {val, idx};
   }
   template <class R> DeviceNArray<R> reduce_axis(int32_t red, int32_t axis) const;

@@ -164,6 +164,7 @@ def load() -> C.CDLL:
         "ph_symm_peer": [vp, i32, C.POINTER(vp)],
         "ph_reduce_full_sharded": [i32, i32, vp, dp, i64, vp, C.POINTER(i64), C.POINTER(C.c_uint32)],
         "ph_alltoallv": [C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), C.POINTER(i64)],
+        "ph_alltoall_strided": [i32, vp, dp, vp, dp],
         "ph_halo_exchange": [vp, vp, i32, vp, vp, i32, i64, vp],
         "ph_heat_run_sharded": [i32, i32, C.POINTER(i64), vp, i32, vp, vp, i64, C.POINTER(i32)],
     }

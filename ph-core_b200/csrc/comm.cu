@@ -236,17 +236,18 @@ static int32_t p2p_setup() {
 int32_t comm_combine_args(CombineArgs* out, int64_t elems_before) {
   Comm& c = cm();
   PeerInfo& p = peers();
-  if (!c.inited) return set_error(PH_ERR_NOT_INIT, "ph_comm_init was not called");
+  // no communicator: a single process with one GPU -- the record mode of the reduction kernels (result and
+  // flags in the pinned host record, no copy, no stream synchronisation) works on its own
   int32_t st = ensure_exchange_buffers();
   if (st != PH_OK) return st;
   CombineArgs a;
-  a.nranks = c.nranks;
-  a.rank = c.rank;
+  a.nranks = c.inited ? c.nranks : 1;
+  a.rank = c.inited ? c.rank : 0;
   a.seq = ++p.reduce_seq;
   a.elems_before = elems_before;
   a.host_out = p.host_result_dev;
   static const bool force_nccl = getenv("PH_REDUCE_NCCL") != nullptr;       // A/B knob: NCCL transport of the records
-  if (c.nranks > 1) {
+  if (a.nranks > 1) {
     if (p.ready && !force_nccl) {
       const int parity = (int)(a.seq & 1u);
       a.my_slots = &p.ctrl[c.rank]->slot[parity][0];
@@ -384,6 +385,12 @@ int32_t ph_comm_init(int32_t nranks, int32_t rank, const uint8_t* id128) {
   PH_REQUIRE_INIT();
   Comm& c = cm();
   if (c.inited) ph_comm_destroy();
+  else {                        // single-process record-mode reductions may have run: call numbers restart at 0 on every rank
+    cudaDeviceSynchronize();
+    PeerInfo& p = peers();
+    p.reduce_seq = 0;
+    if (p.host_result) memset(p.host_result, 0, 64);
+  }
   if (nranks < 1 || rank < 0 || rank >= nranks) return set_error(PH_ERR_INVALID, "bad rank %d of %d", rank, nranks);
   c.nranks = nranks; c.rank = rank;
   if (nranks == 1) { c.inited = true; c.comm = nullptr; return p2p_setup(); }
@@ -518,6 +525,68 @@ int32_t ph_alltoallv(const void* const* send_dev, const int64_t* send_bytes, voi
   }
   PH_NCCL(nccl().GroupEnd());
   return PH_OK;
+}
+
+// Personalised all-to-all of STRIDED blocks as peer stores: the exchange step of a transpose across axis-0
+// shards in ONE pass -- for every peer q the block this rank owes it (src_descs[q]: a view of the rank's rows,
+// already in the destination's axis order) is copied by the ordinary gather / transpose kernels straight into
+// rank q's result through the peer mapping (dst_descs[q], relative to q's copy of the symmetric block): the
+// permuting copy IS the transfer.  No staging buffer, no ncclSend/ncclRecv, no scatter afterwards.  Peers are
+// visited in the order rank+1, rank+2, ... so every phase is a permutation (no receiver takes N streams at once).
+// Two flag rounds bracket the copies: "my destination may be overwritten" before, "my stores have landed" after
+// (stream-ordered; the host does not block).
+struct PeerFlagPtrs {
+  uint32_t* p[PH_MAX_PEERS];
+};
+static __global__ void xchg_signal_kernel(PeerFlagPtrs f, int n, uint32_t event) {
+  __threadfence_system();                       // the copies launched before this kernel have completed (stream order)
+  if ((int)threadIdx.x < n && f.p[threadIdx.x]) st_release_sys(f.p[threadIdx.x], event);
+}
+static __global__ void xchg_wait_kernel(const volatile uint32_t* flags, int n, uint32_t event, uint32_t* err_flags) {
+  if ((int)threadIdx.x < n) {
+    const long long t0 = clock64();
+    while ((int32_t)(flags[threadIdx.x] - event) < 0) {
+      if (clock64() - t0 > 20000000000LL) { atomicOr(err_flags + 1, 1u); break; }   // ~10 s: a peer died
+    }
+  }
+  __threadfence_system();
+}
+static int32_t xchg_round(int which, uint32_t event) {
+  Comm& c = cm();
+  PeerInfo& p = peers();
+  Runtime& r = rt();
+  PeerFlagPtrs f;
+  for (int q = 0; q < PH_MAX_PEERS; q++) f.p[q] = q < c.nranks ? &p.ctrl[q]->xchg_flag[which][c.rank] : nullptr;
+  xchg_signal_kernel<<<1, 32, 0, r.stream>>>(f, c.nranks, event);
+  PH_LAUNCH_CHECK("xchg_signal_kernel");
+  xchg_wait_kernel<<<1, 32, 0, r.stream>>>(&p.ctrl[c.rank]->xchg_flag[which][0], c.nranks, event, r.d_flags);
+  PH_LAUNCH_CHECK("xchg_wait_kernel");
+  return PH_OK;
+}
+
+int32_t ph_alltoall_strided(int32_t elem_size, const void* src_dev, const ph_desc* src_descs, void* dst_symm,
+                            const ph_desc* dst_descs) {
+  PH_REQUIRE_INIT();
+  Comm& c = cm();
+  PeerInfo& p = peers();
+  if (!c.inited) return set_error(PH_ERR_NOT_INIT, "ph_comm_init was not called");
+  if (!src_dev || !src_descs || !dst_symm || !dst_descs) return set_error(PH_ERR_INVALID, "null argument to ph_alltoall_strided");
+  auto elems = [](const ph_desc& d) { int64_t n = 1; for (int i = 0; i < d.rank; i++) n *= d.extent[i]; return n; };
+  if (c.nranks == 1) return elems(src_descs[0]) ? ph_copy_strided(elem_size, src_dev, &src_descs[0], dst_symm, &dst_descs[0]) : PH_OK;
+  if (!p.ready) return set_error(PH_ERR_UNSUPPORTED, "peers are not mapped (no P2P): use ph_alltoallv");
+  const SymmAlloc* sa = symm_find(dst_symm);
+  if (!sa || !sa->mapped) return set_error(PH_ERR_INVALID, "ph_alltoall_strided: the destination must come from ph_symm_alloc");
+  const ptrdiff_t rel = reinterpret_cast<const char*>(dst_symm) - sa->local;
+  const uint32_t event = ++p.xchg_event;
+  int32_t st = xchg_round(0, event);            // every rank has finished whatever read its destination before
+  if (st != PH_OK) return st;
+  for (int i = 0; i < c.nranks; i++) {
+    const int q = (c.rank + i) % c.nranks;
+    if (elems(src_descs[q]) == 0) continue;
+    void* dst = q == c.rank ? dst_symm : (void*)(sa->peer[q] + rel);
+    if ((st = ph_copy_strided(elem_size, src_dev, &src_descs[q], dst, &dst_descs[q])) != PH_OK) return st;
+  }
+  return xchg_round(1, event);                  // every block destined for me has landed
 }
 
 int32_t ph_halo_exchange(const void* send_lo, void* recv_lo, int32_t lo_rank, const void* send_hi,

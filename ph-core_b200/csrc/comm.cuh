@@ -31,6 +31,8 @@ struct ReduceResult {
   int64_t index;       // arg*: global flat index of the FIRST extremum; INT64_MAX when every shard is empty
   int32_t status;      // PH_RED_*
   uint32_t flags;      // arithmetic flags of every rank, read-and-cleared
+  uint32_t seq;        // written LAST (after a system fence): the call number -- the host polls this word
+  uint32_t _pad;
 };
 enum { PH_RED_OK = 0, PH_RED_OVERFLOW = 1, PH_RED_NEED_EXACT = 2, PH_RED_EMPTY = 3, PH_RED_TIMEOUT = 4 };
 
@@ -51,6 +53,9 @@ struct CtrlBlock {
   alignas(128) uint32_t halo_flag[2];        // last halo event my LO ([0]) / HI ([1]) neighbour completed (written by THEM)
   alignas(128) uint32_t halo_ticket[4];      // local: [0]/[1] edge blocks of the running stencil pass that finished, per side; [2] push kernel
   alignas(128) int64_t nbr_planes[2];        // local plane count (ghosts included) of my LO / HI neighbour's slab
+  // strided all-to-all (ph_alltoall_strided): [0][r] rank r is ready for exchange e (its destination may be
+  // overwritten), [1][r] rank r's stores of exchange e into MY memory have landed -- each written by rank r
+  alignas(128) uint32_t xchg_flag[2][PH_MAX_PEERS];
 };
 
 // What the two-steps-per-pass stencil kernel needs to deliver the halo itself (heat_tma.cu): output planes
@@ -77,6 +82,7 @@ struct PeerInfo {
   ReduceResult* host_result_dev = nullptr;        // its device address
   uint32_t reduce_seq = 0;
   uint32_t halo_event = 0;                        // last halo event number this rank issued
+  uint32_t xchg_event = 0;                        // last strided all-to-all this rank issued (collective: same on every rank)
 };
 PeerInfo& peers();
 

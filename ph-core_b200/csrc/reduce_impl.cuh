@@ -21,10 +21,26 @@
 #include "ops.cuh"
 #include "comm.cuh"
 #include <limits>
+#include <atomic>
 
 namespace ph {
 
 constexpr int RED_THREADS = 256;
+
+// Full reductions over a ROW-STRIDED view (`narr[0..2.., ..]`, a column block of a matrix, ...): logical
+// element i = (row, col) lives at x[row * row_stride + col].  When the row length is a whole number of
+// tiles every tile lies inside one row, so the kernels only re-base a tile: one 32-bit division per tile
+// (tiles_per_row == 0: the plain contiguous array, no division).  The view is read in place -- no gather,
+// no temporary: algorithmic bytes = the bytes of the view.
+struct RowsArgs {
+  uint32_t tiles_per_row = 0;
+  int64_t row_stride = 0;
+};
+__device__ __forceinline__ int64_t tile_base(const RowsArgs& r, int64_t t, int64_t tile) {
+  if (r.tiles_per_row == 0) return t * tile;
+  const uint32_t row = (uint32_t)t / r.tiles_per_row;
+  return (int64_t)row * r.row_stride + (int64_t)((uint32_t)t - row * r.tiles_per_row) * tile;
+}
 
 // ---------------------------------------------------------------- helpers
 template <typename T> struct Acc { using type = T; };             // sum accumulator
@@ -159,7 +175,8 @@ __device__ __forceinline__ bool exchange_records(const CombineArgs& c, const Red
 
 template <typename T> __device__ __forceinline__ void sum_finish(typename Acc<T>::type fs, typename Acc<T>::type fp,
                                                                   typename Acc<T>::type fn, uint32_t fl, bool ok,
-                                                                  T* out_value, int* status, ReduceResult* host_out) {
+                                                                  T* out_value, int* status, ReduceResult* host_out,
+                                                                  uint32_t seq) {
   using A = typename Acc<T>::type;
   int st = PH_RED_OK;
   if constexpr (!is_float_t<T>::value) {
@@ -179,12 +196,13 @@ template <typename T> __device__ __forceinline__ void sum_finish(typename Acc<T>
     host_out->flags = fl;
     host_out->status = st;
     __threadfence_system();
+    *reinterpret_cast<volatile uint32_t*>(&host_out->seq) = seq;      // the host is polling this word
   }
 }
 
 // fold of the N sum records in rank order (thread 0)
 template <typename T> __device__ __forceinline__ void sum_fold_records(const ReduceSlot* rec, int nranks, bool ok, T* out_value,
-                                                                        int* status, ReduceResult* host_out) {
+                                                                        int* status, ReduceResult* host_out, uint32_t seq) {
   using A = typename Acc<T>::type;
   A fs = 0, fp = 0, fn = 0;
   uint32_t fl = 0;
@@ -193,11 +211,11 @@ template <typename T> __device__ __forceinline__ void sum_fold_records(const Red
     else { fs += unpack_wide<A>(rec[r].w); fp += unpack_wide<A>(rec[r].w + 2); fn += unpack_wide<A>(rec[r].w + 4); }
     fl |= (uint32_t)rec[r].w[7];
   }
-  sum_finish<T>(fs, fp, fn, fl, ok, out_value, status, host_out);
+  sum_finish<T>(fs, fp, fn, fl, ok, out_value, status, host_out, seq);
 }
 
 template <typename T> __device__ __forceinline__ void ext_finish(Cand<T> fin, uint32_t fl, bool ok, T* out_value,
-                                                                  int64_t* out_index, ReduceResult* host_out) {
+                                                                  int64_t* out_index, ReduceResult* host_out, uint32_t seq) {
   if (out_value) *out_value = fin.v;
   if (out_index) *out_index = fin.i;
   if (host_out) {
@@ -208,12 +226,13 @@ template <typename T> __device__ __forceinline__ void ext_finish(Cand<T> fin, ui
     host_out->flags = fl;
     host_out->status = !ok ? PH_RED_TIMEOUT : (fin.i == INT64_MAX ? PH_RED_EMPTY : PH_RED_OK);
     __threadfence_system();
+    *reinterpret_cast<volatile uint32_t*>(&host_out->seq) = seq;
   }
 }
 
 template <typename T, bool IS_MAX> __device__ __forceinline__ void ext_fold_records(const ReduceSlot* rec, int nranks, bool ok,
                                                                                     T* out_value, int64_t* out_index,
-                                                                                    ReduceResult* host_out) {
+                                                                                    ReduceResult* host_out, uint32_t seq) {
   Cand<T> fin;
   fin.v = IS_MAX ? lowest_of<T>() : highest_of<T>();
   fin.i = INT64_MAX;
@@ -225,17 +244,17 @@ template <typename T, bool IS_MAX> __device__ __forceinline__ void ext_fold_reco
     if (c.i != INT64_MAX) fin = better<T, IS_MAX>(fin, c);      // an empty shard contributes nothing
     fl |= (uint32_t)rec[r].w[7];
   }
-  ext_finish<T>(fin, fl, ok, out_value, out_index, host_out);
+  ext_finish<T>(fin, fl, ok, out_value, out_index, host_out, seq);
 }
 
 // NCCL transport of the same combine: the records were allgathered between the two launches
 template <typename T> __global__ void sum_combine_kernel(const ReduceSlot* rec, int nranks, T* out_value, int* status,
-                                                         ReduceResult* host_out) {
-  if (threadIdx.x == 0) sum_fold_records<T>(rec, nranks, true, out_value, status, host_out);
+                                                         ReduceResult* host_out, uint32_t seq) {
+  if (threadIdx.x == 0) sum_fold_records<T>(rec, nranks, true, out_value, status, host_out, seq);
 }
 template <typename T, bool IS_MAX> __global__ void ext_combine_kernel(const ReduceSlot* rec, int nranks, T* out_value,
-                                                                       int64_t* out_index, ReduceResult* host_out) {
-  if (threadIdx.x == 0) ext_fold_records<T, IS_MAX>(rec, nranks, true, out_value, out_index, host_out);
+                                                                       int64_t* out_index, ReduceResult* host_out, uint32_t seq) {
+  if (threadIdx.x == 0) ext_fold_records<T, IS_MAX>(rec, nranks, true, out_value, out_index, host_out, seq);
 }
 
 // ---------------------------------------------------------------- full sum (floats; ints: S, P, N)
@@ -253,7 +272,8 @@ __global__ void __launch_bounds__(RED_THREADS) sum_partial_kernel(const T* __res
                                                                   SumState<T>* __restrict__ partials,
                                                                   T* __restrict__ out_value, int* __restrict__ status,
                                                                   unsigned int* __restrict__ ticket,
-                                                                  uint32_t* __restrict__ flags, const CombineArgs cmb) {
+                                                                  uint32_t* __restrict__ flags, const CombineArgs cmb,
+                                                                  const RowsArgs rows) {
   using A = typename Acc<T>::type;
   constexpr bool IS_INT = !is_float_t<T>::value;
   constexpr int UNROLL = 4;
@@ -264,7 +284,7 @@ __global__ void __launch_bounds__(RED_THREADS) sum_partial_kernel(const T* __res
   const int64_t tile = (int64_t)RED_THREADS * E * UNROLL;
   const int64_t ntiles = n / tile;
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int64_t base = t * tile + (int64_t)threadIdx.x * E;
+    const int64_t base = tile_base(rows, t, tile) + (int64_t)threadIdx.x * E;
     Group<T, E> g[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; u++) g[u] = load_group<T, E>(x + base + (int64_t)u * RED_THREADS * E);
@@ -352,11 +372,11 @@ __global__ void __launch_bounds__(RED_THREADS) sum_partial_kernel(const T* __res
       return;
     }
     const bool ok = exchange_records(cmb, mine, sh_rec);
-    if (threadIdx.x == 0) sum_fold_records<T>(sh_rec, cmb.nranks, ok, out_value, status, cmb.host_out);
+    if (threadIdx.x == 0) sum_fold_records<T>(sh_rec, cmb.nranks, ok, out_value, status, cmb.host_out, cmb.seq);
     return;
   }
   if (threadIdx.x == 0)
-    sum_finish<T>(fs, fp, fn, cmb.host_out ? atomicExch(flags, 0u) : 0u, true, out_value, status, cmb.host_out);
+    sum_finish<T>(fs, fp, fn, cmb.host_out ? atomicExch(flags, 0u) : 0u, true, out_value, status, cmb.host_out, cmb.seq);
 }
 
 // Exact ordered pass for integer sums: monoid (sum, max prefix, min prefix) combined in lex order.
@@ -484,7 +504,8 @@ __global__ void __launch_bounds__(RED_THREADS) ext_partial_kernel(const T* __res
                                                                   uint32_t* __restrict__ flags,
                                                                   T* __restrict__ out_value,
                                                                   int64_t* __restrict__ out_index,
-                                                                  unsigned int* __restrict__ ticket, const CombineArgs cmb) {
+                                                                  unsigned int* __restrict__ ticket, const CombineArgs cmb,
+                                                                  const RowsArgs rows) {
   constexpr int UNROLL = 4;
   T best_v = IS_MAX ? lowest_of<T>() : highest_of<T>();
   int64_t best_t = -1;
@@ -492,7 +513,7 @@ __global__ void __launch_bounds__(RED_THREADS) ext_partial_kernel(const T* __res
   const int64_t tile = (int64_t)RED_THREADS * E * UNROLL;
   const int64_t ntiles = n / tile;
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int64_t base = t * tile + (int64_t)threadIdx.x * E;
+    const int64_t base = tile_base(rows, t, tile) + (int64_t)threadIdx.x * E;
     Group<T, E> g[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; u++) g[u] = load_group<T, E>(x + base + (int64_t)u * RED_THREADS * E);
@@ -511,7 +532,8 @@ __global__ void __launch_bounds__(RED_THREADS) ext_partial_kernel(const T* __res
   best.v = best_v;
   best.i = INT64_MAX;
   if (best_t >= 0) {                                 // first register of the winning tile holding the extremum
-    const int64_t base = best_t * tile + (int64_t)threadIdx.x * E;
+    const int64_t base = tile_base(rows, best_t, tile) + (int64_t)threadIdx.x * E;      // where the tile lives
+    const int64_t lbase = best_t * tile + (int64_t)threadIdx.x * E;                     // its LOGICAL (lex) index
     bool found = false;
 #pragma unroll
     for (int u = 0; u < UNROLL; u++) {
@@ -521,7 +543,7 @@ __global__ void __launch_bounds__(RED_THREADS) ext_partial_kernel(const T* __res
         if (!found && g.v[i] == best_v) {
           found = true;
           best.v = g.v[i];                           // the element itself (keeps the sign of a zero)
-          best.i = base + (int64_t)u * RED_THREADS * E + i;
+          best.i = lbase + (int64_t)u * RED_THREADS * E + i;
         }
     }
   }
@@ -587,10 +609,10 @@ __global__ void __launch_bounds__(RED_THREADS) ext_partial_kernel(const T* __res
       return;
     }
     const bool ok = exchange_records(cmb, mine, sh_rec);
-    if (threadIdx.x == 0) ext_fold_records<T, IS_MAX>(sh_rec, cmb.nranks, ok, out_value, out_index, cmb.host_out);
+    if (threadIdx.x == 0) ext_fold_records<T, IS_MAX>(sh_rec, cmb.nranks, ok, out_value, out_index, cmb.host_out, cmb.seq);
     return;
   }
-  if (threadIdx.x == 0) ext_finish<T>(fin, cmb.host_out ? atomicExch(flags, 0u) : 0u, true, out_value, out_index, cmb.host_out);
+  if (threadIdx.x == 0) ext_finish<T>(fin, cmb.host_out ? atomicExch(flags, 0u) : 0u, true, out_value, out_index, cmb.host_out, cmb.seq);
 }
 
 // ---------------------------------------------------------------- per-axis: [outer, K, inner]
@@ -599,19 +621,32 @@ __global__ void __launch_bounds__(RED_THREADS) ext_partial_kernel(const T* __res
 template <typename T, int E, int RED, int UNROLL>
 __global__ void __launch_bounds__(RED_THREADS) axis_strip_kernel(const T* __restrict__ x, void* __restrict__ out,
                                                                  int64_t outer, int64_t K, int64_t inner,
+                                                                 int64_t ostride, int64_t kstride, int irev,
                                                                  uint32_t* __restrict__ flags) {
+  // element (o, k, c) lives at x[o * ostride + k * kstride + c]: a contiguous array has ostride = K * inner and
+  // kstride = inner; a row-strided or reversed-outer view only changes the two strides (read in place).
+  // irev: the inner axis runs BACKWARDS in memory (x[... - c]): a thread's group of logical columns c .. c+E-1
+  // is the memory group ending at -c, loaded whole and reversed in registers (free: the loop is unrolled)
   const int64_t groups = inner / E;                         // inner % E == 0 by dispatch
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= outer * groups) return;
   const int64_t o = gid / groups;
   const int64_t c = (gid - o * groups) * E;
-  const T* p = x + o * K * inner + c;
+  const T* p = x + o * ostride + (irev ? -(c + E - 1) : c);
+  auto load = [&](const T* q) {
+    Group<T, E> g = load_group<T, E>(q);
+    if (irev) {
+#pragma unroll
+      for (int i = 0; i < E / 2; i++) { const T t = g.v[i]; g.v[i] = g.v[E - 1 - i]; g.v[E - 1 - i] = t; }
+    }
+    return g;
+  };
   uint32_t err = 0;
   bool nan = false;
   T acc[E];
   int32_t arg[E];                                           // an axis extent always fits Int32
 #pragma unroll
-  for (int i = 0; i < E; i++) { acc[i] = (RED == PH_SUM) ? (T)0 : p[i]; arg[i] = 0; }
+  for (int i = 0; i < E; i++) { acc[i] = (RED == PH_SUM) ? (T)0 : p[irev ? E - 1 - i : i]; arg[i] = 0; }
   int64_t k = (RED == PH_SUM) ? 0 : 1;
   if constexpr (RED != PH_SUM && is_float_t<T>::value) {
 #pragma unroll
@@ -634,11 +669,11 @@ __global__ void __launch_bounds__(RED_THREADS) axis_strip_kernel(const T* __rest
   for (; k + UNROLL <= K; k += UNROLL) {
     Group<T, E> g[UNROLL];
 #pragma unroll
-    for (int u = 0; u < UNROLL; u++) g[u] = load_group<T, E>(p + (k + u) * inner);
+    for (int u = 0; u < UNROLL; u++) g[u] = load(p + (k + u) * kstride);
 #pragma unroll
     for (int u = 0; u < UNROLL; u++) fold(g[u], (int32_t)(k + u));
   }
-  for (; k < K; k++) fold(load_group<T, E>(p + k * inner), (int32_t)k);
+  for (; k < K; k++) fold(load(p + k * kstride), (int32_t)k);
   if constexpr (RED == PH_ARGMAX || RED == PH_ARGMIN) {
     int64_t* q = reinterpret_cast<int64_t*>(out) + o * inner + c;
 #pragma unroll
@@ -653,30 +688,133 @@ __global__ void __launch_bounds__(RED_THREADS) axis_strip_kernel(const T* __rest
   if (nan) atomicOr(flags, (uint32_t)PH_FLAG_NAN);
 }
 
+// ---- the same ordered fold for FEW columns (a [16384, 16384] matrix folded down axis 0 has 16 384 columns: one
+// thread per column leaves ~110 threads per SM, 14 KB in flight, 1.3 TB/s however deep the unrolling; and K
+// cannot be split across threads without changing the association order of a float sum).  Bytes in flight are
+// decoupled from the thread count instead: a block is ONE warp that owns a strip of 32 columns for the whole
+// of K and streams it through a ring of STAGES shared-memory tiles of KT rows with 16-byte `cp.async` copies
+// (LDGSTS, L1 bypassed), STAGES-1 tiles ahead of the fold; lane c then folds column c of each tile in k order
+// from shared memory (conflict-free).  No __syncthreads: cp.async.wait_group + __syncwarp.  Strides may be
+// negative (reversed views); rows of a strip must be 16-byte aligned (dispatch).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename T, int RED, int KT, int STAGES>
+__global__ void __launch_bounds__(32) axis_strip_staged_kernel(const T* __restrict__ x, void* __restrict__ out,
+                                                               int64_t K, int64_t inner, int64_t ostride, int64_t kstride,
+                                                               int irev, int strips_per_outer, uint32_t* __restrict__ flags) {
+  constexpr int CW = 32;                                    // columns per strip: one lane each
+  constexpr int EPC = 16 / (int)sizeof(T);                  // elements per 16-byte chunk
+  constexpr int CPR = CW / EPC;                             // chunks per tile row
+  constexpr int CPL = KT * CPR / 32;                        // chunks per lane per tile
+  static_assert((KT * CPR) % 32 == 0, "a tile is a whole number of chunks per lane");
+  __shared__ __align__(16) T ring[STAGES][KT][CW];
+  const int lane = threadIdx.x;
+  const int64_t o = blockIdx.x / strips_per_outer;
+  const int64_t c0 = (int64_t)(blockIdx.x - o * strips_per_outer) * CW;
+  const int ncols = (int)((inner - c0) < CW ? (inner - c0) : CW);      // a multiple of EPC (dispatch)
+  // irev: the inner axis runs backwards in memory; the strip's LOGICAL columns c0 .. c0+ncols-1 are the memory
+  // columns -(c0+ncols-1) .. -c0: the tile is copied in memory order and lane c reads tile column ncols-1-c
+  const T* base = x + o * ostride + (irev ? -(c0 + ncols - 1) : c0);
+  const int mycol = irev ? ncols - 1 - lane : lane;
+  const int ntiles = (int)((K + KT - 1) / KT);
+  // this lane's chunks of a tile: rows r0 + j * (32 / CPR), columns cc .. cc + EPC
+  const int r0 = lane / CPR, cc = (lane % CPR) * EPC;
+  const bool col_ok = cc < ncols;
+  const T* src0 = base + (int64_t)r0 * kstride + cc;
+  auto issue = [&](int t) {
+    const int slot = t % STAGES;
+    const int64_t k0 = (int64_t)t * KT;
+    if (col_ok) {
+#pragma unroll
+      for (int j = 0; j < CPL; j++) {
+        const int r = r0 + j * (32 / CPR);
+        if (k0 + r < K) cp_async16(&ring[slot][r][cc], src0 + (k0 + j * (32 / CPR)) * kstride);
+      }
+    }
+  };
+#pragma unroll
+  for (int t = 0; t < STAGES - 1; t++) {
+    if (t < ntiles) issue(t);
+    cp_async_commit();
+  }
+  T acc = (RED == PH_SUM) ? (T)0 : ((RED == PH_MAX || RED == PH_ARGMAX) ? lowest_of<T>() : highest_of<T>());
+  int32_t arg = 0;
+  uint32_t err = 0;
+  bool nan = false;
+  const bool act = lane < ncols;
+  auto fold = [&](T v, int32_t kk) {
+    if constexpr (RED == PH_SUM) {
+      if constexpr (is_float_t<T>::value) acc = f_add(acc, v);
+      else acc = i_add<T>(acc, v, true, err);
+    } else {
+      if constexpr (is_float_t<T>::value) nan |= (v != v);
+      const bool take = (RED == PH_MAX || RED == PH_ARGMAX) ? (v > acc) : (v < acc);
+      if (take) { acc = v; arg = kk; }
+    }
+  };
+  for (int t = 0; t < ntiles; t++) {
+    if (t + STAGES - 1 < ntiles) issue(t + STAGES - 1);     // into the slot folded in the previous iteration
+    cp_async_commit();
+    cp_async_wait<STAGES - 1>();                            // tile t has landed (this lane's chunks) ...
+    __syncwarp();                                           // ... and every other lane's
+    const int slot = t % STAGES;
+    const int64_t k0 = (int64_t)t * KT;
+    if (act) {
+      if (k0 + KT <= K) {
+#pragma unroll
+        for (int r = 0; r < KT; r++) fold(ring[slot][r][mycol], (int32_t)(k0 + r));
+      } else {
+        for (int r = 0; k0 + r < K; r++) fold(ring[slot][r][mycol], (int32_t)(k0 + r));
+      }
+    }
+    __syncwarp();                                           // the slot may be refilled
+  }
+  if (act) {
+    if constexpr (RED == PH_ARGMAX || RED == PH_ARGMIN) reinterpret_cast<int64_t*>(out)[o * inner + c0 + lane] = (int64_t)arg;
+    else reinterpret_cast<T*>(out)[o * inner + c0 + lane] = acc;
+  }
+  if (err) atomicOr(flags, err);
+  if (nan) atomicOr(flags, (uint32_t)PH_FLAG_NAN);
+}
+
 // inner == 1: each row of K contiguous elements is reduced by TX cooperating threads (TX a
-// power of two; <= 32 combines with shuffles, larger through shared memory).  Lanes read
-// consecutive 32-byte groups (E elements), UNROLL groups in flight per lane.
-// min/max/arg*: pass 1 finds the row extremum M (one max.NaN per element for f32); the index of
-// its FIRST occurrence -- needed for arg*, and for max/min only when M is a zero whose sign
-// depends on which zero came first -- is found by a second pass over the L1/L2-resident row.
+// power of two; <= 32: lanes of one warp, several rows per warp; larger: TX / 32 whole warps).  Lanes read
+// consecutive 32-byte groups (E elements), UNROLL groups in flight per lane; lanes combine by a shuffle tree,
+// warps through one shared-memory word each (a serial fold of TX shared-memory words by one lane cost a
+// 128 KB row ~4 us of single-thread work: 5.0 TB/s; the tree form streams at the copy peak).
+// min/max/arg*: ONE pass.  The loop keeps the running extremum and the BATCH (first group + group count)
+// that gave it -- the first such batch in the view's order (a reversed view takes the later physical batch
+// on ties) -- exactly like the full reduction keeps a tile number; after the row extremum M is known, only
+// lanes holding M re-read their own winning batch (<= 128 bytes) for the first logical index.  That index is
+// needed for arg*, and for max/min only when M is a zero (its sign depends on which zero came first).
 template <typename T, int E, int RED>
 __global__ void __launch_bounds__(RED_THREADS) axis_row_kernel(const T* __restrict__ x, void* __restrict__ out,
-                                                               int64_t rows, int64_t K, int tx, int tx_log2,
-                                                               uint32_t* __restrict__ flags) {
+                                                               int64_t rows, int64_t K, int64_t rstride, int rev,
+                                                               int tx, int tx_log2, uint32_t* __restrict__ flags) {
+  // row r occupies x[r * rstride .. + K) in memory; rev != 0: its LOGICAL element j is the physical K-1-j (a
+  // reversed view): values are order-free, only "first occurrence" is taken on the logical index
   constexpr bool IS_MAXLIKE = (RED == PH_MAX || RED == PH_ARGMAX);
   constexpr bool IS_ARG = (RED == PH_ARGMAX || RED == PH_ARGMIN);
   constexpr int UNROLL = 4;
+  constexpr int NWARPS = RED_THREADS / 32;
   using A = typename Acc<T>::type;
-  __shared__ A sh_s[RED_THREADS], sh_p[RED_THREADS], sh_n[RED_THREADS];
-  __shared__ T sh_m[RED_THREADS];
-  __shared__ int32_t sh_i[RED_THREADS];
+  __shared__ A sh_s[NWARPS], sh_p[NWARPS], sh_n[NWARPS];
+  __shared__ T sh_m[NWARPS];
+  __shared__ int32_t sh_i[NWARPS];
   const int lane = threadIdx.x & (tx - 1);
   const int ty = threadIdx.x >> tx_log2;
   const int TY = RED_THREADS >> tx_log2;
-  const int b0 = ty << tx_log2;
+  const int warp = threadIdx.x >> 5;
+  const int w0 = (ty << tx_log2) >> 5;           // first warp of this row (tx > 32)
+  const int wn = tx >> 5;                         // warps per row (tx > 32)
+  const int tree = tx < 32 ? tx : 32;             // shuffle-tree width
   const int64_t row = (int64_t)blockIdx.x * TY + ty;
   const bool live = row < rows;
-  const T* p = x + (live ? row : 0) * K;
+  const T* p = x + (live ? row : 0) * rstride;
   const int64_t groups = K / E;                   // K % E == 0 by dispatch (E == 1 otherwise)
   bool nan = false;
   uint32_t err = 0;
@@ -702,18 +840,17 @@ __global__ void __launch_bounds__(RED_THREADS) axis_row_kernel(const T* __restri
       }
       for (; g0 < groups; g0 += tx) fold(load_group<T, E>(p + g0 * E));
     }
-    if (tx <= 32) {
-      for (int off = tx >> 1; off > 0; off >>= 1) {
-        if constexpr (is_float_t<T>::value) s = f_add(s, shfl_xor_t<A>(s, off));
-        else { s += shfl_xor_t<A>(s, off); pos += shfl_xor_t<A>(pos, off); neg += shfl_xor_t<A>(neg, off); }
-      }
-    } else {
-      sh_s[threadIdx.x] = s; sh_p[threadIdx.x] = pos; sh_n[threadIdx.x] = neg;
+    for (int off = tree >> 1; off > 0; off >>= 1) {
+      if constexpr (is_float_t<T>::value) s = f_add(s, shfl_xor_t<A>(s, off));
+      else { s += shfl_xor_t<A>(s, off); pos += shfl_xor_t<A>(pos, off); neg += shfl_xor_t<A>(neg, off); }
+    }
+    if (tx > 32) {
+      if ((threadIdx.x & 31) == 0) { sh_s[warp] = s; sh_p[warp] = pos; sh_n[warp] = neg; }
       __syncthreads();
       if (lane == 0)
-        for (int j = 1; j < tx; j++) {
-          if constexpr (is_float_t<T>::value) s = f_add(s, sh_s[b0 + j]);
-          else { s += sh_s[b0 + j]; pos += sh_p[b0 + j]; neg += sh_n[b0 + j]; }
+        for (int j = 1; j < wn; j++) {
+          if constexpr (is_float_t<T>::value) s = f_add(s, sh_s[w0 + j]);
+          else { s += sh_s[w0 + j]; pos += sh_p[w0 + j]; neg += sh_n[w0 + j]; }
         }
     }
     if (lane == 0 && live) {
@@ -723,17 +860,20 @@ __global__ void __launch_bounds__(RED_THREADS) axis_row_kernel(const T* __restri
         const A hi = (A)std::numeric_limits<T>::max(), lo = (A)std::numeric_limits<T>::lowest();
         if (pos > hi || neg < lo) {
           A run = 0;
-          for (int64_t k = 0; k < K; k++) { run += (A)p[k]; if (run > hi || run < lo) { err |= PH_FLAG_OVERFLOW; break; } }
+          for (int64_t k = 0; k < K; k++) { run += (A)p[rev ? K - 1 - k : k]; if (run > hi || run < lo) { err |= PH_FLAG_OVERFLOW; break; } }
         }
       }
       reinterpret_cast<T*>(out)[row] = (T)s;
     }
   } else {
-    // ---- pass 1: row extremum
+    // ---- the lane's extremum and the batch that gave it
     T m = IS_MAXLIKE ? lowest_of<T>() : highest_of<T>();
-    auto fold = [&](const Group<T, E>& g) {
-#pragma unroll
-      for (int i = 0; i < E; i++) m = ext2<T, IS_MAXLIKE>(m, g.v[i], nan);
+    int64_t bg = -1;                              // first group of that batch (-1: nothing seen yet)
+    int bn = 0;                                   // groups in it (UNROLL, or 1 in the remainder loop)
+    auto consider = [&](T bm, int64_t g0, int n) {
+      if constexpr (std::is_same<T, float>::value) nan |= (bm != bm);
+      const bool improves = IS_MAXLIKE ? (bm > m) : (bm < m);
+      if (improves || (bm == m && (rev || bg < 0))) { m = bm; bg = g0; bn = n; }
     };
     if (live) {
       int64_t g0 = lane;
@@ -741,47 +881,62 @@ __global__ void __launch_bounds__(RED_THREADS) axis_row_kernel(const T* __restri
         Group<T, E> g[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) g[u] = load_group_plain<T, E>(p + (g0 + (int64_t)u * tx) * E);
+        T bm = g[0].v[0];
+        if constexpr (is_float_t<T>::value && !std::is_same<T, float>::value) nan |= (bm != bm);
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++) fold(g[u]);
+        for (int u = 0; u < UNROLL; u++)
+#pragma unroll
+          for (int i = 0; i < E; i++)
+            if (u || i) bm = ext2<T, IS_MAXLIKE>(bm, g[u].v[i], nan);
+        consider(bm, g0, UNROLL);
       }
-      for (; g0 < groups; g0 += tx) fold(load_group_plain<T, E>(p + g0 * E));
-    }
-    if (tx <= 32) {
-      for (int off = tx >> 1; off > 0; off >>= 1) m = ext2<T, IS_MAXLIKE>(m, __shfl_xor_sync(0xffffffffu, m, off), nan);
-    } else {
-      sh_m[threadIdx.x] = m;
-      __syncthreads();
-      m = sh_m[b0];
-      for (int j = 1; j < tx; j++) m = ext2<T, IS_MAXLIKE>(m, sh_m[b0 + j], nan);
-    }
-    if constexpr (std::is_same<T, float>::value) nan |= (m != m);
-    // ---- pass 2: index of the first element equal to M (arg*, or a zero extremum)
-    int32_t bi = INT32_MAX;
-    const bool need_index = IS_ARG || (is_float_t<T>::value && m == (T)0);
-    if (live && need_index && !nan) {
-      for (int64_t g0 = lane; g0 < groups; g0 += tx) {
-        if (bi != INT32_MAX) break;               // k grows inside a lane: the first hit is the lane's first
+      for (; g0 < groups; g0 += tx) {
         const Group<T, E> g = load_group_plain<T, E>(p + g0 * E);
+        T bm = g.v[0];
+        if constexpr (is_float_t<T>::value && !std::is_same<T, float>::value) nan |= (bm != bm);
 #pragma unroll
-        for (int i = 0; i < E; i++)
-          if (bi == INT32_MAX && g.v[i] == m) bi = (int32_t)(g0 * E) + i;
+        for (int i = 1; i < E; i++) bm = ext2<T, IS_MAXLIKE>(bm, g.v[i], nan);
+        consider(bm, g0, 1);
       }
     }
-    if (tx <= 32) {
-      for (int off = tx >> 1; off > 0; off >>= 1) {
-        const int32_t o = __shfl_xor_sync(0xffffffffu, bi, off);
-        bi = o < bi ? o : bi;
-      }
-    } else {
+    // ---- the row's extremum M
+    T M = m;
+    bool dummy = false;
+    for (int off = tree >> 1; off > 0; off >>= 1) M = ext2<T, IS_MAXLIKE>(M, __shfl_xor_sync(0xffffffffu, M, off), dummy);
+    if (tx > 32) {
+      if ((threadIdx.x & 31) == 0) sh_m[warp] = M;
       __syncthreads();
-      sh_i[threadIdx.x] = bi;
+      M = sh_m[w0];
+      for (int j = 1; j < wn; j++) M = ext2<T, IS_MAXLIKE>(M, sh_m[w0 + j], dummy);
+    }
+    // ---- first logical index of M: only lanes whose own extremum IS M look, and only at their winning batch
+    int32_t bi = INT32_MAX;
+    const bool need_index = IS_ARG || (is_float_t<T>::value && M == (T)0);
+    if (live && need_index && bg >= 0 && m == M) {
+      for (int u = 0; u < bn; u++) {
+        const int64_t gq = bg + (int64_t)u * tx;
+        const Group<T, E> g = load_group_plain<T, E>(p + gq * E);
+#pragma unroll
+        for (int i = 0; i < E; i++) {
+          const int32_t phys = (int32_t)(gq * E) + i;
+          const int32_t logical = rev ? (int32_t)K - 1 - phys : phys;
+          if (g.v[i] == M && logical < bi) bi = logical;
+        }
+      }
+    }
+    for (int off = tree >> 1; off > 0; off >>= 1) {
+      const int32_t o = __shfl_xor_sync(0xffffffffu, bi, off);
+      bi = o < bi ? o : bi;
+    }
+    if (tx > 32) {
+      if ((threadIdx.x & 31) == 0) sh_i[warp] = bi;
       __syncthreads();
       if (lane == 0)
-        for (int j = 1; j < tx; j++) bi = sh_i[b0 + j] < bi ? sh_i[b0 + j] : bi;
+        for (int j = 1; j < wn; j++) bi = sh_i[w0 + j] < bi ? sh_i[w0 + j] : bi;
     }
     if (lane == 0 && live) {
       if constexpr (IS_ARG) reinterpret_cast<int64_t*>(out)[row] = (bi == INT32_MAX) ? 0 : (int64_t)bi;
-      else reinterpret_cast<T*>(out)[row] = (need_index && bi != INT32_MAX) ? p[bi] : m;   // keeps the first zero's sign
+      else reinterpret_cast<T*>(out)[row] = (need_index && bi != INT32_MAX) ? p[rev ? K - 1 - bi : bi] : M;   // keeps the first zero's sign
     }
   }
   if (err) atomicOr(flags, err);
@@ -796,8 +951,8 @@ __global__ void __launch_bounds__(RED_THREADS) axis_row_kernel(const T* __restri
 // their registers for the first match (no second pass over memory).
 template <typename T, int E, int G, int RED>
 __global__ void __launch_bounds__(RED_THREADS) axis_rowreg_kernel(const T* __restrict__ x, void* __restrict__ out,
-                                                                  int64_t rows, int64_t K, int tx_log2,
-                                                                  uint32_t* __restrict__ flags) {
+                                                                  int64_t rows, int64_t K, int64_t rstride, int rev,
+                                                                  int tx_log2, uint32_t* __restrict__ flags) {
   constexpr bool IS_MAXLIKE = (RED == PH_MAX || RED == PH_ARGMAX);
   constexpr bool IS_ARG = (RED == PH_ARGMAX || RED == PH_ARGMIN);
   using A = typename Acc<T>::type;
@@ -805,7 +960,7 @@ __global__ void __launch_bounds__(RED_THREADS) axis_rowreg_kernel(const T* __res
   const int lane = threadIdx.x & (tx - 1);
   const int64_t row = (int64_t)blockIdx.x * (RED_THREADS >> tx_log2) + (threadIdx.x >> tx_log2);
   const bool live = row < rows;
-  const T* p = x + (live ? row : 0) * K;
+  const T* p = x + (live ? row : 0) * rstride;
   const int groups = (int)(K / E);                // K % E == 0 and groups <= 32 * G by dispatch
   Group<T, E> g[G];
   bool has[G];
@@ -851,7 +1006,7 @@ __global__ void __launch_bounds__(RED_THREADS) axis_rowreg_kernel(const T* __res
         const A hi = (A)std::numeric_limits<T>::max(), lo = (A)std::numeric_limits<T>::lowest();
         if (pos > hi || neg < lo) {               // some prefix might leave T: replay the row in order (rare)
           A run = 0;
-          for (int64_t k = 0; k < K; k++) { run += (A)p[k]; if (run > hi || run < lo) { err |= PH_FLAG_OVERFLOW; break; } }
+          for (int64_t k = 0; k < K; k++) { run += (A)p[rev ? K - 1 - k : k]; if (run > hi || run < lo) { err |= PH_FLAG_OVERFLOW; break; } }
         }
       }
       reinterpret_cast<T*>(out)[row] = (T)s;
@@ -878,8 +1033,11 @@ __global__ void __launch_bounds__(RED_THREADS) axis_rowreg_kernel(const T* __res
 #pragma unroll
         for (int u = 0; u < G; u++)
 #pragma unroll
-          for (int i = 0; i < E; i++)
-            if (has[u] && bi == INT32_MAX && g[u].v[i] == M) { bi = (lane + u * tx) * E + i; zv = g[u].v[i]; }
+          for (int i = 0; i < E; i++) {
+            const int32_t phys = (lane + u * tx) * E + i;
+            const int32_t logical = rev ? (int32_t)K - 1 - phys : phys;
+            if (has[u] && g[u].v[i] == M && logical < bi) { bi = logical; zv = g[u].v[i]; }
+          }
       }
       for (int off = tx >> 1; off > 0; off >>= 1) {
         const int32_t ob = __shfl_xor_sync(0xffffffffu, bi, off);
@@ -908,6 +1066,38 @@ static bool desc_is_contiguous(const ph_desc* d, int64_t& total) {
   }
   if (d->rank == 0) total = 0;
   return ok;
+}
+
+// Can the full-reduction kernels read this view IN PLACE?  Yes when it coalesces to rows of C contiguous
+// elements at a constant (any sign) row stride and C is a whole number of tiles; `vec` = the 32-byte form
+// is usable (aligned base and stride).  Contiguous arrays never come here (desc_is_contiguous first).
+template <typename T>
+static bool rows_layout(const void* a, const ph_desc* d, const T** x, int64_t& n, RowsArgs& rows, bool& vec) {
+  static const bool off = getenv("PH_REDUCE_GATHER") != nullptr;           // A/B knob: always gather first
+  if (off) return false;
+  int64_t total;
+  if (desc_is_contiguous(d, total) || total == 0) return false;
+  // coalesce: drop extent-1 axes, merge axis j into j+1 when stride[j] == stride[j+1] * extent[j+1]
+  int64_t ext[PH_MAX_RANK], str[PH_MAX_RANK];
+  int rk = 0;
+  for (int i = 0; i < d->rank; i++) {
+    if (d->extent[i] == 1) continue;
+    if (rk > 0 && str[rk - 1] == d->stride[i] * d->extent[i]) { ext[rk - 1] *= d->extent[i]; str[rk - 1] = d->stride[i]; }
+    else { ext[rk] = d->extent[i]; str[rk] = d->stride[i]; rk++; }
+  }
+  if (rk != 2 || str[1] != 1) return false;
+  constexpr int E32 = 32 / (int)sizeof(T);
+  const int64_t R = ext[0], C = ext[1], S = str[0];
+  const T* base = reinterpret_cast<const T*>(a) + d->offset;
+  const int64_t tile32 = (int64_t)RED_THREADS * E32 * 4, tile1 = (int64_t)RED_THREADS * 4;
+  if (E32 > 1 && C % tile32 == 0 && S % E32 == 0 && ((uintptr_t)base % 32) == 0) { vec = true; rows.tiles_per_row = (uint32_t)(C / tile32); }
+  else if (C % tile1 == 0) { vec = false; rows.tiles_per_row = (uint32_t)(C / tile1); }
+  else return false;
+  if (C / tile1 > 0x7fffffffLL || R * (C / tile1) > 0x7fffffffLL) { rows.tiles_per_row = 0; return false; }
+  rows.row_stride = S;
+  *x = base;
+  n = R * C;
+  return true;
 }
 
 // returns a contiguous device pointer holding the described region (gathers if needed)
@@ -945,10 +1135,17 @@ int32_t reduce_full_t(int32_t red, const void* a, const ph_desc* d, void* out_va
   const CombineArgs cmb = cmb_in ? *cmb_in : CombineArgs();
   const bool sharded = cmb.host_out != nullptr;       // record mode: always launch, result to the pinned host record
   const T* x;
-  void* temp;
+  void* temp = nullptr;
   int64_t n;
-  int32_t st = contiguous_input<T>(a, d, &x, &temp, n);
-  if (st != PH_OK) return st;
+  int32_t st = PH_OK;
+  RowsArgs rows;
+  bool rows_vec = false;
+  if (rows_layout<T>(a, d, &x, n, rows, rows_vec)) {
+    // a row-strided view whose rows are whole tiles: read in place (no gather, no temporary)
+  } else {
+    st = contiguous_input<T>(a, d, &x, &temp, n);
+    if (st != PH_OK) return st;
+  }
   // persistent grid: exactly the blocks that are resident at once (a partial second wave would
   // leave the GPU mostly idle while it runs), fewer for small inputs
   static int resident_sum = 0, resident_ext = 0, resident_dev = -1;
@@ -969,7 +1166,7 @@ int32_t reduce_full_t(int32_t red, const void* a, const ph_desc* d, void* out_va
   unsigned int* ticket = reduce_ticket();
   if (!ticket) return set_error(PH_ERR_CUDA, "cannot allocate the reduction ticket");
   constexpr int E32 = 32 / (int)sizeof(T);
-  const bool al32 = ((uintptr_t)x % 32) == 0;
+  const bool al32 = rows.tiles_per_row ? rows_vec : ((uintptr_t)x % 32) == 0;
   if (red == PH_SUM) {
     if (n == 0 && !sharded) {                             // Enumerable#sum of nothing is T.zero
       PH_CUDA(cudaMemsetAsync(out_value_dev, 0, sizeof(T), r.stream));
@@ -977,8 +1174,8 @@ int32_t reduce_full_t(int32_t red, const void* a, const ph_desc* d, void* out_va
       SumState<T>* parts = reinterpret_cast<SumState<T>*>(r.d_scratch);
       static_assert(sizeof(SumState<T>) <= 64, "partial too large");
       T* ov = reinterpret_cast<T*>(out_value_dev);
-      if (al32) sum_partial_kernel<T, E32><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, ov, status, ticket, r.d_flags, cmb);
-      else sum_partial_kernel<T, 1><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, ov, status, ticket, r.d_flags, cmb);
+      if (al32) sum_partial_kernel<T, E32><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, ov, status, ticket, r.d_flags, cmb, rows);
+      else sum_partial_kernel<T, 1><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, ov, status, ticket, r.d_flags, cmb, rows);
       PH_LAUNCH_CHECK("sum_partial_kernel");
       if constexpr (!is_float_t<T>::value) {
         if (!sharded) {                                   // (sharded: the caller decides from the combined record)
@@ -987,6 +1184,9 @@ int32_t reduce_full_t(int32_t red, const void* a, const ph_desc* d, void* out_va
           PH_CUDA(cudaStreamSynchronize(r.stream));
           int code = *h;
           if (code == PH_RED_NEED_EXACT) {                // the filter could not decide: exact ordered pass
+            if (rows.tiles_per_row) {                       // (the ordered pass walks a contiguous buffer)
+              if ((st = contiguous_input<T>(a, d, &x, &temp, n)) != PH_OK) return st;
+            }
             Prefix<T>* pp = reinterpret_cast<Prefix<T>*>(r.d_scratch);
             static_assert(sizeof(Prefix<T>) <= 64, "partial too large");
             sum_exact_kernel<T><<<grid, RED_THREADS, 0, r.stream>>>(x, n, pp);
@@ -1014,11 +1214,11 @@ int32_t reduce_full_t(int32_t red, const void* a, const ph_desc* d, void* out_va
       const bool is_max = (red == PH_MAX || red == PH_ARGMAX);
       T* ov = reinterpret_cast<T*>(out_value_dev);
       if (is_max) {
-        if (al32) ext_partial_kernel<T, E32, true><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags, ov, out_index_dev, ticket, cmb);
-        else ext_partial_kernel<T, 1, true><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags, ov, out_index_dev, ticket, cmb);
+        if (al32) ext_partial_kernel<T, E32, true><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags, ov, out_index_dev, ticket, cmb, rows);
+        else ext_partial_kernel<T, 1, true><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags, ov, out_index_dev, ticket, cmb, rows);
       } else {
-        if (al32) ext_partial_kernel<T, E32, false><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags, ov, out_index_dev, ticket, cmb);
-        else ext_partial_kernel<T, 1, false><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags, ov, out_index_dev, ticket, cmb);
+        if (al32) ext_partial_kernel<T, E32, false><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags, ov, out_index_dev, ticket, cmb, rows);
+        else ext_partial_kernel<T, 1, false><<<grid, RED_THREADS, 0, r.stream>>>(x, n, parts, r.d_flags, ov, out_index_dev, ticket, cmb, rows);
       }
       PH_LAUNCH_CHECK("ext_partial_kernel");
     }
@@ -1048,12 +1248,29 @@ int32_t reduce_full_sharded_t(int32_t red, const void* a, const ph_desc* d, int6
   if (st != PH_OK) return st;
   if (nccl) {
     if ((st = comm_allgather_records(r.stream)) != PH_OK) return st;
-    if (red == PH_SUM) sum_combine_kernel<T><<<1, 32, 0, r.stream>>>(pi.gather_recv, cmb.nranks, nullptr, nullptr, cmb.host_out);
-    else if (is_max) ext_combine_kernel<T, true><<<1, 32, 0, r.stream>>>(pi.gather_recv, cmb.nranks, nullptr, nullptr, cmb.host_out);
-    else ext_combine_kernel<T, false><<<1, 32, 0, r.stream>>>(pi.gather_recv, cmb.nranks, nullptr, nullptr, cmb.host_out);
+    if (red == PH_SUM) sum_combine_kernel<T><<<1, 32, 0, r.stream>>>(pi.gather_recv, cmb.nranks, nullptr, nullptr, cmb.host_out, cmb.seq);
+    else if (is_max) ext_combine_kernel<T, true><<<1, 32, 0, r.stream>>>(pi.gather_recv, cmb.nranks, nullptr, nullptr, cmb.host_out, cmb.seq);
+    else ext_combine_kernel<T, false><<<1, 32, 0, r.stream>>>(pi.gather_recv, cmb.nranks, nullptr, nullptr, cmb.host_out, cmb.seq);
     PH_LAUNCH_CHECK("combine_kernel");
   }
-  PH_CUDA(cudaStreamSynchronize(r.stream));
+  // The finishing block writes the pinned record and then its call number: the host polls that word (the
+  // result is visible ~1 us after the store) instead of paying a stream synchronisation's wake-up; a stream
+  // query every few thousand polls surfaces a faulted launch
+  {
+    const volatile uint32_t* done = &pi.host_result->seq;
+    uint32_t polls = 0;
+    while (*done != cmb.seq) {
+      if ((++polls & 0xfff) == 0) {
+        cudaError_t q = cudaStreamQuery(r.stream);
+        if (q != cudaErrorNotReady) {                      // finished (or failed) without our word: settle it the slow way
+          PH_CUDA(cudaStreamSynchronize(r.stream));
+          if (*done != cmb.seq) return set_error(PH_ERR_CUDA, "sharded reduction finished without writing its result record");
+          break;
+        }
+      }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+  }
   ReduceResult res = *pi.host_result;
   if constexpr (!is_float_t<T>::value) {
     if (red == PH_SUM && res.status == PH_RED_NEED_EXACT) {
@@ -1093,15 +1310,24 @@ int32_t reduce_full_sharded_t(int32_t red, const void* a, const ph_desc* d, int6
   return PH_OK;
 }
 
+// The view's layout as the kernels see it: element (o, k, c) at x[o * ostride + k * kstride + c * istride].
+// inner > 1 needs istride == 1 (threads run along the contiguous inner axis); inner == 1 (the reduced axis is
+// the innermost one) needs kstride == +1 or -1 (rev): rows of K elements, row o at x + o * ostride.
+struct AxisLayout {
+  int64_t ostride, kstride;
+  int rev;                // inner == 1: the reduced (innermost) axis runs backwards
+  int irev = 0;           // inner > 1: the inner axis runs backwards (x is the address of LOGICAL column 0)
+};
+
 template <typename T, int RED>
-static int32_t reduce_axis_launch(const T* x, void* out, int64_t outer, int64_t K, int64_t inner) {
+static int32_t reduce_axis_launch(const T* x, void* out, int64_t outer, int64_t K, int64_t inner, const AxisLayout& lay) {
   Runtime& r = rt();
   if (inner > 1) {
     constexpr int E32 = 32 / (int)sizeof(T), E16 = 16 / (int)sizeof(T);
     constexpr bool ARG = (RED == PH_ARGMAX || RED == PH_ARGMIN);
-    const uintptr_t xa = (uintptr_t)x, oa = (uintptr_t)out;
-    const bool can32 = inner % E32 == 0 && xa % 32 == 0 && (ARG || oa % 32 == 0);
-    const bool can16 = inner % E16 == 0 && xa % 16 == 0 && (ARG || oa % 16 == 0);
+    const uintptr_t xa = (uintptr_t)(lay.irev ? x - (inner - 1) : x), oa = (uintptr_t)out;      // lowest address of a row
+    const bool can32 = inner % E32 == 0 && xa % 32 == 0 && (ARG || oa % 32 == 0) && lay.ostride % E32 == 0 && lay.kstride % E32 == 0;
+    const bool can16 = inner % E16 == 0 && xa % 16 == 0 && (ARG || oa % 16 == 0) && lay.ostride % E16 == 0 && lay.kstride % E16 == 0;
     // Plan = (group width E, groups in flight per thread U, block size), measured on the axis-0
     // shards of the 1e9-element f32 array ([1000/N, 1000, 1000], benchmarks/probe_axis.py):
     //   * outer == 1 (the reduced axis is the leading one; consecutive k are `inner` apart): the widest
@@ -1112,6 +1338,25 @@ static int32_t reduce_axis_launch(const T* x, void* out, int64_t outer, int64_t 
     //     [125, 1000, 1000] and reach 2.1 TB/s however deep the unrolling, scalar columns 5.4 TB/s.
     const int64_t cols = outer * inner;
     const int64_t col_bytes = cols * (int64_t)sizeof(T);
+    // few columns: the cp.async-staged kernel (one warp per 32-column strip); needs 16-byte aligned strip rows
+    // and enough strips to occupy the machine.  PH_AXIS_STAGED=0 / 1 forces the choice (A/B runs).
+    if constexpr (sizeof(T) >= 4) {
+      constexpr int EPC = 16 / (int)sizeof(T);
+      static const int force_staged = getenv("PH_AXIS_STAGED") ? atoi(getenv("PH_AXIS_STAGED")) : -1;
+      const int64_t spo = ceil_div(inner, (int64_t)32);
+      const int64_t strips = outer * spo;
+      const bool aligned = xa % 16 == 0 && inner % EPC == 0 && (lay.ostride * (int64_t)sizeof(T)) % 16 == 0 &&
+                           (lay.kstride * (int64_t)sizeof(T)) % 16 == 0;
+      const bool wanted = force_staged >= 0 ? force_staged != 0
+                                            : (col_bytes < (3LL << 19) && strips >= (int64_t)r.sm_count && K >= 64);
+      if (aligned && wanted && strips <= 0x7fffffffLL && spo <= 0x7fffffffLL && K <= 0x7fffffffLL) {
+        constexpr int KT = 16, STAGES = 8;
+        axis_strip_staged_kernel<T, RED, KT, STAGES><<<(unsigned)strips, 32, 0, r.stream>>>(x, out, K, inner, lay.ostride,
+                                                                                             lay.kstride, lay.irev, (int)spo, r.d_flags);
+        PH_LAUNCH_CHECK("axis_strip_staged_kernel");
+        return PH_OK;
+      }
+    }
     int e = 1, u = 4, block = RED_THREADS;
     if (outer == 1) {
       if (can32 && E32 > 1 && cols / E32 >= (int64_t)r.sm_count * 64) e = E32;
@@ -1138,7 +1383,7 @@ static int32_t reduce_axis_launch(const T* x, void* out, int64_t outer, int64_t 
     if (force_b) block = force_b;
     const int64_t blocks = ceil_div(threads, (int64_t)block);
     if (blocks > 0x7fffffffLL) return set_error(PH_ERR_INVALID, "array too large for one launch");
-#define PH_STRIP(EE, UU) axis_strip_kernel<T, EE, RED, UU><<<(unsigned)blocks, block, 0, r.stream>>>(x, out, outer, K, inner, r.d_flags)
+#define PH_STRIP(EE, UU) axis_strip_kernel<T, EE, RED, UU><<<(unsigned)blocks, block, 0, r.stream>>>(x, out, outer, K, inner, lay.ostride, lay.kstride, lay.irev, r.d_flags)
     if (e == E32 && E32 > 1) { if (u >= 16) PH_STRIP(E32, 16); else if (u >= 8) PH_STRIP(E32, 8); else PH_STRIP(E32, 4); }
     else if (e == E16 && E16 > 1) { if (u >= 8) PH_STRIP(E16, 8); else PH_STRIP(E16, 4); }
     else { if (u >= 16) PH_STRIP(1, 16); else PH_STRIP(1, 4); }
@@ -1148,7 +1393,7 @@ static int32_t reduce_axis_launch(const T* x, void* out, int64_t outer, int64_t 
   }
   // last axis: rows of K contiguous elements
   constexpr int E32 = 32 / (int)sizeof(T);
-  const bool vec = E32 > 1 && K % E32 == 0 && ((uintptr_t)x % 32) == 0;
+  const bool vec = E32 > 1 && K % E32 == 0 && ((uintptr_t)x % 32) == 0 && lay.ostride % E32 == 0;
   const int e = vec ? E32 : 1;
   const int64_t groups = K / e;
   if (vec && groups <= 32 * 8) {                  // the row fits the registers of one warp
@@ -1157,8 +1402,8 @@ static int32_t reduce_axis_launch(const T* x, void* out, int64_t outer, int64_t 
     while (tx < 32 && (int64_t)tx * G < groups) { tx <<= 1; lg++; }
     const int64_t blocks = ceil_div(outer, (int64_t)(RED_THREADS / tx));
     if (blocks > 0x7fffffffLL) return set_error(PH_ERR_INVALID, "array too large for one launch");
-    if (G == 4) axis_rowreg_kernel<T, E32, 4, RED><<<(unsigned)blocks, RED_THREADS, 0, r.stream>>>(x, out, outer, K, lg, r.d_flags);
-    else axis_rowreg_kernel<T, E32, 8, RED><<<(unsigned)blocks, RED_THREADS, 0, r.stream>>>(x, out, outer, K, lg, r.d_flags);
+    if (G == 4) axis_rowreg_kernel<T, E32, 4, RED><<<(unsigned)blocks, RED_THREADS, 0, r.stream>>>(x, out, outer, K, lay.ostride, lay.rev, lg, r.d_flags);
+    else axis_rowreg_kernel<T, E32, 8, RED><<<(unsigned)blocks, RED_THREADS, 0, r.stream>>>(x, out, outer, K, lay.ostride, lay.rev, lg, r.d_flags);
     PH_LAUNCH_CHECK("axis_rowreg_kernel");
     return PH_OK;
   }
@@ -1167,8 +1412,8 @@ static int32_t reduce_axis_launch(const T* x, void* out, int64_t outer, int64_t 
   const int ty = RED_THREADS / tx;
   const int64_t blocks = ceil_div(outer, ty);
   if (blocks > 0x7fffffffLL) return set_error(PH_ERR_INVALID, "array too large for one launch");
-  if (vec) axis_row_kernel<T, E32, RED><<<(unsigned)blocks, RED_THREADS, 0, r.stream>>>(x, out, outer, K, tx, lg, r.d_flags);
-  else axis_row_kernel<T, 1, RED><<<(unsigned)blocks, RED_THREADS, 0, r.stream>>>(x, out, outer, K, tx, lg, r.d_flags);
+  if (vec) axis_row_kernel<T, E32, RED><<<(unsigned)blocks, RED_THREADS, 0, r.stream>>>(x, out, outer, K, lay.ostride, lay.rev, tx, lg, r.d_flags);
+  else axis_row_kernel<T, 1, RED><<<(unsigned)blocks, RED_THREADS, 0, r.stream>>>(x, out, outer, K, lay.ostride, lay.rev, tx, lg, r.d_flags);
   PH_LAUNCH_CHECK("axis_row_kernel");
   return PH_OK;
 }
@@ -1181,24 +1426,57 @@ int32_t reduce_axis_t(int32_t red, const void* a, const ph_desc* d, int32_t axis
   int64_t ototal;
   if (!od || !desc_is_contiguous(od, ototal) )
     return set_error(PH_ERR_UNSUPPORTED, "ph_reduce_axis writes a contiguous output");
-  const T* x;
-  void* temp;
-  int64_t n;
-  int32_t st = contiguous_input<T>(a, d, &x, &temp, n);
-  if (st != PH_OK) return st;
+  const T* x = nullptr;
+  void* temp = nullptr;
+  int64_t n = 0;
+  int32_t st = PH_OK;
   int64_t outer = 1, inner = 1;
   const int64_t K = d->extent[axis];
   for (int i = 0; i < axis; i++) outer *= d->extent[i];
   for (int i = axis + 1; i < d->rank; i++) inner *= d->extent[i];
-  if (outer * inner == 0 || K == 0) { if (temp) cudaFreeAsync(temp, r.stream); return PH_OK; }
+  if (outer * inner == 0 || K == 0) return PH_OK;
+  // Read the view IN PLACE when its outer axes coalesce to one stride, its inner axes to one unit-stride
+  // axis (or, for the innermost axis, the reduced axis itself has stride +1 / -1): row-strided slices,
+  // column blocks, reversed views (`view.reverse.max(axis: 1)`).  Anything else is gathered first.
+  AxisLayout lay{K * inner, inner, 0};
+  bool in_place = false;
+  {
+    static const bool off = getenv("PH_REDUCE_GATHER") != nullptr;         // A/B knob: always gather first
+    auto coalesce = [&](int lo, int hi, int64_t& stride) -> bool {        // axes [lo, hi) as ONE axis of `stride`
+      bool have = false;
+      int64_t s_prev = 0, e_prev = 0;
+      for (int i = hi - 1; i >= lo; i--) {
+        if (d->extent[i] == 1) continue;
+        if (!have) { stride = d->stride[i]; have = true; }
+        else if (d->stride[i] != s_prev * e_prev) return false;
+        s_prev = d->stride[i]; e_prev = d->extent[i];
+      }
+      if (!have) stride = 0;
+      return true;
+    };
+    int64_t total;
+    int64_t os = 0, is = 0;
+    if (!off && !desc_is_contiguous(d, total) && coalesce(0, axis, os) && coalesce(axis + 1, d->rank, is)) {
+      const int64_t ks = d->stride[axis];
+      if (inner > 1 && (is == 1 || is == -1)) { lay = AxisLayout{os, ks, 0, is == -1}; in_place = true; }
+      else if (inner == 1 && (ks == 1 || ks == -1 || K == 1)) { lay = AxisLayout{os, 1, ks == -1 && K > 1}; in_place = true; }
+    }
+  }
+  if (in_place) {
+    x = reinterpret_cast<const T*>(a) + d->offset;
+    if (lay.rev) x -= (K - 1);                    // rows are addressed by their lowest element
+  } else {
+    st = contiguous_input<T>(a, d, &x, &temp, n);
+    if (st != PH_OK) return st;
+  }
   const bool arg = (red == PH_ARGMAX || red == PH_ARGMIN);
   void* o = arg ? (void*)(reinterpret_cast<int64_t*>(out) + od->offset) : (void*)(reinterpret_cast<T*>(out) + od->offset);
   switch (red) {
-    case PH_SUM: st = reduce_axis_launch<T, PH_SUM>(x, o, outer, K, inner); break;
-    case PH_MIN: st = reduce_axis_launch<T, PH_MIN>(x, o, outer, K, inner); break;
-    case PH_MAX: st = reduce_axis_launch<T, PH_MAX>(x, o, outer, K, inner); break;
-    case PH_ARGMAX: st = reduce_axis_launch<T, PH_ARGMAX>(x, o, outer, K, inner); break;
-    case PH_ARGMIN: st = reduce_axis_launch<T, PH_ARGMIN>(x, o, outer, K, inner); break;
+    case PH_SUM: st = reduce_axis_launch<T, PH_SUM>(x, o, outer, K, inner, lay); break;
+    case PH_MIN: st = reduce_axis_launch<T, PH_MIN>(x, o, outer, K, inner, lay); break;
+    case PH_MAX: st = reduce_axis_launch<T, PH_MAX>(x, o, outer, K, inner, lay); break;
+    case PH_ARGMAX: st = reduce_axis_launch<T, PH_ARGMAX>(x, o, outer, K, inner, lay); break;
+    case PH_ARGMIN: st = reduce_axis_launch<T, PH_ARGMIN>(x, o, outer, K, inner, lay); break;
     default: st = set_error(PH_ERR_INVALID, "unknown reduction %d", red);
   }
   if (temp) cudaFreeAsync(temp, r.stream);

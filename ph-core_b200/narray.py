@@ -761,12 +761,17 @@ class _Indexable:
                 return self.dtype.type(0)
             raise CrEmptyError("Empty enumerable")
         dt = np.dtype(np.uint8) if self.dtype == np.dtype(np.bool_) else self.dtype
-        val = np.zeros(1, dtype=dt)
-        idx = C.c_int64(-1)
-        check(lib.ph_reduce_full(K[_RED[name]], dtype_code(dt), self.ptr, C.byref(self.desc()), val.ctypes.data,
-                                 C.byref(idx)))
-        DeviceNArray.raise_pending()
-        return val[0], idx.value
+        # record mode (ph_reduce_full_sharded on one process = no exchange): ONE launch whose finishing block
+        # writes value, index and the pending arithmetic flags into a pinned host record the call polls --
+        # no device-to-host copy, no stream synchronisation, no second read for the flags
+        val, idx, flags = _RED_CELLS
+        st = lib.ph_reduce_full_sharded(K[_RED[name]], dtype_code(dt), self.ptr, C.byref(self.desc()), 0, val,
+                                        C.byref(idx), C.byref(flags))
+        if st:
+            check(st)
+        if flags.value:
+            raise_for_flags(flags.value)
+        return np.frombuffer(val, dtype=dt, count=1)[0].copy(), idx.value
 
     def sum(self, axis: Optional[int] = None):
         if axis is not None:
@@ -830,6 +835,9 @@ class _Indexable:
         """Synchronise and raise OverflowError / DivisionByZeroError / ArgumentError if any
         launched op hit one (SURVEY.md 8(b) error conventions)."""
         raise_for_flags(DeviceNArray.take_flags())
+
+
+_RED_CELLS = ((C.c_uint64 * 2)(), C.c_int64(-1), C.c_uint32(0))      # reused ctypes cells of the full reductions
 
 
 class DeviceNArray(_Indexable):

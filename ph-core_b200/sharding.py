@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -218,6 +218,9 @@ def symm_from_host(arr: np.ndarray):
     return out
 
 
+_RED_OUT = ((C.c_uint64 * 2)(), C.c_int64(-1), C.c_uint32(0))
+
+
 def reduce_full_sharded(local, name: str, row_offset_elems: int = 0):
     """Full reduction of an array sharded along axis 0 (ph_reduce_full_sharded; collective -- every rank
     calls it, also with an EMPTY shard, which contributes the identity).  sum / min / max return the value;
@@ -226,15 +229,15 @@ def reduce_full_sharded(local, name: str, row_offset_elems: int = 0):
     nothing, OverflowError for an integer sum leaving T over the global lexicographic fold, ArgumentError
     for NaN under max -- on EVERY rank (the flags travel with the partials)."""
     from .narray import dtype_code, _RED, raise_for_flags, CrEmptyError
-    lib = _lib.load()
     dt = np.dtype(np.uint8) if local.dtype == np.dtype(np.bool_) else local.dtype
-    val = np.zeros(2, dtype=np.uint64)
-    idx = C.c_int64(-1)
-    flags = C.c_uint32(0)
-    check(lib.ph_reduce_full_sharded(K[_RED[name]], dtype_code(dt), local.ptr, C.byref(local.desc()), int(row_offset_elems),
-                                     val.ctypes.data, C.byref(idx), C.byref(flags)))
-    raise_for_flags(flags.value)
-    value = val.view(np.uint8)[:dt.itemsize].view(dt)[0]
+    val, idx, flags = _RED_OUT                               # reused ctypes cells: the call itself is ~0.1 ms
+    st = _lib.load().ph_reduce_full_sharded(K[_RED[name]], dtype_code(dt), local.ptr, C.byref(local.desc()),
+                                            int(row_offset_elems), val, C.byref(idx), C.byref(flags))
+    if st:
+        check(st)
+    if flags.value:
+        raise_for_flags(flags.value)
+    value = np.frombuffer(val, dtype=dt, count=1)[0]
     if name == "sum":
         return value
     if idx.value < 0:
@@ -349,13 +352,17 @@ class ShardedNArray:
         return ShardedNArray([self.shape[0]] + loc.shape[1:], loc)
 
     # ---- transposes across shards: the one real exchange step (all-to-all) --------------------
-    def permute(self, *pattern) -> "ShardedNArray":
+    def permute(self, *pattern, out: Optional["ShardedNArray"] = None) -> "ShardedNArray":
         """MultiIndexable#permute (src/multi_indexable.cr:795-803; default = reversed axes,
-        transforms.cr:236-238) on the distributed array; the result is sharded along its own axis
-        0.  Every rank cuts its rows into one block per peer, permutes each block locally (one
-        strided gather), exchanges them with ph_alltoallv, and scatters what it receives into its
-        shard of the result (one strided scatter per peer)."""
+        transforms.cr:236-238) on the distributed array; the result is sharded along its own axis 0.
+        With peer-mapped memory (p2p_ready) the exchange is ONE pass of peer stores: for every peer the
+        block this rank owes it -- a permuted VIEW of its rows -- is copied by the transpose kernel
+        straight into that peer's shard of the result over NVLink (ph_alltoall_strided): no staging, no
+        NCCL, no scatter.  The result then lives in peer-mapped memory (collective allocation); pass a
+        previous result as `out` to reuse it.  Otherwise (NCCL form): every rank permutes each block
+        locally (strided gather), exchanges them with ph_alltoallv and scatters what it receives."""
         from .narray import DeviceNArray
+        from ._lib import PhDesc
         from .region import rng, ALL
         nd = len(self.shape)
         pat = list(pattern[0]) if len(pattern) == 1 and isinstance(pattern[0], (list, tuple)) else list(pattern)
@@ -367,6 +374,34 @@ class ShardedNArray:
         lib = _lib.load()
         k, j = plan["k"], plan["j"]
         m0, m1 = plan["my_new_rows"]
+        new_shape = plan["new_shape"]
+        if self.world > 1 and p2p_ready() and not os.environ.get("PH_PERMUTE_NCCL"):
+            my_shape = [m1 - m0] + new_shape[1:]
+            if out is not None:
+                if out.shape != new_shape or out.dtype != self.dtype or not isinstance(out.local._buf, _SymmBuffer):
+                    raise ValueError("permute(out=): `out` must be an earlier P2P result of the same shape and dtype")
+                res = out.local
+            else:
+                res = symm_empty(my_shape, self.dtype)                           # collective
+            r0, r1 = self.row0, self.row1
+            srcs, dsts = (PhDesc * self.world)(), (PhDesc * self.world)()
+            for q in range(self.world):
+                k0, k1 = plan["send"][q]
+                q0, q1 = shard_range(new_shape[0], self.world, q)                # q's rows of the result
+                q_shape = [q1 - q0] + new_shape[1:]
+                if k1 - k0 <= 0 or r1 - r0 <= 0:
+                    srcs[q] = PhDesc.make([0] * nd, [0] * nd, 0)
+                    dsts[q] = PhDesc.make([0] * nd, [0] * nd, 0)
+                    continue
+                lit = [ALL] * nd
+                lit[k] = rng(k0, k1 - 1)
+                srcs[q] = self.local.view(*lit).permute(*pat).desc()             # my rows x q's slice, in q's axis order
+                strides = [int(np.prod(q_shape[i + 1:], dtype=np.int64)) for i in range(nd)]
+                ext = list(q_shape)
+                ext[j] = r1 - r0                                                 # old axis 0 (my rows) lands on new axis j
+                dsts[q] = PhDesc.make(ext, strides, r0 * strides[j])
+            check(lib.ph_alltoall_strided(self.dtype.itemsize, self.local.ptr, srcs, res.ptr, dsts))
+            return out if out is not None else ShardedNArray(new_shape, res)
         out = DeviceNArray([m1 - m0] + plan["new_shape"][1:], self.dtype)
         isz = self.dtype.itemsize
         sends, recvs = [], []

@@ -197,6 +197,13 @@ def main():
     t2 = S.ShardedNArray.from_global(m2).permute()
     assert t2.shape == [517, 1000 * world + 3] and t2.to_global().tobytes() == np.ascontiguousarray(m2.T).tobytes()
     assert t2.permute().to_global().tobytes() == m2.tobytes()              # transposing twice is the identity
+    if S.p2p_ready():                                                      # the P2P form reuses a result buffer on request
+        again = S.ShardedNArray.from_global(m2 + 1.0).permute(out=t2)
+        assert again is t2 and t2.to_global().tobytes() == np.ascontiguousarray((m2 + 1.0).T).tobytes()
+    m3 = rs.rand(3 * world, 1)                                             # the result has ONE row: every rank but 0 owns nothing
+    t3 = S.ShardedNArray.from_global(m3).permute()
+    assert t3.shape == [1, 3 * world] and t3.to_global().tobytes() == np.ascontiguousarray(m3.T).tobytes()
+    assert t3.permute().to_global().tobytes() == m3.tobytes()
     sg.set_mask(sg > sh, 0.0)
     assert sg.to_global().tobytes() == np.where(g > h, np.float32(0), g).tobytes()
     dist.barrier()

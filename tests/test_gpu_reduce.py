@@ -7,7 +7,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 import ph_core_b200 as ph
-from ph_core_b200 import DeviceNArray as D
+from ph_core_b200 import DeviceNArray as D, rng
 from oracle import ph_oracle as O
 from gpu_util import assert_bits, take_flags
 
@@ -219,4 +219,98 @@ def test_sharded_entry_on_one_rank_equals_the_plain_reduction():
     n = D.from_host(np.array([1.0, np.nan, 3.0], np.float64))
     with pytest.raises(ph.CrArgumentError):
         S.reduce_full_sharded(n, "max")
+    assert take_flags() == set()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32])
+def test_reductions_read_strided_views_in_place(dtype):
+    """a row-strided slice, a column block and a reversed view are reduced where they lie --
+    ONE launch, no gather into a temporary (the launch counter proves it) -- with the same results as the
+    gathered form: first extremum on the view's own lexicographic index, ordered folds off the last axis."""
+    lib = ph.load()
+    rs = np.random.RandomState(12)
+    n = (rs.randint(-8, 9, size=(64, 8192)) if np.dtype(dtype).kind == "i" else rs.randint(-8, 9, size=(64, 8192))).astype(dtype)
+    n[10, 5000] = n[40, 17] = 50                     # tie for the max: the lower lex index OF THE VIEW wins
+    n[33, 1] = -50
+    d = D.from_host(n)
+
+    def launches(fn):
+        before = lib.ph_launch_count()
+        out = fn()
+        return out, lib.ph_launch_count() - before
+
+    cases = [("rows 0,2,4..", (rng(0, None, 2), ph.ALL), n[0::2, :]),
+             ("column block", (ph.ALL, rng(1024, 5119)), n[:, 1024:5120]),
+             ("rows reversed", (rng(None, None, -1), ph.ALL), n[::-1, :])]
+    for name, lit, want in cases:
+        v = d.view(*lit)
+        flat = want.reshape(-1)
+        got, k = launches(lambda: v.sum())
+        assert got == dtype(flat.astype(np.float64).sum()) and k == 1, (name, got, k)
+        got, k = launches(lambda: v.argmax())
+        assert got == (dtype(50), list(np.unravel_index(int(np.argmax(flat)), want.shape))) and k == 1, (name, got, k)
+        got, k = launches(lambda: v.argmin())
+        assert got[0] == flat.min() and got[1] == list(np.unravel_index(int(np.argmin(flat)), want.shape)) and k == 1, (name, got)
+    # per axis: strip kernel over a row-strided / reversed-rows view, row kernels over reversed rows
+    views = [("rows 0,2,4..", d.view(rng(0, None, 2), ph.ALL), n[0::2, :]),
+             ("both reversed", d.view().reverse(), n[::-1, ::-1]),
+             ("column block", d.view(ph.ALL, rng(1024, 5119)), n[:, 1024:5120]),
+             ("rows reversed", d.view(rng(None, None, -1), ph.ALL), n[::-1, :])]
+    for name, v, want in views:
+        want = np.ascontiguousarray(want)
+        for axis in (0, 1):
+            for which in ("sum", "max", "min", "argmax", "argmin"):
+                got, k = launches(lambda: getattr(v, which)(axis=axis))
+                assert k == 1, (name, axis, which, k)                   # no gather launch in front of the reduction
+                assert_bits(got.to_host(), O.reduce_axis(want, axis, which), f"{name} {which} axis={axis}")
+    # short reversed rows (the register-resident row kernel) with a zero whose sign depends on the order
+    z = np.zeros((7, 64), dtype if np.dtype(dtype).kind == "f" else np.float32)
+    z[:, 3] = -0.0
+    z[2, 9] = -0.0
+    zv = D.from_host(z).view().reverse()
+    zw = np.ascontiguousarray(z[::-1, ::-1])
+    assert_bits(zv.max(axis=1).to_host(), O.reduce_axis(zw, 1, "max"), "zero sign, reversed rows")
+    assert_bits(zv.argmin(axis=1).to_host(), O.reduce_axis(zw, 1, "argmin"), "argmin, reversed rows")
+    # a view the kernels cannot address in place (column step 2) still works through the gather
+    g = d.view(ph.ALL, rng(0, None, 2))
+    assert g.sum() == dtype(n[:, ::2].astype(np.float64).sum())
+    assert_bits(g.max(axis=0).to_host(), O.reduce_axis(np.ascontiguousarray(n[:, ::2]), 0, "max"), "gathered view")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32, np.int64])
+def test_few_column_axis_folds_through_the_staged_kernel(dtype):
+    """Per-axis folds with FEW columns (>= 148 strips of 32 columns, < 1.5 MB of columns) run in
+    axis_strip_staged_kernel: one warp per strip, cp.async ring, the same k-ordered fold -- float sums stay
+    bit-identical to the sequential each_slice fold (src/multi_indexable.cr:742-748), first extremum wins."""
+    rs = np.random.RandomState(31)
+    for shape, axis in [((200, 4800), 0), ((3, 100, 2000), 1), ((70, 5000), 0), ((2, 77, 3, 800), 1)]:
+        if np.dtype(dtype).kind == "f":
+            a = (rs.rand(*shape) * 2 - 1).astype(dtype)          # general data: only the exact k order is bit-identical
+        else:
+            a = rs.randint(-1000, 1000, size=shape).astype(dtype)
+        idx = tuple(rs.randint(0, s) for s in shape)
+        a[idx] = 5000
+        lo = list(idx); lo[axis] = (idx[axis] + 7) % shape[axis]; a[tuple(lo)] = 5000      # a tie along the folded axis
+        d = D.from_host(a)
+        for which in ("sum", "max", "min", "argmax", "argmin"):
+            assert_bits(getattr(d, which)(axis=axis).to_host(), O.reduce_axis(a, axis, which), f"{shape} {which} axis={axis}")
+        # a row-reversed view of the same array (negative k stride): read in place
+        if axis == 0 and len(shape) == 2:
+            v = d.view(rng(None, None, -1), ph.ALL)
+            w = np.ascontiguousarray(a[::-1])
+            for which in ("sum", "argmax", "min"):
+                assert_bits(getattr(v, which)(axis=0).to_host(), O.reduce_axis(w, 0, which), f"reversed {which}")
+    if np.dtype(dtype).kind == "f":
+        z = np.zeros((80, 4800), dtype)
+        z[3, :] = -0.0
+        z[40, 17] = np.nan
+        dz = D.from_host(z)
+        with pytest.raises(ph.CrArgumentError):
+            dz.max(axis=0).to_host()
+        z[40, 17] = 0.0
+        assert_bits(D.from_host(z).max(axis=0).to_host(), O.reduce_axis(z, 0, "max"), "first zero keeps its sign")
+    else:
+        big = np.full((80, 4800), np.iinfo(dtype).max // 40, dtype)
+        with pytest.raises(ph.CrOverflowError):
+            D.from_host(big).sum(axis=0).to_host()
     assert take_flags() == set()
