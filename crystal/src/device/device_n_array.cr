@@ -39,6 +39,11 @@ module Phase
       @shape
     end
 
+    # An array over storage the caller provides (the peer-mapped shard of a `ShardedNArray`).
+    def self.over(shape : Enumerable(Int), dev : DeviceBuffer) : self
+      new(shape.map(&.to_i32).to_a, dev)
+    end
+
     # Picked up by `MultiIndexable#map_with` through `responds_to?`; a host Slice is uploaded.
     def self.of_buffer(shape : Array(Int32), buffer : Slice(T)) : self
       from_host(NArray.of_buffer(shape, buffer))

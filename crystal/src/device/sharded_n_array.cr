@@ -1,0 +1,351 @@
+require "./device_n_array"
+require "./device_view"
+
+module Phase
+  # One process per GPU: the communicator of the job and who owns which rows.
+  module Comm
+    @@world = 1
+    @@rank = 0
+
+    def self.world : Int32
+      @@world
+    end
+
+    def self.rank : Int32
+      @@rank
+    end
+
+    # Rank 0 creates the id; the launcher hands it to the other ranks (file, environment, MPI ...).
+    def self.unique_id : StaticArray(UInt8, 128)
+      Device.ensure_init
+      id = StaticArray(UInt8, 128).new(0_u8)
+      Device.check LibPhGpu.ph_comm_unique_id(id.to_unsafe)
+      id
+    end
+
+    def self.init(nranks : Int32, rank : Int32, id : StaticArray(UInt8, 128)) : Nil
+      Device.ensure_init
+      Device.check LibPhGpu.ph_comm_init(nranks, rank, id.to_unsafe)
+      @@world, @@rank = nranks, rank
+    end
+
+    def self.destroy : Nil
+      LibPhGpu.ph_comm_destroy
+      @@world, @@rank = 1, 0
+    end
+
+    # true: every rank has mapped its peers' memory (CUDA IPC over NVLink): reductions combine inside the
+    # kernel and `permute` is one pass of peer stores; false: the NCCL forms of the same entry points run.
+    def self.p2p_ready? : Bool
+      Device.check LibPhGpu.ph_comm_p2p_ready(out ready)
+      ready != 0
+    end
+
+    # Contiguous split of `n` leading-axis indices: the first `n % world` ranks get one extra
+    # (the rule of ph_shard_range, include/ph_host.h).
+    def self.shard_range(n : Int, world : Int32 = @@world, rank : Int32 = @@rank) : {Int32, Int32}
+      base, extra = n.to_i32 // world, n.to_i32 % world
+      start = rank * base + {rank, extra}.min
+      {start, start + base + (rank < extra ? 1 : 0)}
+    end
+
+    # Peer-mapped device memory (`ph_symm_alloc`; COLLECTIVE: every rank, same order). Released by
+    # `Comm.destroy`, never by a finalizer -- a collective release cannot depend on the GC.
+    class SymmBuffer < DeviceBuffer
+      def initialize(bytesize : Int64)
+        @bytesize = bytesize
+        @parent = nil
+        @ptr = Pointer(Void).null
+        Device.check LibPhGpu.ph_symm_alloc(LibC::SizeT.new({bytesize, 1_i64}.max), pointerof(@ptr))
+      end
+
+      def free : Nil
+      end
+    end
+  end
+
+  # An `NArray` distributed along axis 0 over the ranks of the job (SURVEY.md 8(f) f-3). Every rank holds the
+  # contiguous row range `Comm.shard_range(shape[0])` as an ordinary `DeviceNArray(T)`:
+  #
+  # * elementwise operators, comparisons and masked stores are local launches;
+  # * `sum` / `min` / `max` / `argmax` are ONE launch per rank with the cross-rank combine inside the kernel
+  #   (`ph_reduce_full_sharded`): the same value -- and the same exception -- on every rank;
+  # * per-axis folds are local unless the folded axis is the sharded one (`sum(axis: 0)`: the partials are
+  #   combined with `ph_allreduce`, checked integer sums with `ph_allgather` + the checked axis-0 fold);
+  # * `permute` is one pass of peer stores (`ph_alltoall_strided`: the transpose kernel writes every block
+  #   straight into its owner's shard over NVLink), or gathers + `ph_alltoallv` + scatters without P2P.
+  #
+  # The reference is single-process; this class covers the seam north_star partitions
+  # (`src/multi_indexable.cr:30-65` for the array it shards).
+  class ShardedNArray(T)
+    getter shape : Array(Int32)
+    getter local : DeviceNArray(T)
+    getter row0 : Int32
+    getter row1 : Int32
+
+    def initialize(global_shape : Enumerable(Int), @local : DeviceNArray(T))
+      @shape = global_shape.map(&.to_i32).to_a
+      raise ShapeError.new("a sharded array needs at least one axis") if @shape.empty?
+      @row0, @row1 = Comm.shard_range(@shape[0])
+      expected = [@row1 - @row0] + @shape[1..]
+      unless @local.shape == expected
+        raise ShapeError.new("local shard has shape #{@local.shape}, expected #{expected}")
+      end
+    end
+
+    # Every rank passes the same host array and keeps its own rows.
+    def self.from_global(host : NArray(T)) : self
+      row0, row1 = Comm.shard_range(host.shape[0])
+      rows = row1 > row0 ? host[row0...row1] : NArray(T).new([0] + host.shape[1..]) { T.zero }
+      new(host.shape, DeviceNArray(T).from_host(rows))
+    end
+
+    def size : Int64
+      Descriptor.element_count(@shape)
+    end
+
+    private def row_elems : Int64
+      @shape.size > 1 ? Descriptor.element_count(@shape[1..]) : 1_i64
+    end
+
+    # The whole array on every rank's host (allgather of the shards, padded to the largest one).
+    def to_global : NArray(T)
+      mine = @local.to_host
+      return mine if Comm.world == 1
+      rows_max = (@shape[0] + Comm.world - 1) // Comm.world
+      slot = rows_max * row_elems * sizeof(T)
+      send = DeviceBuffer.new(slot)
+      recv = DeviceBuffer.new(slot * Comm.world)
+      Device.check LibPhGpu.ph_d2d(send.ptr, @local.dev.ptr, LibC::SizeT.new(@local.size * sizeof(T))) if @local.size > 0
+      Device.check LibPhGpu.ph_allgather(send.ptr, recv.ptr, slot)
+      raw = Slice(UInt8).new(slot * Comm.world)
+      Device.read_checked(raw.to_unsafe.as(Void*), recv.ptr, LibC::SizeT.new(raw.size))
+      buffer = Slice(T).new(size.to_i32) { T.zero }
+      Comm.world.times do |r|
+        a, b = Comm.shard_range(@shape[0], Comm.world, r)
+        count = (b - a) * row_elems
+        (raw.to_unsafe + r * slot).as(T*).copy_to(buffer.to_unsafe + a * row_elems, count) if count > 0
+      end
+      NArray(T).of_buffer(@shape, buffer)
+    end
+
+    private def same_shape!(other : ShardedNArray)
+      unless other.shape == @shape
+        raise ShapeError.new("The shape of this MultiIndexable (#{@shape}) does not match the shape of the one provided (#{other.shape}).")
+      end
+    end
+
+    private def wrap(local : DeviceNArray(U)) : ShardedNArray(U) forall U
+      ShardedNArray(U).new(@shape, local)
+    end
+
+    # ---- elementwise / comparisons: local (the operator list of src/multi_indexable.cr:960-981)
+    {% for op in %w(+ - * / // % ** &+ &- &* > < >= <=) %}
+      def {{op.id}}(other : ShardedNArray(T))
+        same_shape!(other)
+        wrap(@local {{op.id}} other.local)
+      end
+
+      def {{op.id}}(other : T)
+        wrap(@local {{op.id}} other)
+      end
+    {% end %}
+
+    def eq(other : ShardedNArray(T)) : ShardedNArray(Bool)
+      same_shape!(other)
+      wrap(@local.eq(other.local))
+    end
+
+    # `narr[mask] = value` on the distributed array (src/n_array.cr:510-551)
+    def []=(mask : ShardedNArray(Bool), value : T)
+      @local[mask.local] = value
+    end
+
+    def []=(mask : ShardedNArray(Bool), value : ShardedNArray(T))
+      same_shape!(value)
+      @local[mask.local] = value.local
+    end
+
+    # ---- full reductions: collective, one launch per rank
+    private def reduce_full(red : LibPhGpu::Red) : {T, Int64}
+      cell = StaticArray(UInt64, 2).new(0_u64)
+      index = -1_i64
+      flags = 0_u32
+      d = @local.desc
+      Device.check LibPhGpu.ph_reduce_full_sharded(red.value, Device.dtype(T), @local.dev.ptr, pointerof(d), @row0.to_i64 * row_elems,
+        cell.to_unsafe.as(Void*), pointerof(index), pointerof(flags))
+      Device.raise_for(flags)
+      {cell.to_unsafe.as(T*).value, index}
+    end
+
+    private def need(result : {T, Int64}) : {T, Int64}
+      raise Enumerable::EmptyError.new if result[1] < 0
+      result
+    end
+
+    def sum : T
+      reduce_full(LibPhGpu::Red::Sum)[0]
+    end
+
+    def min : T
+      need(reduce_full(LibPhGpu::Red::Min))[0]
+    end
+
+    def max : T
+      need(reduce_full(LibPhGpu::Red::Max))[0]
+    end
+
+    # README.md:56-61 across shards: {max, coordinate of the FIRST maximum of the global array}
+    def argmax : {T, Array(Int32)}
+      value, index = need(reduce_full(LibPhGpu::Red::ArgMax))
+      {value, index_to_coord(index)}
+    end
+
+    def argmin : {T, Array(Int32)}
+      value, index = need(reduce_full(LibPhGpu::Red::ArgMin))
+      {value, index_to_coord(index)}
+    end
+
+    def index_to_coord(index : Int64) : Array(Int32)
+      coord = Array(Int32).new(@shape.size, 0)
+      (@shape.size - 1).downto(0) do |i|
+        coord[i] = (index % @shape[i]).to_i32
+        index //= @shape[i]
+      end
+      coord
+    end
+
+    # ---- per-axis folds. axis >= 1: axis 0 survives, the result is still sharded; axis 0: the partial over my
+    # rows is combined across ranks and the REPLICATED `DeviceNArray` of shape[1..] comes back on every rank.
+    {% for name, red in {sum: "Sum", min: "Min", max: "Max"} %}
+      def {{name.id}}(*, axis : Int32)
+        unless 0 <= axis < @shape.size
+          raise IndexError.new("axis #{axis} is not present in a #{@shape.size}-dimensional MultiIndexable")
+        end
+        if axis > 0
+          kept = @shape.dup
+          kept.delete_at(axis)
+          return ShardedNArray(T).new(kept, @local.{{name.id}}(axis: axis))
+        end
+        over_shards(LibPhGpu::Red::{{red.id}})
+      end
+    {% end %}
+
+    private def over_shards(red : LibPhGpu::Red) : DeviceNArray(T)
+      # every decision that can raise is taken on the GLOBAL shape: all ranks reach the collective, or none
+      raise Enumerable::EmptyError.new if @shape[0] == 0 && !red.sum?
+      out_shape = @shape.size > 1 ? @shape[1..] : [1]
+      part = if @row1 > @row0
+               case red
+               when .sum? then @local.sum(axis: 0)
+               when .max? then @local.max(axis: 0)
+               else            @local.min(axis: 0)
+               end
+             else # an empty shard contributes the identity
+               DeviceNArray(T).fill(out_shape, red.sum? ? T.zero : (red.max? ? lowest : highest))
+             end
+      return part if Comm.world == 1
+      {% if T < Int %}
+        if red.sum?
+          # checked integer sums: an ncclSum would wrap silently. The per-rank partials ([world, inner], rank
+          # order = row order) are gathered and folded by the checked axis-0 sum.
+          gathered = DeviceNArray(T).new([Comm.world] + out_shape)
+          Device.check LibPhGpu.ph_allgather(part.dev.ptr, gathered.dev.ptr, part.size * sizeof(T))
+          return gathered.sum(axis: 0)
+        end
+      {% end %}
+      Device.check LibPhGpu.ph_allreduce(red.value, Device.dtype(T), part.dev.ptr, part.size)
+      part
+    end
+
+    private def lowest : T
+      {% if T < Float %} -T::INFINITY {% else %} T::MIN {% end %}
+    end
+
+    private def highest : T
+      {% if T < Float %} T::INFINITY {% else %} T::MAX {% end %}
+    end
+
+    # ---- `MultiIndexable#permute` (src/multi_indexable.cr:795-803; no pattern = reversed axes) across shards.
+    # The result is sharded along ITS axis 0 (old axis k = pattern[0]). `reuse`: an earlier P2P result of the
+    # same shape whose peer-mapped storage receives the new one.
+    def permute(pattern : Enumerable(Int)? = nil, reuse : ShardedNArray(T)? = nil) : ShardedNArray(T)
+      nd = @shape.size
+      pat = pattern ? pattern.map(&.to_i32).to_a : (0...nd).to_a.reverse
+      unless pat.size == nd && pat.sort == (0...nd).to_a
+        raise IndexError.new("Could not use pattern #{pat} to permute: it is not a permutation of the axes of a #{nd}-dimensional MultiIndexable")
+      end
+      new_shape = pat.map { |axis| @shape[axis] }
+      k = pat[0]
+      return ShardedNArray(T).new(new_shape, @local.permute(pat)) if k == 0 # axis 0 stays put: no exchange
+      j = pat.index(0).not_nil!                                               # where my rows land
+      world, me = Comm.world, Comm.rank
+      m0, m1 = Comm.shard_range(new_shape[0])
+      my_shape = [m1 - m0] + new_shape[1..]
+      # my rows x peer q's slice of old axis k, in q's axis order (a VIEW: nothing is copied yet)
+      block = ->(q : Int32) do
+        k0, k1 = Comm.shard_range(@shape[k], world, q)
+        region = Array(Range(Int32?, Int32?) | Int32).new(nd) { |axis| axis == k ? (k0...k1) : (nil..nil) }
+        {k1 - k0, @local.view(region).permute(pat)}
+      end
+      if world > 1 && Comm.p2p_ready?
+        result = if reuse
+                   raise ShapeError.new("permute(reuse:): shape #{reuse.shape} is not #{new_shape}") unless reuse.shape == new_shape
+                   reuse.local
+                 else
+                   DeviceNArray(T).over(my_shape, Comm::SymmBuffer.new(Descriptor.element_count(my_shape) * sizeof(T))) # collective
+                 end
+        sources = Array(LibPhGpu::Desc).new(world) { Descriptor.make(nd, 0_i64, Descriptor.axes, Descriptor.axes) }
+        targets = Array(LibPhGpu::Desc).new(world) { Descriptor.make(nd, 0_i64, Descriptor.axes, Descriptor.axes) }
+        world.times do |q|
+          count, view = block.call(q)
+          next if count <= 0 || @row1 <= @row0
+          sources[q] = view.desc
+          q0, q1 = Comm.shard_range(new_shape[0], world, q)
+          whole = Descriptor.contiguous([q1 - q0] + new_shape[1..]) # q's shard of the result
+          extent, stride = whole.extent, whole.stride
+          extent[j] = (@row1 - @row0).to_i64
+          targets[q] = Descriptor.make(nd, @row0.to_i64 * stride[j], extent, stride)
+        end
+        Device.check LibPhGpu.ph_alltoall_strided(sizeof(T).to_i32, @local.dev.ptr, sources.to_unsafe, result.dev.ptr, targets.to_unsafe)
+        return reuse || ShardedNArray(T).new(new_shape, result)
+      end
+      # NCCL form: permuting gathers, personalised all-to-all, scatters
+      result = DeviceNArray(T).new(my_shape)
+      landing = ->(q : Int32) do
+        p0, p1 = Comm.shard_range(@shape[0], world, q)
+        Array(Range(Int32?, Int32?) | Int32).new(nd) { |axis| axis == j ? (p0...p1) : (nil..nil) }
+      end
+      sends = Array(DeviceNArray(T)?).new(world, nil)
+      recvs = Array(DeviceNArray(T)?).new(world, nil)
+      world.times do |q|
+        count, view = block.call(q)
+        p0, p1 = Comm.shard_range(@shape[0], world, q)
+        if q == me # my own block never leaves the GPU: one permuting copy into the result
+          result[landing.call(q)] = view if count > 0 && @row1 > @row0
+          next
+        end
+        sends[q] = view.to_narr if count > 0 && @row1 > @row0
+        incoming = new_shape.dup
+        incoming[0] = m1 - m0
+        incoming[j] = p1 - p0
+        recvs[q] = DeviceNArray(T).new(incoming) if Descriptor.element_count(incoming) > 0
+      end
+      send_ptr = sends.map { |b| b ? b.dev.ptr : Pointer(Void).null }
+      recv_ptr = recvs.map { |b| b ? b.dev.ptr : Pointer(Void).null }
+      send_bytes = sends.map { |b| b ? b.size * sizeof(T) : 0_i64 }
+      recv_bytes = recvs.map { |b| b ? b.size * sizeof(T) : 0_i64 }
+      Device.check LibPhGpu.ph_alltoallv(send_ptr.to_unsafe, send_bytes.to_unsafe, recv_ptr.to_unsafe, recv_bytes.to_unsafe)
+      world.times do |q|
+        if incoming = recvs[q]
+          result[landing.call(q)] = incoming
+        end
+      end
+      ShardedNArray(T).new(new_shape, result)
+    end
+
+    def permute(first : Int, *rest : Int) : ShardedNArray(T)
+      permute([first.to_i32] + rest.map(&.to_i32).to_a)
+    end
+  end
+end

@@ -580,12 +580,26 @@ int32_t ph_alltoall_strided(int32_t elem_size, const void* src_dev, const ph_des
   const uint32_t event = ++p.xchg_event;
   int32_t st = xchg_round(0, event);            // every rank has finished whatever read its destination before
   if (st != PH_OK) return st;
-  for (int i = 0; i < c.nranks; i++) {
+  // The peer stores go out on the (high-priority) auxiliary stream: they are bound by the link, need few SMs
+  // and must start first; my own block, which never leaves the GPU and is HBM-bound, is copied on the main
+  // stream at the same time.
+  Runtime& r = rt();
+  cudaStream_t main_stream = r.stream;
+  PH_CUDA(cudaEventRecord(r.ev_a, main_stream));
+  PH_CUDA(cudaStreamWaitEvent(r.aux_stream, r.ev_a, 0));
+  r.stream = r.aux_stream;
+  for (int i = 1; i < c.nranks && st == PH_OK; i++) {
     const int q = (c.rank + i) % c.nranks;
     if (elems(src_descs[q]) == 0) continue;
-    void* dst = q == c.rank ? dst_symm : (void*)(sa->peer[q] + rel);
-    if ((st = ph_copy_strided(elem_size, src_dev, &src_descs[q], dst, &dst_descs[q])) != PH_OK) return st;
+    st = ph_copy_strided(elem_size, src_dev, &src_descs[q], (void*)(sa->peer[q] + rel), &dst_descs[q]);
   }
+  r.stream = main_stream;
+  if (st != PH_OK) return st;
+  PH_CUDA(cudaEventRecord(r.ev_b, r.aux_stream));
+  if (elems(src_descs[c.rank]) != 0 &&
+      (st = ph_copy_strided(elem_size, src_dev, &src_descs[c.rank], dst_symm, &dst_descs[c.rank])) != PH_OK)
+    return st;
+  PH_CUDA(cudaStreamWaitEvent(main_stream, r.ev_b, 0));
   return xchg_round(1, event);                  // every block destined for me has landed
 }
 
