@@ -680,6 +680,21 @@ def run_extras(ph, lib, dist, world, rank, torch, stream):
                                                     "straight into its owner's shard over NVLink (ph_alltoall_strided), result buffer reused"
                                                     if p2p_perm else
                                                     "ShardedNArray.permute: per-peer permuting gathers, ncclSend/ncclRecv all-to-all, scatters")}
+        # ------------------------------------------------------------ N-GPU parity, in the driver's own multi-GPU run
+        # (the GPU test box has ONE GPU, so tests/test_gpu_multi.py is skipped there): every agreement check of
+        # tests/mgpu_check.py -- slabbed stencil vs oracle and vs the 1-GPU run, in-kernel halos, sharded reductions
+        # of every dtype, ShardedNArray vs the undivided array -- outside every timed region.  A disagreement is
+        # reported, never swallowed: "ok": false and the assertion text.
+        if not os.environ.get("PH_BENCH_NO_PARITY"):
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import mgpu_check
+            t0 = time.perf_counter()
+            par = mgpu_check.run_checks(world, rank, soft=True)       # soft: every rank walks every collective
+            oks = _gather_objects(dist, world, bool(par["ok"]))
+            par["ok"] = all(oks)
+            par["ranks_ok"] = oks
+            par["seconds"] = round(time.perf_counter() - t0, 1)
+            out["multi_gpu_parity"] = par
     return out
 
 

@@ -24,10 +24,7 @@ namespace ph {
 // Packed f32x2 adds (FADD2) in the two-step stencil: bit-identical and 20 % fewer instructions
 // (ncu: 1175 M -> 941 M warp instructions, issue 68 % -> 53 %), but SLOWER on B200 (2048^3: 1452 ->
 // 1381 Gcell/s; barrier + short-scoreboard stalls up): FADD2 does not run at twice the FADD rate, so
-// the FP pipe, not the issue slot, becomes the limit.  Kept for A/B runs, off by default.
-#ifndef PH_HEAT_F32X2
-#define PH_HEAT_F32X2 0
-#endif
+// the FP pipe, not the issue slot, becomes the limit.  Kept for A/B runs (PH_HEAT_TB_CFG=5 / 6), off by default.
 constexpr int TMA_STAGES = 6;       // planes resident in shared memory (3 in use + 3 in flight)
 
 __device__ __forceinline__ void st_flag_sys(uint32_t* p, uint32_t v) {
@@ -269,11 +266,11 @@ __device__ __forceinline__ Group<float, 4> heat_row_f32x2(const Group<float, 4>&
   return res;
 }
 
-template <typename T, int E, bool EDGE>
+template <typename T, int E, bool EDGE, bool X2 = false>
 __device__ __forceinline__ Group<T, E> heat_row(const Group<T, E>& c, const Group<T, E>& zl, const Group<T, E>& zh,
                                                 const Group<T, E>& yl, const Group<T, E>& yh, T xl, T xr, T coeff,
                                                 bool fix_first, bool fix_last) {
-  if constexpr (std::is_same<T, float>::value && E == 4 && PH_HEAT_F32X2) {
+  if constexpr (std::is_same<T, float>::value && E == 4 && X2) {
     return heat_row_f32x2<EDGE>(c, zl, zh, yl, yh, xl, xr, coeff, fix_first, fix_last);
   }
   Group<T, E> res;
@@ -290,7 +287,7 @@ __device__ __forceinline__ Group<T, E> heat_row(const Group<T, E>& c, const Grou
   return res;
 }
 
-template <typename T, int TY, int STAGES>
+template <typename T, int TY, int STAGES, bool X2 = false, bool LDSX = true>
 __global__ void __launch_bounds__(Tma2Tile<T, TY, STAGES>::THREADS, (TY <= 16 ? 2 : 1))
 heat_tma2_kernel(const __grid_constant__ CUtensorMap in_map, const HeatTma2Args<T> a) {
   using Tile = Tma2Tile<T, TY, STAGES>;
@@ -371,6 +368,30 @@ heat_tma2_kernel(const __grid_constant__ CUtensorMap in_map, const HeatTma2Args<
     // in x, so no cell of this warp is ever held and every store is in range
     const bool fast = own && gy0 > 0 && gy1 < a.n1 - 1 && tile_x > 0 && tile_x + W < a.n2;
 
+    // x-neighbours of a thread's group: the last cell of the lane to the left, the first of the lane to the right.
+    // Default (LDSX): one scalar LDS per neighbour -- a 4-way bank conflict (lanes are 4 words apart), which makes
+    // the shared-memory pipe the busiest unit (ncu: 81 % of its wavefront peak, l1tex 93 %).  The shuffle form
+    // (PH_HEAT_TB_CFG=8: neighbour lanes' registers, only lanes 0 / 31 read the adjacent tile's halo column)
+    // cuts the wavefronts by 26 % and the conflicts by 69 %, but costs 12 % more instructions (selects, the
+    // predicated edge loads) and the kernel is then issue-bound: 1.637 ms vs 1.568 ms on a (256, 2048, 2048)
+    // slab, 1182 vs 1220 Gcell/s sustained (profiles/r02_ncu_heat_shuffle_vs_lds.csv).  Measured, kept off.
+    const bool edge_lane = lane == 0 || lane == 31;
+    const int eoff = lane == 0 ? -1 : E;
+    auto x_neighbours = [&](const T* S, int o0, int o1, const G& c0v, const G& c1v, T& xl0, T& xr0, T& xl1, T& xr1) {
+      if constexpr (sizeof(T) == 4 && !LDSX) {
+        xl0 = __shfl_up_sync(0xffffffffu, c0v.v[E - 1], 1);
+        xr0 = __shfl_down_sync(0xffffffffu, c0v.v[0], 1);
+        xl1 = __shfl_up_sync(0xffffffffu, c1v.v[E - 1], 1);
+        xr1 = __shfl_down_sync(0xffffffffu, c1v.v[0], 1);
+        if (edge_lane) {
+          const T e0 = S[o0 + eoff], e1 = S[o1 + eoff];
+          if (lane == 0) { xl0 = e0; xl1 = e1; } else { xr0 = e0; xr1 = e1; }
+        }
+      } else {
+        xl0 = S[o0 - 1]; xr0 = S[o0 + E]; xl1 = S[o1 - 1]; xr1 = S[o1 + E];
+      }
+    };
+
     G a0[3], a1[3], b0[3], b1[3];                // rotating roles: [P, C, N] of time t (a) and time t+1 (b)
     a0[0] = *reinterpret_cast<const G*>(ringA + oa0);
     a1[0] = *reinterpret_cast<const G*>(ringA + oa1);
@@ -395,17 +416,18 @@ heat_tma2_kernel(const __grid_constant__ CUtensorMap in_map, const HeatTma2Args<
       {
         const G up0 = *reinterpret_cast<const G*>(Ac + oa0 - PITCH);
         const G dn1 = *reinterpret_cast<const G*>(Ac + oa1 + PITCH);
-        const T xl0 = Ac[oa0 - 1], xr0 = Ac[oa0 + E], xl1 = Ac[oa1 - 1], xr1 = Ac[oa1 + E];
+        T xl0, xr0, xl1, xr1;
+        x_neighbours(Ac, oa0, oa1, aC0, aC1, xl0, xr0, xl1, xr1);
         if constexpr (OWN && FAST) {
-          bN0 = heat_row<T, E, false>(aC0, aP0, aN0, up0, aC1, xl0, xr0, coeff, false, false);
-          bN1 = heat_row<T, E, false>(aC1, aP1, aN1, aC0, dn1, xl1, xr1, coeff, false, false);
+          bN0 = heat_row<T, E, false, X2>(aC0, aP0, aN0, up0, aC1, xl0, xr0, coeff, false, false);
+          bN1 = heat_row<T, E, false, X2>(aC1, aP1, aN1, aC0, dn1, xl1, xr1, coeff, false, false);
         } else {
           const bool plane_held = p <= a.fixed_lo || p >= a.fixed_hi;
           G dn0, up1;
           if constexpr (OWN) { dn0 = aC1; up1 = aC0; }
           else { dn0 = *reinterpret_cast<const G*>(Ac + oa0 + PITCH); up1 = *reinterpret_cast<const G*>(Ac + oa1 - PITCH); }
-          const G t0 = heat_row<T, E, true>(aC0, aP0, aN0, up0, dn0, xl0, xr0, coeff, fix_first, fix_last);
-          const G t1 = heat_row<T, E, true>(aC1, aP1, aN1, up1, dn1, xl1, xr1, coeff, fix_first, fix_last);
+          const G t0 = heat_row<T, E, true, X2>(aC0, aP0, aN0, up0, dn0, xl0, xr0, coeff, fix_first, fix_last);
+          const G t1 = heat_row<T, E, true, X2>(aC1, aP1, aN1, up1, dn1, xl1, xr1, coeff, fix_first, fix_last);
           bN0 = (plane_held || rowfix0) ? aC0 : t0;
           bN1 = (plane_held || rowfix1) ? aC1 : t1;
         }
@@ -418,15 +440,16 @@ heat_tma2_kernel(const __grid_constant__ CUtensorMap in_map, const HeatTma2Args<
         const T* Bq = ringB + (bsel ^ 1) * B_ELEMS;
         const G up0 = *reinterpret_cast<const G*>(Bq + ob0 - PITCH);
         const G dn1 = *reinterpret_cast<const G*>(Bq + ob1 + PITCH);
-        const T xl0 = Bq[ob0 - 1], xr0 = Bq[ob0 + E], xl1 = Bq[ob1 - 1], xr1 = Bq[ob1 + E];
+        T xl0, xr0, xl1, xr1;
+        x_neighbours(Bq, ob0, ob1, bC0, bC1, xl0, xr0, xl1, xr1);
         // MIR: output plane q = p-1 is one of the planes a neighbour slab keeps as ghosts -> the same group
         // also goes to that neighbour's memory over NVLink (a plain store through the peer mapping)
         auto mirror_delta = [&]() -> int64_t {
           return (p - 1 < a.mir.lo_end) ? a.mir.delta_lo : ((p - 1 >= a.mir.hi_begin) ? a.mir.delta_hi : 0);
         };
         if constexpr (FAST) {
-          const G res0 = heat_row<T, E, false>(bC0, bP0, bN0, up0, bC1, xl0, xr0, coeff, false, false);
-          const G res1 = heat_row<T, E, false>(bC1, bP1, bN1, bC0, dn1, xl1, xr1, coeff, false, false);
+          const G res0 = heat_row<T, E, false, X2>(bC0, bP0, bN0, up0, bC1, xl0, xr0, coeff, false, false);
+          const G res1 = heat_row<T, E, false, X2>(bC1, bP1, bN1, bC0, dn1, xl1, xr1, coeff, false, false);
           store_group<T, E>(p_out0, res0);
           store_group<T, E>(p_out1, res1);
           if constexpr (MIR) {
@@ -436,8 +459,8 @@ heat_tma2_kernel(const __grid_constant__ CUtensorMap in_map, const HeatTma2Args<
             }
           }
         } else {
-          const G t0 = heat_row<T, E, true>(bC0, bP0, bN0, up0, bC1, xl0, xr0, coeff, fix_first, fix_last);
-          const G t1 = heat_row<T, E, true>(bC1, bP1, bN1, bC0, dn1, xl1, xr1, coeff, fix_first, fix_last);
+          const G t0 = heat_row<T, E, true, X2>(bC0, bP0, bN0, up0, bC1, xl0, xr0, coeff, fix_first, fix_last);
+          const G t1 = heat_row<T, E, true, X2>(bC1, bP1, bN1, bC0, dn1, xl1, xr1, coeff, fix_first, fix_last);
           if (act0) store_group<T, E>(p_out0, rowfix0 ? bC0 : t0);
           if (act1) store_group<T, E>(p_out1, rowfix1 ? bC1 : t1);
           if constexpr (MIR) {
@@ -617,7 +640,7 @@ static int32_t heat_tma_launch(const T* in, T* out, int64_t n0, int64_t n1, int6
 }
 
 // two steps per pass; *used = false => caller runs two single steps instead
-template <typename T, int TY, int STAGES>
+template <typename T, int TY, int STAGES, bool X2 = false, bool LDSX = true>
 static int32_t heat_tma2_launch(const T* in, T* out, int64_t n0, int64_t n1, int64_t n2, T coeff, int64_t z_begin,
                                 int64_t z_end, int64_t fixed_lo, int64_t fixed_hi, cudaStream_t stream, bool* used,
                                 const HeatMirror* mir) {
@@ -664,11 +687,11 @@ static int32_t heat_tma2_launch(const T* in, T* out, int64_t n0, int64_t n1, int
   }
   static int attr_dev = -1;                         // function attributes are per device
   if (attr_dev != rt().device) {
-    PH_CUDA(cudaFuncSetAttribute(heat_tma2_kernel<T, TY, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tile::SMEM));
+    PH_CUDA(cudaFuncSetAttribute(heat_tma2_kernel<T, TY, STAGES, X2, LDSX>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tile::SMEM));
     attr_dev = rt().device;
   }
   dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)gz), block(Tile::THREADS);
-  heat_tma2_kernel<T, TY, STAGES><<<grid, block, Tile::SMEM, stream>>>(map, a);
+  heat_tma2_kernel<T, TY, STAGES, X2, LDSX><<<grid, block, Tile::SMEM, stream>>>(map, a);
   PH_LAUNCH_CHECK("heat_tma2_kernel");
   *used = true;
   return PH_OK;
@@ -694,6 +717,10 @@ int32_t heat_tma2_planes(const T* in, T* out, int64_t n0, int64_t n1, int64_t n2
     case 2: return heat_tma2_launch<T, 16, 8>(in, out, n0, n1, n2, coeff, z_begin, z_end, fixed_lo, fixed_hi, stream, used, mir);
     case 3: return heat_tma2_launch<T, 24, 5>(in, out, n0, n1, n2, coeff, z_begin, z_end, fixed_lo, fixed_hi, stream, used, mir);
     case 4: return heat_tma2_launch<T, 8, 6>(in, out, n0, n1, n2, coeff, z_begin, z_end, fixed_lo, fixed_hi, stream, used, mir);
+    case 5: return heat_tma2_launch<T, 16, 6, true>(in, out, n0, n1, n2, coeff, z_begin, z_end, fixed_lo, fixed_hi, stream, used, mir);   // packed f32x2 adds
+    case 6: return heat_tma2_launch<T, 16, 4, true>(in, out, n0, n1, n2, coeff, z_begin, z_end, fixed_lo, fixed_hi, stream, used, mir);
+    case 8: return heat_tma2_launch<T, 16, 6, false, false>(in, out, n0, n1, n2, coeff, z_begin, z_end, fixed_lo, fixed_hi, stream, used, mir);   // x-neighbours by warp shuffle (see x_neighbours)
+    case 7: return heat_tma2_launch<T, 24, 5, true>(in, out, n0, n1, n2, coeff, z_begin, z_end, fixed_lo, fixed_hi, stream, used, mir);   // one block per SM: no register cap
     default: return heat_tma2_launch<T, 16, 6>(in, out, n0, n1, n2, coeff, z_begin, z_end, fixed_lo, fixed_hi, stream, used, mir);
   }
 }

@@ -849,7 +849,14 @@ class DeviceNArray(_Indexable):
         self._buf = buf if buf is not None else _Buffer(max(1, self.size) * self.dtype.itemsize)
 
     def desc(self) -> PhDesc:
-        return PhDesc.contiguous(self.shape)
+        # built once per shape (a Python loop over the axes), handed out as a copy: callers edit descriptors
+        c = self.__dict__.get("_desc_cache")
+        if c is None or c[0] != self.shape:
+            c = (list(self.shape), PhDesc.contiguous(self.shape))
+            self.__dict__["_desc_cache"] = c
+        d = PhDesc()
+        C.memmove(C.byref(d), C.byref(c[1]), C.sizeof(PhDesc))
+        return d
 
     # ---- construction / transfer (explicit, never implicit) ------------------
     @classmethod
