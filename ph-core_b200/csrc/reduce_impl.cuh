@@ -531,7 +531,22 @@ __global__ void __launch_bounds__(RED_THREADS) ext_partial_kernel(const T* __res
   Cand<T> best;
   best.v = best_v;
   best.i = INT64_MAX;
-  if (best_t >= 0) {                                 // first register of the winning tile holding the extremum
+  // Only threads whose own extremum EQUALS the block's can hold the block's first extremum: the others skip the
+  // re-read of their winning tile (4 scattered 32-byte groups per thread, which DRAM serves as 128-byte lines:
+  // ~140 MB of extra reads per launch when every thread did it -- 13 % on a 1 GB array).
+  __shared__ T sh_bv[RED_THREADS / 32];
+  T block_v = best_v;
+  {
+    bool ignore = false;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) block_v = ext2<T, IS_MAX>(block_v, shfl_xor_t<T>(block_v, off), ignore);
+    if ((threadIdx.x & 31) == 0) sh_bv[threadIdx.x >> 5] = block_v;
+    __syncthreads();
+    block_v = sh_bv[0];
+#pragma unroll
+    for (int w = 1; w < RED_THREADS / 32; w++) block_v = ext2<T, IS_MAX>(block_v, sh_bv[w], ignore);
+  }
+  if (best_t >= 0 && best_v == block_v) {            // first register of the winning tile holding the extremum
     const int64_t base = tile_base(rows, best_t, tile) + (int64_t)threadIdx.x * E;      // where the tile lives
     const int64_t lbase = best_t * tile + (int64_t)threadIdx.x * E;                     // its LOGICAL (lex) index
     bool found = false;
@@ -741,19 +756,27 @@ __global__ void __launch_bounds__(32) axis_strip_staged_kernel(const T* __restri
     if (t < ntiles) issue(t);
     cp_async_commit();
   }
-  T acc = (RED == PH_SUM) ? (T)0 : ((RED == PH_MAX || RED == PH_ARGMAX) ? lowest_of<T>() : highest_of<T>());
-  int32_t arg = 0;
+  // A sum is ONE chain (the k order is the result).  Extrema are order-free, so they run as NA independent
+  // chains over rows k % NA and merge at the end (better value, then lower k): with ~3.5 warps per SM a single
+  // dependent compare-select chain per lane -- ~10 cycles per f64 element -- was the limit (0.82 of the peak).
+  constexpr bool IS_MAXLIKE = (RED == PH_MAX || RED == PH_ARGMAX);
+  constexpr int NA = (RED == PH_SUM) ? 1 : 4;
+  static_assert(KT % NA == 0, "a tile is a whole number of accumulator rounds");
+  T acc[NA];
+  int32_t arg[NA];
+#pragma unroll
+  for (int j = 0; j < NA; j++) { acc[j] = (RED == PH_SUM) ? (T)0 : (IS_MAXLIKE ? lowest_of<T>() : highest_of<T>()); arg[j] = INT32_MAX; }
   uint32_t err = 0;
   bool nan = false;
   const bool act = lane < ncols;
-  auto fold = [&](T v, int32_t kk) {
+  auto fold = [&](T v, int32_t kk, int j) {
     if constexpr (RED == PH_SUM) {
-      if constexpr (is_float_t<T>::value) acc = f_add(acc, v);
-      else acc = i_add<T>(acc, v, true, err);
+      if constexpr (is_float_t<T>::value) acc[0] = f_add(acc[0], v);
+      else acc[0] = i_add<T>(acc[0], v, true, err);
     } else {
       if constexpr (is_float_t<T>::value) nan |= (v != v);
-      const bool take = (RED == PH_MAX || RED == PH_ARGMAX) ? (v > acc) : (v < acc);
-      if (take) { acc = v; arg = kk; }
+      const bool take = IS_MAXLIKE ? (v > acc[j]) : (v < acc[j]);
+      if (take || arg[j] == INT32_MAX) { acc[j] = v; arg[j] = kk; }       // the chain's first element always enters
     }
   };
   for (int t = 0; t < ntiles; t++) {
@@ -766,16 +789,24 @@ __global__ void __launch_bounds__(32) axis_strip_staged_kernel(const T* __restri
     if (act) {
       if (k0 + KT <= K) {
 #pragma unroll
-        for (int r = 0; r < KT; r++) fold(ring[slot][r][mycol], (int32_t)(k0 + r));
+        for (int r = 0; r < KT; r++) fold(ring[slot][r][mycol], (int32_t)(k0 + r), r % NA);
       } else {
-        for (int r = 0; k0 + r < K; r++) fold(ring[slot][r][mycol], (int32_t)(k0 + r));
+        for (int r = 0; k0 + r < K; r++) fold(ring[slot][r][mycol], (int32_t)(k0 + r), 0);
       }
     }
     __syncwarp();                                           // the slot may be refilled
   }
   if (act) {
-    if constexpr (RED == PH_ARGMAX || RED == PH_ARGMIN) reinterpret_cast<int64_t*>(out)[o * inner + c0 + lane] = (int64_t)arg;
-    else reinterpret_cast<T*>(out)[o * inner + c0 + lane] = acc;
+    T best = acc[0];
+    int32_t barg = arg[0];
+#pragma unroll
+    for (int j = 1; j < NA; j++) {                    // first extremum: better value, then lower k (a zero keeps ITS sign)
+      const bool better = arg[j] != INT32_MAX &&
+                          (barg == INT32_MAX || (IS_MAXLIKE ? acc[j] > best : acc[j] < best) || (acc[j] == best && arg[j] < barg));
+      if (better) { best = acc[j]; barg = arg[j]; }
+    }
+    if constexpr (RED == PH_ARGMAX || RED == PH_ARGMIN) reinterpret_cast<int64_t*>(out)[o * inner + c0 + lane] = (int64_t)(barg == INT32_MAX ? 0 : barg);
+    else reinterpret_cast<T*>(out)[o * inner + c0 + lane] = best;
   }
   if (err) atomicOr(flags, err);
   if (nan) atomicOr(flags, (uint32_t)PH_FLAG_NAN);
@@ -1362,6 +1393,9 @@ static int32_t reduce_axis_launch(const T* x, void* out, int64_t outer, int64_t 
       if (can32 && E32 > 1 && cols / E32 >= (int64_t)r.sm_count * 64) e = E32;
       else if (can16 && E16 > 1 && cols / E16 >= (int64_t)r.sm_count * 64) e = E16;
       u = col_bytes * 4 >= (6LL << 20) ? 4 : 16;
+      // 8 groups in flight in 128-thread blocks: argmax 6.26 -> 6.70 TB/s, sum / max 6.64 / 6.59 -> 6.81 / 6.73 on
+      // [1000,1000,1000] f32 (256-thread blocks x 8 or x 16 are slower: 5.2 / 5.1 for argmax)
+      if (e == E32 && u == 4) { u = 8; block = 128; }
     } else if (col_bytes >= (3LL << 20) && can32 && E32 > 1) {
       e = E32; u = 8; block = 128;
     } else if (col_bytes >= (3LL << 19) && can32 && E32 > 1) {
