@@ -266,6 +266,91 @@ module Phase
       {% if T < Float %} T::INFINITY {% else %} T::MAX {% end %}
     end
 
+    # ---- `narr[region_literal]` (gather, src/multi_indexable.cr:338-356) across shards. A literal that leaves axis 0
+    # whole is local. Anything else re-splits the result over the ranks along ITS axis 0: every (source, destination)
+    # block is ONE strided descriptor over the source's rows -- an arithmetic progression -- and a contiguous row
+    # range of the destination, stored straight into its owner over NVLink (`ph_alltoall_strided`). `SlicePlan`
+    # below is the Crystal statement of `ph_slice_plan_of` (include/ph_host.h), the plan the C++ and Python layers
+    # call; they also carry the form without P2P (blocks gathered, `ph_alltoallv`, received in place).
+    def [](*literal) : ShardedNArray(T)
+      region = IndexRegion.new(literal.to_a, @shape)
+      whole = !region.degeneracy[0] && region.first[0] == 0 && region.stride[0] == 1 && region.proper_shape[0] == @shape[0]
+      if whole
+        rest = [..] + literal.to_a[1..]
+        rows = @row1 > @row0 ? @local[rest] : DeviceNArray(T).new([0] + region.shape[1..])
+        return ShardedNArray(T).new(region.shape, rows)
+      end
+      world, me = Comm.world, Comm.rank
+      plan = SlicePlan.new(@shape, region, world, me) # mirrors ph_slice_plan_of: send / land descriptors, recv ranges
+      new_shape = plan.new_shape
+      m0, m1 = Comm.shard_range(new_shape[0])
+      my_shape = [m1 - m0] + new_shape[1..]
+      unless world > 1 && Comm.p2p_ready?
+        raise RuntimeError.new("slicing the sharded axis needs peer-mapped memory in this layer (the Python and C++ layers carry the ph_alltoallv form)")
+      end
+      result = DeviceNArray(T).over(my_shape, Comm::SymmBuffer.new(Descriptor.element_count(my_shape) * sizeof(T))) # collective
+      sources = plan.send
+      targets = plan.land
+      Device.check LibPhGpu.ph_alltoall_strided(sizeof(T).to_i32, @local.dev.ptr, sources.to_unsafe, result.dev.ptr, targets.to_unsafe)
+      ShardedNArray(T).new(new_shape, result)
+    end
+
+    # Host plan of a slice across shards: the Crystal statement of `ph_slice_plan_of` (include/ph_host.h).
+    struct SlicePlan
+      getter new_shape : Array(Int32)
+      getter send : Array(LibPhGpu::Desc)
+      getter land : Array(LibPhGpu::Desc)
+
+      def initialize(shape : Array(Int32), region : IndexRegion, world : Int32, rank : Int32)
+        nd = shape.size
+        @new_shape = region.shape.map(&.to_i32)
+        kept = (0...nd).reject { |i| region.degeneracy[i] && region.drop }
+        lead = kept.first? # the result's leading axis; nil: every axis indexed (shape [1])
+        gstride = Array(Int64).new(nd, 1_i64)
+        (nd - 2).downto(0) { |i| gstride[i] = gstride[i + 1] * shape[i + 1] }
+        inner = (1...nd).sum(0_i64) { |i| region.first[i].to_i64 * gstride[i] }
+        f0, s0 = region.first[0].to_i64, region.stride[0].to_i64
+        rnk = @new_shape.size
+        blank = Descriptor.make(rnk, 0_i64, Descriptor.axes, Descriptor.axes)
+        @send = Array(LibPhGpu::Desc).new(world) { blank }
+        @land = Array(LibPhGpu::Desc).new(world) { blank }
+        my0, my1 = Comm.shard_range(shape[0], world, rank)
+        world.times do |q|
+          j0, j1 = Comm.shard_range(@new_shape[0], world, q)
+          next if my1 <= my0 || j1 <= j0
+          lo, hi = 0_i64, 0_i64
+          if lead != 0
+            lo, hi = j0.to_i64, j1.to_i64 if my0 <= f0 < my1
+          elsif s0 > 0
+            lo = {0_i64, -((-(my0 - f0)) // s0)}.max
+            hi = my1 - 1 >= f0 ? (my1 - 1 - f0) // s0 + 1 : 0_i64
+          else
+            t = -s0
+            lo = {0_i64, -((-(f0 - (my1 - 1))) // t)}.max
+            hi = f0 >= my0 ? (f0 - my0) // t + 1 : 0_i64
+          end
+          lo, hi = {lo, j0.to_i64}.max, {hi, j1.to_i64}.min
+          next if hi <= lo
+          offset = (lead == 0 ? f0 + s0 * lo - my0 : f0 - my0) * gstride[0] + inner
+          offset += region.stride[lead].to_i64 * lo * gstride[lead] if lead && lead > 0
+          extent, stride = Descriptor.axes, Descriptor.axes
+          if kept.empty?
+            extent[0] = 1_i64
+            stride[0] = 1_i64
+          end
+          kept.each_with_index do |axis, d|
+            extent[d] = axis == lead ? hi - lo : region.proper_shape[axis].to_i64
+            stride[d] = region.stride[axis].to_i64 * gstride[axis]
+          end
+          @send[q] = Descriptor.make(rnk, offset, extent, stride)
+          whole = Descriptor.contiguous([j1 - j0] + @new_shape[1..])
+          lext, lstr = whole.extent, whole.stride
+          lext[0] = hi - lo
+          @land[q] = Descriptor.make(rnk, (lo - j0) * lstr[0], lext, lstr)
+        end
+      end
+    end
+
     # ---- `MultiIndexable#permute` (src/multi_indexable.cr:795-803; no pattern = reversed axes) across shards.
     # The result is sharded along ITS axis 0 (old axis k = pattern[0]). `reuse`: an earlier P2P result of the
     # same shape whose peer-mapped storage receives the new one.

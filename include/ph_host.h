@@ -133,6 +133,28 @@ typedef struct ph_transpose_plan {
 int32_t ph_transpose_plan_of(const int64_t* shape, int32_t dims, const int32_t* pattern, int32_t world,
                              int32_t rank, ph_transpose_plan* plan, ph_transpose_peer* peers /* world entries */);
 
+/* Plan of `narr[region]` (gather, multi_indexable.cr:338-356) on an array sharded along axis 0 whose result is
+ * sharded along ITS axis 0.  local != 0: the region leaves axis 0 whole, every rank slices its own shard.  Otherwise
+ * the result's leading axis is the first axis the region does not drop -- axis 0 itself (its selected rows are
+ * re-split over the ranks) or, when axis 0 is ONE row, a later axis (the row's owner deals it out) -- and for every
+ * peer q (peers[q]):
+ *   send: the block this rank owes q as a strided view of ITS local shard (an arithmetic progression of its rows);
+ *   land: where that block lands in q's shard of the result (a contiguous range of q's rows);
+ *         both have the result's rank; extent 0 on every axis = nothing to send;
+ *   recv0..recv1: the rows of the result (global numbering) q holds for this rank.
+ * send / land are exactly the descriptor lists of ph_alltoall_strided. */
+typedef struct ph_slice_peer {
+  ph_desc send, land;
+  int64_t recv0, recv1;
+} ph_slice_peer;
+typedef struct ph_slice_plan {
+  int32_t local, dims;                 /* dims = rank of the result */
+  int64_t new_shape[PH_MAX_RANK];
+  int64_t my_new_rows[2];
+} ph_slice_plan;
+int32_t ph_slice_plan_of(const int64_t* shape, int32_t dims, const ph_region* region, int32_t world, int32_t rank,
+                         ph_slice_plan* plan, ph_slice_peer* peers /* world entries */);
+
 /* The sharded argmax / argmin: every rank contributes one 32-byte record to ph_allgather --
  * value @0 (one element of dtype, <= 8 bytes), LOCAL flat index of its first extremum @16 (int64, -1 = empty
  * shard), elements owned by lower ranks @24 (int64).  Picks the best value, then the lowest GLOBAL index

@@ -131,6 +131,61 @@ class ShardedNArray {
   DeviceNArray<T> min0() const { return over_shards(PH_MIN); }
   DeviceNArray<T> max0() const { return over_shards(PH_MAX); }
 
+  // ---- narr[region_literal] (gather, multi_indexable.cr:338-356) across shards -----------------------
+  // A literal that leaves axis 0 whole is local.  Anything else re-splits the result over the ranks along ITS
+  // axis 0 (ph_slice_plan_of): every (source, destination) block is ONE strided descriptor over the source's
+  // rows and a contiguous row range of the destination -- stored straight into its owner over NVLink with P2P
+  // (ph_alltoall_strided), gathered + ph_alltoallv (received in place) without.
+  ShardedNArray get_chunk(const RegionLiteral& lits) const {
+    const int32_t nd = (int32_t)shape_.size(), w = Comm::world(), me = Comm::rank();
+    IndexRegion reg(lits, shape_, true);
+    ph_slice_plan plan{};
+    std::vector<ph_slice_peer> peers((size_t)std::max(1, w));
+    Device::host_check(ph_slice_plan_of(shape_.data(), nd, &reg.r, w, me, &plan, peers.data()));
+    Shape new_shape(plan.new_shape, plan.new_shape + plan.dims);
+    if (plan.local) {
+      if (row1_ <= row0_) { Shape e = new_shape; e[0] = 0; return ShardedNArray(new_shape, DeviceNArray<T>(e)); }
+      RegionLiteral mine = lits;
+      mine[0] = all;
+      return ShardedNArray(new_shape, local_.get_chunk(mine));
+    }
+    Shape my_shape = new_shape;
+    my_shape[0] = plan.my_new_rows[1] - plan.my_new_rows[0];
+    if (w > 1 && Comm::p2p_ready()) {
+      DeviceNArray<T> res(my_shape, Comm::symm_buffer((size_t)shape_to_size(my_shape) * sizeof(T)));   // collective
+      std::vector<ph_desc> src((size_t)w), dst((size_t)w);
+      for (int32_t q = 0; q < w; q++) { src[(size_t)q] = peers[(size_t)q].send; dst[(size_t)q] = peers[(size_t)q].land; }
+      Device::check(ph_alltoall_strided((int32_t)sizeof(T), local_.data(), src.data(), res.data(), dst.data()));
+      return ShardedNArray(new_shape, res);
+    }
+    DeviceNArray<T> res(my_shape);
+    int64_t row = 1;
+    for (size_t i = 1; i < new_shape.size(); i++) row *= new_shape[i];
+    std::vector<DeviceNArray<T>> sends;
+    std::vector<const void*> sp((size_t)w, nullptr);
+    std::vector<void*> rp((size_t)w, nullptr);
+    std::vector<int64_t> sb((size_t)w, 0), rb((size_t)w, 0);
+    sends.reserve((size_t)w);
+    for (int32_t q = 0; q < w; q++) {
+      const ph_slice_peer& pq = peers[(size_t)q];
+      int64_t n = 1;
+      for (int i = 0; i < pq.send.rank; i++) n *= pq.send.extent[i];
+      if (n > 0) {
+        sends.push_back(DeviceView<T>(local_.buffer_owner(), pq.send, Shape(pq.send.extent, pq.send.extent + pq.send.rank)).to_narr());
+        sp[(size_t)q] = sends.back().data();
+        sb[(size_t)q] = n * (int64_t)sizeof(T);
+      }
+      if (pq.recv1 > pq.recv0 && row > 0) {
+        rp[(size_t)q] = res.data() + (pq.recv0 - plan.my_new_rows[0]) * row;
+        rb[(size_t)q] = (pq.recv1 - pq.recv0) * row * (int64_t)sizeof(T);
+      }
+    }
+    Device::check(ph_alltoallv(sp.data(), sb.data(), rp.data(), rb.data()));
+    Device::wait();                               // the gathered blocks are released when `sends` goes out of scope
+    return ShardedNArray(new_shape, res);
+  }
+  ShardedNArray operator[](const RegionLiteral& lits) const { return get_chunk(lits); }
+
   // ---- permute (MultiIndexable#permute multi_indexable.cr:795-803; default = reversed axes) ------
   // `reuse`: an earlier P2P result of the same shape whose (peer-mapped) storage receives the new result
   ShardedNArray permute(std::vector<int32_t> pattern = {}, const ShardedNArray* reuse = nullptr) const {

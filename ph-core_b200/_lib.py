@@ -60,6 +60,17 @@ class PhRegion(C.Structure):
         return [int(self.reduced_shape[i]) for i in range(self.reduced_rank)]
 
 
+class PhSlicePeer(C.Structure):
+    """struct ph_slice_peer (include/ph_host.h)"""
+    _fields_ = [("send", PhDesc), ("land", PhDesc), ("recv0", C.c_int64), ("recv1", C.c_int64)]
+
+
+class PhSlicePlan(C.Structure):
+    """struct ph_slice_plan (include/ph_host.h)"""
+    _fields_ = [("local", C.c_int32), ("dims", C.c_int32), ("new_shape", C.c_int64 * PH_MAX_RANK),
+                ("my_new_rows", C.c_int64 * 2)]
+
+
 class PhSlab(C.Structure):
     """struct ph_slab (include/ph_host.h)"""
     _fields_ = [("start", C.c_int64), ("stop", C.c_int64), ("count", C.c_int64), ("local_planes", C.c_int64),
@@ -186,6 +197,7 @@ def load() -> C.CDLL:
         "ph_shard_range": [i64, i32, i32, i64p, i64p],
         "ph_slab_layout": [i64, i32, i32, i32, C.POINTER(PhSlab)],
         "ph_transpose_plan_of": [i64p, i32, i32p, i32, i32, C.POINTER(PhTransposePlan), C.POINTER(PhTransposePeer)],
+        "ph_slice_plan_of": [i64p, i32, rp, i32, i32, C.POINTER(PhSlicePlan), C.POINTER(PhSlicePeer)],
         "ph_combine_extremum_records": [vp, i32, i32, i32, i32p, i64p],
     })
     for name, args in sig.items():

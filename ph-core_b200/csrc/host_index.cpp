@@ -480,6 +480,83 @@ int32_t ph_transpose_plan_of(const int64_t* shape, int32_t dims, const int32_t* 
   return PH_HOST_OK;
 }
 
+int32_t ph_slice_plan_of(const int64_t* shape, int32_t dims, const ph_region* reg, int32_t world, int32_t rank,
+                         ph_slice_plan* plan, ph_slice_peer* peers) {
+  if (!shape || !reg || !plan || dims <= 0 || dims > PH_MAX_RANK || reg->rank != dims || world <= 0 || rank < 0 || rank >= world)
+    return fail(PH_HOST_INVALID, "bad argument to ph_slice_plan_of");
+  memset(plan, 0, sizeof(*plan));
+  plan->dims = reg->reduced_rank;
+  for (int i = 0; i < reg->reduced_rank; i++) plan->new_shape[i] = reg->reduced_shape[i];
+  bool dropped[PH_MAX_RANK];
+  for (int i = 0; i < dims; i++) dropped[i] = reg->drop && reg->degeneracy[i];
+  if (!dropped[0] && reg->first[0] == 0 && reg->step[0] == 1 && reg->proper_shape[0] == shape[0]) { plan->local = 1; return PH_HOST_OK; }
+  if (!peers) return fail(PH_HOST_INVALID, "ph_slice_plan_of needs `world` peer entries for an exchanging plan");
+  int64_t gstride[PH_MAX_RANK];
+  int64_t acc = 1;
+  for (int i = dims - 1; i >= 0; i--) { gstride[i] = acc; acc *= shape[i]; }
+  int kept[PH_MAX_RANK], nkept = 0;
+  for (int i = 0; i < dims; i++) if (!dropped[i]) kept[nkept++] = i;
+  const int a = nkept ? kept[0] : -1;                 // the result's leading axis (-1: every axis indexed, shape [1])
+  const int rnk = reg->reduced_rank;
+  const int64_t n_new = plan->new_shape[0];
+  int64_t inner_off = 0;
+  for (int i = 1; i < dims; i++) inner_off += reg->first[i] * gstride[i];
+  const int64_t f0 = reg->first[0], s0 = reg->step[0];
+  // rows [lo, hi) of the result's leading axis that `dst` owns and whose data `src` holds
+  auto owned = [&](int src, int dst, int64_t* lo, int64_t* hi) {
+    int64_t r0, r1, j0, j1;
+    ph_shard_range(shape[0], world, src, &r0, &r1);
+    ph_shard_range(n_new, world, dst, &j0, &j1);
+    *lo = *hi = 0;
+    if (r1 <= r0 || j1 <= j0) return;
+    if (a != 0) { if (r0 <= f0 && f0 < r1) { *lo = j0; *hi = j1; } return; }
+    auto ceil_div64 = [](int64_t x, int64_t y) { return x >= 0 ? (x + y - 1) / y : -((-x) / y); };
+    int64_t l, h;
+    if (s0 > 0) {
+      l = std::max<int64_t>(0, ceil_div64(r0 - f0, s0));
+      h = (r1 - 1 >= f0) ? (r1 - 1 - f0) / s0 + 1 : 0;
+    } else {
+      const int64_t t = -s0;
+      l = std::max<int64_t>(0, ceil_div64(f0 - (r1 - 1), t));
+      h = (f0 >= r0) ? (f0 - r0) / t + 1 : 0;
+    }
+    l = std::max(l, j0);
+    h = std::min(h, j1);
+    if (h > l) { *lo = l; *hi = h; }
+  };
+  int64_t my0, my1;
+  ph_shard_range(shape[0], world, rank, &my0, &my1);
+  ph_shard_range(n_new, world, rank, &plan->my_new_rows[0], &plan->my_new_rows[1]);
+  for (int q = 0; q < world; q++) {
+    ph_slice_peer& p = peers[q];
+    memset(&p, 0, sizeof(p));
+    p.send.rank = p.land.rank = rnk;
+    owned(q, rank, &p.recv0, &p.recv1);
+    int64_t lo, hi;
+    owned(rank, q, &lo, &hi);
+    if (hi <= lo) continue;
+    int64_t off = (a == 0 ? f0 + s0 * lo - my0 : f0 - my0) * gstride[0] + inner_off;
+    if (a > 0) off += reg->step[a] * lo * gstride[a];
+    if (nkept == 0) { p.send.extent[0] = 1; p.send.stride[0] = 1; }
+    for (int d = 0; d < nkept; d++) {
+      const int i = kept[d];
+      p.send.extent[d] = (i == a) ? hi - lo : reg->proper_shape[i];
+      p.send.stride[d] = reg->step[i] * gstride[i];
+    }
+    p.send.offset = off;
+    int64_t j0, j1;
+    ph_shard_range(n_new, world, q, &j0, &j1);
+    int64_t dacc = 1;
+    for (int d = rnk - 1; d >= 0; d--) {
+      p.land.extent[d] = d == 0 ? hi - lo : plan->new_shape[d];
+      p.land.stride[d] = dacc;
+      dacc *= d == 0 ? j1 - j0 : plan->new_shape[d];
+    }
+    p.land.offset = (lo - j0) * p.land.stride[0];
+  }
+  return PH_HOST_OK;
+}
+
 int32_t ph_combine_extremum_records(const uint8_t* records, int32_t world, int32_t dtype, int32_t is_max,
                                     int32_t* winner_rank, int64_t* global_index) {
   if (!records || !winner_rank || !global_index || world <= 0) return fail(PH_HOST_INVALID, "bad argument to ph_combine_extremum_records");

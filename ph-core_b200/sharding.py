@@ -16,6 +16,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import K, check
+from .region import ALL as ALL_
 
 
 def _host_check(status: int) -> None:
@@ -86,6 +87,41 @@ def transpose_plan(shape: Sequence[int], pattern: Sequence[int], world: int, ran
         plan["send"].append((p.send0, p.send1)); plan["recv"].append((p.recv0, p.recv1))
         plan["send_shape"].append([int(p.send_shape[i]) for i in range(nd)])
         plan["recv_shape"].append([int(p.recv_shape[i]) for i in range(nd)])
+    return plan
+
+
+def slice_plan(shape: Sequence[int], literal: Sequence, world: int, rank: int) -> dict:
+    """Host plan of `narr[region_literal]` (IndexRegion.new, src/index_region.cr:192-224) on an array sharded along
+    axis 0, result sharded along ITS axis 0 (ph_slice_plan_of, include/ph_host.h -- the compiled host layers use the
+    same plan).  `local` = True when the literal leaves axis 0 whole (nothing moves).  Otherwise, for every peer q:
+      send[q] = (extents, strides, offset) of the block this rank owes q, as a strided view of ITS local shard
+                (element units; None when there is nothing) -- an arithmetic progression of its rows;
+      land[q] = (extents, strides, offset) of where that block lands in q's shard of the result (a contiguous
+                range of q's rows);
+      recv[q] = (j_lo, j_hi): the rows of the result (global numbering) q holds for this rank.
+    The leading axis of the result is the first axis the literal does not index with an Int: axis 0 itself (its
+    selected rows are re-split over the ranks) or, when axis 0 is ONE row, a later axis (the row's owner deals it out)."""
+    from .narray import make_region, host_check, _i64
+    shape = [int(v) for v in shape]
+    reg = make_region(list(literal), shape, True)                         # raises IndexError / DimensionError like the reference
+    plan_c = _lib.PhSlicePlan()
+    peers = (_lib.PhSlicePeer * max(1, int(world)))()
+    host_check(_lib.load().ph_slice_plan_of(_i64(shape), len(shape), C.byref(reg), int(world), int(rank), C.byref(plan_c), peers))
+    new_shape = [int(plan_c.new_shape[i]) for i in range(plan_c.dims)]
+    if plan_c.local:
+        return {"local": True, "new_shape": new_shape}
+    plan = {"local": False, "new_shape": new_shape, "my_new_rows": (int(plan_c.my_new_rows[0]), int(plan_c.my_new_rows[1])),
+            "send": [], "land": [], "recv": []}
+
+    def unpack(d):
+        n = d.rank
+        ext = [int(d.extent[i]) for i in range(n)]
+        return (ext, [int(d.stride[i]) for i in range(n)], int(d.offset)) if all(ext) else None
+
+    for q in range(world):
+        plan["send"].append(unpack(peers[q].send))
+        plan["land"].append(unpack(peers[q].land))
+        plan["recv"].append((int(peers[q].recv0), int(peers[q].recv1)))
     return plan
 
 
@@ -340,16 +376,112 @@ class ShardedNArray:
         self.local.set_mask(mask.local, self._peer(value))
 
     def __getitem__(self, key):
-        """Slicing that leaves axis 0 whole is local (the result stays sharded the same way)."""
+        """`narr[region_literal]` on the distributed array (gather, src/multi_indexable.cr:338-356, across
+        shards).  A literal that leaves axis 0 whole is local: the result stays sharded the same way.  Anything
+        else changes who owns what -- the result is sharded along ITS axis 0 -- and is one redistribution
+        (`slice_plan`): every (source rank, destination rank) block is an arithmetic progression of the source's
+        rows, i.e. ONE strided descriptor, and lands as a contiguous row range of the destination's shard.  With
+        peer-mapped memory the gather kernels store the blocks straight into their owners (ph_alltoall_strided,
+        one pass); otherwise the blocks are gathered locally and exchanged with ph_alltoallv, received in place."""
+        from .narray import DeviceNArray, DeviceView
+        from ._lib import PhDesc
         if not isinstance(key, tuple):
             key = (key,)
-        first = key[0] if key else None
-        whole = first is None or (hasattr(first, "begin") and first.begin is None and first.end is None
-                                  and not getattr(first, "exclusive", False))
-        if not whole:
-            raise NotImplementedError("slicing the sharded axis needs a redistribution: gather first (f-3 'next')")
-        loc = self.local.get_chunk(list(key))
-        return ShardedNArray([self.shape[0]] + loc.shape[1:], loc)
+        plan = slice_plan(self.shape, list(key), self.world, self.rank)
+        new_shape = plan["new_shape"]
+        if plan["local"]:
+            loc = self.local.get_chunk([ALL_] + list(key[1:])) if self.row1 > self.row0 else \
+                DeviceNArray([0] + new_shape[1:], self.dtype)
+            return ShardedNArray(new_shape, loc)
+        lib = _lib.load()
+        isz = self.dtype.itemsize
+        m0, m1 = plan["my_new_rows"]
+        my_shape = [m1 - m0] + new_shape[1:]
+        rnk = len(new_shape)
+        if self.world > 1 and p2p_ready() and not os.environ.get("PH_PERMUTE_NCCL"):
+            res = symm_empty(my_shape, self.dtype)                          # collective
+            srcs, dsts = (PhDesc * self.world)(), (PhDesc * self.world)()
+            for q in range(self.world):
+                sd, dd = plan["send"][q], plan["land"][q]
+                srcs[q] = PhDesc.make(*sd) if sd else PhDesc.make([0] * rnk, [0] * rnk, 0)
+                dsts[q] = PhDesc.make(*dd) if dd else PhDesc.make([0] * rnk, [0] * rnk, 0)
+            check(lib.ph_alltoall_strided(isz, self.local.ptr, srcs, res.ptr, dsts))
+            return ShardedNArray(new_shape, res)
+        res = DeviceNArray(my_shape, self.dtype)
+        row_bytes = int(np.prod(new_shape[1:], dtype=np.int64)) * isz
+        vp = C.c_void_p
+        sends, sp, sb, rp, rb = [], [], [], [], []
+        for q in range(self.world):
+            sd = plan["send"][q]
+            if sd:
+                blk = DeviceView(self.local._buf, PhDesc.make(*sd), list(sd[0]), self.dtype).to_narr()
+                sends.append(blk); sp.append(blk.ptr); sb.append(blk.size * isz)
+            else:
+                sp.append(None); sb.append(0)
+            lo, hi = plan["recv"][q]                                        # what q holds for me: a contiguous row range
+            rp.append(res.ptr + (lo - m0) * row_bytes if hi > lo else None)
+            rb.append((hi - lo) * row_bytes)
+        check(lib.ph_alltoallv((vp * self.world)(*sp), (C.c_int64 * self.world)(*sb), (vp * self.world)(*rp), (C.c_int64 * self.world)(*rb)))
+        del sends
+        return ShardedNArray(new_shape, res)
+
+    def set_chunk(self, literal: Sequence, value) -> None:
+        """`narr[region_literal] = value` across shards (scatter / fill, src/multi_writable.cr:55-84).  A scalar
+        fills this rank's part of the region (no exchange).  A ShardedNArray of the region's shape is the gather
+        run backwards with the same plan: the rows of `value` this rank holds leave as contiguous blocks
+        (ph_alltoallv) and every block received is scattered into the arithmetic progression of local rows it
+        belongs to (one strided copy per peer)."""
+        from .narray import DeviceNArray, ShapeError
+        from ._lib import PhDesc
+        literal = list(literal)
+        plan = slice_plan(self.shape, literal, self.world, self.rank)
+        lib = _lib.load()
+        isz = self.dtype.itemsize
+        if isinstance(value, ShardedNArray):
+            if value.shape != plan["new_shape"]:                       # multi_writable.cr:58-60
+                raise ShapeError(f"Cannot substitute: the given array has shape {value.shape}, but the region has "
+                                 f"shape {plan['new_shape']}.")
+            if value.dtype != self.dtype:
+                raise TypeError("device path: source and destination must share a dtype")
+            if plan["local"]:
+                if self.row1 > self.row0:
+                    self.local.set_chunk([ALL_] + literal[1:], value.local)
+                return
+            m0, _ = plan["my_new_rows"]
+            row_bytes = int(np.prod(plan["new_shape"][1:], dtype=np.int64)) * isz
+            vp = C.c_void_p
+            temps, sp, sb, rp, rb = [], [], [], [], []
+            for q in range(self.world):
+                lo, hi = plan["recv"][q]                               # rows of `value` I hold that q's shard receives
+                sp.append(value.local.ptr + (lo - m0) * row_bytes if hi > lo and row_bytes else None)
+                sb.append((hi - lo) * row_bytes if hi > lo else 0)
+                sd = plan["send"][q]                                   # where q's rows land in MY shard
+                t = DeviceNArray(list(sd[0]), self.dtype) if sd else None
+                temps.append(t)
+                rp.append(t.ptr if t is not None else None)
+                rb.append(t.size * isz if t is not None else 0)
+            check(lib.ph_alltoallv((vp * self.world)(*sp), (C.c_int64 * self.world)(*sb), (vp * self.world)(*rp), (C.c_int64 * self.world)(*rb)))
+            for q, t in enumerate(temps):
+                if t is not None:
+                    d = PhDesc.make(*plan["send"][q])
+                    check(lib.ph_copy_strided(isz, t.ptr, C.byref(t.desc()), self.local.ptr, C.byref(d)))
+            return
+        scalar = np.array(value, dtype=self.dtype)
+        if plan["local"]:
+            if self.row1 > self.row0:
+                self.local.set_chunk([ALL_] + literal[1:], value)
+            return
+        for q in range(self.world):                                    # my cells of the region, one block per destination
+            sd = plan["send"][q]
+            if sd:
+                d = PhDesc.make(*sd)
+                check(lib.ph_fill_region(isz, self.local.ptr, C.byref(d), scalar.ctypes.data))
+
+    def __setitem__(self, key, value) -> None:
+        if isinstance(key, ShardedNArray):                             # narr[mask] = value
+            self.set_mask(key, value)
+            return
+        self.set_chunk(list(key) if isinstance(key, tuple) else [key], value)
 
     # ---- transposes across shards: the one real exchange step (all-to-all) --------------------
     def permute(self, *pattern, out: Optional["ShardedNArray"] = None) -> "ShardedNArray":

@@ -187,6 +187,29 @@ int main() {
     EXPECT(t4.shape() == Shape({1, 3 * world}) && t4.to_global() == m4);
     EXPECT(t4.permute().to_global() == m4);
   });
+  it("slicing across shards (multi_indexable.cr:338-356): ranges, steps, reversal, an Int on the sharded axis", [&] {
+    // host gather: out[j, y, x] = g[f0 + s0 * j, y0 + sy * y, x]
+    auto host_slice = [&](int64_t f0, int64_t s0, int64_t n0, int64_t y0, int64_t sy, int64_t ny) {
+      V<float> out;
+      for (int64_t j = 0; j < n0; j++)
+        for (int64_t y = 0; y < ny; y++)
+          for (int64_t x = 0; x < gs[2]; x++) out.push_back(g[(size_t)(((f0 + s0 * j) * gs[1] + (y0 + sy * y)) * gs[2] + x)]);
+      return out;
+    };
+    auto a = sg[{range(2, 4 * world)}];
+    EXPECT(a.shape() == Shape({4 * world - 1, 12, 10}) && a.to_global() == host_slice(2, 1, 4 * world - 1, 0, 1, 12));
+    auto b = sg[{range(nil, -1, nil), range(1, 2, 9)}];                      // rows reversed, every 2nd column-row
+    EXPECT(b.shape() == Shape({gs[0], 5, 10}) && b.to_global() == host_slice(gs[0] - 1, -1, gs[0], 1, 2, 5));
+    auto c = sg[{range(1, 3, nil)}];
+    EXPECT(c.to_global() == host_slice(1, 3, (gs[0] - 1 - 1) / 3 + 1, 0, 1, 12));
+    auto d = sg[{5, range(nil, -1, nil)}];                                   // ONE row of the sharded axis: its owner deals it out
+    EXPECT(d.shape() == Shape({12, 10}) && d.to_global() == host_slice(5, 1, 1, 11, -1, 12));
+    auto e = sg[{6 * world + 1, 3, 2}];                                      // every axis indexed: shape [1]
+    EXPECT(e.shape() == Shape({1}) && e.to_global() == V<float>{g[(size_t)(((6 * world + 1) * 12 + 3) * 10 + 2)]});
+    auto f = sg[{all, range(1, 3)}];                                         // axis 0 whole: local
+    EXPECT(f.shape() == Shape({gs[0], 3, 10}) && f.to_global() == host_slice(0, 1, gs[0], 1, 1, 3));
+    EXPECT_RAISES(IndexError, sg[{range(0, gs[0])}]);
+  });
   it("masked store on the distributed array (n_array.cr:510-551)", [&] {
     auto a = ShardedNArray<float>::from_global(gs, g);
     a.set_mask(a > sh, 0.0f);

@@ -234,6 +234,32 @@ def run_checks(world: int, rank: int, soft: bool = False) -> dict:
     t3 = S.ShardedNArray.from_global(m3).permute()
     _chk(t3.shape == [1, 3 * world] and t3.to_global().tobytes() == np.ascontiguousarray(m3.T).tobytes(), "tests/mgpu_check.py:216")
     _chk(t3.permute().to_global().tobytes() == m3.tobytes(), "tests/mgpu_check.py:217")
+    # slicing ACROSS shards (the result is re-split over the ranks): ranges, steps, reversal, an Int on the sharded axis
+    for lit, npkey in (((ph.rng(2, 4 * world),), np.s_[2:4 * world + 1]), ((ph.rng(None, None, -1), ph.rng(1, 9, 2)), np.s_[::-1, 1:10:2]),
+                       ((ph.rng(1, None, 3), ph.ALL, 4), np.s_[1::3, :, 4]), ((5, ph.rng(None, None, -1)), np.s_[5, ::-1]),
+                       ((6 * world + 1, 3, 2), np.s_[6 * world + 1, 3, 2])):
+        got = sg[lit]
+        want = np.asarray(g[npkey])
+        want = np.ascontiguousarray(want.reshape(want.shape if want.ndim else (1,)))
+        _chk(got.shape == list(want.shape) and got.to_global().tobytes() == want.tobytes(), f"sharded slice {lit}")
+    # ... and the scatter / fill twins: `narr[region] = sharded array | scalar` (the gather plan run backwards)
+    for lit, npkey in (((ph.rng(2, 4 * world),), np.s_[2:4 * world + 1]), ((ph.rng(None, None, -1), ph.rng(1, 9, 2)), np.s_[::-1, 1:10:2]),
+                       ((ph.rng(1, None, 3), ph.ALL, 4), np.s_[1::3, :, 4]), ((5, ph.rng(None, None, -1)), np.s_[5, ::-1]),
+                       ((ph.ALL, 7), np.s_[:, 7])):
+        dst_h = g.copy()
+        src_h = np.ascontiguousarray(rs.randint(-8, 9, size=np.asarray(dst_h[npkey]).shape).astype(np.float32))
+        dst = S.ShardedNArray.from_global(g)
+        dst[lit] = S.ShardedNArray.from_global(src_h)
+        dst_h[npkey] = src_h
+        _chk(dst.to_global().tobytes() == dst_h.tobytes(), f"sharded scatter {lit}")
+        dst[lit] = 2.5
+        dst_h[npkey] = np.float32(2.5)
+        _chk(dst.to_global().tobytes() == dst_h.tobytes(), f"sharded fill {lit}")
+    try:
+        S.ShardedNArray.from_global(g)[(ph.rng(0, 1),)] = S.ShardedNArray.from_global(g)
+        _chk(False, "a source of the wrong shape must raise ShapeError")
+    except ph.ShapeError:
+        pass
     sg.set_mask(sg > sh, 0.0)
     _chk(sg.to_global().tobytes() == np.where(g > h, np.float32(0), g).tobytes(), "tests/mgpu_check.py:219")
     return {"ok": not _FAILED, "failed": list(_FAILED), "checks": _CHECKS, "world": world, "p2p": bool(p2p),
