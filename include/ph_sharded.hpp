@@ -186,6 +186,58 @@ class ShardedNArray {
   }
   ShardedNArray operator[](const RegionLiteral& lits) const { return get_chunk(lits); }
 
+  // ---- narr[region_literal] = value (scatter / fill, multi_writable.cr:55-84) across shards -------------
+  // A scalar fills this rank's cells of the region (no exchange).  An array source of the region's shape is the
+  // gather run backwards with the same plan: the rows of `src` this rank holds leave as contiguous blocks
+  // (ph_alltoallv), every block received is scattered into the arithmetic progression of local rows it belongs to.
+  void set_chunk(const RegionLiteral& lits, type_identity_t<T> value) {
+    ph_slice_plan plan{};
+    std::vector<ph_slice_peer> peers = slice_plan(lits, &plan);
+    if (plan.local) {
+      if (row1_ > row0_) { RegionLiteral mine = lits; mine[0] = all; local_.set_chunk(mine, value); }
+      return;
+    }
+    for (const ph_slice_peer& pq : peers)
+      if (desc_elems(pq.send) > 0) Device::check(ph_fill_region((int32_t)sizeof(T), local_.data(), &pq.send, &value));
+  }
+  void set_chunk(const RegionLiteral& lits, const ShardedNArray& src) {
+    ph_slice_plan plan{};
+    std::vector<ph_slice_peer> peers = slice_plan(lits, &plan);
+    Shape new_shape(plan.new_shape, plan.new_shape + plan.dims);
+    if (src.shape_ != new_shape)   // multi_writable.cr:58-60
+      throw ShapeError("Cannot substitute: the given array has shape " + shape_str(src.shape_) + ", but the region has shape " + shape_str(new_shape) + ".");
+    if (plan.local) {
+      if (row1_ > row0_) { RegionLiteral mine = lits; mine[0] = all; local_.set_chunk(mine, src.local_); }
+      return;
+    }
+    const int32_t w = Comm::world();
+    int64_t row = 1;
+    for (size_t i = 1; i < new_shape.size(); i++) row *= new_shape[i];
+    std::vector<DeviceNArray<T>> temps;
+    std::vector<int32_t> from;
+    std::vector<const void*> sp((size_t)w, nullptr);
+    std::vector<void*> rp((size_t)w, nullptr);
+    std::vector<int64_t> sb((size_t)w, 0), rb((size_t)w, 0);
+    temps.reserve((size_t)w);
+    for (int32_t q = 0; q < w; q++) {
+      const ph_slice_peer& pq = peers[(size_t)q];
+      if (pq.recv1 > pq.recv0 && row > 0) {                      // rows of `src` I hold that q's shard receives
+        sp[(size_t)q] = src.local_.data() + (pq.recv0 - plan.my_new_rows[0]) * row;
+        sb[(size_t)q] = (pq.recv1 - pq.recv0) * row * (int64_t)sizeof(T);
+      }
+      if (desc_elems(pq.send) > 0) {                              // where q's rows land in MY shard
+        temps.push_back(DeviceNArray<T>(Shape(pq.send.extent, pq.send.extent + pq.send.rank)));
+        from.push_back(q);
+        rp[(size_t)q] = temps.back().data();
+        rb[(size_t)q] = desc_elems(pq.send) * (int64_t)sizeof(T);
+      }
+    }
+    Device::check(ph_alltoallv(sp.data(), sb.data(), rp.data(), rb.data()));
+    for (size_t i = 0; i < temps.size(); i++)
+      Device::check(ph_copy_strided((int32_t)sizeof(T), temps[i].data(), &temps[i].desc(), local_.data(), &peers[(size_t)from[i]].send));
+    Device::wait();                               // the temporaries die with this scope
+  }
+
   // ---- permute (MultiIndexable#permute multi_indexable.cr:795-803; default = reversed axes) ------
   // `reuse`: an earlier P2P result of the same shape whose (peer-mapped) storage receives the new result
   ShardedNArray permute(std::vector<int32_t> pattern = {}, const ShardedNArray* reuse = nullptr) const {
@@ -278,6 +330,13 @@ class ShardedNArray {
   int64_t row0_ = 0, row1_ = 0;
   template <class U> friend class ShardedNArray;
 
+  static int64_t desc_elems(const ph_desc& d) { int64_t n = 1; for (int i = 0; i < d.rank; i++) n *= d.extent[i]; return d.rank ? n : 0; }
+  std::vector<ph_slice_peer> slice_plan(const RegionLiteral& lits, ph_slice_plan* plan) const {
+    IndexRegion reg(lits, shape_, true);
+    std::vector<ph_slice_peer> peers((size_t)std::max(1, Comm::world()));
+    Device::host_check(ph_slice_plan_of(shape_.data(), (int32_t)shape_.size(), &reg.r, Comm::world(), Comm::rank(), plan, peers.data()));
+    return peers;
+  }
   static int64_t row_elems(const Shape& s) { int64_t n = 1; for (size_t i = 1; i < s.size(); i++) n *= s[i]; return n; }
   static int64_t count(const int64_t* ext, int32_t nd) { int64_t n = 1; for (int32_t i = 0; i < nd; i++) n *= ext[i]; return n; }
   ShardedNArray wrap(DeviceNArray<T> l) const { return ShardedNArray(shape_, std::move(l)); }

@@ -210,6 +210,27 @@ int main() {
     EXPECT(f.shape() == Shape({gs[0], 3, 10}) && f.to_global() == host_slice(0, 1, gs[0], 1, 1, 3));
     EXPECT_RAISES(IndexError, sg[{range(0, gs[0])}]);
   });
+  it("scatter / fill across shards (multi_writable.cr:55-84): the gather plan run backwards", [&] {
+    // rows reversed, every 2nd column-row <- a sharded source of that shape; then a scalar into a stepped range
+    const Shape ss = {gs[0], 5, 10};
+    const V<float> src = ints<float>(shape_to_size(ss));
+    auto dst = ShardedNArray<float>::from_global(gs, g);
+    dst.set_chunk({range(nil, -1, nil), range(1, 2, 9)}, ShardedNArray<float>::from_global(ss, src));
+    V<float> want = g;
+    for (int64_t j = 0; j < gs[0]; j++)
+      for (int64_t y = 0; y < 5; y++)
+        for (int64_t x = 0; x < 10; x++) want[(size_t)(((gs[0] - 1 - j) * 12 + (1 + 2 * y)) * 10 + x)] = src[(size_t)((j * 5 + y) * 10 + x)];
+    EXPECT(dst.to_global() == want);
+    dst.set_chunk({range(1, 3, nil), all, 4}, 2.5f);
+    for (int64_t r = 1; r < gs[0]; r += 3)
+      for (int64_t y = 0; y < 12; y++) want[(size_t)((r * 12 + y) * 10 + 4)] = 2.5f;
+    EXPECT(dst.to_global() == want);
+    const V<float> rowsrc = ints<float>(12 * 10);
+    dst.set_chunk({5}, ShardedNArray<float>::from_global({12, 10}, rowsrc));      // ONE row of the sharded axis
+    for (int64_t i = 0; i < 120; i++) want[(size_t)(5 * 120 + i)] = rowsrc[(size_t)i];
+    EXPECT(dst.to_global() == want);
+    EXPECT_RAISES(ShapeError, dst.set_chunk({range(0, 1)}, ShardedNArray<float>::from_global(gs, g)));
+  });
   it("masked store on the distributed array (n_array.cr:510-551)", [&] {
     auto a = ShardedNArray<float>::from_global(gs, g);
     a.set_mask(a > sh, 0.0f);
