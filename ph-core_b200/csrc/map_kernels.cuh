@@ -33,6 +33,7 @@ struct MapArgs {
   int all_array;            // every input is OPND_ARRAY
   uint32_t period;          // flat: OPND_PERIODIC operands repeat every `period` elements (0 = none)
   int reverse;              // flat: visit the tiles from the last to the first (see launch_flat)
+  int l2_hint;              // flat: 1 = inputs evict_first; 2 = + results evict_last in L2 (see launch_flat)
   int64_t gx;               // rows: number of column tiles (1-D grid = gx * slabs * chunks)
   uint32_t chunks;          // rows: row chunks of the last outer axis per slab
   uint32_t slabs;           // rows: product of the leading outer extents
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(MAP_THREADS) map_flat_kernel(const MapArgs<F::
     else scalar[k] = In();
   }
 
+  const bool hint_in = a.l2_hint >= 1, hint_out = a.l2_hint >= 2;
   if (base + tile <= a.n) {
     Group<In, E> x[UNROLL][NIN];
     if (a.all_array) {                       // hot path: no per-operand predicates
@@ -82,7 +84,7 @@ __global__ void __launch_bounds__(MAP_THREADS) map_flat_kernel(const MapArgs<F::
       for (int u = 0; u < UNROLL; u++) {
         const int64_t idx = base + ((int64_t)u * MAP_THREADS + threadIdx.x) * E;
 #pragma unroll
-        for (int k = 0; k < NIN; k++) x[u][k] = load_group<In, E>(reinterpret_cast<const In*>(a.in[k]) + idx);
+        for (int k = 0; k < NIN; k++) x[u][k] = load_group_hint<In, E>(reinterpret_cast<const In*>(a.in[k]) + idx, hint_in);
       }
     } else {
 #pragma unroll
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(MAP_THREADS) map_flat_kernel(const MapArgs<F::
         if (a.period) pcol = (a.n >> 32) ? (uint32_t)(idx % (int64_t)a.period) : (uint32_t)idx % a.period;
 #pragma unroll
         for (int k = 0; k < NIN; k++) {
-          if (a.mode[k] == OPND_ARRAY) x[u][k] = load_group<In, E>(reinterpret_cast<const In*>(a.in[k]) + idx);
+          if (a.mode[k] == OPND_ARRAY) x[u][k] = load_group_hint<In, E>(reinterpret_cast<const In*>(a.in[k]) + idx, hint_in);
           else if (a.mode[k] == OPND_PERIODIC) x[u][k] = load_group_plain<In, E>(reinterpret_cast<const In*>(a.in[k]) + pcol);
           else x[u][k] = splat_group<In, E>(scalar[k]);
         }
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(MAP_THREADS) map_flat_kernel(const MapArgs<F::
       const int64_t idx = base + ((int64_t)u * MAP_THREADS + threadIdx.x) * E;
       Group<Out, E> y;
       apply_group<F, E>(x[u], y, err);
-      store_group<Out, E>(out + idx, y);
+      store_group_hint<Out, E>(out + idx, y, hint_out);
     }
   } else {
     for (int64_t i = base + threadIdx.x; i < a.n; i += MAP_THREADS) {
@@ -242,6 +244,8 @@ inline int32_t launch_flat(MapArgs<F::NIN>& a) {
   if (blocks > 0x7fffffffLL) return set_error(PH_ERR_INVALID, "array too large for one launch");
   static const bool alternate = getenv("PH_FLAT_NO_ALTERNATE") == nullptr;
   a.reverse = alternate ? (int)(rt().flat_launches++ & 1) : 0;
+  static const int l2_hint = getenv("PH_FLAT_L2_HINT") ? atoi(getenv("PH_FLAT_L2_HINT")) : 0;     // A/B knob (see ld_stream_evict_first)
+  a.l2_hint = l2_hint;
   map_flat_kernel<F, E, UNROLL><<<(unsigned)blocks, MAP_THREADS, 0, rt().stream>>>(a);
   PH_LAUNCH_CHECK("map_flat_kernel");
   return PH_OK;

@@ -167,6 +167,42 @@ template <typename T, int N>
 __device__ __forceinline__ void store_group(T* p, const Group<T, N>& g) {
   st_stream<Group<T, N>::BYTES>(p, g.raw);
 }
+// L2 eviction priorities for CHAINED elementwise launches (map_flat_kernel): inputs are read once -> evict_first
+// (SASS LDG.E.NA.EFL2), results are what the next operator of a fluent expression reads -> evict_last (STG ... ELL2).
+// A consumed line that was hit with evict_first becomes the first victim, so the part of a temporary still waiting in
+// L2 is not pushed out by the consumer's own output.  `hint` is launch-uniform.
+template <int BYTES>
+__device__ __forceinline__ RawVec<BYTES> ld_stream_evict_first(const void* p) {
+  RawVec<BYTES> r;
+  if constexpr (BYTES == 32) {
+    asm("ld.global.L1::no_allocate.L2::evict_first.v4.b64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(r.q[0]), "=l"(r.q[1]), "=l"(r.q[2]), "=l"(r.q[3]) : "l"(p));
+  } else {                                   // the .L2::evict_* qualifiers exist for 256-bit accesses only
+    r = ld_stream<BYTES>(p);
+  }
+  return r;
+}
+template <int BYTES>
+__device__ __forceinline__ void st_stream_evict_last(void* p, const RawVec<BYTES>& r) {
+  if constexpr (BYTES == 32) {
+    asm volatile("st.global.L1::no_allocate.L2::evict_last.v4.b64 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "l"(r.q[0]), "l"(r.q[1]), "l"(r.q[2]), "l"(r.q[3]) : "memory");
+  } else {
+    st_stream<BYTES>(p, r);
+  }
+}
+template <typename T, int N>
+__device__ __forceinline__ Group<T, N> load_group_hint(const T* p, bool hint) {
+  Group<T, N> g;
+  if (hint) g.raw = ld_stream_evict_first<Group<T, N>::BYTES>(p);
+  else g.raw = ld_stream<Group<T, N>::BYTES>(p);
+  return g;
+}
+template <typename T, int N>
+__device__ __forceinline__ void store_group_hint(T* p, const Group<T, N>& g, bool hint) {
+  if (hint) st_stream_evict_last<Group<T, N>::BYTES>(p, g.raw);
+  else st_stream<Group<T, N>::BYTES>(p, g.raw);
+}
 template <typename T, int N>
 __device__ __forceinline__ Group<T, N> splat_group(T x) {
   Group<T, N> g;

@@ -118,6 +118,40 @@ def _worker(rank, world, port, out_dir):
                 sl = [slice(None)] * 3; sl[j] = slice(p0, p1)
                 res[tuple(sl)] = bufs[q].numpy()
         np.save(os.path.join(out_dir, f"perm_{''.join(map(str, pat))}_{rank}.npy"), res)
+    # ---- slicing across shards: the plan of ShardedNArray#[] (ph_slice_plan_of) driven with numpy strided views,
+    #      gloo send/recv standing in for the peer stores of ph_alltoall_strided
+    from ph_core_b200 import rng, ALL
+    r0, r1 = S.shard_range(tsrc.shape[0], world, rank)
+    mine = np.ascontiguousarray(tsrc[r0:r1]).reshape(-1)
+    for tag, lit in (("rev", [rng(None, None, -1), rng(0, None, 2)]), ("step", [rng(1, None, 2), ALL, 3]), ("row", [5, rng(None, None, -1)])):
+        plan = S.slice_plan(tsrc.shape, lit, world, rank)
+        m0, m1 = plan["my_new_rows"]
+        res = np.full([m1 - m0] + plan["new_shape"][1:], -1, np.int32)
+        flat = res.reshape(-1)
+        reqs, inbox = [], {}
+        for q in range(world):
+            sd = plan["send"][q]
+            blk = None
+            if sd:
+                ext, strd, off = sd
+                blk = np.array([mine[off + sum(c * t for c, t in zip(idx, strd))] for idx in np.ndindex(*ext)], np.int32).reshape(ext)
+            lo, hi = plan["recv"][q]
+            if q == rank:
+                inbox[q] = blk
+            else:
+                if blk is not None:
+                    reqs.append(dist.isend(torch.from_numpy(blk.copy()), q))
+                if hi > lo:
+                    inbox[q] = torch.zeros([hi - lo] + plan["new_shape"][1:], dtype=torch.int32)
+                    reqs.append(dist.irecv(inbox[q], q))
+        for rq in reqs:
+            rq.wait()
+        for q in range(world):
+            lo, hi = plan["recv"][q]
+            if hi > lo:
+                got = inbox[q] if isinstance(inbox[q], np.ndarray) else inbox[q].numpy()
+                res[lo - m0:hi - m0] = got.reshape([hi - lo] + plan["new_shape"][1:])
+        np.save(os.path.join(out_dir, f"slice_{tag}_{rank}.npy"), res)
     # ---- reductions over axis-0 shards
     data = rs.randint(-8, 9, size=(10, 7)).astype(np.float32)
     data[3, 2] = data[8, 1] = 50.0                                 # tie across the two shards
@@ -157,6 +191,9 @@ def test_two_rank_partitioning(tmp_path):
     for pat in ([2, 1, 0], [1, 0, 2], [2, 0, 1], [0, 2, 1]):
         got = np.concatenate([np.load(tmp_path / f"perm_{''.join(map(str, pat))}_{r}.npy") for r in range(world)])
         assert got.tobytes() == np.ascontiguousarray(tsrc.transpose(pat)).tobytes(), pat
+    for tag, key in (("rev", np.s_[::-1, ::2]), ("step", np.s_[1::2, :, 3]), ("row", np.s_[5, ::-1])):
+        got = np.concatenate([np.load(tmp_path / f"slice_{tag}_{r}.npy") for r in range(world)])
+        assert got.tobytes() == np.ascontiguousarray(tsrc[key]).tobytes(), tag
     data = rs.randint(-8, 9, size=(10, 7)).astype(np.float32)
     data[3, 2] = data[8, 1] = 50.0
     for r in range(world):
