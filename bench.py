@@ -51,10 +51,11 @@ METRIC = "f32 elementwise HBM GB/s"   # BASELINE.json metric, first clause (the 
 WORKLOAD = ("elementwise a*b+c, b=[1,8192] row-vector broadcast, 8192x8192 f32 "
             "(two reference-faithful kernels)")
 # dram__bytes_read.sum + dram__bytes_write.sum of one `out = t + c` launch of this very command,
-# captured in ONE ncu pass with the caches left alone (profiles/r01_bench_dram_warm.csv):
-# 504.0 MB read (33 MB of the temporary come from L2) + 273.3 MB written.  The cold-cache
-# `--set full` capture (profiles/r01_ncu_bench_kernels.csv) reads 536.9 MB = the algorithmic bytes.
-NCU_TRAFFIC_ADD = 777292032
+# captured in ONE ncu pass with the caches left alone (profiles/r02_bench_dram_warm.csv):
+# 477.6 MB read (59 MB of the temporary come from L2: alternating traversal + L2 eviction priorities;
+# round 1 without the priorities: 504.0 MB) + 269.8 MB written.  The cold-cache `--set full` capture
+# (profiles/r01_ncu_bench_kernels.csv) reads 536.9 MB = the algorithmic bytes.
+NCU_TRAFFIC_ADD = 747322368
 
 
 def measured_peak():
@@ -418,14 +419,15 @@ def run_ours(args):
                        "parallelism": f"axis0-shard x{world}, no collective",
                        "l2": "no flush: each 256 MiB operand exceeds the 126 MB L2; consecutive launches traverse in opposite "
                              "directions, so `t + c` finds the last-written part of the temporary t in L2 "
-                             "(3.7 % of that kernel's time; PH_FLAT_NO_ALTERNATE=1 gives 6653 GB/s instead of 6798)",
+                             "(3.7 % of that kernel's time; PH_FLAT_NO_ALTERNATE=1 gives 6653 GB/s instead of 6798); inputs are read "
+                             "with L2 evict_first and results stored evict_last (PH_FLAT_L2_HINT=0: 6786 instead of 6843)",
                        "seed": SEED},
             "pct_of_peak": {"of_measured_copy": round(value / world / peak, 4), "of_nominal_8000": round(value / world / 8000, 4)},
             "roofline": {"bound": "hbm", "kernel": "map_flat_kernel<BinaryOp<float,ADD>,8,2> (out = t + c, all operands contiguous)",
                          "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": NCU_TRAFFIC_ADD, "peak_source": peak_src,
-                         "traffic_source": "profiles/r01_bench_dram_warm.csv (ncu, one pass, --cache-control none: dram__bytes_read.sum 504.0 MB "
-                                           "+ dram__bytes_write.sum 273.3 MB per launch; cold-cache --set full capture: 536.9 MB read)",
+                         "traffic_source": "profiles/r02_bench_dram_warm.csv (ncu, one pass, --cache-control none: dram__bytes_read.sum 477.6 MB "
+                                           "+ dram__bytes_write.sum 269.8 MB per launch; cold-cache --set full capture: 536.9 MB read)",
                          "algorithmic_bytes_per_launch": BYTES_ADD, "avg_launch_ms": round(dom_ms, 5),
                          "launches_timed": len(add_ms),
                          "other_kernels": {"map_flat_kernel<BinaryOp<float,MUL>,8,2> (t = a * b, b periodic: the [1,8192] row vector)": {

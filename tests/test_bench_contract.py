@@ -33,9 +33,10 @@ def test_reference_arm_is_silent_on_other_ranks():
     assert out.returncode == 0 and out.stdout.strip() == ""
 
 
-def test_committed_gpu_line_meets_the_contract():
-    d = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_final.json")))
-    ref = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_reference_arm.json")))
+@__import__("pytest").mark.parametrize("rnd", ["r01", "r02"])
+def test_committed_gpu_line_meets_the_contract(rnd):
+    d = json.load(open(os.path.join(ROOT, "profiles", f"{rnd}_bench_final.json")))
+    ref = json.load(open(os.path.join(ROOT, "profiles", f"{rnd}_bench_reference_arm.json")))
     assert BASE_KEYS <= set(d) and "impl" not in d or d.get("impl") == "ours"
     assert d["metric"] == ref["metric"] and d["unit"] == ref["unit"] and d["config"]["workload"] == ref["config"]["workload"]
     assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["gpu_launches"] == 2 * d["steps"] and d["scaling"] == "weak"
@@ -51,3 +52,24 @@ def test_committed_gpu_line_meets_the_contract():
     c = d["clocks"]
     assert c["sm_mhz"] > 0.9 * c["sm_max_mhz"] and not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     assert d["value"] * d["ms_per_step"] * 1e-3 * 1e9 / d["config"]["bytes_per_step_per_gpu"] == __import__("pytest").approx(1.0, rel=1e-3)
+    if rnd == "r02":                                                         # round 2: the reference arm times the whole workload
+        assert ref["impl"] == "reference" and ref["ms_per_step"] > 500 and ref["config"]["sample"] == "the full workload per step"
+        x = d["extras"]
+        assert x["heat3d_2048_f32"]["steps"] == 100 and x["heat3d_2048_f32"]["subcube_vs_oracle"] and len(x["heat3d_2048_f32"]["field_hash"]) == 16
+        assert x["reduce_sum_1e9_f32"]["result_ok"] and x["reduce_argmax_1e9_f32"]["result_ok"]
+        e2 = d["e2e"]
+        assert e2["naive"]["same_result"] and 0.85 < e2["frac_of_host_link_ceiling"] < 1.1
+
+
+def test_committed_multi_gpu_lines_agree_with_each_other():
+    """The 2 / 4 / 8-GPU lines of round 2 (both transports): the stencil's field hash is the single GPU's, every
+    self-check holds, the in-bench agreement checks passed on every rank."""
+    one = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_final.json")))["extras"]["heat3d_2048_f32"]["field_hash"]
+    for name in ("n2_p2p", "n2_nccl", "n4_p2p", "n8_p2p", "n8_nccl"):
+        d = json.load(open(os.path.join(ROOT, "profiles", f"r02_bench_{name}.json")))
+        n = int(name[1])
+        x = d["extras"]
+        assert d["n_gpus"] == n and x["heat3d_2048_f32"]["field_hash"] == one and x["heat3d_2048_f32"]["subcube_vs_oracle"]
+        assert x["reduce_sum_1e9_f32"]["result_ok"] and x["reduce_argmax_1e9_f32"]["result_ok"] and x["sharded_permute_16384_f64"]["result_ok"]
+        if "multi_gpu_parity" in x:
+            assert x["multi_gpu_parity"]["ok"] and all(x["multi_gpu_parity"]["ranks_ok"]) and x["multi_gpu_parity"]["checks"] >= 100
