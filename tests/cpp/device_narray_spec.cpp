@@ -244,9 +244,8 @@ int main(int argc, char** argv) {
   io_host_specs();
   partition_host_specs();
 
-  // Written after the round's last GPU minute was spent: opt-in until it has run on a device once
-  // (PH_SPEC_DEVICE_IO=1); its host half (io_host_specs) is part of every run.
-  if (std::getenv("PH_SPEC_DEVICE_IO"))
+  // (ran on a B200 in round 2: profiles/r02_cpp_host_spec.log; PH_SPEC_NO_DEVICE_IO=1 skips it, e.g. on a read-only /tmp)
+  if (!std::getenv("PH_SPEC_NO_DEVICE_IO"))
   it("device arrays through the I/O formats (n_array.cr:807-912; binary checkpoint)", [] {
     auto stock = stock_narr();
     EXPECT(IO::to_json(stock) == "{\"shape\":[2,3],\"elements\":[0,1,2,3,4,5]}");

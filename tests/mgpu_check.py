@@ -177,16 +177,17 @@ def run_checks(world: int, rank: int, soft: bool = False) -> dict:
         _chk(False, "global Int32 sum overflow must raise on every rank")
     except ph.CrOverflowError:
         pass
-    pre = np.zeros((world, 2), np.int32)
+    pre = np.zeros((max(2, world), 2), np.int32)                                 # (one rank: both rows are its own)
     pre[0] = [2**31 - 2, 0]; pre[-1] = [5, -10]                                   # a PREFIX leaves Int32, the total does not
-    xp = D.from_host(pre[rank:rank + 1])
+    p0, p1 = S.shard_range(pre.shape[0], world, rank)
+    xp = D.from_host(pre[p0:p1])
     try:
         S.reduce_full_sharded(xp, "sum")
         _chk(False, "a prefix of the global fold leaves Int32: must raise")
     except ph.CrOverflowError:
         pass
     pre[-1] = [-10, 5]                                                            # same values, no prefix leaves Int32
-    _chk(S.reduce_full_sharded(D.from_host(pre[rank:rank + 1]), "sum") == np.int32(2**31 - 2 - 5), "tests/mgpu_check.py:170")
+    _chk(S.reduce_full_sharded(D.from_host(pre[p0:p1]), "sum") == np.int32(2**31 - 2 - 5), "same values, no prefix leaves Int32")
     si = S.ShardedNArray.from_global(big32)
     try:
         si.sum(axis=0)
