@@ -274,18 +274,18 @@ module Phase
     # call; they also carry the form without P2P (blocks gathered, `ph_alltoallv`, received in place).
     def [](*literal) : ShardedNArray(T)
       region = IndexRegion.new(literal.to_a, @shape)
-      whole = !region.degeneracy[0] && region.first[0] == 0 && region.stride[0] == 1 && region.proper_shape[0] == @shape[0]
-      if whole
+      world, me = Comm.world, Comm.rank
+      plan = SlicePlan.new(@shape, region, world, me) # send / land descriptors, recv ranges
+      if plan.local?
         rest = [..] + literal.to_a[1..]
         rows = @row1 > @row0 ? @local[rest] : DeviceNArray(T).new([0] + region.shape[1..])
         return ShardedNArray(T).new(region.shape, rows)
       end
-      world, me = Comm.world, Comm.rank
-      plan = SlicePlan.new(@shape, region, world, me) # mirrors ph_slice_plan_of: send / land descriptors, recv ranges
       new_shape = plan.new_shape
+      return ShardedNArray(T).new(new_shape, @local[literal.to_a]) if world == 1 # one rank owns everything
       m0, m1 = Comm.shard_range(new_shape[0])
       my_shape = [m1 - m0] + new_shape[1..]
-      unless world > 1 && Comm.p2p_ready?
+      unless Comm.p2p_ready?
         raise RuntimeError.new("slicing the sharded axis needs peer-mapped memory in this layer (the Python and C++ layers carry the ph_alltoallv form)")
       end
       result = DeviceNArray(T).over(my_shape, Comm::SymmBuffer.new(Descriptor.element_count(my_shape) * sizeof(T))) # collective
@@ -295,43 +295,112 @@ module Phase
       ShardedNArray(T).new(new_shape, result)
     end
 
+    # `narr[region_literal] = value` across shards (scatter / fill, src/multi_writable.cr:55-84). A scalar fills this
+    # rank's cells of the region (no exchange). A `ShardedNArray` of the region's shape is the gather run backwards
+    # with the same plan: the rows of `value` this rank holds leave as contiguous blocks (`ph_alltoallv`), and every
+    # block received is scattered into the arithmetic progression of local rows it belongs to (one strided copy).
+    def []=(*literal, value : T)
+      args = literal.to_a
+      region = IndexRegion.new(args, @shape)
+      plan = SlicePlan.new(@shape, region, Comm.world, Comm.rank)
+      if plan.local?
+        @local[[..] + args[1..]] = value if @row1 > @row0
+        return value
+      end
+      plan.send.each do |cells|
+        next if Descriptor.count(cells) == 0
+        d = cells
+        Device.check LibPhGpu.ph_fill_region(sizeof(T).to_i32, @local.dev.ptr, pointerof(d), pointerof(value).as(Void*))
+      end
+      Device.wait # `value` is a stack temporary
+      value
+    end
+
+    def []=(*literal, value : ShardedNArray(T))
+      args = literal.to_a
+      region = IndexRegion.new(args, @shape)
+      world = Comm.world
+      plan = SlicePlan.new(@shape, region, world, Comm.rank)
+      unless value.shape == plan.new_shape
+        raise ShapeError.new("Cannot substitute: the given array has shape #{value.shape}, but the region has shape #{plan.new_shape}.")
+      end
+      if plan.local?
+        @local[[..] + args[1..]] = value.local if @row1 > @row0
+        return value
+      end
+      m0, _ = Comm.shard_range(plan.new_shape[0])
+      row = plan.new_shape.size > 1 ? Descriptor.element_count(plan.new_shape[1..]) : 1_i64
+      incoming = Array(DeviceNArray(T)?).new(world, nil)
+      send_ptr = Array(Void*).new(world, Pointer(Void).null)
+      recv_ptr = Array(Void*).new(world, Pointer(Void).null)
+      send_bytes = Array(Int64).new(world, 0_i64)
+      recv_bytes = Array(Int64).new(world, 0_i64)
+      world.times do |q|
+        lo, hi = plan.recv[q] # rows of `value` I hold that q's shard receives
+        if hi > lo && row > 0
+          send_ptr[q] = (value.local.dev.ptr.as(UInt8*) + (lo - m0) * row * sizeof(T)).as(Void*)
+          send_bytes[q] = (hi - lo) * row * sizeof(T)
+        end
+        cells = plan.send[q] # where q's rows land in MY shard
+        if (count = Descriptor.count(cells)) > 0
+          extents = cells.extent
+          block = DeviceNArray(T).new(Array(Int32).new(cells.rank) { |i| extents[i].to_i32 })
+          incoming[q] = block
+          recv_ptr[q] = block.dev.ptr
+          recv_bytes[q] = count * sizeof(T)
+        end
+      end
+      Device.check LibPhGpu.ph_alltoallv(send_ptr.to_unsafe, send_bytes.to_unsafe, recv_ptr.to_unsafe, recv_bytes.to_unsafe)
+      world.times do |q|
+        if block = incoming[q]
+          from, onto = block.desc, plan.send[q]
+          Device.check LibPhGpu.ph_copy_strided(sizeof(T).to_i32, block.dev.ptr, pointerof(from), @local.dev.ptr, pointerof(onto))
+        end
+      end
+      Device.wait # the received blocks are released with this scope
+      value
+    end
+
     # Host plan of a slice across shards: the Crystal statement of `ph_slice_plan_of` (include/ph_host.h).
+    #   send[q] : the block this rank owes q, a strided view of ITS shard (every extent 0: nothing)
+    #   land[q] : where it lands in q's shard of the result (a contiguous range of q's rows)
+    #   recv[q] : {lo, hi}, the rows of the result (global numbering) q holds for this rank
     struct SlicePlan
       getter new_shape : Array(Int32)
       getter send : Array(LibPhGpu::Desc)
       getter land : Array(LibPhGpu::Desc)
+      getter recv : Array({Int64, Int64})
+      getter? local : Bool
 
-      def initialize(shape : Array(Int32), region : IndexRegion, world : Int32, rank : Int32)
-        nd = shape.size
+      @shape : Array(Int32)
+      @world : Int32
+      @lead : Int32?
+      @f0 : Int64
+      @s0 : Int64
+
+      def initialize(@shape : Array(Int32), region : IndexRegion, @world : Int32, rank : Int32)
+        nd = @shape.size
         @new_shape = region.shape.map(&.to_i32)
         kept = (0...nd).reject { |i| region.degeneracy[i] && region.drop }
-        lead = kept.first? # the result's leading axis; nil: every axis indexed (shape [1])
-        gstride = Array(Int64).new(nd, 1_i64)
-        (nd - 2).downto(0) { |i| gstride[i] = gstride[i + 1] * shape[i + 1] }
-        inner = (1...nd).sum(0_i64) { |i| region.first[i].to_i64 * gstride[i] }
-        f0, s0 = region.first[0].to_i64, region.stride[0].to_i64
+        @lead = kept.first? # the result's leading axis; nil: every axis indexed (shape [1])
+        @f0, @s0 = region.first[0].to_i64, region.stride[0].to_i64
         rnk = @new_shape.size
         blank = Descriptor.make(rnk, 0_i64, Descriptor.axes, Descriptor.axes)
-        @send = Array(LibPhGpu::Desc).new(world) { blank }
-        @land = Array(LibPhGpu::Desc).new(world) { blank }
-        my0, my1 = Comm.shard_range(shape[0], world, rank)
-        world.times do |q|
-          j0, j1 = Comm.shard_range(@new_shape[0], world, q)
-          next if my1 <= my0 || j1 <= j0
-          lo, hi = 0_i64, 0_i64
-          if lead != 0
-            lo, hi = j0.to_i64, j1.to_i64 if my0 <= f0 < my1
-          elsif s0 > 0
-            lo = {0_i64, -((-(my0 - f0)) // s0)}.max
-            hi = my1 - 1 >= f0 ? (my1 - 1 - f0) // s0 + 1 : 0_i64
-          else
-            t = -s0
-            lo = {0_i64, -((-(f0 - (my1 - 1))) // t)}.max
-            hi = f0 >= my0 ? (f0 - my0) // t + 1 : 0_i64
-          end
-          lo, hi = {lo, j0.to_i64}.max, {hi, j1.to_i64}.min
+        @send = Array(LibPhGpu::Desc).new(@world) { blank }
+        @land = Array(LibPhGpu::Desc).new(@world) { blank }
+        @recv = Array({Int64, Int64}).new(@world) { {0_i64, 0_i64} }
+        @local = @lead == 0 && @f0 == 0 && @s0 == 1 && region.proper_shape[0] == @shape[0]
+        return if @local
+        gstride = Array(Int64).new(nd, 1_i64)
+        (nd - 2).downto(0) { |i| gstride[i] = gstride[i + 1] * @shape[i + 1] }
+        inner = (1...nd).sum(0_i64) { |i| region.first[i].to_i64 * gstride[i] }
+        my0, _ = Comm.shard_range(@shape[0], @world, rank)
+        lead = @lead
+        @world.times do |q|
+          @recv[q] = owned(q, rank)
+          lo, hi = owned(rank, q)
           next if hi <= lo
-          offset = (lead == 0 ? f0 + s0 * lo - my0 : f0 - my0) * gstride[0] + inner
+          offset = (lead == 0 ? @f0 + @s0 * lo - my0 : @f0 - my0) * gstride[0] + inner
           offset += region.stride[lead].to_i64 * lo * gstride[lead] if lead && lead > 0
           extent, stride = Descriptor.axes, Descriptor.axes
           if kept.empty?
@@ -343,11 +412,33 @@ module Phase
             stride[d] = region.stride[axis].to_i64 * gstride[axis]
           end
           @send[q] = Descriptor.make(rnk, offset, extent, stride)
+          j0, j1 = Comm.shard_range(@new_shape[0], @world, q)
           whole = Descriptor.contiguous([j1 - j0] + @new_shape[1..])
           lext, lstr = whole.extent, whole.stride
           lext[0] = hi - lo
           @land[q] = Descriptor.make(rnk, (lo - j0) * lstr[0], lext, lstr)
         end
+      end
+
+      # rows [lo, hi) of the result's leading axis that `dst` owns and whose data `src` holds
+      private def owned(src : Int32, dst : Int32) : {Int64, Int64}
+        r0, r1 = Comm.shard_range(@shape[0], @world, src)
+        j0, j1 = Comm.shard_range(@new_shape[0], @world, dst)
+        none = {0_i64, 0_i64}
+        return none if r1 <= r0 || j1 <= j0
+        if @lead != 0 # axis 0 is ONE row: its owner has everything
+          return r0 <= @f0 < r1 ? {j0.to_i64, j1.to_i64} : none
+        end
+        if @s0 > 0
+          lo = {0_i64, -((-(r0 - @f0)) // @s0)}.max
+          hi = r1 - 1 >= @f0 ? (r1 - 1 - @f0) // @s0 + 1 : 0_i64
+        else
+          t = -@s0
+          lo = {0_i64, -((-(@f0 - (r1 - 1))) // t)}.max
+          hi = @f0 >= r0 ? (@f0 - r0) // t + 1 : 0_i64
+        end
+        lo, hi = {lo, j0.to_i64}.max, {hi, j1.to_i64}.min
+        hi > lo ? {lo, hi} : none
       end
     end
 
