@@ -189,6 +189,10 @@ del v_rows, v_rev
 #      (PH_AXIS_STAGED=0 restores one thread per column); long rows: the one-pass row kernel
 for name in ["sum", "max", "argmax"]:
     row(f"reduce axis=0 {name} f64 [{S},{S}] (few columns: staged strips)", NS * 8 + S * 8, lambda name=name: getattr(src, name)(axis=0), reps=10)
+src32 = dev_rand((S, S), np.float32, 11)
+for name in ["sum", "max"]:
+    row(f"reduce axis=0 {name} f32 [{S},{S}] (few columns: staged strips)", NS * 4 + S * 4, lambda name=name: getattr(src32, name)(axis=0), reps=10)
+del src32
 for name in ["sum", "max", "argmax"]:
     row(f"reduce axis=1 {name} f64 [{S},{S}] (128 KiB rows)", NS * 8 + S * 8, lambda name=name: getattr(src, name)(axis=1), reps=10)
 # ---- f-2: each_slice on a rank-3 view of the same buffer (one gather launch per slice)

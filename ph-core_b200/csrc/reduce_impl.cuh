@@ -739,21 +739,38 @@ __global__ void __launch_bounds__(32) axis_strip_staged_kernel(const T* __restri
   // this lane's chunks of a tile: rows r0 + j * (32 / CPR), columns cc .. cc + EPC
   const int r0 = lane / CPR, cc = (lane % CPR) * EPC;
   const bool col_ok = cc < ncols;
-  const T* src0 = base + (int64_t)r0 * kstride + cc;
-  auto issue = [&](int t) {
-    const int slot = t % STAGES;
-    const int64_t k0 = (int64_t)t * KT;
+  // Issue path kept to ~3 instructions per 16-byte chunk: the lane's source pointer walks the strip (one 64-bit add
+  // per chunk, one per tile), whole tiles carry no bounds test.  (Recomputing `(k0 + r) * kstride` and testing
+  // `k0 + r < K` per chunk cost ~12 instructions each -- more than the fold itself -- and made f32 strips
+  // instruction-bound per warp.)
+  const int Ki = (int)K;                                    // K < 2^31 (dispatch)
+  const int64_t row_step = (int64_t)(32 / CPR) * kstride;   // between a lane's consecutive chunks of one tile
+  const int64_t tile_step = (int64_t)KT * kstride;
+  const T* next_src = base + (int64_t)r0 * kstride + cc;    // this lane's first chunk of the next tile to issue
+  int next_tile = 0;
+  auto issue = [&]() {
+    const int slot = next_tile % STAGES;
+    const int k0 = next_tile * KT;
     if (col_ok) {
+      T* dst = &ring[slot][r0][cc];
+      const T* p = next_src;
+      if (k0 + KT <= Ki) {
 #pragma unroll
-      for (int j = 0; j < CPL; j++) {
-        const int r = r0 + j * (32 / CPR);
-        if (k0 + r < K) cp_async16(&ring[slot][r][cc], src0 + (k0 + j * (32 / CPR)) * kstride);
+        for (int j = 0; j < CPL; j++) { cp_async16(dst + j * (32 / CPR) * CW, p); p += row_step; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < CPL; j++) {
+          if (k0 + r0 + j * (32 / CPR) < Ki) cp_async16(dst + j * (32 / CPR) * CW, p);
+          p += row_step;
+        }
       }
     }
+    next_src += tile_step;
+    next_tile++;
   };
 #pragma unroll
   for (int t = 0; t < STAGES - 1; t++) {
-    if (t < ntiles) issue(t);
+    if (t < ntiles) issue();
     cp_async_commit();
   }
   // A sum is ONE chain (the k order is the result).  Extrema are order-free, so they run as NA independent
@@ -780,18 +797,18 @@ __global__ void __launch_bounds__(32) axis_strip_staged_kernel(const T* __restri
     }
   };
   for (int t = 0; t < ntiles; t++) {
-    if (t + STAGES - 1 < ntiles) issue(t + STAGES - 1);     // into the slot folded in the previous iteration
+    if (t + STAGES - 1 < ntiles) issue();                   // tile t + STAGES - 1, into the slot folded in the previous iteration
     cp_async_commit();
     cp_async_wait<STAGES - 1>();                            // tile t has landed (this lane's chunks) ...
     __syncwarp();                                           // ... and every other lane's
     const int slot = t % STAGES;
-    const int64_t k0 = (int64_t)t * KT;
+    const int k0 = t * KT;
     if (act) {
-      if (k0 + KT <= K) {
+      if (k0 + KT <= Ki) {
 #pragma unroll
         for (int r = 0; r < KT; r++) fold(ring[slot][r][mycol], (int32_t)(k0 + r), r % NA);
       } else {
-        for (int r = 0; k0 + r < K; r++) fold(ring[slot][r][mycol], (int32_t)(k0 + r), 0);
+        for (int r = 0; k0 + r < Ki; r++) fold(ring[slot][r][mycol], (int32_t)(k0 + r), 0);
       }
     }
     __syncwarp();                                           // the slot may be refilled
@@ -1381,7 +1398,10 @@ static int32_t reduce_axis_launch(const T* x, void* out, int64_t outer, int64_t 
       const bool wanted = force_staged >= 0 ? force_staged != 0
                                             : (col_bytes < (3LL << 19) && strips >= (int64_t)r.sm_count && K >= 64);
       if (aligned && wanted && strips <= 0x7fffffffLL && spo <= 0x7fffffffLL && K <= 0x7fffffffLL) {
-        constexpr int KT = 16, STAGES = 8;
+        // 4 KB tiles, 7 in flight per warp: bytes in flight, not instructions, bound this kernel (f32 with 16-row
+        // = 2 KB tiles: 7 MB in flight over the GPU, 4.1 TB/s on [16384,16384]; Little's law wants ~5 MB at 6.5 TB/s
+        // and ~0.8 us, with little margin)
+        constexpr int KT = sizeof(T) >= 8 ? 16 : 32, STAGES = 8;
         axis_strip_staged_kernel<T, RED, KT, STAGES><<<(unsigned)strips, 32, 0, r.stream>>>(x, out, K, inner, lay.ostride,
                                                                                              lay.kstride, lay.irev, (int)spo, r.d_flags);
         PH_LAUNCH_CHECK("axis_strip_staged_kernel");
