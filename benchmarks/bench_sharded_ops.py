@@ -75,6 +75,7 @@ emit("sharded full sum f32 %s (allreduce of one scalar)" % R, nb, timed(lambda: 
 emit("sharded full max f32 (allreduce)", nb, timed(lambda: x.max()))
 emit("sharded full argmax f32 (allgather of (value, index))", nb, timed(lambda: x.argmax()))
 emit("sharded axis-0 sum f32 (allreduce of the [1000,1000] partial)", nb, timed(lambda: x.sum(axis=0)))
+emit("sharded axis-0 max f32 (allreduce of the [1000,1000] partial)", nb, timed(lambda: x.max(axis=0)))
 emit("sharded axis-1 sum f32 (no collective)", nb, timed(lambda: x.sum(axis=1)))
 del x, loc
 
@@ -87,7 +88,10 @@ sm = S.ShardedNArray([N, N], mat)
 t = sm.permute()
 # every rank's rows of the transpose hold, in column block q, the fill value of rank q
 probe = [float(t.local.get(0, S.shard_range(N, world, q)[0])) for q in range(world)]
-emit("sharded permute (transpose across shards) f64 %dx%d" % (N, N), 2.0 * N * N * 8, timed(lambda: sm.permute(), reps=3, warm=1),
+p2p_perm = S.p2p_ready() and not os.environ.get("PH_PERMUTE_NCCL")        # the P2P form writes into a reused symmetric result
+emit("sharded permute (transpose across shards) f64 %dx%d" % (N, N), 2.0 * N * N * 8,
+     timed((lambda: sm.permute(out=t)) if p2p_perm else (lambda: sm.permute()), reps=3, warm=1),
      result_ok=bool(probe == [float(q + 1) for q in range(world)]),
-     note="algorithmic bytes = read + write of the matrix once; the implementation also stages send/receive blocks")
+     transport="peer stores (ph_alltoall_strided)" if p2p_perm else "ncclSend/ncclRecv (ph_alltoallv)",
+     note="algorithmic bytes = read + write of the matrix once")
 dist.destroy_process_group()

@@ -246,7 +246,7 @@ module Phase
              end
       return part if Comm.world == 1
       {% if T < Int %}
-        if red.sum?
+        if red.sum? && !Comm.p2p_ready? # (with P2P `ph_allreduce` folds in rank order with checked adds)
           # checked integer sums: an ncclSum would wrap silently. The per-rank partials ([world, inner], rank
           # order = row order) are gathered and folded by the checked axis-0 sum.
           gathered = DeviceNArray(T).new([Comm.world] + out_shape)
@@ -255,6 +255,7 @@ module Phase
         end
       {% end %}
       Device.check LibPhGpu.ph_allreduce(red.value, Device.dtype(T), part.dev.ptr, part.size)
+      Device.raise_pending # per-axis folds are raise points: the cross-rank fold too
       part
     end
 

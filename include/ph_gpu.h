@@ -307,7 +307,12 @@ int32_t ph_symm_peer(const void* local_dev, int32_t peer_rank, void** out_peer_d
 int32_t ph_reduce_full_sharded(int32_t red, int32_t dtype, const void* a, const ph_desc* a_desc,
                                int64_t elems_before, void* out_value_host, int64_t* out_index_host,
                                uint32_t* out_flags);
-int32_t ph_allreduce(int32_t red, int32_t dtype, void* buf_dev, int64_t count); /* SUM/MIN/MAX in place */
+/* SUM / MIN / MAX in place over the ranks.  With peer-mapped memory (ph_comm_p2p_ready): reduce-scatter + all-gather
+ * as three small launches of peer stores / loads over NVLink, folded IN RANK ORDER -- deterministic, and for an axis-0
+ * sharded array rank order is row order, so integer SUMs are overflow-checked (PH_FLAG_OVERFLOW) like the single-GPU
+ * fold; every rank's arithmetic flags reach every rank.  Otherwise (or PH_ALLREDUCE_NCCL=1) ncclAllReduce: unordered,
+ * integer sums wrap -- callers that need the check gather and fold (ph_allgather + ph_reduce_axis). */
+int32_t ph_allreduce(int32_t red, int32_t dtype, void* buf_dev, int64_t count);
 int32_t ph_allgather(const void* send_dev, void* recv_dev, int64_t nbytes_per_rank);
 /* personalised all-to-all (the exchange step of a transpose across axis-0 shards): arrays of
  * nranks entries; block p of the send list goes to rank p, block p of the receive list comes from

@@ -378,7 +378,7 @@ class ShardedNArray {
                                          : DeviceNArray<T>::fill(out_shape, identity(red));     // an empty shard contributes the identity
     const int32_t w = Comm::world();
     if (w == 1) return part;
-    if (red == PH_SUM && std::is_integral<T>::value) {
+    if (red == PH_SUM && std::is_integral<T>::value && !Comm::p2p_ready()) {   // (P2P: ph_allreduce folds in rank order, checked)
       // integer sums are overflow-CHECKED: an ncclSum would wrap silently.  The per-rank partials ([world, inner],
       // rank order = row order) are gathered and folded by the checked axis-0 sum.
       Shape gs = out_shape;
@@ -388,6 +388,7 @@ class ShardedNArray {
       return gathered.sum(0);
     }
     Device::check(ph_allreduce(red, DType<T>::value, part.data(), part.size()));
+    Device::raise_pending();                      // per-axis folds are raise points (reduce_axis): the cross-rank fold too
     return part;
   }
   static T identity(int32_t red) {

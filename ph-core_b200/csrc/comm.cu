@@ -7,6 +7,7 @@
 // being updated on the main stream.
 #include "ph_common.cuh"
 #include "comm.cuh"
+#include "ops.cuh"
 #include <cuda.h>
 #include <stdlib.h>
 #include <dlfcn.h>
@@ -369,6 +370,206 @@ static int32_t halo_exchange_impl(const void* send_lo, void* recv_lo, int lo_ran
 
 using namespace ph;
 
+// ---- flag rounds over the peer-mapped control blocks (strided all-to-all, ordered all-reduce)
+struct PeerFlagPtrs {
+  uint32_t* p[PH_MAX_PEERS];
+};
+static __global__ void xchg_signal_kernel(PeerFlagPtrs f, int n, uint32_t event) {
+  __threadfence_system();                       // the copies launched before this kernel have completed (stream order)
+  if ((int)threadIdx.x < n && f.p[threadIdx.x]) st_release_sys(f.p[threadIdx.x], event);
+}
+static __global__ void xchg_wait_kernel(const volatile uint32_t* flags, int n, uint32_t event, uint32_t* err_flags) {
+  if ((int)threadIdx.x < n) {
+    const long long t0 = clock64();
+    while ((int32_t)(flags[threadIdx.x] - event) < 0) {
+      if (clock64() - t0 > 20000000000LL) { atomicOr(err_flags + 1, 1u); break; }   // ~10 s: a peer died
+    }
+  }
+  __threadfence_system();
+}
+static int32_t xchg_round(int which, uint32_t event) {
+  Comm& c = cm();
+  PeerInfo& p = peers();
+  Runtime& r = rt();
+  PeerFlagPtrs f;
+  for (int q = 0; q < PH_MAX_PEERS; q++) f.p[q] = q < c.nranks ? &p.ctrl[q]->xchg_flag[which][c.rank] : nullptr;
+  xchg_signal_kernel<<<1, 32, 0, r.stream>>>(f, c.nranks, event);
+  PH_LAUNCH_CHECK("xchg_signal_kernel");
+  xchg_wait_kernel<<<1, 32, 0, r.stream>>>(&p.ctrl[c.rank]->xchg_flag[which][0], c.nranks, event, r.d_flags);
+  PH_LAUNCH_CHECK("xchg_wait_kernel");
+  return PH_OK;
+}
+
+// ---------------------------------------------------------------- ordered all-reduce over peer memory
+// ph_allreduce when every peer is mapped: reduce-scatter + all-gather as three small launches over NVLink,
+// folded IN RANK ORDER (deterministic; for an axis-0 sharded array rank order is row order, so integer sums are
+// overflow-checked exactly like the single-GPU fold) with every rank's arithmetic flags delivered to every rank:
+//   1. push : chunk q of my buffer -> rank q's staging slot [my rank]                 (peer stores)
+//      -- flag round "partials have landed"
+//   2. fold : my chunk = slot[0] (op) slot[1] (op) ... in rank order -> my result chunk (double-buffered by call
+//      parity); my flag word -> every peer              -- flag round "results are ready"
+//   3. pull : every rank's result chunk -> my buffer (peer loads); the peers' flag words are OR-ed into mine.
+// An N x 4 MB all-reduce moves 2 x 7/8 x 4 MB per rank instead of NCCL's ring / tree schedule: 0.12 -> ~0.10 ms for
+// the [1000,1000] f32 partial of an axis-0 fold at 8 GPUs (the local fold is ~75 us of it).
+static __global__ void __launch_bounds__(256) ar_push_kernel(const char* __restrict__ buf, size_t total, size_t chunk,
+                                                             PeerFlagPtrs stage_of /* base of each peer's staging */, size_t my_slot_offset) {
+  const int q = blockIdx.y;
+  const size_t lo = (size_t)q * chunk;
+  if (lo >= total) return;
+  const size_t n = (total - lo < chunk) ? total - lo : chunk;
+  const char* src = buf + lo;
+  char* dst = reinterpret_cast<char*>(stage_of.p[q]) + my_slot_offset;
+  const size_t stride = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+    const size_t n16 = n / 16;
+    for (size_t i = tid; i < n16; i += stride) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+    for (size_t i = n16 * 16 + tid; i < n; i += stride) dst[i] = src[i];
+  } else {
+    for (size_t i = tid; i < n; i += stride) dst[i] = src[i];
+  }
+}
+template <typename T, int RED>
+static __global__ void __launch_bounds__(256) ar_fold_kernel(const char* __restrict__ staging, size_t slot_stride, int64_t n_mine,
+                                                             int nranks, T* __restrict__ result, uint32_t* __restrict__ flags) {
+  uint32_t err = 0;
+  bool nan = false;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_mine; i += stride) {
+    T acc = reinterpret_cast<const T*>(staging)[i];
+    if constexpr (is_float_t<T>::value && RED != PH_SUM) nan |= (acc != acc);
+    for (int r = 1; r < nranks; r++) {
+      const T v = reinterpret_cast<const T*>(staging + (size_t)r * slot_stride)[i];
+      if constexpr (RED == PH_SUM) {
+        if constexpr (is_float_t<T>::value) acc = f_add(acc, v);
+        else acc = i_add<T>(acc, v, true, err);
+      } else {
+        if constexpr (is_float_t<T>::value) nan |= (v != v);
+        const bool take = RED == PH_MAX ? (v > acc) : (v < acc);
+        if (take) acc = v;
+      }
+    }
+    result[i] = acc;
+  }
+  if (err) atomicOr(flags, err);
+  if (nan) atomicOr(flags, (uint32_t)PH_FLAG_NAN);
+}
+// round "results are ready": my flag word goes with it
+static __global__ void ar_signal_kernel(PeerFlagPtrs done, PeerFlagPtrs flag_slot, int n, uint32_t event, const uint32_t* my_flags) {
+  if ((int)threadIdx.x < n) {
+    *reinterpret_cast<volatile uint32_t*>(flag_slot.p[threadIdx.x]) = *reinterpret_cast<const volatile uint32_t*>(my_flags);
+    __threadfence_system();
+    st_release_sys(done.p[threadIdx.x], event);
+  }
+}
+static __global__ void __launch_bounds__(256) ar_pull_kernel(char* __restrict__ buf, size_t total, size_t chunk,
+                                                             PeerFlagPtrs result_of, const uint32_t* __restrict__ peer_flags, int nranks,
+                                                             uint32_t* __restrict__ flags) {
+  const int q = blockIdx.y;
+  const size_t lo = (size_t)q * chunk;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    uint32_t f = 0;
+    for (int r = 0; r < nranks; r++) f |= reinterpret_cast<const volatile uint32_t*>(peer_flags)[r];
+    if (f) atomicOr(flags, f);
+  }
+  if (lo >= total) return;
+  const size_t n = (total - lo < chunk) ? total - lo : chunk;
+  const char* src = reinterpret_cast<const char*>(result_of.p[q]);
+  char* dst = buf + lo;
+  const size_t stride = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+    const size_t n16 = n / 16;
+    for (size_t i = tid; i < n16; i += stride) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+    for (size_t i = n16 * 16 + tid; i < n; i += stride) dst[i] = src[i];
+  } else {
+    for (size_t i = tid; i < n; i += stride) dst[i] = src[i];
+  }
+}
+
+template <typename T>
+static int32_t ar_fold_launch(int32_t red, const char* staging, size_t slot_stride, int64_t n_mine, int nranks, void* result, unsigned blocks) {
+  Runtime& r = rt();
+  T* res = reinterpret_cast<T*>(result);
+  switch (red) {
+    case PH_SUM: ar_fold_kernel<T, PH_SUM><<<blocks, 256, 0, r.stream>>>(staging, slot_stride, n_mine, nranks, res, r.d_flags); break;
+    case PH_MIN: ar_fold_kernel<T, PH_MIN><<<blocks, 256, 0, r.stream>>>(staging, slot_stride, n_mine, nranks, res, r.d_flags); break;
+    case PH_MAX: ar_fold_kernel<T, PH_MAX><<<blocks, 256, 0, r.stream>>>(staging, slot_stride, n_mine, nranks, res, r.d_flags); break;
+    default: return set_error(PH_ERR_UNSUPPORTED, "allreduce supports SUM / MIN / MAX (arg* use ph_allgather)");
+  }
+  PH_LAUNCH_CHECK("ar_fold_kernel");
+  return PH_OK;
+}
+
+// returns PH_OK with *done = false when the P2P form cannot take this call (the caller then uses NCCL)
+static int32_t allreduce_p2p(int32_t red, int32_t dtype, void* buf_dev, int64_t count, bool* done) {
+  *done = false;
+  Comm& c = cm();
+  PeerInfo& p = peers();
+  static const bool off = getenv("PH_ALLREDUCE_NCCL") != nullptr;
+  const size_t esz = (size_t)dtype_size(dtype);
+  const size_t total = (size_t)count * esz;
+  if (off || !p.ready || esz == 0 || total > ((size_t)256 << 20)) return PH_OK;
+  if (red != PH_SUM && red != PH_MIN && red != PH_MAX) return PH_OK;
+  Runtime& r = rt();
+  const int n = c.nranks;
+  // chunk: elements per rank, a multiple of 16 bytes (so that the vector copies and the folds stay aligned)
+  const int64_t per = ceil_div(count, (int64_t)n);
+  const size_t chunk = (((size_t)per * esz + 255) / 256) * 256;
+  if (chunk > p.ar_chunk_cap) {                       // collective growth: every rank sees the same `count`
+    if (p.ar_scratch) { int32_t st = ph_symm_free(p.ar_scratch); if (st != PH_OK) return st; p.ar_scratch = nullptr; }
+    const size_t cap = std::max<size_t>(chunk, (size_t)1 << 20);
+    void* block = nullptr;
+    int32_t st = ph_symm_alloc(cap * (size_t)(n + 2), &block);
+    if (st != PH_OK) return st;
+    p.ar_scratch = reinterpret_cast<char*>(block);
+    p.ar_chunk_cap = cap;
+  }
+  const SymmAlloc* sa = symm_find(p.ar_scratch);
+  if (!sa || !sa->mapped) return PH_OK;
+  const size_t cap = p.ar_chunk_cap;
+  const uint32_t event = ++p.xchg_event;
+  const int parity = (int)(event & 1u);
+  PeerFlagPtrs stage_of, result_of, landed, flag_slot;
+  for (int q = 0; q < PH_MAX_PEERS; q++) {
+    const bool live = q < n;
+    char* base = live ? (q == c.rank ? p.ar_scratch : sa->peer[q]) : nullptr;
+    stage_of.p[q] = reinterpret_cast<uint32_t*>(base);
+    result_of.p[q] = reinterpret_cast<uint32_t*>(live ? base + cap * (size_t)(n + parity) : nullptr);
+    landed.p[q] = live ? &p.ctrl[q]->xchg_flag[1][c.rank] : nullptr;
+    flag_slot.p[q] = live ? &p.ctrl[q]->ar_flags[c.rank] : nullptr;
+  }
+  // the user's buffer is cut into chunks of `chunk` bytes; staging slots and result chunks are `cap` bytes apart
+  const unsigned bx = (unsigned)std::max<size_t>(1, std::min<size_t>(32, chunk / ((size_t)256 * 64) + 1));
+  int32_t st;
+  // 1. push my chunks to their owners' staging slot [my rank]
+  ar_push_kernel<<<dim3(bx, (unsigned)n), 256, 0, r.stream>>>(reinterpret_cast<const char*>(buf_dev), total, chunk, stage_of,
+                                                              cap * (size_t)c.rank);
+  PH_LAUNCH_CHECK("ar_push_kernel");
+  if ((st = xchg_round(0, event)) != PH_OK) return st;                    // every rank's partials have landed in my staging
+  // 2. fold my chunk in rank order
+  const size_t my_lo = (size_t)c.rank * chunk;
+  const int64_t n_mine = my_lo >= total ? 0 : (int64_t)(std::min(chunk, total - my_lo) / esz);
+  const unsigned fb = (unsigned)std::max<int64_t>(1, std::min<int64_t>(8 * r.sm_count, ceil_div(std::max<int64_t>(n_mine, 1), 256 * 4)));
+  void* my_result = p.ar_scratch + cap * (size_t)(n + parity);
+  switch (dtype) {
+#define PH_AR(code, T) case code: st = ar_fold_launch<T>(red, p.ar_scratch, cap, n_mine, n, my_result, fb); break;
+    PH_AR(PH_F32, float) PH_AR(PH_F64, double) PH_AR(PH_I32, int32_t) PH_AR(PH_I64, int64_t) PH_AR(PH_U8, uint8_t)
+    PH_AR(PH_I8, int8_t) PH_AR(PH_I16, int16_t) PH_AR(PH_U16, uint16_t) PH_AR(PH_U32, uint32_t) PH_AR(PH_U64, uint64_t)
+#undef PH_AR
+    default: return set_error(PH_ERR_UNSUPPORTED, "dtype %d has no all-reduce", dtype);
+  }
+  if (st != PH_OK) return st;
+  ar_signal_kernel<<<1, 32, 0, r.stream>>>(landed, flag_slot, n, event, r.d_flags);   // results ready + my flag word
+  PH_LAUNCH_CHECK("ar_signal_kernel");
+  xchg_wait_kernel<<<1, 32, 0, r.stream>>>(&p.ctrl[c.rank]->xchg_flag[1][0], n, event, r.d_flags);
+  PH_LAUNCH_CHECK("xchg_wait_kernel");
+  // 3. pull every rank's result chunk; OR the peers' flag words into mine
+  ar_pull_kernel<<<dim3(bx, (unsigned)n), 256, 0, r.stream>>>(reinterpret_cast<char*>(buf_dev), total, chunk, result_of,
+                                                              &p.ctrl[c.rank]->ar_flags[0], n, r.d_flags);
+  PH_LAUNCH_CHECK("ar_pull_kernel");
+  *done = true;
+  return PH_OK;
+}
+
 extern "C" {
 
 int32_t ph_comm_unique_id(uint8_t* out128) {
@@ -474,6 +675,11 @@ int32_t ph_allreduce(int32_t red, int32_t dtype, void* buf_dev, int64_t count) {
   Comm& c = cm();
   if (!c.inited) return set_error(PH_ERR_NOT_INIT, "ph_comm_init was not called");
   if (c.nranks == 1 || count == 0) return PH_OK;
+  {
+    bool done = false;                                  // peers mapped: reduce-scatter + all-gather over peer memory, rank order
+    int32_t st = allreduce_p2p(red, dtype, buf_dev, count, &done);
+    if (st != PH_OK || done) return st;
+  }
   ncclDataType_t t;
   int32_t st = nccl_type(dtype, &t);
   if (st != PH_OK) return st;
@@ -535,35 +741,6 @@ int32_t ph_alltoallv(const void* const* send_dev, const int64_t* send_bytes, voi
 // visited in the order rank+1, rank+2, ... so every phase is a permutation (no receiver takes N streams at once).
 // Two flag rounds bracket the copies: "my destination may be overwritten" before, "my stores have landed" after
 // (stream-ordered; the host does not block).
-struct PeerFlagPtrs {
-  uint32_t* p[PH_MAX_PEERS];
-};
-static __global__ void xchg_signal_kernel(PeerFlagPtrs f, int n, uint32_t event) {
-  __threadfence_system();                       // the copies launched before this kernel have completed (stream order)
-  if ((int)threadIdx.x < n && f.p[threadIdx.x]) st_release_sys(f.p[threadIdx.x], event);
-}
-static __global__ void xchg_wait_kernel(const volatile uint32_t* flags, int n, uint32_t event, uint32_t* err_flags) {
-  if ((int)threadIdx.x < n) {
-    const long long t0 = clock64();
-    while ((int32_t)(flags[threadIdx.x] - event) < 0) {
-      if (clock64() - t0 > 20000000000LL) { atomicOr(err_flags + 1, 1u); break; }   // ~10 s: a peer died
-    }
-  }
-  __threadfence_system();
-}
-static int32_t xchg_round(int which, uint32_t event) {
-  Comm& c = cm();
-  PeerInfo& p = peers();
-  Runtime& r = rt();
-  PeerFlagPtrs f;
-  for (int q = 0; q < PH_MAX_PEERS; q++) f.p[q] = q < c.nranks ? &p.ctrl[q]->xchg_flag[which][c.rank] : nullptr;
-  xchg_signal_kernel<<<1, 32, 0, r.stream>>>(f, c.nranks, event);
-  PH_LAUNCH_CHECK("xchg_signal_kernel");
-  xchg_wait_kernel<<<1, 32, 0, r.stream>>>(&p.ctrl[c.rank]->xchg_flag[which][0], c.nranks, event, r.d_flags);
-  PH_LAUNCH_CHECK("xchg_wait_kernel");
-  return PH_OK;
-}
-
 int32_t ph_alltoall_strided(int32_t elem_size, const void* src_dev, const ph_desc* src_descs, void* dst_symm,
                             const ph_desc* dst_descs) {
   PH_REQUIRE_INIT();

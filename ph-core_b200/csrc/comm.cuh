@@ -56,6 +56,8 @@ struct CtrlBlock {
   // strided all-to-all (ph_alltoall_strided): [0][r] rank r is ready for exchange e (its destination may be
   // overwritten), [1][r] rank r's stores of exchange e into MY memory have landed -- each written by rank r
   alignas(128) uint32_t xchg_flag[2][PH_MAX_PEERS];
+  // ordered all-reduce (ph_allreduce over peer memory): rank r's arithmetic flag word at the end of its fold
+  alignas(128) uint32_t ar_flags[PH_MAX_PEERS];
 };
 
 // What the two-steps-per-pass stencil kernel needs to deliver the halo itself (heat_tma.cu): output planes
@@ -82,7 +84,9 @@ struct PeerInfo {
   ReduceResult* host_result_dev = nullptr;        // its device address
   uint32_t reduce_seq = 0;
   uint32_t halo_event = 0;                        // last halo event number this rank issued
-  uint32_t xchg_event = 0;                        // last strided all-to-all this rank issued (collective: same on every rank)
+  uint32_t xchg_event = 0;                        // last strided all-to-all / ordered all-reduce this rank issued (collective: same on every rank)
+  char* ar_scratch = nullptr;                     // ordered all-reduce: symmetric block [nranks staging chunks | 2 result chunks]
+  size_t ar_chunk_cap = 0;                        // bytes per chunk the block was sized for
 };
 PeerInfo& peers();
 

@@ -633,12 +633,15 @@ class ShardedNArray:
                 ident = info.min if name == "max" else info.max
             part = DeviceNArray.fill(out_shape, ident, dt)
         lib = _lib.load()
-        if name == "sum" and self.dtype.kind in "iu" and self.world > 1:
+        if name == "sum" and self.dtype.kind in "iu" and self.world > 1 and not p2p_ready():
             # integer sums are overflow-CHECKED: an ncclSum would wrap silently.  The per-rank partials
             # ([world, inner], rank order = row order) are gathered and folded by the checked axis-0 sum.
+            # (With peer-mapped memory ph_allreduce itself folds in rank order with checked adds.)
             nbytes = part.size * part.dtype.itemsize
             gathered = DeviceNArray([self.world] + out_shape, part.dtype, _Buffer(max(1, nbytes * self.world)))
             check(lib.ph_allgather(part.ptr, gathered.ptr, nbytes))
             return gathered.sum(axis=0)
         check(lib.ph_allreduce(K[_RED[name]], dtype_code(part.dtype), part.ptr, part.size))
+        if self.world > 1:
+            DeviceNArray.raise_pending()       # per-axis folds are raise points (narray._reduce_axis): the cross-rank fold too
         return part                            # replicated DeviceNArray
