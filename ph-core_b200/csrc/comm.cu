@@ -401,25 +401,30 @@ static int32_t xchg_round(int which, uint32_t event) {
 }
 
 // ---------------------------------------------------------------- ordered all-reduce over peer memory
-// ph_allreduce when every peer is mapped: reduce-scatter + all-gather as three small launches over NVLink,
-// folded IN RANK ORDER (deterministic; for an axis-0 sharded array rank order is row order, so integer sums are
-// overflow-checked exactly like the single-GPU fold) with every rank's arithmetic flags delivered to every rank:
-//   1. push : chunk q of my buffer -> rank q's staging slot [my rank]                 (peer stores)
-//      -- flag round "partials have landed"
-//   2. fold : my chunk = slot[0] (op) slot[1] (op) ... in rank order -> my result chunk (double-buffered by call
-//      parity); my flag word -> every peer              -- flag round "results are ready"
-//   3. pull : every rank's result chunk -> my buffer (peer loads); the peers' flag words are OR-ed into mine.
-// An N x 4 MB all-reduce moves 2 x 7/8 x 4 MB per rank instead of NCCL's ring / tree schedule: 0.12 -> ~0.10 ms for
-// the [1000,1000] f32 partial of an axis-0 fold at 8 GPUs (the local fold is ~75 us of it).
-static __global__ void __launch_bounds__(256) ar_push_kernel(const char* __restrict__ buf, size_t total, size_t chunk,
-                                                             PeerFlagPtrs stage_of /* base of each peer's staging */, size_t my_slot_offset) {
-  const int q = blockIdx.y;
-  const size_t lo = (size_t)q * chunk;
-  if (lo >= total) return;
-  const size_t n = (total - lo < chunk) ? total - lo : chunk;
-  const char* src = buf + lo;
-  char* dst = reinterpret_cast<char*>(stage_of.p[q]) + my_slot_offset;
-  const size_t stride = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+// ph_allreduce when every peer is mapped: reduce-scatter + all-gather as THREE launches over NVLink, folded IN RANK
+// ORDER (deterministic; for an axis-0 sharded array rank order is row order, so integer sums are overflow-checked
+// exactly like the single-GPU fold) with every rank's arithmetic flags delivered to every rank:
+//   1. push : chunk q of my buffer -> rank q's staging slot [my rank] (peer stores); the last block to finish
+//             releases "my partials have landed" in every peer's control block
+//   2. fold : every block waits for that word from all N ranks, then my chunk = slot[0] (op) slot[1] (op) ... in rank
+//             order -> my result chunk (double-buffered by call parity); the last block sends my flag word to every
+//             peer and releases "my result is ready"
+//   3. pull : every block waits for that word from all N ranks, then every rank's result chunk -> my buffer (peer
+//             loads); the peers' flag words are OR-ed into mine.
+// The launches carry their own flag rounds (no separate signal / wait kernels): lanes 0..n-1 of each block spin on the
+// n words; the grids are small enough to be resident at once, and the signals a block waits for come from OTHER GPUs.
+__device__ __forceinline__ void ar_wait_round(const uint32_t* words, int n, uint32_t event, uint32_t* err_flags) {
+  if ((int)threadIdx.x < n) {
+    const volatile uint32_t* w = words;
+    const long long t0 = clock64();
+    while ((int32_t)(w[threadIdx.x] - event) < 0) {
+      if (clock64() - t0 > 20000000000LL) { atomicOr(err_flags + 1, 1u); break; }      // ~10 s: a peer died
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void ar_copy(char* dst, const char* src, size_t n, size_t tid, size_t stride) {
   if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
     const size_t n16 = n / 16;
     for (size_t i = tid; i < n16; i += stride) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
@@ -428,9 +433,37 @@ static __global__ void __launch_bounds__(256) ar_push_kernel(const char* __restr
     for (size_t i = tid; i < n; i += stride) dst[i] = src[i];
   }
 }
+// true in exactly one block of the launch: the last one to get here (every block fences before it takes its
+// ticket, so all the launch's earlier stores -- also those into peer memory -- are visible system-wide by then)
+__device__ __forceinline__ bool ar_last_block(uint32_t* ticket) {
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+    if (last) { *ticket = 0; __threadfence_system(); }
+  }
+  __syncthreads();
+  return last;
+}
+static __global__ void __launch_bounds__(256) ar_push_kernel(const char* __restrict__ buf, size_t total, size_t chunk,
+                                                             PeerFlagPtrs stage_of /* base of each peer's staging */, size_t my_slot_offset,
+                                                             uint32_t* ticket, PeerFlagPtrs landed, int nranks, uint32_t event) {
+  const int q = blockIdx.y;
+  const size_t lo = (size_t)q * chunk;
+  if (lo < total) {
+    const size_t n = (total - lo < chunk) ? total - lo : chunk;
+    ar_copy(reinterpret_cast<char*>(stage_of.p[q]) + my_slot_offset, buf + lo, n,
+            (size_t)blockIdx.x * blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x);
+  }
+  if (ar_last_block(ticket) && (int)threadIdx.x < nranks) st_release_sys(landed.p[threadIdx.x], event);
+}
 template <typename T, int RED>
 static __global__ void __launch_bounds__(256) ar_fold_kernel(const char* __restrict__ staging, size_t slot_stride, int64_t n_mine,
-                                                             int nranks, T* __restrict__ result, uint32_t* __restrict__ flags) {
+                                                             int nranks, T* __restrict__ result, uint32_t* __restrict__ flags,
+                                                             const uint32_t* landed_words, uint32_t* ticket, PeerFlagPtrs ready,
+                                                             PeerFlagPtrs flag_slot, uint32_t event) {
+  ar_wait_round(landed_words, nranks, event, flags);        // every rank's partials are in my staging
   uint32_t err = 0;
   bool nan = false;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -452,18 +485,16 @@ static __global__ void __launch_bounds__(256) ar_fold_kernel(const char* __restr
   }
   if (err) atomicOr(flags, err);
   if (nan) atomicOr(flags, (uint32_t)PH_FLAG_NAN);
-}
-// round "results are ready": my flag word goes with it
-static __global__ void ar_signal_kernel(PeerFlagPtrs done, PeerFlagPtrs flag_slot, int n, uint32_t event, const uint32_t* my_flags) {
-  if ((int)threadIdx.x < n) {
-    *reinterpret_cast<volatile uint32_t*>(flag_slot.p[threadIdx.x]) = *reinterpret_cast<const volatile uint32_t*>(my_flags);
+  if (ar_last_block(ticket) && (int)threadIdx.x < nranks) {           // my result chunk is ready; my flag word goes with it
+    *reinterpret_cast<volatile uint32_t*>(flag_slot.p[threadIdx.x]) = *reinterpret_cast<const volatile uint32_t*>(flags);
     __threadfence_system();
-    st_release_sys(done.p[threadIdx.x], event);
+    st_release_sys(ready.p[threadIdx.x], event);
   }
 }
 static __global__ void __launch_bounds__(256) ar_pull_kernel(char* __restrict__ buf, size_t total, size_t chunk,
                                                              PeerFlagPtrs result_of, const uint32_t* __restrict__ peer_flags, int nranks,
-                                                             uint32_t* __restrict__ flags) {
+                                                             uint32_t* __restrict__ flags, const uint32_t* ready_words, uint32_t event) {
+  ar_wait_round(ready_words, nranks, event, flags);         // every rank's result chunk is ready
   const int q = blockIdx.y;
   const size_t lo = (size_t)q * chunk;
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
@@ -473,28 +504,27 @@ static __global__ void __launch_bounds__(256) ar_pull_kernel(char* __restrict__ 
   }
   if (lo >= total) return;
   const size_t n = (total - lo < chunk) ? total - lo : chunk;
-  const char* src = reinterpret_cast<const char*>(result_of.p[q]);
-  char* dst = buf + lo;
-  const size_t stride = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
-    const size_t n16 = n / 16;
-    for (size_t i = tid; i < n16; i += stride) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
-    for (size_t i = n16 * 16 + tid; i < n; i += stride) dst[i] = src[i];
-  } else {
-    for (size_t i = tid; i < n; i += stride) dst[i] = src[i];
-  }
+  ar_copy(buf + lo, reinterpret_cast<const char*>(result_of.p[q]), n, (size_t)blockIdx.x * blockDim.x + threadIdx.x,
+          (size_t)gridDim.x * blockDim.x);
 }
 
+struct ArFoldArgs {
+  const char* staging; size_t slot_stride; int64_t n_mine; int nranks; void* result;
+  const uint32_t* landed_words; uint32_t* ticket; PeerFlagPtrs ready, flag_slot; uint32_t event; unsigned blocks;
+};
 template <typename T>
-static int32_t ar_fold_launch(int32_t red, const char* staging, size_t slot_stride, int64_t n_mine, int nranks, void* result, unsigned blocks) {
+static int32_t ar_fold_launch(int32_t red, const ArFoldArgs& a) {
   Runtime& r = rt();
-  T* res = reinterpret_cast<T*>(result);
+  T* res = reinterpret_cast<T*>(a.result);
+#define PH_FOLD(RED) ar_fold_kernel<T, RED><<<a.blocks, 256, 0, r.stream>>>(a.staging, a.slot_stride, a.n_mine, a.nranks, res, r.d_flags, \
+                                                                             a.landed_words, a.ticket, a.ready, a.flag_slot, a.event)
   switch (red) {
-    case PH_SUM: ar_fold_kernel<T, PH_SUM><<<blocks, 256, 0, r.stream>>>(staging, slot_stride, n_mine, nranks, res, r.d_flags); break;
-    case PH_MIN: ar_fold_kernel<T, PH_MIN><<<blocks, 256, 0, r.stream>>>(staging, slot_stride, n_mine, nranks, res, r.d_flags); break;
-    case PH_MAX: ar_fold_kernel<T, PH_MAX><<<blocks, 256, 0, r.stream>>>(staging, slot_stride, n_mine, nranks, res, r.d_flags); break;
+    case PH_SUM: PH_FOLD(PH_SUM); break;
+    case PH_MIN: PH_FOLD(PH_MIN); break;
+    case PH_MAX: PH_FOLD(PH_MAX); break;
     default: return set_error(PH_ERR_UNSUPPORTED, "allreduce supports SUM / MIN / MAX (arg* use ph_allgather)");
   }
+#undef PH_FOLD
   PH_LAUNCH_CHECK("ar_fold_kernel");
   return PH_OK;
 }
@@ -511,60 +541,56 @@ static int32_t allreduce_p2p(int32_t red, int32_t dtype, void* buf_dev, int64_t 
   if (red != PH_SUM && red != PH_MIN && red != PH_MAX) return PH_OK;
   Runtime& r = rt();
   const int n = c.nranks;
-  // chunk: elements per rank, a multiple of 16 bytes (so that the vector copies and the folds stay aligned)
+  // the user's buffer is cut into n chunks of `chunk` bytes (a multiple of 256, so vector copies and folds stay aligned)
   const int64_t per = ceil_div(count, (int64_t)n);
   const size_t chunk = (((size_t)per * esz + 255) / 256) * 256;
   if (chunk > p.ar_chunk_cap) {                       // collective growth: every rank sees the same `count`
-    if (p.ar_scratch) { int32_t st = ph_symm_free(p.ar_scratch); if (st != PH_OK) return st; p.ar_scratch = nullptr; }
-    const size_t cap = std::max<size_t>(chunk, (size_t)1 << 20);
+    if (p.ar_scratch) { int32_t st = ph_symm_free(p.ar_scratch); if (st != PH_OK) return st; p.ar_scratch = nullptr; p.ar_chunk_cap = 0; }
+    const size_t want = std::max<size_t>(chunk, (size_t)1 << 20);
     void* block = nullptr;
-    int32_t st = ph_symm_alloc(cap * (size_t)(n + 2), &block);
+    int32_t st = ph_symm_alloc(want * (size_t)(n + 2), &block);
     if (st != PH_OK) return st;
     p.ar_scratch = reinterpret_cast<char*>(block);
-    p.ar_chunk_cap = cap;
+    p.ar_chunk_cap = want;
   }
   const SymmAlloc* sa = symm_find(p.ar_scratch);
   if (!sa || !sa->mapped) return PH_OK;
-  const size_t cap = p.ar_chunk_cap;
+  const size_t cap = p.ar_chunk_cap;                  // staging slots and result chunks are `cap` bytes apart in the block
   const uint32_t event = ++p.xchg_event;
   const int parity = (int)(event & 1u);
-  PeerFlagPtrs stage_of, result_of, landed, flag_slot;
+  CtrlBlock* mine = p.ctrl[c.rank];
+  PeerFlagPtrs stage_of, result_of, landed, ready, flag_slot;
   for (int q = 0; q < PH_MAX_PEERS; q++) {
     const bool live = q < n;
     char* base = live ? (q == c.rank ? p.ar_scratch : sa->peer[q]) : nullptr;
     stage_of.p[q] = reinterpret_cast<uint32_t*>(base);
     result_of.p[q] = reinterpret_cast<uint32_t*>(live ? base + cap * (size_t)(n + parity) : nullptr);
-    landed.p[q] = live ? &p.ctrl[q]->xchg_flag[1][c.rank] : nullptr;
+    landed.p[q] = live ? &p.ctrl[q]->xchg_flag[0][c.rank] : nullptr;
+    ready.p[q] = live ? &p.ctrl[q]->xchg_flag[1][c.rank] : nullptr;
     flag_slot.p[q] = live ? &p.ctrl[q]->ar_flags[c.rank] : nullptr;
   }
-  // the user's buffer is cut into chunks of `chunk` bytes; staging slots and result chunks are `cap` bytes apart
   const unsigned bx = (unsigned)std::max<size_t>(1, std::min<size_t>(32, chunk / ((size_t)256 * 64) + 1));
-  int32_t st;
-  // 1. push my chunks to their owners' staging slot [my rank]
   ar_push_kernel<<<dim3(bx, (unsigned)n), 256, 0, r.stream>>>(reinterpret_cast<const char*>(buf_dev), total, chunk, stage_of,
-                                                              cap * (size_t)c.rank);
+                                                              cap * (size_t)c.rank, &mine->ar_ticket[0], landed, n, event);
   PH_LAUNCH_CHECK("ar_push_kernel");
-  if ((st = xchg_round(0, event)) != PH_OK) return st;                    // every rank's partials have landed in my staging
-  // 2. fold my chunk in rank order
   const size_t my_lo = (size_t)c.rank * chunk;
-  const int64_t n_mine = my_lo >= total ? 0 : (int64_t)(std::min(chunk, total - my_lo) / esz);
-  const unsigned fb = (unsigned)std::max<int64_t>(1, std::min<int64_t>(8 * r.sm_count, ceil_div(std::max<int64_t>(n_mine, 1), 256 * 4)));
-  void* my_result = p.ar_scratch + cap * (size_t)(n + parity);
+  ArFoldArgs fa;
+  fa.staging = p.ar_scratch; fa.slot_stride = cap; fa.nranks = n;
+  fa.n_mine = my_lo >= total ? 0 : (int64_t)(std::min(chunk, total - my_lo) / esz);
+  fa.result = p.ar_scratch + cap * (size_t)(n + parity);
+  fa.landed_words = &mine->xchg_flag[0][0]; fa.ticket = &mine->ar_ticket[1]; fa.ready = ready; fa.flag_slot = flag_slot; fa.event = event;
+  fa.blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(4 * r.sm_count, ceil_div(std::max<int64_t>(fa.n_mine, 1), 256 * 4)));
+  int32_t st;
   switch (dtype) {
-#define PH_AR(code, T) case code: st = ar_fold_launch<T>(red, p.ar_scratch, cap, n_mine, n, my_result, fb); break;
+#define PH_AR(code, T) case code: st = ar_fold_launch<T>(red, fa); break;
     PH_AR(PH_F32, float) PH_AR(PH_F64, double) PH_AR(PH_I32, int32_t) PH_AR(PH_I64, int64_t) PH_AR(PH_U8, uint8_t)
     PH_AR(PH_I8, int8_t) PH_AR(PH_I16, int16_t) PH_AR(PH_U16, uint16_t) PH_AR(PH_U32, uint32_t) PH_AR(PH_U64, uint64_t)
 #undef PH_AR
     default: return set_error(PH_ERR_UNSUPPORTED, "dtype %d has no all-reduce", dtype);
   }
   if (st != PH_OK) return st;
-  ar_signal_kernel<<<1, 32, 0, r.stream>>>(landed, flag_slot, n, event, r.d_flags);   // results ready + my flag word
-  PH_LAUNCH_CHECK("ar_signal_kernel");
-  xchg_wait_kernel<<<1, 32, 0, r.stream>>>(&p.ctrl[c.rank]->xchg_flag[1][0], n, event, r.d_flags);
-  PH_LAUNCH_CHECK("xchg_wait_kernel");
-  // 3. pull every rank's result chunk; OR the peers' flag words into mine
   ar_pull_kernel<<<dim3(bx, (unsigned)n), 256, 0, r.stream>>>(reinterpret_cast<char*>(buf_dev), total, chunk, result_of,
-                                                              &p.ctrl[c.rank]->ar_flags[0], n, r.d_flags);
+                                                              &mine->ar_flags[0], n, r.d_flags, &mine->xchg_flag[1][0], event);
   PH_LAUNCH_CHECK("ar_pull_kernel");
   *done = true;
   return PH_OK;

@@ -58,6 +58,7 @@ struct CtrlBlock {
   alignas(128) uint32_t xchg_flag[2][PH_MAX_PEERS];
   // ordered all-reduce (ph_allreduce over peer memory): rank r's arithmetic flag word at the end of its fold
   alignas(128) uint32_t ar_flags[PH_MAX_PEERS];
+  alignas(128) uint32_t ar_ticket[2];         // local: blocks of the push / fold launch that have finished
 };
 
 // What the two-steps-per-pass stencil kernel needs to deliver the halo itself (heat_tma.cu): output planes
