@@ -806,7 +806,7 @@ class _Indexable:
             index //= length
         return list(reversed(coord))
 
-    def _reduce_axis(self, name: str, axis: int) -> "DeviceNArray":
+    def _reduce_axis(self, name: str, axis: int, raise_now: bool = True) -> "DeviceNArray":
         if axis < 0 or axis >= len(self.shape):
             raise CrIndexError(f"axis {axis} is not present in a {len(self.shape)}-dimensional MultiIndexable")
         if self.shape[axis] == 0 and name != "sum":
@@ -820,7 +820,8 @@ class _Indexable:
             else:
                 check(_lib.load().ph_reduce_axis(K[_RED[name]], dtype_code(self.dtype), self.ptr, C.byref(self.desc()),
                                                  axis, out.ptr, C.byref(out.desc())))
-        DeviceNArray.raise_pending()
+        if raise_now:                               # (a sharded fold checks once, after the cross-rank combine)
+            DeviceNArray.raise_pending()
         return out
 
     # ---- data-dependent errors -----------------------------------------------------------

@@ -621,7 +621,7 @@ class ShardedNArray:
             raise CrEmptyError("Empty enumerable")
         out_shape = self.shape[1:] or [1]
         if self.row1 - self.row0 > 0:
-            part = getattr(self.local, name)(axis=0)
+            part = self.local._reduce_axis(name, 0, raise_now=self.world == 1)   # flags are read once, after the combine
         else:                                                            # an empty shard contributes the identity
             dt = self.dtype
             if name == "sum":
