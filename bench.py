@@ -86,8 +86,41 @@ class ClockSampler:
         self.index = index
         self.rows = []
         self.proc = None
+        self.nvml = None
+        self.stop_flag = threading.Event()
+
+    def _start_nvml(self) -> bool:
+        """NVML in-process, one sample every ~5 ms: the multi-GPU legs last tens of milliseconds, too short for a
+        freshly started nvidia-smi loop (its first line arrives after ~100 ms)."""
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            mx = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            bits = [("hw_slowdown", N.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", N.nvmlClocksEventReasonHwThermalSlowdown),
+                    ("sw_thermal_slowdown", N.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", N.nvmlClocksEventReasonSwPowerCap)]
+
+            def loop():
+                while not self.stop_flag.is_set():
+                    try:
+                        sm = float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM))
+                        pw = N.nvmlDeviceGetPowerUsage(h) / 1000.0
+                        r = int(N.nvmlDeviceGetCurrentClocksEventReasons(h))
+                        self.rows.append([str(sm), str(mx), str(pw)] + ["Active" if r & b else "Not Active" for _, b in bits])
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+            self.nvml = N
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            return True
+        except Exception:
+            self.nvml = None
+            return False
 
     def start(self):
+        if self._start_nvml():
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
@@ -102,14 +135,18 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self) -> dict:
-        if not self.proc:
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=1)
+        elif not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+        else:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
@@ -121,7 +158,7 @@ class ClockSampler:
             except Exception:
                 continue
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvml, 5 ms" if self.nvml is not None else "nvidia-smi -lms 50"}
 
 
 def physical_gpu_index(local: int) -> int:
@@ -539,7 +576,10 @@ def run_extras(ph, lib, dist, world, rank, torch, stream):
     subcube_ok = bool(crop2.shape == (CN, CN, CN) and crop2[2:-2, 2:-2, 2:-2].tobytes() == want[2:-2, 2:-2, 2:-2].tobytes()
                       and not np.array_equal(crop2, crop0))
     other = b if cur is a else a
+    ph.check(lib.ph_timer_start())
     cur2 = run(cur, other, WARM - 2)
+    ph.check(lib.ph_timer_stop(C.byref(ms)))
+    warm_ms = max_over_ranks(ms.value) / (WARM - 2)
     other = cur if cur2 is not cur else other
     if dist is not None:
         dist.barrier()
@@ -566,7 +606,10 @@ def run_extras(ph, lib, dist, world, rank, torch, stream):
         "decomposition": f"axis-0 slabs x{world}, two time steps per pass over HBM (temporal blocking, bit-identical)",
         "algorithmic_bytes_per_cell_update": 8,
         "hbm_gbs_per_gpu": round(8 * G ** 3 / world / (heat_ms * 1e-3) / 1e9, 1),
-        "clocks": heat_clk}
+        "clocks": heat_clk,
+        "first_steps": {"steps": WARM - 2, "gcell_updates_per_s": round(G ** 3 / (warm_ms * 1e-3) / 1e9, 2),
+                        "note": "the warm-up steps right after set-up, timed the same way: the kernel's rate before the "
+                                "GPU's power limit settles (the 100 timed steps run under it: see clocks.reasons)"}}
     if world == 1:
         # the reference's CPU path beside it: the slice-arithmetic step through ph-core's operator
         # structure (C port, one thread) on a 160^3 sample, and the flat OpenMP loop nest on 512^3
