@@ -18,7 +18,9 @@ struct Runtime {
   cudaStream_t aux_stream = nullptr;   // halo exchange / overlap
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   uint32_t* d_flags = nullptr;         // device arithmetic flag word (d_flags[8] = reduction ticket)
-  uint32_t* h_flags = nullptr;         // pinned mirror
+  uint32_t* h_flags = nullptr;         // pinned, device-mapped record: [0] flag word, [1] call number
+  uint32_t* h_flags_dev = nullptr;     // its device address
+  uint32_t flag_seq = 0;
   void* d_scratch = nullptr;           // reduction partials
   size_t scratch_bytes = 0;
   void* h_scratch = nullptr;           // pinned result staging (64 B)

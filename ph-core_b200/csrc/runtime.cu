@@ -2,6 +2,7 @@
 // and the descriptor planner shared by every kernel family.
 // Replaces the storage half of NArray (src/n_array.cr:20-79, 230-232, 372-395).
 #include "ph_common.cuh"
+#include <atomic>
 #include <stdarg.h>
 #include <stdio.h>
 #include <algorithm>
@@ -258,7 +259,10 @@ int32_t ph_init(int32_t device) {
   PH_CUDA(cudaEventCreate(&r.ev_t1));
   PH_CUDA(cudaMalloc((void**)&r.d_flags, 64));
   PH_CUDA(cudaMemset(r.d_flags, 0, 64));
-  PH_CUDA(cudaMallocHost((void**)&r.h_flags, 64));
+  PH_CUDA(cudaHostAlloc((void**)&r.h_flags, 64, cudaHostAllocMapped));   // [0] flag word, [1] call number (see take_flags)
+  memset(r.h_flags, 0, 64);
+  PH_CUDA(cudaHostGetDevicePointer((void**)&r.h_flags_dev, r.h_flags, 0));
+  r.flag_seq = 0;
   PH_CUDA(cudaMallocHost(&r.h_scratch, 256));
   // keep freed blocks in the pool: fluent ops allocate one result array per operator
   cudaMemPool_t pool;
@@ -334,6 +338,47 @@ int32_t ph_d2h(void* dst_host, const void* src_dev, size_t nbytes) {
 // ph_d2h plus the arithmetic flag word in the SAME synchronisation: the read a host layer uses for
 // `to_host` / `get`, so that a data-dependent error of any earlier launch surfaces at the read that
 // would hand its result to the caller (the reference raises at the offending operator).
+// The flag word travels like the result record of a full reduction: one tiny launch takes it (read and clear in
+// ONE atomic), stores it and then the call number into a pinned, device-mapped record, and the host polls that
+// number.  Stream order makes the poll a synchronisation point for everything enqueued before it (the data copy
+// of ph_d2h_flags included).  A 4-byte cudaMemcpyAsync + cudaMemsetAsync + cudaStreamSynchronize cost ~25 us per
+// raise point (a per-axis fold of [16384,16384] f32 runs for 150 us); PH_FLAGS_MEMCPY=1 restores that form (A/B).
+static __global__ void take_flags_kernel(uint32_t* __restrict__ d_flags, volatile uint32_t* __restrict__ host_rec, uint32_t seq) {
+  const uint32_t f = atomicExch(d_flags, 0u);
+  host_rec[0] = f;
+  __threadfence_system();
+  host_rec[1] = seq;
+}
+static int32_t take_flags(uint32_t* out_flags) {
+  Runtime& r = rt();
+  static const bool memcpy_form = getenv("PH_FLAGS_MEMCPY") != nullptr;
+  if (memcpy_form || !r.h_flags_dev) {
+    PH_CUDA(cudaMemcpyAsync(r.h_flags, r.d_flags, 4, cudaMemcpyDeviceToHost, r.stream));
+    PH_CUDA(cudaMemsetAsync(r.d_flags, 0, 4, r.stream));
+    PH_CUDA(cudaStreamSynchronize(r.stream));
+    *out_flags = r.h_flags[0];
+    return PH_OK;
+  }
+  const uint32_t seq = ++r.flag_seq;
+  take_flags_kernel<<<1, 1, 0, r.stream>>>(r.d_flags, r.h_flags_dev, seq);
+  PH_CUDA(cudaGetLastError());                       // not counted by ph_launch_count: it stands in for a 4-byte copy
+  const volatile uint32_t* done = r.h_flags + 1;
+  uint32_t polls = 0;
+  while (*done != seq) {
+    if ((++polls & 0xfff) == 0) {                    // a faulted launch never writes the record: ask the stream now and then
+      const cudaError_t q = cudaStreamQuery(r.stream);
+      if (q != cudaErrorNotReady) {
+        PH_CUDA(cudaStreamSynchronize(r.stream));
+        if (*done != seq) return set_error(PH_ERR_CUDA, "the flag record was not written");
+        break;
+      }
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  *out_flags = r.h_flags[0];
+  return PH_OK;
+}
+
 int32_t ph_d2h_flags(void* dst_host, const void* src_dev, size_t nbytes, uint32_t* out_flags) {
   PH_REQUIRE_INIT();
   if (!out_flags) return set_error(PH_ERR_INVALID, "null out_flags");
@@ -342,11 +387,7 @@ int32_t ph_d2h_flags(void* dst_host, const void* src_dev, size_t nbytes, uint32_
     if (!dst_host || !src_dev) return set_error(PH_ERR_INVALID, "null pointer in ph_d2h_flags");
     PH_CUDA(cudaMemcpyAsync(dst_host, src_dev, nbytes, cudaMemcpyDeviceToHost, r.stream));
   }
-  PH_CUDA(cudaMemcpyAsync(r.h_flags, r.d_flags, 4, cudaMemcpyDeviceToHost, r.stream));
-  PH_CUDA(cudaMemsetAsync(r.d_flags, 0, 4, r.stream));
-  PH_CUDA(cudaStreamSynchronize(r.stream));
-  *out_flags = *r.h_flags;
-  return PH_OK;
+  return take_flags(out_flags);
 }
 
 int32_t ph_d2h_async(void* dst_host, const void* src_dev, size_t nbytes) {
@@ -398,12 +439,7 @@ const char* ph_last_error_string(void) { return rt().err; }
 int32_t ph_take_arith_flags(uint32_t* out_flags) {
   PH_REQUIRE_INIT();
   if (!out_flags) return set_error(PH_ERR_INVALID, "null out_flags");
-  Runtime& r = rt();
-  PH_CUDA(cudaMemcpyAsync(r.h_flags, r.d_flags, 4, cudaMemcpyDeviceToHost, r.stream));
-  PH_CUDA(cudaMemsetAsync(r.d_flags, 0, 4, r.stream));
-  PH_CUDA(cudaStreamSynchronize(r.stream));
-  *out_flags = *r.h_flags;
-  return PH_OK;
+  return take_flags(out_flags);
 }
 
 int32_t ph_timer_start(void) {

@@ -283,7 +283,10 @@ def test_few_column_axis_folds_through_the_staged_kernel(dtype):
     axis_strip_staged_kernel: one warp per strip, cp.async ring, the same k-ordered fold -- float sums stay
     bit-identical to the sequential each_slice fold (src/multi_indexable.cr:742-748), first extremum wins."""
     rs = np.random.RandomState(31)
-    for shape, axis in [((200, 4800), 0), ((3, 100, 2000), 1), ((70, 5000), 0), ((2, 77, 3, 800), 1)]:
+    # the last three shapes have >= 148 strips of 64 columns: 4-byte elements take the two-columns-per-lane form
+    # (256-byte strip rows), incl. a ragged last strip (4900 % 64 = 36) and a strip count that is not a multiple of 2
+    for shape, axis in [((200, 4800), 0), ((3, 100, 2000), 1), ((70, 5000), 0), ((2, 77, 3, 800), 1),
+                        ((100, 9604), 0), ((3, 70, 3200), 1), ((2, 66, 4900), 1)]:
         if np.dtype(dtype).kind == "f":
             a = (rs.rand(*shape) * 2 - 1).astype(dtype)          # general data: only the exact k order is bit-identical
         else:
@@ -300,6 +303,11 @@ def test_few_column_axis_folds_through_the_staged_kernel(dtype):
             w = np.ascontiguousarray(a[::-1])
             for which in ("sum", "argmax", "min"):
                 assert_bits(getattr(v, which)(axis=0).to_host(), O.reduce_axis(w, 0, which), f"reversed {which}")
+            # both axes reversed: the strip is copied in memory order and the lanes read it backwards
+            v = d.view().reverse()
+            w = np.ascontiguousarray(a[::-1, ::-1])
+            for which in ("sum", "argmin", "max"):
+                assert_bits(getattr(v, which)(axis=0).to_host(), O.reduce_axis(w, 0, which), f"{shape} fully reversed {which}")
     if np.dtype(dtype).kind == "f":
         z = np.zeros((80, 4800), dtype)
         z[3, :] = -0.0
