@@ -586,9 +586,11 @@ def run_extras(ph, lib, dist, world, rank, torch, stream):
     torch.cuda.synchronize()
     heat_clocks = ClockSampler(physical_gpu_index(torch.cuda.current_device()))
     heat_clocks.start()
+    nccl0 = lib.ph_nccl_call_count()
     ph.check(lib.ph_timer_start())
     fin = run(cur2, other, STEPS)
     ph.check(lib.ph_timer_stop(C.byref(ms)))
+    heat_nccl = max(_gather_objects(dist, world, int(lib.ph_nccl_call_count() - nccl0)))
     heat_clk = heat_clocks.stop()
     heat_ms = max_over_ranks(ms.value) / STEPS
     h = C.c_uint64(0)
@@ -607,6 +609,7 @@ def run_extras(ph, lib, dist, world, rank, torch, stream):
         "algorithmic_bytes_per_cell_update": 8,
         "hbm_gbs_per_gpu": round(8 * G ** 3 / world / (heat_ms * 1e-3) / 1e9, 1),
         "clocks": heat_clk,
+        "nccl_calls_in_timed_region": heat_nccl,
         "first_steps": {"steps": WARM - 2, "gcell_updates_per_s": round(G ** 3 / (warm_ms * 1e-3) / 1e9, 2),
                         "note": "the warm-up steps right after set-up, timed the same way: the kernel's rate before the "
                                 "GPU's power limit settles (the 100 timed steps run under it: see clocks.reasons)"}}
@@ -665,10 +668,12 @@ def run_extras(ph, lib, dist, world, rank, torch, stream):
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+        nccl0 = lib.ph_nccl_call_count()
         ph.check(lib.ph_timer_start())
         for _ in range(reps):
             got = S.reduce_full_sharded(x, name, off)
         ph.check(lib.ph_timer_stop(C.byref(ms)))
+        red_nccl = max(_gather_objects(dist, world, int(lib.ph_nccl_call_count() - nccl0)))
         red_ms = max_over_ranks(ms.value) / reps
         ok = (float(got) == float(exact)) if name == "sum" else (float(got[0]) == 99.0 and int(got[1]) == P1)
         ok = all(_gather_objects(dist, world, bool(ok)))
@@ -680,7 +685,7 @@ def run_extras(ph, lib, dist, world, rank, torch, stream):
                     "collective": ("none (1 GPU)" if world == 1 else
                                    ("in-kernel one-shot combine over peer-mapped slots (no NCCL, one launch, one sync)" if p2p
                                     else "ncclAllGather of one 64-byte record per GPU + a combine launch")),
-                    "reps": reps}
+                    "nccl_calls_in_timed_region": red_nccl, "reps": reps}
     if world == 1:
         from oracle import c_oracle as CO
         xs = np.random.RandomState(2).rand(200_000_000).astype(np.float32)
@@ -708,11 +713,13 @@ def run_extras(ph, lib, dist, world, rank, torch, stream):
             dist.barrier()
         torch.cuda.synchronize()
         preps = 3
+        nccl0 = lib.ph_nccl_call_count()
         ph.check(lib.ph_timer_start())
         p2p_perm = S.p2p_ready() and not os.environ.get("PH_PERMUTE_NCCL")
         for _ in range(preps):
             t = src.permute(out=t) if p2p_perm else src.permute()
         ph.check(lib.ph_timer_stop(C.byref(ms)))
+        perm_nccl = max(_gather_objects(dist, world, int(lib.ph_nccl_call_count() - nccl0)))
         perm_ms = max_over_ranks(ms.value) / preps
         # transposed[i, j] = j * n + i on my rows i in [q0, q1)
         expect = D.from_host(np.arange(q0, q1, dtype=np.float64).reshape(q1 - q0, 1)).broadcast_op(
@@ -720,7 +727,7 @@ def run_extras(ph, lib, dist, world, rank, torch, stream):
         ok = all(_gather_objects(dist, world, bool(t.local.equals(expect))))
         hsum = sum(_gather_objects(dist, world, t.local.checksum64(q0 * n))) % (1 << 64)
         out["sharded_permute_16384_f64"] = {"ms": round(perm_ms, 4), "gbs_aggregate": round(2 * n * n * 8 / (perm_ms * 1e-3) / 1e9, 1),
-                                            "result_ok": ok, "checksum": f"{hsum:016x}",
+                                            "result_ok": ok, "checksum": f"{hsum:016x}", "nccl_calls_in_timed_region": perm_nccl,
                                             "how": ("ShardedNArray.permute: ONE pass of peer stores -- the transpose kernel writes every block "
                                                     "straight into its owner's shard over NVLink (ph_alltoall_strided), result buffer reused"
                                                     if p2p_perm else

@@ -167,6 +167,7 @@ lib LibPhGpu
   fun ph_comm_init(nranks : Int32, rank : Int32, id128 : UInt8*) : Int32
   fun ph_comm_destroy : Int32
   fun ph_comm_p2p_ready(out_ready : Int32*) : Int32
+  fun ph_nccl_call_count : Int64
   fun ph_symm_alloc(nbytes : LibC::SizeT, out_dev : Void**) : Int32
   fun ph_symm_free(dev : Void*) : Int32
   fun ph_symm_peer(local_dev : Void*, peer_rank : Int32, out_peer_dev : Void**) : Int32

@@ -283,6 +283,9 @@ int32_t ph_comm_destroy(void);
  * combine inside the reduction kernel and the stencil delivers its own halos (no NCCL on either path).
  * 0 (IPC refused, PH_NO_P2P=1, a single rank): the NCCL forms of the same entry points run instead. */
 int32_t ph_comm_p2p_ready(int32_t* out);
+/* Data-path NCCL calls (all-reduce, all-gather, send, recv) this process has issued so far: a measurement aid --
+ * the peer-memory forms leave it unchanged over a timed region (bench.py prints the difference per leg). */
+int64_t ph_nccl_call_count(void);
 /* Peer-mapped device memory for arrays whose kernels write into a neighbour rank (heat slabs).
  * COLLECTIVE: every rank calls ph_symm_alloc / ph_symm_free in the same order.  Works (as a plain
  * allocation) without P2P too.  ph_symm_peer: the address of `local_dev` (any address inside a

@@ -214,9 +214,10 @@ def load() -> C.CDLL:
     if hasattr(lib, "ph_host_last_error"):
         lib.ph_host_last_error.restype = C.c_char_p
         lib.ph_host_last_error.argtypes = []
-    if hasattr(lib, "ph_launch_count"):
-        lib.ph_launch_count.restype = i64
-        lib.ph_launch_count.argtypes = []
+    for counter in ("ph_launch_count", "ph_nccl_call_count"):
+        if hasattr(lib, counter):
+            getattr(lib, counter).restype = i64
+            getattr(lib, counter).argtypes = []
     _lib = lib
     return lib
 

@@ -72,6 +72,10 @@ static Comm& cm() {
   return c;
 }
 
+// data-path NCCL calls (all-reduce, all-gather, send, recv) issued since ph_init: the peer-memory forms must leave
+// this number unchanged over a timed region (bench.py prints the difference beside every multi-GPU leg)
+static long long g_nccl_calls = 0;
+
 static int32_t check_nccl(ncclResult_t r, const char* what) {
   if (r == ncclSuccess) return PH_OK;
   return set_error(PH_ERR_NCCL, "NCCL error %d (%s) at %s", (int)r, nccl().GetErrorString(r), what);
@@ -81,6 +85,7 @@ static int32_t check_nccl(ncclResult_t r, const char* what) {
     int32_t _s = check_nccl((call), #call);             \
     if (_s != PH_OK) return _s;                         \
   } while (0)
+#define PH_NCCL_DATA(call) do { g_nccl_calls++; PH_NCCL(call); } while (0)
 
 int32_t heat_slab_dispatch(int32_t dtype, int rank, const int64_t* ext, const void* coeff_host, int ghost, int has_lo,
                            int has_hi, int64_t p_begin, int64_t p_end, const void* in, void* out,
@@ -134,7 +139,7 @@ int32_t comm_allgather_records(cudaStream_t s) {
     PH_CUDA(cudaMemcpyAsync(p.gather_recv, p.gather_send, sizeof(ReduceSlot), cudaMemcpyDeviceToDevice, s));
     return PH_OK;
   }
-  PH_NCCL(nccl().AllGather(p.gather_send + c.rank, p.gather_recv, sizeof(ReduceSlot), ncclUint8, c.comm, s));
+  PH_NCCL_DATA(nccl().AllGather(p.gather_send + c.rank, p.gather_recv, sizeof(ReduceSlot), ncclUint8, c.comm, s));
   return PH_OK;
 }
 
@@ -355,12 +360,12 @@ static int32_t halo_exchange_impl(const void* send_lo, void* recv_lo, int lo_ran
   if (!c.inited) return set_error(PH_ERR_NOT_INIT, "ph_comm_init was not called");
   PH_NCCL(nccl().GroupStart());
   if (lo_rank >= 0) {
-    PH_NCCL(nccl().Send(send_lo, (size_t)nbytes, ncclUint8, lo_rank, c.comm, s));
-    PH_NCCL(nccl().Recv(recv_lo, (size_t)nbytes, ncclUint8, lo_rank, c.comm, s));
+    PH_NCCL_DATA(nccl().Send(send_lo, (size_t)nbytes, ncclUint8, lo_rank, c.comm, s));
+    PH_NCCL_DATA(nccl().Recv(recv_lo, (size_t)nbytes, ncclUint8, lo_rank, c.comm, s));
   }
   if (hi_rank >= 0) {
-    PH_NCCL(nccl().Send(send_hi, (size_t)nbytes, ncclUint8, hi_rank, c.comm, s));
-    PH_NCCL(nccl().Recv(recv_hi, (size_t)nbytes, ncclUint8, hi_rank, c.comm, s));
+    PH_NCCL_DATA(nccl().Send(send_hi, (size_t)nbytes, ncclUint8, hi_rank, c.comm, s));
+    PH_NCCL_DATA(nccl().Recv(recv_hi, (size_t)nbytes, ncclUint8, hi_rank, c.comm, s));
   }
   PH_NCCL(nccl().GroupEnd());
   return PH_OK;
@@ -630,6 +635,8 @@ int32_t ph_comm_init(int32_t nranks, int32_t rank, const uint8_t* id128) {
   return p2p_setup();     // map the peers' control blocks (CUDA IPC); the NCCL paths remain when that is impossible
 }
 
+int64_t ph_nccl_call_count(void) { return g_nccl_calls; }
+
 int32_t ph_comm_p2p_ready(int32_t* out) {
   if (!out) return set_error(PH_ERR_INVALID, "null out");
   *out = peers().ready ? 1 : 0;
@@ -716,7 +723,7 @@ int32_t ph_allreduce(int32_t red, int32_t dtype, void* buf_dev, int64_t count) {
     case PH_MAX: op = ncclMax; break;
     default: return set_error(PH_ERR_UNSUPPORTED, "allreduce supports SUM / MIN / MAX (arg* use ph_allgather)");
   }
-  PH_NCCL(nccl().AllReduce(buf_dev, buf_dev, (size_t)count, t, op, c.comm, rt().stream));
+  PH_NCCL_DATA(nccl().AllReduce(buf_dev, buf_dev, (size_t)count, t, op, c.comm, rt().stream));
   return PH_OK;
 }
 
@@ -729,7 +736,7 @@ int32_t ph_allgather(const void* send_dev, void* recv_dev, int64_t nbytes_per_ra
       PH_CUDA(cudaMemcpyAsync(recv_dev, send_dev, (size_t)nbytes_per_rank, cudaMemcpyDeviceToDevice, rt().stream));
     return PH_OK;
   }
-  PH_NCCL(nccl().AllGather(send_dev, recv_dev, (size_t)nbytes_per_rank, ncclUint8, c.comm, rt().stream));
+  PH_NCCL_DATA(nccl().AllGather(send_dev, recv_dev, (size_t)nbytes_per_rank, ncclUint8, c.comm, rt().stream));
   return PH_OK;
 }
 
@@ -752,8 +759,8 @@ int32_t ph_alltoallv(const void* const* send_dev, const int64_t* send_bytes, voi
   PH_NCCL(nccl().GroupStart());
   for (int p = 0; p < c.nranks; p++) {
     if (p == me) continue;
-    if (send_bytes[p] > 0) PH_NCCL(nccl().Send(send_dev[p], (size_t)send_bytes[p], ncclUint8, p, c.comm, s));
-    if (recv_bytes[p] > 0) PH_NCCL(nccl().Recv(recv_dev[p], (size_t)recv_bytes[p], ncclUint8, p, c.comm, s));
+    if (send_bytes[p] > 0) PH_NCCL_DATA(nccl().Send(send_dev[p], (size_t)send_bytes[p], ncclUint8, p, c.comm, s));
+    if (recv_bytes[p] > 0) PH_NCCL_DATA(nccl().Recv(recv_dev[p], (size_t)recv_bytes[p], ncclUint8, p, c.comm, s));
   }
   PH_NCCL(nccl().GroupEnd());
   return PH_OK;
