@@ -357,7 +357,7 @@ def run_ours(args):
     # overlap; the expression is written with the array API (no hand-built descriptors, no torch streams).
     a_pin, b_pin, c_pin = ph.pinned_from(a_h), ph.pinned_from(b_h), ph.pinned_from(c_h)
     out_pin = ph.pinned_empty(a_h.shape, np.float32)
-    pipe = ph.pipeline.RowPipeline(chunks=16)
+    pipe = ph.pipeline.RowPipeline(chunks=4, taper=7)          # 11 chunks: 3 x 2048 rows, then 1024, 512, ... 16, 16 (benchmarks/bench_pipeline.py)
     expr = lambda x, z, y: x.broadcast_op("*", y) + z          # (a * b) + c, b the [1, COLS] row vector
 
     def e2e_step():
@@ -477,7 +477,8 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(a_h.nbytes + b_h.nbytes + c_h.nbytes), "d2h_bytes_per_step": int(a_h.nbytes),
                     "steps": e2e_steps,
                     "how": "array API: pipeline.RowPipeline.map_rows (from_host_async of pinned a, b, c -> a.broadcast_op('*', b) + c "
-                           "-> to_host_async), 16 row chunks on upload / compute / download streams of the library so H2D, kernels and D2H overlap",
+                           "-> to_host_async), 11 row chunks (3 x 2048 rows, then halving down to 16: the un-overlapped tail is one small chunk) on upload / "
+                           "compute / download streams of the library so H2D, kernels and D2H overlap",
                     "naive": {"value": round(BYTES_STEP * world / (naive_ms * 1e-3) / 1e9, 3), "ms_per_step": round(naive_ms, 3),
                               "how": "from_host(pageable numpy) x3 -> operators -> to_host, one stream, wall clock", "same_result": naive_ok},
                     "host_link_ceiling": {"value": round(link_ceiling, 3), "unit": "GB/s", "ms_per_step": round(link_ms, 4),

@@ -142,3 +142,34 @@ describe DeviceNArray do
     end
   end
 end
+
+# Twin of the "RowPipeline.map_rows" block of tests/cpp/device_narray_spec.cpp.
+describe RowPipeline do
+  it "partitions the rows in order, tapering the last chunk" do
+    RowPipeline.row_chunks(8192_i64, 4_i64, 7).map { |(a, b)| b - a }.should eq [2048, 2048, 2048, 1024, 512, 256, 128, 64, 32, 16, 16]
+    RowPipeline.row_chunks(10_i64, 3_i64, 2).should eq [{0_i64, 4_i64}, {4_i64, 8_i64}, {8_i64, 9_i64}, {9_i64, 10_i64}]
+    RowPipeline.row_chunks(0_i64, 4_i64, 1).empty?.should be_true
+  end
+
+  it "computes a * b + c over pinned host operands like the resident arrays do" do
+    rows, cols = 1000, 768
+    a = NArray.build(rows, cols) { |_, i| ((i * 2654435761) % 2001).to_f32 / 1000 - 1 }
+    c = NArray.build(rows, cols) { |_, i| ((i * 40503) % 1999).to_f32 / 999 - 1 }
+    b = NArray.build(1, cols) { |_, i| ((i * 7919) % 2003).to_f32 / 1001 - 1 }
+    want = (a.to_device.broadcast(LibPhGpu::Op::Mul, b.to_device) + c.to_device).to_host
+    pa, pc, pb = PinnedArray(Float32).from(a), PinnedArray(Float32).from(c), PinnedArray(Float32).from(b)
+    out = PinnedArray(Float32).new([rows, cols])
+    pipe = RowPipeline.new(4_i64, 7)
+    pipe.map_rows([pa, pc], out, [pb]) { |ins, shared| ins[0].broadcast(LibPhGpu::Op::Mul, shared[0]) + ins[1] }
+    out.to_narr.should eq want
+    pipe.close
+  end
+
+  it "raises a pipelined step's data-dependent errors at its synchronising end" do
+    ia = PinnedArray(Int32).from(NArray.fill([64, 8], Int32::MAX))
+    io = PinnedArray(Int32).new([64, 8])
+    expect_raises(OverflowError) do
+      RowPipeline.new(4_i64, 2).map_rows([ia], io) { |ins, _| ins[0] + 1 }
+    end
+  end
+end

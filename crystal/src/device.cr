@@ -9,3 +9,4 @@ require "./device/device_view"
 require "./device/number_patch"
 require "./device/heat"
 require "./device/sharded_n_array"
+require "./device/pipeline"

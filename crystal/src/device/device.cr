@@ -107,11 +107,22 @@ module Phase
     getter ptr : Void*
     getter bytesize : Int64
     @parent : DeviceBuffer? = nil
+    @home : Void* = Pointer(Void).null
 
     def initialize(@bytesize : Int64)
       Device.ensure_init
       @ptr = Pointer(Void).null
       Device.check LibPhGpu.ph_alloc(LibC::SizeT.new({@bytesize, 1_i64}.max), pointerof(@ptr))
+      @home = LibPhGpu.ph_stream # the pool block is released on the stream it was handed out on
+    end
+
+    # The stream the block was allocated on (its release is ordered there).
+    def home_stream : Void*
+      if parent = @parent
+        parent.home_stream
+      else
+        @home
+      end
     end
 
     # A byte range of another buffer (one slice of a batched `slices` copy). It keeps its parent
@@ -124,7 +135,7 @@ module Phase
     # Eager release; the finalizer is only the safety net.
     def free : Nil
       return if @ptr.null? || @parent
-      LibPhGpu.ph_free(@ptr)
+      LibPhGpu.ph_free_on(@ptr, @home)
       @ptr = Pointer(Void).null
     end
 

@@ -187,6 +187,7 @@ class DeviceBuffer {
   explicit DeviceBuffer(size_t n) : nbytes(n ? n : 1) {
     Device::ensure_init();
     Device::check(ph_alloc(nbytes, &ptr));
+    home_ = ph_stream();              // the pool block is released on the stream it was handed out on
   }
   // A byte range of another buffer (one slice of a batched `slices` copy): keeps the parent alive and
   // never frees; the parent releases the whole allocation when the last range dies.
@@ -201,7 +202,8 @@ class DeviceBuffer {
     b->adopted_ = true;
     return b;
   }
-  ~DeviceBuffer() { if (ptr && !parent_ && !adopted_) ph_free(ptr); }
+  ~DeviceBuffer() { if (ptr && !parent_ && !adopted_) ph_free_on(ptr, home_); }
+  void* home_stream() const { return parent_ ? parent_->home_stream() : home_; }
   DeviceBuffer(const DeviceBuffer&) = delete;
   DeviceBuffer& operator=(const DeviceBuffer&) = delete;
 
@@ -209,6 +211,7 @@ class DeviceBuffer {
   DeviceBuffer() = default;
   std::shared_ptr<DeviceBuffer> parent_;
   bool adopted_ = false;
+  void* home_ = nullptr;
 };
 
 template <class T> class DeviceNArray;

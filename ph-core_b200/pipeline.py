@@ -18,13 +18,36 @@ import numpy as np
 from .narray import DeviceNArray, Stream, ShapeError, main_stream_wait, sync
 
 
+def row_chunks(n: int, chunks: int, taper: int = 0):
+    """[r0, r1) row ranges: `chunks` equal chunks; with taper = t the LAST one is cut again into halves t times
+    (per/2, per/4, ..., per/2^t, per/2^t).  What is left when the last upload ends is one chunk's kernels and
+    download -- nothing overlaps that tail -- so the final chunks are small while the early ones stay large
+    (every copy pays a fixed set-up, so many small chunks everywhere would cost more than the tail they save)."""
+    per = -(-n // max(1, chunks))
+    bounds, r = [], 0
+    while r < n:
+        bounds.append((r, min(n, r + per)))
+        r += per
+    if taper > 0 and bounds:
+        r0, r1 = bounds.pop()
+        for _ in range(taper):
+            mid = r0 + (r1 - r0 + 1) // 2
+            if mid >= r1:
+                break
+            bounds.append((r0, mid))
+            r0 = mid
+        bounds.append((r0, r1))
+    return bounds
+
+
 class RowPipeline:
     """Three streams by ROLE, reused across calls: one uploads, one computes, one downloads.  Uploads of all
     chunks are queued back to back (the host-to-device engine never waits for a kernel or a download of an
     earlier chunk); chunk k's operators wait for its upload, its download for its operators."""
 
-    def __init__(self, chunks: int = 16, streams: int = 3):
+    def __init__(self, chunks: int = 16, streams: int = 3, taper: int = 0):
         self.chunks = int(chunks)
+        self.taper = int(taper)
         self.up, self.comp, self.down = Stream(), Stream(), Stream()
         self.streams = [self.up, self.comp, self.down]
 
@@ -43,12 +66,8 @@ class RowPipeline:
             s.wait(None)                                           # behind whatever the main stream has queued
         with up:
             shared_dev = [DeviceNArray.from_host_async(x) for x in shared]
-        per = -(-n // self.chunks)
         keep = []
-        for k in range(self.chunks):
-            r0, r1 = k * per, min(n, (k + 1) * per)
-            if r0 >= r1:
-                break
+        for r0, r1 in row_chunks(n, self.chunks, self.taper):
             with up:
                 ins = [DeviceNArray.from_host_async(r[r0:r1]) for r in rows]
             comp.wait(up)                                          # chunk k's operands (and the shared ones) have landed

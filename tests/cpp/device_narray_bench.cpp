@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/ph_narray.hpp"
+#include "../../include/ph_pipeline.hpp"
 
 using namespace Phase;
 
@@ -56,6 +57,30 @@ int main() {
   ms = time_ms([&] { total = a.sum(); }, 2, 10, 1);
   std::printf("{\"row\": \"a.sum() incl. result read-back and flag check\", \"ms\": %.5f, \"gbs\": %.1f, \"ok\": %s}\n", ms,
               (double)N * 4 / ms / 1e6, (total > 1.5 * N * (1 - 1e-4) && total < 1.5 * N * (1 + 1e-4)) ? "true" : "false");
+  {
+    // per-axis fold incl. its raise point (the flag word read through the pinned record)
+    auto m32 = DeviceNArray<float>::fill({16384, 16384}, 0.5f);
+    ms = time_ms([&] { auto s = m32.sum(0); (void)s; }, 2, 10, 4);
+    std::printf("{\"row\": \"sum(axis 0) of [16384,16384] f32 incl. the flag check\", \"ms\": %.5f, \"gbs\": %.1f}\n", ms,
+                (16384.0 * 16384 * 4 + 16384 * 4) / ms / 1e6);
+  }
+  {
+    // END TO END with HOST operands through the compiled host layer: pinned a, b, c -> a * b + c -> pinned result,
+    // uploads, kernels and download inside every timed step (RowPipeline, ph_pipeline.hpp)
+    PinnedArray<float> ha({R, Cc}), hc({R, Cc}), hb({1, Cc}), hout({R, Cc});
+    for (int64_t i = 0; i < N; i++) { ha[i] = (float)((i * 2654435761u) % 2001) / 1000.0f - 1.0f; hc[i] = (float)((i * 40503u) % 1999) / 999.0f - 1.0f; }
+    for (int64_t i = 0; i < Cc; i++) hb[i] = (float)((i * 7919u) % 2003) / 1001.0f - 1.0f;
+    RowPipeline pipe(4, 7);
+    auto expr = [](const std::vector<DeviceNArray<float>>& in, const std::vector<DeviceNArray<float>>& shared) {
+      return in[0].broadcast_op(PH_MUL, shared[0]) + in[1];
+    };
+    ms = time_ms([&] { pipe.map_rows<float>(expr, {&ha, &hc}, hout, {&hb}, false); }, 1, 3, 4);
+    Device::sync();
+    bool ok = true;
+    for (int64_t i = 0; i < N && ok; i += 4099) ok = hout[i] == ha[i] * hb[i % Cc] + hc[i];       // two roundings, no FMA (-ffp-contract=off)
+    std::printf("{\"row\": \"e2e: RowPipeline.map_rows(a * b + c), pinned host in / out, 11 tapered chunks\", \"ms\": %.5f, \"gbs\": %.1f, "
+                "\"h2d_bytes\": %.0f, \"d2h_bytes\": %.0f, \"ok\": %s}\n", ms, bytes_two / ms / 1e6, 2.0 * N * 4 + Cc * 4, 1.0 * N * 4, ok ? "true" : "false");
+  }
   std::printf("{\"kernel_launches\": %lld}\n", (long long)ph_launch_count());
   Device::shutdown();
   return 0;

@@ -21,6 +21,7 @@
 
 #include "../../include/ph_narray.hpp"
 #include "../../include/ph_narray_io.hpp"
+#include "../../include/ph_pipeline.hpp"
 
 using namespace Phase;
 template <class T> using V = std::vector<T>;
@@ -160,6 +161,23 @@ static void partition_host_specs() {
 }
 
 // JSON / YAML goldens of spec/n_array_spec.cr:520-558 and the binary dump, host side only
+static void pipeline_host_specs() {
+  it("row_chunks: every schedule is an ordered partition of the rows; the taper halves the last chunk", [] {
+    for (int64_t n : {0, 1, 7, 10, 1000, 8192})
+      for (int64_t chunks : {1, 2, 3, 4, 8, 16, 50})
+        for (int taper : {0, 1, 3, 7, 12}) {
+          int64_t at = 0;
+          bool ok = true;
+          for (const auto& c : row_chunks(n, chunks, taper)) { ok = ok && c.first == at && c.second > c.first; at = c.second; }
+          EXPECT(ok && at == n);
+        }
+    std::vector<int64_t> sizes;
+    for (const auto& c : row_chunks(8192, 4, 7)) sizes.push_back(c.second - c.first);
+    EXPECT(sizes == std::vector<int64_t>({2048, 2048, 2048, 1024, 512, 256, 128, 64, 32, 16, 16}));
+    EXPECT(row_chunks(8192, 16).size() == 16 && row_chunks(8192, 16)[15] == std::make_pair<int64_t, int64_t>(7680, 8192));
+  });
+}
+
 static void io_host_specs() {
   it("to_json / from_json / to_yaml / from_yaml goldens (n_array_spec.cr:520-558)", [] {
     namespace H = IO::host;
@@ -231,6 +249,7 @@ int main(int argc, char** argv) {
     host_specs();
     io_host_specs();
     partition_host_specs();
+    pipeline_host_specs();
     std::printf("%d expectations passed, %d failed (host-only)\n", g_passed, g_failed);
     return g_failed ? 1 : 0;
   }
@@ -517,6 +536,42 @@ int main(int argc, char** argv) {
     auto nxt = s.clone();
     nxt.set_chunk({range_ex(1, -1), range_ex(1, -1)}, c + (d0 + d1) * C);
     EXPECT(Heat::update_temp(s, C) == nxt);                                  // bit-identical
+  });
+
+  // ---- streams, pinned arrays, asynchronous transfers, the chunked host -> device -> host pipeline (ph_pipeline.hpp)
+  it("RowPipeline.map_rows: a*b+c over pinned host operands equals the resident computation, bit for bit", [] {
+    const int64_t R = 1000, Cc = 768;                                        // ragged chunks
+    V<float> av((size_t)(R * Cc)), cv((size_t)(R * Cc)), bv((size_t)Cc);
+    for (size_t i = 0; i < av.size(); i++) { av[i] = (float)((i * 2654435761u) % 2001) / 1000.0f - 1.0f; cv[i] = (float)((i * 40503u) % 1999) / 999.0f - 1.0f; }
+    for (size_t i = 0; i < bv.size(); i++) bv[i] = (float)((i * 7919u) % 2003) / 1001.0f - 1.0f;
+    PinnedArray<float> a({R, Cc}, av), c({R, Cc}, cv), b({1, Cc}, bv), out({R, Cc});
+    auto want = (narr<float>({R, Cc}, av).broadcast_op(PH_MUL, narr<float>({1, Cc}, bv)) + narr<float>({R, Cc}, cv)).to_host();
+    auto expr = [](const std::vector<DeviceNArray<float>>& in, const std::vector<DeviceNArray<float>>& shared) {
+      return in[0].broadcast_op(PH_MUL, shared[0]) + in[1];
+    };
+    RowPipeline equal(8, 0), tapered(4, 7);
+    for (RowPipeline* pipe : {&equal, &tapered, &equal}) {                   // streams and pool blocks are reused
+      std::memset(out.data(), 0, (size_t)out.size() * sizeof(float));
+      pipe->map_rows<float>(expr, {&a, &c}, out, {&b});
+      EXPECT(std::memcmp(out.data(), want.data(), want.size() * sizeof(float)) == 0);
+    }
+    // data-dependent errors of a pipelined step surface at its synchronising end
+    PinnedArray<int32_t> ia({64, 8}, V<int32_t>(512, std::numeric_limits<int32_t>::max())), io({64, 8});
+    RowPipeline ip(4, 2);
+    EXPECT_RAISES(OverflowError, ip.map_rows<int32_t>([](const std::vector<DeviceNArray<int32_t>>& in, const std::vector<DeviceNArray<int32_t>>&) { return in[0] + 1; }, {&ia}, io));
+    // a row operand with another leading extent is a ShapeError before anything is queued
+    PinnedArray<float> shorter({R - 1, Cc});
+    EXPECT_RAISES(ShapeError, equal.map_rows<float>(expr, {&a, &shorter}, out, {&b}));
+    // explicit streams: two chains ordered by wait(), joined by the main stream
+    Stream s1, s2;
+    DeviceNArray<float> x = [&] { StreamScope on(s1); return from_host_async<float>({R, Cc}, a.data()) * 2.0f; }();
+    s2.wait(&s1);
+    { StreamScope on(s2); to_host_async<float>(x + 1.0f, out.data()); }
+    main_stream_wait(s2);
+    Device::sync();
+    bool same = true;
+    for (size_t i = 0; i < av.size() && same; i++) same = out[(int64_t)i] == av[i] * 2.0f + 1.0f;
+    EXPECT(same);
   });
 
   std::printf("%d expectations passed, %d failed, %lld kernel launches\n", g_passed, g_failed, (long long)ph_launch_count());

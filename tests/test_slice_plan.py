@@ -59,3 +59,18 @@ def test_whole_leading_axis_is_local_and_bad_literals_raise_like_the_reference()
         S.slice_plan(G.shape, [rng(0, 11)], 4, 0)                          # ..11 on a bound of 11 (spec_helper.cr:133-139)
     with pytest.raises(Exception):
         S.slice_plan(G.shape, [0, 0, 0, 0], 4, 0)                          # more entries than axes -> DimensionError
+
+
+def test_row_chunks_cover_the_rows_once_and_taper_at_the_end():
+    """pipeline.row_chunks: equal chunks, the last one optionally cut into halves (the un-overlapped tail of a
+    host -> device -> host pipeline is its last chunk); every schedule is a partition of [0, n) in order."""
+    from ph_core_b200.pipeline import row_chunks
+    for n in (0, 1, 7, 10, 1000, 8192):
+        for chunks in (1, 2, 3, 4, 8, 16, 50):
+            for taper in (0, 1, 3, 7, 12):
+                b = row_chunks(n, chunks, taper)
+                assert [r for lo, hi in b for r in range(lo, hi)] == list(range(n)), (n, chunks, taper)
+                assert all(lo < hi for lo, hi in b)
+    b = row_chunks(8192, 4, 7)
+    assert [hi - lo for lo, hi in b] == [2048, 2048, 2048, 1024, 512, 256, 128, 64, 32, 16, 16]
+    assert row_chunks(8192, 16, 0) == [(k * 512, (k + 1) * 512) for k in range(16)]
