@@ -26,8 +26,8 @@ BYTES = 5 * R * COLS * 4 + COLS * 4
 expr = lambda x, z, y: x.broadcast_op("*", y) + z
 ms = C.c_float()
 ref = None
-for chunks, taper in [(16, 0), (8, 4), (4, 7), (3, 7), (2, 7), (2, 9), (1, 8), (1, 10), (1, 12)]:
-    pipe = ph.pipeline.RowPipeline(chunks=chunks, taper=taper)
+for chunks, taper, ups in [(16, 0, 1), (4, 7, 1), (4, 7, 2), (16, 0, 2), (8, 4, 2), (2, 7, 2), (32, 0, 2)]:
+    pipe = ph.pipeline.RowPipeline(chunks=chunks, taper=taper, uploaders=ups)
     step = lambda: pipe.map_rows(expr, rows=[a_pin, c_pin], out=out_pin, shared=[b_pin], wait=False)
     step(); ph.sync()
     if ref is None:
@@ -41,7 +41,7 @@ for chunks, taper in [(16, 0), (8, 4), (4, 7), (3, 7), (2, 7), (2, 9), (1, 8), (
         ts.append(ms.value / 4)
     ph.sync()
     ok = bool(out_pin.tobytes() == ref.tobytes())
-    print(json.dumps({"chunks": chunks, "taper": taper, "n_chunks": len(ph.pipeline.row_chunks(R, chunks, taper)),
+    print(json.dumps({"chunks": chunks, "taper": taper, "uploaders": ups, "n_chunks": len(ph.pipeline.row_chunks(R, chunks, taper)),
                       "ms_best": round(min(ts), 4), "ms_median": round(sorted(ts)[1], 4),
                       "gbs": round(BYTES / (sorted(ts)[1] * 1e-3) / 1e9, 2), "same_result": ok}), flush=True)
     pipe.close()

@@ -45,11 +45,14 @@ class RowPipeline:
     chunks are queued back to back (the host-to-device engine never waits for a kernel or a download of an
     earlier chunk); chunk k's operators wait for its upload, its download for its operators."""
 
-    def __init__(self, chunks: int = 16, streams: int = 3, taper: int = 0):
+    def __init__(self, chunks: int = 16, streams: int = 3, taper: int = 0, uploaders: int = 1):
         self.chunks = int(chunks)
         self.taper = int(taper)
         self.up, self.comp, self.down = Stream(), Stream(), Stream()
-        self.streams = [self.up, self.comp, self.down]
+        # uploaders > 1: the row operands of a chunk go up on different streams, so one copy's set-up runs under
+        # another copy's transfer (experiment knob; 1 = every upload on `up`)
+        self.ups = [self.up] + [Stream() for _ in range(max(0, int(uploaders) - 1))]
+        self.streams = self.ups + [self.comp, self.down]
 
     def map_rows(self, fn: Callable, rows: Sequence[np.ndarray], out: np.ndarray, shared: Sequence[np.ndarray] = (),
                  wait: bool = True) -> None:
@@ -68,9 +71,12 @@ class RowPipeline:
             shared_dev = [DeviceNArray.from_host_async(x) for x in shared]
         keep = []
         for r0, r1 in row_chunks(n, self.chunks, self.taper):
-            with up:
-                ins = [DeviceNArray.from_host_async(r[r0:r1]) for r in rows]
-            comp.wait(up)                                          # chunk k's operands (and the shared ones) have landed
+            ins = []
+            for i, r in enumerate(rows):
+                with self.ups[i % len(self.ups)]:
+                    ins.append(DeviceNArray.from_host_async(r[r0:r1]))
+            for u in self.ups:
+                comp.wait(u)                                       # chunk k's operands (and the shared ones) have landed
             with comp:
                 res = fn(*ins, *shared_dev)
             down.wait(comp)
@@ -80,7 +86,9 @@ class RowPipeline:
             del ins, res
         # device temporaries are released on the streams they were allocated on: order each of those behind
         # every consumer before letting go, then join the main stream
-        up.wait(comp); up.wait(down); comp.wait(down)
+        for u in self.ups:
+            u.wait(comp); u.wait(down)
+        comp.wait(down)
         for s in self.streams:
             main_stream_wait(s)
         del keep, shared_dev
