@@ -43,7 +43,10 @@ def row_chunks(n: int, chunks: int, taper: int = 0):
 class RowPipeline:
     """Three streams by ROLE, reused across calls: one uploads, one computes, one downloads.  Uploads of all
     chunks are queued back to back (the host-to-device engine never waits for a kernel or a download of an
-    earlier chunk); chunk k's operators wait for its upload, its download for its operators."""
+    earlier chunk); chunk k's operators wait for its upload, its download for its operators.  (Spreading the
+    uploads of a chunk over TWO streams is slower: 4 + 7 halvings 10.74 -> 11.77 ms, 16 equal chunks 11.18 -> 11.40,
+    profiles/r02_pipeline_schedules.jsonl -- concurrent host-to-device copies share the link and the chunk is
+    complete later.)"""
 
     def __init__(self, chunks: int = 16, streams: int = 3, taper: int = 0, uploaders: int = 1):
         self.chunks = int(chunks)
