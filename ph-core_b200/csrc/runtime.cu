@@ -244,6 +244,9 @@ int32_t ph_init(int32_t device) {
   cudaDeviceProp prop;
   PH_CUDA(cudaGetDeviceProperties(&prop, device));
   r.sm_count = prop.multiProcessorCount;
+  // (An L2 set-aside for persisting lines -- cudaLimitPersistingL2CacheSize -- makes the chained elementwise launches
+  // SLOWER, not faster: a*b+c 6831 GB/s with the driver's default, 5959 / 5190 / 4859 with 32 / 64 / 128 MB set aside,
+  // profiles/r02_l2_persist_setaside.txt.  The evict_first / evict_last qualifiers of ph_common.cuh work without it.)
   PH_CUDA(cudaStreamCreateWithFlags(&r.own_stream, cudaStreamNonBlocking));
   {
     // the side stream carries halo edges + exchange of sharded stencil runs: highest priority, so its
