@@ -173,3 +173,25 @@ describe RowPipeline do
     end
   end
 end
+
+# Twin of the "NArray.concatenate / push / << / wrap" block of tests/cpp/device_narray_spec.cpp.
+describe "joins" do
+  it "concatenates along an axis with one copy per input" do
+    a = NArray[[0, 1, 2], [3, 4, 5]].to_device
+    b = NArray[[10, 11, 12]].to_device
+    c = NArray[[20, 21], [22, 23]].to_device
+    DeviceNArray(Int32).concatenate(a, b, axis: 0).to_host.should eq NArray[[0, 1, 2], [3, 4, 5], [10, 11, 12]]
+    a.concatenate(c, axis: 1).to_host.should eq NArray[[0, 1, 2, 20, 21], [3, 4, 5, 22, 23]]
+    expect_raises(DimensionError) { DeviceNArray(Int32).concatenate(a, c, axis: 0) }
+    expect_raises(DimensionError) { DeviceNArray(Int32).concatenate(a, c, axis: -1) } # a negative axis excludes nothing
+  end
+
+  it "pushes in place and wraps" do
+    a = NArray[[0, 1, 2], [3, 4, 5]].to_device
+    p = a.clone
+    (p << NArray[[10, 11, 12]].to_device).should be p
+    p.to_host.should eq NArray[[0, 1, 2], [3, 4, 5], [10, 11, 12]]
+    DeviceNArray(Int32).wrap(a, a).shape.should eq [2, 2, 3]
+    expect_raises(DimensionError) { DeviceNArray(Int32).wrap(a, p) }
+  end
+end

@@ -122,6 +122,87 @@ module Phase
       view.reverse.to_narr
     end
 
+    # ---- joins (`src/n_array.cr:321-344, 666-750`): one strided copy per input ---------------
+
+    # `NArray#compatible?` (`src/n_array.cr:666-673`), kept as it is: the comparison is `idx != axis`
+    # on the raw argument, so a negative axis excludes nothing.
+    def compatible?(*others : DeviceIndexable(T), axis = -1) : Bool
+      DeviceNArray.compatible_shapes?(shape, others.map(&.shape).to_a, axis)
+    end
+
+    protected def self.compatible_shapes?(first : Array(Int32), others : Array(Array(Int32)), axis : Int) : Bool
+      first.each_with_index do |dim, idx|
+        others.each do |other|
+          return false if dim != other[idx] && idx != axis # `other[idx]` raises IndexError on a shorter shape
+        end
+      end
+      true
+    end
+
+    # `NArray.concatenate(*narrs, axis)`: the inputs side by side along `axis`; arrays and views alike.
+    def self.concatenate(*narrs : DeviceIndexable(T), axis = 0) : DeviceNArray(T)
+      first = narrs[0]
+      shapes = narrs.map(&.shape).to_a
+      unless compatible_shapes?(first.shape, shapes, axis) && shapes.all? { |other| other.size == first.shape.size }
+        raise DimensionError.new("Cannot concatenate these arrays along axis #{axis}: shapes do not match")
+      end
+      concat_shape = first.shape
+      concat_shape[axis] = narrs.sum { |narr| narr.shape[axis] } # IndexError when `axis` is not an axis
+      ax = axis < 0 ? axis + concat_shape.size : axis
+      result = DeviceNArray(T).new(concat_shape)
+      at = 0
+      narrs.each do |narr|
+        n = narr.shape[ax]
+        if n > 0 && result.size > 0
+          literal = Array(Range(Int32, Int32)).new(concat_shape.size) { |i| i == ax ? (at..at + n - 1) : (0..concat_shape[i] - 1) }
+          result.unsafe_set_chunk(IndexRegion.new(literal, concat_shape, drop: false), narr)
+        end
+        at += n
+      end
+      result
+    end
+
+    def concatenate(*others : DeviceIndexable(T), axis = 0) : DeviceNArray(T)
+      DeviceNArray(T).concatenate(self, *others, axis: axis)
+    end
+
+    # `NArray#push`, in place: the buffers are appended as they lie and only `shape[0]` grows,
+    # whatever `axis` says (`axis` merely relaxes the compatibility test -- the reference's own
+    # TODO). Arrays made by `reshape` before the push keep the old buffer.
+    def push(*others : DeviceIndexable(T), axis = 0) : self
+      raise DimensionError.new("Cannot concatenate these arrays along axis #{axis}: shapes do not match") if !compatible?(*others, axis: axis)
+      total = size + others.sum(&.size)
+      grown = DeviceBuffer.new(total * sizeof(T))
+      at = 0_i64
+      {self, *others}.each do |narr|
+        flat = narr.is_a?(DeviceNArray(T)) ? narr : narr.to_narr
+        if flat.size > 0
+          dst = (grown.ptr.as(UInt8*) + at * sizeof(T)).as(Void*)
+          Device.check LibPhGpu.ph_d2d(dst, flat.dev.ptr, LibC::SizeT.new(flat.size * sizeof(T)))
+        end
+        at += flat.size
+      end
+      @shape[0] += others.sum { |narr| narr.shape[0] }
+      @dev = grown
+      @desc = Descriptor.contiguous(@shape)
+      self
+    end
+
+    def <<(other : DeviceIndexable(T)) : self
+      push(other)
+    end
+
+    # `NArray.wrap(*objects, pad: false)`: a new leading axis with one input per row.
+    def self.wrap(*objects : DeviceIndexable(T), pad = false) : DeviceNArray(T)
+      raise NotImplementedError.new("As of this time, NArray.wrap() cannot pad arrays for you.") if pad
+      container = objects[0].shape
+      if objects.any? { |obj| obj.shape != container }
+        raise DimensionError.new("Cannot wrap these arrays: shapes do not match. Pass argument pad:true if you want to reshape arrays as necessary.")
+      end
+      rows = objects.map { |obj| obj.to_narr.reshape([1] + container) }
+      concatenate(*rows, axis: 0)
+    end
+
     # Releases the HBM now instead of at the next GC cycle.
     def free : Nil
       @dev.free

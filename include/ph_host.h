@@ -76,6 +76,12 @@ int32_t ph_region_translate(ph_region* r, const int64_t* offset, int32_t noffset
 int32_t ph_shapes_compatible(const int64_t* a, int32_t na, const int64_t* b, int32_t nb, int32_t* ok);
 /* NEW ShapeUtil.broadcast_shapes: equal rank, each axis equal or 1 */
 int32_t ph_broadcast_shapes(const int64_t* a, const int64_t* b, int32_t rank, int64_t* out);
+/* NArray.concatenate's shape rule (n_array.cr:666-673 compatible?, :722-731): `shapes` holds n shapes of `ranks[i]`
+ * entries each, packed at a pitch of PH_MAX_RANK.  Every dimension of the FIRST shape must equal the same dimension of
+ * every other shape except at index `axis` -- compared on the raw argument, so a negative axis excludes nothing
+ * (PH_HOST_DIMENSION_ERROR; a shorter shape, or an axis outside the first shape, is PH_HOST_INDEX_ERROR).
+ * out_shape = the first shape with extent[axis] summed over the inputs; *out_axis = the canonical (non-negative) axis. */
+int32_t ph_concat_shape(const int64_t* shapes, const int32_t* ranks, int32_t n, int32_t axis, int64_t* out_shape, int32_t* out_axis);
 
 /* Buffered.axis_strides (buffered.cr:15-24) as a descriptor of a whole row-major array */
 int32_t ph_desc_contiguous(const int64_t* shape, int32_t rank, ph_desc* out);

@@ -500,6 +500,12 @@ class DeviceNArray : public MultiIndexable<T> {
     return DeviceNArray(new_shape, this->buf_);
   }
   DeviceNArray flatten() const { return reshape({this->size()}); }
+  // ---- joins (n_array.cr:321-344, 666-750): one strided copy per input ----------------------
+  static DeviceNArray concatenate(const std::vector<const MultiIndexable<T>*>& narrs, int32_t axis = 0);   // NArray.concatenate :722-724
+  DeviceNArray concatenate(const MultiIndexable<T>& other, int32_t axis = 0) const { return concatenate({this, &other}, axis); }   // :712-714
+  DeviceNArray& push(const std::vector<const MultiIndexable<T>*>& others, int32_t axis = 0);               // push :688-710, in place
+  DeviceNArray& operator<<(const MultiIndexable<T>& other) { return push({&other}); }                      // << :682-684
+  static DeviceNArray wrap(const std::vector<const MultiIndexable<T>*>& narrs);                            // NArray.wrap :321-340
   // copying permute / reverse = view + to_narr (multi_indexable.cr:795-803)
   DeviceNArray permute(const std::vector<int32_t>& order = {}) const;
   DeviceNArray reverse() const;
@@ -842,6 +848,86 @@ PH_CMP_(<=, PH_LE, PH_GE)
 #undef PH_CMP_
 template <class T> bool operator==(const MultiIndexable<T>& a, const MultiIndexable<T>& b) { return a.equals(b); }
 template <class T> bool operator!=(const MultiIndexable<T>& a, const MultiIndexable<T>& b) { return !a.equals(b); }
+
+// ---- joins: NArray.concatenate / push / wrap (n_array.cr:321-344, 666-750) ----------------------------------
+// The shape rule is the reference's `compatible?` (ph_concat_shape: `idx != axis` on the raw argument, so a negative
+// axis excludes nothing and every dimension must then match).  Each input is ONE scatter into its range of the result.
+inline Shape concat_shape_of(const std::vector<Shape>& shapes, int32_t axis, int32_t* canonical_axis) {
+  std::vector<int64_t> packed(shapes.size() * PH_MAX_RANK, 0);
+  std::vector<int32_t> ranks(shapes.size());
+  for (size_t k = 0; k < shapes.size(); k++) {
+    if (shapes[k].size() > (size_t)PH_MAX_RANK) throw ShapeError("the device path supports rank <= " + std::to_string(PH_MAX_RANK));
+    ranks[k] = (int32_t)shapes[k].size();
+    for (size_t i = 0; i < shapes[k].size(); i++) packed[k * PH_MAX_RANK + i] = shapes[k][i];
+  }
+  int64_t out[PH_MAX_RANK] = {0};
+  Device::host_check(ph_concat_shape(packed.data(), ranks.data(), (int32_t)shapes.size(), axis, out, canonical_axis));
+  return Shape(out, out + shapes[0].size());
+}
+template <class T>
+DeviceNArray<T> DeviceNArray<T>::concatenate(const std::vector<const MultiIndexable<T>*>& narrs, int32_t axis) {
+  if (narrs.empty()) throw DimensionError("Cannot concatenate: nothing to concatenate");
+  std::vector<Shape> shapes;
+  for (const MultiIndexable<T>* a : narrs) shapes.push_back(a->shape());
+  int32_t ax = 0;
+  const Shape shape = concat_shape_of(shapes, axis, &ax);
+  DeviceNArray<T> out(shape);
+  int64_t at = 0;
+  for (const MultiIndexable<T>* a : narrs) {
+    const int64_t n = a->shape()[(size_t)ax];
+    if (n && out.size()) {
+      RegionLiteral lit(shape.size(), all);
+      lit[(size_t)ax] = range(at, at + n - 1);
+      out.unsafe_set_chunk(IndexRegion(lit, shape, false), *a);
+    }
+    at += n;
+  }
+  return out;
+}
+// push: the buffers are appended as they lie and ONLY shape[0] grows, whatever `axis` says (`axis` merely relaxes the
+// compatibility test -- the reference's own TODO).  Arrays made by reshape before the push keep the old buffer.
+template <class T>
+DeviceNArray<T>& DeviceNArray<T>::push(const std::vector<const MultiIndexable<T>*>& others, int32_t axis) {
+  if (others.empty()) return *this;
+  std::vector<Shape> shapes{this->shape_};
+  for (const MultiIndexable<T>* o : others) shapes.push_back(o->shape());
+  int32_t ax = 0;
+  concat_shape_of(shapes, axis, &ax);                                  // compatible? -> DimensionError
+  int64_t total = this->size(), rows = this->shape_[0];
+  for (const MultiIndexable<T>* o : others) { total += o->size(); rows += o->shape()[0]; }
+  Shape new_shape = this->shape_;
+  new_shape[0] = rows;
+  if (shape_to_size(new_shape) != total)
+    throw ShapeError("Cannot change shape from [" + std::to_string(total) + "] to " + shape_str(new_shape) + ": reshape cannot add or remove elements.");
+  auto buf = std::make_shared<DeviceBuffer>((size_t)total * sizeof(T));
+  int64_t at = 0;
+  auto append = [&](const MultiIndexable<T>& a) {
+    const DeviceNArray<T> flat = a.to_narr();
+    if (flat.size()) Device::check(ph_d2d(static_cast<T*>(buf->ptr) + at, flat.data(), (size_t)flat.size() * sizeof(T)));
+    at += flat.size();
+  };
+  append(*this);
+  for (const MultiIndexable<T>* o : others) append(*o);
+  this->buf_ = std::move(buf);
+  this->shape_ = new_shape;
+  this->desc_ = contiguous_desc(new_shape);
+  return *this;
+}
+template <class T>
+DeviceNArray<T> DeviceNArray<T>::wrap(const std::vector<const MultiIndexable<T>*>& narrs) {
+  if (narrs.empty()) throw DimensionError("Cannot wrap these arrays: nothing to wrap");
+  const Shape container = narrs[0]->shape();
+  for (const MultiIndexable<T>* a : narrs)
+    if (a->shape() != container)
+      throw DimensionError("Cannot wrap these arrays: shapes do not match. Pass argument pad:true if you want to reshape arrays as necessary.");
+  Shape row = container;
+  row.insert(row.begin(), 1);
+  std::vector<DeviceNArray<T>> rows;
+  for (const MultiIndexable<T>* a : narrs) rows.push_back(a->to_narr().reshape(row));
+  std::vector<const MultiIndexable<T>*> ptrs;
+  for (const DeviceNArray<T>& r : rows) ptrs.push_back(&r);
+  return concatenate(ptrs, 0);
+}
 
 // ---- the stencil of examples/heat_equation.cr:26-51 ---------------------------------------------
 namespace Heat {

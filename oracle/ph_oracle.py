@@ -744,6 +744,74 @@ def each_slice(narr: np.ndarray, axis: int = 0):
 
 
 # --------------------------------------------------------------------------
+# concatenate / push / wrap (src/n_array.cr:321-344, 666-750): the joins one step above the gather / scatter path
+# --------------------------------------------------------------------------
+def shapes_compatible_except(first_shape: Sequence[int], other_shapes: Sequence[Sequence[int]], axis: int = -1) -> bool:
+    """NArray#compatible?(*others, axis) (n_array.cr:666-673): every dimension of `first` equals the same dimension
+    of every other array, except at index `axis`.  The comparison is `idx != axis` on the RAW argument: a negative
+    axis excludes nothing (so `concatenate(axis: -1)` demands identical shapes -- kept, it is the reference's rule)."""
+    for idx, dim in enumerate(first_shape):
+        for sh in other_shapes:
+            if idx >= len(sh):
+                raise CrIndexError("Index out of bounds")            # Array#[] on the shorter shape
+            if dim != sh[idx] and idx != axis:
+                return False
+    return True
+
+
+def concatenate(narrs: Sequence[np.ndarray], axis: int = 0) -> np.ndarray:
+    """NArray.concatenate / concatenate_to_slice (n_array.cr:722-750), loop for loop: for every index over the axes
+    in FRONT of `axis` (`num_chunks`), every array in turn contributes `shape[axis] * axis_strides[axis]` elements
+    from its own lexicographic iterator.  The stride is taken from the FIRST array (`narrs[0].axis_strides[axis]`)."""
+    narrs = [np.asarray(a) for a in narrs]
+    first = narrs[0]
+    if not shapes_compatible_except(first.shape, [a.shape for a in narrs], axis):
+        raise DimensionError(f"Cannot concatenate these arrays along axis {axis}: shapes do not match")
+    if axis >= first.ndim or axis < -first.ndim:
+        raise CrIndexError("Index out of bounds")
+    concat_shape = list(first.shape)
+    concat_shape[axis] = sum(a.shape[axis] for a in narrs)
+    partial_chunk_size = axis_strides(first.shape)[axis]
+    chunk_sizes = [a.shape[axis] * partial_chunk_size for a in narrs]
+    lead = concat_shape[:axis] if axis >= 0 else concat_shape[:first.ndim + axis]     # concat_shape[...axis]
+    num_chunks = shape_to_size(lead) if lead else 1                                    # ([] of Int32).product == 1
+    flats = [a.reshape(-1) for a in narrs]                                             # BufferedECIterator: lex order
+    pos = [0] * len(narrs)
+    values = []
+    for _ in range(num_chunks):
+        for i, flat in enumerate(flats):
+            values.append(flat[pos[i]:pos[i] + chunk_sizes[i]])
+            pos[i] += chunk_sizes[i]
+    out = np.concatenate(values) if values else np.zeros(0, first.dtype)
+    return out.astype(first.dtype, copy=False).reshape(concat_shape)
+
+
+def push(narr: np.ndarray, others: Sequence[np.ndarray], axis: int = 0) -> np.ndarray:
+    """NArray#push / << (n_array.cr:682-710): the buffers are appended as they lie and ONLY shape[0] grows, whatever
+    `axis` says (the reference's own TODO: "axis = 0 should not be a user modifiable parameter"); `axis` only
+    relaxes the compatibility test."""
+    others = [np.asarray(o) for o in others]
+    if not shapes_compatible_except(narr.shape, [o.shape for o in others], axis):
+        raise DimensionError(f"Cannot concatenate these arrays along axis {axis}: shapes do not match")
+    flat = np.concatenate([narr.reshape(-1)] + [o.reshape(-1) for o in others])
+    shape = list(narr.shape)
+    shape[0] += sum(o.shape[0] for o in others)
+    return flat.reshape(shape)          # raises when an `axis` != 0 let sizes through that do not fill the rows
+
+
+def wrap(narrs: Sequence[np.ndarray]) -> np.ndarray:
+    """NArray.wrap(*objects, pad: false) (n_array.cr:321-340): a new leading axis, one input per row; shapes must
+    be identical (DimensionError)."""
+    narrs = [np.asarray(a) for a in narrs]
+    container = list(narrs[0].shape)
+    if any(list(a.shape) != container for a in narrs):
+        raise DimensionError("Cannot wrap these arrays: shapes do not match. Pass argument pad:true if you want to "
+                             "reshape arrays as necessary.")
+    flat = np.concatenate([a.reshape(-1) for a in narrs]) if narrs else np.zeros(0)
+    return flat.reshape([len(narrs)] + container)
+
+
+# --------------------------------------------------------------------------
 # Elementwise number semantics (Crystal 1.0.0 stdlib; SURVEY.md 7.3).
 # Every function returns (result ndarray, flags) where flags is a set of
 # {"overflow", "div0", "argument"} naming the exception the reference would raise.

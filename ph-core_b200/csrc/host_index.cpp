@@ -284,6 +284,29 @@ int32_t ph_broadcast_shapes(const int64_t* a, const int64_t* b, int32_t rank, in
   return PH_HOST_OK;
 }
 
+int32_t ph_concat_shape(const int64_t* shapes, const int32_t* ranks, int32_t n, int32_t axis, int64_t* out_shape, int32_t* out_axis) {
+  if (!shapes || !ranks || !out_shape || !out_axis || n < 1) return fail(PH_HOST_INVALID, "bad argument to ph_concat_shape");
+  const int rank = ranks[0];
+  if (rank < 0 || rank > PH_MAX_RANK) return fail(PH_HOST_INVALID, "rank out of range");
+  for (int idx = 0; idx < rank; idx++)                       // shape.each_with_index { |dim, idx| others.each { ... } }
+    for (int k = 0; k < n; k++) {
+      if (ranks[k] > PH_MAX_RANK) return fail(PH_HOST_INVALID, "rank out of range");
+      if (idx >= ranks[k]) return fail(PH_HOST_INDEX_ERROR, "Index out of bounds");
+      if (shapes[(size_t)k * PH_MAX_RANK + idx] != shapes[idx] && idx != axis)
+        return fail(PH_HOST_DIMENSION_ERROR, "Cannot concatenate these arrays along axis %d: shapes do not match", axis);
+    }
+  for (int k = 1; k < n; k++)                                // (an input of HIGHER rank would desynchronise the reference's iterators)
+    if (ranks[k] != rank) return fail(PH_HOST_DIMENSION_ERROR, "Cannot concatenate these arrays along axis %d: shapes do not match", axis);
+  if (axis >= rank || axis < -rank) return fail(PH_HOST_INDEX_ERROR, "Index out of bounds");
+  const int ax = axis < 0 ? axis + rank : axis;
+  int64_t total = 0;
+  for (int k = 0; k < n; k++) total += shapes[(size_t)k * PH_MAX_RANK + ax];
+  for (int i = 0; i < rank; i++) out_shape[i] = shapes[i];
+  out_shape[ax] = total;
+  *out_axis = ax;
+  return PH_HOST_OK;
+}
+
 int32_t ph_desc_contiguous(const int64_t* shape, int32_t rank, ph_desc* out) {
   if (!out || rank < 0 || rank > PH_MAX_RANK) return fail(PH_HOST_INVALID, "bad argument");
   memset(out, 0, sizeof(*out));

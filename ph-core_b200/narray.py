@@ -838,6 +838,41 @@ class _Indexable:
         raise_for_flags(DeviceNArray.take_flags())
 
 
+def _concat_shape(shapes, axis: int):
+    """ph_concat_shape (include/ph_host.h): the reference's `compatible?` + the concatenated shape."""
+    n = len(shapes)
+    packed = (C.c_int64 * (n * _lib.PH_MAX_RANK))()
+    ranks = (C.c_int32 * n)()
+    for k, sh in enumerate(shapes):
+        if len(sh) > _lib.PH_MAX_RANK:
+            raise ShapeError(f"the device path supports rank <= {_lib.PH_MAX_RANK}")
+        ranks[k] = len(sh)
+        for i, d in enumerate(sh):
+            packed[k * _lib.PH_MAX_RANK + i] = int(d)
+    out = (C.c_int64 * _lib.PH_MAX_RANK)()
+    ax = C.c_int32(0)
+    host_check(_lib.load().ph_concat_shape(packed, ranks, n, int(axis), out, C.byref(ax)))
+    return [int(out[i]) for i in range(len(shapes[0]))], ax.value
+
+
+def _concatenate(narrs, axis: int) -> "DeviceNArray":
+    first = narrs[0]
+    for a in narrs:
+        if a.dtype != first.dtype:
+            raise TypeError("device path: concatenate needs arrays of one dtype")
+    shape, ax = _concat_shape([list(a.shape) for a in narrs], axis)
+    out = DeviceNArray(shape, first.dtype)
+    at = 0
+    for a in narrs:
+        n = int(a.shape[ax])
+        if n and out.size:
+            lit = [_region.ALL] * len(shape)
+            lit[ax] = _region.rng(at, at + n - 1)
+            out.unsafe_set_chunk(make_region(lit, shape, False), a)
+        at += n
+    return out
+
+
 _RED_CELLS = ((C.c_uint64 * 2)(), C.c_int64(-1), C.c_uint32(0))      # reused ctypes cells of the full reductions
 
 
@@ -915,6 +950,62 @@ class DeviceNArray(_Indexable):
 
     def flatten(self) -> "DeviceNArray":
         return self.reshape(self.size)
+
+    # ---- joins (src/n_array.cr:321-344, 666-750): one strided copy per input, nothing touches the host ---------
+    def concatenate(self, *others, axis: int = 0) -> "DeviceNArray":
+        """NArray#concatenate(*others, axis) and, called on the class with the arrays as arguments,
+        NArray.concatenate(*narrs, axis) (src/n_array.cr:712-750): the inputs laid side by side along `axis`.
+        The shape rule is the reference's `compatible?` (ph_concat_shape: a negative axis excludes nothing, so
+        every dimension must then match).  Each input is ONE scatter into its range of the result."""
+        return _concatenate((self,) + tuple(others), axis)
+
+    def push(self, *others, axis: int = 0) -> "DeviceNArray":
+        """NArray#push / << (src/n_array.cr:682-710), in place: the buffers are appended as they lie and only
+        shape[0] grows, whatever `axis` says (`axis` merely relaxes the compatibility test, as in the reference)."""
+        if not others:
+            return self
+        shapes = [self.shape] + [list(o.shape) for o in others]
+        _concat_shape(shapes, axis)                                   # compatible? -> DimensionError
+        for o in others:
+            if o.dtype != self.dtype:
+                raise TypeError("device path: push needs arrays of one dtype")
+        total = self.size + sum(o.size for o in others)
+        rows = self.shape[0] + sum(o.shape[0] for o in others)
+        new_shape = [rows] + self.shape[1:]
+        n = 1
+        for d in new_shape:
+            n *= d
+        if n != total:                                                # an axis != 0 let through rows that do not fill the shape
+            raise ShapeError(f"Cannot change shape from [{total}] to {new_shape}: reshape cannot add or remove elements.")
+        lib = _lib.load()
+        isz = self.dtype.itemsize
+        buf = _Buffer(max(1, total) * isz)
+        at = 0
+        for a in (self,) + tuple(others):
+            flat = a if isinstance(a, DeviceNArray) else a.to_narr()
+            if flat.size:
+                check(lib.ph_d2d(buf.ptr + at * isz, flat.ptr, flat.size * isz))
+            at += flat.size
+        self.shape = new_shape
+        self._buf = buf
+        self.__dict__.pop("_desc_cache", None)
+        return self
+
+    def __lshift__(self, other) -> "DeviceNArray":
+        return self.push(other)
+
+    @staticmethod
+    def wrap(*narrs) -> "DeviceNArray":
+        """NArray.wrap(*objects, pad: false) (src/n_array.cr:321-340): a new leading axis with one input per row;
+        identical shapes or DimensionError (padding is NotImplementedError in the reference as well)."""
+        if not narrs:
+            raise DimensionError("Cannot wrap these arrays: nothing to wrap")
+        container = list(narrs[0].shape)
+        if any(list(a.shape) != container for a in narrs):
+            raise DimensionError("Cannot wrap these arrays: shapes do not match. Pass argument pad:true if you want to "
+                                 "reshape arrays as necessary.")
+        rows = [(a if isinstance(a, DeviceNArray) else a.to_narr()).reshape([1] + container) for a in narrs]
+        return _concatenate(rows, 0)
 
     def permute(self, *order) -> "DeviceNArray":
         """MultiIndexable#permute = view.permute + copy (src/multi_indexable.cr:795-803)."""

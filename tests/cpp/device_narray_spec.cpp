@@ -178,6 +178,20 @@ static void pipeline_host_specs() {
   });
 }
 
+static void join_host_specs() {
+  it("ph_concat_shape: NArray#compatible? (n_array.cr:666-673) and the concatenated shape", [] {
+    int32_t ax = -9;
+    EXPECT(concat_shape_of({{2, 3}, {4, 3}}, 0, &ax) == Shape({6, 3}) && ax == 0);
+    EXPECT(concat_shape_of({{2, 3, 4}, {2, 1, 4}, {2, 5, 4}}, 1, &ax) == Shape({2, 9, 4}) && ax == 1);
+    EXPECT(concat_shape_of({{2, 3}, {2, 3}}, -1, &ax) == Shape({2, 6}) && ax == 1);
+    EXPECT_RAISES(DimensionError, concat_shape_of({{2, 3}, {2, 4}}, 0, &ax));
+    EXPECT_RAISES(DimensionError, concat_shape_of({{2, 3}, {2, 4}}, -1, &ax));      // `idx != axis` on the raw argument
+    EXPECT_RAISES(IndexError, concat_shape_of({{2, 3}, {2}}, 0, &ax));
+    EXPECT_RAISES(IndexError, concat_shape_of({{2, 3}, {2, 3}}, 2, &ax));
+    EXPECT_RAISES(DimensionError, concat_shape_of({{2}, {2, 3}}, 0, &ax));
+  });
+}
+
 static void io_host_specs() {
   it("to_json / from_json / to_yaml / from_yaml goldens (n_array_spec.cr:520-558)", [] {
     namespace H = IO::host;
@@ -250,6 +264,7 @@ int main(int argc, char** argv) {
     io_host_specs();
     partition_host_specs();
     pipeline_host_specs();
+    join_host_specs();
     std::printf("%d expectations passed, %d failed (host-only)\n", g_passed, g_failed);
     return g_failed ? 1 : 0;
   }
@@ -536,6 +551,32 @@ int main(int argc, char** argv) {
     auto nxt = s.clone();
     nxt.set_chunk({range_ex(1, -1), range_ex(1, -1)}, c + (d0 + d1) * C);
     EXPECT(Heat::update_temp(s, C) == nxt);                                  // bit-identical
+  });
+
+  it("NArray.concatenate / push / << / wrap (n_array.cr:321-344, 666-750): one strided copy per input", [] {
+    auto a = narr<int32_t>({2, 3}, {0, 1, 2, 3, 4, 5});
+    auto b = narr<int32_t>({1, 3}, {10, 11, 12});
+    auto c = narr<int32_t>({2, 2}, {20, 21, 22, 23});
+    EXPECT(DeviceNArray<int32_t>::concatenate({&a, &b}, 0).to_host() == V<int32_t>({0, 1, 2, 3, 4, 5, 10, 11, 12}));
+    auto side = a.concatenate(c, 1);
+    EXPECT(side.shape() == Shape({2, 5}) && side.to_host() == V<int32_t>({0, 1, 2, 20, 21, 3, 4, 5, 22, 23}));
+    auto t = a.view().permute();                                            // views join like arrays: [3,2] ++ [3,2] along axis 1
+    EXPECT(DeviceNArray<int32_t>::concatenate({&t, &t}, 1).to_host() == V<int32_t>({0, 3, 0, 3, 1, 4, 1, 4, 2, 5, 2, 5}));
+    EXPECT(DeviceNArray<int32_t>::concatenate({&a, &a}, -1).shape() == Shape({2, 6}));
+    EXPECT_RAISES(DimensionError, DeviceNArray<int32_t>::concatenate({&a, &c}, 0));
+    EXPECT_RAISES(DimensionError, DeviceNArray<int32_t>::concatenate({&a, &c}, -1));   // a negative axis excludes nothing (compatible?)
+    EXPECT_RAISES(IndexError, DeviceNArray<int32_t>::concatenate({&a, &a}, 2));
+    auto p = a.clone();
+    auto alias = p.reshape({3, 2});
+    p << b;
+    EXPECT(p.shape() == Shape({3, 3}) && p.to_host() == V<int32_t>({0, 1, 2, 3, 4, 5, 10, 11, 12}));
+    EXPECT(alias.to_host() == V<int32_t>({0, 1, 2, 3, 4, 5}));              // an alias made before the push keeps the old buffer
+    p.push({&b, &a});
+    EXPECT(p.shape() == Shape({6, 3}) && p.get({5, 2}) == 5 && p.get({3, 0}) == 10);
+    EXPECT_RAISES(DimensionError, p.push({&c}));
+    auto w = DeviceNArray<int32_t>::wrap({&a, &a});
+    EXPECT(w.shape() == Shape({2, 2, 3}) && w.get({1, 1, 2}) == 5 && w.get({0, 0, 1}) == 1);
+    EXPECT_RAISES(DimensionError, DeviceNArray<int32_t>::wrap({&a, &b}));
   });
 
   // ---- streams, pinned arrays, asynchronous transfers, the chunked host -> device -> host pipeline (ph_pipeline.hpp)

@@ -405,3 +405,49 @@ def _raises(exc, fn):
     except exc:
         return True
     return False
+
+
+def test_concatenate_push_wrap_on_the_device():
+    """NArray.concatenate / #concatenate / #push / << / NArray.wrap (src/n_array.cr:321-344, 666-750) on device
+    arrays and views: one strided copy per input, bit-exact vs the oracle's restatement of concatenate_to_slice."""
+    rs = np.random.RandomState(9)
+    lib = ph.load()
+    for dtype in (np.float32, np.int64, np.uint8):
+        for shapes, axis in [([(2, 3), (4, 3)], 0), ([(2, 3), (2, 5), (2, 1)], 1), ([(3, 4, 5), (3, 1, 5), (3, 7, 5)], 1),
+                             ([(3, 4, 5), (3, 4, 2)], 2), ([(5,), (3,)], 0), ([(0, 3), (2, 3)], 0), ([(2, 0), (2, 3)], 1),
+                             ([(64, 96), (64, 96)], -1), ([(300, 129), (41, 129), (1, 129)], 0)]:
+            arrs = [rs.randint(0, 200, size=s).astype(dtype) for s in shapes]
+            devs = [D.from_host(a) for a in arrs]
+            before = lib.ph_launch_count()
+            got = D.concatenate(*devs, axis=axis)                       # class form
+            launches = lib.ph_launch_count() - before
+            assert launches <= sum(1 for a in arrs if a.size), (shapes, launches)     # one copy per non-empty input
+            assert_bits(got.to_host(), O.concatenate(arrs, axis), f"concatenate {shapes} axis={axis}")
+            assert_bits(devs[0].concatenate(*devs[1:], axis=axis).to_host(), O.concatenate(arrs, axis), "instance form")
+    a = rs.rand(6, 8).astype(np.float64)
+    d = D.from_host(a)
+    # views join like arrays (the source is read through its descriptor): transposed and strided pieces
+    got = D.concatenate(d.view().permute(), d.view(rng(None, None, 2), rng(None, None)).permute(), axis=1)
+    assert_bits(got.to_host(), O.concatenate([a.T, a[::2].T], 1), "views")
+    with pytest.raises(ph.DimensionError):
+        D.concatenate(d, D.from_host(a[:, :7]), axis=0)
+    with pytest.raises(ph.DimensionError):
+        D.concatenate(d, D.from_host(a[:5]), axis=-1)                    # a negative axis excludes nothing (compatible?)
+    with pytest.raises(ph.CrIndexError):
+        D.concatenate(d, d, axis=2)
+    with pytest.raises(TypeError):
+        D.concatenate(d, D.from_host(a.astype(np.float32)))
+    # push / << grow shape[0] in place; reshape aliases made before keep the OLD buffer (like the reference's new Slice)
+    p = D.from_host(a)
+    alias = p.reshape(8, 6)
+    assert (p << D.from_host(a[:2] + 1)) is p and p.shape == [8, 8]
+    assert_bits(p.to_host(), O.push(a, [a[:2] + 1]), "push")
+    assert_bits(alias.to_host(), a.reshape(8, 6), "an alias made before push keeps the old contents")
+    p.push(D.from_host(a[:1]), D.from_host(a[3:]), axis=0)
+    assert_bits(p.to_host(), O.push(O.push(a, [a[:2] + 1]), [a[:1], a[3:]]), "push of two")
+    with pytest.raises(ph.DimensionError):
+        p.push(D.from_host(a[:, :3]))
+    w = D.wrap(d, d + 1.0, d.view().reverse())
+    assert_bits(w.to_host(), O.wrap([a, a + 1.0, a[::-1, ::-1]]), "wrap")
+    with pytest.raises(ph.DimensionError):
+        D.wrap(d, D.from_host(a[:5]))

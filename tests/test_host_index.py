@@ -340,3 +340,39 @@ def test_float_text_follows_crystal_float_to_s():
     with pytest.raises(ValueError):
         io._typed_elements([1, True], np.int32, "JSON")
     assert io._typed_elements([1, 2], np.float32, "JSON").tolist() == [1.0, 2.0]
+
+
+def test_concatenate_push_wrap_oracle_and_the_host_shape_rule():
+    """NArray.concatenate / push / wrap (src/n_array.cr:321-344, 666-750).  The reference holds no spec for them
+    (`.wrap` is `pending`, spec/n_array_spec.cr:109), so the oracle's loop-for-loop restatement of
+    `concatenate_to_slice` is checked against the independent numpy definition, and ph_concat_shape (the host half
+    of the device form) against the oracle's `compatible?`, quirks included."""
+    from ph_core_b200.narray import _concat_shape, DimensionError, CrIndexError
+    rs = np.random.RandomState(5)
+    cases = [([(2, 3), (4, 3)], 0), ([(2, 3), (2, 5), (2, 1)], 1), ([(2, 3, 4), (2, 1, 4)], 1), ([(2, 3, 4), (2, 3, 2)], 2),
+             ([(5,), (3,)], 0), ([(0, 3), (2, 3)], 0), ([(2, 0), (2, 3)], 1), ([(3, 2, 2)] * 4, 0), ([(2, 3), (2, 3)], -1),
+             ([(2, 3, 4), (2, 3, 4)], -2)]
+    for shapes, axis in cases:
+        arrs = [rs.randint(-50, 50, size=s).astype(np.int16) for s in shapes]
+        want = np.concatenate(arrs, axis)
+        got = O.concatenate(arrs, axis)
+        assert got.dtype == want.dtype and got.shape == want.shape and np.array_equal(got, want), (shapes, axis)
+        shape, ax = _concat_shape([list(s) for s in shapes], axis)
+        assert shape == list(want.shape) and ax == axis % len(shapes[0])
+    # `compatible?` compares `idx != axis` on the raw argument: a negative axis excludes nothing
+    for shapes, axis, exc_o, exc_h in [([(2, 3), (2, 4)], -1, O.DimensionError, DimensionError),
+                                       ([(2, 3), (3, 3)], 1, O.DimensionError, DimensionError),
+                                       ([(2, 3), (2,)], 0, O.CrIndexError, CrIndexError),
+                                       ([(2, 3), (2, 3)], 2, O.CrIndexError, CrIndexError)]:
+        with pytest.raises(exc_o):
+            O.concatenate([np.zeros(s) for s in shapes], axis)
+        with pytest.raises(exc_h):
+            _concat_shape([list(s) for s in shapes], axis)
+    a, b = np.arange(6).reshape(2, 3), np.arange(10, 13).reshape(1, 3)
+    assert O.push(a, [b]).tolist() == [[0, 1, 2], [3, 4, 5], [10, 11, 12]]
+    assert O.push(a, [b, b], axis=0).shape == (4, 3)
+    with pytest.raises(O.DimensionError):
+        O.push(a, [np.zeros((1, 4))])
+    assert O.wrap([a, a + 1, a + 2]).shape == (3, 2, 3) and O.wrap([a, a + 1])[1].tolist() == (a + 1).tolist()
+    with pytest.raises(O.DimensionError):
+        O.wrap([a, b])
