@@ -285,6 +285,21 @@ class MultiIndexable {
   DeviceNArray<T> unsafe_fetch_chunk(const IndexRegion& region) const;
   DeviceNArray<T> get_chunk(const RegionLiteral& lits, bool drop = true) const { return unsafe_fetch_chunk(IndexRegion(lits, shape_, drop)); }
   DeviceNArray<T> get_chunk(const IndexRegion& region) const { return unsafe_fetch_chunk(region); }
+  // get_chunk(coord, region_shape) :369-395: the block of `region_shape` whose lowermost corner is `coord`
+  DeviceNArray<T> get_chunk(const Coord& coord, const Shape& region_shape) const {
+    if (coord.size() != region_shape.size())
+      throw DimensionError("'coord' and 'region_shape' had a different number of dimensions. Note that you must fully specify your coordinate and region shape for this overload of get_chunk.");
+    if (coord.size() != shape_.size())
+      throw DimensionError("'coord' had a different number of dimensions than this MultiIndexable (must have " + std::to_string(shape_.size()) + ", but has " + std::to_string(coord.size()) + ").");
+    for (size_t i = 0; i < coord.size(); i++) {
+      if (coord[i] < 0) throw ArgumentError("'coord' was negative on axis " + std::to_string(i) + ", but must be strictly nonnegative.");
+      if (region_shape[i] < 0) throw ArgumentError("'region_shape' was negative on axis " + std::to_string(i) + ", but must be strictly nonnegative.");
+      if (coord[i] + region_shape[i] > shape_[i])
+        throw ShapeError("The region defined by shape " + shape_str(region_shape) + " and lowermost coordinate " + shape_str(coord) +
+                         " is not contained within this MultiIndexable on axis " + std::to_string(i) + ".");
+    }
+    return unsafe_fetch_chunk(IndexRegion::cover(region_shape).translate(coord));
+  }
   DeviceNArray<T> operator[](const RegionLiteral& lits) const { return get_chunk(lits); }
   // narr[mask] returns self (multi_indexable.cr:479-481); the spec-visible use is `narr[mask] = v`
   const MultiIndexable<T>& operator[](const MultiIndexable<Bool>&) const { return *this; }

@@ -549,6 +549,24 @@ def get_chunk(narr: np.ndarray, literal: Sequence, drop: bool = True) -> np.ndar
     return fetch_chunk(narr, IndexRegion.new(literal, list(narr.shape), drop))
 
 
+def get_chunk_at(narr: np.ndarray, coord: Sequence[int], region_shape: Sequence[int]) -> np.ndarray:
+    """MultiIndexable#get_chunk(coord, region_shape) (src/multi_indexable.cr:369-395): the block of `region_shape`
+    whose lowermost corner is `coord`; both fully specified, nonnegative, contained."""
+    if len(coord) != len(region_shape):
+        raise DimensionError("'coord' and 'region_shape' had a different number of dimensions")
+    if len(coord) != narr.ndim:
+        raise DimensionError("'coord' had a different number of dimensions than this MultiIndexable")
+    for idx, (c, r) in enumerate(zip(coord, region_shape)):
+        if c < 0 or r < 0:
+            raise CrArgumentError(f"negative on axis {idx}, but must be strictly nonnegative")
+        if c + r > narr.shape[idx]:
+            raise ShapeError(f"The region is not contained within this MultiIndexable on axis {idx}")
+    out = np.empty(tuple(region_shape), dtype=narr.dtype)
+    for local in np.ndindex(*region_shape):                          # cover(region_shape).translate!(coord), lex order
+        out[local] = narr[tuple(c + l for c, l in zip(coord, local))]
+    return out
+
+
 def set_chunk_array(narr: np.ndarray, region: IndexRegion, src: np.ndarray) -> None:
     """NArray#unsafe_set_chunk(region, src), src/n_array.cr:484-492: src is streamed
     in ITS OWN lex order onto the region's lex order."""

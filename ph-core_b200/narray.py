@@ -362,8 +362,32 @@ class _Indexable:
     mutable_view = view
 
     # ---- gather: [] / get_chunk (src/multi_indexable.cr:338-356, 523-531) ---------------
-    def get_chunk(self, literal: Sequence, drop: bool = True) -> "DeviceNArray":
+    def get_chunk(self, literal: Sequence, drop=True) -> "DeviceNArray":
+        """get_chunk(region_literal, drop) (:354-356) and, with a second list, get_chunk(coord, region_shape)
+        (:369-395): the block of `region_shape` whose lowermost corner is `coord`."""
+        if isinstance(drop, (list, tuple)):
+            return self._get_chunk_at(list(literal), list(drop))
         reg = literal if isinstance(literal, PhRegion) else make_region(literal, self.shape, drop)
+        return self.unsafe_fetch_chunk(reg)
+
+    def _get_chunk_at(self, coord: List[int], region_shape: List[int]) -> "DeviceNArray":
+        if len(coord) != len(region_shape):
+            raise DimensionError(f"'coord' ({coord}) and 'region_shape' {region_shape} had a different number of dimensions. Note "
+                                 "that you must fully specify your coordinate and region shape for this overload of get_chunk.")
+        if len(coord) != len(self.shape):
+            raise DimensionError(f"'coord' ({coord}) had a different number of dimensions than this MultiIndexable (must have "
+                                 f"{len(self.shape)}, but has {len(coord)}).")
+        for idx, (c, r) in enumerate(zip(coord, region_shape)):
+            if c < 0:
+                raise CrArgumentError(f"'coord' {coord} was negative on axis {idx}, but must be strictly nonnegative.")
+            if r < 0:
+                raise CrArgumentError(f"'region_shape' {region_shape} was negative on axis {idx}, but must be strictly nonnegative.")
+            if c + r > self.shape[idx]:
+                raise ShapeError(f"The region defined by shape {region_shape} and lowermost coordinate {coord} is not contained "
+                                 f"within this MultiIndexable on axis {idx} (this MultiIndexable has {self.shape[idx]} elements "
+                                 f"on axis {idx}).")
+        reg = cover_region(region_shape)                              # IndexRegion.cover(region_shape).translate!(coord)
+        host_check(_lib.load().ph_region_translate(C.byref(reg), _i64(coord), len(coord)))
         return self.unsafe_fetch_chunk(reg)
 
     def unsafe_fetch_chunk(self, reg: PhRegion) -> "DeviceNArray":
@@ -1056,7 +1080,9 @@ class DeviceView(_Indexable):
         """View#unsafe_fetch_chunk returns a view (src/view.cr:105-107)."""
         return self.view(reg)
 
-    def get_chunk(self, literal: Sequence, drop: bool = True) -> "DeviceView":
+    def get_chunk(self, literal: Sequence, drop=True) -> "DeviceView":
+        if isinstance(drop, (list, tuple)):                          # get_chunk(coord, region_shape): a view of the block
+            return self._get_chunk_at(list(literal), list(drop))
         reg = literal if isinstance(literal, PhRegion) else make_region(literal, self.shape, drop)
         return self.view(reg)
 

@@ -553,6 +553,16 @@ int main(int argc, char** argv) {
     EXPECT(Heat::update_temp(s, C) == nxt);                                  // bit-identical
   });
 
+  it("get_chunk(coord, region_shape) (multi_indexable.cr:369-395): the source's own examples", [] {
+    auto n = narr<int32_t>({3, 3}, {1, 2, 3, 4, 5, 6, 7, 8, 9});
+    EXPECT(n.get_chunk(Coord{1, 0}, Shape{1, 3}).to_host() == V<int32_t>({4, 5, 6}));
+    EXPECT(n.get_chunk(Coord{1, 1}, Shape{2, 2}).to_host() == V<int32_t>({5, 6, 8, 9}));
+    EXPECT(n.get_chunk(Coord{3, 3}, Shape{0, 0}).shape() == Shape({0, 0}));
+    EXPECT_RAISES(ShapeError, n.get_chunk(Coord{1, 0}, Shape{10, 10}));
+    EXPECT_RAISES(DimensionError, n.get_chunk(Coord{0}, Shape{1}));
+    EXPECT_RAISES(ArgumentError, n.get_chunk(Coord{-1, 0}, Shape{1, 1}));
+  });
+
   it("NArray.concatenate / push / << / wrap (n_array.cr:321-344, 666-750): one strided copy per input", [] {
     auto a = narr<int32_t>({2, 3}, {0, 1, 2, 3, 4, 5});
     auto b = narr<int32_t>({1, 3}, {10, 11, 12});

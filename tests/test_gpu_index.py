@@ -451,3 +451,29 @@ def test_concatenate_push_wrap_on_the_device():
     assert_bits(w.to_host(), O.wrap([a, a + 1.0, a[::-1, ::-1]]), "wrap")
     with pytest.raises(ph.DimensionError):
         D.wrap(d, D.from_host(a[:5]))
+
+
+def test_get_chunk_by_corner_and_shape():
+    """MultiIndexable#get_chunk(coord, region_shape) (src/multi_indexable.cr:369-395), the source's own examples first."""
+    n = np.arange(1, 10, dtype=np.int32).reshape(3, 3)
+    d = D.from_host(n)
+    assert d.get_chunk([1, 0], [1, 3]).to_host().tolist() == [[4, 5, 6]]
+    with pytest.raises(ph.ShapeError):
+        d.get_chunk([1, 0], [10, 10])
+    with pytest.raises(ph.DimensionError):
+        d.get_chunk([0], [1])
+    with pytest.raises(ph.DimensionError):
+        d.get_chunk([0, 0], [1])
+    with pytest.raises(ph.CrArgumentError):
+        d.get_chunk([-1, 0], [1, 1])
+    with pytest.raises(ph.CrArgumentError):
+        d.get_chunk([0, 0], [1, -1])
+    rs = np.random.RandomState(4)
+    a = rs.rand(7, 9, 11).astype(np.float32)
+    da = D.from_host(a)
+    for coord, shape in [([0, 0, 0], [7, 9, 11]), ([2, 3, 4], [3, 1, 7]), ([6, 8, 10], [1, 1, 1]), ([1, 2, 3], [0, 4, 2]), ([7, 9, 11], [0, 0, 0])]:
+        got = da.get_chunk(coord, shape)
+        assert got.shape == shape
+        assert_bits(got.to_host(), O.get_chunk_at(a, coord, shape), f"get_chunk({coord}, {shape})")
+    v = da.view().permute()                                           # the same through a view
+    assert_bits(v.get_chunk([3, 1, 2], [5, 4, 3]).to_host(), O.get_chunk_at(a.transpose(2, 1, 0), [3, 1, 2], [5, 4, 3]), "view")
