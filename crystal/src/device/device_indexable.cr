@@ -313,6 +313,22 @@ module Phase
       eq(value)
     end
 
+    # Printing is a host activity: the reference's `Formatter` walks elements one by one
+    # (`multi_indexable/formatter/formatter.cr:61-62` calls `each`), which a device array refuses.
+    # The elements come back in ONE explicit transfer and the host array prints itself.
+    def to_s(io : IO) : Nil
+      io << "device "
+      to_host.to_s(io)
+    end
+
+    def inspect(io : IO) : Nil
+      io << "#<" << self.class.name << " shape=" << shape_internal << ">"
+    end
+
+    def to_literal_s(io : IO) : Nil
+      to_host.to_literal_s(io)
+    end
+
     def ==(other : DeviceIndexable(T)) : Bool
       return false if shape_internal != other.shape_internal
       return true if size == 0

@@ -298,6 +298,10 @@ class _Indexable:
     def dimensions(self) -> int:
         return len(self.shape)
 
+    def __repr__(self) -> str:
+        """No transfer: printing the elements is `to_host()` first (the reference's Formatter walks elements)."""
+        return f"<{type(self).__name__} {self.dtype} shape={self.shape}>"
+
     # ---- small host-side queries (src/multi_indexable.cr:100-237) -----------------------
     def empty(self) -> bool:
         """MultiIndexable#empty? (:107-109)."""
