@@ -357,7 +357,10 @@ def run_ours(args):
     # overlap; the expression is written with the array API (no hand-built descriptors, no torch streams).
     a_pin, b_pin, c_pin = ph.pinned_from(a_h), ph.pinned_from(b_h), ph.pinned_from(c_h)
     out_pin = ph.pinned_empty(a_h.shape, np.float32)
-    pipe = ph.pipeline.RowPipeline(chunks=4, taper=7)          # 11 chunks: 3 x 2048 rows, then 1024, 512, ... 16, 16 (benchmarks/bench_pipeline.py)
+    # 16 chunks: 64, 64, 128, ... 1024 rows (the first download starts after 64 rows), 2 x 2048, then 1024, 512, ... 16, 16
+    # (the tail nothing overlaps is a 16-row chunk) -- benchmarks/bench_pipeline.py; PH_E2E_SCHEDULE=chunks,taper,ramp overrides
+    sched = [int(v) for v in os.environ.get("PH_E2E_SCHEDULE", "4,7,5").split(",")]
+    pipe = ph.pipeline.RowPipeline(chunks=sched[0], taper=sched[1], ramp=sched[2])
     expr = lambda x, z, y: x.broadcast_op("*", y) + z          # (a * b) + c, b the [1, COLS] row vector
 
     def e2e_step():
@@ -477,7 +480,8 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(a_h.nbytes + b_h.nbytes + c_h.nbytes), "d2h_bytes_per_step": int(a_h.nbytes),
                     "steps": e2e_steps,
                     "how": "array API: pipeline.RowPipeline.map_rows (from_host_async of pinned a, b, c -> a.broadcast_op('*', b) + c "
-                           "-> to_host_async), 11 row chunks (3 x 2048 rows, then halving down to 16: the un-overlapped tail is one small chunk) on upload / "
+                           "-> to_host_async), 16 row chunks (64 rows doubling up to 2048, then halving down to 16: downloads start early and the "
+                           "un-overlapped tail is one small chunk) on upload / "
                            "compute / download streams of the library so H2D, kernels and D2H overlap",
                     "naive": {"value": round(BYTES_STEP * world / (naive_ms * 1e-3) / 1e9, 3), "ms_per_step": round(naive_ms, 3),
                               "how": "from_host(pageable numpy) x3 -> operators -> to_host, one stream, wall clock", "same_result": naive_ok},

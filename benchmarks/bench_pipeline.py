@@ -26,8 +26,8 @@ BYTES = 5 * R * COLS * 4 + COLS * 4
 expr = lambda x, z, y: x.broadcast_op("*", y) + z
 ms = C.c_float()
 ref = None
-for chunks, taper, ups in [(16, 0, 1), (4, 7, 1), (4, 7, 2), (16, 0, 2), (8, 4, 2), (2, 7, 2), (32, 0, 2)]:
-    pipe = ph.pipeline.RowPipeline(chunks=chunks, taper=taper, uploaders=ups)
+for chunks, taper, ups, ramp in [(16, 0, 1, 0), (4, 7, 1, 0), (4, 7, 1, 3), (4, 7, 1, 5), (8, 6, 1, 3), (3, 7, 1, 4)]:
+    pipe = ph.pipeline.RowPipeline(chunks=chunks, taper=taper, uploaders=ups, ramp=ramp)
     step = lambda: pipe.map_rows(expr, rows=[a_pin, c_pin], out=out_pin, shared=[b_pin], wait=False)
     step(); ph.sync()
     if ref is None:
@@ -41,7 +41,7 @@ for chunks, taper, ups in [(16, 0, 1), (4, 7, 1), (4, 7, 2), (16, 0, 2), (8, 4, 
         ts.append(ms.value / 4)
     ph.sync()
     ok = bool(out_pin.tobytes() == ref.tobytes())
-    print(json.dumps({"chunks": chunks, "taper": taper, "uploaders": ups, "n_chunks": len(ph.pipeline.row_chunks(R, chunks, taper)),
+    print(json.dumps({"chunks": chunks, "taper": taper, "uploaders": ups, "ramp": ramp, "n_chunks": len(ph.pipeline.row_chunks(R, chunks, taper, ramp)),
                       "ms_best": round(min(ts), 4), "ms_median": round(sorted(ts)[1], 4),
                       "gbs": round(BYTES / (sorted(ts)[1] * 1e-3) / 1e9, 2), "same_result": ok}), flush=True)
     pipe.close()

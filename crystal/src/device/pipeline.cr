@@ -139,7 +139,7 @@ module Phase
     # What is left when the last upload ends is one chunk's kernels and download -- nothing
     # overlaps that tail -- so the final chunks are small while the early ones stay large (every
     # copy pays a fixed set-up).
-    def self.row_chunks(n : Int64, chunks : Int64, taper : Int32 = 0) : Array({Int64, Int64})
+    def self.row_chunks(n : Int64, chunks : Int64, taper : Int32 = 0, ramp : Int32 = 0) : Array({Int64, Int64})
       per = (n + {chunks, 1_i64}.max - 1) // {chunks, 1_i64}.max
       bounds = [] of {Int64, Int64}
       r = 0_i64
@@ -157,10 +157,24 @@ module Phase
         end
         bounds << {r0, r1}
       end
+      # `ramp` = t: the mirror image at the FRONT (per/2^t, per/2^t, ..., per/2) -- the first download
+      # can only start after the first chunk, so that one is small too.
+      if ramp > 0 && !bounds.empty?
+        r0, r1 = bounds.shift
+        head = [] of {Int64, Int64}
+        ramp.times do
+          mid = r1 - (r1 - r0 + 1) // 2
+          break if mid <= r0
+          head.unshift({mid, r1})
+          r1 = mid
+        end
+        head.unshift({r0, r1})
+        bounds = head + bounds
+      end
       bounds
     end
 
-    def initialize(@chunks : Int64 = 4_i64, @taper : Int32 = 7)
+    def initialize(@chunks : Int64 = 4_i64, @taper : Int32 = 7, @ramp : Int32 = 5)
       @up = Stream.new
       @comp = Stream.new
       @down = Stream.new
@@ -183,7 +197,7 @@ module Phase
       shared_dev = [] of DeviceNArray(T)
       up.use { shared.each { |x| shared_dev << DeviceNArray(T).from_host_async(x.shape, x.ptr) } }
       keep = [] of DeviceNArray(T)
-      RowPipeline.row_chunks(n, @chunks, @taper).each do |(r0, r1)|
+      RowPipeline.row_chunks(n, @chunks, @taper, @ramp).each do |(r0, r1)|
         ins = [] of DeviceNArray(T)
         up.use { rows.each { |r| ins << DeviceNArray(T).from_host_async(r.rows_shape(r0, r1), r.rows(r0)) } }
         comp.wait(up) # chunk k's operands (and the shared ones) have landed

@@ -18,7 +18,7 @@ import numpy as np
 from .narray import DeviceNArray, Stream, ShapeError, main_stream_wait, sync
 
 
-def row_chunks(n: int, chunks: int, taper: int = 0):
+def row_chunks(n: int, chunks: int, taper: int = 0, ramp: int = 0):
     """[r0, r1) row ranges: `chunks` equal chunks; with taper = t the LAST one is cut again into halves t times
     (per/2, per/4, ..., per/2^t, per/2^t).  What is left when the last upload ends is one chunk's kernels and
     download -- nothing overlaps that tail -- so the final chunks are small while the early ones stay large
@@ -37,6 +37,17 @@ def row_chunks(n: int, chunks: int, taper: int = 0):
             bounds.append((r0, mid))
             r0 = mid
         bounds.append((r0, r1))
+    if ramp > 0 and bounds:                                   # mirror image at the front: per/2^ramp, per/2^ramp, ..., per/2
+        r0, r1 = bounds.pop(0)                                # (the first download can only start after the first chunk)
+        head = []
+        for _ in range(ramp):
+            mid = r1 - (r1 - r0 + 1) // 2
+            if mid <= r0:
+                break
+            head.insert(0, (mid, r1))
+            r1 = mid
+        head.insert(0, (r0, r1))
+        bounds = head + bounds
     return bounds
 
 
@@ -48,9 +59,10 @@ class RowPipeline:
     profiles/r02_pipeline_schedules.jsonl -- concurrent host-to-device copies share the link and the chunk is
     complete later.)"""
 
-    def __init__(self, chunks: int = 16, streams: int = 3, taper: int = 0, uploaders: int = 1):
+    def __init__(self, chunks: int = 16, streams: int = 3, taper: int = 0, uploaders: int = 1, ramp: int = 0):
         self.chunks = int(chunks)
         self.taper = int(taper)
+        self.ramp = int(ramp)
         self.up, self.comp, self.down = Stream(), Stream(), Stream()
         # uploaders > 1: the row operands of a chunk go up on different streams, so one copy's set-up runs under
         # another copy's transfer (experiment knob; 1 = every upload on `up`)
@@ -73,7 +85,7 @@ class RowPipeline:
         with up:
             shared_dev = [DeviceNArray.from_host_async(x) for x in shared]
         keep = []
-        for r0, r1 in row_chunks(n, self.chunks, self.taper):
+        for r0, r1 in row_chunks(n, self.chunks, self.taper, self.ramp):
             ins = []
             for i, r in enumerate(rows):
                 with self.ups[i % len(self.ups)]:

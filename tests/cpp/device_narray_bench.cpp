@@ -70,7 +70,7 @@ int main() {
     PinnedArray<float> ha({R, Cc}), hc({R, Cc}), hb({1, Cc}), hout({R, Cc});
     for (int64_t i = 0; i < N; i++) { ha[i] = (float)((i * 2654435761u) % 2001) / 1000.0f - 1.0f; hc[i] = (float)((i * 40503u) % 1999) / 999.0f - 1.0f; }
     for (int64_t i = 0; i < Cc; i++) hb[i] = (float)((i * 7919u) % 2003) / 1001.0f - 1.0f;
-    RowPipeline pipe(4, 7);
+    RowPipeline pipe;                                            // 4 chunks, the last halved 7x, the first 5x
     auto expr = [](const std::vector<DeviceNArray<float>>& in, const std::vector<DeviceNArray<float>>& shared) {
       return in[0].broadcast_op(PH_MUL, shared[0]) + in[1];
     };
@@ -78,7 +78,7 @@ int main() {
     Device::sync();
     bool ok = true;
     for (int64_t i = 0; i < N && ok; i += 4099) ok = hout[i] == ha[i] * hb[i % Cc] + hc[i];       // two roundings, no FMA (-ffp-contract=off)
-    std::printf("{\"row\": \"e2e: RowPipeline.map_rows(a * b + c), pinned host in / out, 11 tapered chunks\", \"ms\": %.5f, \"gbs\": %.1f, "
+    std::printf("{\"row\": \"e2e: RowPipeline.map_rows(a * b + c), pinned host in / out, 16 ramped / tapered chunks\", \"ms\": %.5f, \"gbs\": %.1f, "
                 "\"h2d_bytes\": %.0f, \"d2h_bytes\": %.0f, \"ok\": %s}\n", ms, bytes_two / ms / 1e6, 2.0 * N * 4 + Cc * 4, 1.0 * N * 4, ok ? "true" : "false");
   }
   std::printf("{\"kernel_launches\": %lld}\n", (long long)ph_launch_count());

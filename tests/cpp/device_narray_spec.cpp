@@ -174,6 +174,16 @@ static void pipeline_host_specs() {
     std::vector<int64_t> sizes;
     for (const auto& c : row_chunks(8192, 4, 7)) sizes.push_back(c.second - c.first);
     EXPECT(sizes == std::vector<int64_t>({2048, 2048, 2048, 1024, 512, 256, 128, 64, 32, 16, 16}));
+    sizes.clear();
+    for (const auto& c : row_chunks(8192, 4, 7, 5)) sizes.push_back(c.second - c.first);
+    EXPECT(sizes == std::vector<int64_t>({64, 64, 128, 256, 512, 1024, 2048, 2048, 1024, 512, 256, 128, 64, 32, 16, 16}));
+    for (int64_t n : {0, 1, 7, 10, 1000})
+      for (int ramp : {1, 2, 5}) {
+        int64_t at = 0;
+        bool ok = true;
+        for (const auto& c : row_chunks(n, 3, 2, ramp)) { ok = ok && c.first == at && c.second > c.first; at = c.second; }
+        EXPECT(ok && at == n);
+      }
     EXPECT(row_chunks(8192, 16).size() == 16 && row_chunks(8192, 16)[15] == std::make_pair<int64_t, int64_t>(7680, 8192));
   });
 }
@@ -600,7 +610,7 @@ int main(int argc, char** argv) {
     auto expr = [](const std::vector<DeviceNArray<float>>& in, const std::vector<DeviceNArray<float>>& shared) {
       return in[0].broadcast_op(PH_MUL, shared[0]) + in[1];
     };
-    RowPipeline equal(8, 0), tapered(4, 7);
+    RowPipeline equal(8, 0, 0), tapered(4, 7, 5);
     for (RowPipeline* pipe : {&equal, &tapered, &equal}) {                   // streams and pool blocks are reused
       std::memset(out.data(), 0, (size_t)out.size() * sizeof(float));
       pipe->map_rows<float>(expr, {&a, &c}, out, {&b});

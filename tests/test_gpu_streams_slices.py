@@ -83,7 +83,7 @@ def test_streams_async_transfers_and_the_row_pipeline():
         pipe.map_rows(lambda x, z, y: x.broadcast_op("*", y) + z, rows=[a_pin, c_pin], out=out, shared=[b_pin])
         assert_bits(np.array(out), want, "pipelined a*b+c")
     # the tapered schedule of the bench's e2e leg (few large chunks, the last one cut into halves): same bits
-    taper = ph.pipeline.RowPipeline(chunks=4, taper=7)
+    taper = ph.pipeline.RowPipeline(chunks=4, taper=7, ramp=5)
     out[...] = 0
     taper.map_rows(lambda x, z, y: x.broadcast_op("*", y) + z, rows=[a_pin, c_pin], out=out, shared=[b_pin])
     assert_bits(np.array(out), want, "pipelined a*b+c, tapered chunks")

@@ -71,6 +71,11 @@ def test_row_chunks_cover_the_rows_once_and_taper_at_the_end():
                 b = row_chunks(n, chunks, taper)
                 assert [r for lo, hi in b for r in range(lo, hi)] == list(range(n)), (n, chunks, taper)
                 assert all(lo < hi for lo, hi in b)
+    for n in (0, 1, 7, 10, 1000, 8192):
+        for ramp in (1, 2, 5, 9):
+            b = row_chunks(n, 3, 2, ramp)
+            assert [r for lo, hi in b for r in range(lo, hi)] == list(range(n)) and all(lo < hi for lo, hi in b)
+    assert [hi - lo for lo, hi in row_chunks(8192, 4, 7, 5)] == [64, 64, 128, 256, 512, 1024, 2048, 2048, 1024, 512, 256, 128, 64, 32, 16, 16]
     b = row_chunks(8192, 4, 7)
     assert [hi - lo for lo, hi in b] == [2048, 2048, 2048, 1024, 512, 256, 128, 64, 32, 16, 16]
     assert row_chunks(8192, 16, 0) == [(k * 512, (k + 1) * 512) for k in range(16)]
