@@ -357,9 +357,12 @@ def run_ours(args):
     # overlap; the expression is written with the array API (no hand-built descriptors, no torch streams).
     a_pin, b_pin, c_pin = ph.pinned_from(a_h), ph.pinned_from(b_h), ph.pinned_from(c_h)
     out_pin = ph.pinned_empty(a_h.shape, np.float32)
-    # 16 chunks: 64, 64, 128, ... 1024 rows (the first download starts after 64 rows), 2 x 2048, then 1024, 512, ... 16, 16
-    # (the tail nothing overlaps is a 16-row chunk) -- benchmarks/bench_pipeline.py; PH_E2E_SCHEDULE=chunks,taper,ramp overrides
-    sched = [int(v) for v in os.environ.get("PH_E2E_SCHEDULE", "4,7,5").split(",")]
+    # 13 chunks: 512, 512, 1024 rows (the first download starts after 512 rows), 2 x 2048, then 1024, 512, ... 16, 16 (the
+    # tail nothing overlaps is a 16-row chunk).  Measured inside this harness (profiles/r02_pipeline_schedules.jsonl):
+    # 16 equal chunks 120.5 GB/s, "4,7,0" 124.2, "4,7,2" 124.8, "4,7,5" 124.8 (and once 100.7: every chunk costs ~0.35 ms of
+    # Python to enqueue, so the Python mirror keeps the chunk count moderate; the compiled host layer uses the deeper ramp:
+    # 126.2).  PH_E2E_SCHEDULE=chunks,taper,ramp overrides.
+    sched = [int(v) for v in os.environ.get("PH_E2E_SCHEDULE", "4,7,2").split(",")]
     pipe = ph.pipeline.RowPipeline(chunks=sched[0], taper=sched[1], ramp=sched[2])
     expr = lambda x, z, y: x.broadcast_op("*", y) + z          # (a * b) + c, b the [1, COLS] row vector
 
@@ -480,7 +483,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(a_h.nbytes + b_h.nbytes + c_h.nbytes), "d2h_bytes_per_step": int(a_h.nbytes),
                     "steps": e2e_steps,
                     "how": "array API: pipeline.RowPipeline.map_rows (from_host_async of pinned a, b, c -> a.broadcast_op('*', b) + c "
-                           "-> to_host_async), 16 row chunks (64 rows doubling up to 2048, then halving down to 16: downloads start early and the "
+                           "-> to_host_async), 13 row chunks (512, 512, 1024, 2 x 2048, then halving down to 16: downloads start early and the "
                            "un-overlapped tail is one small chunk) on upload / "
                            "compute / download streams of the library so H2D, kernels and D2H overlap",
                     "naive": {"value": round(BYTES_STEP * world / (naive_ms * 1e-3) / 1e9, 3), "ms_per_step": round(naive_ms, 3),
