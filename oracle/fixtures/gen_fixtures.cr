@@ -136,6 +136,39 @@ tie.each_with_coord do |el, coord|
   end
 end
 
+# joins one step above gather / scatter: NArray.concatenate / #push / NArray.wrap (src/n_array.cr:321-344, 666-750) and
+# get_chunk(coord, region_shape) (src/multi_indexable.cr:369-395); the reference's specs hold nothing for them
+def join_outcome(&block : -> NArray(Int32)) : Hash(String, Array(Int32)) | String
+  begin
+    r = yield
+    {"shape" => r.shape, "elements" => r.to_a}
+  rescue ex : DimensionError | ShapeError | IndexError | ArgumentError
+    ex.class.name
+  end
+end
+
+j_a = NArray.build(2, 3, 4) { |_, i| i }
+j_b = NArray.build(2, 1, 4) { |_, i| 100 + i }
+j_c = NArray.build(2, 3, 2) { |_, i| 200 + i }
+j_d = NArray.build(3, 3, 4) { |_, i| 300 + i }
+joins = {
+  "inputs" => {"a" => j_a.to_a, "b" => j_b.to_a, "c" => j_c.to_a, "d" => j_d.to_a},
+  "concatenate(a,d,axis:0)"  => join_outcome { NArray.concatenate(j_a, j_d, axis: 0) },
+  "concatenate(a,b,a,axis:1)" => join_outcome { NArray.concatenate(j_a, j_b, j_a, axis: 1) },
+  "concatenate(a,c,axis:2)"  => join_outcome { NArray.concatenate(j_a, j_c, axis: 2) },
+  "concatenate(a,a,axis:-1)" => join_outcome { NArray.concatenate(j_a, j_a, axis: -1) },
+  "concatenate(a,c,axis:-1)" => join_outcome { NArray.concatenate(j_a, j_c, axis: -1) },
+  "concatenate(a,b,axis:0)"  => join_outcome { NArray.concatenate(j_a, j_b, axis: 0) },
+  "a.concatenate(b,axis:1)"  => join_outcome { j_a.concatenate(j_b, axis: 1) },
+  "a.clone.push(d)"          => join_outcome { j_a.clone.push(j_d) },
+  "a.clone.push(b)"          => join_outcome { j_a.clone.push(j_b) },
+  "wrap(a,a)"                => join_outcome { NArray.wrap(j_a, j_a) },
+  "wrap(a,b)"                => join_outcome { NArray.wrap(j_a, j_b) },
+  "a.get_chunk([1,0,2],[1,3,2])" => join_outcome { j_a.get_chunk([1, 0, 2], [1, 3, 2]) },
+  "a.get_chunk([0,0,0],[3,1,1])" => join_outcome { j_a.get_chunk([0, 0, 0], [3, 1, 1]) },
+  "a.get_chunk([0,0],[1,1])"     => join_outcome { j_a.get_chunk([0, 0], [1, 1]) },
+}
+
 # Float#to_s as NArray#to_json / #to_yaml write it (src/n_array.cr:807-869)
 text_values = [0.1, 2.0, -1.5e-7, 1e22, 5e-324, 0.30000000000000004, 1e14, 1e15, 1e16, 1e-4, 1e-5, -0.0, 123456789.125, 1e300]
 text32 = [0.1_f32, 3.4e38_f32, 1e-38_f32, 16777216_f32, 1e16_f32, -2.5e-7_f32]
@@ -159,6 +192,7 @@ File.open(path, "w") do |io|
       json.field "whole_f64", whole
       json.field "reductions", reductions
       json.field "argmax_first", {"values" => tie.to_a.map { |v| bits(v) }, "shape" => [3, 4], "max" => bits(max), "coord" => argmax}
+      json.field "joins", joins
       json.field "float_text_f64", text_values.map { |v| [bits(v), v.to_s] }
       json.field "float_text_f32", text32.map { |v| [bits(v), v.to_s] }
       json.field "to_json_f64", NArray.new(text_values[0, 6]).to_json

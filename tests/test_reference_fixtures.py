@@ -205,3 +205,71 @@ def test_device_stencil_matches_the_reference():
         g = _floats(fx[key]["in"], np.float32).reshape(fx[key]["shape"])
         assert heat.update_temp(D.from_host(g), 0.1).to_host().tobytes() == _floats(fx[key]["step1"], np.float32).tobytes(), key
         assert heat.simulate(D.from_host(g), 0.1, 2).to_host().tobytes() == _floats(fx[key]["step2"], np.float32).tobytes(), key
+
+
+def _join_cases(fx):
+    """(key, thunk over numpy inputs / over device inputs) for every entry of the fixture's `joins` table"""
+    ins = fx["joins"]["inputs"]
+    shapes = {"a": (2, 3, 4), "b": (2, 1, 4), "c": (2, 3, 2), "d": (3, 3, 4)}
+    arrs = {k: np.array(v, dtype=np.int32).reshape(shapes[k]) for k, v in ins.items()}
+    return arrs, {
+        "concatenate(a,d,axis:0)": (["a", "d"], 0, "cat"), "concatenate(a,b,a,axis:1)": (["a", "b", "a"], 1, "cat"),
+        "concatenate(a,c,axis:2)": (["a", "c"], 2, "cat"), "concatenate(a,a,axis:-1)": (["a", "a"], -1, "cat"),
+        "concatenate(a,c,axis:-1)": (["a", "c"], -1, "cat"), "concatenate(a,b,axis:0)": (["a", "b"], 0, "cat"),
+        "a.concatenate(b,axis:1)": (["a", "b"], 1, "cat"), "a.clone.push(d)": (["a", "d"], 0, "push"),
+        "a.clone.push(b)": (["a", "b"], 0, "push"), "wrap(a,a)": (["a", "a"], 0, "wrap"), "wrap(a,b)": (["a", "b"], 0, "wrap"),
+        "a.get_chunk([1,0,2],[1,3,2])": ([[1, 0, 2], [1, 3, 2]], 0, "chunk"), "a.get_chunk([0,0,0],[3,1,1])": ([[0, 0, 0], [3, 1, 1]], 0, "chunk"),
+        "a.get_chunk([0,0],[1,1])": ([[0, 0], [1, 1]], 0, "chunk")}
+
+
+def _join_same(got, want, key):
+    if isinstance(want, str):
+        assert got == want, (key, got, want)
+    else:
+        assert not isinstance(got, str), (key, got)
+        assert list(got.shape) == want["shape"] and got.reshape(-1).tolist() == want["elements"], key
+
+
+@needs_fix
+def test_oracle_joins_match_the_reference():
+    fx = _load(FIX)
+    arrs, cases = _join_cases(fx)
+    names = {O.DimensionError: "Phase::DimensionError", O.ShapeError: "Phase::ShapeError", O.CrIndexError: "IndexError",
+             O.CrArgumentError: "ArgumentError"}
+    for key, (args, axis, kind) in cases.items():
+        try:
+            if kind == "cat":
+                got = O.concatenate([arrs[k] for k in args], axis)
+            elif kind == "push":
+                got = O.push(arrs[args[0]].copy(), [arrs[k] for k in args[1:]])
+            elif kind == "wrap":
+                got = O.wrap([arrs[k] for k in args])
+            else:
+                got = O.get_chunk_at(arrs["a"], args[0], args[1])
+        except tuple(names) as e:
+            got = next(v for k, v in names.items() if type(e) is k)
+        _join_same(got, fx["joins"][key], key)
+
+
+@pytest.mark.gpu
+@needs_fix
+def test_device_joins_match_the_reference():
+    import ph_core_b200 as ph
+    from ph_core_b200 import DeviceNArray as D
+    fx = _load(FIX)
+    arrs, cases = _join_cases(fx)
+    names = {ph.DimensionError: "Phase::DimensionError", ph.ShapeError: "Phase::ShapeError", ph.CrIndexError: "IndexError",
+             ph.CrArgumentError: "ArgumentError"}
+    for key, (args, axis, kind) in cases.items():
+        try:
+            if kind == "cat":
+                got = D.concatenate(*[D.from_host(arrs[k]) for k in args], axis=axis).to_host()
+            elif kind == "push":
+                got = D.from_host(arrs[args[0]]).push(*[D.from_host(arrs[k]) for k in args[1:]]).to_host()
+            elif kind == "wrap":
+                got = D.wrap(*[D.from_host(arrs[k]) for k in args]).to_host()
+            else:
+                got = D.from_host(arrs["a"]).get_chunk(args[0], args[1]).to_host()
+        except tuple(names) as e:
+            got = next(v for k, v in names.items() if type(e) is k)
+        _join_same(got, fx["joins"][key], key)
