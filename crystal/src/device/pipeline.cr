@@ -197,15 +197,22 @@ module Phase
       shared_dev = [] of DeviceNArray(T)
       up.use { shared.each { |x| shared_dev << DeviceNArray(T).from_host_async(x.shape, x.ptr) } }
       keep = [] of DeviceNArray(T)
-      RowPipeline.row_chunks(n, @chunks, @taper, @ramp).each do |(r0, r1)|
-        ins = [] of DeviceNArray(T)
-        up.use { rows.each { |r| ins << DeviceNArray(T).from_host_async(r.rows_shape(r0, r1), r.rows(r0)) } }
-        comp.wait(up) # chunk k's operands (and the shared ones) have landed
-        res = comp.use { block.call(ins, shared_dev) }
-        down.wait(comp)
-        down.use { res.to_host_async(out.rows(r0)) }
-        keep.concat(ins)
-        keep << res
+      begin
+        RowPipeline.row_chunks(n, @chunks, @taper, @ramp).each do |(r0, r1)|
+          ins = [] of DeviceNArray(T)
+          up.use { rows.each { |r| ins << DeviceNArray(T).from_host_async(r.rows_shape(r0, r1), r.rows(r0)) } }
+          comp.wait(up) # chunk k's operands (and the shared ones) have landed
+          res = comp.use { block.call(ins, shared_dev) }
+          down.wait(comp)
+          down.use { res.to_host_async(out.rows(r0)) }
+          keep.concat(ins)
+          keep << res
+        end
+      rescue ex
+        # the block raised half way: chunks already queued still use the temporaries, so nothing is
+        # released (by the GC's finalizers) before the three streams have drained
+        up.synchronize; comp.synchronize; down.synchronize
+        raise ex
       end
       # device temporaries are released on the streams they were allocated on: order each of
       # those behind every consumer before letting go, then join the main stream

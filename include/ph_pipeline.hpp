@@ -162,23 +162,30 @@ class RowPipeline {
     }
     std::vector<std::vector<DeviceNArray<T>>> keep_in;
     std::vector<DeviceNArray<T>> keep_out;
-    for (const auto& ch : row_chunks(n, chunks_, taper_, ramp_)) {
-      const int64_t r0 = ch.first, r1 = ch.second;
-      std::vector<DeviceNArray<T>> ins;
-      {
-        StreamScope on(up_);
-        for (const PinnedArray<T>* r : rows) ins.push_back(from_host_async<T>(r->rows_shape(r0, r1), r->rows(r0)));
+    try {
+      for (const auto& ch : row_chunks(n, chunks_, taper_, ramp_)) {
+        const int64_t r0 = ch.first, r1 = ch.second;
+        std::vector<DeviceNArray<T>> ins;
+        {
+          StreamScope on(up_);
+          for (const PinnedArray<T>* r : rows) ins.push_back(from_host_async<T>(r->rows_shape(r0, r1), r->rows(r0)));
+        }
+        comp_.wait(&up_);                                       // chunk k's operands (and the shared ones) have landed
+        DeviceNArray<T> res = [&] { StreamScope on(comp_); return fn(ins, shared_dev); }();
+        if (res.shape() != out.rows_shape(r0, r1)) throw ShapeError("map_rows: the expression returned shape " + shape_str(res.shape()) + " for a chunk of shape " + shape_str(out.rows_shape(r0, r1)));
+        down_.wait(&comp_);
+        {
+          StreamScope on(down_);
+          to_host_async<T>(res, out.rows(r0));
+        }
+        keep_in.push_back(std::move(ins));
+        keep_out.push_back(std::move(res));
       }
-      comp_.wait(&up_);                                       // chunk k's operands (and the shared ones) have landed
-      DeviceNArray<T> res = [&] { StreamScope on(comp_); return fn(ins, shared_dev); }();
-      if (res.shape() != out.rows_shape(r0, r1)) throw ShapeError("map_rows: the expression returned shape " + shape_str(res.shape()) + " for a chunk of shape " + shape_str(out.rows_shape(r0, r1)));
-      down_.wait(&comp_);
-      {
-        StreamScope on(down_);
-        to_host_async<T>(res, out.rows(r0));
-      }
-      keep_in.push_back(std::move(ins));
-      keep_out.push_back(std::move(res));
+    } catch (...) {
+      // the caller's expression threw half way: chunks already queued still read and write the temporaries, so
+      // nothing is released before the three streams have drained
+      ph_stream_sync(up_.handle()); ph_stream_sync(comp_.handle()); ph_stream_sync(down_.handle());
+      throw;
     }
     // device temporaries are released on the streams they were allocated on: order each of those behind every
     // consumer before letting go, then join the main stream

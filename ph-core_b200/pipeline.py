@@ -85,20 +85,27 @@ class RowPipeline:
         with up:
             shared_dev = [DeviceNArray.from_host_async(x) for x in shared]
         keep = []
-        for r0, r1 in row_chunks(n, self.chunks, self.taper, self.ramp):
-            ins = []
-            for i, r in enumerate(rows):
-                with self.ups[i % len(self.ups)]:
-                    ins.append(DeviceNArray.from_host_async(r[r0:r1]))
-            for u in self.ups:
-                comp.wait(u)                                       # chunk k's operands (and the shared ones) have landed
-            with comp:
-                res = fn(*ins, *shared_dev)
-            down.wait(comp)
-            with down:
-                res.to_host_async(out[r0:r1])
-            keep.append((ins, res))
-            del ins, res
+        try:
+            for r0, r1 in row_chunks(n, self.chunks, self.taper, self.ramp):
+                ins = []
+                for i, r in enumerate(rows):
+                    with self.ups[i % len(self.ups)]:
+                        ins.append(DeviceNArray.from_host_async(r[r0:r1]))
+                for u in self.ups:
+                    comp.wait(u)                                       # chunk k's operands (and the shared ones) have landed
+                with comp:
+                    res = fn(*ins, *shared_dev)
+                down.wait(comp)
+                with down:
+                    res.to_host_async(out[r0:r1])
+                keep.append((ins, res))
+                del ins, res
+        except BaseException:
+            # the caller's expression raised half way: chunks already queued still use the temporaries, so nothing
+            # is released before the streams have drained
+            for s in self.streams:
+                s.synchronize()
+            raise
         # device temporaries are released on the streams they were allocated on: order each of those behind
         # every consumer before letting go, then join the main stream
         for u in self.ups:

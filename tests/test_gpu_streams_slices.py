@@ -93,6 +93,19 @@ def test_streams_async_transfers_and_the_row_pipeline():
     io = ph.pinned_empty((64, 8), np.int32)
     with pytest.raises(ph.CrOverflowError):
         pipe.map_rows(lambda x: x + 1, rows=[ia], out=io)
+    # an expression that raises half way leaves the pipeline usable (the queued chunks drain before anything is released)
+    calls = {"n": 0}
+    def flaky(x, z, y):
+        calls["n"] += 1
+        if calls["n"] == 3:
+            raise ValueError("third chunk")
+        return x.broadcast_op("*", y) + z
+    with pytest.raises(ValueError):
+        pipe.map_rows(flaky, rows=[a_pin, c_pin], out=out, shared=[b_pin])
+    ph.sync()
+    out[...] = 0
+    pipe.map_rows(lambda x, z, y: x.broadcast_op("*", y) + z, rows=[a_pin, c_pin], out=out, shared=[b_pin])
+    assert_bits(np.array(out), want, "pipeline reused after a failed call")
     pipe.close()
     # explicit streams: two independent chains, ordered by wait(), joined by sync()
     s1, s2 = ph.Stream(), ph.Stream()
