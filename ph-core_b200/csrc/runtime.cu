@@ -362,7 +362,8 @@ static int32_t take_flags(uint32_t* out_flags) {
     *out_flags = r.h_flags[0];
     return PH_OK;
   }
-  const uint32_t seq = ++r.flag_seq;
+  if (++r.flag_seq == 0) ++r.flag_seq;                // 0 is the record's initial state: never a call number
+  const uint32_t seq = r.flag_seq;
   take_flags_kernel<<<1, 1, 0, r.stream>>>(r.d_flags, r.h_flags_dev, seq);
   PH_CUDA(cudaGetLastError());                       // not counted by ph_launch_count: it stands in for a 4-byte copy
   const volatile uint32_t* done = r.h_flags + 1;
