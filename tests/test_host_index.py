@@ -376,3 +376,41 @@ def test_concatenate_push_wrap_oracle_and_the_host_shape_rule():
     assert O.wrap([a, a + 1, a + 2]).shape == (3, 2, 3) and O.wrap([a, a + 1])[1].tolist() == (a + 1).tolist()
     with pytest.raises(O.DimensionError):
         O.wrap([a, b])
+
+
+def test_concat_shape_agrees_with_the_oracle_on_random_shapes():
+    """ph_concat_shape vs oracle.shapes_compatible_except / concatenate on seeded random shape lists: same
+    accept / reject decision (exception class included) and the same result shape."""
+    from ph_core_b200.narray import _concat_shape, DimensionError, CrIndexError
+    rs = np.random.RandomState(77)
+    outcomes = {"ok": 0, "dim": 0, "idx": 0}
+    for _ in range(600):
+        rank = int(rs.randint(1, 5))
+        base = [int(v) for v in rs.randint(0, 4, size=rank)]
+        n = int(rs.randint(1, 5))
+        axis = int(rs.randint(-rank - 1, rank + 1))
+        shapes = []
+        for k in range(n):
+            sh = list(base)
+            if rs.rand() < 0.5 and -rank <= axis < rank:
+                sh[axis % rank] = int(rs.randint(0, 5))            # differ along the (canonical) axis only
+            if rs.rand() < 0.15:
+                sh[int(rs.randint(0, rank))] += 1                  # differ somewhere else
+            if rs.rand() < 0.07 and k > 0:
+                sh = sh[:-1]                                       # a shorter shape
+            shapes.append(sh)
+        try:
+            want = ("ok", list(O.concatenate([np.zeros(s, np.int8) for s in shapes], axis).shape))
+        except O.DimensionError:
+            want = ("dim", None)
+        except O.CrIndexError:
+            want = ("idx", None)
+        try:
+            got = ("ok", _concat_shape(shapes, axis)[0])
+        except DimensionError:
+            got = ("dim", None)
+        except CrIndexError:
+            got = ("idx", None)
+        assert got == want, (shapes, axis, got, want)
+        outcomes[want[0]] += 1
+    assert min(outcomes.values()) > 20, outcomes                   # every branch is exercised
