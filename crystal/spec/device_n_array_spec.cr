@@ -158,10 +158,10 @@ describe RowPipeline do
     b = NArray.build(1, cols) { |_, i| ((i * 7919) % 2003).to_f32 / 1001 - 1 }
     want = (a.to_device.broadcast(LibPhGpu::Op::Mul, b.to_device) + c.to_device).to_host
     pa, pc, pb = PinnedArray(Float32).from(a), PinnedArray(Float32).from(c), PinnedArray(Float32).from(b)
-    out = PinnedArray(Float32).new([rows, cols])
+    result = PinnedArray(Float32).new([rows, cols])
     pipe = RowPipeline.new(4_i64, 7)
-    pipe.map_rows([pa, pc], out, [pb]) { |ins, shared| ins[0].broadcast(LibPhGpu::Op::Mul, shared[0]) + ins[1] }
-    out.to_narr.should eq want
+    pipe.map_rows([pa, pc], result, [pb]) { |ins, shared| ins[0].broadcast(LibPhGpu::Op::Mul, shared[0]) + ins[1] }
+    result.to_narr.should eq want
     pipe.close
   end
 

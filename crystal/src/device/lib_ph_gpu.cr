@@ -120,19 +120,19 @@ lib LibPhGpu
 
   # ---- elementwise / compare / mask
   fun ph_ewise_binary(op : Int32, dtype : Int32, a : Void*, a_desc : Desc*, b : Void*, b_desc : Desc*,
-                      out : Void*, out_desc : Desc*) : Int32
+                      result : Void*, out_desc : Desc*) : Int32
   fun ph_ewise_scalar(op : Int32, dtype : Int32, a : Void*, a_desc : Desc*, scalar_host : Void*,
-                      scalar_on_left : Int32, out : Void*, out_desc : Desc*) : Int32
-  fun ph_ewise_unary(op : Int32, dtype : Int32, a : Void*, a_desc : Desc*, out : Void*, out_desc : Desc*) : Int32
+                      scalar_on_left : Int32, result : Void*, out_desc : Desc*) : Int32
+  fun ph_ewise_unary(op : Int32, dtype : Int32, a : Void*, a_desc : Desc*, result : Void*, out_desc : Desc*) : Int32
   fun ph_ewise_mul_add(dtype : Int32, a : Void*, a_desc : Desc*, b : Void*, b_desc : Desc*,
-                       c : Void*, c_desc : Desc*, out : Void*, out_desc : Desc*) : Int32
+                       c : Void*, c_desc : Desc*, result : Void*, out_desc : Desc*) : Int32
   fun ph_compare(cmp : Int32, dtype : Int32, a : Void*, a_desc : Desc*, b : Void*, b_desc : Desc*,
-                 out : UInt8*, out_desc : Desc*) : Int32
+                 result : UInt8*, out_desc : Desc*) : Int32
   fun ph_compare_scalar(cmp : Int32, dtype : Int32, a : Void*, a_desc : Desc*, scalar_host : Void*,
-                        scalar_on_left : Int32, out : UInt8*, out_desc : Desc*) : Int32
-  fun ph_compare3(dtype : Int32, a : Void*, a_desc : Desc*, b : Void*, b_desc : Desc*, out : Int32*, out_desc : Desc*) : Int32
+                        scalar_on_left : Int32, result : UInt8*, out_desc : Desc*) : Int32
+  fun ph_compare3(dtype : Int32, a : Void*, a_desc : Desc*, b : Void*, b_desc : Desc*, result : Int32*, out_desc : Desc*) : Int32
   fun ph_compare3_scalar(dtype : Int32, a : Void*, a_desc : Desc*, scalar_host : Void*, scalar_on_left : Int32,
-                         out : Int32*, out_desc : Desc*) : Int32
+                         result : Int32*, out_desc : Desc*) : Int32
   fun ph_mask_set_scalar(elem_size : Int32, dst : Void*, dst_desc : Desc*, mask : UInt8*, mask_desc : Desc*,
                          scalar_host : Void*) : Int32
   fun ph_mask_set_array(elem_size : Int32, dst : Void*, dst_desc : Desc*, mask : UInt8*, mask_desc : Desc*,
@@ -147,7 +147,7 @@ lib LibPhGpu
                      out_index_host : Int64*) : Int32
   fun ph_reduce_full_dev(red : Int32, dtype : Int32, a : Void*, a_desc : Desc*, out_value_dev : Void*,
                          out_index_dev : Int64*) : Int32
-  fun ph_reduce_axis(red : Int32, dtype : Int32, a : Void*, a_desc : Desc*, axis : Int32, out : Void*,
+  fun ph_reduce_axis(red : Int32, dtype : Int32, a : Void*, a_desc : Desc*, axis : Int32, result : Void*,
                      out_desc : Desc*) : Int32
 
   # ---- heat stencil

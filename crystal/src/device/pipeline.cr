@@ -180,13 +180,13 @@ module Phase
       @down = Stream.new
     end
 
-    # `out[r0...r1] = yield(rows[k][r0...r1] as device arrays, shared as device arrays)` for every
+    # `dest[r0...r1] = yield(rows[k][r0...r1] as device arrays, shared as device arrays)` for every
     # row chunk. The block composes device operators (it runs on the host and only launches
-    # kernels -- it is not a per-element block). `wait: true` returns when `out` is complete and
+    # kernels -- it is not a per-element block). `wait: true` returns when `dest` is complete and
     # raises pending data-dependent errors.
-    def map_rows(rows : Array(PinnedArray(T)), out : PinnedArray(T), shared : Array(PinnedArray(T)) = [] of PinnedArray(T),
+    def map_rows(rows : Array(PinnedArray(T)), dest : PinnedArray(T), shared : Array(PinnedArray(T)) = [] of PinnedArray(T),
                  wait : Bool = true, &block : Array(DeviceNArray(T)), Array(DeviceNArray(T)) -> DeviceNArray(T)) : Nil forall T
-      n = out.shape.empty? ? 0_i64 : out.shape[0].to_i64
+      n = dest.shape.empty? ? 0_i64 : dest.shape[0].to_i64
       rows.each do |r|
         if r.shape.empty? || r.shape[0] != n
           raise ShapeError.new("map_rows: every row operand needs the leading extent of the output")
@@ -204,7 +204,7 @@ module Phase
           comp.wait(up) # chunk k's operands (and the shared ones) have landed
           res = comp.use { block.call(ins, shared_dev) }
           down.wait(comp)
-          down.use { res.to_host_async(out.rows(r0)) }
+          down.use { res.to_host_async(dest.rows(r0)) }
           keep.concat(ins)
           keep << res
         end
