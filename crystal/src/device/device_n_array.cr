@@ -130,7 +130,7 @@ module Phase
       DeviceNArray.compatible_shapes?(shape, others.map(&.shape).to_a, axis)
     end
 
-    protected def self.compatible_shapes?(first : Array(Int32), others : Array(Array(Int32)), axis : Int) : Bool
+    def self.compatible_shapes?(first : Array(Int32), others : Array(Array(Int32)), axis : Int) : Bool
       first.each_with_index do |dim, idx|
         others.each do |other|
           return false if dim != other[idx] && idx != axis # `other[idx]` raises IndexError on a shorter shape
@@ -173,15 +173,8 @@ module Phase
       raise DimensionError.new("Cannot concatenate these arrays along axis #{axis}: shapes do not match") if !compatible?(*others, axis: axis)
       total = size + others.sum(&.size)
       grown = DeviceBuffer.new(total * sizeof(T))
-      at = 0_i64
-      {self, *others}.each do |narr|
-        flat = narr.is_a?(DeviceNArray(T)) ? narr : narr.to_narr
-        if flat.size > 0
-          dst = (grown.ptr.as(UInt8*) + at * sizeof(T)).as(Void*)
-          Device.check LibPhGpu.ph_d2d(dst, flat.dev.ptr, LibC::SizeT.new(flat.size * sizeof(T)))
-        end
-        at += flat.size
-      end
+      at = append_flat(self, grown, 0_i64)
+      others.each { |narr| at = append_flat(narr, grown, at) }
       @shape[0] += others.sum { |narr| narr.shape[0] }
       @dev = grown
       @desc = Descriptor.contiguous(@shape)
@@ -190,6 +183,16 @@ module Phase
 
     def <<(other : DeviceIndexable(T)) : self
       push(other)
+    end
+
+    # Copies `narr`'s elements (lexicographic order) to element `at` of `grown`; returns the next free element.
+    private def append_flat(narr : DeviceIndexable(T), grown : DeviceBuffer, at : Int64) : Int64
+      flat = narr.is_a?(DeviceNArray(T)) ? narr : narr.to_narr
+      if flat.size > 0
+        dst = (grown.ptr.as(UInt8*) + at * sizeof(T)).as(Void*)
+        Device.check LibPhGpu.ph_d2d(dst, flat.dev.ptr, LibC::SizeT.new(flat.size * sizeof(T)))
+      end
+      at + flat.size
     end
 
     # `NArray.wrap(*objects, pad: false)`: a new leading axis with one input per row.
