@@ -76,6 +76,12 @@ int32_t ph_region_translate(ph_region* r, const int64_t* offset, int32_t noffset
 int32_t ph_shapes_compatible(const int64_t* a, int32_t na, const int64_t* b, int32_t nb, int32_t* ok);
 /* NEW ShapeUtil.broadcast_shapes: equal rank, each axis equal or 1 */
 int32_t ph_broadcast_shapes(const int64_t* a, const int64_t* b, int32_t rank, int64_t* out);
+/* Row schedule of a chunked host -> device -> host pipeline over `n` leading-axis rows (pipeline.RowPipeline /
+ * Phase::RowPipeline; no reference counterpart -- NArray lives on the host): `chunks` equal chunks; the LAST one is cut
+ * into halves `taper` times (per/2, per/4, ..., per/2^t, per/2^t: the tail nothing overlaps is one small chunk), the
+ * FIRST one is the mirror image `ramp` times (per/2^r, per/2^r, ..., per/2: the first download starts early).
+ * bounds[2i], bounds[2i+1] = [r0, r1) of chunk i, in order, a partition of [0, n); *count <= cap chunks. */
+int32_t ph_row_chunks(int64_t n, int64_t chunks, int32_t taper, int32_t ramp, int64_t* bounds, int32_t cap, int32_t* count);
 /* NArray.concatenate's shape rule (n_array.cr:666-673 compatible?, :722-731): `shapes` holds n shapes of `ranks[i]`
  * entries each, packed at a pitch of PH_MAX_RANK.  Every dimension of the FIRST shape must equal the same dimension of
  * every other shape except at index `axis` -- compared on the raw argument, so a negative axis excludes nothing

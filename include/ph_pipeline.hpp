@@ -105,36 +105,15 @@ void to_host_async(const DeviceView<T>& v, T* pinned_dst) { to_host_async<T>(v.t
 // download -- nothing overlaps that tail -- so the final chunks are small while the early ones stay large
 // (every copy pays a fixed set-up: 16 equal chunks 120.4 GB/s on the BASELINE config, 4 + 7 halvings 125.1).
 inline std::vector<std::pair<int64_t, int64_t>> row_chunks(int64_t n, int64_t chunks, int taper = 0, int ramp = 0) {
-  const int64_t per = (n + std::max<int64_t>(1, chunks) - 1) / std::max<int64_t>(1, chunks);
-  std::vector<std::pair<int64_t, int64_t>> b;
-  for (int64_t r = 0; r < n; r += per) b.push_back({r, std::min(n, r + per)});
-  if (taper > 0 && !b.empty()) {
-    int64_t r0 = b.back().first, r1 = b.back().second;
-    b.pop_back();
-    for (int t = 0; t < taper; t++) {
-      const int64_t mid = r0 + (r1 - r0 + 1) / 2;
-      if (mid >= r1) break;
-      b.push_back({r0, mid});
-      r0 = mid;
-    }
-    b.push_back({r0, r1});
-  }
   // ramp = t: the mirror image at the FRONT (per/2^t, per/2^t, ..., per/2): the first download can only start after
   // the first chunk, so that one is small too (no cost on one GPU -- 10.73 vs 10.77 ms -- and the downloads start
-  // 32 times earlier when the host side is the slower half)
-  if (ramp > 0 && !b.empty()) {
-    int64_t r0 = b.front().first, r1 = b.front().second;
-    b.erase(b.begin());
-    std::vector<std::pair<int64_t, int64_t>> head;
-    for (int t = 0; t < ramp; t++) {
-      const int64_t mid = r1 - (r1 - r0 + 1) / 2;
-      if (mid <= r0) break;
-      head.insert(head.begin(), {mid, r1});
-      r1 = mid;
-    }
-    head.insert(head.begin(), {r0, r1});
-    b.insert(b.begin(), head.begin(), head.end());
-  }
+  // 32 times earlier when the host side is the slower half).  The schedule itself is ph_row_chunks (ph_host.h).
+  const int32_t cap = (int32_t)std::max<int64_t>(1, chunks) + std::max(0, taper) + std::max(0, ramp) + 2;
+  std::vector<int64_t> bounds((size_t)2 * cap);
+  int32_t count = 0;
+  Device::host_check(ph_row_chunks(n, chunks, taper, ramp, bounds.data(), cap, &count));
+  std::vector<std::pair<int64_t, int64_t>> b;
+  for (int32_t i = 0; i < count; i++) b.push_back({bounds[(size_t)2 * i], bounds[(size_t)2 * i + 1]});
   return b;
 }
 

@@ -191,6 +191,7 @@ def load() -> C.CDLL:
         "ph_shapes_compatible": [i64p, i32, i64p, i32, i32p],
         "ph_broadcast_shapes": [i64p, i64p, i32, i64p],
         "ph_concat_shape": [i64p, i32p, i32, i32, i64p, i32p],
+        "ph_row_chunks": [i64, i64, i32, i32, i64p, i32, i32p],
         "ph_desc_contiguous": [i64p, i32, dp], "ph_desc_region": [dp, rp, dp],
         "ph_desc_permute": [dp, i32p, i32, dp], "ph_desc_reverse": [dp, dp],
         "ph_desc_reshape": [dp, i64p, i32, dp], "ph_desc_broadcast": [dp, i64p, i32, dp],

@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
+#include <vector>
 
 namespace {
 
@@ -281,6 +282,42 @@ int32_t ph_broadcast_shapes(const int64_t* a, const int64_t* b, int32_t rank, in
     else if (a[i] == 1) out[i] = b[i];
     else return fail(PH_HOST_SHAPE_ERROR, "shapes cannot be broadcast on axis %d (%lld vs %lld)", i, (long long)a[i], (long long)b[i]);
   }
+  return PH_HOST_OK;
+}
+
+int32_t ph_row_chunks(int64_t n, int64_t chunks, int32_t taper, int32_t ramp, int64_t* bounds, int32_t cap, int32_t* count) {
+  if (!bounds || !count || cap < 0 || n < 0) return fail(PH_HOST_INVALID, "bad argument to ph_row_chunks");
+  std::vector<std::pair<int64_t, int64_t>> b;
+  const int64_t k = std::max<int64_t>(1, chunks);
+  const int64_t per = (n + k - 1) / k;
+  for (int64_t r = 0; r < n; r += per) b.push_back({r, std::min(n, r + per)});
+  if (taper > 0 && !b.empty()) {
+    int64_t r0 = b.back().first, r1 = b.back().second;
+    b.pop_back();
+    for (int t = 0; t < taper; t++) {
+      const int64_t mid = r0 + (r1 - r0 + 1) / 2;
+      if (mid >= r1) break;
+      b.push_back({r0, mid});
+      r0 = mid;
+    }
+    b.push_back({r0, r1});
+  }
+  if (ramp > 0 && !b.empty()) {
+    int64_t r0 = b.front().first, r1 = b.front().second;
+    b.erase(b.begin());
+    std::vector<std::pair<int64_t, int64_t>> head;
+    for (int t = 0; t < ramp; t++) {
+      const int64_t mid = r1 - (r1 - r0 + 1) / 2;
+      if (mid <= r0) break;
+      head.insert(head.begin(), {mid, r1});
+      r1 = mid;
+    }
+    head.insert(head.begin(), {r0, r1});
+    b.insert(b.begin(), head.begin(), head.end());
+  }
+  if ((int64_t)b.size() > (int64_t)cap) return fail(PH_HOST_INVALID, "ph_row_chunks: %lld chunks do not fit the caller's %d", (long long)b.size(), cap);
+  for (size_t i = 0; i < b.size(); i++) { bounds[2 * i] = b[i].first; bounds[2 * i + 1] = b[i].second; }
+  *count = (int32_t)b.size();
   return PH_HOST_OK;
 }
 

@@ -11,6 +11,7 @@ builds descriptors by hand.
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Callable, Sequence
 
 import numpy as np
@@ -19,36 +20,19 @@ from .narray import DeviceNArray, Stream, ShapeError, main_stream_wait, sync
 
 
 def row_chunks(n: int, chunks: int, taper: int = 0, ramp: int = 0):
-    """[r0, r1) row ranges: `chunks` equal chunks; with taper = t the LAST one is cut again into halves t times
-    (per/2, per/4, ..., per/2^t, per/2^t).  What is left when the last upload ends is one chunk's kernels and
-    download -- nothing overlaps that tail -- so the final chunks are small while the early ones stay large
-    (every copy pays a fixed set-up, so many small chunks everywhere would cost more than the tail they save)."""
-    per = -(-n // max(1, chunks))
-    bounds, r = [], 0
-    while r < n:
-        bounds.append((r, min(n, r + per)))
-        r += per
-    if taper > 0 and bounds:
-        r0, r1 = bounds.pop()
-        for _ in range(taper):
-            mid = r0 + (r1 - r0 + 1) // 2
-            if mid >= r1:
-                break
-            bounds.append((r0, mid))
-            r0 = mid
-        bounds.append((r0, r1))
-    if ramp > 0 and bounds:                                   # mirror image at the front: per/2^ramp, per/2^ramp, ..., per/2
-        r0, r1 = bounds.pop(0)                                # (the first download can only start after the first chunk)
-        head = []
-        for _ in range(ramp):
-            mid = r1 - (r1 - r0 + 1) // 2
-            if mid <= r0:
-                break
-            head.insert(0, (mid, r1))
-            r1 = mid
-        head.insert(0, (r0, r1))
-        bounds = head + bounds
-    return bounds
+    """[r0, r1) row ranges (ph_row_chunks, include/ph_host.h -- the schedule is C++ host code shared with the
+    compiled host layer; this function marshals): `chunks` equal chunks; with taper = t the LAST one is cut again
+    into halves t times (per/2, per/4, ..., per/2^t, per/2^t).  What is left when the last upload ends is one
+    chunk's kernels and download -- nothing overlaps that tail -- so the final chunks are small while the early ones
+    stay large.  With ramp = r the FIRST chunk is the mirror image (per/2^r, per/2^r, ..., per/2): the first download
+    can only start after the first chunk."""
+    from . import _lib
+    from .narray import host_check
+    cap = max(1, int(chunks)) + max(0, int(taper)) + max(0, int(ramp)) + 2
+    bounds = (C.c_int64 * (2 * cap))()
+    count = C.c_int32(0)
+    host_check(_lib.load().ph_row_chunks(int(n), int(chunks), int(taper), int(ramp), bounds, cap, C.byref(count)))
+    return [(int(bounds[2 * i]), int(bounds[2 * i + 1])) for i in range(count.value)]
 
 
 class RowPipeline:
